@@ -1,0 +1,158 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Mints `tests/golden/*.npz` from the REAL reference.
+
+Run in the dev container (needs /root/reference):   python -m oracle.make_golden
+
+Every case builds the unmodified reference modules (`oracle/ref_loader.py`), loads the
+deterministic synthetic weights of `scldm_b200/synthetic.py` with `strict=True` (which also
+proves the key/shape contract), runs the reference in fp32 on CPU and stores inputs+outputs.
+Weights are NOT stored: they are regenerated from (seed, tensor name) on both sides.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import ref_loader  # noqa: E402
+from scldm_b200 import synthetic  # noqa: E402
+from scldm_b200.config import DiTConfig, VAEConfig  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+WEIGHT_SEED = 1234
+
+
+def golden_cases() -> dict:
+    """Case table shared with the tests (configs + input recipes are derived from this)."""
+    return {
+        "dit_me1": dict(cfg=DiTConfig(class_vocab_sizes={"clusters": 14}), B=4, scales={"clusters": 2.0}),
+        "dit_me2": dict(cfg=DiTConfig(class_vocab_sizes={"cell_type": 5, "tissue": 3}, n_layer=2), B=3,
+                        scales={"cell_type": 1.5, "tissue": 0.5}),
+        "dit_joint": dict(cfg=DiTConfig(class_vocab_sizes={"cell_line": 4, "gene": 7}, n_layer=2,
+                                        condition_strategy="joint"), B=3, scales={"cell_line": 1.0, "gene": 3.0}),
+    }
+
+
+def dit_inputs(name: str, cfg: DiTConfig, B: int):
+    x = synthetic.randn(name + ".x", (2 * B, cfg.seq_len, cfg.n_embed_input))
+    t = torch.from_numpy(np.linspace(0.05, 0.95, 2 * B).astype(np.float32))
+    labels = {k: synthetic.randint(name + ".label." + k, v, (2 * B,)) for k, v in cfg.class_vocab_sizes.items()}
+    return x, t, labels
+
+
+def vae_inputs(name: str, cfg: VAEConfig, B: int, S: int):
+    z = synthetic.randn(name + ".z", (B, cfg.n_inducing_points, cfg.n_embed_latent))
+    genes = torch.arange(1, cfg.n_genes + 1, dtype=torch.int64).unsqueeze(0).repeat(B, 1)
+    lib = torch.exp(8.0 + 0.3 * synthetic.randn(name + ".lib", (B, 1)))
+    # "expressed"-mode encoder inputs (reference datamodule.py:708-731): distinct ids packed left, zero padded
+    rng = np.random.default_rng(99)
+    gs = np.zeros((B, S), dtype=np.int64)
+    cs = np.zeros((B, S), dtype=np.float32)
+    for b in range(B):
+        n = int(rng.integers(S // 3, S))
+        gs[b, :n] = rng.choice(np.arange(1, cfg.n_genes + 1), size=n, replace=False)
+        cs[b, :n] = 1 + rng.poisson(2.0, size=n)
+    return z, genes, lib, torch.from_numpy(cs), torch.from_numpy(gs)
+
+
+@torch.no_grad()
+def main() -> None:
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(0)
+    ref = ref_loader.load_reference()
+    keys: dict[str, dict] = {}
+
+    # ---- DiT forward / forward_with_cfg -------------------------------------------------
+    for name, case in golden_cases().items():
+        cfg, B = case["cfg"], case["B"]
+        sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+        model = ref_loader.build_reference_dit(cfg, sd)
+        keys[name] = {k: list(v.shape) for k, v in model.state_dict().items()}
+        x, t, labels = dit_inputs(name, cfg, B)
+        # (a DiT without class tables cannot run in the reference: `_get_condition_embedding`
+        #  indexes `condition.values()` unconditionally, nnets.py:381 -- so every case has classes)
+        if cfg.condition_strategy == "joint":
+            out_fwd = model.forward(x, t, labels, force_drop_ids=False)
+        else:
+            first = sorted(labels)[0]
+            out_fwd = model.forward(x, t, {first: labels[first]}, force_drop_ids=False)
+        arrays = dict(x=x.numpy(), t=t.numpy())
+        for k, v in labels.items():
+            arrays["label." + k] = v.numpy()
+        arrays["out_forward"] = out_fwd.numpy()
+        arrays["out_cfg"] = model.forward_with_cfg(x, t, labels, case["scales"]).numpy()
+        arrays["out_cfg_none"] = model.forward_with_cfg(x, t, None, None).numpy()
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
+        print(name, {k: v.shape for k, v in arrays.items()})
+
+    # ---- ODE sampler through the reference's Sampler / ode classes -----------------------
+    case = golden_cases()["dit_me1"]
+    cfg = case["cfg"]
+    sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    model = ref_loader.build_reference_dit(cfg, sd)
+    transport = ref.transport.create_transport(path_type="Linear", prediction="velocity", loss_weight="velocity",
+                                               train_eps=1e-5, sample_eps=1e-5)
+    sampler = ref.transport.Sampler(transport)
+    B = 2
+    z0 = synthetic.randn("ode.z0", (B, cfg.seq_len, cfg.n_embed_input))
+    lab = {"clusters": synthetic.randint("ode.label", 14, (B,))}
+    z_cfg = torch.cat([z0, z0])
+    lab_cfg = {k: torch.cat([v, v]) for k, v in lab.items()}
+    arrays = dict(z0=z0.numpy(), label=lab["clusters"].numpy())
+    for method, steps, w in (("euler", 50, 2.0), ("euler", 50, 1.0), ("heun2", 10, 2.0), ("midpoint", 10, 2.0)):
+        fn = sampler.sample_ode(sampling_method=method, num_steps=steps)
+        model_fn = lambda x, t, **kw: model.forward_with_cfg(x, t, **kw, cfg_scale={"clusters": w})  # noqa: E731
+        traj = fn(z_cfg, model_fn, condition=lab_cfg)
+        arrays[f"z_{method}_{steps}_w{w}"] = traj[-1].numpy()
+        print("ode", method, steps, w, traj.shape, float(traj[-1].abs().mean()))
+    t0t1 = transport.check_interval(transport.train_eps, transport.sample_eps, sde=False, eval=True)
+    arrays["t0t1"] = np.asarray(t0t1, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "ode_me1.npz"), **arrays)
+
+    # ---- VAE decode / encode ----------------------------------------------------------------
+    for name, G, B, S in (("vae_small", 1500, 3, 400), ("vae_dentate", 17002, 2, 600)):
+        vcfg = VAEConfig(n_genes=G)
+        vsd = synthetic.vae_state_dict(vcfg, WEIGHT_SEED)
+        vae = ref_loader.build_reference_vae(vcfg, vsd)
+        keys[name] = {k: list(v.shape) for k, v in vae.state_dict().items()}
+        z, genes, lib, cs, gs = vae_inputs(name, vcfg, B, S)
+        nb = vae.decode(z, genes, lib)
+        h = vae.decoder(z, vae.input_layer.gene_embedding(genes))
+        z_enc = vae.encode(None, None, cs, gs)
+        arrays = dict(z=z.numpy(), lib=lib.numpy(), counts_subset=cs.numpy(), genes_subset=gs.numpy(),
+                      mu=nb.mu.numpy(), theta=nb.theta[0].numpy(), z_enc=z_enc.numpy(),
+                      h_first64=h[:, :64].numpy())
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
+        print(name, {k: v.shape for k, v in arrays.items()}, "mu.sum/lib", (nb.mu.sum(1) / lib[:, 0]).tolist())
+
+    # ---- full sample(): reference pieces composed as LatentDiffusion.sample composes them ----
+    cfg = golden_cases()["dit_me1"]["cfg"]
+    vcfg = VAEConfig(n_genes=1500)
+    model = ref_loader.build_reference_dit(cfg, synthetic.dit_state_dict(cfg, WEIGHT_SEED))
+    vae = ref_loader.build_reference_vae(vcfg, synthetic.vae_state_dict(vcfg, WEIGHT_SEED))
+    B = 2
+    z0 = synthetic.randn("sample.z0", (B, cfg.seq_len, cfg.n_embed_input))
+    lab = {"clusters": synthetic.randint("sample.label", 14, (B,))}
+    lsf = 8.0 + 0.3 * synthetic.randn("sample.lsf", (B,))
+    genes = torch.arange(1, vcfg.n_genes + 1, dtype=torch.int64).unsqueeze(0).repeat(B, 1)
+    fn = sampler.sample_ode(sampling_method="euler", num_steps=50)
+    w = {"clusters": 2.0}
+    model_fn = lambda x, t, **kw: model.forward_with_cfg(x, t, **kw, cfg_scale=w)  # noqa: E731
+    z_fin = fn(torch.cat([z0, z0]), model_fn, condition={k: torch.cat([v, v]) for k, v in lab.items()})[-1]
+    lib = torch.exp(lsf).view(-1, 1)
+    nb = vae.decode(z_fin, torch.cat([genes, genes]), torch.cat([lib, lib]))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "sample_me1.npz"), z0=z0.numpy(), label=lab["clusters"].numpy(),
+                        log_size_factors=lsf.numpy(), z_final=z_fin.numpy(), mu=nb.mu.numpy(), theta=nb.theta[0].numpy())
+    print("sample", z_fin.shape, nb.mu.shape)
+
+    with open(os.path.join(GOLDEN_DIR, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""Pins the oracle restatement (`oracle/scldm_oracle.py`) against golden vectors minted from the
+unmodified reference (`oracle/make_golden.py`).  fp32 CPU both sides: tolerance 2e-5 relative-L2
+(only op-ordering differences)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scldm_oracle as O
+from oracle.make_golden import WEIGHT_SEED, dit_inputs, golden_cases, vae_inputs
+from scldm_b200 import synthetic
+from scldm_b200.config import VAEConfig
+
+TOL = 2e-5
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz")))
+
+
+@pytest.mark.parametrize("name", list(golden_cases().keys()))
+def test_dit_forward_and_cfg(golden_dir, name):
+    case = golden_cases()[name]
+    cfg, B = case["cfg"], case["B"]
+    g = load(golden_dir, name)
+    sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    x, t, labels = dit_inputs(name, cfg, B)
+    assert np.array_equal(x.numpy(), g["x"])  # input recipe is reproducible
+    with torch.no_grad():
+        if cfg.condition_strategy == "joint":
+            fwd = O.dit_forward(x, t, labels, sd, cfg)
+        else:
+            first = sorted(labels)[0]
+            fwd = O.dit_forward(x, t, {first: labels[first]}, sd, cfg)
+        assert rel_l2(fwd, g["out_forward"]) < TOL
+        out = O.dit_forward_with_cfg(x, t, labels, case["scales"], sd, cfg)
+        assert rel_l2(out, g["out_cfg"]) < TOL
+        out_none = O.dit_forward_with_cfg(x, t, None, None, sd, cfg)
+        assert rel_l2(out_none, g["out_cfg_none"]) < TOL
+    # guided half differs from unguided base => conditioning is exercised (not vacuous)
+    assert rel_l2(g["out_cfg"], g["out_cfg_none"]) > 1e-2
+
+
+@pytest.mark.parametrize("method,steps,w", [("euler", 50, 2.0), ("euler", 50, 1.0), ("heun2", 10, 2.0), ("midpoint", 10, 2.0)])
+def test_ode_sampler(golden_dir, method, steps, w):
+    g = load(golden_dir, "ode_me1")
+    assert tuple(g["t0t1"]) == (0.0, 1.0)  # eps forced to 0 for Linear+velocity (transport/__init__.py:55-57)
+    cfg = golden_cases()["dit_me1"]["cfg"]
+    sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    z0 = torch.from_numpy(g["z0"])
+    lab = {"clusters": torch.from_numpy(g["label"])}
+    lab2 = {k: torch.cat([v, v]) for k, v in lab.items()}
+    with torch.no_grad():
+        traj = O.sample_ode(torch.cat([z0, z0]), lambda x, t: O.dit_forward_with_cfg(x, t, lab2, {"clusters": w}, sd, cfg),
+                            num_steps=steps, method=method)
+    assert traj.shape[0] == steps  # N grid points = N-1 steps (quirk 4)
+    assert rel_l2(traj[-1], g[f"z_{method}_{steps}_w{w}"]) < 1e-4
+
+
+@pytest.mark.parametrize("name,G,B,S", [("vae_small", 1500, 3, 400), ("vae_dentate", 17002, 2, 600)])
+def test_vae_decode_encode(golden_dir, name, G, B, S):
+    g = load(golden_dir, name)
+    cfg = VAEConfig(n_genes=G)
+    sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
+    z, genes, lib, cs, gs = vae_inputs(name, cfg, B, S)
+    with torch.no_grad():
+        h = O.decoder_forward(z, genes, sd, cfg)
+        assert rel_l2(h[:, :64], g["h_first64"]) < TOL
+        mu, theta = O.vae_decode(z, genes, lib, sd, cfg)
+        assert rel_l2(mu, g["mu"]) < 1e-4
+        assert rel_l2(theta[0], g["theta"]) < 1e-6
+        assert torch.allclose(mu.sum(1), lib[:, 0], rtol=1e-5)
+        z_enc = O.vae_encode(cs, gs, sd, cfg)
+        assert rel_l2(z_enc, g["z_enc"]) < 1e-4
+
+
+def test_full_sample(golden_dir):
+    g = load(golden_dir, "sample_me1")
+    cfg = golden_cases()["dit_me1"]["cfg"]
+    vcfg = VAEConfig(n_genes=1500)
+    dsd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    vsd = synthetic.vae_state_dict(vcfg, WEIGHT_SEED)
+    B = 2
+    genes = torch.arange(1, vcfg.n_genes + 1, dtype=torch.int64).unsqueeze(0).repeat(B, 1)
+    with torch.no_grad():
+        mu, theta, zf = O.latent_diffusion_sample(
+            torch.from_numpy(g["z0"]), {"clusters": torch.from_numpy(g["label"])}, {"clusters": 2.0}, genes,
+            torch.from_numpy(g["log_size_factors"]), dsd, cfg, vsd, vcfg, num_steps=50, method="euler")
+    assert rel_l2(zf, g["z_final"]) < 1e-4
+    assert rel_l2(mu, g["mu"]) < 1e-3
+    assert rel_l2(theta[0], g["theta"]) < 1e-6
+
+
+def test_state_dict_contract(golden_dir):
+    """synthetic specs == the reference modules' own state_dict keys/shapes."""
+    with open(os.path.join(golden_dir, "state_dict_keys.json")) as f:
+        keys = json.load(f)
+    for name, case in golden_cases().items():
+        spec = synthetic.dit_state_spec(case["cfg"])
+        assert {k: list(s) for k, (s, _) in spec.items()} == keys[name]
+    for name, G in (("vae_small", 1500), ("vae_dentate", 17002)):
+        spec = synthetic.vae_state_spec(VAEConfig(n_genes=G))
+        assert {k: list(s) for k, (s, _) in spec.items()} == keys[name]
+
+
+def test_nb_sample_moments():
+    """restated scvi Gamma-Poisson: mean mu, variance mu + mu^2/theta."""
+    gen = torch.Generator().manual_seed(7)
+    mu = torch.tensor([[0.3, 2.0, 15.0, 120.0]]).repeat(200000, 1)
+    theta = torch.tensor([0.5, 1.5, 3.0, 8.0])
+    x = O.nb_sample(mu, theta, generator=gen)
+    m, v = x.mean(0), x.var(0)
+    exp_v = mu[0] + mu[0] ** 2 / theta
+    assert torch.allclose(m, mu[0], rtol=0.03)
+    assert torch.allclose(v, exp_v, rtol=0.06)
