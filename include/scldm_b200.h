@@ -1,0 +1,146 @@
+/* scldm_b200 C-ABI: B200 (sm_100a) kernels for scLDM's generation hot path.
+ *
+ * The reference (czi-ai/scldm) has NO FFI / plugin interface for this path -- it is plain
+ * nn.Module composition.  This header is therefore the *new* seam a
+ * maintainer would bind underneath the reference's Python classes; every entry point names the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host
+ *   - the caller owns every buffer incl. the workspace; the library never allocates or frees
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation and no H2D/D2H copies => capturable in a CUDA graph
+ *   - return value: 0 on success, negative SCLDM_E* on error; scldm_last_error() gives the message
+ *   - there is no CPU fallback: without a CUDA device every compute call returns SCLDM_ECUDA
+ */
+#ifndef SCLDM_B200_H
+#define SCLDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCLDM_OK 0
+#define SCLDM_EINVAL -1  /* bad argument / unsupported shape */
+#define SCLDM_ECUDA -2   /* CUDA runtime error              */
+#define SCLDM_ENOMEM -3  /* workspace too small             */
+
+#define SCLDM_MAX_CLASSES 8
+#define SCLDM_MAX_COMBINE 8
+
+#define SCLDM_ODE_EULER 0
+#define SCLDM_ODE_HEUN2 1
+#define SCLDM_ODE_MIDPOINT 2
+
+/* Packed DiT weights (device).  Produced from the reference state_dict by scldm_b200/pack.py.
+ * bf16 matrices are stored as 128B-swizzled K-major UMMA tiles [n_tile][k_slab][256 x 64]. */
+typedef struct scldm_dit_weights {
+  int32_t n_layer;    /* DiT blocks (nnets.py:247-262)                                        */
+  int32_t hidden;     /* SwiGLU hidden width, 684 for n_embed=256 (layers.py:165-167)          */
+  int32_t hid_slabs;  /* ceil(hidden/64): K slabs of mlp.c_proj                                */
+  int32_t mlp1_tiles; /* ceil(hidden/128): N tiles of the fused [w1|w2] GEMM                   */
+  int32_t mod_stride; /* n_layer*1536 + 512: floats per row of the modulation table            */
+  int32_t n_class;    /* number of class-embedding tables (sorted by class name)               */
+  float eps;          /* LayerNorm eps (1e-8)                                                  */
+  const void* w_mod;    /* bf16 [mod_stride/256][4][256x64]: all adaLN Linear weights, stacked   */
+  const float* b_mod;   /* [mod_stride]                                                          */
+  const void* w_qkv;    /* bf16 [n_layer][3][4][256x64]   attn.c_attn                             */
+  const float* b_qkv;   /* [n_layer][768]                                                        */
+  const void* w_proj;   /* bf16 [n_layer][4][256x64]      attn.c_proj                             */
+  const float* b_proj;  /* [n_layer][256]                                                        */
+  const void* w_mlp1;   /* bf16 [n_layer][mlp1_tiles][4][256x64]  rows 0-127 = w1, 128-255 = w2   */
+  const void* w_mlp2;   /* bf16 [n_layer][hid_slabs][256x64]      mlp.c_proj                      */
+  const float* temb_w0t; /* t_embedder.mlp.0.weight^T [256][256] */
+  const float* temb_b0;
+  const float* temb_w2t; /* t_embedder.mlp.2.weight^T [256][256] */
+  const float* temb_b2;
+  const float* w_in;   /* input_proj.weight [256][16]        */
+  const float* b_in;   /* [256]                               */
+  const float* pos;    /* pos_embed [16][256]                 */
+  const float* w_out;  /* final_layer.linear.weight [16][256] */
+  const float* b_out;  /* [16]                                */
+  const float* class_tables[SCLDM_MAX_CLASSES]; /* class_embeddings.<name>.weight [(V+1)][256] */
+} scldm_dit_weights;
+
+/* Which model evaluations one call performs and how they are combined.
+ *   states [0,n_u)       : evaluated once (slot = state)
+ *   states [n_u,n_u+n_g) : evaluated n_f times (consecutive slots); v = sum_k coef[k]*out_k
+ * This expresses DiT.forward (n_g=0) and DiT.forward_with_cfg (nnets.py:336-378: first half
+ * unconditional, second half guided with coef = [1-sum(w), w_1, ...]).                        */
+typedef struct scldm_dit_plan {
+  int32_t n_u, n_g, n_f;
+  float coef[SCLDM_MAX_COMBINE];
+  int32_t n_mod;          /* distinct conditioning rows                                   */
+  const int32_t* cls_idx; /* [n_class][n_mod_pad] embedding row per class (null = vocab)   */
+  const int32_t* slot_mod;/* [slots_pad] conditioning row of every slot                    */
+} scldm_dit_plan;
+
+/* padded sizes the index arrays / workspace must honour (multiples of 8 slots / 128 mod rows) */
+int32_t scldm_dit_slots_pad(const scldm_dit_plan* plan);
+int32_t scldm_dit_mod_pad(const scldm_dit_plan* plan);
+size_t scldm_dit_workspace_bytes(const scldm_dit_weights* w, const scldm_dit_plan* plan, int32_t n_evals);
+
+/* Introspection for tests: byte offsets (from the 1024-aligned workspace base) of
+ * {X, qkv, attn_out, hidden, mod, cls, temb, acc, tvals}; returns the number of entries written. */
+int32_t scldm_dit_workspace_layout(const scldm_dit_weights* w, const scldm_dit_plan* plan, int32_t n_evals, size_t* offsets,
+                                   int32_t max_entries);
+
+/* Replaces DiT.forward / DiT.forward_with_cfg (nnets.py:273-297, 336-378).
+ *   x      [n_u+n_g][16][16] fp32 states;  t_mod [n_mod_pad] fp32 time of every conditioning row
+ *   v_out  [n_u+n_g][16][16] fp32 combined model output                                        */
+int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, const float* t_mod,
+                      float* v_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces Sampler.sample_ode(...)(x, model) -> [-1] for fixed-grid solvers
+ * (transport.py:324-369, integrators.py:100-112 + torchdiffeq fixed-grid step).  x is advanced in
+ * place over t_grid_host[0..n_grid) (n_grid points => n_grid-1 steps); all rows share t.         */
+int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan, float* x, const float* t_grid_host,
+                         int32_t n_grid, int32_t method, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Packed VAE decoder weights (device, fp32).  scldm_b200/pack.py documents every layout. */
+typedef struct scldm_vae_dec_weights {
+  int32_t n_layer;
+  int32_t n_ids;           /* n_genes + 1 rows in the embedding / theta tables */
+  float eps;
+  const float* win_t;      /* decoder_latent_input.1.weight^T [16][32]                       */
+  const float* blocks;     /* n_layer packed Blocks (decoder.decoder_layers.i)                */
+  const float* ca_ln1_w;   /* decoder_cross_attention.ln_1                                    */
+  const float* ca_ln1_b;
+  const float* ca_wkv_t;   /* decoder_cross_attention.attn.c_attn.weight^T [32][64]           */
+  const float* ca_ln1q_w;  /* decoder_cross_attention.ln_1q                                   */
+  const float* ca_ln1q_b;
+  const float* ca_wq;      /* decoder_cross_attention.attn.c_attn_q.weight [32][32]           */
+  const float* mcab_blob;  /* c_proj | ln_2 | mlp.w1 | mlp.w2 | mlp.c_proj^T | head w | head b */
+  const float* emb;        /* input_layer.gene_embedding.weight [n_ids][32]                   */
+  const float* theta_tbl;  /* decoder_head.theta.weight [n_ids]                               */
+} scldm_vae_dec_weights;
+
+/* Cell-invariant query side of the decoder MCAB: qp[g] = c_attn_q(ln_1q(emb[g])) (layers.py:253,326). */
+int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* stream);
+
+size_t scldm_vae_decode_workspace_bytes(int32_t n_cells, int32_t n_genes);
+
+/* Replaces TransformerVAE.decode (vae.py:71-87) [+ NegativeBinomial.sample, models.py:819].
+ *   z [n_cells][16][16]; genes [n_genes] int64 vocabulary ids shared by all cells; lib [n_cells]
+ *   mu [n_cells][n_genes] / theta [n_genes] / counts [n_cells][n_genes]: any may be NULL           */
+int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const float* z, int32_t n_cells,
+                     const int64_t* genes, int32_t n_genes, const float* lib, float* mu, float* theta, float* counts,
+                     uint64_t seed, int64_t cell_offset, void* workspace, size_t workspace_bytes, void* stream);
+
+/* N(0,1) draws keyed by (seed, global cell index, element): latent noise (models.py:788) and the
+ * size-factor normals (models.py:585-596).                                                        */
+int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t seed, int64_t cell_offset,
+                      uint32_t stream_id, void* stream);
+
+/* kernels launched by this library since load (bench.py reports it as gpu_launches) */
+uint64_t scldm_launch_count(void);
+const char* scldm_last_error(void);
+const char* scldm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,105 @@
+"""ctypes binding of the C-ABI in `include/scldm_b200.h` (libscldm_b200.so, built in-tree by
+`scldm_b200/build.py`).  There is no fallback: if the library is missing the import of any
+compute path raises."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libscldm_b200.so")
+
+MAX_CLASSES = 8
+MAX_COMBINE = 8
+ODE_METHODS = {"euler": 0, "heun2": 1, "midpoint": 2}
+
+EXPORTS = [
+    "scldm_dit_slots_pad", "scldm_dit_mod_pad", "scldm_dit_workspace_bytes", "scldm_dit_workspace_layout",
+    "scldm_dit_forward", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
+    "scldm_vae_decode", "scldm_randn_cells", "scldm_launch_count", "scldm_last_error", "scldm_version",
+]
+
+
+class DitWeights(C.Structure):
+    _fields_ = [
+        ("n_layer", C.c_int32), ("hidden", C.c_int32), ("hid_slabs", C.c_int32), ("mlp1_tiles", C.c_int32),
+        ("mod_stride", C.c_int32), ("n_class", C.c_int32), ("eps", C.c_float),
+        ("w_mod", C.c_void_p), ("b_mod", C.c_void_p), ("w_qkv", C.c_void_p), ("b_qkv", C.c_void_p),
+        ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("w_mlp1", C.c_void_p), ("w_mlp2", C.c_void_p),
+        ("temb_w0t", C.c_void_p), ("temb_b0", C.c_void_p), ("temb_w2t", C.c_void_p), ("temb_b2", C.c_void_p),
+        ("w_in", C.c_void_p), ("b_in", C.c_void_p), ("pos", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+        ("class_tables", C.c_void_p * MAX_CLASSES),
+    ]
+
+
+class DitPlan(C.Structure):
+    _fields_ = [
+        ("n_u", C.c_int32), ("n_g", C.c_int32), ("n_f", C.c_int32), ("coef", C.c_float * MAX_COMBINE),
+        ("n_mod", C.c_int32), ("cls_idx", C.c_void_p), ("slot_mod", C.c_void_p),
+    ]
+
+
+class VaeDecWeights(C.Structure):
+    _fields_ = [
+        ("n_layer", C.c_int32), ("n_ids", C.c_int32), ("eps", C.c_float),
+        ("win_t", C.c_void_p), ("blocks", C.c_void_p), ("ca_ln1_w", C.c_void_p), ("ca_ln1_b", C.c_void_p),
+        ("ca_wkv_t", C.c_void_p), ("ca_ln1q_w", C.c_void_p), ("ca_ln1q_b", C.c_void_p), ("ca_wq", C.c_void_p),
+        ("mcab_blob", C.c_void_p), ("emb", C.c_void_p), ("theta_tbl", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libscldm_b200.so (once) and declare the prototypes of include/scldm_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "scldm_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.scldm_dit_slots_pad.argtypes = [P(DitPlan)]
+    lib.scldm_dit_slots_pad.restype = C.c_int32
+    lib.scldm_dit_mod_pad.argtypes = [P(DitPlan)]
+    lib.scldm_dit_mod_pad.restype = C.c_int32
+    lib.scldm_dit_workspace_bytes.argtypes = [P(DitWeights), P(DitPlan), C.c_int32]
+    lib.scldm_dit_workspace_bytes.restype = C.c_size_t
+    lib.scldm_dit_workspace_layout.argtypes = [P(DitWeights), P(DitPlan), C.c_int32, P(C.c_size_t), C.c_int32]
+    lib.scldm_dit_workspace_layout.restype = C.c_int32
+    lib.scldm_dit_forward.argtypes = [P(DitWeights), P(DitPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_dit_forward.restype = C.c_int
+    lib.scldm_dit_sample_ode.argtypes = [P(DitWeights), P(DitPlan), C.c_void_p, P(C.c_float), C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]
+    lib.scldm_dit_sample_ode.restype = C.c_int
+    lib.scldm_vae_qside.argtypes = [P(VaeDecWeights), C.c_void_p, C.c_void_p]
+    lib.scldm_vae_qside.restype = C.c_int
+    lib.scldm_vae_decode_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.scldm_vae_decode_workspace_bytes.restype = C.c_size_t
+    lib.scldm_vae_decode.argtypes = [P(VaeDecWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_vae_decode.restype = C.c_int
+    lib.scldm_randn_cells.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]
+    lib.scldm_randn_cells.restype = C.c_int
+    lib.scldm_launch_count.argtypes = []
+    lib.scldm_launch_count.restype = C.c_uint64
+    lib.scldm_last_error.argtypes = []
+    lib.scldm_last_error.restype = C.c_char_p
+    lib.scldm_version.argtypes = []
+    lib.scldm_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class ScldmError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().scldm_last_error().decode(errors="replace")
+        raise ScldmError(f"{what} failed (code {rc}): {msg}")

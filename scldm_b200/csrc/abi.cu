@@ -1,0 +1,407 @@
+// C-ABI entry points (include/scldm_b200.h) and kernel launch sequences.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/scldm_b200.h"
+#include "dit_kernels.cuh"
+#include "vae_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) return fail(SCLDM_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                                     \
+  do {                                                                                         \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+    cudaError_t _e = cudaPeekAtLastError();                                                    \
+    if (_e != cudaSuccess) return fail(SCLDM_ECUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+struct DitWs {
+  float* X;
+  dit::bf16* qkv;
+  dit::bf16* ao;
+  dit::bf16* hid;
+  float* mod;
+  float* cls;
+  float* temb;
+  float* acc;
+  float* tvals;
+  size_t total;
+};
+
+DitWs carve_dit(void* base, const scldm_dit_weights* w, const scldm_dit_plan* plan, int n_evals) {
+  const size_t slots_pad = scldm_dit_slots_pad(plan), mod_pad = scldm_dit_mod_pad(plan);
+  const size_t rows = slots_pad * dit::TOK, row_tiles = rows / dit::BLOCK_M;
+  const size_t n_states = (size_t)plan->n_u + plan->n_g;
+  const size_t temb_rows = (size_t)n_evals > mod_pad ? (size_t)n_evals : mod_pad;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  char* b = static_cast<char*>(base);
+  DitWs ws;
+  ws.X = reinterpret_cast<float*>(b + take(rows * dit::D * 4));
+  ws.qkv = reinterpret_cast<dit::bf16*>(b + take(rows * 3 * dit::D * 2));
+  ws.ao = reinterpret_cast<dit::bf16*>(b + take(rows * dit::D * 2));
+  ws.hid = reinterpret_cast<dit::bf16*>(b + take(row_tiles * w->hid_slabs * dit::A_SLAB_BYTES));
+  ws.mod = reinterpret_cast<float*>(b + take(mod_pad * (size_t)w->mod_stride * 4));
+  ws.cls = reinterpret_cast<float*>(b + take(mod_pad * dit::D * 4));
+  ws.temb = reinterpret_cast<float*>(b + take(temb_rows * dit::D * 4));
+  ws.acc = reinterpret_cast<float*>(b + take(n_states * dit::TOK * dit::LAT * 4));
+  ws.tvals = reinterpret_cast<float*>(b + take(align_up((size_t)(n_evals > 0 ? n_evals : 1) * 4, 1024)));
+  ws.total = off;
+  return ws;
+}
+
+int check_dit(const scldm_dit_weights* w, const scldm_dit_plan* plan) {
+  if (!w || !plan) return fail(SCLDM_EINVAL, "null weights/plan");
+  if (w->n_layer < 1 || w->hidden < 1 || w->hidden > 768) return fail(SCLDM_EINVAL, "unsupported DiT dims: n_layer=%d hidden=%d", w->n_layer, w->hidden);
+  if (w->hid_slabs != ceil_div(w->hidden, 64) || w->mlp1_tiles != ceil_div(w->hidden, 128))
+    return fail(SCLDM_EINVAL, "inconsistent hid_slabs/mlp1_tiles");
+  if (w->mod_stride != w->n_layer * 6 * dit::D + 2 * dit::D) return fail(SCLDM_EINVAL, "bad mod_stride %d", w->mod_stride);
+  if (w->n_class < 0 || w->n_class > SCLDM_MAX_CLASSES) return fail(SCLDM_EINVAL, "n_class %d out of range", w->n_class);
+  if (plan->n_u < 0 || plan->n_g < 0 || plan->n_u + plan->n_g < 1) return fail(SCLDM_EINVAL, "empty plan");
+  if (plan->n_g > 0 && (plan->n_f < 1 || plan->n_f > SCLDM_MAX_COMBINE)) return fail(SCLDM_EINVAL, "n_f %d out of range", plan->n_f);
+  if (plan->n_mod < 1) return fail(SCLDM_EINVAL, "n_mod must be >= 1");
+  if (!plan->slot_mod || (w->n_class > 0 && !plan->cls_idx)) return fail(SCLDM_EINVAL, "null index arrays");
+  return SCLDM_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return SCLDM_OK;
+}
+
+struct TimeArgs { float t[64]; };
+__global__ void set_times_kernel(float* dst, TimeArgs a, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = a.t[threadIdx.x];
+}
+
+// adaLN modulation vectors of every block + final layer for all conditioning rows
+int launch_mod(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, const float* temb, long long temb_stride,
+               cudaStream_t st) {
+  const int mod_pad = scldm_dit_mod_pad(plan);
+  dit::AResParams p{};
+  p.temb = temb;
+  p.temb_row_stride = temb_stride;
+  p.cls = ws.cls;
+  p.Wp = static_cast<const dit::bf16*>(w->w_mod);
+  p.n_tiles_total = w->mod_stride / dit::BLOCK_N;
+  const int row_tiles = mod_pad / dit::BLOCK_M;
+  int groups = ceil_div(2 * 148, row_tiles);              // aim for ~2 waves of CTAs
+  if (groups > p.n_tiles_total) groups = p.n_tiles_total;
+  if (groups < 1) groups = 1;
+  p.tiles_per_cta = ceil_div(p.n_tiles_total, groups);
+  p.bias = w->b_mod;
+  p.out_f32 = ws.mod;
+  p.out_ld = w->mod_stride;
+  dim3 grid(row_tiles, ceil_div(p.n_tiles_total, p.tiles_per_cta));
+  dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD><<<grid, dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p);
+  LAUNCH_CHECK("gemm_ares<COND,MOD>");
+  return SCLDM_OK;
+}
+
+// the n_layer adaLN blocks on the residual stream ws.X (reference layers.py:208-221)
+int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, cudaStream_t st) {
+  const int slots_pad = scldm_dit_slots_pad(plan);
+  const int row_tiles = slots_pad * dit::TOK / dit::BLOCK_M;
+  const size_t tile_elems = (size_t)dit::KSLABS_D * dit::B_SLAB_ELEMS;
+  for (int l = 0; l < w->n_layer; ++l) {
+    const int mo = l * 6 * dit::D;
+    {  // LN1 + modulate + QKV
+      dit::AResParams p{};
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride;
+      p.mod_off_mul = mo + 0 * dit::D; p.mod_off_add = mo + 1 * dit::D; p.eps = w->eps;
+      p.Wp = static_cast<const dit::bf16*>(w->w_qkv) + (size_t)l * 3 * tile_elems;
+      p.n_tiles_total = 3; p.tiles_per_cta = 3;
+      p.bias = w->b_qkv + (size_t)l * 3 * dit::D;
+      p.out_bf16 = ws.qkv; p.out_ld = 3 * dit::D;
+      dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p);
+      LAUNCH_CHECK("gemm_ares<LN,QKV>");
+    }
+    dit::attn16_kernel<<<slots_pad, 256, 0, st>>>(ws.qkv, ws.ao, slots_pad);
+    LAUNCH_CHECK("attn16");
+    {  // c_proj + gated residual
+      dit::AStreamParams p{};
+      p.Ap = ws.ao; p.Wp = static_cast<const dit::bf16*>(w->w_proj) + (size_t)l * tile_elems; p.k_slabs = dit::KSLABS_D;
+      p.bias = w->b_proj + (size_t)l * dit::D;
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 2 * dit::D;
+      dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p);
+      LAUNCH_CHECK("gemm_astream<proj>");
+    }
+    {  // LN2 + modulate + [w1|w2] + SwiGLU
+      dit::AResParams p{};
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride;
+      p.mod_off_mul = mo + 3 * dit::D; p.mod_off_add = mo + 4 * dit::D; p.eps = w->eps;
+      p.Wp = static_cast<const dit::bf16*>(w->w_mlp1) + (size_t)l * w->mlp1_tiles * tile_elems;
+      p.n_tiles_total = w->mlp1_tiles; p.tiles_per_cta = w->mlp1_tiles;
+      p.out_packed = ws.hid; p.out_slabs = w->hid_slabs;
+      dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p);
+      LAUNCH_CHECK("gemm_ares<LN,SWIGLU>");
+    }
+    {  // mlp.c_proj + gated residual
+      dit::AStreamParams p{};
+      p.Ap = ws.hid; p.Wp = static_cast<const dit::bf16*>(w->w_mlp2) + (size_t)l * w->hid_slabs * dit::B_SLAB_ELEMS;
+      p.k_slabs = w->hid_slabs; p.bias = nullptr;
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 5 * dit::D;
+      dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p);
+      LAUNCH_CHECK("gemm_astream<mlp2>");
+    }
+  }
+  return SCLDM_OK;
+}
+
+dit::StepParams make_step(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws) {
+  dit::StepParams s{};
+  s.X = ws.X; s.mod = ws.mod; s.slot_mod = plan->slot_mod; s.mod_stride = w->mod_stride;
+  s.mod_off_final = w->n_layer * 6 * dit::D; s.eps = w->eps;
+  s.w_out = w->w_out; s.b_out = w->b_out; s.w_in = w->w_in; s.b_in = w->b_in; s.pos = w->pos;
+  s.n_u = plan->n_u; s.n_g = plan->n_g; s.n_f = plan->n_g > 0 ? plan->n_f : 1;
+  for (int i = 0; i < SCLDM_MAX_COMBINE; ++i) s.coef[i] = plan->coef[i];
+  s.acc = ws.acc;
+  return s;
+}
+
+int launch_cls(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, cudaStream_t st) {
+  const int mod_pad = scldm_dit_mod_pad(plan);
+  dit::ClsParams c{};
+  for (int i = 0; i < w->n_class; ++i) c.tables[i] = w->class_tables[i];
+  c.idx = plan->cls_idx; c.n_class = w->n_class; c.n_mod_pad = mod_pad;
+  dit::cls_kernel<<<mod_pad, 256, 0, st>>>(c, ws.cls);
+  LAUNCH_CHECK("cls");
+  return SCLDM_OK;
+}
+
+int prepare_kernels() {
+  static std::atomic<int> done{0};
+  if (done.load()) return SCLDM_OK;
+  int rc;
+  if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV>, dit::ares_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU>, dit::ares_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD>, dit::ares_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::gemm_astream_resid_kernel, dit::astream_smem_bytes()))) return rc;
+  if ((rc = set_smem(vae::mcab_decode_kernel, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float)))) return rc;
+  done.store(1);
+  return SCLDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t scldm_dit_slots_pad(const scldm_dit_plan* plan) {
+  const int n_f = plan->n_g > 0 ? plan->n_f : 1;
+  const int slots = plan->n_u + plan->n_g * n_f;
+  return ceil_div(slots, 8) * 8;
+}
+int32_t scldm_dit_mod_pad(const scldm_dit_plan* plan) { return ceil_div(plan->n_mod, dit::BLOCK_M) * dit::BLOCK_M; }
+
+size_t scldm_dit_workspace_bytes(const scldm_dit_weights* w, const scldm_dit_plan* plan, int32_t n_evals) {
+  if (!w || !plan) return 0;
+  return carve_dit(nullptr, w, plan, n_evals).total + 1024;
+}
+
+int32_t scldm_dit_workspace_layout(const scldm_dit_weights* w, const scldm_dit_plan* plan, int32_t n_evals, size_t* offsets,
+                                   int32_t max_entries) {
+  if (!w || !plan || !offsets) return 0;
+  const DitWs ws = carve_dit(nullptr, w, plan, n_evals);
+  const size_t v[9] = {(size_t)ws.X,   (size_t)ws.qkv,  (size_t)ws.ao,  (size_t)ws.hid,  (size_t)ws.mod,
+                       (size_t)ws.cls, (size_t)ws.temb, (size_t)ws.acc, (size_t)ws.tvals};
+  int n = 0;
+  for (; n < 9 && n < max_entries; ++n) offsets[n] = v[n];
+  return n;
+}
+
+int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, const float* t_mod, float* v_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_dit(w, plan))) return rc;
+  if (!x || !t_mod || !v_out || !workspace) return fail(SCLDM_EINVAL, "null buffer");
+  if (workspace_bytes < scldm_dit_workspace_bytes(w, plan, 0)) return fail(SCLDM_ENOMEM, "workspace too small");
+  if ((rc = prepare_kernels())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  const DitWs ws = carve_dit(base, w, plan, 0);
+  const int mod_pad = scldm_dit_mod_pad(plan);
+  const int n_states = plan->n_u + plan->n_g;
+
+  if ((rc = launch_cls(w, plan, ws, st))) return rc;
+  dit::temb_kernel<<<mod_pad, 256, 0, st>>>(t_mod, mod_pad, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb);
+  LAUNCH_CHECK("temb");
+  if ((rc = launch_mod(w, plan, ws, ws.temb, dit::D, st))) return rc;
+
+  dit::StepParams s = make_step(w, plan, ws);
+  s.x_base = const_cast<float*>(x);  // read only in inproj
+  dit::inproj_kernel<<<n_states, 256, 0, st>>>(s);
+  LAUNCH_CHECK("inproj");
+  if ((rc = launch_blocks(w, plan, ws, st))) return rc;
+  s.v_out = v_out; s.do_update = 0; s.do_inproj = 0;
+  dit::final_step_kernel<<<n_states, 256, 0, st>>>(s);
+  LAUNCH_CHECK("final_step");
+  return SCLDM_OK;
+}
+
+int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan, float* x, const float* t_grid_host, int32_t n_grid,
+                         int32_t method, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_dit(w, plan))) return rc;
+  if (!x || !t_grid_host || !workspace) return fail(SCLDM_EINVAL, "null buffer");
+  if (n_grid < 2) return fail(SCLDM_EINVAL, "need at least 2 grid points");
+  if (method != SCLDM_ODE_EULER && method != SCLDM_ODE_HEUN2 && method != SCLDM_ODE_MIDPOINT)
+    return fail(SCLDM_EINVAL, "unsupported ODE method %d (fixed-grid euler/heun2/midpoint only)", method);
+  const int n_steps = n_grid - 1;
+  const int stages = method == SCLDM_ODE_EULER ? 1 : 2;
+  const int n_evals = n_steps * stages;
+  if (workspace_bytes < scldm_dit_workspace_bytes(w, plan, n_evals)) return fail(SCLDM_ENOMEM, "workspace too small");
+  if ((rc = prepare_kernels())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  const DitWs ws = carve_dit(base, w, plan, n_evals);
+  const int n_states = plan->n_u + plan->n_g;
+
+  // evaluation times (fp32 arithmetic as torchdiffeq's fixed-grid solvers: t0, t0+dt/2 or t1)
+  {
+    int e = 0;
+    while (e < n_evals) {
+      TimeArgs ta{};
+      int n = 0;
+      for (; n < 64 && e + n < n_evals; ++n) {
+        const int idx = e + n, k = idx / stages, sg = idx % stages;
+        const float t0 = t_grid_host[k], t1 = t_grid_host[k + 1];
+        const float dt = t1 - t0;
+        float tv = t0;
+        if (sg == 1) tv = (method == SCLDM_ODE_HEUN2) ? t1 : t0 + 0.5f * dt;
+        ta.t[n] = tv;
+      }
+      set_times_kernel<<<1, 64, 0, st>>>(ws.tvals + e, ta, n);
+      LAUNCH_CHECK("set_times");
+      e += n;
+    }
+  }
+  dit::temb_kernel<<<n_evals, 256, 0, st>>>(ws.tvals, n_evals, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb);
+  LAUNCH_CHECK("temb");
+  if ((rc = launch_cls(w, plan, ws, st))) return rc;
+
+  dit::StepParams s = make_step(w, plan, ws);
+  s.x_base = x;
+  dit::inproj_kernel<<<n_states, 256, 0, st>>>(s);
+  LAUNCH_CHECK("inproj");
+  s.do_update = 1;
+  for (int k = 0; k < n_steps; ++k) {
+    const float dt = t_grid_host[k + 1] - t_grid_host[k];
+    for (int sg = 0; sg < stages; ++sg) {
+      const int e = k * stages + sg;
+      if ((rc = launch_mod(w, plan, ws, ws.temb + (size_t)e * dit::D, 0, st))) return rc;
+      if ((rc = launch_blocks(w, plan, ws, st))) return rc;
+      s.first_stage = sg == 0;
+      s.last_stage = sg == stages - 1;
+      if (method == SCLDM_ODE_EULER) { s.a_dt = 0.f; s.b_dt = dt; }
+      else if (method == SCLDM_ODE_HEUN2) { s.a_dt = dt; s.b_dt = 0.5f * dt; }
+      else { s.a_dt = 0.5f * dt; s.b_dt = sg == 0 ? 0.f : dt; }
+      s.do_inproj = !(k == n_steps - 1 && s.last_stage);
+      dit::final_step_kernel<<<n_states, 256, 0, st>>>(s);
+      LAUNCH_CHECK("final_step");
+    }
+  }
+  return SCLDM_OK;
+}
+
+int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* stream) {
+  if (!w || !qp) return fail(SCLDM_EINVAL, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  vae::qside_kernel<<<ceil_div(w->n_ids, 128), 128, 0, st>>>(w->emb, w->ca_ln1q_w, w->ca_ln1q_b, w->ca_wq, w->eps, w->n_ids, qp);
+  LAUNCH_CHECK("qside");
+  return SCLDM_OK;
+}
+
+size_t scldm_vae_decode_workspace_bytes(int32_t n_cells, int32_t n_genes) {
+  const size_t tiles = ceil_div(n_genes, 128);
+  return align_up((size_t)n_cells * vae::TOK * vae::KV * 4, 1024) + align_up((size_t)n_cells * n_genes * 4, 1024) +
+         align_up((size_t)n_cells * tiles * 8, 1024) + 1024;
+}
+
+int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const float* z, int32_t n_cells, const int64_t* genes,
+                     int32_t n_genes, const float* lib, float* mu, float* theta, float* counts, uint64_t seed, int64_t cell_offset,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w || !qp || !z || !genes || !lib || !workspace) return fail(SCLDM_EINVAL, "null argument");
+  if (n_cells < 1 || n_genes < 1) return fail(SCLDM_EINVAL, "empty decode: n_cells=%d n_genes=%d", n_cells, n_genes);
+  if (workspace_bytes < scldm_vae_decode_workspace_bytes(n_cells, n_genes)) return fail(SCLDM_ENOMEM, "workspace too small");
+  int rc;
+  if ((rc = prepare_kernels())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tiles = ceil_div(n_genes, 128);
+  char* b = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  float* kv = reinterpret_cast<float*>(b);
+  b += align_up((size_t)n_cells * vae::TOK * vae::KV * 4, 1024);
+  float* logits_ws = reinterpret_cast<float*>(b);
+  b += align_up((size_t)n_cells * n_genes * 4, 1024);
+  float2* partials = reinterpret_cast<float2*>(b);
+  float* logits = mu ? mu : logits_ws;  // finalised in place when mu is requested
+
+  vae::DecLatentParams dp{};
+  dp.z = z; dp.win_t = w->win_t; dp.blocks = w->blocks; dp.n_layer = w->n_layer;
+  dp.ca_ln1_w = w->ca_ln1_w; dp.ca_ln1_b = w->ca_ln1_b; dp.ca_wkv_t = w->ca_wkv_t; dp.eps = w->eps; dp.kv = kv;
+  vae::dec_latent_kernel<<<n_cells, 128, 0, st>>>(dp, n_cells);
+  LAUNCH_CHECK("dec_latent");
+
+  vae::McabParams mp{};
+  mp.emb = w->emb; mp.qp = qp; mp.genes = reinterpret_cast<const long long*>(genes); mp.G = n_genes; mp.kv = kv; mp.n_cells = n_cells;
+  // enough blocks for ~4 waves, but amortise the gene-side loads over several cells
+  int cpb = (int)(((long long)tiles * n_cells) / (148LL * 2 * 4));
+  if (cpb < 1) cpb = 1;
+  if (cpb > 32) cpb = 32;
+  mp.cells_per_block = cpb;
+  mp.wblob = w->mcab_blob; mp.eps = w->eps; mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
+  vae::mcab_decode_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 128, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float), st>>>(mp);
+  LAUNCH_CHECK("mcab_decode");
+
+  vae::NbParams np{};
+  np.logits = logits; np.partials = partials; np.gene_tiles = tiles; np.G = n_genes; np.n_cells = n_cells; np.lib = lib;
+  np.theta_tbl = w->theta_tbl; np.genes = reinterpret_cast<const long long*>(genes); np.mu = mu; np.theta = theta; np.counts = counts;
+  np.seed = seed; np.cell_offset = cell_offset;
+  int gx = ceil_div(n_genes, 256 * 4);
+  if (gx < 1) gx = 1;
+  vae::nb_finalize_kernel<<<dim3(n_cells, gx), 256, 0, st>>>(np);
+  LAUNCH_CHECK("nb_finalize");
+  return SCLDM_OK;
+}
+
+int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t seed, int64_t cell_offset, uint32_t stream_id,
+                      void* stream) {
+  if (!out || n_cells < 1 || per_cell < 1) return fail(SCLDM_EINVAL, "bad randn arguments");
+  const long long n = (long long)n_cells * per_cell;
+  vae::randn_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n_cells, per_cell, seed,
+                                                                                                      cell_offset, stream_id);
+  LAUNCH_CHECK("randn_cells");
+  return SCLDM_OK;
+}
+
+uint64_t scldm_launch_count(void) { return g_launches.load(); }
+const char* scldm_last_error(void) { return g_err; }
+const char* scldm_version(void) { return "scldm_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

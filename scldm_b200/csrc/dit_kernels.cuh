@@ -1,0 +1,788 @@
+// DiT denoiser kernels for sm_100a (scLDM generation hot path).
+//
+// Work unit: a "slot" = one cell-forward = 16 latent tokens x 256 channels.  A 128-row GEMM
+// tile is exactly 8 slots, so LayerNorm rows and attention cells never straddle tiles.
+//
+// Per DiT block (reference layers.py:208-221) four launches:
+//   gemm_ares<PRO_LN , EPI_QKV   >  LN + adaLN modulate (prologue)  -> QKV GEMM (tcgen05)  -> +bias, bf16
+//   attn16_kernel                   16-token self attention per (slot, head) on mma.sync    -> swizzled A tiles
+//   gemm_astream<EPI_RESID>         c_proj GEMM (tcgen05, A+B by bulk TMA) -> x += gate*(acc+bias)
+//   gemm_ares<PRO_LN , EPI_SWIGLU>  LN + modulate -> [w1|w2] GEMM -> silu(a)*b -> swizzled A tiles
+//   gemm_astream<EPI_RESID>         mlp.c_proj GEMM -> x += gate*acc
+// plus per model evaluation:
+//   gemm_ares<PRO_COND, EPI_MOD>    SiLU(t_emb + class_emb) -> all adaLN modulation vectors of all blocks
+//   final_step_kernel               final LN/modulate/linear + CFG combine + ODE stage update + next input_proj
+#pragma once
+
+#include "sm100.cuh"
+
+namespace dit {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int D = 256;      // n_embed
+constexpr int TOK = 16;     // latent tokens per cell (seq_len)
+constexpr int LAT = 16;     // latent channels (n_embed_input)
+constexpr int NHEAD = 8;
+constexpr int HD = 32;
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;
+constexpr int KSLABS_D = D / BLOCK_K;                  // 4
+constexpr int A_SLAB_BYTES = BLOCK_M * BLOCK_K * 2;    // 16384
+constexpr int B_SLAB_BYTES = BLOCK_N * BLOCK_K * 2;    // 32768
+constexpr int A_SLAB_ELEMS = BLOCK_M * BLOCK_K;
+constexpr int B_SLAB_ELEMS = BLOCK_N * BLOCK_K;
+constexpr int STG_BYTES = 128 * 272;                   // epilogue staging (fp32 64-col chunk, 16 B row pad)
+constexpr int NUM_THREADS = 192;                       // warp0 TMA, warp1 MMA, warps 2-5 prologue/epilogue
+constexpr int EPI_THREADS = 128;
+constexpr int MAX_COMBINE = 8;
+
+enum { PRO_LN = 0, PRO_COND = 1 };
+enum { EPI_QKV = 0, EPI_SWIGLU = 1, EPI_MOD = 2 };
+
+struct AResParams {
+  // ---- A operand source -----------------------------------------------------------------
+  const float* X;        // PRO_LN: residual stream [rows_pad][256] fp32
+  const float* mod;      // PRO_LN: modulation table [n_mod_pad][mod_stride] fp32
+  const int* slot_mod;   // PRO_LN: [slots_pad] -> row of mod
+  int mod_stride;
+  int mod_off_mul;       // column offset of the multiplicative chunk (h = LN(x)*(1+mul)+add)
+  int mod_off_add;
+  float eps;
+  const float* temb;     // PRO_COND: [*, 256] timestep embedding rows
+  long long temb_row_stride;  // PRO_COND: 0 => one shared row (sampling), 256 => one row per mod row
+  const float* cls;      // PRO_COND: [n_mod_pad][256] summed class embeddings
+  // ---- B operand ------------------------------------------------------------------------
+  const bf16* Wp;        // packed [n_tiles][4 slabs][256 x 64 swizzled]
+  int n_tiles_total;
+  int tiles_per_cta;
+  const float* bias;     // [n_tiles_total*256] fp32 (EPI_QKV / EPI_MOD) or nullptr
+  // ---- output ---------------------------------------------------------------------------
+  bf16* out_bf16;        // EPI_QKV : [rows_pad][out_ld] bf16 row-major
+  float* out_f32;        // EPI_MOD : [rows_pad][out_ld] fp32 row-major
+  int out_ld;
+  bf16* out_packed;      // EPI_SWIGLU: [row_tiles][out_slabs][128 x 64 swizzled]
+  int out_slabs;
+};
+
+struct AStreamParams {
+  const bf16* Ap;        // packed A [row_tiles][k_slabs][128 x 64 swizzled]
+  const bf16* Wp;        // packed B [k_slabs][256 x 64 swizzled]
+  int k_slabs;
+  const float* bias;     // [256] or nullptr
+  float* X;              // residual stream, updated in place
+  const float* mod;
+  const int* slot_mod;
+  int mod_stride;
+  int mod_off_gate;
+};
+
+// ==========================================================================================
+// shared pipeline pieces
+// ==========================================================================================
+struct RingState {
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t nstages) {
+    if (++stage == nstages) { stage = 0; phase ^= 1; }
+  }
+};
+
+// Issue the 4 K=16 MMAs of one 64-wide K slab.  a_smem / b_smem are slab base addresses (u32).
+__device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc,
+                                                bool first_slab) {
+  const uint64_t a_desc = sm100::make_kmajor_sw128_desc(a_smem);
+  const uint64_t b_desc = sm100::make_kmajor_sw128_desc(b_smem);
+#pragma unroll
+  for (uint32_t k = 0; k < BLOCK_K / 16; ++k) {
+    // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+    sm100::umma_bf16_ss(tmem_d, a_desc + 2ull * k, b_desc + 2ull * k, idesc, (first_slab && k == 0) ? 0u : 1u);
+  }
+}
+
+// ==========================================================================================
+// GEMM with an A operand produced in-kernel (resident for the CTA's whole N loop)
+// ==========================================================================================
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResParams p) {
+  constexpr uint32_t NSTAGE = 3;
+  constexpr uint32_t TMEM_COLS = 512;  // two 256-column fp32 accumulators
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                                     // 4 x 16 KB
+  uint8_t* smB = smem + KSLABS_D * A_SLAB_BYTES;           // NSTAGE x 32 KB
+  uint8_t* smStg = smB + NSTAGE * B_SLAB_BYTES;            // 34 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smStg + STG_BYTES);
+  uint64_t* full = bars;                 // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
+  uint64_t* tmem_full = bars + 2 * NSTAGE;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint64_t* a_ready = tmem_empty + 2;        // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const int row_tile = blockIdx.x;
+  const int tile0 = blockIdx.y * p.tiles_per_cta;
+  const int ntiles = min(p.tiles_per_cta, p.n_tiles_total - tile0);
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < NSTAGE; ++i) {
+      sm100::mbar_init(&full[i], 1);
+      sm100::mbar_init(&empty[i], 1);
+    }
+    for (uint32_t i = 0; i < 2; ++i) {
+      sm100::mbar_init(&tmem_full[i], 1);
+      sm100::mbar_init(&tmem_empty[i], EPI_THREADS);
+    }
+    sm100::mbar_init(a_ready, EPI_THREADS);
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: stream packed weight slabs ======================
+    if (lane == 0) {
+      RingState rs;
+      for (int t = 0; t < ntiles; ++t) {
+        const bf16* wt = p.Wp + (size_t)(tile0 + t) * KSLABS_D * B_SLAB_ELEMS;
+        for (int ks = 0; ks < KSLABS_D; ++ks) {
+          sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+          sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
+          sm100::bulk_g2s(smB + rs.stage * B_SLAB_BYTES, wt + (size_t)ks * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
+          rs.advance(NSTAGE);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) ====================================
+    if (lane == 0) {
+      const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
+      sm100::mbar_wait(a_ready, 0);
+      sm100::tc_fence_after();
+      RingState rs;
+      for (int t = 0; t < ntiles; ++t) {
+        const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+        sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        sm100::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int ks = 0; ks < KSLABS_D; ++ks) {
+          sm100::mbar_wait(&full[rs.stage], rs.phase);
+          sm100::tc_fence_after();
+          issue_slab_mmas(tmem_d, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smB + rs.stage * B_SLAB_BYTES),
+                          idesc, ks == 0);
+          sm100::umma_commit(&empty[rs.stage]);  // frees the B stage when these MMAs retire
+          rs.advance(NSTAGE);
+        }
+        sm100::umma_commit(&tmem_full[acc]);     // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== prologue + epilogue warps (128 threads) =======================
+    const uint32_t ew = warp - 2;          // 0..3: A-production work split
+    const uint32_t q = warp & 3;           // TMEM sub-partition this warp may read
+    const uint32_t etid = threadIdx.x - 64;
+
+    // ---------- produce the A tile (128 rows x 256 K, bf16, swizzled) ----------
+    if constexpr (PRO == PRO_LN) {
+      // warp ew owns rows [32*ew, 32*ew+32) = 2 slots; lane owns columns [8*lane, 8*lane+8)
+      const float inv_d = 1.0f / D;
+#pragma unroll 1
+      for (int sl = 0; sl < 2; ++sl) {
+        const int slot = row_tile * 8 + ew * 2 + sl;
+        const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride;
+        const float4 m0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8);
+        const float4 m1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8 + 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8 + 4);
+        const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
+        const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll 4
+        for (int tk = 0; tk < TOK; ++tk) {
+          const int r = ew * 32 + sl * 16 + tk;  // row within tile
+          const float* xr = p.X + ((size_t)row_tile * BLOCK_M + r) * D + lane * 8;
+          const float4 x0 = *reinterpret_cast<const float4*>(xr);
+          const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+          float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += v[j];
+          const float mean = sm100::warp_sum(s) * inv_d;
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] -= mean; ss += v[j] * v[j]; }
+          const float rstd = rsqrtf(sm100::warp_sum(ss) * inv_d + p.eps);
+          uint4 o;
+          o.x = sm100::pack_bf16x2(v[0] * rstd * mul[0] + add[0], v[1] * rstd * mul[1] + add[1]);
+          o.y = sm100::pack_bf16x2(v[2] * rstd * mul[2] + add[2], v[3] * rstd * mul[3] + add[3]);
+          o.z = sm100::pack_bf16x2(v[4] * rstd * mul[4] + add[4], v[5] * rstd * mul[5] + add[5]);
+          o.w = sm100::pack_bf16x2(v[6] * rstd * mul[6] + add[6], v[7] * rstd * mul[7] + add[7]);
+          // column 8*lane -> slab lane/8, 16-byte chunk lane%8
+          *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
+        }
+      }
+    } else {
+      // PRO_COND: A[m][k] = SiLU(temb[k] + cls[m][k]); warp ew owns 32 rows, lane owns 8 columns
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int r = ew * 32 + i;
+        const size_t m = (size_t)row_tile * BLOCK_M + r;
+        const float* tr = p.temb + m * p.temb_row_stride + lane * 8;
+        const float* cr = p.cls + m * D + lane * 8;
+        const float4 t0 = *reinterpret_cast<const float4*>(tr);
+        const float4 t1 = *reinterpret_cast<const float4*>(tr + 4);
+        const float4 c0 = *reinterpret_cast<const float4*>(cr);
+        const float4 c1 = *reinterpret_cast<const float4*>(cr + 4);
+        uint4 o;
+        o.x = sm100::pack_bf16x2(sm100::silu(t0.x + c0.x), sm100::silu(t0.y + c0.y));
+        o.y = sm100::pack_bf16x2(sm100::silu(t0.z + c0.z), sm100::silu(t0.w + c0.w));
+        o.z = sm100::pack_bf16x2(sm100::silu(t1.x + c1.x), sm100::silu(t1.y + c1.y));
+        o.w = sm100::pack_bf16x2(sm100::silu(t1.z + c1.z), sm100::silu(t1.w + c1.w));
+        *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
+      }
+    }
+    sm100::fence_proxy_async_smem();   // generic-proxy smem writes -> visible to UMMA
+    sm100::mbar_arrive(a_ready);
+
+    // ---------- epilogue over this CTA's N tiles ----------
+    const uint32_t row = q * 32 + lane;                       // accumulator row == TMEM lane
+    const size_t grow = (size_t)row_tile * BLOCK_M + row;     // global row
+    uint32_t store_cnt = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+      const int tile = tile0 + t;
+      sm100::mbar_wait(&tmem_full[acc], acc_phase);
+      sm100::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BLOCK_N;
+
+      if constexpr (EPI == EPI_QKV) {
+        // 4 chunks of 64 columns: acc + bias -> bf16 -> swizzled staging -> coalesced row-major store
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          sm100::named_bar_sync(1, EPI_THREADS);  // staging free
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            sm100::tmem_ld_32x32b_x32(taddr + ch * 64 + h * 32, v);
+            sm100::tmem_ld_wait();
+            const float* bp = p.bias + tile * BLOCK_N + ch * 64 + h * 32;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 o;
+              o.x = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 0]) + bp[c * 8 + 0], __uint_as_float(v[c * 8 + 1]) + bp[c * 8 + 1]);
+              o.y = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 2]) + bp[c * 8 + 2], __uint_as_float(v[c * 8 + 3]) + bp[c * 8 + 3]);
+              o.z = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 4]) + bp[c * 8 + 4], __uint_as_float(v[c * 8 + 5]) + bp[c * 8 + 5]);
+              o.w = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 6]) + bp[c * 8 + 6], __uint_as_float(v[c * 8 + 7]) + bp[c * 8 + 7]);
+              *reinterpret_cast<uint4*>(smStg + sm100::swz_chunk_offset(row, h * 4 + c)) = o;
+            }
+          }
+          sm100::named_bar_sync(1, EPI_THREADS);  // staging full
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const uint32_t r = it * 16 + (etid >> 3), c = etid & 7;
+            const uint4 o = *reinterpret_cast<const uint4*>(smStg + sm100::swz_chunk_offset(r, c));
+            bf16* dst = p.out_bf16 + ((size_t)row_tile * BLOCK_M + r) * p.out_ld + tile * BLOCK_N + ch * 64 + c * 8;
+            *reinterpret_cast<uint4*>(dst) = o;
+          }
+        }
+      } else if constexpr (EPI == EPI_MOD) {
+        // fp32 row-major + bias; staging rows padded to 272 B (conflict-free 16 B accesses)
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          sm100::named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            sm100::tmem_ld_32x32b_x32(taddr + ch * 64 + h * 32, v);
+            sm100::tmem_ld_wait();
+            const float* bp = p.bias + tile * BLOCK_N + ch * 64 + h * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 o;
+              o.x = __uint_as_float(v[c * 4 + 0]) + bp[c * 4 + 0];
+              o.y = __uint_as_float(v[c * 4 + 1]) + bp[c * 4 + 1];
+              o.z = __uint_as_float(v[c * 4 + 2]) + bp[c * 4 + 2];
+              o.w = __uint_as_float(v[c * 4 + 3]) + bp[c * 4 + 3];
+              *reinterpret_cast<float4*>(smStg + row * 272 + (h * 8 + c) * 16) = o;
+            }
+          }
+          sm100::named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const uint32_t r = it * 8 + (etid >> 4), c = etid & 15;
+            const float4 o = *reinterpret_cast<const float4*>(smStg + r * 272 + c * 16);
+            float* dst = p.out_f32 + ((size_t)row_tile * BLOCK_M + r) * p.out_ld + tile * BLOCK_N + ch * 64 + c * 4;
+            *reinterpret_cast<float4*>(dst) = o;
+          }
+        }
+      } else {
+        // EPI_SWIGLU: tile columns [0,128) = w1 rows, [128,256) = w2 rows of hidden [128*tile, 128*tile+128)
+        // -> two 64-wide hidden slabs, each written as a swizzled A slab and bulk-stored (16 KB contiguous)
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {
+          const int slab = tile * 2 + hs;
+          if (slab >= p.out_slabs) break;  // uniform across threads
+          uint8_t* buf = smStg + (store_cnt & 1) * A_SLAB_BYTES;
+          if (etid == 0) sm100::bulk_wait_read<1>();  // the store that last used this buffer has drained
+          sm100::named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t va[32], vb[32];
+            sm100::tmem_ld_32x32b_x32(taddr + hs * 64 + h * 32, va);
+            sm100::tmem_ld_32x32b_x32(taddr + 128 + hs * 64 + h * 32, vb);
+            sm100::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float hv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                hv[j] = sm100::silu(__uint_as_float(va[c * 8 + j])) * __uint_as_float(vb[c * 8 + j]);
+              uint4 o;
+              o.x = sm100::pack_bf16x2(hv[0], hv[1]);
+              o.y = sm100::pack_bf16x2(hv[2], hv[3]);
+              o.z = sm100::pack_bf16x2(hv[4], hv[5]);
+              o.w = sm100::pack_bf16x2(hv[6], hv[7]);
+              *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, h * 4 + c)) = o;
+            }
+          }
+          sm100::fence_proxy_async_smem();
+          sm100::named_bar_sync(1, EPI_THREADS);
+          if (etid == 0) {
+            sm100::bulk_s2g(p.out_packed + ((size_t)row_tile * p.out_slabs + slab) * A_SLAB_ELEMS, buf, A_SLAB_BYTES);
+            sm100::bulk_commit();
+          }
+          ++store_cnt;
+        }
+      }
+      // accumulator drained -> MMA warp may overwrite it
+      sm100::tc_fence_before();
+      sm100::mbar_arrive(&tmem_empty[acc]);
+    }
+    if constexpr (EPI == EPI_SWIGLU) {
+      if (etid == 0) sm100::bulk_wait<0>();
+    }
+    (void)grow;
+  }
+
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) sm100::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+constexpr size_t ares_smem_bytes() {
+  return 1024 + KSLABS_D * A_SLAB_BYTES + 3 * B_SLAB_BYTES + STG_BYTES + 256;
+}
+
+// ==========================================================================================
+// GEMM with both operands streamed by bulk TMA; epilogue x += gate * (acc + bias)
+// ==========================================================================================
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(const AStreamParams p) {
+  constexpr uint32_t NSTAGE = 3;
+  constexpr uint32_t STAGE_BYTES = A_SLAB_BYTES + B_SLAB_BYTES;  // 48 KB
+  constexpr uint32_t TMEM_COLS = 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smStage = smem;                              // NSTAGE x (A 16 KB | B 32 KB)
+  uint8_t* smStg = smem + NSTAGE * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smStg + STG_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NSTAGE;
+  uint64_t* tmem_full = bars + 2 * NSTAGE;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const int row_tile = blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < NSTAGE; ++i) {
+      sm100::mbar_init(&full[i], 1);
+      sm100::mbar_init(&empty[i], 1);
+    }
+    sm100::mbar_init(tmem_full, 1);
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      RingState rs;
+      const bf16* a_src = p.Ap + (size_t)row_tile * p.k_slabs * A_SLAB_ELEMS;
+      for (int ks = 0; ks < p.k_slabs; ++ks) {
+        sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+        sm100::mbar_arrive_expect_tx(&full[rs.stage], STAGE_BYTES);
+        uint8_t* st = smStage + rs.stage * STAGE_BYTES;
+        sm100::bulk_g2s(st, a_src + (size_t)ks * A_SLAB_ELEMS, A_SLAB_BYTES, &full[rs.stage]);
+        sm100::bulk_g2s(st + A_SLAB_BYTES, p.Wp + (size_t)ks * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
+        rs.advance(NSTAGE);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
+      RingState rs;
+      for (int ks = 0; ks < p.k_slabs; ++ks) {
+        sm100::mbar_wait(&full[rs.stage], rs.phase);
+        sm100::tc_fence_after();
+        const uint32_t st = sm100::smem_u32(smStage + rs.stage * STAGE_BYTES);
+        issue_slab_mmas(tmem_base, st, st + A_SLAB_BYTES, idesc, ks == 0);
+        sm100::umma_commit(&empty[rs.stage]);
+        rs.advance(NSTAGE);
+      }
+      sm100::umma_commit(tmem_full);
+    }
+  } else {
+    const uint32_t q = warp & 3;
+    const uint32_t etid = threadIdx.x - 64;
+    const uint32_t row = q * 32 + lane;
+    sm100::mbar_wait(tmem_full, 0);
+    sm100::tc_fence_after();
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      sm100::named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        sm100::tmem_ld_32x32b_x32(taddr + ch * 64 + h * 32, v);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 o;
+          o.x = __uint_as_float(v[c * 4 + 0]);
+          o.y = __uint_as_float(v[c * 4 + 1]);
+          o.z = __uint_as_float(v[c * 4 + 2]);
+          o.w = __uint_as_float(v[c * 4 + 3]);
+          *reinterpret_cast<float4*>(smStg + row * 272 + (h * 8 + c) * 16) = o;
+        }
+      }
+      sm100::named_bar_sync(1, EPI_THREADS);
+      // coalesced read-modify-write of the residual stream: 2 rows x 256 B per warp instruction
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const uint32_t r = it * 8 + (etid >> 4), c = etid & 15;
+        const int col = ch * 64 + c * 4;
+        float4 a = *reinterpret_cast<const float4*>(smStg + r * 272 + c * 16);
+        if (p.bias != nullptr) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        const int slot = row_tile * 8 + (r >> 4);
+        const float4 g = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod[slot] * p.mod_stride + p.mod_off_gate + col);
+        float* xp = p.X + ((size_t)row_tile * BLOCK_M + r) * D + col;
+        float4 x = *reinterpret_cast<float4*>(xp);
+        x.x += g.x * a.x; x.y += g.y * a.y; x.z += g.z * a.z; x.w += g.w * a.w;
+        *reinterpret_cast<float4*>(xp) = x;
+      }
+    }
+  }
+
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) sm100::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+constexpr size_t astream_smem_bytes() { return 1024 + 3 * (A_SLAB_BYTES + B_SLAB_BYTES) + STG_BYTES + 256; }
+
+// ==========================================================================================
+// 16-token self attention, one warp per (slot, head), tensor cores via mma.sync m16n8k16 (bf16)
+//   qkv: [rows_pad][768] bf16 row-major (q | k | v, heads = contiguous 32-channel groups; layers.py:147-151)
+//   out: swizzled A tiles [row_tiles][4 slabs][128 x 64] bf16 (A operand of the c_proj GEMM)
+// ==========================================================================================
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out_packed, int n_slots) {
+  const int slot = blockIdx.x;
+  const int head = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t g = lane >> 2, t = lane & 3;
+  if (slot >= n_slots) return;
+  const bf16* base = qkv + (size_t)slot * TOK * (3 * D) + head * HD;
+  auto ld2 = [&](int token, int part, int dim) -> uint32_t {
+    return *reinterpret_cast<const uint32_t*>(base + (size_t)token * (3 * D) + part * D + dim);
+  };
+  // S = Q K^T : A = Q (16 tokens x 32 dims) in two k-steps; B[k=dim][n=key] = K[key][dim]
+  float s[2][4] = {};
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t a[4];
+    a[0] = ld2(g, 0, ks * 16 + 2 * t);
+    a[1] = ld2(g + 8, 0, ks * 16 + 2 * t);
+    a[2] = ld2(g, 0, ks * 16 + 2 * t + 8);
+    a[3] = ld2(g + 8, 0, ks * 16 + 2 * t + 8);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const uint32_t b0 = ld2(nt * 8 + g, 1, ks * 16 + 2 * t);
+      const uint32_t b1 = ld2(nt * 8 + g, 1, ks * 16 + 2 * t + 8);
+      mma_bf16_16816(s[nt], a, b0, b1);
+    }
+  }
+  // softmax over the 16 keys of rows g (c0,c1) and g+8 (c2,c3); a row lives in the 4 lanes of a quad
+  const float scale_log2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+  float m0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+  float m1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    s[nt][0] = exp2f((s[nt][0] - m0) * scale_log2);
+    s[nt][1] = exp2f((s[nt][1] - m0) * scale_log2);
+    s[nt][2] = exp2f((s[nt][2] - m1) * scale_log2);
+    s[nt][3] = exp2f((s[nt][3] - m1) * scale_log2);
+    l0 += s[nt][0] + s[nt][1];
+    l1 += s[nt][2] + s[nt][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float r0 = 1.0f / l0, r1 = 1.0f / l1;
+  // P (normalised, bf16) as the A operand of O = P V : C-fragment layout == A-fragment layout
+  uint32_t pa[4];
+  pa[0] = sm100::pack_bf16x2(s[0][0] * r0, s[0][1] * r0);
+  pa[1] = sm100::pack_bf16x2(s[0][2] * r1, s[0][3] * r1);
+  pa[2] = sm100::pack_bf16x2(s[1][0] * r0, s[1][1] * r0);
+  pa[3] = sm100::pack_bf16x2(s[1][2] * r1, s[1][3] * r1);
+  // B[k=key][n=dim] = V[key][dim]: load V as 8x8 (token, dim-pair) tiles and transpose in registers
+  float o[4][4] = {};
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const uint32_t v0 = ld2(g, 2, nt * 8 + 2 * t);      // tokens 0-7 , dims nt*8 + (2t, 2t+1)
+    const uint32_t v1 = ld2(g + 8, 2, nt * 8 + 2 * t);  // tokens 8-15
+    const uint32_t b0 = movmatrix_trans(v0);            // -> (keys 2t,2t+1 ; dim nt*8+g)
+    const uint32_t b1 = movmatrix_trans(v1);            // -> (keys 2t+8,.. ; dim nt*8+g)
+    mma_bf16_16816(o[nt], pa, b0, b1);
+  }
+  // write O rows (g, g+8) x dims (nt*8 + 2t, +1) into the swizzled A-tile layout
+  const size_t grow0 = (size_t)slot * TOK + g, grow1 = grow0 + 8;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = head * HD + nt * 8 + 2 * t;
+    const int slab = col >> 6, chunk = (col & 63) >> 3, within = col & 7;
+    {
+      const size_t tile = grow0 >> 7; const uint32_t r = grow0 & 127;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(out_packed + (tile * KSLABS_D + slab) * A_SLAB_ELEMS) + sm100::swz_chunk_offset(r, chunk) + within * 2;
+      *reinterpret_cast<uint32_t*>(dst) = sm100::pack_bf16x2(o[nt][0], o[nt][1]);
+    }
+    {
+      const size_t tile = grow1 >> 7; const uint32_t r = grow1 & 127;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(out_packed + (tile * KSLABS_D + slab) * A_SLAB_ELEMS) + sm100::swz_chunk_offset(r, chunk) + within * 2;
+      *reinterpret_cast<uint32_t*>(dst) = sm100::pack_bf16x2(o[nt][2], o[nt][3]);
+    }
+  }
+}
+
+// ==========================================================================================
+// small fp32 kernels: timestep embedding, class-embedding sum, input projection
+// ==========================================================================================
+// temb[i] = W2 * SiLU(W0 * [cos(t f) | sin(t f)] + b0) + b2  (layers.py:351-364). Weights transposed [in][out].
+__global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, int n_t, const float* __restrict__ w0t,
+                                                    const float* __restrict__ b0, const float* __restrict__ w2t,
+                                                    const float* __restrict__ b2, float* __restrict__ temb) {
+  __shared__ float f[256];
+  __shared__ float h[256];
+  const int i = blockIdx.x;
+  if (i >= n_t) return;
+  const int d = threadIdx.x;
+  const float tv = t[i];
+  {
+    const int k = d & 127;
+    const float freq = expf(-9.210340371976184f * (float)k / 128.0f);  // exp(-ln(1e4) k / half)
+    const float arg = tv * freq;
+    f[d] = (d < 128) ? cosf(arg) : sinf(arg);
+  }
+  __syncthreads();
+  float acc = b0[d];
+#pragma unroll 8
+  for (int k = 0; k < 256; ++k) acc += f[k] * w0t[k * D + d];
+  h[d] = sm100::silu(acc);
+  __syncthreads();
+  float acc2 = b2[d];
+#pragma unroll 8
+  for (int k = 0; k < D; ++k) acc2 += h[k] * w2t[k * D + d];
+  temb[(size_t)i * D + d] = acc2;
+}
+
+// cls[m] = sum over class tables of emb_c[idx[c][m]]   (nnets.py:403-426, 447-456)
+struct ClsParams {
+  const float* tables[8];
+  const int* idx;   // [n_class][n_mod_pad]
+  int n_class;
+  int n_mod_pad;
+};
+__global__ void __launch_bounds__(256) cls_kernel(const ClsParams p, float* __restrict__ cls) {
+  const int m = blockIdx.x, d = threadIdx.x;
+  float acc = 0.f;
+  for (int c = 0; c < p.n_class; ++c) acc += p.tables[c][(size_t)p.idx[c * p.n_mod_pad + m] * D + d];
+  cls[(size_t)m * D + d] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// State <-> slot mapping for one model evaluation.
+//   states [0, n_u)        : one slot each (slot = state), coefficient 1
+//   states [n_u, n_u+n_g)  : n_f consecutive slots starting at n_u + (state-n_u)*n_f, combined as
+//                            v = sum_k coef[k] * out[slot_k]   (CFG: coef = [1-sum w, w_1, ...], nnets.py:353-378)
+// ------------------------------------------------------------------------------------------
+struct StepParams {
+  float* X;               // residual stream [slots_pad*16][256]
+  const float* mod;       // modulation table
+  const int* slot_mod;
+  int mod_stride;
+  int mod_off_final;      // offset of the final layer's (shift | scale) chunks in a mod row
+  float eps;
+  const float* w_out;     // final_layer.linear.weight [16][256]
+  const float* b_out;     // [16]
+  const float* w_in;      // input_proj.weight [256][16]
+  const float* b_in;      // [256]
+  const float* pos;       // pos_embed [16][256]
+  int n_u, n_g, n_f;
+  float coef[MAX_COMBINE];
+  // ODE stage update (fixed-grid explicit RK whose stage s only needs k_{s-1}):
+  //   acc (+)= b*dt*v ;  last stage: x_base += acc, x_eval = x_base ; else x_eval = x_base + a*dt*v
+  float* x_base;          // [n_states][16][16]
+  float* acc;             // [n_states][16][16]
+  float* v_out;           // optional: write the combined model output here (plain forward)
+  float a_dt, b_dt;
+  int first_stage, last_stage;
+  int do_update;          // 0: only v_out
+  int do_inproj;          // project x_eval for the next evaluation
+};
+
+__device__ __forceinline__ void state_slots(const StepParams& p, int state, int& slot0, int& nslots) {
+  if (state < p.n_u) { slot0 = state; nslots = 1; }
+  else { slot0 = p.n_u + (state - p.n_u) * p.n_f; nslots = p.n_f; }
+}
+
+// x (state) -> X rows of every slot of that state:  input_proj(x) + pos_embed  (nnets.py:290-291)
+__global__ void __launch_bounds__(256) inproj_kernel(const StepParams p) {
+  __shared__ float xs[TOK * LAT];
+  const int state = blockIdx.x, d = threadIdx.x;
+  xs[d] = p.x_base[(size_t)state * TOK * LAT + d];
+  __syncthreads();
+  float w[LAT];
+#pragma unroll
+  for (int o = 0; o < LAT; ++o) w[o] = p.w_in[d * LAT + o];
+  const float b = p.b_in ? p.b_in[d] : 0.f;
+  int slot0, ns;
+  state_slots(p, state, slot0, ns);
+  for (int tk = 0; tk < TOK; ++tk) {
+    float acc = b + p.pos[tk * D + d];
+#pragma unroll
+    for (int o = 0; o < LAT; ++o) acc += xs[tk * LAT + o] * w[o];
+    for (int k = 0; k < ns; ++k) p.X[((size_t)(slot0 + k) * TOK + tk) * D + d] = acc;
+  }
+}
+
+// final layer (layers.py:397-401: LN(x)*(1+scale)+shift with shift = chunk 0, scale = chunk 1; Linear 256->16)
+// + CFG combine + ODE stage update + input projection of the next evaluation point.
+// One block per state, 8 warps, each warp handles 2 tokens.
+__global__ void __launch_bounds__(256) final_step_kernel(const StepParams p) {
+  __shared__ float s_wout[LAT * D];   // 16 KB
+  __shared__ float s_win[D * LAT];    // 16 KB
+  const int state = blockIdx.x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < LAT * D; i += 256) {
+    s_wout[i] = p.w_out[i];
+    s_win[i] = p.w_in[i];
+  }
+  __syncthreads();
+  int slot0, ns;
+  state_slots(p, state, slot0, ns);
+  const float inv_d = 1.0f / D;
+#pragma unroll 1
+  for (int ti = 0; ti < 2; ++ti) {
+    const int tk = warp * 2 + ti;
+    float vsum = 0.f;  // lane o (<16) accumulates combined output channel o
+#pragma unroll 1
+    for (int k = 0; k < ns; ++k) {
+      const int slot = slot0 + k;
+      const float* xr = p.X + ((size_t)slot * TOK + tk) * D + lane * 8;
+      const float4 x0 = *reinterpret_cast<const float4*>(xr);
+      const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+      float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+      const float mean = sm100::warp_sum(s) * inv_d;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[j] -= mean; ss += v[j] * v[j]; }
+      const float rstd = rsqrtf(sm100::warp_sum(ss) * inv_d + p.eps);
+      const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride + p.mod_off_final;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float shift = mrow[lane * 8 + j], scale = mrow[D + lane * 8 + j];
+        v[j] = v[j] * rstd * (1.f + scale) + shift;
+      }
+      float mine = 0.f;
+#pragma unroll 4
+      for (int o = 0; o < LAT; ++o) {
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part += v[j] * s_wout[o * D + lane * 8 + j];
+        part = sm100::warp_sum(part);
+        if ((int)lane == o) mine = part;
+      }
+      if (lane < LAT) mine += (p.b_out ? p.b_out[lane] : 0.f);
+      const float coef = (ns == 1) ? 1.0f : p.coef[k];
+      vsum += coef * mine;
+    }
+    // lane o < 16 holds v[state][tk][o]
+    float x_eval = 0.f;
+    if (lane < LAT) {
+      const size_t idx = ((size_t)state * TOK + tk) * LAT + lane;
+      if (p.v_out) p.v_out[idx] = vsum;
+      if (p.do_update) {
+        float acc = p.first_stage ? 0.f : p.acc[idx];
+        acc += p.b_dt * vsum;
+        const float xb = p.x_base[idx];
+        if (p.last_stage) {
+          x_eval = xb + acc;
+          p.x_base[idx] = x_eval;
+        } else {
+          p.acc[idx] = acc;
+          x_eval = xb + p.a_dt * vsum;
+        }
+      }
+    }
+    if (p.do_inproj) {
+      float h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = (p.b_in ? p.b_in[lane * 8 + j] : 0.f) + p.pos[tk * D + lane * 8 + j];
+#pragma unroll
+      for (int o = 0; o < LAT; ++o) {
+        const float xo = __shfl_sync(0xffffffffu, x_eval, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] += xo * s_win[(lane * 8 + j) * LAT + o];
+      }
+      for (int k = 0; k < ns; ++k) {
+        float* dst = p.X + ((size_t)(slot0 + k) * TOK + tk) * D + lane * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(h[4], h[5], h[6], h[7]);
+      }
+    }
+  }
+}
+
+}  // namespace dit

@@ -1,0 +1,441 @@
+// Transformer-VAE decoder kernels (scLDM generation hot path), fp32 CUDA-core first version.
+//
+//   dec_latent_kernel   per cell: LN16 -> Linear(16->32) -> n_layer Blocks (E=32, 8 heads of 4) ->
+//                       K,V = c_attn(LN1(x)) of the MCAB (16 keys x 64)      nnets.py:203-205, layers.py:252
+//   qside_kernel        per gene id: Qp = c_attn_q(LN1q(emb[g]))  -- cell-invariant when use_adaln=false,
+//                       computed once per vocabulary                            layers.py:253,326
+//   mcab_decode_kernel  per (cell, gene): 4-head attention over the 16 latent keys, c_proj, x = q + attn,
+//                       LN2, SwiGLU MLP, residual, NB-head logit; never materialises (G,E) activations
+//                       or the (cells,4,G,16) score tensor                       layers.py:325-330
+//   nb_finalize_kernel  softmax over genes * library size -> mu; theta = exp(table[g]); optional
+//                       Gamma-Poisson draw                                      stochastic_layers.py:102-116
+#pragma once
+
+#include "rng.cuh"
+#include "sm100.cuh"
+
+namespace vae {
+
+constexpr int E = 32;        // n_embed
+constexpr int LAT = 16;      // n_embed_latent
+constexpr int TOK = 16;      // latent tokens
+constexpr int NH = 8;        // self-attention heads (head_dim 4)
+constexpr int NHC = 4;       // cross-attention heads (head_dim 8)
+constexpr int HID = 88;      // SwiGLU hidden
+constexpr int KV = 2 * E;    // 64
+
+// ---- packed fp32 weights of one non-adaLN Block (all matrices transposed to [in][out]) ----
+struct BlockW {
+  const float* ln1_w; const float* ln1_b; const float* ln2_w; const float* ln2_b;
+  const float* wqkv_t;   // [32][96]
+  const float* wproj_t;  // [32][32]
+  const float* w1_t;     // [32][88]
+  const float* w2_t;     // [32][88]
+  const float* w3_t;     // [88][32]
+};
+
+struct DecLatentParams {
+  const float* z;        // [cells][16][16]
+  const float* win_t;    // decoder_latent_input.1.weight^T [16][32]
+  const float* blocks;   // n_layer x BLOCK_STRIDE floats (see pack.py)
+  int n_layer;
+  const float* ca_ln1_w; const float* ca_ln1_b;
+  const float* ca_wkv_t; // [32][64]  (k | v)
+  float eps;
+  float* kv;             // [cells][16][64]
+};
+
+constexpr int BLK_LN1W = 0, BLK_LN1B = 32, BLK_LN2W = 64, BLK_LN2B = 96, BLK_WQKV = 128, BLK_WPROJ = BLK_WQKV + 32 * 96,
+              BLK_W1 = BLK_WPROJ + 32 * 32, BLK_W2 = BLK_W1 + 32 * HID, BLK_W3 = BLK_W2 + 32 * HID,
+              BLOCK_STRIDE = BLK_W3 + HID * 32;
+
+// LayerNorm over 32 channels for 16 tokens; 128 threads: thread = (token = tid/8, part = tid%8 -> 4 channels)
+__device__ __forceinline__ void ln32_tokens(const float (*x)[E], float (*y)[E], const float* w, const float* b, float eps, int tid) {
+  const int tok = tid >> 3, part = tid & 7;
+  float v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[j] = x[tok][part * 4 + j]; s += v[j]; }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  const float mean = s * (1.0f / E);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[j] -= mean; ss += v[j] * v[j]; }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  const float rstd = rsqrtf(ss * (1.0f / E) + eps);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = part * 4 + j;
+    y[tok][c] = v[j] * rstd * (w ? w[c] : 1.f) + (b ? b[c] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(128) dec_latent_kernel(const DecLatentParams p, int n_cells) {
+  __shared__ float x[TOK][E];
+  __shared__ float h[TOK][E];
+  __shared__ float qkv[TOK][3 * E];
+  __shared__ float hid[TOK][HID];
+  const int cell = blockIdx.x, tid = threadIdx.x;
+  if (cell >= n_cells) return;
+  // LN over the 16 latent channels (no affine) then Linear(16 -> 32, no bias)
+  {
+    float (*zs)[LAT] = reinterpret_cast<float (*)[LAT]>(&qkv[0][0]);
+    for (int i = tid; i < TOK * LAT; i += 128) zs[i / LAT][i % LAT] = p.z[(size_t)cell * TOK * LAT + i];
+    __syncthreads();
+    if (tid < TOK) {
+      float m = 0.f;
+      for (int j = 0; j < LAT; ++j) m += zs[tid][j];
+      m *= (1.0f / LAT);
+      float var = 0.f;
+      for (int j = 0; j < LAT; ++j) { const float dlt = zs[tid][j] - m; var += dlt * dlt; }
+      const float rstd = rsqrtf(var * (1.0f / LAT) + p.eps);
+      for (int j = 0; j < LAT; ++j) zs[tid][j] = (zs[tid][j] - m) * rstd;
+    }
+    __syncthreads();
+    for (int i = tid; i < TOK * E; i += 128) {
+      const int tok = i / E, c = i % E;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < LAT; ++k) acc += zs[tok][k] * p.win_t[k * E + c];
+      x[tok][c] = acc;
+    }
+    __syncthreads();
+  }
+  for (int l = 0; l < p.n_layer; ++l) {
+    const float* w = p.blocks + (size_t)l * BLOCK_STRIDE;
+    ln32_tokens(x, h, w + BLK_LN1W, w + BLK_LN1B, p.eps, tid);
+    __syncthreads();
+    for (int i = tid; i < TOK * 3 * E; i += 128) {
+      const int tok = i / (3 * E), j = i % (3 * E);
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WQKV + k * 3 * E + j];
+      qkv[tok][j] = acc;
+    }
+    __syncthreads();
+    {
+      // one thread per (query token, head): head_dim 4, softmax over 16 keys, scale 1/sqrt(4)
+      const int tok = tid >> 3, hd = tid & 7;
+      float q[4], s[TOK];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) q[d] = qkv[tok][hd * 4 + d];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) a += q[d] * qkv[k][E + hd * 4 + d];
+        s[k] = a * 0.5f;
+        mx = fmaxf(mx, s[k]);
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) { s[k] = __expf(s[k] - mx); den += s[k]; }
+      const float inv = 1.0f / den;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) o[d] += s[k] * qkv[k][2 * E + hd * 4 + d];
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d) h[tok][hd * 4 + d] = o[d] * inv;
+    }
+    __syncthreads();
+    for (int i = tid; i < TOK * E; i += 128) {
+      const int tok = i / E, c = i % E;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WPROJ + k * E + c];
+      x[tok][c] += acc;
+    }
+    __syncthreads();
+    ln32_tokens(x, h, w + BLK_LN2W, w + BLK_LN2B, p.eps, tid);
+    __syncthreads();
+    for (int i = tid; i < TOK * HID; i += 128) {
+      const int tok = i / HID, j = i % HID;
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < E; ++k) {
+        a += h[tok][k] * w[BLK_W1 + k * HID + j];
+        b += h[tok][k] * w[BLK_W2 + k * HID + j];
+      }
+      hid[tok][j] = sm100::silu(a) * b;
+    }
+    __syncthreads();
+    for (int i = tid; i < TOK * E; i += 128) {
+      const int tok = i / E, c = i % E;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < HID; ++k) acc += hid[tok][k] * w[BLK_W3 + k * E + c];
+      x[tok][c] += acc;
+    }
+    __syncthreads();
+  }
+  // MCAB key/value projection of the latents
+  ln32_tokens(x, h, p.ca_ln1_w, p.ca_ln1_b, p.eps, tid);
+  __syncthreads();
+  for (int i = tid; i < TOK * KV; i += 128) {
+    const int tok = i / KV, j = i % KV;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < E; ++k) acc += h[tok][k] * p.ca_wkv_t[k * KV + j];
+    p.kv[(size_t)cell * TOK * KV + i] = acc;
+  }
+}
+
+// Qp[g] = Wq * LN1q(emb[g]) for every vocabulary id (incl. the mask id 0)
+__global__ void __launch_bounds__(128) qside_kernel(const float* __restrict__ emb, const float* __restrict__ ln_w,
+                                                     const float* __restrict__ ln_b, const float* __restrict__ wq /*[out][in]*/,
+                                                     float eps, int n_ids, float* __restrict__ qp) {
+  __shared__ float s_wq[E * E];
+  for (int i = threadIdx.x; i < E * E; i += 128) s_wq[i] = wq[i];
+  __syncthreads();
+  const int g = blockIdx.x * 128 + threadIdx.x;
+  if (g >= n_ids) return;
+  float v[E];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < E; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(emb + (size_t)g * E + c);
+    v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+    s += t.x + t.y + t.z + t.w;
+  }
+  const float mean = s * (1.0f / E);
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < E; ++c) { v[c] -= mean; ss += v[c] * v[c]; }
+  const float rstd = rsqrtf(ss * (1.0f / E) + eps);
+#pragma unroll
+  for (int c = 0; c < E; ++c) v[c] = v[c] * rstd * ln_w[c] + ln_b[c];
+#pragma unroll 4
+  for (int j = 0; j < E; j += 4) {
+    float o[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < E; ++c) acc += v[c] * s_wq[(j + jj) * E + c];
+      o[jj] = acc;
+    }
+    *reinterpret_cast<float4*>(qp + (size_t)g * E + j) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- MCAB decode + NB-head logit ---------------------------------------------------------
+struct McabParams {
+  const float* emb;       // gene embedding table [n_ids][32]
+  const float* qp;        // Q-side table [n_ids][32]
+  const long long* genes; // [G] vocabulary ids shared by all cells (datamodule.py:689 tiles one row)
+  int G;
+  const float* kv;        // [cells][16][64]
+  int n_cells;
+  int cells_per_block;
+  // smem-resident weights, one contiguous fp32 blob:
+  //   wproj [32][32] (out,in) | ln2_w[32] | ln2_b[32] | w1 [88][32] | w2 [88][32] | w3_t [88][32] | head_w[32] | head_b
+  const float* wblob;
+  float eps;
+  float* logits;          // [cells][G]
+  float2* partials;       // [cells][gene_tiles] (max, sum exp(l - max))
+  int gene_tiles;
+};
+constexpr int MW_PROJ = 0, MW_LN2W = 1024, MW_LN2B = 1056, MW_W1 = 1088, MW_W2 = MW_W1 + HID * E, MW_W3T = MW_W2 + HID * E,
+              MW_HW = MW_W3T + HID * E, MW_HB = MW_HW + E, MW_TOTAL = MW_HB + 4;
+
+__global__ void __launch_bounds__(128) mcab_decode_kernel(const McabParams p) {
+  extern __shared__ __align__(16) float smf[];
+  float* sw = smf;                      // MW_TOTAL
+  float* skv = smf + MW_TOTAL;          // [16][64]
+  __shared__ float red_m[4], red_s[4];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < MW_TOTAL; i += 128) sw[i] = p.wblob[i];
+  const int gi = blockIdx.x * 128 + tid;
+  const bool valid = gi < p.G;
+  float emb[E], qv[E];
+  {
+    const long long gid = valid ? p.genes[gi] : 0;
+#pragma unroll
+    for (int c = 0; c < E; c += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(p.emb + (size_t)gid * E + c);
+      const float4 b = *reinterpret_cast<const float4*>(p.qp + (size_t)gid * E + c);
+      emb[c] = a.x; emb[c + 1] = a.y; emb[c + 2] = a.z; emb[c + 3] = a.w;
+      qv[c] = b.x; qv[c + 1] = b.y; qv[c + 2] = b.z; qv[c + 3] = b.w;
+    }
+  }
+  const int cell0 = blockIdx.y * p.cells_per_block;
+  const int cell1 = min(cell0 + p.cells_per_block, p.n_cells);
+  const float sc = 0.35355339059327373f * 1.4426950408889634f;  // 1/sqrt(8) * log2(e)
+  for (int cell = cell0; cell < cell1; ++cell) {
+    __syncthreads();
+    for (int i = tid; i < TOK * KV / 4; i += 128)
+      reinterpret_cast<float4*>(skv)[i] = reinterpret_cast<const float4*>(p.kv + (size_t)cell * TOK * KV)[i];
+    __syncthreads();
+    // ---- 4-head cross attention over the 16 latent keys (head_dim 8) ----
+    float o[E];
+#pragma unroll
+    for (int hh = 0; hh < NHC; ++hh) {
+      float s[TOK];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) {
+        const float4 k0 = *reinterpret_cast<const float4*>(skv + k * KV + hh * 8);
+        const float4 k1 = *reinterpret_cast<const float4*>(skv + k * KV + hh * 8 + 4);
+        float a = qv[hh * 8 + 0] * k0.x + qv[hh * 8 + 1] * k0.y + qv[hh * 8 + 2] * k0.z + qv[hh * 8 + 3] * k0.w +
+                  qv[hh * 8 + 4] * k1.x + qv[hh * 8 + 5] * k1.y + qv[hh * 8 + 6] * k1.z + qv[hh * 8 + 7] * k1.w;
+        s[k] = a;
+        mx = fmaxf(mx, a);
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) { s[k] = exp2f((s[k] - mx) * sc); den += s[k]; }
+      const float inv = 1.0f / den;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) {
+        const float4 v0 = *reinterpret_cast<const float4*>(skv + k * KV + E + hh * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(skv + k * KV + E + hh * 8 + 4);
+        acc[0] += s[k] * v0.x; acc[1] += s[k] * v0.y; acc[2] += s[k] * v0.z; acc[3] += s[k] * v0.w;
+        acc[4] += s[k] * v1.x; acc[5] += s[k] * v1.y; acc[6] += s[k] * v1.z; acc[7] += s[k] * v1.w;
+      }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) o[hh * 8 + d] = acc[d] * inv;
+    }
+    // ---- x = q + c_proj(attn) ----
+    float x[E];
+#pragma unroll
+    for (int c = 0; c < E; ++c) {
+      float acc = emb[c];
+#pragma unroll
+      for (int j = 0; j < E; j += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + MW_PROJ + c * E + j);
+        acc += o[j] * w.x + o[j + 1] * w.y + o[j + 2] * w.z + o[j + 3] * w.w;
+      }
+      x[c] = acc;
+    }
+    // ---- LN2 ----
+    float hl[E];
+    {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < E; ++c) s += x[c];
+      const float mean = s * (1.0f / E);
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < E; ++c) { hl[c] = x[c] - mean; ss += hl[c] * hl[c]; }
+      const float rstd = rsqrtf(ss * (1.0f / E) + p.eps);
+#pragma unroll
+      for (int c = 0; c < E; ++c) hl[c] = hl[c] * rstd * sw[MW_LN2W + c] + sw[MW_LN2B + c];
+    }
+    // ---- SwiGLU MLP, hidden unit by hidden unit (rank-1 updates of x) ----
+#pragma unroll 2
+    for (int j = 0; j < HID; ++j) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int c = 0; c < E; c += 4) {
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + MW_W1 + j * E + c);
+        const float4 w2 = *reinterpret_cast<const float4*>(sw + MW_W2 + j * E + c);
+        a += hl[c] * w1.x + hl[c + 1] * w1.y + hl[c + 2] * w1.z + hl[c + 3] * w1.w;
+        b += hl[c] * w2.x + hl[c + 1] * w2.y + hl[c + 2] * w2.z + hl[c + 3] * w2.w;
+      }
+      const float hv = sm100::silu(a) * b;
+#pragma unroll
+      for (int c = 0; c < E; c += 4) {
+        const float4 w3 = *reinterpret_cast<const float4*>(sw + MW_W3T + j * E + c);
+        x[c] += hv * w3.x; x[c + 1] += hv * w3.y; x[c + 2] += hv * w3.z; x[c + 3] += hv * w3.w;
+      }
+    }
+    // ---- NB head logit + per-tile softmax partials ----
+    float logit = sw[MW_HB];
+#pragma unroll
+    for (int c = 0; c < E; ++c) logit += x[c] * sw[MW_HW + c];
+    if (valid) p.logits[(size_t)cell * p.G + gi] = logit;
+    const float lm = valid ? logit : -INFINITY;
+    const float wm = sm100::warp_max(lm);
+    if ((tid & 31) == 0) red_m[tid >> 5] = wm;
+    __syncthreads();
+    const float bm = fmaxf(fmaxf(red_m[0], red_m[1]), fmaxf(red_m[2], red_m[3]));
+    const float ev = valid ? __expf(logit - bm) : 0.f;
+    const float ws = sm100::warp_sum(ev);
+    if ((tid & 31) == 0) red_s[tid >> 5] = ws;
+    __syncthreads();
+    if (tid == 0) p.partials[(size_t)cell * p.gene_tiles + blockIdx.x] = make_float2(bm, red_s[0] + red_s[1] + red_s[2] + red_s[3]);
+  }
+}
+
+// ---- softmax-over-genes finalisation + optional NB sampling --------------------------------
+struct NbParams {
+  const float* logits;     // [cells][G]
+  const float2* partials;  // [cells][gene_tiles]
+  int gene_tiles;
+  int G;
+  int n_cells;
+  const float* lib;        // [cells] library size
+  const float* theta_tbl;  // decoder_head.theta.weight [n_ids] (log theta)
+  const long long* genes;  // [G]
+  float* mu;               // [cells][G] or nullptr
+  float* theta;            // [G] or nullptr (written by cell 0 blocks)
+  float* counts;           // [cells][G] or nullptr
+  unsigned long long seed;
+  long long cell_offset;   // global index of cell 0 (sharding / chunking invariance)
+};
+
+__global__ void __launch_bounds__(256) nb_finalize_kernel(const NbParams p) {
+  __shared__ float s_m, s_s;
+  __shared__ float rm[8], rs[8];
+  const int cell = blockIdx.x, tid = threadIdx.x;
+  // combine the per-tile (max, sum) pairs of this cell
+  float m = -INFINITY;
+  for (int i = tid; i < p.gene_tiles; i += 256) m = fmaxf(m, p.partials[(size_t)cell * p.gene_tiles + i].x);
+  m = sm100::warp_max(m);
+  if ((tid & 31) == 0) rm[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float mm = rm[0];
+    for (int i = 1; i < 8; ++i) mm = fmaxf(mm, rm[i]);
+    s_m = mm;
+  }
+  __syncthreads();
+  const float gm = s_m;
+  float s = 0.f;
+  for (int i = tid; i < p.gene_tiles; i += 256) {
+    const float2 pr = p.partials[(size_t)cell * p.gene_tiles + i];
+    s += pr.y * __expf(pr.x - gm);
+  }
+  s = sm100::warp_sum(s);
+  if ((tid & 31) == 0) rs[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += rs[i];
+    s_s = t;
+  }
+  __syncthreads();
+  const float scale = p.lib[cell] / s_s;
+  const long long gcell = p.cell_offset + cell;
+  for (int gi = blockIdx.y * 256 + tid; gi < p.G; gi += gridDim.y * 256) {
+    const float muv = __expf(p.logits[(size_t)cell * p.G + gi] - gm) * scale;
+    const float th = __expf(p.theta_tbl[p.genes[gi]]);
+    if (p.mu) p.mu[(size_t)cell * p.G + gi] = muv;
+    if (p.theta && cell == 0) p.theta[gi] = th;
+    if (p.counts) {
+      rng::Philox g(p.seed, (uint32_t)gi, (uint32_t)gcell, (uint32_t)(gcell >> 32) ^ 0x4E42u);
+      p.counts[(size_t)cell * p.G + gi] = rng::negative_binomial(g, muv, th);
+    }
+  }
+}
+
+// standard normal noise / log-normal size factors keyed by global cell index
+__global__ void __launch_bounds__(256) randn_cells_kernel(float* out, int n_cells, int per_cell, unsigned long long seed,
+                                                           long long cell_offset, unsigned int stream) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long long)n_cells * per_cell) return;
+  const long long cell = cell_offset + i / per_cell;
+  rng::Philox g(seed, (uint32_t)(i % per_cell), (uint32_t)cell, (uint32_t)(cell >> 32) ^ stream);
+  out[i] = g.normal();
+}
+
+}  // namespace vae

@@ -1,0 +1,133 @@
+"""`LatentDiffusion.sample` drop-in (`scldm/models.py:766-819`) without the Lightning shell.
+
+The reference class is a LightningModule whose generation entry point is `sample(condition,
+guidance_weight, batch_size, genes, timesteps)`; training/optimizer/EMA/logging glue is out of scope
+(SURVEY.md §2a row 6).  This class keeps the attribute names (`vae_model`, `diffusion_model`,
+`transport`, `transport_sampler`) and the `sample` signature/return (`(counts (2B,G), z (2B,M,L))`,
+rows [0,B) unconditional, rows [B,2B) guided) and runs every stage on the GPU:
+
+  size factors  table lookup + Philox normal (replaces the per-cell `.item()` loop, models.py:585-596)
+  noise         Philox N(0,1) keyed by global cell index
+  ODE + CFG     one C-ABI call per chunk of cells (all steps, both CFG branches batched)
+  decode        fused latent blocks -> MCAB -> NB head -> Gamma-Poisson draw
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .nnets import DiT
+from .transport import Sampler, Transport
+from .transport.transport import FusedCFGModel
+from .vae import TransformerVAE
+
+STREAM_NOISE = 0x5A01
+STREAM_SIZE_FACTOR = 0x5A02
+
+
+class LatentDiffusion(nn.Module):
+    def __init__(self, vae_model: TransformerVAE, diffusion_model: DiT, transport: Transport,
+                 mu_size_factor: dict | None = None, sd_size_factor: dict | None = None,
+                 size_factor_condition_key: str | None = None, sampling_method: str = "euler", num_steps: int = 50,
+                 seed: int = 0, cell_chunk: int = 1024, **_unused_training_kwargs):
+        super().__init__()
+        self.vae_model = vae_model
+        self.diffusion_model = diffusion_model
+        self.transport = transport
+        self.transport_sampler = Sampler(transport)
+        self.mu_size_factor, self.sd_size_factor = mu_size_factor, sd_size_factor
+        self.size_factor_condition_key = size_factor_condition_key
+        self.sampling_method, self.num_steps = sampling_method, num_steps
+        self.seed = seed
+        self.cell_chunk = cell_chunk
+        self.cells_generated = 0  # global cell counter -> RNG offsets independent of batching / sharding
+        self._sf_tables: dict = {}
+
+    @property
+    def device(self):
+        return self.diffusion_model.pos_embed.device
+
+    # ---- size factors (independent path of `_sample_log_size_factors`, models.py:552-597) ----
+    def _size_factor_key(self, condition) -> str | None:
+        if condition is None or self.mu_size_factor is None or self.sd_size_factor is None:
+            return None
+        k = self.size_factor_condition_key
+        if k and k in condition and k in self.mu_size_factor and k in self.sd_size_factor:
+            return k
+        inter = sorted(set(condition) & set(self.mu_size_factor) & set(self.sd_size_factor))
+        return inter[0] if inter else None
+
+    def _sample_log_size_factors(self, condition, batch_size: int, cell_offset: int) -> torch.Tensor:
+        key = self._size_factor_key(condition)
+        if key is None:
+            return torch.zeros(batch_size, device=self.device)
+        if key not in self._sf_tables:
+            vocab = self.diffusion_model.class_vocab_sizes.get(key, max(self.mu_size_factor[key]) + 1)
+            mu = torch.zeros(vocab + 1)
+            sd = torch.zeros(vocab + 1)  # classes without statistics draw exactly 0, as the reference
+            for c, v in self.mu_size_factor[key].items():
+                if c in self.sd_size_factor[key]:
+                    mu[c], sd[c] = float(v), float(self.sd_size_factor[key][c])
+            self._sf_tables[key] = (mu.to(self.device), sd.to(self.device))
+        mu, sd = self._sf_tables[key]
+        eps = ops.randn_cells(batch_size, 1, self.seed, cell_offset, STREAM_SIZE_FACTOR, self.device).reshape(-1)
+        lab = condition[key].to(self.device).long()
+        return mu[lab] + sd[lab] * eps
+
+    @torch.no_grad()
+    def sample(self, condition: dict[str, torch.Tensor] | None, guidance_weight: dict[str, float] | None, batch_size: int,
+               genes: torch.Tensor, timesteps: int = 50, *, z0: torch.Tensor | None = None,
+               log_size_factors: torch.Tensor | None = None, return_mu: bool = False):
+        """Generation (`models.py:766-819`).  `timesteps` is accepted and ignored exactly as in the reference
+        (`models.py:773,793`); the grid is `self.num_steps` points.  `z0` / `log_size_factors` may be injected
+        (parity tests share them with the oracle); otherwise they are drawn on device."""
+        if len(genes) != batch_size:
+            raise ValueError(f"genes batch dimension ({genes.shape[0]}) must match batch_size ({batch_size})")
+        if condition is not None:
+            for key, values in condition.items():
+                if len(values) != batch_size:
+                    raise ValueError(f"Condition '{key}' length ({len(values)}) must match batch size ({batch_size})")
+        if guidance_weight is not None and condition is not None:
+            assert set(guidance_weight.keys()) == set(condition.keys()), (
+                f"Guidance weight keys {set(guidance_weight.keys())} must match condition keys {set(condition.keys())}")
+        dev = self.device
+        dit = self.diffusion_model
+        offset = self.cells_generated
+        self.cells_generated += batch_size
+        lsf = log_size_factors.to(dev).float() if log_size_factors is not None else \
+            self._sample_log_size_factors(condition, batch_size, offset)
+        if z0 is None:
+            z0 = ops.randn_cells(batch_size, dit.seq_len * dit.config.n_embed_input, self.seed, offset, STREAM_NOISE, dev)
+            z0 = z0.view(batch_size, dit.seq_len, dit.config.n_embed_input)
+        z0 = z0.to(dev).float()
+        sample_fn = self.transport_sampler.sample_ode(sampling_method=self.sampling_method, num_steps=self.num_steps)
+        model_fn = FusedCFGModel(dit, guidance_weight)
+        cond = {k: v.to(dev) for k, v in (condition or {}).items()}
+        gvec = genes[0] if genes.dim() == 2 else genes
+        gvec = gvec.to(dev).contiguous()
+        lib = torch.exp(lsf)
+        G = gvec.numel()
+        counts = torch.empty(2 * batch_size, G, dtype=torch.float32, device=dev)
+        mu_out = torch.empty(2 * batch_size, G, dtype=torch.float32, device=dev) if return_mu else None
+        z_out = torch.empty(2 * batch_size, dit.seq_len, dit.config.n_embed_input, dtype=torch.float32, device=dev)
+        # cells are independent: run the ODE + decode chunk by chunk so the working set stays L2-sized
+        for c0 in range(0, batch_size, self.cell_chunk):
+            c1 = min(c0 + self.cell_chunk, batch_size)
+            zc = z0[c0:c1]
+            cc = {k: torch.cat([v[c0:c1], v[c0:c1]]) for k, v in cond.items()}
+            zf = sample_fn(torch.cat([zc, zc]), model_fn, condition=cc)[-1]
+            n = c1 - c0
+            libc = torch.cat([lib[c0:c1], lib[c0:c1]])
+            for half, rows in ((0, slice(c0, c1)), (1, slice(batch_size + c0, batch_size + c1))):
+                zh = zf[half * n:(half + 1) * n]
+                cts, mu, _ = self.vae_model.decode_counts(zh, gvec, libc[half * n:(half + 1) * n], seed=self.seed,
+                                                          cell_offset=offset + c0 + half * (1 << 40), want_mu=return_mu)
+                counts[rows] = cts
+                z_out[rows] = zh
+                if return_mu:
+                    mu_out[rows] = mu
+        if return_mu:
+            return counts, z_out, mu_out
+        return counts, z_out

@@ -1,0 +1,225 @@
+"""Drop-in replacements for `scldm.nnets.{DiT, Encoder, Decoder}`: same constructor kwargs, same
+`state_dict` layout, same call signatures -- the arithmetic runs in hand-written sm_100a kernels
+through the C-ABI (`include/scldm_b200.h`).  Inference (eval-mode) semantics only in this round.
+"""
+
+from __future__ import annotations
+
+from typing import Literal
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import DiTConfig
+from .layers import Block, CrossAttentionBlock, FinalLayerDit, TimestepEmbedder, get_1d_sincos_pos_embed
+from .pack import PackedDiT
+
+
+class Encoder(nn.Module):
+    """weights of `scldm.nnets.Encoder` (`nnets.py:81-135`); driven by `TransformerVAE.encode`."""
+
+    def __init__(self, n_layer, n_inducing_points, n_embed, n_embed_latent, n_head, n_head_cross, dropout, bias, multiple_of,
+                 layernorm_eps, norm_layer, positional_encoding=False):
+        super().__init__()
+        self.latent_embedding = n_embed_latent
+        self.latent_dim = n_inducing_points
+        self.pos_embed = nn.Parameter(torch.zeros(1, n_inducing_points, n_embed), requires_grad=False) if positional_encoding else None
+        self.ca_layer = CrossAttentionBlock(n_embed=n_embed, n_inducing_points=n_inducing_points, n_head=n_head_cross, dropout=dropout,
+                                            bias=bias, norm_layer=norm_layer, multiple_of=multiple_of, layernorm_eps=layernorm_eps)
+        self.encoder_layers = nn.ModuleList([
+            Block(n_embed=n_embed, n_head=n_head, dropout=dropout, bias=bias, norm_layer=norm_layer, multiple_of=multiple_of,
+                  layernorm_eps=layernorm_eps) for _ in range(n_layer)])
+        self.encoder_latent_input = nn.Sequential(
+            nn.Linear(n_embed, n_embed_latent, bias=bias),
+            nn.LayerNorm(n_embed_latent, eps=layernorm_eps, elementwise_affine=False))
+        self.hparams_ = dict(n_layer=n_layer, n_inducing_points=n_inducing_points, n_embed=n_embed, n_embed_latent=n_embed_latent,
+                             n_head=n_head, n_head_cross=n_head_cross, bias=bias, multiple_of=multiple_of,
+                             layernorm_eps=layernorm_eps, positional_encoding=positional_encoding)
+
+    def forward(self, x):
+        raise RuntimeError("Encoder is driven through TransformerVAE.encode (fused kernels); no eager fallback")
+
+
+class Decoder(nn.Module):
+    """weights of `scldm.nnets.Decoder` (`nnets.py:147-198`); driven by `TransformerVAE.decode`."""
+
+    def __init__(self, n_genes, n_embed, n_embed_latent, n_head, n_head_cross, n_layer, n_inducing_points, dropout, bias,
+                 multiple_of, layernorm_eps, norm_layer, shared_embedding, use_adaln=False):
+        super().__init__()
+        self.gene_embedding = nn.Embedding(n_genes + 1, n_embed) if not shared_embedding else nn.Identity()
+        self.decoder_latent_input = nn.Sequential(
+            nn.LayerNorm(n_embed_latent, eps=layernorm_eps, elementwise_affine=False),
+            nn.Linear(n_embed_latent, n_embed, bias=bias))
+        self.decoder_layers = nn.ModuleList([
+            Block(n_embed=n_embed, n_head=n_head, dropout=dropout, bias=bias, norm_layer=norm_layer, multiple_of=multiple_of,
+                  layernorm_eps=layernorm_eps, use_adaln=use_adaln) for _ in range(n_layer)])
+        self.decoder_cross_attention = CrossAttentionBlock(
+            n_embed=n_embed, n_inducing_points=0, n_head=n_head_cross, dropout=dropout, bias=bias, norm_layer=norm_layer,
+            multiple_of=multiple_of, layernorm_eps=layernorm_eps, use_adaln=use_adaln)
+        self.hparams_ = dict(n_genes=n_genes, n_embed=n_embed, n_embed_latent=n_embed_latent, n_head=n_head,
+                             n_head_cross=n_head_cross, n_layer=n_layer, n_inducing_points=n_inducing_points, bias=bias,
+                             multiple_of=multiple_of, layernorm_eps=layernorm_eps, shared_embedding=shared_embedding,
+                             use_adaln=use_adaln)
+
+    def forward(self, x, genes, condition=None):
+        raise RuntimeError("Decoder is driven through TransformerVAE.decode (fused MCAB + NB-head kernel); no eager fallback")
+
+
+class DiT(nn.Module):
+    """Diffusion Transformer, drop-in for `scldm.nnets.DiT` (`nnets.py:216-492`)."""
+
+    def __init__(self, n_embed: int, n_embed_input: int, n_layer: int, n_head: int, seq_len: int, dropout: float, bias: bool,
+                 norm_layer: str, multiple_of: int, layernorm_eps: float, class_vocab_sizes: dict[str, int],
+                 cfg_dropout_prob: float = 0.1, condition_strategy: Literal["mutually_exclusive", "joint"] = "mutually_exclusive"):
+        super().__init__()
+        self.class_vocab_sizes = dict(class_vocab_sizes)
+        self.cfg_dropout_prob = cfg_dropout_prob
+        self.condition_strategy = condition_strategy
+        self.class_embeddings = nn.ModuleDict()
+        for name, vocab in class_vocab_sizes.items():
+            self.class_embeddings[name] = nn.Embedding(vocab + int(cfg_dropout_prob > 0), n_embed)
+        self.t_embedder = TimestepEmbedder(n_embed)
+        self.pos_embed = nn.Parameter(torch.zeros(1, seq_len, n_embed), requires_grad=False)
+        self.blocks = nn.ModuleList([
+            Block(n_embed=n_embed, n_head=n_head, dropout=dropout, bias=bias, norm_layer=norm_layer, multiple_of=multiple_of,
+                  layernorm_eps=layernorm_eps, use_adaln=True, elementwise_affine=False) for _ in range(n_layer)])
+        self.n_embed, self.seq_len = n_embed, seq_len
+        self.input_proj = nn.Linear(n_embed_input, n_embed, bias=bias)
+        self.final_layer = FinalLayerDit(n_embed, n_embed_input, bias, layernorm_eps)
+        self.config = DiTConfig(n_embed=n_embed, n_embed_input=n_embed_input, n_layer=n_layer, n_head=n_head, seq_len=seq_len,
+                                dropout=dropout, bias=bias, norm_layer=norm_layer, multiple_of=multiple_of,
+                                layernorm_eps=layernorm_eps, class_vocab_sizes=dict(class_vocab_sizes),
+                                cfg_dropout_prob=cfg_dropout_prob, condition_strategy=condition_strategy)
+        self._packed: PackedDiT | None = None
+        self._packed_key = None
+        self.initialize_weights()
+
+    # ---- initialisation with the reference's distributions (`nnets.py:458-492`) ----
+    def initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        self.pos_embed.data.copy_(torch.from_numpy(get_1d_sincos_pos_embed(self.n_embed, self.seq_len)).float().unsqueeze(0))
+        for emb in self.class_embeddings.values():
+            nn.init.normal_(emb.weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+        for block in self.blocks:  # adaLN-zero
+            nn.init.zeros_(block.adaln_modulation[-1].weight)
+            nn.init.zeros_(block.adaln_modulation[-1].bias)
+        for lin in (self.final_layer.adaln_modulation[-1], self.final_layer.linear):
+            nn.init.zeros_(lin.weight)
+            if lin.bias is not None:
+                nn.init.zeros_(lin.bias)
+
+    # ---- packed-weight cache ----
+    def packed(self) -> PackedDiT:
+        params = list(self.state_dict(keep_vars=True).values())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        dev = self.pos_embed.device
+        if dev.type != "cuda":
+            raise RuntimeError("scldm_b200.DiT runs on CUDA only (no CPU fallback): call .cuda() first")
+        if self._packed is None or self._packed_key != key:
+            self._packed = PackedDiT({k: v.detach() for k, v in self.state_dict().items()}, self.config, dev)
+            self._packed_key = key
+        return self._packed
+
+    # ---- label bookkeeping (host side, tiny int tensors) ----
+    def _null(self, name: str) -> int:
+        return self.class_vocab_sizes[name]
+
+    def _cls_rows(self, labels: dict[str, torch.Tensor], n: int, device) -> torch.Tensor:
+        """[n_class, n] embedding rows: given labels where present, the class's null token otherwise
+        (sum over *all* tables, reference `nnets.py:403-426, 447-456`)."""
+        names = sorted(self.class_vocab_sizes.keys())
+        rows = []
+        for name in names:
+            if name in labels:
+                rows.append(labels[name].to(device=device, dtype=torch.int32).reshape(n))
+            else:
+                rows.append(torch.full((n,), self._null(name), dtype=torch.int32, device=device))
+        if not rows:
+            return torch.zeros(0, n, dtype=torch.int32, device=device)
+        return torch.stack(rows)
+
+    def _active_labels(self, condition: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        """Which labels enter the embedding in eval mode (`nnets.py:389-456`): joint -> all given classes;
+        mutually_exclusive -> ONE class, picked with torch.randint when several are given (as the reference)."""
+        avail = [n for n in sorted(self.class_vocab_sizes.keys()) if n in condition]
+        if self.condition_strategy == "joint" or len(avail) <= 1:
+            return {n: condition[n] for n in avail}
+        pick = int(torch.randint(0, len(avail), ()).item())
+        return {avail[pick]: condition[avail[pick]]}
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, condition: dict[str, torch.Tensor], force_drop_ids: bool | None = None):
+        """`DiT.forward` (`nnets.py:273-297`), eval semantics (no CFG label dropout)."""
+        if force_drop_ids is None:
+            force_drop_ids = self.training
+        if force_drop_ids:
+            raise NotImplementedError("training-mode CFG label dropout: the training step is a later row (SURVEY.md §8f)")
+        packed = self.packed()
+        n = x.shape[0]
+        cls = self._cls_rows(self._active_labels(condition or {}), n, x.device)
+        plan = ops.DitPlan(packed, n_u=n, n_g=0, n_f=1, coef=[1.0], cls_idx=cls,
+                           slot_mod=torch.arange(n, dtype=torch.int32, device=x.device))
+        return ops.dit_forward(plan, x.contiguous().float(), t.float())
+
+    def cfg_layout(self, condition: dict[str, torch.Tensor] | None, cfg_scale: dict[str, float] | None, half: int, device,
+                   shared_time: bool) -> dict:
+        """Slot / conditioning-row layout of one `forward_with_cfg` evaluation (`nnets.py:336-378`); pure host
+        logic (runs on any device, see tests/test_host_logic.py).
+
+        states [0,half) are the unconditional first half (one slot each); states [half,2*half) are guided:
+        n_f = 1 + n_cond consecutive slots (unconditional pass, then one pass per guidance term) combined with
+        `coef`.  Returns n_f, coef, cls_idx [n_class, n_mod], slot_mod [n_slots] and t_index (which input row's
+        time every conditioning row uses; None when `shared_time`: all rows share t and 1 + half*n_cond rows suffice)."""
+        passes: list[dict[str, torch.Tensor]] = []
+        coef = [1.0]
+        if condition is not None and cfg_scale is not None:
+            second = {k: v[half:] for k, v in condition.items()}
+            if self.condition_strategy == "joint":
+                avg = sum(cfg_scale.values()) / len(cfg_scale)
+                passes, coef = [second], [1.0 - avg, avg]
+            else:
+                passes = [{name: second[name]} for name in cfg_scale]
+                coef = [1.0 - sum(cfg_scale.values())] + [float(s) for s in cfg_scale.values()]
+        n_f = 1 + len(passes)
+        null_rows = lambda n: self._cls_rows({}, n, device)  # noqa: E731
+        ar = torch.arange(half, dtype=torch.int32, device=device)
+        if shared_time:
+            # row 0 = unconditional; row 1 + j*n_c + k = guided cell j, conditional pass k
+            n_c = len(passes)
+            cls = [null_rows(1)] + ([torch.stack([self._cls_rows(p, half, device) for p in passes], 2).reshape(-1, half * n_c)] if n_c else [])
+            cls_idx = torch.cat(cls, 1)
+            slot_u = torch.zeros(half, dtype=torch.int32, device=device)
+            slot_g = torch.zeros(half, n_f, dtype=torch.int32, device=device)
+            for k in range(n_c):
+                slot_g[:, 1 + k] = 1 + ar * n_c + k
+            t_index = None
+        else:
+            # rows [0,half): unconditional first half; then per guided cell j: n_f rows (uncond, cond passes)
+            per = [null_rows(half)] + [self._cls_rows(p, half, device) for p in passes]  # each [n_class, half]
+            cls_g = torch.stack(per, 2).reshape(-1, half * n_f)
+            cls_idx = torch.cat([null_rows(half), cls_g], 1)
+            slot_u = ar
+            slot_g = half + ar[:, None] * n_f + torch.arange(n_f, dtype=torch.int32, device=device)[None, :]
+            t_index = torch.cat([ar, (half + ar).repeat_interleave(n_f)]).long()
+        slot_mod = torch.cat([slot_u, slot_g.reshape(-1)])
+        return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index)
+
+    def cfg_plan(self, condition, cfg_scale, half: int, device, shared_time: bool):
+        lay = self.cfg_layout(condition, cfg_scale, half, device, shared_time)
+        plan = ops.DitPlan(self.packed(), n_u=lay["n_u"], n_g=lay["n_g"], n_f=lay["n_f"], coef=lay["coef"],
+                           cls_idx=lay["cls_idx"], slot_mod=lay["slot_mod"])
+        return plan, lay["t_index"]
+
+    def forward_with_cfg(self, x: torch.Tensor, t: torch.Tensor, condition: dict[str, torch.Tensor] | None = None,
+                         cfg_scale: dict[str, float] | None = None) -> torch.Tensor:
+        """`DiT.forward_with_cfg` (`nnets.py:336-378`): rows [0,B) unconditional, rows [B,2B) guided; the
+        unconditional and conditional passes of every guided cell are batched in one launch sequence."""
+        half = x.shape[0] // 2
+        plan, t_index = self.cfg_plan(condition, cfg_scale, half, x.device, shared_time=False)
+        return ops.dit_forward(plan, x.contiguous().float(), t.float()[t_index])

@@ -1,0 +1,188 @@
+"""Thin torch-tensor wrappers over the C-ABI calls.  PyTorch supplies device memory and the
+current stream; all arithmetic happens in libscldm_b200.so.  No CPU path exists."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .pack import PackedDiT, PackedVAEDecoder
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"scldm_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"scldm_b200: `{name}` must be contiguous")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class DitPlan:
+    """Host-side description of one batched DiT evaluation (see `scldm_dit_plan` in the header).
+
+    n_u states are evaluated once, n_g states n_f times; `cls_idx` gives, for every conditioning row
+    and class table, the embedding row (null token = vocab size, reference `nnets.py:319,403-426`);
+    `slot_mod` maps every cell-forward slot to its conditioning row.
+    """
+
+    def __init__(self, packed: PackedDiT, n_u: int, n_g: int, n_f: int, coef, cls_idx: torch.Tensor, slot_mod: torch.Tensor):
+        lib = _lib.load()
+        dev = packed.device
+        s = _lib.DitPlan()
+        s.n_u, s.n_g, s.n_f = int(n_u), int(n_g), int(n_f)
+        coef = list(coef)
+        if len(coef) > _lib.MAX_COMBINE:
+            raise NotImplementedError(f"at most {_lib.MAX_COMBINE} evaluations per guided state")
+        for i in range(_lib.MAX_COMBINE):
+            s.coef[i] = float(coef[i]) if i < len(coef) else 0.0
+        n_class = len(packed.class_names)
+        n_mod = int(cls_idx.shape[1]) if n_class > 0 else int(slot_mod.max().item()) + 1
+        s.n_mod = n_mod
+        self.n_mod = n_mod
+        mod_pad = lib.scldm_dit_mod_pad(C.byref(s))
+        slots_pad = lib.scldm_dit_slots_pad(C.byref(s))
+        n_slots = n_u + n_g * (n_f if n_g > 0 else 1)
+        assert slot_mod.numel() == n_slots, (slot_mod.numel(), n_slots)
+        ci = torch.zeros(max(n_class, 1), mod_pad, dtype=torch.int32, device=dev)
+        if n_class > 0:
+            assert cls_idx.shape == (n_class, n_mod)
+            ci[:, :n_mod] = cls_idx.to(device=dev, dtype=torch.int32)
+            # padded conditioning rows use the null token of every class (valid table rows)
+            for c, name in enumerate(packed.class_names):
+                ci[c, n_mod:] = packed.cfg.class_vocab_sizes[name] if packed.cfg.cfg_dropout_prob > 0 else 0
+        sm = torch.zeros(slots_pad, dtype=torch.int32, device=dev)
+        sm[:n_slots] = slot_mod.to(device=dev, dtype=torch.int32)
+        self.cls_idx, self.slot_mod = ci.contiguous(), sm.contiguous()
+        s.cls_idx, s.slot_mod = self.cls_idx.data_ptr(), self.slot_mod.data_ptr()
+        self.struct = s
+        self.n_states = n_u + n_g
+        self.n_slots, self.slots_pad, self.mod_pad = n_slots, slots_pad, mod_pad
+        self.packed = packed
+
+    def workspace_bytes(self, n_evals: int) -> int:
+        return int(_lib.load().scldm_dit_workspace_bytes(C.byref(self.packed.struct), C.byref(self.struct), n_evals))
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
+    key = (str(device), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)  # zero-filled: padded slots stay finite
+        _ws_cache[key] = buf
+    return buf
+
+
+def dit_forward(plan: DitPlan, x: torch.Tensor, t_mod: torch.Tensor, workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """v = combine(DiT(x, t, cond)) for the states of `plan`.  x [n_states,16,16] fp32, t_mod [n_mod] fp32."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.shape == (plan.n_states, 16, 16), x.shape
+    tm = torch.zeros(plan.mod_pad, dtype=torch.float32, device=x.device)
+    tm[: plan.n_mod] = t_mod.to(torch.float32)
+    ws = workspace if workspace is not None else _workspace(x.device, plan.workspace_bytes(0), "dit")
+    v = torch.empty_like(x)
+    rc = lib.scldm_dit_forward(C.byref(plan.packed.struct), C.byref(plan.struct), x.data_ptr(), tm.data_ptr(), v.data_ptr(),
+                               ws.data_ptr(), ws.numel(), _stream_ptr(x.device))
+    _lib.check(rc, "scldm_dit_forward")
+    return v
+
+
+def dit_sample_ode(plan: DitPlan, x: torch.Tensor, t_grid: torch.Tensor, method: str = "euler",
+                   workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """Integrates x (in place) over the fixed time grid; returns x."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.shape == (plan.n_states, 16, 16), x.shape
+    if method not in _lib.ODE_METHODS:
+        raise NotImplementedError(f"ODE method '{method}': fixed-grid {sorted(_lib.ODE_METHODS)} are implemented on device")
+    grid = [float(v) for v in t_grid.detach().cpu().to(torch.float32).tolist()]
+    n_grid = len(grid)
+    stages = 1 if method == "euler" else 2
+    arr = (C.c_float * n_grid)(*grid)
+    ws = workspace if workspace is not None else _workspace(x.device, plan.workspace_bytes((n_grid - 1) * stages), "dit")
+    rc = lib.scldm_dit_sample_ode(C.byref(plan.packed.struct), C.byref(plan.struct), x.data_ptr(), arr, n_grid,
+                                  _lib.ODE_METHODS[method], ws.data_ptr(), ws.numel(), _stream_ptr(x.device))
+    _lib.check(rc, "scldm_dit_sample_ode")
+    return x
+
+
+def dit_workspace_views(plan: DitPlan, ws: torch.Tensor, n_evals: int = 0) -> dict:
+    """Test helper: typed views of the intermediates a call left in the workspace."""
+    lib = _lib.load()
+    offs = (C.c_size_t * 9)()
+    n = lib.scldm_dit_workspace_layout(C.byref(plan.packed.struct), C.byref(plan.struct), n_evals, offs, 9)
+    assert n == 9
+    base = (-ws.data_ptr()) % 1024
+    rows = plan.slots_pad * 16
+    w = plan.packed
+    names = ["X", "qkv", "ao", "hid", "mod", "cls", "temb", "acc", "tvals"]
+    o = {k: base + int(offs[i]) for i, k in enumerate(names)}
+
+    def view(off, nbytes, dtype, shape):
+        return ws[off: off + nbytes].view(dtype).view(*shape)
+
+    return {
+        "X": view(o["X"], rows * 256 * 4, torch.float32, (rows, 256)),
+        "qkv": view(o["qkv"], rows * 768 * 2, torch.bfloat16, (rows, 768)),
+        "ao": view(o["ao"], rows * 256 * 2, torch.bfloat16, (rows // 128, 4, 128 * 64)),
+        "hid": view(o["hid"], (rows // 128) * w.hid_slabs * 16384, torch.bfloat16, (rows // 128, w.hid_slabs, 128 * 64)),
+        "mod": view(o["mod"], plan.mod_pad * w.mod_stride * 4, torch.float32, (plan.mod_pad, w.mod_stride)),
+        "cls": view(o["cls"], plan.mod_pad * 256 * 4, torch.float32, (plan.mod_pad, 256)),
+        "temb": view(o["temb"], plan.mod_pad * 256 * 4, torch.float32, (plan.mod_pad, 256)),
+    }
+
+
+def vae_qside(packed: PackedVAEDecoder) -> torch.Tensor:
+    """Cell-invariant MCAB query projections for the whole vocabulary (cached on `packed`)."""
+    if packed.qp is None:
+        lib = _lib.load()
+        qp = torch.empty(packed.emb.shape[0], 32, dtype=torch.float32, device=packed.device)
+        rc = lib.scldm_vae_qside(C.byref(packed.struct), qp.data_ptr(), _stream_ptr(packed.device))
+        _lib.check(rc, "scldm_vae_qside")
+        packed.qp = qp
+    return packed.qp
+
+
+def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, lib_size: torch.Tensor, want_mu=True,
+               want_counts=False, seed: int = 0, cell_offset: int = 0):
+    """z [cells,16,16] fp32, genes [G] int64 (shared by all cells), lib_size [cells] fp32 ->
+    (mu [cells,G] | None, theta [G], counts [cells,G] | None)."""
+    lib = _lib.load()
+    _require_cuda(z, "z")
+    n_cells, G = z.shape[0], genes.numel()
+    assert z.dtype == torch.float32 and z.shape[1:] == (16, 16)
+    assert genes.dtype == torch.int64 and genes.is_cuda and genes.dim() == 1
+    assert int(lib_size.numel()) == n_cells
+    lib_size = lib_size.reshape(-1).to(torch.float32).contiguous()
+    qp = vae_qside(packed)
+    mu = torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_mu else None
+    counts = torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_counts else None
+    theta = torch.empty(G, dtype=torch.float32, device=z.device)
+    nbytes = int(lib.scldm_vae_decode_workspace_bytes(n_cells, G))
+    ws = _workspace(z.device, nbytes, "vae")
+    rc = lib.scldm_vae_decode(C.byref(packed.struct), qp.data_ptr(), z.data_ptr(), n_cells, genes.data_ptr(), G,
+                              lib_size.data_ptr(), mu.data_ptr() if mu is not None else None, theta.data_ptr(),
+                              counts.data_ptr() if counts is not None else None, seed & (2**64 - 1), cell_offset, ws.data_ptr(),
+                              ws.numel(), _stream_ptr(z.device))
+    _lib.check(rc, "scldm_vae_decode")
+    return mu, theta, counts
+
+
+def randn_cells(n_cells: int, per_cell: int, seed: int, cell_offset: int, stream_id: int, device) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(n_cells, per_cell, dtype=torch.float32, device=device)
+    rc = lib.scldm_randn_cells(out.data_ptr(), n_cells, per_cell, seed & (2**64 - 1), cell_offset, stream_id, _stream_ptr(device))
+    _lib.check(rc, "scldm_randn_cells")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().scldm_launch_count())

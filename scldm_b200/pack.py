@@ -1,0 +1,168 @@
+"""Weight packing: reference `state_dict` (fp32, nn.Linear (out,in) layout) -> device blobs the
+sm_100a kernels consume.
+
+bf16 GEMM operands are stored as UMMA-canonical K-major tiles with the 128-byte swizzle:
+a tile is [rows][64 bf16] (128 B per row); the 16-byte chunk c of row r lives at chunk position
+c ^ (r & 7).  One tile per (256-row N block, 64-wide K slab) is contiguous in memory, so a
+pipeline stage is a single 1-D bulk-TMA copy and `tcgen05.mma` reads it with
+SBO = 1024 B / SWIZZLE_128B descriptors (csrc/sm100.cuh).
+
+Everything here is plain torch indexing and runs on CPU too (tests/test_pack.py).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .config import DiTConfig, VAEConfig
+
+BLOCK_M, BLOCK_N, BLOCK_K = 128, 256, 64
+
+
+def _swizzle_rows(tile: torch.Tensor) -> torch.Tensor:
+    """tile [..., R, 64] -> same shape with 16-byte chunks XOR-swizzled by (row & 7)."""
+    R = tile.shape[-2]
+    t = tile.reshape(*tile.shape[:-1], 8, 8)  # [..., R, chunk, elem]
+    rows = torch.arange(R, device=tile.device)
+    idx = torch.arange(8, device=tile.device)[None, :] ^ (rows[:, None] & 7)  # out[r, p] = in[r, p ^ (r&7)]
+    idx = idx.view(*([1] * (t.dim() - 3)), R, 8, 1).expand(*t.shape)
+    return torch.gather(t, -2, idx).reshape(tile.shape)
+
+
+def pack_kmajor_tiles(w: torch.Tensor, block_rows: int) -> torch.Tensor:
+    """w [N, K] (K contiguous) -> bf16 [ceil(N/block_rows)][ceil(K/64)][block_rows*64], zero padded, swizzled."""
+    N, K = w.shape
+    nt, ks = -(-N // block_rows), -(-K // BLOCK_K)
+    wp = torch.zeros(nt * block_rows, ks * BLOCK_K, dtype=torch.bfloat16, device=w.device)
+    wp[:N, :K] = w.to(torch.bfloat16)
+    tiles = wp.view(nt, block_rows, ks, BLOCK_K).permute(0, 2, 1, 3).contiguous()  # [nt][ks][rows][64]
+    return _swizzle_rows(tiles).reshape(nt, ks, block_rows * BLOCK_K).contiguous()
+
+
+def unpack_kmajor_tiles(p: torch.Tensor, block_rows: int) -> torch.Tensor:
+    """inverse of `pack_kmajor_tiles` -> [nt*block_rows, ks*64] (the swizzle is an involution)."""
+    nt, ks, _ = p.shape
+    tiles = _swizzle_rows(p.view(nt, ks, block_rows, BLOCK_K))
+    return tiles.permute(0, 2, 1, 3).reshape(nt * block_rows, ks * BLOCK_K)
+
+
+class PackedDiT:
+    """Device-resident packed DiT weights + the ctypes struct handed to the C-ABI."""
+
+    def __init__(self, sd: dict, cfg: DiTConfig, device):
+        if cfg.n_embed != 256 or cfg.seq_len != 16 or cfg.n_embed_input != 16 or cfg.n_head != 8:
+            raise NotImplementedError(
+                f"sm_100a DiT kernels are specialised to n_embed=256, seq_len=16, n_embed_input=16, n_head=8; got {cfg}")
+        if len(cfg.class_vocab_sizes) > _lib.MAX_CLASSES:
+            raise NotImplementedError("too many class tables")
+        D, H, L = cfg.n_embed, cfg.hidden, cfg.n_layer
+        if H > 768:
+            raise NotImplementedError("hidden > 768")
+        self.cfg = cfg
+        self.class_names = sorted(cfg.class_vocab_sizes.keys())
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+        dev = lambda t: t.to(device).contiguous()  # noqa: E731
+
+        def get(name, shape=None):
+            t = sd.get(name)
+            if t is None:
+                return torch.zeros(shape, dtype=torch.float32)
+            return t.detach().float()
+
+        mod_w = [get(f"blocks.{i}.adaln_modulation.1.weight") for i in range(L)] + [get("final_layer.adaln_modulation.1.weight")]
+        mod_b = [get(f"blocks.{i}.adaln_modulation.1.bias", (6 * D,)) for i in range(L)] + [get("final_layer.adaln_modulation.1.bias", (2 * D,))]
+        self.w_mod = dev(pack_kmajor_tiles(torch.cat(mod_w, 0), BLOCK_N))
+        self.b_mod = f32(torch.cat(mod_b, 0))
+        self.mod_stride = L * 6 * D + 2 * D
+        self.w_qkv = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.attn.c_attn.weight"), BLOCK_N) for i in range(L)]))
+        self.b_qkv = f32(torch.stack([get(f"blocks.{i}.attn.c_attn.bias", (3 * D,)) for i in range(L)]))
+        self.w_proj = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.attn.c_proj.weight"), BLOCK_N) for i in range(L)]))
+        self.b_proj = f32(torch.stack([get(f"blocks.{i}.attn.c_proj.bias", (D,)) for i in range(L)]))
+        self.mlp1_tiles = -(-H // 128)
+        self.hid_slabs = -(-H // 64)
+        mlp1 = []
+        for i in range(L):
+            w1 = torch.zeros(self.mlp1_tiles * 128, D)
+            w2 = torch.zeros(self.mlp1_tiles * 128, D)
+            w1[:H] = get(f"blocks.{i}.mlp.w1.weight")
+            w2[:H] = get(f"blocks.{i}.mlp.w2.weight")
+            # N tile j = [w1 rows 128j..128j+127 | w2 rows 128j..128j+127] so SwiGLU pairs share an accumulator tile
+            inter = torch.stack([w1.view(self.mlp1_tiles, 128, D), w2.view(self.mlp1_tiles, 128, D)], 1).reshape(-1, D)
+            mlp1.append(pack_kmajor_tiles(inter, BLOCK_N))
+        self.w_mlp1 = dev(torch.stack(mlp1))
+        self.w_mlp2 = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.mlp.c_proj.weight"), BLOCK_N)[0] for i in range(L)]))
+        assert self.w_mlp2.shape[1] == self.hid_slabs
+        self.temb_w0t = f32(get("t_embedder.mlp.0.weight").T)
+        self.temb_b0 = f32(get("t_embedder.mlp.0.bias"))
+        self.temb_w2t = f32(get("t_embedder.mlp.2.weight").T)
+        self.temb_b2 = f32(get("t_embedder.mlp.2.bias"))
+        self.w_in = f32(get("input_proj.weight"))
+        self.b_in = f32(get("input_proj.bias", (D,)))
+        self.pos = f32(get("pos_embed").reshape(cfg.seq_len, D))
+        self.w_out = f32(get("final_layer.linear.weight"))
+        self.b_out = f32(get("final_layer.linear.bias", (cfg.n_embed_input,)))
+        self.class_tables = [f32(get(f"class_embeddings.{n}.weight")) for n in self.class_names]
+
+        s = _lib.DitWeights()
+        s.n_layer, s.hidden, s.hid_slabs, s.mlp1_tiles = L, H, self.hid_slabs, self.mlp1_tiles
+        s.mod_stride, s.n_class, s.eps = self.mod_stride, len(self.class_names), float(cfg.layernorm_eps)
+        for name in ("w_mod", "b_mod", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_mlp1", "w_mlp2", "temb_w0t", "temb_b0",
+                     "temb_w2t", "temb_b2", "w_in", "b_in", "pos", "w_out", "b_out"):
+            setattr(s, name, getattr(self, name).data_ptr())
+        for i, t in enumerate(self.class_tables):
+            s.class_tables[i] = t.data_ptr()
+        self.struct = s
+        self.device = torch.device(device)
+
+
+# offsets inside one packed VAE Block / the MCAB blob: must match csrc/vae_kernels.cuh
+VAE_HID = 88
+VAE_BLOCK_STRIDE = 128 + 32 * 96 + 32 * 32 + 2 * 32 * VAE_HID + VAE_HID * 32
+MCAB_TOTAL = 1024 + 64 + 3 * VAE_HID * 32 + 32 + 4
+
+
+class PackedVAEDecoder:
+    """Device-resident packed decoder (+ NB head + gene-embedding tables) and the cached Q-side table."""
+
+    def __init__(self, sd: dict, cfg: VAEConfig, device):
+        if (cfg.n_embed, cfg.n_embed_latent, cfg.n_inducing_points, cfg.n_head, cfg.n_head_cross, cfg.hidden) != (32, 16, 16, 8, 4, VAE_HID):
+            raise NotImplementedError(f"sm_100a VAE kernels are specialised to the shipped vae_base dims; got {cfg}")
+        if cfg.bias or cfg.use_adaln or not cfg.shared_embedding or not cfg.shared_theta:
+            raise NotImplementedError("decoder kernels cover bias=False, use_adaln=False, shared_embedding, shared_theta")
+        self.cfg = cfg
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+        g = lambda n: sd[n].detach().float()  # noqa: E731
+        self.win_t = f32(g("decoder.decoder_latent_input.1.weight").T)
+        blocks = []
+        for i in range(cfg.n_layer):
+            p = f"decoder.decoder_layers.{i}."
+            blocks.append(torch.cat([
+                g(p + "ln_1.weight"), g(p + "ln_1.bias"), g(p + "ln_2.weight"), g(p + "ln_2.bias"),
+                g(p + "attn.c_attn.weight").T.reshape(-1), g(p + "attn.c_proj.weight").T.reshape(-1),
+                g(p + "mlp.w1.weight").T.reshape(-1), g(p + "mlp.w2.weight").T.reshape(-1), g(p + "mlp.c_proj.weight").T.reshape(-1),
+            ]))
+            assert blocks[-1].numel() == VAE_BLOCK_STRIDE
+        self.blocks = f32(torch.stack(blocks))
+        c = "decoder.decoder_cross_attention."
+        self.ca_ln1_w, self.ca_ln1_b = f32(g(c + "ln_1.weight")), f32(g(c + "ln_1.bias"))
+        self.ca_wkv_t = f32(g(c + "attn.c_attn.weight").T)
+        self.ca_ln1q_w, self.ca_ln1q_b = f32(g(c + "ln_1q.weight")), f32(g(c + "ln_1q.bias"))
+        self.ca_wq = f32(g(c + "attn.c_attn_q.weight"))
+        blob = torch.cat([
+            g(c + "attn.c_proj.weight").reshape(-1), g(c + "ln_2.weight"), g(c + "ln_2.bias"),
+            g(c + "mlp.w1.weight").reshape(-1), g(c + "mlp.w2.weight").reshape(-1), g(c + "mlp.c_proj.weight").T.reshape(-1),
+            g("decoder_head.params.weight").reshape(-1), g("decoder_head.params.bias").reshape(-1), torch.zeros(3),
+        ])
+        assert blob.numel() == MCAB_TOTAL
+        self.mcab_blob = f32(blob)
+        self.emb = f32(g("input_layer.gene_embedding.weight"))
+        self.theta_tbl = f32(g("decoder_head.theta.weight").reshape(-1))
+        s = _lib.VaeDecWeights()
+        s.n_layer, s.n_ids, s.eps = cfg.n_layer, self.emb.shape[0], float(cfg.layernorm_eps)
+        for name in ("win_t", "blocks", "ca_ln1_w", "ca_ln1_b", "ca_wkv_t", "ca_ln1q_w", "ca_ln1q_b", "ca_wq", "mcab_blob", "emb",
+                     "theta_tbl"):
+            setattr(s, name, getattr(self, name).data_ptr())
+        self.struct = s
+        self.device = torch.device(device)
+        self.qp = None  # Q-side table, filled lazily by ops.vae_qside

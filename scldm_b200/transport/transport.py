@@ -1,0 +1,113 @@
+from __future__ import annotations
+
+import enum
+
+import torch
+
+from .. import ops
+
+
+class ModelType(enum.Enum):
+    NOISE = enum.auto()
+    SCORE = enum.auto()
+    VELOCITY = enum.auto()
+
+
+class PathType(enum.Enum):
+    LINEAR = enum.auto()
+    GVP = enum.auto()
+    VP = enum.auto()
+
+
+class WeightType(enum.Enum):
+    NONE = enum.auto()
+    VELOCITY = enum.auto()
+    LIKELIHOOD = enum.auto()
+
+
+class Transport:
+    """State of the flow (`transport.py:35-57`).  Only LINEAR + VELOCITY is on the generation path."""
+
+    def __init__(self, *, model_type, path_type, loss_type, train_eps, sample_eps):
+        if path_type is not PathType.LINEAR or model_type is not ModelType.VELOCITY:
+            raise NotImplementedError("scldm_b200 covers the Linear path with velocity prediction (ldm_base.yaml:29-35)")
+        self.model_type, self.path_type, self.loss_type = model_type, path_type, loss_type
+        self.train_eps, self.sample_eps = train_eps, sample_eps
+
+    def check_interval(self, train_eps, sample_eps, *, diffusion_form="SBDM", sde=False, reverse=False, eval=False,
+                       last_step_size=0.0):
+        """`Transport.check_interval` (`transport.py:69-95`) for the velocity/Linear ODE case: t0=0, t1=1."""
+        if sde:
+            raise NotImplementedError("SDE sampling is outside the hot path (SURVEY.md §8f rank 4)")
+        t0, t1 = 0, 1
+        if reverse:
+            t0, t1 = 1 - t0, 1 - t1
+        return t0, t1
+
+
+def create_transport(path_type="Linear", prediction="velocity", loss_weight=None, train_eps=None, sample_eps=None) -> Transport:
+    """`create_transport` (`transport/__init__.py:6-68`); velocity & Linear forces both eps to 0 (`:55-57`)."""
+    model_type = {"noise": ModelType.NOISE, "score": ModelType.SCORE}.get(prediction, ModelType.VELOCITY)
+    loss_type = {"velocity": WeightType.VELOCITY, "likelihood": WeightType.LIKELIHOOD}.get(loss_weight, WeightType.NONE)
+    ptype = {"Linear": PathType.LINEAR, "GVP": PathType.GVP, "VP": PathType.VP}[path_type]
+    return Transport(model_type=model_type, path_type=ptype, loss_type=loss_type, train_eps=0, sample_eps=0)
+
+
+class FusedCFGModel:
+    """Callable handed to the sampler in place of the reference's
+    `lambda x, t, **kw: dit.forward_with_cfg(x, t, **kw, cfg_scale=w)` (`models.py:809-811`).
+    Being a recognisable object (not an opaque lambda) lets `Sampler.sample_ode` run the whole
+    time loop inside one C-ABI call instead of a Python loop of model calls."""
+
+    def __init__(self, dit, cfg_scale: dict[str, float] | None):
+        self.dit, self.cfg_scale = dit, cfg_scale
+
+    def __call__(self, x, t, condition=None):
+        return self.dit.forward_with_cfg(x, t, condition=condition, cfg_scale=self.cfg_scale)
+
+
+class Sampler:
+    """`Sampler` (`transport.py:206-225, 324-369`): `sample_ode(...)` returns fn(x, model, **model_kwargs)."""
+
+    FIXED = ("euler", "heun2", "midpoint")
+
+    def __init__(self, transport: Transport):
+        self.transport = transport
+
+    def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-5, rtol=1e-5, reverse=False):
+        if reverse:
+            raise NotImplementedError("reverse-time ODE is outside the generation path")
+        method = sampling_method.lower()
+        if method not in self.FIXED:
+            raise NotImplementedError(
+                f"sampling_method='{sampling_method}': the device stepper implements the fixed-grid solvers {self.FIXED}; "
+                "the reference's default adaptive dopri5 is a later row (SURVEY.md §8f rank 4)")
+        t0, t1 = self.transport.check_interval(self.transport.train_eps, self.transport.sample_eps, sde=False, eval=True)
+        grid = torch.linspace(t0, t1, num_steps)  # `ode.__init__`, integrators.py:95
+
+        def sample(x, model, **model_kwargs):
+            """Returns the trajectory end points stacked as (2, ...): [x(t0), x(t1)] (the reference returns all
+            `num_steps` states but `LatentDiffusion.sample` only reads `[-1]`, `models.py:812`)."""
+            x0 = x.contiguous().float()
+            if isinstance(model, FusedCFGModel):
+                half = x0.shape[0] // 2
+                plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
+                xf = ops.dit_sample_ode(plan, x0.clone(), grid, method)
+                return torch.stack([x0, xf])
+            # generic callable: host-driven loop with the same fixed-grid formulas (slow path, still CUDA model calls)
+            xk = x0
+            for k in range(num_steps - 1):
+                ta, tb = grid[k].item(), grid[k + 1].item()
+                dt = torch.tensor(tb, dtype=torch.float32) - torch.tensor(ta, dtype=torch.float32)
+                dt = float(dt)
+                tv = lambda v: torch.full((xk.shape[0],), v, dtype=torch.float32, device=xk.device)  # noqa: E731
+                k1 = model(xk, tv(ta), **model_kwargs)
+                if method == "euler":
+                    xk = xk + dt * k1
+                elif method == "heun2":
+                    xk = xk + dt * 0.5 * (k1 + model(xk + dt * k1, tv(tb), **model_kwargs))
+                else:
+                    xk = xk + dt * model(xk + 0.5 * dt * k1, tv(ta + 0.5 * dt), **model_kwargs)
+            return torch.stack([x0, xk])
+
+        return sample

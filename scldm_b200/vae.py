@@ -1,0 +1,97 @@
+"""Drop-in for `scldm.vae.TransformerVAE` (`vae.py:15-87`): same constructor, same `state_dict`
+keys (`encoder.*`, `decoder.*`, `decoder_head.*`, `input_layer.*`), `.decode` runs the fused
+sm_100a decoder (latent blocks -> MCAB unpool -> NB head -> optional Gamma-Poisson draw)."""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import VAEConfig
+from .layers import InputTransformerVAE
+from .nnets import Decoder, Encoder
+from .pack import PackedVAEDecoder
+from .stochastic_layers import NegativeBinomial, NegativeBinomialTransformerLayer
+
+
+def shared_gene_vector(genes: torch.Tensor) -> torch.Tensor:
+    """The reference feeds `genes` as a (B,G) int64 tile of ONE row (`datamodule.py:689`).
+    The kernels take that row once; a batch with differing rows is rejected loudly."""
+    if genes.dim() == 1:
+        return genes.contiguous()
+    if genes.shape[0] > 1 and genes.stride(0) != 0 and not bool((genes == genes[0:1]).all()):
+        raise NotImplementedError("decode with per-cell gene orderings: only the tiled layout the reference's tokenizer emits is supported")
+    return genes[0].contiguous()
+
+
+class TransformerVAE(nn.Module):
+    def __init__(self, encoder: Encoder, decoder: Decoder, decoder_head: NegativeBinomialTransformerLayer,
+                 input_layer: InputTransformerVAE):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.decoder_head = decoder_head
+        self.input_layer = input_layer
+        self._packed_dec: PackedVAEDecoder | None = None
+        self._packed_key = None
+        self.sample_seed = 0
+        self.sample_offset = 0
+
+    @classmethod
+    def from_config(cls, cfg: VAEConfig) -> "TransformerVAE":
+        return cls(encoder=Encoder(**cfg.encoder_kwargs()), decoder=Decoder(**cfg.decoder_kwargs()),
+                   decoder_head=NegativeBinomialTransformerLayer(**cfg.head_kwargs()),
+                   input_layer=InputTransformerVAE(**cfg.input_kwargs()))
+
+    def config(self) -> VAEConfig:
+        d, e = self.decoder.hparams_, self.encoder.hparams_
+        return VAEConfig(n_genes=d["n_genes"], n_embed=d["n_embed"], n_embed_latent=d["n_embed_latent"],
+                         n_inducing_points=d["n_inducing_points"], n_layer=d["n_layer"], n_head=d["n_head"],
+                         n_head_cross=d["n_head_cross"], bias=d["bias"], multiple_of=d["multiple_of"],
+                         layernorm_eps=d["layernorm_eps"], positional_encoding=e["positional_encoding"],
+                         shared_embedding=d["shared_embedding"], use_adaln=d["use_adaln"],
+                         shared_theta=self.decoder_head.shared_theta)
+
+    def packed_decoder(self) -> PackedVAEDecoder:
+        sd = self.state_dict(keep_vars=True)
+        key = tuple((p.data_ptr(), p._version) for k, p in sd.items() if not k.startswith("encoder."))
+        dev = self.input_layer.gene_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("scldm_b200.TransformerVAE runs on CUDA only (no CPU fallback): call .cuda() first")
+        if self._packed_dec is None or self._packed_key != key:
+            self._packed_dec = PackedVAEDecoder({k: v.detach() for k, v in sd.items()}, self.config(), dev)
+            self._packed_key = key
+        return self._packed_dec
+
+    def decode(self, z: torch.Tensor, genes: torch.Tensor, library_size: torch.Tensor,
+               condition: dict[str, torch.Tensor] | None = None) -> NegativeBinomial:
+        """`TransformerVAE.decode` (`vae.py:71-87`) -> NB(mu, theta); `.sample()` draws counts on device."""
+        if condition is not None:
+            raise NotImplementedError("conditioned decoder (use_adaln=True) is not on the shipped path")
+        packed = self.packed_decoder()
+        gvec = shared_gene_vector(genes)
+        zc = z.contiguous().float()
+        mu, theta, _ = ops.vae_decode(packed, zc, gvec, library_size, want_mu=True, want_counts=False)
+        theta_full = theta.unsqueeze(0).expand(z.shape[0], -1)
+        seed, offset = self.sample_seed, self.sample_offset
+
+        def sampler():
+            _, _, counts = ops.vae_decode(packed, zc, gvec, library_size, want_mu=False, want_counts=True, seed=seed,
+                                          cell_offset=offset)
+            return counts
+
+        return NegativeBinomial(mu, theta_full, _sampler=sampler)
+
+    def decode_counts(self, z, genes, library_size, seed: int = 0, cell_offset: int = 0, want_mu: bool = False):
+        """Fast path of `decode(...).sample()` (`models.py:818-819`): one pass, counts only (+mu on request)."""
+        packed = self.packed_decoder()
+        mu, theta, counts = ops.vae_decode(packed, z.contiguous().float(), shared_gene_vector(genes), library_size,
+                                           want_mu=want_mu, want_counts=True, seed=seed, cell_offset=cell_offset)
+        return counts, mu, theta
+
+    def encode(self, counts, genes, counts_subset=None, genes_subset=None):
+        raise NotImplementedError("MCAB encode kernels are the next row of the scope table (SURVEY.md §8a row a20)")
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("VAE training forward is a later row (SURVEY.md §8f rank 3)")

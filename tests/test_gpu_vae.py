@@ -1,0 +1,170 @@
+"""GPU parity: fused VAE decoder (latent blocks -> MCAB -> NB head -> Gamma-Poisson) vs oracle / golden.
+
+The decoder kernels compute in fp32 throughout, so tolerances are tight:
+  mu: rel-L2 <= 1e-4 and |sum_g mu - library| / library <= 1e-4;  theta: rel <= 1e-5.
+Sampled counts: distributional agreement only (moments within Monte-Carlo error)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scldm_oracle as O
+from oracle.make_golden import WEIGHT_SEED, vae_inputs
+from scldm_b200 import synthetic
+from scldm_b200.config import DiTConfig, VAEConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def make_vae(cfg):
+    from scldm_b200.vae import TransformerVAE
+
+    vae = TransformerVAE.from_config(cfg)
+    sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
+    vae.load_state_dict(sd, strict=True)
+    return vae.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("name,G,B,S", [("vae_small", 1500, 3, 400), ("vae_dentate", 17002, 2, 600)])
+def test_decode_vs_golden(golden_dir, name, G, B, S):
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    cfg = VAEConfig(n_genes=G)
+    vae, sd = make_vae(cfg)
+    z, genes, lib, _, _ = vae_inputs(name, cfg, B, S)
+    nb = vae.decode(z.cuda(), genes.cuda(), lib.cuda())
+    e_mu, e_th = rel_l2(nb.mu, g["mu"]), rel_l2(nb.theta[0], g["theta"])
+    tot = (nb.mu.sum(1).cpu() / lib[:, 0] - 1).abs().max().item()
+    print(name, f"mu {e_mu:.2e} theta {e_th:.2e} |sum/lib-1| {tot:.2e}")
+    assert e_mu < 1e-4 and e_th < 1e-5 and tot < 1e-4
+    assert nb.mu.shape == (B, G) and nb.theta.shape == (B, G)
+
+
+def test_decode_many_cells_vs_oracle():
+    """cells_per_block > 1 path, ragged last gene tile (G=1000 is not a multiple of 128)."""
+    cfg = VAEConfig(n_genes=1000, n_layer=3)
+    vae, sd = make_vae(cfg)
+    B = 700
+    z = synthetic.randn("dm.z", (B, 16, 16))
+    lib = torch.exp(8.0 + 0.3 * synthetic.randn("dm.lib", (B, 1)))
+    genes = torch.arange(1, 1001).unsqueeze(0).expand(B, -1)
+    nb = vae.decode(z.cuda(), genes.cuda(), lib.cuda())
+    with torch.no_grad():
+        mu, theta = O.vae_decode(z, genes, lib, sd, cfg)
+    assert rel_l2(nb.mu, mu) < 1e-4
+    assert rel_l2(nb.theta, theta) < 1e-5
+
+
+def test_decode_gene_subset_and_order():
+    """gene ids are looked up, not assumed to be arange: a shuffled subset gives the matching columns' logits."""
+    cfg = VAEConfig(n_genes=600, n_layer=2)
+    vae, sd = make_vae(cfg)
+    B = 5
+    z = synthetic.randn("gs.z", (B, 16, 16))
+    lib = torch.full((B, 1), 1000.0)
+    perm = torch.randperm(600, generator=torch.Generator().manual_seed(5))[:333] + 1
+    genes = perm.unsqueeze(0).repeat(B, 1)
+    nb = vae.decode(z.cuda(), genes.cuda(), lib.cuda())
+    with torch.no_grad():
+        mu, theta = O.vae_decode(z, genes, lib, sd, cfg)
+    assert rel_l2(nb.mu, mu) < 1e-4 and rel_l2(nb.theta, theta) < 1e-5
+
+
+def test_nb_sampling_moments():
+    """counts ~ NB(mu, theta): per-gene mean and variance over many cells sharing one latent."""
+    cfg = VAEConfig(n_genes=256, n_layer=1)
+    vae, sd = make_vae(cfg)
+    B = 20000
+    z = synthetic.randn("nb.z", (1, 16, 16)).expand(B, -1, -1).contiguous()
+    lib = torch.full((B,), 3000.0)
+    genes = torch.arange(1, 257)
+    counts, mu, theta = vae.decode_counts(z.cuda(), genes.cuda(), lib.cuda(), seed=11, cell_offset=0, want_mu=True)
+    counts, mu, theta = counts.cpu().double(), mu[0].cpu().double(), theta.cpu().double()
+    assert bool((counts >= 0).all()) and bool((counts == counts.round()).all())
+    m, v = counts.mean(0), counts.var(0)
+    exp_v = mu + mu**2 / theta
+    # standard error of the mean ~ sqrt(var/B); allow 5 sigma, plus 8% on the variance
+    assert bool(((m - mu).abs() <= 5 * (exp_v / B).sqrt() + 1e-3).all()), float(((m - mu).abs() / (exp_v / B).sqrt()).max())
+    big = mu > 0.5
+    assert float(((v[big] - exp_v[big]).abs() / exp_v[big]).median()) < 0.05
+    assert float(((v[big] - exp_v[big]).abs() / exp_v[big]).max()) < 0.35
+    # zero fraction for the NB: (theta/(theta+mu))^theta
+    p0 = (theta / (theta + mu)) ** theta
+    z0 = (counts == 0).double().mean(0)
+    assert float((z0 - p0).abs().max()) < 0.02
+    # determinism + offset sensitivity
+    c2, _, _ = vae.decode_counts(z.cuda(), genes.cuda(), lib.cuda(), seed=11, cell_offset=0)
+    c3, _, _ = vae.decode_counts(z.cuda(), genes.cuda(), lib.cuda(), seed=11, cell_offset=B)
+    assert torch.equal(c2.cpu().double(), counts) and not torch.equal(c3.cpu().double(), counts)
+
+
+def test_randn_cells_statistics_and_sharding_invariance():
+    from scldm_b200 import ops
+
+    a = ops.randn_cells(4096, 256, seed=5, cell_offset=0, stream_id=1, device="cuda")
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1) < 5e-3
+    b = ops.randn_cells(1024, 256, seed=5, cell_offset=1024, stream_id=1, device="cuda")
+    assert torch.equal(a[1024:2048], b)  # keyed by global cell index
+
+
+def test_full_sample_vs_golden(golden_dir):
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    g = dict(np.load(os.path.join(golden_dir, "sample_me1.npz")))
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14})
+    vcfg = VAEConfig(n_genes=1500)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
+    vae, _ = make_vae(vcfg)
+    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), sampling_method="euler", num_steps=50)
+    B = 2
+    genes = torch.arange(1, vcfg.n_genes + 1).unsqueeze(0).repeat(B, 1).cuda()
+    counts, z, mu = ldm.sample({"clusters": torch.from_numpy(g["label"]).cuda()}, {"clusters": 2.0}, B, genes,
+                               z0=torch.from_numpy(g["z0"]).cuda(), log_size_factors=torch.from_numpy(g["log_size_factors"]).cuda(),
+                               return_mu=True)
+    e_z, e_mu = rel_l2(z, g["z_final"]), rel_l2(mu, g["mu"])
+    print(f"sample: z {e_z:.2e} mu {e_mu:.2e}")
+    assert e_z < 3e-2 and e_mu < 6e-2
+    assert counts.shape == (2 * B, vcfg.n_genes) and z.shape == (2 * B, 16, 16)
+    lib = torch.exp(torch.from_numpy(g["log_size_factors"]))
+    assert torch.allclose(mu.sum(1).cpu(), torch.cat([lib, lib]), rtol=1e-4)
+
+
+def test_sample_rng_path_and_size_factors():
+    """device-drawn noise / size factors: shapes, determinism under a fixed seed, class-dependent library size."""
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=1)
+    vcfg = VAEConfig(n_genes=500, n_layer=1)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
+    vae, _ = make_vae(vcfg)
+    mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes)
+    B = 64
+    lab = {"clusters": synthetic.randint("rp.lab", 14, (B,)).cuda()}
+    genes = torch.arange(1, 501).unsqueeze(0).repeat(B, 1).cuda()
+    outs = []
+    for _ in range(2):
+        ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t,
+                              sd_size_factor=sd_t, num_steps=5, seed=3, cell_chunk=24)
+        outs.append(ldm.sample(lab, {"clusters": 1.0}, B, genes, return_mu=True))
+    (c1, z1, m1), (c2, z2, m2) = outs
+    assert torch.equal(c1, c2) and torch.equal(z1, z2)
+    lib = m1.sum(1)[:B].log().cpu()
+    want = torch.tensor([mu_t["clusters"][int(c)] for c in lab["clusters"].cpu()])
+    assert float((lib - want).abs().max()) < 6 * 0.5  # within 6 sd of the class mean
+    # chunking invariance: one big chunk gives the same cells
+    ldm = LatentDiffusion(vae, dit, create_transport("Linear", "velocity"), mu_size_factor=mu_t, sd_size_factor=sd_t,
+                          num_steps=5, seed=3, cell_chunk=4096)
+    c3, z3, _ = ldm.sample(lab, {"clusters": 1.0}, B, genes, return_mu=True)
+    assert torch.equal(z3, z1) and torch.equal(c3, c1)

@@ -1,0 +1,174 @@
+"""CPU tests of the host side: weight packing layout, CFG slot layout semantics, state_dict contract of the
+drop-in modules, the C-ABI library (loads, exports every declared symbol), error behaviour without CUDA."""
+
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import scldm_oracle as O
+from oracle.make_golden import WEIGHT_SEED, dit_inputs, golden_cases
+from scldm_b200 import _lib, pack, synthetic
+from scldm_b200.config import DiTConfig, VAEConfig, swiglu_hidden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_swiglu_hidden():
+    assert swiglu_hidden(256, 4) == 684 and swiglu_hidden(32, 4) == 88  # layers.py:165-167
+
+
+def test_pack_roundtrip_and_swizzle_positions():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(700, 300, generator=g)
+    p = pack.pack_kmajor_tiles(w, 256)
+    assert p.shape == (3, 5, 256 * 64) and p.dtype == torch.bfloat16
+    back = pack.unpack_kmajor_tiles(p, 256)
+    assert torch.equal(back[:700, :300], w.to(torch.bfloat16))
+    assert float(back[700:].abs().max()) == 0 and float(back[:, 300:].abs().max()) == 0
+    # explicit address check of the 128B swizzle: element (r, c) of tile (nt, ks) sits at
+    # r*64 + ((c//8) ^ (r&7))*8 + c%8   (elements; csrc/sm100.cuh swz_chunk_offset)
+    for (r, c) in [(0, 0), (1, 0), (7, 63), (9, 17), (255, 8), (130, 40)]:
+        nt, ks = 1, 2
+        off = r * 64 + (((c // 8) ^ (r & 7)) * 8) + c % 8
+        assert p[nt, ks, off] == w[nt * 256 + r, ks * 64 + c].to(torch.bfloat16)
+
+
+def test_dit_pack_layout_cpu():
+    """PackedDiT arranges [w1|w2] tiles and the stacked adaLN matrix as the kernels index them."""
+    cfg = DiTConfig(class_vocab_sizes={"a": 3}, n_layer=2)
+    sd = synthetic.dit_state_dict(cfg, 1)
+    pk = pack.PackedDiT(sd, cfg, "cpu")
+    assert pk.mod_stride == 2 * 1536 + 512 and pk.hid_slabs == 11 and pk.mlp1_tiles == 6
+    mod = pack.unpack_kmajor_tiles(pk.w_mod, 256)
+    assert torch.equal(mod[1536:3072], sd["blocks.1.adaln_modulation.1.weight"].to(torch.bfloat16))
+    assert torch.equal(mod[3072:3584], sd["final_layer.adaln_modulation.1.weight"].to(torch.bfloat16))
+    m1 = pack.unpack_kmajor_tiles(pk.w_mlp1[1], 256)  # layer 1: [6*256, 256]
+    assert torch.equal(m1[256:256 + 128], sd["blocks.1.mlp.w1.weight"][128:256].to(torch.bfloat16))
+    assert torch.equal(m1[256 + 128:512], sd["blocks.1.mlp.w2.weight"][128:256].to(torch.bfloat16))
+    assert torch.equal(m1[5 * 256:5 * 256 + 44], sd["blocks.1.mlp.w1.weight"][640:684].to(torch.bfloat16))
+    assert float(m1[5 * 256 + 44:5 * 256 + 128].abs().max()) == 0
+    m2 = pack.unpack_kmajor_tiles(pk.w_mlp2[0].unsqueeze(0), 256)
+    assert torch.equal(m2[:, :684], sd["blocks.0.mlp.c_proj.weight"].to(torch.bfloat16))
+
+
+def test_vae_pack_layout_cpu():
+    cfg = VAEConfig(n_genes=50, n_layer=2)
+    sd = synthetic.vae_state_dict(cfg, 1)
+    pk = pack.PackedVAEDecoder(sd, cfg, "cpu")
+    assert pk.blocks.shape == (2, pack.VAE_BLOCK_STRIDE) and pk.mcab_blob.numel() == pack.MCAB_TOTAL
+    b = pk.blocks[1]
+    assert torch.equal(b[128:128 + 32 * 96].view(32, 96), sd["decoder.decoder_layers.1.attn.c_attn.weight"].T)
+    assert torch.equal(pk.mcab_blob[1088:1088 + 88 * 32].view(88, 32), sd["decoder.decoder_cross_attention.mlp.w1.weight"])
+    # constants duplicated in csrc/vae_kernels.cuh
+    src = open(os.path.join(ROOT, "scldm_b200", "csrc", "vae_kernels.cuh")).read()
+    assert "MW_LN2W = 1024" in src and "BLK_WQKV = 128" in src and "HID = 88" in src
+
+
+def test_drop_in_state_dict_contract(golden_dir):
+    """the drop-in modules expose exactly the reference's state_dict keys/shapes and load them strictly."""
+    from scldm_b200.nnets import DiT
+    from scldm_b200.vae import TransformerVAE
+
+    keys = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
+    for name, case in golden_cases().items():
+        m = DiT(**case["cfg"].kwargs())
+        assert {k: list(v.shape) for k, v in m.state_dict().items()} == keys[name]
+        m.load_state_dict(synthetic.dit_state_dict(case["cfg"], WEIGHT_SEED), strict=True)
+    for name, G in (("vae_small", 1500), ("vae_dentate", 17002)):
+        cfg = VAEConfig(n_genes=G)
+        v = TransformerVAE.from_config(cfg)
+        assert {k: list(t.shape) for k, t in v.state_dict().items()} == keys[name]
+        v.load_state_dict(synthetic.vae_state_dict(cfg, WEIGHT_SEED), strict=True)
+        assert v.config() == cfg
+
+
+def test_fresh_dit_init_matches_reference_scheme():
+    """adaLN-zero + zero final layer (nnets.py:480-492), sincos pos_embed (sin first)."""
+    from scldm_b200.nnets import DiT
+
+    m = DiT(**DiTConfig(class_vocab_sizes={"c": 4}, n_layer=2).kwargs())
+    assert float(m.blocks[1].adaln_modulation[1].weight.abs().max()) == 0
+    assert float(m.final_layer.linear.weight.abs().max()) == 0
+    assert torch.allclose(m.pos_embed[0], torch.from_numpy(synthetic.sincos_pos_embed(256, 16)))
+    assert m.class_embeddings["c"].weight.shape == (5, 256)
+
+
+@pytest.mark.parametrize("name", list(golden_cases().keys()))
+@pytest.mark.parametrize("shared_time", [False, True])
+def test_cfg_layout_reproduces_forward_with_cfg(golden_dir, name, shared_time):
+    """Evaluate every slot of the batched CFG layout with the ORACLE's plain forward and combine with `coef`:
+    must equal the oracle's (= the reference's) forward_with_cfg.  Pins the host-side batching logic."""
+    from scldm_b200.nnets import DiT
+
+    case = golden_cases()[name]
+    cfg, B = case["cfg"], case["B"]
+    sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    x, t, labels = dit_inputs(name, cfg, B)
+    if shared_time:
+        t = torch.full_like(t, 0.3)
+    m = DiT(**cfg.kwargs())
+    lay = m.cfg_layout(labels, case["scales"], B, "cpu", shared_time)
+    names = sorted(cfg.class_vocab_sizes)
+    n_f, coef = lay["n_f"], lay["coef"]
+    assert lay["slot_mod"].numel() == B + B * n_f
+
+    def run_slot(state_row, mod_row):
+        # labels of this conditioning row; a null index (== vocab) means "class absent" for the oracle
+        lab = {}
+        for ci, cname in enumerate(names):
+            idx = int(lay["cls_idx"][ci, mod_row])
+            if idx != cfg.class_vocab_sizes[cname]:
+                lab[cname] = torch.tensor([idx])
+        tt = t[state_row:state_row + 1] if lay["t_index"] is None else t[lay["t_index"][mod_row]].reshape(1)
+        return O.dit_forward(x[state_row:state_row + 1], tt, lab, sd, cfg)[0]
+
+    with torch.no_grad():
+        ref = O.dit_forward_with_cfg(x, t, labels, case["scales"], sd, cfg)
+        for s in (0, B - 1):  # unguided states
+            out = run_slot(s, int(lay["slot_mod"][s]))
+            assert torch.allclose(out, ref[s], atol=2e-5, rtol=1e-4)
+        for j in (0, B - 1):  # guided states
+            acc = 0
+            for k in range(n_f):
+                acc = acc + coef[k] * run_slot(B + j, int(lay["slot_mod"][B + j * n_f + k]))
+            assert torch.allclose(acc, ref[B + j], atol=5e-5, rtol=1e-3)
+
+
+def test_abi_library_loads_and_exports_declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "scldm_b200.h")).read()
+    declared = set(re.findall(r"\b(scldm_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"scldm_b200"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert b"sm_100a" in lib.scldm_version()
+    assert lib.scldm_vae_decode_workspace_bytes(4, 1000) > 4 * 1000 * 4
+    # ctypes struct sizes match the C structs (8-byte pointers, natural alignment)
+    assert ctypes.sizeof(_lib.DitWeights) == 7 * 4 + 4 + 17 * 8 + 8 * 8
+    assert ctypes.sizeof(_lib.DitPlan) == 3 * 4 + 8 * 4 + 4 + 2 * 8
+
+
+def test_no_cpu_fallback():
+    """the product path fails loudly without CUDA instead of computing on the CPU."""
+    from scldm_b200.nnets import DiT
+
+    cfg = DiTConfig(class_vocab_sizes={"c": 4}, n_layer=1)
+    m = DiT(**cfg.kwargs()).eval()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            m(torch.zeros(2, 16, 16), torch.zeros(2), {"c": torch.zeros(2, dtype=torch.long)})
+    with pytest.raises(RuntimeError, match="weight container"):
+        m.blocks[0](torch.zeros(1, 16, 256))
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "scldm_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("with the oracle", ""), f
