@@ -68,7 +68,7 @@ class PackedDiT:
             t = sd.get(name)
             if t is None:
                 return torch.zeros(shape, dtype=torch.float32)
-            return t.detach().float()
+            return t.detach().float().cpu()  # pack on the host once, then upload
 
         mod_w = [get(f"blocks.{i}.adaln_modulation.1.weight") for i in range(L)] + [get("final_layer.adaln_modulation.1.weight")]
         mod_b = [get(f"blocks.{i}.adaln_modulation.1.bias", (6 * D,)) for i in range(L)] + [get("final_layer.adaln_modulation.1.bias", (2 * D,))]
@@ -132,7 +132,7 @@ class PackedVAEDecoder:
             raise NotImplementedError("decoder kernels cover bias=False, use_adaln=False, shared_embedding, shared_theta")
         self.cfg = cfg
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
-        g = lambda n: sd[n].detach().float()  # noqa: E731
+        g = lambda n: sd[n].detach().float().cpu()  # noqa: E731  (pack on the host once, then upload)
         self.win_t = f32(g("decoder.decoder_latent_input.1.weight").T)
         blocks = []
         for i in range(cfg.n_layer):
