@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the scLDM generation hot path: generated cells/sec (ODE steps + CFG + VAE decode).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one `LatentDiffusion.sample()` call for B cells per GPU on the dentate_gyrus-shaped model
+(BASELINE.json configs[1]): device-side size factors + noise -> 49-eval Euler ODE with classifier-free
+guidance (3 DiT forwards per cell and eval, batched) -> fused VAE decode -> NB sampling; it returns 2B
+generated rows (B unconditional + B guided), which is what `value` counts.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "generated cells/sec (ODE steps + CFG + VAE decode)"
+DATASET = "dentate_gyrus"
+NUM_STEPS = 50  # grid points => 49 Euler steps
+GUIDANCE = 2.0
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        d["source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def build_models(device, dataset=DATASET, seed=1234):
+    from scldm_b200 import synthetic
+    from scldm_b200.config import dataset_configs
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+    from scldm_b200.vae import TransformerVAE
+
+    dcfg, vcfg = dataset_configs(dataset)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, seed))
+    vae = TransformerVAE.from_config(vcfg)
+    vae.load_state_dict(synthetic.vae_state_dict(vcfg, seed))
+    mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes, seed)
+    ldm = LatentDiffusion(vae.to(device).eval(), dit.to(device).eval(), create_transport("Linear", "velocity", "velocity"),
+                          mu_size_factor=mu_t, sd_size_factor=sd_t, sampling_method="euler", num_steps=NUM_STEPS, seed=4321)
+    return ldm, dcfg, vcfg
+
+
+def algorithmic_flops_per_row(G: int) -> dict:
+    """DiT forward 210.8 MFLOP/cell; 49 evals; CFG => 1.5 forwards per output row; decode 2.2M + G*23104."""
+    D, H, M, L, N = 256, 684, 16, 16, 8
+    dit = M * (N * (8 * D * D + 6 * D * H + 4 * M * D) + 4 * L * D) + N * 12 * D * D + 4 * D * D + 2 * (256 * D + D * D)
+    dec = 2.2e6 + G * 23104
+    return {"dit_forward": dit, "decode": dec, "row_cfg": 1.5 * 49 * dit + dec}
+
+
+# per-launch algorithmic FLOPs of the GEMM kernel classes (rows = slots*16 actual, unpadded N/K)
+def kernel_flops(name: str, rows: int, mod_rows: int) -> float | None:
+    D, H = 256, 684
+    return {
+        "gemm_ares<LN,QKV>": 2.0 * rows * D * 3 * D,
+        "gemm_astream<proj>": 2.0 * rows * D * D,
+        "gemm_ares<LN,SWIGLU>": 2.0 * rows * D * 2 * H,
+        "gemm_astream<mlp2>": 2.0 * rows * H * D,
+        "gemm_ares<COND,MOD>": 2.0 * mod_rows * D * (8 * 6 * D + 2 * D),
+        "attn16": 4.0 * rows * 16 * D,
+    }.get(name)
+
+
+def cpu_sample(B: int, dcfg, vcfg, threads: int):
+    """The reference's CPU path (oracle restatement of the reference modules), fp32, `threads` host threads."""
+    from oracle import scldm_oracle as O
+    from scldm_b200 import synthetic
+
+    torch.set_num_threads(threads)
+    dsd, vsd = synthetic.dit_state_dict(dcfg, 1234), synthetic.vae_state_dict(vcfg, 1234)
+    z0 = synthetic.randn("cpu.z0", (B, 16, 16))
+    lab = {k: synthetic.randint("cpu.lab." + k, v, (B,)) for k, v in dcfg.class_vocab_sizes.items()}
+    w = {k: GUIDANCE for k in dcfg.class_vocab_sizes}
+    lsf = 8.0 + 0.3 * synthetic.randn("cpu.lsf", (B,))
+    genes = torch.arange(1, vcfg.n_genes + 1).unsqueeze(0).expand(B, -1)
+
+    def step():
+        with torch.no_grad():
+            mu, theta, z = O.latent_diffusion_sample(z0, lab, w, genes, lsf, dsd, dcfg, vsd, vcfg, num_steps=NUM_STEPS, method="euler")
+            return O.nb_sample(mu, theta)
+
+    return step
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle port; the
+    reference tree itself does not exist on the GPU box).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from scldm_b200.config import dataset_configs
+
+    dcfg, vcfg = dataset_configs(DATASET)
+    threads = os.cpu_count() or 1
+    B = args.ref_batch
+    step = cpu_sample(B, dcfg, vcfg, threads)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = 2 * B * args.steps / dt
+    line = {
+        "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"{DATASET}-shaped generation with CFG: G=17002, 49-eval Euler, guidance {GUIDANCE}",
+                   "cells_per_step": B, "rows_per_step": 2 * B, "note": "bounded sample of the GPU arm's workload; CPU only"},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} x sample() of {B} cells (2B={2 * B} rows), oracle port of the reference modules"},
+        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=2048, help="cells per step per GPU (2x rows are generated)")
+    ap.add_argument("--chunk", type=int, default=0, help="cells per ODE chunk (0 = library default)")
+    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prof", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (scldm_b200 has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    from scldm_b200 import ops
+
+    ldm, dcfg, vcfg = build_models(device)
+    if args.chunk > 0:
+        ldm.cell_chunk = args.chunk
+    B, G = args.batch, vcfg.n_genes
+    gw = {k: GUIDANCE for k in dcfg.class_vocab_sizes}
+    gen = torch.Generator().manual_seed(100 + rank)
+    labels_h = {k: torch.randint(0, v, (B,), generator=gen).pin_memory() for k, v in dcfg.class_vocab_sizes.items()}
+    genes_row_h = torch.arange(1, G + 1, dtype=torch.int64).pin_memory()
+    labels_d = {k: v.to(device) for k, v in labels_h.items()}
+    genes_d = genes_row_h.to(device).unsqueeze(0).expand(B, -1)  # (B,G) view of one row, as the tokenizer tiles it
+    counts_h = torch.empty(2 * B, G, dtype=torch.float32).pin_memory()
+    z_h = torch.empty(2 * B, 16, 16, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return ldm.sample(labels_d, gw, B, genes_d)
+
+    def step_e2e():
+        lab = {k: v.to(device, non_blocking=True) for k, v in labels_h.items()}
+        genes = genes_row_h.to(device, non_blocking=True).unsqueeze(0).expand(B, -1)
+        counts, z = ldm.sample(lab, gw, B, genes)
+        counts_h.copy_(counts, non_blocking=True)
+        z_h.copy_(z, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return counts_h, z_h
+
+    def timed(fn, steps):
+        """device time of `steps` calls (CUDA events per step on the launching stream, L2 flushed between steps)."""
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            total += a.elapsed_time(b)
+        return total  # ms
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = ops.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = None
+    if not args.no_e2e:
+        step_e2e()
+        barrier()
+        e2e_ms = timed(step_e2e, args.steps)
+        barrier()
+    t = torch.tensor([ms, e2e_ms or 0.0], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms_max = float(t[0]), float(t[1])
+    rows_per_step = 2 * B * world
+    value = rows_per_step * args.steps / (ms / 1e3)
+
+    # ---- live per-kernel timing (CUDA events around every launch) for the roofline of the dominant kernel ----
+    roofline, breakdown = None, None
+    peaks = measured_peaks()
+    if rank == 0 and not args.no_prof:
+        ops.prof_enable(True, device)
+        step_device()
+        prof = ops.prof_summary()
+        ops.prof_enable(False, device)
+        tot = sum(v[1] for v in prof.values())
+        breakdown = {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot, 4)} for k, v in
+                     sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        chunk = min(ldm.cell_chunk, B)
+        rows = 3 * chunk * 16  # slots of a full chunk x 16 tokens (CFG: 3 forwards per cell)
+        gemm = {k: v for k, v in prof.items() if k.startswith("gemm_")}
+        top = max(gemm.items(), key=lambda kv: kv[1][1])
+        name, (cnt, tms) = top
+        fl = kernel_flops(name, rows, 1 + chunk)
+        ach = fl / (tms / cnt * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "kernel": name, "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                    "avg_launch_us": round(1e3 * tms / cnt, 2), "flops_per_launch": fl}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        stepc = cpu_sample(args.cpu_batch, dcfg, vcfg, threads)
+        t0 = time.perf_counter()
+        stepc()
+        dtc = time.perf_counter() - t0
+        cpu_baseline = {"value": 2 * args.cpu_batch / dtc, "unit": "cells/s", "cores": threads, "kind": "port",
+                        "sample": f"1 x sample() of {args.cpu_batch} cells ({2 * args.cpu_batch} rows): same model, 49-eval Euler + CFG + decode + NB draw, fp32 oracle port",
+                        "seconds": round(dtc, 2)}
+
+    if rank == 0:
+        fl = algorithmic_flops_per_row(G)
+        line = {
+            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{DATASET}-shaped generation with CFG (BASELINE configs[1]): G={G}, 14 clusters, "
+                                   f"sample_ode('euler', num_steps=50) = 49 evals, guidance {GUIDANCE}, decode + NB draw",
+                       "cells_per_step_per_gpu": B, "rows_per_step": rows_per_step, "ode_chunk_cells": min(ldm.cell_chunk, B),
+                       "l2": "256 MB flush buffer written between timed steps", "parallelism": f"cells sharded over {world} GPU(s), no collective",
+                       "algorithmic_gflop_per_row": round(fl["row_cfg"] / 1e9, 3)},
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "model_tflops": round(value * fl["row_cfg"] / 1e12, 1),
+        }
+        if e2e_ms is not None:
+            h2d = sum(v.numel() * v.element_size() for v in labels_h.values()) + genes_row_h.numel() * 8
+            d2h = counts_h.numel() * 4 + z_h.numel() * 4
+            line["e2e"] = {"value": rows_per_step * args.steps / (e2e_ms_max / 1e3), "unit": "cells/s", "h2d_bytes_per_step": h2d,
+                           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps}
+        if roofline:
+            line["roofline"] = roofline
+            line["kernel_breakdown"] = breakdown
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

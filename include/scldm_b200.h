@@ -135,6 +135,12 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const floa
 int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t seed, int64_t cell_offset,
                       uint32_t stream_id, void* stream);
 
+/* Live per-kernel timing for bench.py: when enabled every launch is bracketed by CUDA events recorded on
+ * `stream` (must be the stream the calls run on; disables CUDA-graph capturability while on).
+ * scldm_prof_summary synchronises the device and writes "name count total_ms\n" lines.            */
+void scldm_prof_enable(int32_t on, void* stream);
+int32_t scldm_prof_summary(char* buf, int32_t cap);
+
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 uint64_t scldm_launch_count(void);
 const char* scldm_last_error(void);

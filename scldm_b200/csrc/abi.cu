@@ -3,6 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <string>
+#include <vector>
 
 #include "../../include/scldm_b200.h"
 #include "dit_kernels.cuh"
@@ -27,8 +30,35 @@ int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(SCLDM_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
-#define LAUNCH_CHECK(name)                                                                     \
+// ---- optional live per-kernel timing (CUDA events on the launching stream; not graph-capturable) ----
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;
+bool g_prof_on = false;
+cudaStream_t g_prof_stream = nullptr;
+
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+inline void prof_begin(const char* name) {
+  if (!g_prof_on) return;
+  ProfRec r{name, prof_event(), prof_event()};
+  cudaEventRecord(r.a, g_prof_stream);
+  g_prof.push_back(r);
+}
+inline void prof_end() {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, g_prof_stream);
+}
+
+#define LAUNCH(name, ...)                                                                      \
   do {                                                                                         \
+    prof_begin(name);                                                                          \
+    __VA_ARGS__;                                                                               \
+    prof_end();                                                                                \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
     cudaError_t _e = cudaPeekAtLastError();                                                    \
     if (_e != cudaSuccess) return fail(SCLDM_ECUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
@@ -120,8 +150,7 @@ int launch_mod(const scldm_dit_weights* w, const scldm_dit_plan* plan, const Dit
   p.out_f32 = ws.mod;
   p.out_ld = w->mod_stride;
   dim3 grid(row_tiles, ceil_div(p.n_tiles_total, p.tiles_per_cta));
-  dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD><<<grid, dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p);
-  LAUNCH_CHECK("gemm_ares<COND,MOD>");
+  LAUNCH("gemm_ares<COND,MOD>", dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD><<<grid, dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
   return SCLDM_OK;
 }
 
@@ -140,18 +169,15 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.n_tiles_total = 3; p.tiles_per_cta = 3;
       p.bias = w->b_qkv + (size_t)l * 3 * dit::D;
       p.out_bf16 = ws.qkv; p.out_ld = 3 * dit::D;
-      dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p);
-      LAUNCH_CHECK("gemm_ares<LN,QKV>");
+      LAUNCH("gemm_ares<LN,QKV>", dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
     }
-    dit::attn16_kernel<<<slots_pad, 256, 0, st>>>(ws.qkv, ws.ao, slots_pad);
-    LAUNCH_CHECK("attn16");
+    LAUNCH("attn16", dit::attn16_kernel<<<slots_pad, 256, 0, st>>>(ws.qkv, ws.ao, slots_pad));
     {  // c_proj + gated residual
       dit::AStreamParams p{};
       p.Ap = ws.ao; p.Wp = static_cast<const dit::bf16*>(w->w_proj) + (size_t)l * tile_elems; p.k_slabs = dit::KSLABS_D;
       p.bias = w->b_proj + (size_t)l * dit::D;
       p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 2 * dit::D;
-      dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p);
-      LAUNCH_CHECK("gemm_astream<proj>");
+      LAUNCH("gemm_astream<proj>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
     }
     {  // LN2 + modulate + [w1|w2] + SwiGLU
       dit::AResParams p{};
@@ -160,16 +186,14 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.Wp = static_cast<const dit::bf16*>(w->w_mlp1) + (size_t)l * w->mlp1_tiles * tile_elems;
       p.n_tiles_total = w->mlp1_tiles; p.tiles_per_cta = w->mlp1_tiles;
       p.out_packed = ws.hid; p.out_slabs = w->hid_slabs;
-      dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p);
-      LAUNCH_CHECK("gemm_ares<LN,SWIGLU>");
+      LAUNCH("gemm_ares<LN,SWIGLU>", dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
     }
     {  // mlp.c_proj + gated residual
       dit::AStreamParams p{};
       p.Ap = ws.hid; p.Wp = static_cast<const dit::bf16*>(w->w_mlp2) + (size_t)l * w->hid_slabs * dit::B_SLAB_ELEMS;
       p.k_slabs = w->hid_slabs; p.bias = nullptr;
       p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 5 * dit::D;
-      dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p);
-      LAUNCH_CHECK("gemm_astream<mlp2>");
+      LAUNCH("gemm_astream<mlp2>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
     }
   }
   return SCLDM_OK;
@@ -191,8 +215,7 @@ int launch_cls(const scldm_dit_weights* w, const scldm_dit_plan* plan, const Dit
   dit::ClsParams c{};
   for (int i = 0; i < w->n_class; ++i) c.tables[i] = w->class_tables[i];
   c.idx = plan->cls_idx; c.n_class = w->n_class; c.n_mod_pad = mod_pad;
-  dit::cls_kernel<<<mod_pad, 256, 0, st>>>(c, ws.cls);
-  LAUNCH_CHECK("cls");
+  LAUNCH("cls", dit::cls_kernel<<<mod_pad, 256, 0, st>>>(c, ws.cls));
   return SCLDM_OK;
 }
 
@@ -250,18 +273,15 @@ int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, co
   const int n_states = plan->n_u + plan->n_g;
 
   if ((rc = launch_cls(w, plan, ws, st))) return rc;
-  dit::temb_kernel<<<mod_pad, 256, 0, st>>>(t_mod, mod_pad, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb);
-  LAUNCH_CHECK("temb");
+  LAUNCH("temb", dit::temb_kernel<<<mod_pad, 256, 0, st>>>(t_mod, mod_pad, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
   if ((rc = launch_mod(w, plan, ws, ws.temb, dit::D, st))) return rc;
 
   dit::StepParams s = make_step(w, plan, ws);
   s.x_base = const_cast<float*>(x);  // read only in inproj
-  dit::inproj_kernel<<<n_states, 256, 0, st>>>(s);
-  LAUNCH_CHECK("inproj");
+  LAUNCH("inproj", dit::inproj_kernel<<<n_states, 256, 0, st>>>(s));
   if ((rc = launch_blocks(w, plan, ws, st))) return rc;
   s.v_out = v_out; s.do_update = 0; s.do_inproj = 0;
-  dit::final_step_kernel<<<n_states, 256, 0, st>>>(s);
-  LAUNCH_CHECK("final_step");
+  LAUNCH("final_step", dit::final_step_kernel<<<n_states, 256, 0, st>>>(s));
   return SCLDM_OK;
 }
 
@@ -297,19 +317,16 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
         if (sg == 1) tv = (method == SCLDM_ODE_HEUN2) ? t1 : t0 + 0.5f * dt;
         ta.t[n] = tv;
       }
-      set_times_kernel<<<1, 64, 0, st>>>(ws.tvals + e, ta, n);
-      LAUNCH_CHECK("set_times");
+      LAUNCH("set_times", set_times_kernel<<<1, 64, 0, st>>>(ws.tvals + e, ta, n));
       e += n;
     }
   }
-  dit::temb_kernel<<<n_evals, 256, 0, st>>>(ws.tvals, n_evals, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb);
-  LAUNCH_CHECK("temb");
+  LAUNCH("temb", dit::temb_kernel<<<n_evals, 256, 0, st>>>(ws.tvals, n_evals, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
   if ((rc = launch_cls(w, plan, ws, st))) return rc;
 
   dit::StepParams s = make_step(w, plan, ws);
   s.x_base = x;
-  dit::inproj_kernel<<<n_states, 256, 0, st>>>(s);
-  LAUNCH_CHECK("inproj");
+  LAUNCH("inproj", dit::inproj_kernel<<<n_states, 256, 0, st>>>(s));
   s.do_update = 1;
   for (int k = 0; k < n_steps; ++k) {
     const float dt = t_grid_host[k + 1] - t_grid_host[k];
@@ -323,8 +340,7 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
       else if (method == SCLDM_ODE_HEUN2) { s.a_dt = dt; s.b_dt = 0.5f * dt; }
       else { s.a_dt = 0.5f * dt; s.b_dt = sg == 0 ? 0.f : dt; }
       s.do_inproj = !(k == n_steps - 1 && s.last_stage);
-      dit::final_step_kernel<<<n_states, 256, 0, st>>>(s);
-      LAUNCH_CHECK("final_step");
+      LAUNCH("final_step", dit::final_step_kernel<<<n_states, 256, 0, st>>>(s));
     }
   }
   return SCLDM_OK;
@@ -333,8 +349,7 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
 int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* stream) {
   if (!w || !qp) return fail(SCLDM_EINVAL, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  vae::qside_kernel<<<ceil_div(w->n_ids, 128), 128, 0, st>>>(w->emb, w->ca_ln1q_w, w->ca_ln1q_b, w->ca_wq, w->eps, w->n_ids, qp);
-  LAUNCH_CHECK("qside");
+  LAUNCH("qside", vae::qside_kernel<<<ceil_div(w->n_ids, 128), 128, 0, st>>>(w->emb, w->ca_ln1q_w, w->ca_ln1q_b, w->ca_wq, w->eps, w->n_ids, qp));
   return SCLDM_OK;
 }
 
@@ -365,8 +380,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const floa
   vae::DecLatentParams dp{};
   dp.z = z; dp.win_t = w->win_t; dp.blocks = w->blocks; dp.n_layer = w->n_layer;
   dp.ca_ln1_w = w->ca_ln1_w; dp.ca_ln1_b = w->ca_ln1_b; dp.ca_wkv_t = w->ca_wkv_t; dp.eps = w->eps; dp.kv = kv;
-  vae::dec_latent_kernel<<<n_cells, 128, 0, st>>>(dp, n_cells);
-  LAUNCH_CHECK("dec_latent");
+  LAUNCH("dec_latent", vae::dec_latent_kernel<<<n_cells, 128, 0, st>>>(dp, n_cells));
 
   vae::McabParams mp{};
   mp.emb = w->emb; mp.qp = qp; mp.genes = reinterpret_cast<const long long*>(genes); mp.G = n_genes; mp.kv = kv; mp.n_cells = n_cells;
@@ -376,8 +390,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const floa
   if (cpb > 32) cpb = 32;
   mp.cells_per_block = cpb;
   mp.wblob = w->mcab_blob; mp.eps = w->eps; mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
-  vae::mcab_decode_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 128, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float), st>>>(mp);
-  LAUNCH_CHECK("mcab_decode");
+  LAUNCH("mcab_decode", vae::mcab_decode_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 128, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float), st>>>(mp));
 
   vae::NbParams np{};
   np.logits = logits; np.partials = partials; np.gene_tiles = tiles; np.G = n_genes; np.n_cells = n_cells; np.lib = lib;
@@ -385,8 +398,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const floa
   np.seed = seed; np.cell_offset = cell_offset;
   int gx = ceil_div(n_genes, 256 * 4);
   if (gx < 1) gx = 1;
-  vae::nb_finalize_kernel<<<dim3(n_cells, gx), 256, 0, st>>>(np);
-  LAUNCH_CHECK("nb_finalize");
+  LAUNCH("nb_finalize", vae::nb_finalize_kernel<<<dim3(n_cells, gx), 256, 0, st>>>(np));
   return SCLDM_OK;
 }
 
@@ -394,13 +406,41 @@ int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t se
                       void* stream) {
   if (!out || n_cells < 1 || per_cell < 1) return fail(SCLDM_EINVAL, "bad randn arguments");
   const long long n = (long long)n_cells * per_cell;
-  vae::randn_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n_cells, per_cell, seed,
-                                                                                                      cell_offset, stream_id);
-  LAUNCH_CHECK("randn_cells");
+  LAUNCH("randn_cells", vae::randn_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n_cells, per_cell, seed,
+                                                                                                      cell_offset, stream_id));
   return SCLDM_OK;
 }
 
 uint64_t scldm_launch_count(void) { return g_launches.load(); }
+
+void scldm_prof_enable(int32_t on, void* stream) {
+  g_prof_on = on != 0;
+  g_prof_stream = static_cast<cudaStream_t>(stream);
+}
+
+// "name count total_ms\n" per kernel class since the last call; returns the number of bytes written
+int32_t scldm_prof_summary(char* buf, int32_t cap) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += ms;
+    }
+    g_prof_pool.push_back(r.a);
+    g_prof_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  int off = 0;
+  for (auto& kv : agg) {
+    int n = snprintf(buf + off, cap > off ? cap - off : 0, "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    if (n < 0 || off + n >= cap) break;
+    off += n;
+  }
+  return off;
+}
 const char* scldm_last_error(void) { return g_err; }
 const char* scldm_version(void) { return "scldm_b200 0.1 (sm_100a)"; }
 

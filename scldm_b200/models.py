@@ -122,12 +122,10 @@ class LatentDiffusion(nn.Module):
             libc = torch.cat([lib[c0:c1], lib[c0:c1]])
             for half, rows in ((0, slice(c0, c1)), (1, slice(batch_size + c0, batch_size + c1))):
                 zh = zf[half * n:(half + 1) * n]
-                cts, mu, _ = self.vae_model.decode_counts(zh, gvec, libc[half * n:(half + 1) * n], seed=self.seed,
-                                                          cell_offset=offset + c0 + half * (1 << 40), want_mu=return_mu)
-                counts[rows] = cts
+                self.vae_model.decode_counts(zh, gvec, libc[half * n:(half + 1) * n], seed=self.seed,
+                                             cell_offset=offset + c0 + half * (1 << 40), want_mu=return_mu,
+                                             out_counts=counts[rows], out_mu=mu_out[rows] if return_mu else None)
                 z_out[rows] = zh
-                if return_mu:
-                    mu_out[rows] = mu
         if return_mu:
             return counts, z_out, mu_out
         return counts, z_out

@@ -152,7 +152,8 @@ def vae_qside(packed: PackedVAEDecoder) -> torch.Tensor:
 
 
 def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, lib_size: torch.Tensor, want_mu=True,
-               want_counts=False, seed: int = 0, cell_offset: int = 0):
+               want_counts=False, seed: int = 0, cell_offset: int = 0, out_mu: torch.Tensor | None = None,
+               out_counts: torch.Tensor | None = None):
     """z [cells,16,16] fp32, genes [G] int64 (shared by all cells), lib_size [cells] fp32 ->
     (mu [cells,G] | None, theta [G], counts [cells,G] | None)."""
     lib = _lib.load()
@@ -163,8 +164,12 @@ def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, l
     assert int(lib_size.numel()) == n_cells
     lib_size = lib_size.reshape(-1).to(torch.float32).contiguous()
     qp = vae_qside(packed)
-    mu = torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_mu else None
-    counts = torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_counts else None
+    for o in (out_mu, out_counts):
+        if o is not None:
+            assert o.is_cuda and o.is_contiguous() and o.dtype == torch.float32 and o.shape == (n_cells, G)
+    mu = out_mu if out_mu is not None else (torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_mu else None)
+    counts = out_counts if out_counts is not None else (
+        torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_counts else None)
     theta = torch.empty(G, dtype=torch.float32, device=z.device)
     nbytes = int(lib.scldm_vae_decode_workspace_bytes(n_cells, G))
     ws = _workspace(z.device, nbytes, "vae")
@@ -181,6 +186,23 @@ def randn_cells(n_cells: int, per_cell: int, seed: int, cell_offset: int, stream
     out = torch.empty(n_cells, per_cell, dtype=torch.float32, device=device)
     rc = lib.scldm_randn_cells(out.data_ptr(), n_cells, per_cell, seed & (2**64 - 1), cell_offset, stream_id, _stream_ptr(device))
     _lib.check(rc, "scldm_randn_cells")
+    return out
+
+
+def prof_enable(on: bool, device=None) -> None:
+    """Bracket every library launch with CUDA events on the current stream (bench.py roofline timing)."""
+    dev = device if device is not None else torch.cuda.current_device()
+    _lib.load().scldm_prof_enable(1 if on else 0, _stream_ptr(dev))
+
+
+def prof_summary() -> dict[str, tuple[int, float]]:
+    """{kernel class: (launches, total ms)} since the last call (synchronises the device)."""
+    buf = C.create_string_buffer(1 << 16)
+    n = _lib.load().scldm_prof_summary(buf, len(buf))
+    out = {}
+    for line in buf.raw[:n].decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
     return out
 
 

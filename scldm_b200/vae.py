@@ -83,11 +83,14 @@ class TransformerVAE(nn.Module):
 
         return NegativeBinomial(mu, theta_full, _sampler=sampler)
 
-    def decode_counts(self, z, genes, library_size, seed: int = 0, cell_offset: int = 0, want_mu: bool = False):
-        """Fast path of `decode(...).sample()` (`models.py:818-819`): one pass, counts only (+mu on request)."""
+    def decode_counts(self, z, genes, library_size, seed: int = 0, cell_offset: int = 0, want_mu: bool = False,
+                      out_counts=None, out_mu=None):
+        """Fast path of `decode(...).sample()` (`models.py:818-819`): one pass, counts only (+mu on request),
+        optionally written straight into caller-provided output rows."""
         packed = self.packed_decoder()
         mu, theta, counts = ops.vae_decode(packed, z.contiguous().float(), shared_gene_vector(genes), library_size,
-                                           want_mu=want_mu, want_counts=True, seed=seed, cell_offset=cell_offset)
+                                           want_mu=want_mu, want_counts=True, seed=seed, cell_offset=cell_offset,
+                                           out_counts=out_counts, out_mu=out_mu)
         return counts, mu, theta
 
     def encode(self, counts, genes, counts_subset=None, genes_subset=None):
