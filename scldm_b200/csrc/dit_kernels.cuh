@@ -34,8 +34,9 @@ constexpr int B_SLAB_BYTES = BLOCK_N * BLOCK_K * 2;    // 32768
 constexpr int A_SLAB_ELEMS = BLOCK_M * BLOCK_K;
 constexpr int B_SLAB_ELEMS = BLOCK_N * BLOCK_K;
 constexpr int STG_BYTES = 128 * 272;                   // epilogue staging (fp32 64-col chunk, 16 B row pad)
-constexpr int NUM_THREADS = 192;                       // warp0 TMA, warp1 MMA, warps 2-5 prologue/epilogue
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;            // 512
+constexpr int NUM_THREADS = 64 + EPI_THREADS;          // warp0 TMA, warp1 MMA, warps 2-17 prologue/epilogue
 constexpr int MAX_COMBINE = 8;
 
 enum { PRO_LN = 0, PRO_COND = 1 };
@@ -102,6 +103,10 @@ __device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_d, uint32_t a_smem
 
 // ==========================================================================================
 // GEMM with an A operand produced in-kernel (resident for the CTA's whole N loop)
+//
+// 18 warps: warp 0 = bulk-TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..17 = 16
+// prologue/epilogue warps.  Epilogue warp w may only read TMEM lanes [32*(w%4), +32), so the 16 warps
+// form a 4 (lane quadrant q) x 4 (column quarter `sub`) grid over each accumulator chunk.
 // ==========================================================================================
 template <int PRO, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResParams p) {
@@ -133,9 +138,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
     }
     for (uint32_t i = 0; i < 2; ++i) {
       sm100::mbar_init(&tmem_full[i], 1);
-      sm100::mbar_init(&tmem_empty[i], EPI_THREADS);
+      sm100::mbar_init(&tmem_empty[i], EPI_WARPS);
     }
-    sm100::mbar_init(a_ready, EPI_THREADS);
+    sm100::mbar_init(a_ready, EPI_WARPS);
     sm100::fence_barrier_init();
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -182,54 +187,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
       }
     }
   } else {
-    // ===================== prologue + epilogue warps (128 threads) =======================
-    const uint32_t ew = warp - 2;          // 0..3: A-production work split
-    const uint32_t q = warp & 3;           // TMEM sub-partition this warp may read
+    // ===================== 16 prologue + epilogue warps (512 threads) ====================
+    const uint32_t ew = warp - 2;          // 0..15
+    const uint32_t q = warp & 3;           // TMEM lane quadrant this warp may read
+    const uint32_t sub = ew >> 2;          // column quarter
     const uint32_t etid = threadIdx.x - 64;
 
-    // ---------- produce the A tile (128 rows x 256 K, bf16, swizzled) ----------
+    // ---------- produce the A tile (128 rows x 256 K, bf16, swizzled); warp ew owns rows [8*ew, 8*ew+8) ----------
     if constexpr (PRO == PRO_LN) {
-      // warp ew owns rows [32*ew, 32*ew+32) = 2 slots; lane owns columns [8*lane, 8*lane+8)
       const float inv_d = 1.0f / D;
-#pragma unroll 1
-      for (int sl = 0; sl < 2; ++sl) {
-        const int slot = row_tile * 8 + ew * 2 + sl;
-        const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride;
-        const float4 m0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8);
-        const float4 m1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8 + 4);
-        const float4 a0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8 + 4);
-        const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
-        const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const int slot = row_tile * 8 + (ew >> 1);
+      const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride;
+      const float4 m0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8);
+      const float4 m1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8 + 4);
+      const float4 a0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8);
+      const float4 a1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8 + 4);
+      const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
+      const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll 4
-        for (int tk = 0; tk < TOK; ++tk) {
-          const int r = ew * 32 + sl * 16 + tk;  // row within tile
-          const float* xr = p.X + ((size_t)row_tile * BLOCK_M + r) * D + lane * 8;
-          const float4 x0 = *reinterpret_cast<const float4*>(xr);
-          const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
-          float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-          float s = 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int r = ew * 8 + i;  // row within tile
+        const float* xr = p.X + ((size_t)row_tile * BLOCK_M + r) * D + lane * 8;
+        const float4 x0 = *reinterpret_cast<const float4*>(xr);
+        const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+        float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s += v[j];
-          const float mean = sm100::warp_sum(s) * inv_d;
-          float ss = 0.f;
+        for (int j = 0; j < 8; ++j) s += v[j];
+        const float mean = sm100::warp_sum(s) * inv_d;
+        float ss = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { v[j] -= mean; ss += v[j] * v[j]; }
-          const float rstd = rsqrtf(sm100::warp_sum(ss) * inv_d + p.eps);
-          uint4 o;
-          o.x = sm100::pack_bf16x2(v[0] * rstd * mul[0] + add[0], v[1] * rstd * mul[1] + add[1]);
-          o.y = sm100::pack_bf16x2(v[2] * rstd * mul[2] + add[2], v[3] * rstd * mul[3] + add[3]);
-          o.z = sm100::pack_bf16x2(v[4] * rstd * mul[4] + add[4], v[5] * rstd * mul[5] + add[5]);
-          o.w = sm100::pack_bf16x2(v[6] * rstd * mul[6] + add[6], v[7] * rstd * mul[7] + add[7]);
-          // column 8*lane -> slab lane/8, 16-byte chunk lane%8
-          *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
-        }
+        for (int j = 0; j < 8; ++j) { v[j] -= mean; ss += v[j] * v[j]; }
+        const float rstd = rsqrtf(sm100::warp_sum(ss) * inv_d + p.eps);
+        uint4 o;
+        o.x = sm100::pack_bf16x2(v[0] * rstd * mul[0] + add[0], v[1] * rstd * mul[1] + add[1]);
+        o.y = sm100::pack_bf16x2(v[2] * rstd * mul[2] + add[2], v[3] * rstd * mul[3] + add[3]);
+        o.z = sm100::pack_bf16x2(v[4] * rstd * mul[4] + add[4], v[5] * rstd * mul[5] + add[5]);
+        o.w = sm100::pack_bf16x2(v[6] * rstd * mul[6] + add[6], v[7] * rstd * mul[7] + add[7]);
+        // column 8*lane -> slab lane/8, 16-byte chunk lane%8
+        *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
       }
     } else {
-      // PRO_COND: A[m][k] = SiLU(temb[k] + cls[m][k]); warp ew owns 32 rows, lane owns 8 columns
+      // PRO_COND: A[m][k] = SiLU(temb[k] + cls[m][k])
 #pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const int r = ew * 32 + i;
+      for (int i = 0; i < 8; ++i) {
+        const int r = ew * 8 + i;
         const size_t m = (size_t)row_tile * BLOCK_M + r;
         const float* tr = p.temb + m * p.temb_row_stride + lane * 8;
         const float* cr = p.cls + m * D + lane * 8;
@@ -246,12 +248,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
       }
     }
     sm100::fence_proxy_async_smem();   // generic-proxy smem writes -> visible to UMMA
-    sm100::mbar_arrive(a_ready);
+    __syncwarp();
+    if (lane == 0) sm100::mbar_arrive(a_ready);
 
     // ---------- epilogue over this CTA's N tiles ----------
     const uint32_t row = q * 32 + lane;                       // accumulator row == TMEM lane
-    const size_t grow = (size_t)row_tile * BLOCK_M + row;     // global row
-    uint32_t store_cnt = 0;
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
       const int tile = tile0 + t;
@@ -260,112 +261,118 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BLOCK_N;
 
       if constexpr (EPI == EPI_QKV) {
-        // 4 chunks of 64 columns: acc + bias -> bf16 -> swizzled staging -> coalesced row-major store
+        // 2 chunks of 128 columns; this warp: 32 columns [32*sub, +32) of the chunk.
+        // acc + bias -> bf16 -> two swizzled [128][64] staging slabs -> coalesced row-major store
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           sm100::named_bar_sync(1, EPI_THREADS);  // staging free
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          {
             uint32_t v[32];
-            sm100::tmem_ld_32x32b_x32(taddr + ch * 64 + h * 32, v);
+            sm100::tmem_ld_32x32b_x32(taddr + ch * 128 + sub * 32, v);
             sm100::tmem_ld_wait();
-            const float* bp = p.bias + tile * BLOCK_N + ch * 64 + h * 32;
+            const float* bp = p.bias + tile * BLOCK_N + ch * 128 + sub * 32;
+            uint8_t* slab = smStg + (sub >> 1) * A_SLAB_BYTES;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bp + c * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bp + c * 8 + 4);
               uint4 o;
-              o.x = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 0]) + bp[c * 8 + 0], __uint_as_float(v[c * 8 + 1]) + bp[c * 8 + 1]);
-              o.y = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 2]) + bp[c * 8 + 2], __uint_as_float(v[c * 8 + 3]) + bp[c * 8 + 3]);
-              o.z = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 4]) + bp[c * 8 + 4], __uint_as_float(v[c * 8 + 5]) + bp[c * 8 + 5]);
-              o.w = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 6]) + bp[c * 8 + 6], __uint_as_float(v[c * 8 + 7]) + bp[c * 8 + 7]);
-              *reinterpret_cast<uint4*>(smStg + sm100::swz_chunk_offset(row, h * 4 + c)) = o;
+              o.x = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y);
+              o.y = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w);
+              o.z = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y);
+              o.w = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w);
+              *reinterpret_cast<uint4*>(slab + sm100::swz_chunk_offset(row, (sub & 1) * 4 + c)) = o;
             }
           }
           sm100::named_bar_sync(1, EPI_THREADS);  // staging full
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const uint32_t r = it * 16 + (etid >> 3), c = etid & 7;
-            const uint4 o = *reinterpret_cast<const uint4*>(smStg + sm100::swz_chunk_offset(r, c));
-            bf16* dst = p.out_bf16 + ((size_t)row_tile * BLOCK_M + r) * p.out_ld + tile * BLOCK_N + ch * 64 + c * 8;
+          for (int it = 0; it < 4; ++it) {
+            const uint32_t idx = it * EPI_THREADS + etid;
+            const uint32_t r = idx >> 4, c16 = idx & 15;  // 16 x 16 B per 256 B row segment
+            const uint4 o = *reinterpret_cast<const uint4*>(smStg + (c16 >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, c16 & 7));
+            bf16* dst = p.out_bf16 + ((size_t)row_tile * BLOCK_M + r) * p.out_ld + tile * BLOCK_N + ch * 128 + c16 * 8;
             *reinterpret_cast<uint4*>(dst) = o;
           }
         }
       } else if constexpr (EPI == EPI_MOD) {
-        // fp32 row-major + bias; staging rows padded to 272 B (conflict-free 16 B accesses)
+        // 4 chunks of 64 fp32 columns; this warp: 16 columns; staging rows padded to 272 B
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           sm100::named_bar_sync(1, EPI_THREADS);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            sm100::tmem_ld_32x32b_x32(taddr + ch * 64 + h * 32, v);
+          {
+            uint32_t v[16];
+            sm100::tmem_ld_32x32b_x16(taddr + ch * 64 + sub * 16, v);
             sm100::tmem_ld_wait();
-            const float* bp = p.bias + tile * BLOCK_N + ch * 64 + h * 32;
+            const float* bp = p.bias + tile * BLOCK_N + ch * 64 + sub * 16;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
+              const float4 b = *reinterpret_cast<const float4*>(bp + c * 4);
               float4 o;
-              o.x = __uint_as_float(v[c * 4 + 0]) + bp[c * 4 + 0];
-              o.y = __uint_as_float(v[c * 4 + 1]) + bp[c * 4 + 1];
-              o.z = __uint_as_float(v[c * 4 + 2]) + bp[c * 4 + 2];
-              o.w = __uint_as_float(v[c * 4 + 3]) + bp[c * 4 + 3];
-              *reinterpret_cast<float4*>(smStg + row * 272 + (h * 8 + c) * 16) = o;
+              o.x = __uint_as_float(v[c * 4 + 0]) + b.x;
+              o.y = __uint_as_float(v[c * 4 + 1]) + b.y;
+              o.z = __uint_as_float(v[c * 4 + 2]) + b.z;
+              o.w = __uint_as_float(v[c * 4 + 3]) + b.w;
+              *reinterpret_cast<float4*>(smStg + row * 272 + (sub * 4 + c) * 16) = o;
             }
           }
           sm100::named_bar_sync(1, EPI_THREADS);
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const uint32_t r = it * 8 + (etid >> 4), c = etid & 15;
+          for (int it = 0; it < 4; ++it) {
+            const uint32_t idx = it * EPI_THREADS + etid;
+            const uint32_t r = idx >> 4, c = idx & 15;
             const float4 o = *reinterpret_cast<const float4*>(smStg + r * 272 + c * 16);
             float* dst = p.out_f32 + ((size_t)row_tile * BLOCK_M + r) * p.out_ld + tile * BLOCK_N + ch * 64 + c * 4;
             *reinterpret_cast<float4*>(dst) = o;
           }
         }
       } else {
-        // EPI_SWIGLU: tile columns [0,128) = w1 rows, [128,256) = w2 rows of hidden [128*tile, 128*tile+128)
-        // -> two 64-wide hidden slabs, each written as a swizzled A slab and bulk-stored (16 KB contiguous)
-#pragma unroll 1
-        for (int hs = 0; hs < 2; ++hs) {
-          const int slab = tile * 2 + hs;
-          if (slab >= p.out_slabs) break;  // uniform across threads
-          uint8_t* buf = smStg + (store_cnt & 1) * A_SLAB_BYTES;
-          if (etid == 0) sm100::bulk_wait_read<1>();  // the store that last used this buffer has drained
-          sm100::named_bar_sync(1, EPI_THREADS);
+        // EPI_SWIGLU: tile columns [0,128) = w1 rows, [128,256) = w2 rows of hidden [128*tile, +128)
+        // -> two 64-wide hidden slabs written as swizzled A slabs and bulk-stored (16 KB contiguous each).
+        // this warp: slab hs = sub/2, 32 hidden columns h = sub%2
+        const int hs = sub >> 1, h = sub & 1;
+        if (etid == 0) sm100::bulk_wait_read<0>();  // previous tile's stores have drained the staging slabs
+        sm100::named_bar_sync(1, EPI_THREADS);
+        if (tile * 2 + hs < p.out_slabs) {
+          uint32_t va[32], vb[32];
+          sm100::tmem_ld_32x32b_x32(taddr + hs * 64 + h * 32, va);
+          sm100::tmem_ld_32x32b_x32(taddr + 128 + hs * 64 + h * 32, vb);
+          sm100::tmem_ld_wait();
+          uint8_t* buf = smStg + hs * A_SLAB_BYTES;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t va[32], vb[32];
-            sm100::tmem_ld_32x32b_x32(taddr + hs * 64 + h * 32, va);
-            sm100::tmem_ld_32x32b_x32(taddr + 128 + hs * 64 + h * 32, vb);
-            sm100::tmem_ld_wait();
+          for (int c = 0; c < 4; ++c) {
+            float hv[8];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float hv[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                hv[j] = sm100::silu(__uint_as_float(va[c * 8 + j])) * __uint_as_float(vb[c * 8 + j]);
-              uint4 o;
-              o.x = sm100::pack_bf16x2(hv[0], hv[1]);
-              o.y = sm100::pack_bf16x2(hv[2], hv[3]);
-              o.z = sm100::pack_bf16x2(hv[4], hv[5]);
-              o.w = sm100::pack_bf16x2(hv[6], hv[7]);
-              *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, h * 4 + c)) = o;
-            }
+            for (int j = 0; j < 8; ++j)
+              hv[j] = sm100::silu(__uint_as_float(va[c * 8 + j])) * __uint_as_float(vb[c * 8 + j]);
+            uint4 o;
+            o.x = sm100::pack_bf16x2(hv[0], hv[1]);
+            o.y = sm100::pack_bf16x2(hv[2], hv[3]);
+            o.z = sm100::pack_bf16x2(hv[4], hv[5]);
+            o.w = sm100::pack_bf16x2(hv[6], hv[7]);
+            *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, h * 4 + c)) = o;
           }
-          sm100::fence_proxy_async_smem();
-          sm100::named_bar_sync(1, EPI_THREADS);
-          if (etid == 0) {
-            sm100::bulk_s2g(p.out_packed + ((size_t)row_tile * p.out_slabs + slab) * A_SLAB_ELEMS, buf, A_SLAB_BYTES);
-            sm100::bulk_commit();
+        }
+        sm100::fence_proxy_async_smem();
+        sm100::named_bar_sync(1, EPI_THREADS);
+        if (etid == 0) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int slab = tile * 2 + s2;
+            if (slab < p.out_slabs)
+              sm100::bulk_s2g(p.out_packed + ((size_t)row_tile * p.out_slabs + slab) * A_SLAB_ELEMS, smStg + s2 * A_SLAB_BYTES,
+                              A_SLAB_BYTES);
           }
-          ++store_cnt;
+          sm100::bulk_commit();
         }
       }
       // accumulator drained -> MMA warp may overwrite it
       sm100::tc_fence_before();
-      sm100::mbar_arrive(&tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
     }
     if constexpr (EPI == EPI_SWIGLU) {
       if (etid == 0) sm100::bulk_wait<0>();
     }
-    (void)grow;
   }
 
   sm100::tc_fence_before();
@@ -440,47 +447,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
       sm100::umma_commit(tmem_full);
     }
   } else {
+    const uint32_t ew = warp - 2;
     const uint32_t q = warp & 3;
+    const uint32_t sub = ew >> 2;
     const uint32_t etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
+    // operands of the read-modify-write pass that do not depend on the accumulator: fetch while the MMAs run
+    // thread handles items idx = it*512 + etid -> (row r = idx/16, float4 column c = idx%16) of each 64-column chunk
+    const uint32_t cc = etid & 15;
+    int mrow[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const uint32_t r = (it * EPI_THREADS + etid) >> 4;
+      mrow[it] = p.slot_mod[row_tile * 8 + (r >> 4)];
+    }
     sm100::mbar_wait(tmem_full, 0);
     sm100::tc_fence_after();
     const uint32_t taddr = tmem_base + ((q * 32u) << 16);
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
-      sm100::named_bar_sync(1, EPI_THREADS);
+      const int col = ch * 64 + cc * 4;
+      // issue the global loads of this chunk early (gate, residual, bias)
+      float4 g[4], x[4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        sm100::tmem_ld_32x32b_x32(taddr + ch * 64 + h * 32, v);
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
+        g[it] = *reinterpret_cast<const float4*>(p.mod + (size_t)mrow[it] * p.mod_stride + p.mod_off_gate + col);
+        x[it] = *reinterpret_cast<const float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + col);
+      }
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr) b = *reinterpret_cast<const float4*>(p.bias + col);
+      sm100::named_bar_sync(1, EPI_THREADS);   // staging free
+      {
+        uint32_t v[16];
+        sm100::tmem_ld_32x32b_x16(taddr + ch * 64 + sub * 16, v);
         sm100::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           float4 o;
           o.x = __uint_as_float(v[c * 4 + 0]);
           o.y = __uint_as_float(v[c * 4 + 1]);
           o.z = __uint_as_float(v[c * 4 + 2]);
           o.w = __uint_as_float(v[c * 4 + 3]);
-          *reinterpret_cast<float4*>(smStg + row * 272 + (h * 8 + c) * 16) = o;
+          *reinterpret_cast<float4*>(smStg + row * 272 + (sub * 4 + c) * 16) = o;
         }
       }
-      sm100::named_bar_sync(1, EPI_THREADS);
+      sm100::named_bar_sync(1, EPI_THREADS);   // staging full
       // coalesced read-modify-write of the residual stream: 2 rows x 256 B per warp instruction
-#pragma unroll 4
-      for (int it = 0; it < 16; ++it) {
-        const uint32_t r = it * 8 + (etid >> 4), c = etid & 15;
-        const int col = ch * 64 + c * 4;
-        float4 a = *reinterpret_cast<const float4*>(smStg + r * 272 + c * 16);
-        if (p.bias != nullptr) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
-          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        const int slot = row_tile * 8 + (r >> 4);
-        const float4 g = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod[slot] * p.mod_stride + p.mod_off_gate + col);
-        float* xp = p.X + ((size_t)row_tile * BLOCK_M + r) * D + col;
-        float4 x = *reinterpret_cast<float4*>(xp);
-        x.x += g.x * a.x; x.y += g.y * a.y; x.z += g.z * a.z; x.w += g.w * a.w;
-        *reinterpret_cast<float4*>(xp) = x;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
+        const float4 a = *reinterpret_cast<const float4*>(smStg + r * 272 + cc * 16);
+        float4 o = x[it];
+        o.x += g[it].x * (a.x + b.x); o.y += g[it].y * (a.y + b.y); o.z += g[it].z * (a.z + b.z); o.w += g[it].w * (a.w + b.w);
+        *reinterpret_cast<float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + col) = o;
       }
     }
   }
