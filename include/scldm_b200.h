@@ -141,6 +141,10 @@ int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t se
 void scldm_prof_enable(int32_t on, void* stream);
 int32_t scldm_prof_summary(char* buf, int32_t cap);
 
+/* Debug: when device_buf != NULL the four GEMM kernels of DiT block `layer` write clock64() phase stamps into
+ * device_buf (4 regions of 2^17 int64: qkv, proj, mlp1, mlp2; 32 stamps per CTA).  NULL disables.      */
+void scldm_debug_timeline(long long* device_buf, int32_t layer);
+
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 uint64_t scldm_launch_count(void);
 const char* scldm_last_error(void);

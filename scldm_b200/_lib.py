@@ -16,7 +16,7 @@ ODE_METHODS = {"euler": 0, "heun2": 1, "midpoint": 2}
 EXPORTS = [
     "scldm_dit_slots_pad", "scldm_dit_mod_pad", "scldm_dit_workspace_bytes", "scldm_dit_workspace_layout",
     "scldm_dit_forward", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
-    "scldm_vae_decode", "scldm_randn_cells", "scldm_prof_enable", "scldm_prof_summary", "scldm_launch_count", "scldm_last_error", "scldm_version",
+    "scldm_vae_decode", "scldm_randn_cells", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
 ]
 
 
@@ -89,6 +89,8 @@ def load() -> C.CDLL:
     lib.scldm_prof_enable.restype = None
     lib.scldm_prof_summary.argtypes = [C.c_char_p, C.c_int32]
     lib.scldm_prof_summary.restype = C.c_int32
+    lib.scldm_debug_timeline.argtypes = [C.c_void_p, C.c_int32]
+    lib.scldm_debug_timeline.restype = None
     lib.scldm_launch_count.argtypes = []
     lib.scldm_launch_count.restype = C.c_uint64
     lib.scldm_last_error.argtypes = []

@@ -14,6 +14,8 @@
 namespace {
 
 thread_local char g_err[512] = "";
+long long* g_dbg_clk = nullptr;   // optional device buffer for kernel phase timestamps (tools/kernel_timeline.py)
+int g_dbg_layer = -1;             // which layer's kernels write to it
 std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -168,7 +170,8 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.Wp = static_cast<const dit::bf16*>(w->w_qkv) + (size_t)l * 3 * tile_elems;
       p.n_tiles_total = 3; p.tiles_per_cta = 3;
       p.bias = w->b_qkv + (size_t)l * 3 * dit::D;
-      p.out_bf16 = ws.qkv; p.out_ld = 3 * dit::D;
+      p.out_bf16 = ws.qkv; p.out_ld = 3 * dit::D;  // 12 packed slabs per row tile
+      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk : nullptr;
       LAUNCH("gemm_ares<LN,QKV>", dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
     }
     LAUNCH("attn16", dit::attn16_kernel<<<slots_pad, 256, 0, st>>>(ws.qkv, ws.ao, slots_pad));
@@ -177,6 +180,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.Ap = ws.ao; p.Wp = static_cast<const dit::bf16*>(w->w_proj) + (size_t)l * tile_elems; p.k_slabs = dit::KSLABS_D;
       p.bias = w->b_proj + (size_t)l * dit::D;
       p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 2 * dit::D;
+      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + (1 << 17) : nullptr;
       LAUNCH("gemm_astream<proj>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
     }
     {  // LN2 + modulate + [w1|w2] + SwiGLU
@@ -186,6 +190,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.Wp = static_cast<const dit::bf16*>(w->w_mlp1) + (size_t)l * w->mlp1_tiles * tile_elems;
       p.n_tiles_total = w->mlp1_tiles; p.tiles_per_cta = w->mlp1_tiles;
       p.out_packed = ws.hid; p.out_slabs = w->hid_slabs;
+      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 2 * (1 << 17) : nullptr;
       LAUNCH("gemm_ares<LN,SWIGLU>", dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
     }
     {  // mlp.c_proj + gated residual
@@ -193,6 +198,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.Ap = ws.hid; p.Wp = static_cast<const dit::bf16*>(w->w_mlp2) + (size_t)l * w->hid_slabs * dit::B_SLAB_ELEMS;
       p.k_slabs = w->hid_slabs; p.bias = nullptr;
       p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 5 * dit::D;
+      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 3 * (1 << 17) : nullptr;
       LAUNCH("gemm_astream<mlp2>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
     }
   }
@@ -281,7 +287,7 @@ int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, co
   LAUNCH("inproj", dit::inproj_kernel<<<n_states, 256, 0, st>>>(s));
   if ((rc = launch_blocks(w, plan, ws, st))) return rc;
   s.v_out = v_out; s.do_update = 0; s.do_inproj = 0;
-  LAUNCH("final_step", dit::final_step_kernel<<<n_states, 256, 0, st>>>(s));
+  LAUNCH("final_step", dit::final_step_kernel<<<n_states < 296 ? n_states : 296, 512, 0, st>>>(s, n_states));
   return SCLDM_OK;
 }
 
@@ -340,7 +346,7 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
       else if (method == SCLDM_ODE_HEUN2) { s.a_dt = dt; s.b_dt = 0.5f * dt; }
       else { s.a_dt = 0.5f * dt; s.b_dt = sg == 0 ? 0.f : dt; }
       s.do_inproj = !(k == n_steps - 1 && s.last_stage);
-      LAUNCH("final_step", dit::final_step_kernel<<<n_states, 256, 0, st>>>(s));
+      LAUNCH("final_step", dit::final_step_kernel<<<n_states < 296 ? n_states : 296, 512, 0, st>>>(s, n_states));
     }
   }
   return SCLDM_OK;
@@ -412,6 +418,11 @@ int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t se
 }
 
 uint64_t scldm_launch_count(void) { return g_launches.load(); }
+
+void scldm_debug_timeline(long long* device_buf, int32_t layer) {
+  g_dbg_clk = device_buf;
+  g_dbg_layer = layer;
+}
 
 void scldm_prof_enable(int32_t on, void* stream) {
   g_prof_on = on != 0;

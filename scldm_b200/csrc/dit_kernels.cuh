@@ -34,6 +34,7 @@ constexpr int B_SLAB_BYTES = BLOCK_N * BLOCK_K * 2;    // 32768
 constexpr int A_SLAB_ELEMS = BLOCK_M * BLOCK_K;
 constexpr int B_SLAB_ELEMS = BLOCK_N * BLOCK_K;
 constexpr int STG_BYTES = 128 * 272;                   // epilogue staging (fp32 64-col chunk, 16 B row pad)
+constexpr int STG_ARES_BYTES = 4 * A_SLAB_BYTES;       // A-resident kernel: 2 x (two 16 KB slabs), double buffered
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;            // 512
 constexpr int NUM_THREADS = 64 + EPI_THREADS;          // warp0 TMA, warp1 MMA, warps 2-17 prologue/epilogue
@@ -60,11 +61,12 @@ struct AResParams {
   int tiles_per_cta;
   const float* bias;     // [n_tiles_total*256] fp32 (EPI_QKV / EPI_MOD) or nullptr
   // ---- output ---------------------------------------------------------------------------
-  bf16* out_bf16;        // EPI_QKV : [rows_pad][out_ld] bf16 row-major
+  bf16* out_bf16;        // EPI_QKV : packed [row_tiles][out_ld/64 slabs][128 x 64 swizzled] bf16
   float* out_f32;        // EPI_MOD : [rows_pad][out_ld] fp32 row-major
   int out_ld;
   bf16* out_packed;      // EPI_SWIGLU: [row_tiles][out_slabs][128 x 64 swizzled]
   int out_slabs;
+  long long* dbg;        // optional per-CTA phase timestamps (clock64), nullptr in production
 };
 
 struct AStreamParams {
@@ -77,11 +79,17 @@ struct AStreamParams {
   const int* slot_mod;
   int mod_stride;
   int mod_off_gate;
+  long long* dbg;
 };
 
 // ==========================================================================================
 // shared pipeline pieces
 // ==========================================================================================
+// debug timeline: slot i of CTA b lives at dbg[b*32 + i]
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int slot) {
+  if (dbg != nullptr) dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 + slot] = clock64();
+}
+
 struct RingState {
   uint32_t stage = 0, phase = 0;
   __device__ __forceinline__ void advance(uint32_t nstages) {
@@ -116,8 +124,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                                     // 4 x 16 KB
   uint8_t* smB = smem + KSLABS_D * A_SLAB_BYTES;           // NSTAGE x 32 KB
-  uint8_t* smStg = smB + NSTAGE * B_SLAB_BYTES;            // 34 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smStg + STG_BYTES);
+  uint8_t* smStg = smB + NSTAGE * B_SLAB_BYTES;            // 64 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smStg + STG_ARES_BYTES);
   uint64_t* full = bars;                 // [NSTAGE]
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
   uint64_t* tmem_full = bars + 2 * NSTAGE;   // [2]
@@ -130,6 +138,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
   const int row_tile = blockIdx.x;
   const int tile0 = blockIdx.y * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.n_tiles_total - tile0);
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 0);
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < NSTAGE; ++i) {
@@ -167,8 +176,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
     // ===================== MMA issuer (single thread) ====================================
     if (lane == 0) {
       const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
+      dbg_stamp(p.dbg, 1);
       sm100::mbar_wait(a_ready, 0);
       sm100::tc_fence_after();
+      dbg_stamp(p.dbg, 2);
       RingState rs;
       for (int t = 0; t < ntiles; ++t) {
         const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
     sm100::fence_proxy_async_smem();   // generic-proxy smem writes -> visible to UMMA
     __syncwarp();
     if (lane == 0) sm100::mbar_arrive(a_ready);
+    if (etid == 0) dbg_stamp(p.dbg, 3);
 
     // ---------- epilogue over this CTA's N tiles ----------
     const uint32_t row = q * 32 + lane;                       // accumulator row == TMEM lane
@@ -258,24 +270,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
       const int tile = tile0 + t;
       sm100::mbar_wait(&tmem_full[acc], acc_phase);
       sm100::tc_fence_after();
+      if (etid == 0 && t < 12) dbg_stamp(p.dbg, 4 + 2 * t);
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BLOCK_N;
 
       if constexpr (EPI == EPI_QKV) {
         // 2 chunks of 128 columns; this warp: 32 columns [32*sub, +32) of the chunk.
-        // acc + bias -> bf16 -> two swizzled [128][64] staging slabs -> coalesced row-major store
+        // acc + bias -> bf16 -> two swizzled [128][64] slabs in (double-buffered) staging -> two 16 KB bulk stores into
+        // the packed activation layout [row_tile][768/64 slabs][128 x 64 swizzled] that attn16_kernel reads.
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
-          sm100::named_bar_sync(1, EPI_THREADS);  // staging free
+          const int par = (t * 2 + ch) & 1;
+          uint8_t* stg = smStg + par * 2 * A_SLAB_BYTES;
+          const float* bp = p.bias + tile * BLOCK_N + ch * 128 + sub * 32;
+          float4 bb[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) bb[c] = *reinterpret_cast<const float4*>(bp + c * 4);
+          if (etid == 0) sm100::bulk_wait_read<1>();   // the stores issued two chunks ago have drained this buffer
+          sm100::named_bar_sync(1, EPI_THREADS);
           {
             uint32_t v[32];
             sm100::tmem_ld_32x32b_x32(taddr + ch * 128 + sub * 32, v);
             sm100::tmem_ld_wait();
-            const float* bp = p.bias + tile * BLOCK_N + ch * 128 + sub * 32;
-            uint8_t* slab = smStg + (sub >> 1) * A_SLAB_BYTES;
+            uint8_t* slab = stg + (sub >> 1) * A_SLAB_BYTES;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bp + c * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bp + c * 8 + 4);
+              const float4 b0 = bb[2 * c];
+              const float4 b1 = bb[2 * c + 1];
               uint4 o;
               o.x = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y);
               o.y = sm100::pack_bf16x2(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w);
@@ -284,14 +304,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
               *reinterpret_cast<uint4*>(slab + sm100::swz_chunk_offset(row, (sub & 1) * 4 + c)) = o;
             }
           }
-          sm100::named_bar_sync(1, EPI_THREADS);  // staging full
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const uint32_t idx = it * EPI_THREADS + etid;
-            const uint32_t r = idx >> 4, c16 = idx & 15;  // 16 x 16 B per 256 B row segment
-            const uint4 o = *reinterpret_cast<const uint4*>(smStg + (c16 >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, c16 & 7));
-            bf16* dst = p.out_bf16 + ((size_t)row_tile * BLOCK_M + r) * p.out_ld + tile * BLOCK_N + ch * 128 + c16 * 8;
-            *reinterpret_cast<uint4*>(dst) = o;
+          if (ch == 1) {  // both halves of the accumulator have been read
+            sm100::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
+          }
+          sm100::fence_proxy_async_smem();
+          sm100::named_bar_sync(1, EPI_THREADS);
+          if (etid == 0) {
+            const size_t slab0 = (size_t)row_tile * (p.out_ld / BLOCK_K) + (size_t)tile * 4 + ch * 2;
+            sm100::bulk_s2g(p.out_bf16 + slab0 * A_SLAB_ELEMS, stg, 2 * A_SLAB_BYTES);  // two consecutive slabs
+            sm100::bulk_commit();
           }
         }
       } else if constexpr (EPI == EPI_MOD) {
@@ -330,20 +353,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
         // -> two 64-wide hidden slabs written as swizzled A slabs and bulk-stored (16 KB contiguous each).
         // this warp: slab hs = sub/2, 32 hidden columns h = sub%2
         const int hs = sub >> 1, h = sub & 1;
-        if (etid == 0) sm100::bulk_wait_read<0>();  // previous tile's stores have drained the staging slabs
+        uint8_t* stg = smStg + (t & 1) * 2 * A_SLAB_BYTES;  // double buffered: tile t-2's bulk stores must have drained
+        if (etid == 0) sm100::bulk_wait_read<1>();
         sm100::named_bar_sync(1, EPI_THREADS);
         if (tile * 2 + hs < p.out_slabs) {
           uint32_t va[32], vb[32];
           sm100::tmem_ld_32x32b_x32(taddr + hs * 64 + h * 32, va);
           sm100::tmem_ld_32x32b_x32(taddr + 128 + hs * 64 + h * 32, vb);
           sm100::tmem_ld_wait();
-          uint8_t* buf = smStg + hs * A_SLAB_BYTES;
+          uint8_t* buf = stg + hs * A_SLAB_BYTES;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float hv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              hv[j] = sm100::silu(__uint_as_float(va[c * 8 + j])) * __uint_as_float(vb[c * 8 + j]);
+              hv[j] = sm100::silu_tanh(__uint_as_float(va[c * 8 + j])) * __uint_as_float(vb[c * 8 + j]);
             uint4 o;
             o.x = sm100::pack_bf16x2(hv[0], hv[1]);
             o.y = sm100::pack_bf16x2(hv[2], hv[3]);
@@ -352,6 +376,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
             *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, h * 4 + c)) = o;
           }
         }
+        // TMEM has been read: release the accumulator to the MMA warp before the store handshake
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
         sm100::fence_proxy_async_smem();
         sm100::named_bar_sync(1, EPI_THREADS);
         if (etid == 0) {
@@ -359,18 +387,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
           for (int s2 = 0; s2 < 2; ++s2) {
             const int slab = tile * 2 + s2;
             if (slab < p.out_slabs)
-              sm100::bulk_s2g(p.out_packed + ((size_t)row_tile * p.out_slabs + slab) * A_SLAB_ELEMS, smStg + s2 * A_SLAB_BYTES,
+              sm100::bulk_s2g(p.out_packed + ((size_t)row_tile * p.out_slabs + slab) * A_SLAB_ELEMS, stg + s2 * A_SLAB_BYTES,
                               A_SLAB_BYTES);
           }
           sm100::bulk_commit();
         }
       }
-      // accumulator drained -> MMA warp may overwrite it
-      sm100::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
+      // accumulator drained -> MMA warp may overwrite it (the SwiGLU path released it right after its TMEM reads)
+      if constexpr (EPI == EPI_MOD) {
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
+      }
+      if (etid == 0 && t < 12) dbg_stamp(p.dbg, 5 + 2 * t);
     }
-    if constexpr (EPI == EPI_SWIGLU) {
+    if constexpr (EPI != EPI_MOD) {
       if (etid == 0) sm100::bulk_wait<0>();
     }
   }
@@ -378,10 +409,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
   sm100::tc_fence_before();
   __syncthreads();
   if (warp == 1) sm100::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 31);
 }
 
 constexpr size_t ares_smem_bytes() {
-  return 1024 + KSLABS_D * A_SLAB_BYTES + 3 * B_SLAB_BYTES + STG_BYTES + 256;
+  return 1024 + KSLABS_D * A_SLAB_BYTES + 3 * B_SLAB_BYTES + STG_ARES_BYTES + 256;
 }
 
 // ==========================================================================================
@@ -395,7 +427,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smStage = smem;                              // NSTAGE x (A 16 KB | B 32 KB)
   uint8_t* smStg = smem + NSTAGE * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smStg + STG_BYTES);
+  float* smGate = reinterpret_cast<float*>(smStg + STG_BYTES);   // [8 cells][256]
+  float* smBias = smGate + 8 * D;                                // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smBias + D);
   uint64_t* full = bars;
   uint64_t* empty = bars + NSTAGE;
   uint64_t* tmem_full = bars + 2 * NSTAGE;
@@ -404,6 +438,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const int row_tile = blockIdx.x;
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 0);
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < NSTAGE; ++i) {
@@ -436,9 +471,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
     if (lane == 0) {
       const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
       RingState rs;
+      dbg_stamp(p.dbg, 1);
       for (int ks = 0; ks < p.k_slabs; ++ks) {
         sm100::mbar_wait(&full[rs.stage], rs.phase);
         sm100::tc_fence_after();
+        if (ks == 0) dbg_stamp(p.dbg, 2);
         const uint32_t st = sm100::smem_u32(smStage + rs.stage * STAGE_BYTES);
         issue_slab_mmas(tmem_base, st, st + A_SLAB_BYTES, idesc, ks == 0);
         sm100::umma_commit(&empty[rs.stage]);
@@ -452,54 +489,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
     const uint32_t sub = ew >> 2;
     const uint32_t etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
-    // operands of the read-modify-write pass that do not depend on the accumulator: fetch while the MMAs run
-    // thread handles items idx = it*512 + etid -> (row r = idx/16, float4 column c = idx%16) of each 64-column chunk
+    // while the MMAs run: stage the 8 cells' gate vectors (8 x 256 fp32) and the bias in shared memory, and start
+    // fetching the residual rows.  thread -> items idx = it*512 + etid -> (row r = idx/16, float4 column cc) per chunk
     const uint32_t cc = etid & 15;
-    int mrow[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const uint32_t r = (it * EPI_THREADS + etid) >> 4;
-      mrow[it] = p.slot_mod[row_tile * 8 + (r >> 4)];
+    {
+      // 8 cells x 64 float4 = 512 float4: one per thread
+      const int cell = etid >> 6, c4 = etid & 63;
+      const int mr = p.slot_mod[row_tile * 8 + cell];
+      reinterpret_cast<float4*>(smGate)[etid] =
+          *reinterpret_cast<const float4*>(p.mod + (size_t)mr * p.mod_stride + p.mod_off_gate + c4 * 4);
+      if (etid < 64)
+        reinterpret_cast<float4*>(smBias)[etid] =
+            p.bias != nullptr ? *reinterpret_cast<const float4*>(p.bias + etid * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    sm100::mbar_wait(tmem_full, 0);
-    sm100::tc_fence_after();
-    const uint32_t taddr = tmem_base + ((q * 32u) << 16);
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      const int col = ch * 64 + cc * 4;
-      // issue the global loads of this chunk early (gate, residual, bias)
-      float4 g[4], x[4];
+    if (etid == 0) dbg_stamp(p.dbg, 3);
+    float4 x[2][4];
+    auto load_chunk = [&](int ch, int buf) {
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const uint32_t r = (it * EPI_THREADS + etid) >> 4;
-        g[it] = *reinterpret_cast<const float4*>(p.mod + (size_t)mrow[it] * p.mod_stride + p.mod_off_gate + col);
-        x[it] = *reinterpret_cast<const float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + col);
+        x[buf][it] = *reinterpret_cast<const float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + ch * 64 + cc * 4);
       }
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias != nullptr) b = *reinterpret_cast<const float4*>(p.bias + col);
-      sm100::named_bar_sync(1, EPI_THREADS);   // staging free
+    };
+    load_chunk(0, 0);
+    sm100::mbar_wait(tmem_full, 0);
+    sm100::tc_fence_after();
+    if (etid == 0) dbg_stamp(p.dbg, 4);
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      if (etid == 0) dbg_stamp(p.dbg, 5 + ch);
+      const int col = ch * 64 + cc * 4;
+      if (ch + 1 < 4) load_chunk(ch + 1, (ch + 1) & 1);
+      sm100::named_bar_sync(1, EPI_THREADS);   // staging free (and, for ch = 0, gate/bias staged)
       {
         uint32_t v[16];
         sm100::tmem_ld_32x32b_x16(taddr + ch * 64 + sub * 16, v);
         sm100::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float4 o;
-          o.x = __uint_as_float(v[c * 4 + 0]);
-          o.y = __uint_as_float(v[c * 4 + 1]);
-          o.z = __uint_as_float(v[c * 4 + 2]);
-          o.w = __uint_as_float(v[c * 4 + 3]);
-          *reinterpret_cast<float4*>(smStg + row * 272 + (sub * 4 + c) * 16) = o;
-        }
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(smStg + row * 272 + (sub * 4 + c) * 16) = make_float4(
+              __uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
       }
       sm100::named_bar_sync(1, EPI_THREADS);   // staging full
+      const float4 bb = *reinterpret_cast<const float4*>(smBias + col);
       // coalesced read-modify-write of the residual stream: 2 rows x 256 B per warp instruction
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const uint32_t r = (it * EPI_THREADS + etid) >> 4;
         const float4 a = *reinterpret_cast<const float4*>(smStg + r * 272 + cc * 16);
-        float4 o = x[it];
-        o.x += g[it].x * (a.x + b.x); o.y += g[it].y * (a.y + b.y); o.z += g[it].z * (a.z + b.z); o.w += g[it].w * (a.w + b.w);
+        const float4 gg = *reinterpret_cast<const float4*>(smGate + (r >> 4) * D + col);
+        float4 o = x[ch & 1][it];
+        o.x += gg.x * (a.x + bb.x); o.y += gg.y * (a.y + bb.y);
+        o.z += gg.z * (a.z + bb.z); o.w += gg.w * (a.w + bb.w);
         *reinterpret_cast<float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + col) = o;
       }
     }
@@ -508,13 +550,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
   sm100::tc_fence_before();
   __syncthreads();
   if (warp == 1) sm100::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 31);
 }
 
-constexpr size_t astream_smem_bytes() { return 1024 + 3 * (A_SLAB_BYTES + B_SLAB_BYTES) + STG_BYTES + 256; }
+constexpr size_t astream_smem_bytes() { return 1024 + 3 * (A_SLAB_BYTES + B_SLAB_BYTES) + STG_BYTES + 9 * D * 4 + 256; }
 
 // ==========================================================================================
 // 16-token self attention, one warp per (slot, head), tensor cores via mma.sync m16n8k16 (bf16)
-//   qkv: [rows_pad][768] bf16 row-major (q | k | v, heads = contiguous 32-channel groups; layers.py:147-151)
+//   qkv: packed [row_tiles][12 slabs][128 x 64 swizzled] bf16; logical columns q | k | v, heads = contiguous
+//        32-channel groups (layers.py:147-151)
 //   out: swizzled A tiles [row_tiles][4 slabs][128 x 64] bf16 (A operand of the c_proj GEMM)
 // ==========================================================================================
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -535,9 +579,13 @@ __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qk
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t g = lane >> 2, t = lane & 3;
   if (slot >= n_slots) return;
-  const bf16* base = qkv + (size_t)slot * TOK * (3 * D) + head * HD;
+  const size_t row0 = (size_t)slot * TOK;                 // first token row of this slot
+  const uint8_t* tile_base = reinterpret_cast<const uint8_t*>(qkv + (row0 >> 7) * (3 * D / BLOCK_K) * A_SLAB_ELEMS);
+  const uint32_t rbase = row0 & 127;
   auto ld2 = [&](int token, int part, int dim) -> uint32_t {
-    return *reinterpret_cast<const uint32_t*>(base + (size_t)token * (3 * D) + part * D + dim);
+    const uint32_t col = part * D + head * HD + dim, r = rbase + token;
+    return *reinterpret_cast<const uint32_t*>(tile_base + (size_t)(col >> 6) * A_SLAB_BYTES +
+                                              sm100::swz_chunk_offset(r, (col & 63) >> 3) + (col & 7) * 2);
   };
   // S = Q K^T : A = Q (16 tokens x 32 dims) in two k-steps; B[k=dim][n=key] = K[key][dim]
   float s[2][4] = {};
@@ -717,22 +765,21 @@ __global__ void __launch_bounds__(256) inproj_kernel(const StepParams p) {
 // final layer (layers.py:397-401: LN(x)*(1+scale)+shift with shift = chunk 0, scale = chunk 1; Linear 256->16)
 // + CFG combine + ODE stage update + input projection of the next evaluation point.
 // One block per state, 8 warps, each warp handles 2 tokens.
-__global__ void __launch_bounds__(256) final_step_kernel(const StepParams p) {
-  __shared__ float s_wout[LAT * D];   // 16 KB
-  __shared__ float s_win[D * LAT];    // 16 KB
-  const int state = blockIdx.x;
+__global__ void __launch_bounds__(512) final_step_kernel(const StepParams p, int n_states) {
+  __shared__ float s_wout[LAT * D];   // 16 KB  [o][d]
+  __shared__ float s_win[LAT * D];    // 16 KB  transposed to [o][d] (w_in is [d][o]): conflict-free float4 reads
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < LAT * D; i += 256) {
+  for (int i = threadIdx.x; i < LAT * D; i += 512) {
     s_wout[i] = p.w_out[i];
-    s_win[i] = p.w_in[i];
+    s_win[(i & (LAT - 1)) * D + (i >> 4)] = p.w_in[i];
   }
   __syncthreads();
-  int slot0, ns;
-  state_slots(p, state, slot0, ns);
   const float inv_d = 1.0f / D;
+  const int tk = warp;  // one warp per (state, token); the weight tiles are loaded into shared memory once per CTA
 #pragma unroll 1
-  for (int ti = 0; ti < 2; ++ti) {
-    const int tk = warp * 2 + ti;
+  for (int state = blockIdx.x; state < n_states; state += gridDim.x) {
+    int slot0, ns;
+    state_slots(p, state, slot0, ns);
     float vsum = 0.f;  // lane o (<16) accumulates combined output channel o
 #pragma unroll 1
     for (int k = 0; k < ns; ++k) {
@@ -740,7 +787,12 @@ __global__ void __launch_bounds__(256) final_step_kernel(const StepParams p) {
       const float* xr = p.X + ((size_t)slot * TOK + tk) * D + lane * 8;
       const float4 x0 = *reinterpret_cast<const float4*>(xr);
       const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+      const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride + p.mod_off_final + lane * 8;
+      const float4 sh0 = *reinterpret_cast<const float4*>(mrow), sh1 = *reinterpret_cast<const float4*>(mrow + 4);
+      const float4 sc0 = *reinterpret_cast<const float4*>(mrow + D), sc1 = *reinterpret_cast<const float4*>(mrow + D + 4);
       float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const float shift[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+      const float scale[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[j];
@@ -749,21 +801,29 @@ __global__ void __launch_bounds__(256) final_step_kernel(const StepParams p) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { v[j] -= mean; ss += v[j] * v[j]; }
       const float rstd = rsqrtf(sm100::warp_sum(ss) * inv_d + p.eps);
-      const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride + p.mod_off_final;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float shift = mrow[lane * 8 + j], scale = mrow[D + lane * 8 + j];
-        v[j] = v[j] * rstd * (1.f + scale) + shift;
-      }
-      float mine = 0.f;
-#pragma unroll 4
+      for (int j = 0; j < 8; ++j) v[j] = v[j] * rstd * (1.f + scale[j]) + shift[j];
+      // 16 partial dot products per lane, then a reduce-scatter butterfly (16 shuffles instead of 16 x 5)
+      float part[LAT];
+#pragma unroll
       for (int o = 0; o < LAT; ++o) {
-        float part = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) part += v[j] * s_wout[o * D + lane * 8 + j];
-        part = sm100::warp_sum(part);
-        if ((int)lane == o) mine = part;
+        const float4 w0 = *reinterpret_cast<const float4*>(s_wout + o * D + lane * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_wout + o * D + lane * 8 + 4);
+        part[o] = v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
       }
+#pragma unroll
+      for (int width = 8, off = 16; width >= 1; width >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < width; ++i) {
+          const float send = hi ? part[i] : part[i + width];
+          const float keep = hi ? part[i + width] : part[i];
+          part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      // lanes 2o and 2o+1 now hold the two halves of output o
+      float full = part[0] + __shfl_xor_sync(0xffffffffu, part[0], 1);
+      float mine = __shfl_sync(0xffffffffu, full, (lane & 15) * 2);
       if (lane < LAT) mine += (p.b_out ? p.b_out[lane] : 0.f);
       const float coef = (ns == 1) ? 1.0f : p.coef[k];
       vsum += coef * mine;
@@ -793,8 +853,10 @@ __global__ void __launch_bounds__(256) final_step_kernel(const StepParams p) {
 #pragma unroll
       for (int o = 0; o < LAT; ++o) {
         const float xo = __shfl_sync(0xffffffffu, x_eval, o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] += xo * s_win[(lane * 8 + j) * LAT + o];
+        const float4 w0 = *reinterpret_cast<const float4*>(s_win + o * D + lane * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_win + o * D + lane * 8 + 4);
+        h[0] += xo * w0.x; h[1] += xo * w0.y; h[2] += xo * w0.z; h[3] += xo * w0.w;
+        h[4] += xo * w1.x; h[5] += xo * w1.y; h[6] += xo * w1.z; h[7] += xo * w1.w;
       }
       for (int k = 0; k < ns; ++k) {
         float* dst = p.X + ((size_t)(slot0 + k) * TOK + tk) * D + lane * 8;

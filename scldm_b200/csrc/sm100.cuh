@@ -210,6 +210,15 @@ __device__ __forceinline__ float warp_max(float v) {
 // x * sigmoid(x) with the fast exp2/rcp SFU paths (rel. error ~1e-6, far below the bf16 rounding that follows)
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// SiLU with ONE SFU op per element: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx: max rel. error 2^-11).
+// Used only where the result is rounded to bf16 right away (SwiGLU epilogue), where the SFU pipe is the limiter.
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

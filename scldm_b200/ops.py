@@ -131,7 +131,7 @@ def dit_workspace_views(plan: DitPlan, ws: torch.Tensor, n_evals: int = 0) -> di
 
     return {
         "X": view(o["X"], rows * 256 * 4, torch.float32, (rows, 256)),
-        "qkv": view(o["qkv"], rows * 768 * 2, torch.bfloat16, (rows, 768)),
+        "qkv": view(o["qkv"], rows * 768 * 2, torch.bfloat16, (rows // 128, 12, 128 * 64)),
         "ao": view(o["ao"], rows * 256 * 2, torch.bfloat16, (rows // 128, 4, 128 * 64)),
         "hid": view(o["hid"], (rows // 128) * w.hid_slabs * 16384, torch.bfloat16, (rows // 128, w.hid_slabs, 128 * 64)),
         "mod": view(o["mod"], plan.mod_pad * w.mod_stride * 4, torch.float32, (plan.mod_pad, w.mod_stride)),
