@@ -116,19 +116,26 @@ typedef struct scldm_vae_dec_weights {
   const float* mcab_blob;  /* c_proj | ln_2 | mlp.w1 | mlp.w2 | mlp.c_proj^T | head w | head b */
   const float* emb;        /* input_layer.gene_embedding.weight [n_ids][32]                   */
   const float* theta_tbl;  /* decoder_head.theta.weight [n_ids]                               */
+  const void* mcab_wfrag;  /* bf16 MCAB weights in mma.sync B-fragment order (80 x 64 u32)    */
+  const float* mcab_small; /* ln_2.weight[32] | ln_2.bias[32] | head w[32] | head b           */
 } scldm_vae_dec_weights;
 
-/* Cell-invariant query side of the decoder MCAB: qp[g] = c_attn_q(ln_1q(emb[g])) (layers.py:253,326). */
-int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* stream);
+#define SCLDM_DECODE_TC 0   /* MCAB on tensor cores (bf16 operands, fp32 accumulate): default   */
+#define SCLDM_DECODE_FP32 1 /* MCAB in fp32 on CUDA cores (exact variant)                       */
+
+/* Cell-invariant query side of the decoder MCAB: qp[g] = c_attn_q(ln_1q(emb[g])) (layers.py:253,326).
+ * qp [n_ids][32] fp32 and qp_bf16 [n_ids][32] bf16 (either may be NULL).                              */
+int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* qp_bf16, void* stream);
 
 size_t scldm_vae_decode_workspace_bytes(int32_t n_cells, int32_t n_genes);
 
 /* Replaces TransformerVAE.decode (vae.py:71-87) [+ NegativeBinomial.sample, models.py:819].
  *   z [n_cells][16][16]; genes [n_genes] int64 vocabulary ids shared by all cells; lib [n_cells]
  *   mu [n_cells][n_genes] / theta [n_genes] / counts [n_cells][n_genes]: any may be NULL           */
-int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const float* z, int32_t n_cells,
+int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void* qp_bf16, const float* z, int32_t n_cells,
                      const int64_t* genes, int32_t n_genes, const float* lib, float* mu, float* theta, float* counts,
-                     uint64_t seed, int64_t cell_offset, void* workspace, size_t workspace_bytes, void* stream);
+                     uint64_t seed, int64_t cell_offset, int32_t precision, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* N(0,1) draws keyed by (seed, global cell index, element): latent noise (models.py:788) and the
  * size-factor normals (models.py:585-596).                                                        */

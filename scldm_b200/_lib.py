@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libs
 MAX_CLASSES = 8
 MAX_COMBINE = 8
 ODE_METHODS = {"euler": 0, "heun2": 1, "midpoint": 2}
+DECODE_PRECISION = {"bf16": 0, "fp32": 1}
 
 EXPORTS = [
     "scldm_dit_slots_pad", "scldm_dit_mod_pad", "scldm_dit_workspace_bytes", "scldm_dit_workspace_layout",
@@ -45,6 +46,7 @@ class VaeDecWeights(C.Structure):
         ("win_t", C.c_void_p), ("blocks", C.c_void_p), ("ca_ln1_w", C.c_void_p), ("ca_ln1_b", C.c_void_p),
         ("ca_wkv_t", C.c_void_p), ("ca_ln1q_w", C.c_void_p), ("ca_ln1q_b", C.c_void_p), ("ca_wq", C.c_void_p),
         ("mcab_blob", C.c_void_p), ("emb", C.c_void_p), ("theta_tbl", C.c_void_p),
+        ("mcab_wfrag", C.c_void_p), ("mcab_small", C.c_void_p),
     ]
 
 
@@ -76,12 +78,13 @@ def load() -> C.CDLL:
     lib.scldm_dit_sample_ode.argtypes = [P(DitWeights), P(DitPlan), C.c_void_p, P(C.c_float), C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_size_t, C.c_void_p]
     lib.scldm_dit_sample_ode.restype = C.c_int
-    lib.scldm_vae_qside.argtypes = [P(VaeDecWeights), C.c_void_p, C.c_void_p]
+    lib.scldm_vae_qside.argtypes = [P(VaeDecWeights), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scldm_vae_qside.restype = C.c_int
     lib.scldm_vae_decode_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.scldm_vae_decode_workspace_bytes.restype = C.c_size_t
-    lib.scldm_vae_decode.argtypes = [P(VaeDecWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_vae_decode.argtypes = [P(VaeDecWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]
     lib.scldm_vae_decode.restype = C.c_int
     lib.scldm_randn_cells.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]
     lib.scldm_randn_cells.restype = C.c_int

@@ -352,23 +352,26 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
   return SCLDM_OK;
 }
 
-int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* stream) {
-  if (!w || !qp) return fail(SCLDM_EINVAL, "null argument");
+int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* qp_bf16, void* stream) {
+  if (!w || (!qp && !qp_bf16)) return fail(SCLDM_EINVAL, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH("qside", vae::qside_kernel<<<ceil_div(w->n_ids, 128), 128, 0, st>>>(w->emb, w->ca_ln1q_w, w->ca_ln1q_b, w->ca_wq, w->eps, w->n_ids, qp));
+  LAUNCH("qside", vae::qside_kernel<<<ceil_div(w->n_ids, 128), 128, 0, st>>>(w->emb, w->ca_ln1q_w, w->ca_ln1q_b, w->ca_wq, w->eps, w->n_ids, qp, static_cast<__nv_bfloat16*>(qp_bf16)));
   return SCLDM_OK;
 }
 
 size_t scldm_vae_decode_workspace_bytes(int32_t n_cells, int32_t n_genes) {
   const size_t tiles = ceil_div(n_genes, 128);
   return align_up((size_t)n_cells * vae::TOK * vae::KV * 4, 1024) + align_up((size_t)n_cells * n_genes * 4, 1024) +
-         align_up((size_t)n_cells * tiles * 8, 1024) + 1024;
+         align_up((size_t)n_cells * tiles * 8, 1024) + align_up((size_t)n_cells * 1024 * 2, 1024) + 1024;
 }
 
-int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const float* z, int32_t n_cells, const int64_t* genes,
-                     int32_t n_genes, const float* lib, float* mu, float* theta, float* counts, uint64_t seed, int64_t cell_offset,
-                     void* workspace, size_t workspace_bytes, void* stream) {
-  if (!w || !qp || !z || !genes || !lib || !workspace) return fail(SCLDM_EINVAL, "null argument");
+int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void* qp_bf16, const float* z, int32_t n_cells,
+                     const int64_t* genes, int32_t n_genes, const float* lib, float* mu, float* theta, float* counts, uint64_t seed,
+                     int64_t cell_offset, int32_t precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w || !z || !genes || !lib || !workspace) return fail(SCLDM_EINVAL, "null argument");
+  if (precision != SCLDM_DECODE_TC && precision != SCLDM_DECODE_FP32) return fail(SCLDM_EINVAL, "bad precision %d", precision);
+  if (precision == SCLDM_DECODE_TC && (!qp_bf16 || !w->mcab_wfrag || !w->mcab_small)) return fail(SCLDM_EINVAL, "tensor-core decode needs qp_bf16 + fragment weights");
+  if (precision == SCLDM_DECODE_FP32 && !qp) return fail(SCLDM_EINVAL, "fp32 decode needs the fp32 Q-side table");
   if (n_cells < 1 || n_genes < 1) return fail(SCLDM_EINVAL, "empty decode: n_cells=%d n_genes=%d", n_cells, n_genes);
   if (workspace_bytes < scldm_vae_decode_workspace_bytes(n_cells, n_genes)) return fail(SCLDM_ENOMEM, "workspace too small");
   int rc;
@@ -381,22 +384,35 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const floa
   float* logits_ws = reinterpret_cast<float*>(b);
   b += align_up((size_t)n_cells * n_genes * 4, 1024);
   float2* partials = reinterpret_cast<float2*>(b);
+  b += align_up((size_t)n_cells * tiles * 8, 1024);
+  __nv_bfloat16* kvb = reinterpret_cast<__nv_bfloat16*>(b);
   float* logits = mu ? mu : logits_ws;  // finalised in place when mu is requested
+  const bool tc = precision == SCLDM_DECODE_TC;
 
   vae::DecLatentParams dp{};
   dp.z = z; dp.win_t = w->win_t; dp.blocks = w->blocks; dp.n_layer = w->n_layer;
-  dp.ca_ln1_w = w->ca_ln1_w; dp.ca_ln1_b = w->ca_ln1_b; dp.ca_wkv_t = w->ca_wkv_t; dp.eps = w->eps; dp.kv = kv;
+  dp.ca_ln1_w = w->ca_ln1_w; dp.ca_ln1_b = w->ca_ln1_b; dp.ca_wkv_t = w->ca_wkv_t; dp.eps = w->eps;
+  dp.kv = tc ? nullptr : kv; dp.kvb = tc ? kvb : nullptr;
   LAUNCH("dec_latent", vae::dec_latent_kernel<<<n_cells, 128, 0, st>>>(dp, n_cells));
 
-  vae::McabParams mp{};
-  mp.emb = w->emb; mp.qp = qp; mp.genes = reinterpret_cast<const long long*>(genes); mp.G = n_genes; mp.kv = kv; mp.n_cells = n_cells;
   // enough blocks for ~4 waves, but amortise the gene-side loads over several cells
   int cpb = (int)(((long long)tiles * n_cells) / (148LL * 2 * 4));
   if (cpb < 1) cpb = 1;
   if (cpb > 32) cpb = 32;
-  mp.cells_per_block = cpb;
-  mp.wblob = w->mcab_blob; mp.eps = w->eps; mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
-  LAUNCH("mcab_decode", vae::mcab_decode_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 128, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float), st>>>(mp));
+  if (tc) {
+    vae::McabTcParams mp{};
+    mp.emb = w->emb; mp.qp = static_cast<const __nv_bfloat16*>(qp_bf16); mp.genes = reinterpret_cast<const long long*>(genes);
+    mp.G = n_genes; mp.kvb = kvb; mp.n_cells = n_cells; mp.cells_per_block = cpb;
+    mp.wfrag = static_cast<const uint32_t*>(w->mcab_wfrag); mp.small = w->mcab_small; mp.eps = w->eps;
+    mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
+    LAUNCH("mcab_decode_tc", vae::mcab_decode_tc_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 256, 0, st>>>(mp));
+  } else {
+    vae::McabParams mp{};
+    mp.emb = w->emb; mp.qp = qp; mp.genes = reinterpret_cast<const long long*>(genes); mp.G = n_genes; mp.kv = kv; mp.n_cells = n_cells;
+    mp.cells_per_block = cpb;
+    mp.wblob = w->mcab_blob; mp.eps = w->eps; mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
+    LAUNCH("mcab_decode", vae::mcab_decode_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 128, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float), st>>>(mp));
+  }
 
   vae::NbParams np{};
   np.logits = logits; np.partials = partials; np.gene_tiles = tiles; np.G = n_genes; np.n_cells = n_cells; np.lib = lib;

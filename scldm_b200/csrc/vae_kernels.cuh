@@ -42,7 +42,8 @@ struct DecLatentParams {
   const float* ca_ln1_w; const float* ca_ln1_b;
   const float* ca_wkv_t; // [32][64]  (k | v)
   float eps;
-  float* kv;             // [cells][16][64]
+  float* kv;             // [cells][16][64] fp32 (k | v), or nullptr
+  __nv_bfloat16* kvb;    // [cells][ K: 16x32 | V^T: 32x16 ] bf16 for the tensor-core MCAB kernel, or nullptr
 };
 
 constexpr int BLK_LN1W = 0, BLK_LN1B = 32, BLK_LN2W = 64, BLK_LN2B = 96, BLK_WQKV = 128, BLK_WPROJ = BLK_WQKV + 32 * 96,
@@ -184,14 +185,19 @@ __global__ void __launch_bounds__(128) dec_latent_kernel(const DecLatentParams p
     float acc = 0.f;
 #pragma unroll 8
     for (int k = 0; k < E; ++k) acc += h[tok][k] * p.ca_wkv_t[k * KV + j];
-    p.kv[(size_t)cell * TOK * KV + i] = acc;
+    if (p.kv) p.kv[(size_t)cell * TOK * KV + i] = acc;
+    if (p.kvb) {
+      if (j < E) p.kvb[(size_t)cell * 1024 + tok * E + j] = __float2bfloat16(acc);
+      else p.kvb[(size_t)cell * 1024 + 512 + (j - E) * TOK + tok] = __float2bfloat16(acc);
+    }
   }
 }
 
 // Qp[g] = Wq * LN1q(emb[g]) for every vocabulary id (incl. the mask id 0)
 __global__ void __launch_bounds__(128) qside_kernel(const float* __restrict__ emb, const float* __restrict__ ln_w,
                                                      const float* __restrict__ ln_b, const float* __restrict__ wq /*[out][in]*/,
-                                                     float eps, int n_ids, float* __restrict__ qp) {
+                                                     float eps, int n_ids, float* __restrict__ qp,
+                                                     __nv_bfloat16* __restrict__ qp_bf16) {
   __shared__ float s_wq[E * E];
   for (int i = threadIdx.x; i < E * E; i += 128) s_wq[i] = wq[i];
   __syncthreads();
@@ -222,7 +228,13 @@ __global__ void __launch_bounds__(128) qside_kernel(const float* __restrict__ em
       for (int c = 0; c < E; ++c) acc += v[c] * s_wq[(j + jj) * E + c];
       o[jj] = acc;
     }
-    *reinterpret_cast<float4*>(qp + (size_t)g * E + j) = make_float4(o[0], o[1], o[2], o[3]);
+    if (qp) *reinterpret_cast<float4*>(qp + (size_t)g * E + j) = make_float4(o[0], o[1], o[2], o[3]);
+    if (qp_bf16) {
+      uint2 pk;
+      pk.x = sm100::pack_bf16x2(o[0], o[1]);
+      pk.y = sm100::pack_bf16x2(o[2], o[3]);
+      *reinterpret_cast<uint2*>(qp_bf16 + (size_t)g * E + j) = pk;
+    }
   }
 }
 
@@ -363,6 +375,223 @@ __global__ void __launch_bounds__(128) mcab_decode_kernel(const McabParams p) {
     if ((tid & 31) == 0) red_s[tid >> 5] = ws;
     __syncthreads();
     if (tid == 0) p.partials[(size_t)cell * p.gene_tiles + blockIdx.x] = make_float2(bm, red_s[0] + red_s[1] + red_s[2] + red_s[3]);
+  }
+}
+
+// ---- MCAB decode on tensor cores (mma.sync bf16, fp32 accumulate) -------------------------------
+// One warp owns 16 genes (one m16 tile) and keeps the whole per-gene chain in registers:
+//   S_h = Q_h K_h^T (m16n8k8 x2 per head) -> softmax over 16 keys (quad shuffles) -> O_h = P_h V_h (m16n8k16)
+//   -> x = emb + O Wproj^T (8 mma) -> LN2 -> for each 16-wide hidden chunk: [w1|w2] (8 mma) -> silu*mul ->
+//   x += h W3^T (4 mma) -> logit = x . w_head + b.   C fragments feed the next GEMM's A fragments directly.
+// Weights arrive pre-arranged in B-fragment order (pack.py: mma_b_frags), 64 x u32 per (k-step, n-tile).
+struct McabTcParams {
+  const float* emb;            // [n_ids][32] fp32 (residual uses the unrounded embedding)
+  const __nv_bfloat16* qp;     // [n_ids][32] bf16 Q-side table
+  const long long* genes;
+  int G;
+  const __nv_bfloat16* kvb;    // [cells][ K: 16 keys x 32 | V^T: 32 dims x 16 keys ] bf16
+  int n_cells;
+  int cells_per_block;
+  const uint32_t* wfrag;       // 80 fragments x 64 u32: proj (2x4) | per hidden chunk c<6: w1 (2x2) | w2 (2x2) | w3 (4)
+  const float* small;          // ln2_w[32] | ln2_b[32] | head_w[32] | head_b
+  float eps;
+  float* logits;
+  float2* partials;
+  int gene_tiles;
+};
+constexpr int TC_NFRAG = 8 + 6 * 12;
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+
+__global__ void __launch_bounds__(256, 2) mcab_decode_tc_kernel(const McabTcParams p) {
+  __shared__ uint2 s_frag[TC_NFRAG * 32];   // 20 KB
+  __shared__ float s_small[100];
+  __shared__ float red_m[2][8], red_s[2][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < TC_NFRAG * 32; i += 256) s_frag[i] = reinterpret_cast<const uint2*>(p.wfrag)[i];
+  if (tid < 97) s_small[tid] = p.small[tid];
+  __syncthreads();
+
+  // ---- gene-side operands of this warp's 16 genes (cell invariant) ----
+  const int gene0 = blockIdx.x * 128 + warp * 16;
+  const int gi0 = gene0 + g, gi1 = gene0 + g + 8;
+  const bool v0 = gi0 < p.G, v1 = gi1 < p.G;
+  const long long id0 = v0 ? p.genes[gi0] : 0, id1 = v1 ? p.genes[gi1] : 0;
+  float embf[4][4];   // C-fragment layout: [nt]{(row g: cols 8nt+2t,+1), (row g+8: ...)}
+  uint32_t qa[4][2];  // per head h: a0 = (row g, dims 8h+2t,+1), a1 = (row g+8, ...)
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float2 e0 = *reinterpret_cast<const float2*>(p.emb + (size_t)id0 * E + nt * 8 + 2 * t);
+    const float2 e1 = *reinterpret_cast<const float2*>(p.emb + (size_t)id1 * E + nt * 8 + 2 * t);
+    embf[nt][0] = e0.x; embf[nt][1] = e0.y; embf[nt][2] = e1.x; embf[nt][3] = e1.y;
+    qa[nt][0] = *reinterpret_cast<const uint32_t*>(p.qp + (size_t)id0 * E + nt * 8 + 2 * t);
+    qa[nt][1] = *reinterpret_cast<const uint32_t*>(p.qp + (size_t)id1 * E + nt * 8 + 2 * t);
+  }
+  // LN2 affine + head weights in C-fragment column order
+  float lw[4][2], lb[4][2], hw[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = nt * 8 + 2 * t + j;
+      lw[nt][j] = s_small[c]; lb[nt][j] = s_small[32 + c]; hw[nt][j] = s_small[64 + c];
+    }
+  }
+  const float head_b = s_small[96];
+  const float sc = 0.35355339059327373f * 1.4426950408889634f;  // 1/sqrt(8) * log2(e)
+
+  const int cell0 = blockIdx.y * p.cells_per_block;
+  const int cell1 = min(cell0 + p.cells_per_block, p.n_cells);
+  // K/V B-fragments of a cell: kb[h][nt2] = K[key 8nt2+g][dims 8h+2t,+1]; vb[h][half] = V^T[dim 8h+g][keys 2t+8half,+1]
+  uint32_t kb[4][2], vb[4][2];
+  auto load_kv = [&](int cell, uint32_t (&kk)[4][2], uint32_t (&vv)[4][2]) {
+    const __nv_bfloat16* base = p.kvb + (size_t)cell * 1024;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        kk[h][j] = *reinterpret_cast<const uint32_t*>(base + (8 * j + g) * 32 + 8 * h + 2 * t);
+        vv[h][j] = *reinterpret_cast<const uint32_t*>(base + 512 + (8 * h + g) * 16 + 2 * t + 8 * j);
+      }
+    }
+  };
+  if (cell0 < cell1) load_kv(cell0, kb, vb);
+
+  for (int cell = cell0; cell < cell1; ++cell) {
+    uint32_t kn[4][2], vn[4][2];
+    if (cell + 1 < cell1) load_kv(cell + 1, kn, vn);   // prefetch the next cell's fragments
+
+    // ---- attention over the 16 latent keys, head by head; O stays in C fragments ----
+    float o[4][4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_1688(s0, qa[h][0], qa[h][1], kb[h][0]);   // keys 0-7
+      mma_1688(s1, qa[h][0], qa[h][1], kb[h][1]);   // keys 8-15
+      float m0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));   // row g
+      float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));   // row g+8
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      s0[0] = exp2f((s0[0] - m0) * sc); s0[1] = exp2f((s0[1] - m0) * sc); s1[0] = exp2f((s1[0] - m0) * sc); s1[1] = exp2f((s1[1] - m0) * sc);
+      s0[2] = exp2f((s0[2] - m1) * sc); s0[3] = exp2f((s0[3] - m1) * sc); s1[2] = exp2f((s1[2] - m1) * sc); s1[3] = exp2f((s1[3] - m1) * sc);
+      float l0 = (s0[0] + s0[1]) + (s1[0] + s1[1]), l1 = (s0[2] + s0[3]) + (s1[2] + s1[3]);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float r0 = __fdividef(1.0f, l0), r1 = __fdividef(1.0f, l1);
+      o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
+      mma_16816(o[h], sm100::pack_bf16x2(s0[0] * r0, s0[1] * r0), sm100::pack_bf16x2(s0[2] * r1, s0[3] * r1),
+                sm100::pack_bf16x2(s1[0] * r0, s1[1] * r0), sm100::pack_bf16x2(s1[2] * r1, s1[3] * r1), vb[h][0], vb[h][1]);
+    }
+    // ---- x = q + c_proj(attn): A k-step 0 = heads (0,1), k-step 1 = heads (2,3) ----
+    float x[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { x[nt][0] = embf[nt][0]; x[nt][1] = embf[nt][1]; x[nt][2] = embf[nt][2]; x[nt][3] = embf[nt][3]; }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint32_t a0 = sm100::pack_bf16x2(o[2 * ks][0], o[2 * ks][1]), a1 = sm100::pack_bf16x2(o[2 * ks][2], o[2 * ks][3]);
+      const uint32_t a2 = sm100::pack_bf16x2(o[2 * ks + 1][0], o[2 * ks + 1][1]), a3 = sm100::pack_bf16x2(o[2 * ks + 1][2], o[2 * ks + 1][3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint2 b = s_frag[(ks * 4 + nt) * 32 + lane];
+        mma_16816(x[nt], a0, a1, a2, a3, b.x, b.y);
+      }
+    }
+    // ---- LN2 (rows g and g+8 live in the 4 lanes of a quad) -> A fragments of the MLP ----
+    uint32_t ha[2][4];
+    {
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { sa += x[nt][0] + x[nt][1]; sb += x[nt][2] + x[nt][3]; }
+      sa += __shfl_xor_sync(0xffffffffu, sa, 1); sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+      sb += __shfl_xor_sync(0xffffffffu, sb, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+      const float ma = sa * (1.0f / E), mb = sb * (1.0f / E);
+      float qa2 = 0.f, qb2 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float d0 = x[nt][0] - ma, d1 = x[nt][1] - ma, d2 = x[nt][2] - mb, d3 = x[nt][3] - mb;
+        qa2 += d0 * d0 + d1 * d1; qb2 += d2 * d2 + d3 * d3;
+      }
+      qa2 += __shfl_xor_sync(0xffffffffu, qa2, 1); qa2 += __shfl_xor_sync(0xffffffffu, qa2, 2);
+      qb2 += __shfl_xor_sync(0xffffffffu, qb2, 1); qb2 += __shfl_xor_sync(0xffffffffu, qb2, 2);
+      const float ra = rsqrtf(qa2 * (1.0f / E) + p.eps), rb = rsqrtf(qb2 * (1.0f / E) + p.eps);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int nt = 2 * ks + j;
+          ha[ks][2 * j] = sm100::pack_bf16x2((x[nt][0] - ma) * ra * lw[nt][0] + lb[nt][0], (x[nt][1] - ma) * ra * lw[nt][1] + lb[nt][1]);
+          ha[ks][2 * j + 1] = sm100::pack_bf16x2((x[nt][2] - mb) * rb * lw[nt][0] + lb[nt][0], (x[nt][3] - mb) * rb * lw[nt][1] + lb[nt][1]);
+        }
+      }
+    }
+    // ---- SwiGLU MLP streamed over 16-wide hidden chunks (hidden 88 zero-padded to 96) ----
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const uint2* fr = s_frag + (8 + c * 12) * 32 + lane;
+      float a1[2][4] = {}, a2[2][4] = {};
+#pragma unroll
+      for (int n2 = 0; n2 < 2; ++n2) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint2 b1 = fr[(n2 * 2 + ks) * 32], b2 = fr[(4 + n2 * 2 + ks) * 32];
+          mma_16816(a1[n2], ha[ks][0], ha[ks][1], ha[ks][2], ha[ks][3], b1.x, b1.y);
+          mma_16816(a2[n2], ha[ks][0], ha[ks][1], ha[ks][2], ha[ks][3], b2.x, b2.y);
+        }
+      }
+      const uint32_t h0 = sm100::pack_bf16x2(sm100::silu_tanh(a1[0][0]) * a2[0][0], sm100::silu_tanh(a1[0][1]) * a2[0][1]);
+      const uint32_t h1 = sm100::pack_bf16x2(sm100::silu_tanh(a1[0][2]) * a2[0][2], sm100::silu_tanh(a1[0][3]) * a2[0][3]);
+      const uint32_t h2 = sm100::pack_bf16x2(sm100::silu_tanh(a1[1][0]) * a2[1][0], sm100::silu_tanh(a1[1][1]) * a2[1][1]);
+      const uint32_t h3 = sm100::pack_bf16x2(sm100::silu_tanh(a1[1][2]) * a2[1][2], sm100::silu_tanh(a1[1][3]) * a2[1][3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint2 b3 = fr[(8 + nt) * 32];
+        mma_16816(x[nt], h0, h1, h2, h3, b3.x, b3.y);
+      }
+    }
+    // ---- NB-head logit + softmax-over-genes partials ----
+    float la = 0.f, lb2 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      la += x[nt][0] * hw[nt][0] + x[nt][1] * hw[nt][1];
+      lb2 += x[nt][2] * hw[nt][0] + x[nt][3] * hw[nt][1];
+    }
+    la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
+    lb2 += __shfl_xor_sync(0xffffffffu, lb2, 1); lb2 += __shfl_xor_sync(0xffffffffu, lb2, 2);
+    la += head_b; lb2 += head_b;
+    if (t == 0) {
+      if (v0) p.logits[(size_t)cell * p.G + gi0] = la;
+      if (v1) p.logits[(size_t)cell * p.G + gi1] = lb2;
+    }
+    const float lm = fmaxf(v0 ? la : -INFINITY, v1 ? lb2 : -INFINITY);
+    const float wm = sm100::warp_max(lm);
+    const float ev = (t == 0) ? ((v0 ? __expf(la - wm) : 0.f) + (v1 ? __expf(lb2 - wm) : 0.f)) : 0.f;
+    const float wsum = sm100::warp_sum(ev);
+    const int par = cell & 1;
+    if (lane == 0) { red_m[par][warp] = wm; red_s[par][warp] = wsum; }
+    __syncthreads();
+    if (tid == 0) {
+      float bm = red_m[par][0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) bm = fmaxf(bm, red_m[par][w]);
+      float bs = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) bs += red_m[par][w] == -INFINITY ? 0.f : red_s[par][w] * __expf(red_m[par][w] - bm);
+      p.partials[(size_t)cell * p.gene_tiles + blockIdx.x] = make_float2(bm, bs);
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h) { kb[h][0] = kn[h][0]; kb[h][1] = kn[h][1]; vb[h][0] = vn[h][0]; vb[h][1] = vn[h][1]; }
   }
 }
 

@@ -140,20 +140,21 @@ def dit_workspace_views(plan: DitPlan, ws: torch.Tensor, n_evals: int = 0) -> di
     }
 
 
-def vae_qside(packed: PackedVAEDecoder) -> torch.Tensor:
-    """Cell-invariant MCAB query projections for the whole vocabulary (cached on `packed`)."""
+def vae_qside(packed: PackedVAEDecoder):
+    """Cell-invariant MCAB query projections for the whole vocabulary, fp32 and bf16 (cached on `packed`)."""
     if packed.qp is None:
         lib = _lib.load()
         qp = torch.empty(packed.emb.shape[0], 32, dtype=torch.float32, device=packed.device)
-        rc = lib.scldm_vae_qside(C.byref(packed.struct), qp.data_ptr(), _stream_ptr(packed.device))
+        qpb = torch.empty(packed.emb.shape[0], 32, dtype=torch.bfloat16, device=packed.device)
+        rc = lib.scldm_vae_qside(C.byref(packed.struct), qp.data_ptr(), qpb.data_ptr(), _stream_ptr(packed.device))
         _lib.check(rc, "scldm_vae_qside")
-        packed.qp = qp
-    return packed.qp
+        packed.qp, packed.qp_bf16 = qp, qpb
+    return packed.qp, packed.qp_bf16
 
 
 def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, lib_size: torch.Tensor, want_mu=True,
                want_counts=False, seed: int = 0, cell_offset: int = 0, out_mu: torch.Tensor | None = None,
-               out_counts: torch.Tensor | None = None):
+               out_counts: torch.Tensor | None = None, precision: str = "bf16"):
     """z [cells,16,16] fp32, genes [G] int64 (shared by all cells), lib_size [cells] fp32 ->
     (mu [cells,G] | None, theta [G], counts [cells,G] | None)."""
     lib = _lib.load()
@@ -163,7 +164,7 @@ def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, l
     assert genes.dtype == torch.int64 and genes.is_cuda and genes.dim() == 1
     assert int(lib_size.numel()) == n_cells
     lib_size = lib_size.reshape(-1).to(torch.float32).contiguous()
-    qp = vae_qside(packed)
+    qp, qpb = vae_qside(packed)
     for o in (out_mu, out_counts):
         if o is not None:
             assert o.is_cuda and o.is_contiguous() and o.dtype == torch.float32 and o.shape == (n_cells, G)
@@ -173,10 +174,10 @@ def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, l
     theta = torch.empty(G, dtype=torch.float32, device=z.device)
     nbytes = int(lib.scldm_vae_decode_workspace_bytes(n_cells, G))
     ws = _workspace(z.device, nbytes, "vae")
-    rc = lib.scldm_vae_decode(C.byref(packed.struct), qp.data_ptr(), z.data_ptr(), n_cells, genes.data_ptr(), G,
+    rc = lib.scldm_vae_decode(C.byref(packed.struct), qp.data_ptr(), qpb.data_ptr(), z.data_ptr(), n_cells, genes.data_ptr(), G,
                               lib_size.data_ptr(), mu.data_ptr() if mu is not None else None, theta.data_ptr(),
-                              counts.data_ptr() if counts is not None else None, seed & (2**64 - 1), cell_offset, ws.data_ptr(),
-                              ws.numel(), _stream_ptr(z.device))
+                              counts.data_ptr() if counts is not None else None, seed & (2**64 - 1), cell_offset,
+                              _lib.DECODE_PRECISION[precision], ws.data_ptr(), ws.numel(), _stream_ptr(z.device))
     _lib.check(rc, "scldm_vae_decode")
     return mu, theta, counts
 

@@ -47,6 +47,18 @@ def unpack_kmajor_tiles(p: torch.Tensor, block_rows: int) -> torch.Tensor:
     return tiles.permute(0, 2, 1, 3).reshape(nt * block_rows, ks * BLOCK_K)
 
 
+def mma_b_frags(w: torch.Tensor) -> torch.Tensor:
+    """w [N, K] (out, in) -> bf16 [K/16][N/8][32 lanes][4]: the B operand B[k][n] = w[n][k] of `mma.sync.m16n8k16`
+    in per-lane fragment order.  Lane (g = lane/4, t = lane%4) holds b0 = w[8nt+g][16ks+2t, +1] and
+    b1 = w[8nt+g][16ks+2t+8, +9] (N, K zero padded to multiples of 8 / 16)."""
+    N, K = w.shape
+    NT, KS = -(-N // 8), -(-K // 16)
+    wp = torch.zeros(NT * 8, KS * 16, dtype=torch.bfloat16)
+    wp[:N, :K] = w.to(torch.bfloat16)
+    v = wp.view(NT, 8, KS, 2, 4, 2)            # [nt][g][ks][half][t][pair]
+    return v.permute(2, 0, 1, 4, 3, 5).contiguous().view(KS, NT, 32, 4)
+
+
 class PackedDiT:
     """Device-resident packed DiT weights + the ctypes struct handed to the C-ABI."""
 
@@ -156,13 +168,30 @@ class PackedVAEDecoder:
         ])
         assert blob.numel() == MCAB_TOTAL
         self.mcab_blob = f32(blob)
+        # tensor-core MCAB: fragments in the order csrc/vae_kernels.cuh::mcab_decode_tc_kernel walks them
+        fp = mma_b_frags(g(c + "attn.c_proj.weight"))                 # [2][4]
+        f1 = mma_b_frags(g(c + "mlp.w1.weight"))                      # [2][11 -> 12 n-tiles after padding below]
+        f2 = mma_b_frags(g(c + "mlp.w2.weight"))
+        f3 = mma_b_frags(g(c + "mlp.c_proj.weight"))                  # [6][4]  (K = 88 -> 96)
+        pad = lambda f: torch.cat([f, torch.zeros(f.shape[0], 12 - f.shape[1], 32, 4, dtype=f.dtype)], 1)  # noqa: E731
+        f1, f2 = pad(f1), pad(f2)
+        frags = [fp[ks, nt] for ks in range(2) for nt in range(4)]
+        for ch in range(6):
+            frags += [f1[ks, 2 * ch + n2] for n2 in range(2) for ks in range(2)]
+            frags += [f2[ks, 2 * ch + n2] for n2 in range(2) for ks in range(2)]
+            frags += [f3[ch, nt] for nt in range(4)]
+        self.mcab_wfrag = torch.stack(frags).to(device).contiguous()   # [80][32][4] bf16
+        assert self.mcab_wfrag.shape == (80, 32, 4)
+        self.mcab_small = f32(torch.cat([g(c + "ln_2.weight"), g(c + "ln_2.bias"), g("decoder_head.params.weight").reshape(-1),
+                                         g("decoder_head.params.bias").reshape(-1), torch.zeros(3)]))
         self.emb = f32(g("input_layer.gene_embedding.weight"))
         self.theta_tbl = f32(g("decoder_head.theta.weight").reshape(-1))
         s = _lib.VaeDecWeights()
         s.n_layer, s.n_ids, s.eps = cfg.n_layer, self.emb.shape[0], float(cfg.layernorm_eps)
         for name in ("win_t", "blocks", "ca_ln1_w", "ca_ln1_b", "ca_wkv_t", "ca_ln1q_w", "ca_ln1q_b", "ca_wq", "mcab_blob", "emb",
-                     "theta_tbl"):
+                     "theta_tbl", "mcab_wfrag", "mcab_small"):
             setattr(s, name, getattr(self, name).data_ptr())
         self.struct = s
         self.device = torch.device(device)
-        self.qp = None  # Q-side table, filled lazily by ops.vae_qside
+        self.qp = None  # Q-side tables (fp32, bf16), filled lazily by ops.vae_qside
+        self.qp_bf16 = None

@@ -37,6 +37,7 @@ class TransformerVAE(nn.Module):
         self._packed_key = None
         self.sample_seed = 0
         self.sample_offset = 0
+        self.decode_precision = "bf16"  # "bf16": MCAB on tensor cores; "fp32": exact CUDA-core variant
 
     @classmethod
     def from_config(cls, cfg: VAEConfig) -> "TransformerVAE":
@@ -72,13 +73,14 @@ class TransformerVAE(nn.Module):
         packed = self.packed_decoder()
         gvec = shared_gene_vector(genes)
         zc = z.contiguous().float()
-        mu, theta, _ = ops.vae_decode(packed, zc, gvec, library_size, want_mu=True, want_counts=False)
+        prec = self.decode_precision
+        mu, theta, _ = ops.vae_decode(packed, zc, gvec, library_size, want_mu=True, want_counts=False, precision=prec)
         theta_full = theta.unsqueeze(0).expand(z.shape[0], -1)
         seed, offset = self.sample_seed, self.sample_offset
 
         def sampler():
             _, _, counts = ops.vae_decode(packed, zc, gvec, library_size, want_mu=False, want_counts=True, seed=seed,
-                                          cell_offset=offset)
+                                          cell_offset=offset, precision=prec)
             return counts
 
         return NegativeBinomial(mu, theta_full, _sampler=sampler)
@@ -90,7 +92,7 @@ class TransformerVAE(nn.Module):
         packed = self.packed_decoder()
         mu, theta, counts = ops.vae_decode(packed, z.contiguous().float(), shared_gene_vector(genes), library_size,
                                            want_mu=want_mu, want_counts=True, seed=seed, cell_offset=cell_offset,
-                                           out_counts=out_counts, out_mu=out_mu)
+                                           out_counts=out_counts, out_mu=out_mu, precision=self.decode_precision)
         return counts, mu, theta
 
     def encode(self, counts, genes, counts_subset=None, genes_subset=None):

@@ -1,7 +1,10 @@
 """GPU parity: fused VAE decoder (latent blocks -> MCAB -> NB head -> Gamma-Poisson) vs oracle / golden.
 
-The decoder kernels compute in fp32 throughout, so tolerances are tight:
-  mu: rel-L2 <= 1e-4 and |sum_g mu - library| / library <= 1e-4;  theta: rel <= 1e-5.
+Two MCAB variants share every other kernel:
+  precision="fp32": CUDA-core fp32 throughout      -> mu rel-L2 <= 1e-4
+  precision="bf16": tensor cores (mma.sync), bf16 operands / fp32 accumulate / fp32 residual (default)
+                                                    -> mu rel-L2 <= 2e-2 (SURVEY.md section 7 starting tolerance)
+Both: |sum_g mu - library| / library <= 1e-4; theta (fp32 exp of a table) rel <= 1e-5.
 Sampled counts: distributional agreement only (moments within Monte-Carlo error)."""
 
 import os
@@ -23,33 +26,42 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def make_vae(cfg):
+MU_TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def make_vae(cfg, precision="bf16"):
     from scldm_b200.vae import TransformerVAE
 
     vae = TransformerVAE.from_config(cfg)
     sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
     vae.load_state_dict(sd, strict=True)
+    vae.decode_precision = precision
     return vae.cuda().eval(), sd
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name,G,B,S", [("vae_small", 1500, 3, 400), ("vae_dentate", 17002, 2, 600)])
-def test_decode_vs_golden(golden_dir, name, G, B, S):
+def test_decode_vs_golden(golden_dir, name, G, B, S, precision):
     g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     cfg = VAEConfig(n_genes=G)
-    vae, sd = make_vae(cfg)
+    vae, sd = make_vae(cfg, precision)
     z, genes, lib, _, _ = vae_inputs(name, cfg, B, S)
     nb = vae.decode(z.cuda(), genes.cuda(), lib.cuda())
     e_mu, e_th = rel_l2(nb.mu, g["mu"]), rel_l2(nb.theta[0], g["theta"])
     tot = (nb.mu.sum(1).cpu() / lib[:, 0] - 1).abs().max().item()
-    print(name, f"mu {e_mu:.2e} theta {e_th:.2e} |sum/lib-1| {tot:.2e}")
-    assert e_mu < 1e-4 and e_th < 1e-5 and tot < 1e-4
+    big = torch.from_numpy(g["mu"]) >= 1e-3 * float(g["mu"].max())
+    e_rel = float(((nb.mu.cpu() - torch.from_numpy(g["mu"])).abs() / torch.from_numpy(g["mu"]))[big].max())
+    print(name, precision, f"mu rel-L2 {e_mu:.2e} max-rel(big) {e_rel:.2e} theta {e_th:.2e} |sum/lib-1| {tot:.2e}")
+    assert e_mu < MU_TOL[precision] and e_th < 1e-5 and tot < 1e-4
+    assert e_rel < 5 * MU_TOL[precision]
     assert nb.mu.shape == (B, G) and nb.theta.shape == (B, G)
 
 
-def test_decode_many_cells_vs_oracle():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decode_many_cells_vs_oracle(precision):
     """cells_per_block > 1 path, ragged last gene tile (G=1000 is not a multiple of 128)."""
     cfg = VAEConfig(n_genes=1000, n_layer=3)
-    vae, sd = make_vae(cfg)
+    vae, sd = make_vae(cfg, precision)
     B = 700
     z = synthetic.randn("dm.z", (B, 16, 16))
     lib = torch.exp(8.0 + 0.3 * synthetic.randn("dm.lib", (B, 1)))
@@ -57,14 +69,17 @@ def test_decode_many_cells_vs_oracle():
     nb = vae.decode(z.cuda(), genes.cuda(), lib.cuda())
     with torch.no_grad():
         mu, theta = O.vae_decode(z, genes, lib, sd, cfg)
-    assert rel_l2(nb.mu, mu) < 1e-4
+    e = rel_l2(nb.mu, mu)
+    print("many cells", precision, f"{e:.2e}")
+    assert e < MU_TOL[precision]
     assert rel_l2(nb.theta, theta) < 1e-5
 
 
-def test_decode_gene_subset_and_order():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decode_gene_subset_and_order(precision):
     """gene ids are looked up, not assumed to be arange: a shuffled subset gives the matching columns' logits."""
     cfg = VAEConfig(n_genes=600, n_layer=2)
-    vae, sd = make_vae(cfg)
+    vae, sd = make_vae(cfg, precision)
     B = 5
     z = synthetic.randn("gs.z", (B, 16, 16))
     lib = torch.full((B, 1), 1000.0)
@@ -73,7 +88,7 @@ def test_decode_gene_subset_and_order():
     nb = vae.decode(z.cuda(), genes.cuda(), lib.cuda())
     with torch.no_grad():
         mu, theta = O.vae_decode(z, genes, lib, sd, cfg)
-    assert rel_l2(nb.mu, mu) < 1e-4 and rel_l2(nb.theta, theta) < 1e-5
+    assert rel_l2(nb.mu, mu) < MU_TOL[precision] and rel_l2(nb.theta, theta) < 1e-5
 
 
 def test_nb_sampling_moments():

@@ -68,6 +68,23 @@ def test_vae_pack_layout_cpu():
     assert "MW_LN2W = 1024" in src and "BLK_WQKV = 128" in src and "HID = 88" in src
 
 
+def test_mma_b_fragment_layout():
+    """pack.mma_b_frags: lane (g,t) of fragment (ks,nt) holds w[8nt+g][16ks+2t,+1] and w[8nt+g][16ks+2t+8,+9]."""
+    g0 = torch.Generator().manual_seed(1)
+    w = torch.randn(88, 32, generator=g0)
+    f = pack.mma_b_frags(w)
+    assert f.shape == (2, 11, 32, 4)
+    wb = w.to(torch.bfloat16)
+    for ks, nt, lane in [(0, 0, 0), (1, 10, 31), (0, 5, 13), (1, 3, 6)]:
+        g, t = lane // 4, lane % 4
+        r = 8 * nt + g
+        exp = torch.stack([wb[r, 16 * ks + 2 * t], wb[r, 16 * ks + 2 * t + 1], wb[r, 16 * ks + 2 * t + 8], wb[r, 16 * ks + 2 * t + 9]])
+        assert torch.equal(f[ks, nt, lane], exp)
+    f3 = pack.mma_b_frags(torch.randn(32, 88, generator=g0))  # K = 88 -> padded to 96
+    assert f3.shape == (6, 4, 32, 4) and float(f3[5, :, :, :].float().abs().sum()) > 0
+    assert float(f3[5, 0, 2, 2:].float().abs().sum()) == 0  # lane t=2: columns 80+2t+8 >= 88 are padding
+
+
 def test_drop_in_state_dict_contract(golden_dir):
     """the drop-in modules expose exactly the reference's state_dict keys/shapes and load them strictly."""
     from scldm_b200.nnets import DiT
