@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=2048, help="cells per step per GPU (2x rows are generated)")
+    ap.add_argument("--batch", type=int, default=2352, help="cells per step per GPU (2x rows are generated)")
     ap.add_argument("--chunk", type=int, default=0, help="cells per ODE chunk (0 = library default)")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--cpu-batch", type=int, default=8)
@@ -306,8 +306,14 @@ def main():
         fl = kernel_flops(name, rows, 1 + chunk)
         ach = fl / (tms / cnt * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tp):
+            tj = json.load(open(tp))
+            if tj.get("ode_chunk_cells") == chunk:
+                traffic = tj["per_launch_bytes"].get(name)
         roofline = {"bound": "tensor", "kernel": name, "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                    "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                     "avg_launch_us": round(1e3 * tms / cnt, 2), "flops_per_launch": fl}
 
     cpu_baseline = None

@@ -31,7 +31,7 @@ class LatentDiffusion(nn.Module):
     def __init__(self, vae_model: TransformerVAE, diffusion_model: DiT, transport: Transport,
                  mu_size_factor: dict | None = None, sd_size_factor: dict | None = None,
                  size_factor_condition_key: str | None = None, sampling_method: str = "euler", num_steps: int = 50,
-                 seed: int = 0, cell_chunk: int = 1024, **_unused_training_kwargs):
+                 seed: int = 0, cell_chunk: int = 784, **_unused_training_kwargs):
         super().__init__()
         self.vae_model = vae_model
         self.diffusion_model = diffusion_model
@@ -79,7 +79,7 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def sample(self, condition: dict[str, torch.Tensor] | None, guidance_weight: dict[str, float] | None, batch_size: int,
                genes: torch.Tensor, timesteps: int = 50, *, z0: torch.Tensor | None = None,
-               log_size_factors: torch.Tensor | None = None, return_mu: bool = False):
+               log_size_factors: torch.Tensor | None = None, return_mu: bool = False, cell_offset: int | None = None):
         """Generation (`models.py:766-819`).  `timesteps` is accepted and ignored exactly as in the reference
         (`models.py:773,793`); the grid is `self.num_steps` points.  `z0` / `log_size_factors` may be injected
         (parity tests share them with the oracle); otherwise they are drawn on device."""
@@ -94,8 +94,8 @@ class LatentDiffusion(nn.Module):
                 f"Guidance weight keys {set(guidance_weight.keys())} must match condition keys {set(condition.keys())}")
         dev = self.device
         dit = self.diffusion_model
-        offset = self.cells_generated
-        self.cells_generated += batch_size
+        offset = self.cells_generated if cell_offset is None else cell_offset  # global index of cell 0 (RNG key)
+        self.cells_generated = offset + batch_size
         lsf = log_size_factors.to(dev).float() if log_size_factors is not None else \
             self._sample_log_size_factors(condition, batch_size, offset)
         if z0 is None:

@@ -183,3 +183,34 @@ def test_sample_rng_path_and_size_factors():
                           num_steps=5, seed=3, cell_chunk=4096)
     c3, z3, _ = ldm.sample(lab, {"clusters": 1.0}, B, genes, return_mu=True)
     assert torch.equal(z3, z1) and torch.equal(c3, c1)
+
+
+def test_shard_invariance_single_gpu():
+    """generating cells [0,10) in one call == generating [0,6) and [6,10) as two 'ranks' with global offsets
+    (what scldm_b200.dist.sample_sharded does per rank): RNG is keyed by the global cell index."""
+    from scldm_b200.dist import shard_range
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=1)
+    vcfg = VAEConfig(n_genes=300, n_layer=1)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
+    vae, _ = make_vae(vcfg)
+    mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes)
+    mk = lambda: LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t,  # noqa: E731
+                                 sd_size_factor=sd_t, num_steps=4, seed=9)
+    B = 10
+    lab = {"clusters": synthetic.randint("si.lab", 14, (B,)).cuda()}
+    genes = torch.arange(1, 301).unsqueeze(0).repeat(B, 1).cuda()
+    c_all, z_all = mk().sample(lab, {"clusters": 1.5}, B, genes)
+    parts = []
+    for r in range(2):
+        a, b = shard_range(B, r, 2)
+        parts.append(mk().sample({"clusters": lab["clusters"][a:b]}, {"clusters": 1.5}, b - a, genes[a:b], cell_offset=a))
+    n0 = parts[0][0].shape[0] // 2
+    n1 = parts[1][0].shape[0] // 2
+    c_cat = torch.cat([parts[0][0][:n0], parts[1][0][:n1], parts[0][0][n0:], parts[1][0][n1:]])
+    z_cat = torch.cat([parts[0][1][:n0], parts[1][1][:n1], parts[0][1][n0:], parts[1][1][n1:]])
+    assert torch.equal(z_cat, z_all) and torch.equal(c_cat, c_all)
