@@ -53,6 +53,9 @@ typedef struct scldm_dit_weights {
   const float* b_proj;  /* [n_layer][256]                                                        */
   const void* w_mlp1;   /* bf16 [n_layer][mlp1_tiles][4][256x64]  rows 0-127 = w1, 128-255 = w2   */
   const void* w_mlp2;   /* bf16 [n_layer][hid_slabs][256x64]      mlp.c_proj                      */
+  const void* w_mlp_stream; /* bf16 [n_layer][mlp1_tiles*4 + hid_slabs][256x64]: the same [w1|w2] tiles and c_proj slabs
+                               in the consumption order of the fused MLP kernel (M1_0, M1_1, M2_0, M1_2, M2_1, ...);
+                               NULL selects the unfused pair of kernels                                              */
   const float* temb_w0t; /* t_embedder.mlp.0.weight^T [256][256] */
   const float* temb_b0;
   const float* temb_w2t; /* t_embedder.mlp.2.weight^T [256][256] */

@@ -183,6 +183,17 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + (1 << 17) : nullptr;
       LAUNCH("gemm_astream<proj>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
     }
+    if (w->w_mlp_stream != nullptr) {  // fused MLP half: LN2 + modulate + [w1|w2] + SwiGLU + c_proj + gated residual
+      dit::MlpFusedParams p{};
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride;
+      p.mod_off_mul = mo + 3 * dit::D; p.mod_off_add = mo + 4 * dit::D; p.mod_off_gate = mo + 5 * dit::D; p.eps = w->eps;
+      const size_t n_stream = (size_t)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs;
+      p.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream) + (size_t)l * n_stream * dit::B_SLAB_ELEMS;
+      p.n_chunks = w->mlp1_tiles; p.hid_slabs = w->hid_slabs;
+      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 2 * (1 << 17) : nullptr;
+      LAUNCH("mlp_fused", dit::mlp_fused_kernel<<<row_tiles, dit::NUM_THREADS, dit::mlp_fused_smem_bytes(), st>>>(p));
+      continue;
+    }
     {  // LN2 + modulate + [w1|w2] + SwiGLU
       dit::AResParams p{};
       p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride;
@@ -233,6 +244,7 @@ int prepare_kernels() {
   if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU>, dit::ares_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD>, dit::ares_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::gemm_astream_resid_kernel, dit::astream_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::mlp_fused_kernel, dit::mlp_fused_smem_bytes()))) return rc;
   if ((rc = set_smem(vae::mcab_decode_kernel, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float)))) return rc;
   done.store(1);
   return SCLDM_OK;

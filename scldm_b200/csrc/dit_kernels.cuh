@@ -109,6 +109,82 @@ __device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_d, uint32_t a_smem
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// LN + adaLN-modulate prologue fed by bulk TMA: the producer warp streams the CTA's 128 x 256 fp32 rows of X through
+// two 32 KB shared-memory buffers (4 passes of 32 rows); the 16 prologue warps normalise 2 rows each per pass and write
+// the bf16 A tile in the swizzled UMMA layout.  No long-latency global loads sit in the warps' dependency chains.
+// ------------------------------------------------------------------------------------------
+constexpr int XPASS_ROWS = 32;
+constexpr int XPASS_BYTES = XPASS_ROWS * D * 4;   // 32 KB
+
+__device__ __forceinline__ void producer_issue_x_pass(const float* X, int row_tile, int pass, uint8_t* smX, uint64_t* x_full) {
+  sm100::mbar_arrive_expect_tx(&x_full[pass & 1], XPASS_BYTES);
+  sm100::bulk_g2s(smX + (pass & 1) * XPASS_BYTES, X + ((size_t)row_tile * BLOCK_M + pass * XPASS_ROWS) * D, XPASS_BYTES, &x_full[pass & 1]);
+}
+
+__device__ __forceinline__ void ln_prologue_tma(const uint8_t* smX, uint64_t* x_full, uint64_t* x_empty, uint8_t* smA, const float* mod,
+                                                const int* slot_mod, int mod_stride, int off_mul, int off_add, float eps, int row_tile,
+                                                uint32_t ew, uint32_t lane) {
+  const float inv_d = 1.0f / D;
+  const int half = ew >> 3;          // which of the pass's two slots this warp serves
+  const int r2 = (ew & 7) * 2;       // first of this warp's two rows inside that slot
+  int mr[4];
+#pragma unroll
+  for (int pss = 0; pss < 4; ++pss) mr[pss] = slot_mod[row_tile * 8 + 2 * pss + half];
+  float4 m0, m1, a0, a1;
+  {
+    const float* mrow = mod + (size_t)mr[0] * mod_stride;
+    m0 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8); m1 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8 + 4);
+    a0 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8); a1 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8 + 4);
+  }
+#pragma unroll
+  for (int pss = 0; pss < 4; ++pss) {
+    float4 nm0 = m0, nm1 = m1, na0 = a0, na1 = a1;
+    if (pss + 1 < 4) {  // prefetch the next pass's modulation vectors
+      const float* mrow = mod + (size_t)mr[pss + 1] * mod_stride;
+      nm0 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8); nm1 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8 + 4);
+      na0 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8); na1 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8 + 4);
+    }
+    sm100::mbar_wait(&x_full[pss & 1], (pss >> 1) & 1);
+    const uint8_t* xb = smX + (pss & 1) * XPASS_BYTES + (half * 16 + r2) * (D * 4) + lane * 32;
+    float v[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xb + i * (D * 4));
+      const float4 x1 = *reinterpret_cast<const float4*>(xb + i * (D * 4) + 16);
+      v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w; v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+    }
+    __syncwarp();
+    if (pss < 2 && lane == 0) sm100::mbar_arrive(&x_empty[pss & 1]);   // buffer may be refilled with pass pss+2
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0 += v[0][j]; s1 += v[1][j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    const float mean0 = s0 * inv_d, mean1 = s1 * inv_d;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[0][j] -= mean0; q0 += v[0][j] * v[0][j]; v[1][j] -= mean1; q1 += v[1][j] * v[1][j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+    const float rs[2] = {rsqrtf(q0 * inv_d + eps), rsqrtf(q1 * inv_d + eps)};
+    const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
+    const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = pss * XPASS_ROWS + half * 16 + r2 + i;   // row within the tile
+      uint4 o;
+      o.x = sm100::pack_bf16x2(v[i][0] * rs[i] * mul[0] + add[0], v[i][1] * rs[i] * mul[1] + add[1]);
+      o.y = sm100::pack_bf16x2(v[i][2] * rs[i] * mul[2] + add[2], v[i][3] * rs[i] * mul[3] + add[3]);
+      o.z = sm100::pack_bf16x2(v[i][4] * rs[i] * mul[4] + add[4], v[i][5] * rs[i] * mul[5] + add[5]);
+      o.w = sm100::pack_bf16x2(v[i][6] * rs[i] * mul[6] + add[6], v[i][7] * rs[i] * mul[7] + add[7]);
+      *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
+    }
+    m0 = nm0; m1 = nm1; a0 = na0; a1 = na1;
+  }
+}
+
 // ==========================================================================================
 // GEMM with an A operand produced in-kernel (resident for the CTA's whole N loop)
 //
@@ -131,7 +207,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
   uint64_t* tmem_full = bars + 2 * NSTAGE;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* a_ready = tmem_empty + 2;        // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint64_t* x_full = a_ready + 1;            // [2]  (PRO_LN: X passes landed)
+  uint64_t* x_empty = x_full + 2;            // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(x_empty + 2);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -150,6 +228,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
       sm100::mbar_init(&tmem_empty[i], EPI_WARPS);
     }
     sm100::mbar_init(a_ready, EPI_WARPS);
+    for (uint32_t i = 0; i < 2; ++i) { sm100::mbar_init(&x_full[i], 1); sm100::mbar_init(&x_empty[i], EPI_WARPS); }
     sm100::fence_barrier_init();
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -162,9 +241,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
     // ===================== TMA producer: stream packed weight slabs ======================
     if (lane == 0) {
       RingState rs;
+      if constexpr (PRO == PRO_LN) {  // the X tile goes first: the prologue is on the critical path
+        producer_issue_x_pass(p.X, row_tile, 0, smStg, x_full);
+        producer_issue_x_pass(p.X, row_tile, 1, smStg, x_full);
+      }
+      int issued = 0;
       for (int t = 0; t < ntiles; ++t) {
         const bf16* wt = p.Wp + (size_t)(tile0 + t) * KSLABS_D * B_SLAB_ELEMS;
         for (int ks = 0; ks < KSLABS_D; ++ks) {
+          if constexpr (PRO == PRO_LN) {
+            if (issued == (int)NSTAGE) {  // ring primed; refill the X buffers before blocking on the weight ring
+              for (int pss = 2; pss < 4; ++pss) {
+                sm100::mbar_wait(&x_empty[pss & 1], 0);
+                producer_issue_x_pass(p.X, row_tile, pss, smStg, x_full);
+              }
+            }
+          }
+          ++issued;
           sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
           sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
           sm100::bulk_g2s(smB + rs.stage * B_SLAB_BYTES, wt + (size_t)ks * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
@@ -206,38 +299,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
 
     // ---------- produce the A tile (128 rows x 256 K, bf16, swizzled); warp ew owns rows [8*ew, 8*ew+8) ----------
     if constexpr (PRO == PRO_LN) {
-      const float inv_d = 1.0f / D;
-      const int slot = row_tile * 8 + (ew >> 1);
-      const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride;
-      const float4 m0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8);
-      const float4 m1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_mul + lane * 8 + 4);
-      const float4 a0 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8);
-      const float4 a1 = *reinterpret_cast<const float4*>(mrow + p.mod_off_add + lane * 8 + 4);
-      const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
-      const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll 4
-      for (int i = 0; i < 8; ++i) {
-        const int r = ew * 8 + i;  // row within tile
-        const float* xr = p.X + ((size_t)row_tile * BLOCK_M + r) * D + lane * 8;
-        const float4 x0 = *reinterpret_cast<const float4*>(xr);
-        const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
-        float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[j];
-        const float mean = sm100::warp_sum(s) * inv_d;
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { v[j] -= mean; ss += v[j] * v[j]; }
-        const float rstd = rsqrtf(sm100::warp_sum(ss) * inv_d + p.eps);
-        uint4 o;
-        o.x = sm100::pack_bf16x2(v[0] * rstd * mul[0] + add[0], v[1] * rstd * mul[1] + add[1]);
-        o.y = sm100::pack_bf16x2(v[2] * rstd * mul[2] + add[2], v[3] * rstd * mul[3] + add[3]);
-        o.z = sm100::pack_bf16x2(v[4] * rstd * mul[4] + add[4], v[5] * rstd * mul[5] + add[5]);
-        o.w = sm100::pack_bf16x2(v[6] * rstd * mul[6] + add[6], v[7] * rstd * mul[7] + add[7]);
-        // column 8*lane -> slab lane/8, 16-byte chunk lane%8
-        *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
-      }
+      ln_prologue_tma(smStg, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane);
     } else {
       // PRO_COND: A[m][k] = SiLU(temb[k] + cls[m][k])
 #pragma unroll 4
@@ -415,6 +477,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
 constexpr size_t ares_smem_bytes() {
   return 1024 + KSLABS_D * A_SLAB_BYTES + 3 * B_SLAB_BYTES + STG_ARES_BYTES + 256;
 }
+static_assert(2 * XPASS_BYTES <= STG_ARES_BYTES, "X pass buffers alias the epilogue staging");
 
 // ==========================================================================================
 // GEMM with both operands streamed by bulk TMA; epilogue x += gate * (acc + bias)
@@ -554,6 +617,236 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
 }
 
 constexpr size_t astream_smem_bytes() { return 1024 + 3 * (A_SLAB_BYTES + B_SLAB_BYTES) + STG_BYTES + 9 * D * 4 + 256; }
+
+// ==========================================================================================
+// Fused MLP half of a DiT block (layers.py:219-221): x += gate * c_proj( silu(w1 h) * (w2 h) ),  h = LN(x)*(1+c3)+c4
+//
+//   prologue   LN + modulate -> A tile (4 swizzled slabs, smem); X rows arrive by bulk TMA (ln_prologue_tma)
+//   per hidden chunk j (128 hidden units):
+//     M1_j     acc1[128 x 256] = A x [w1_j | w2_j]^T            (TMEM cols 0-255)
+//     E1_j     acc1 -> registers -> silu(a)*b -> bf16 -> H_j (2 swizzled slabs in smem = A operand of M2_j)
+//     M2_j     acc2[128 x 256] += H_j x w3_j^T                   (TMEM cols 256-511)
+//   epilogue   x += gate * acc2   (smem-staged coalesced RMW; staging reuses the A tile)
+//
+// The MMA issue order M1_0, M1_1, M2_0, M1_2, M2_1, ... keeps the tensor pipe busy while E1_j runs, and the weight
+// slabs are packed in exactly that order (pack.py: mlp stream) so the producer is one linear bulk-TMA stream.
+// The hidden activations never leave the SM.
+// ==========================================================================================
+struct MlpFusedParams {
+  float* X;               // residual stream [rows_pad][256] fp32, updated in place
+  const float* mod;
+  const int* slot_mod;
+  int mod_stride;
+  int mod_off_mul, mod_off_add, mod_off_gate;
+  float eps;
+  const bf16* Wstream;    // [n_slabs][256 x 64 swizzled] in consumption order
+  int n_chunks;           // ceil(hidden/128)
+  int hid_slabs;          // ceil(hidden/64)
+  long long* dbg;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFusedParams p) {
+  constexpr uint32_t NSTAGE = 3;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                                     // 4 x 16 KB (later: epilogue staging + gates)
+  uint8_t* smH = smA + KSLABS_D * A_SLAB_BYTES;            // 2 x (2 x 16 KB); first the X pass buffers
+  uint8_t* smB = smH + 4 * A_SLAB_BYTES;                   // NSTAGE x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + NSTAGE * B_SLAB_BYTES);
+  uint64_t* full = bars;                  // [3]
+  uint64_t* empty = bars + 3;             // [3]
+  uint64_t* a_ready = bars + 6;
+  uint64_t* acc1_full = bars + 7;
+  uint64_t* acc1_free = bars + 8;
+  uint64_t* h_ready = bars + 9;           // [2]
+  uint64_t* h_free = bars + 11;           // [2]
+  uint64_t* acc2_full = bars + 13;
+  uint64_t* x_full = bars + 14;           // [2]
+  uint64_t* x_empty = bars + 16;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_tile = blockIdx.x;
+  const int T = p.n_chunks;
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 0);
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < NSTAGE; ++i) { sm100::mbar_init(&full[i], 1); sm100::mbar_init(&empty[i], 1); }
+    sm100::mbar_init(a_ready, EPI_WARPS);
+    sm100::mbar_init(acc1_full, 1);
+    sm100::mbar_init(acc1_free, EPI_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      sm100::mbar_init(&h_ready[i], EPI_WARPS); sm100::mbar_init(&h_free[i], 1);
+      sm100::mbar_init(&x_full[i], 1); sm100::mbar_init(&x_empty[i], EPI_WARPS);
+    }
+    sm100::mbar_init(acc2_full, 1);
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  auto m2_slabs = [&](int j) { return min(2, p.hid_slabs - 2 * j); };
+
+  if (warp == 0) {
+    // ===================== producer: X passes, then one linear stream of weight slabs =======
+    if (lane == 0) {
+      int total = 0;
+      for (int j = 0; j < T; ++j) total += KSLABS_D + m2_slabs(j);
+      RingState rs;
+      producer_issue_x_pass(p.X, row_tile, 0, smH, x_full);   // X streams through the (still idle) H buffers
+      producer_issue_x_pass(p.X, row_tile, 1, smH, x_full);
+      for (int i = 0; i < total; ++i) {
+        if (i == (int)NSTAGE) {  // ring primed; refill the X buffers before blocking on the weight ring
+          for (int pss = 2; pss < 4; ++pss) {
+            sm100::mbar_wait(&x_empty[pss & 1], 0);
+            producer_issue_x_pass(p.X, row_tile, pss, smH, x_full);
+          }
+        }
+        sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+        sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
+        sm100::bulk_g2s(smB + rs.stage * B_SLAB_BYTES, p.Wstream + (size_t)i * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
+        rs.advance(NSTAGE);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =======================================================
+    if (lane == 0) {
+      const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
+      const uint32_t acc1 = tmem_base, acc2 = tmem_base + BLOCK_N;
+      dbg_stamp(p.dbg, 1);
+      sm100::mbar_wait(a_ready, 0);
+      sm100::tc_fence_after();
+      dbg_stamp(p.dbg, 2);
+      RingState rs;
+      for (int j = 0; j <= T; ++j) {
+        if (j < T) {  // M1_j
+          if (j > 0) { sm100::mbar_wait(acc1_free, (j - 1) & 1); sm100::tc_fence_after(); }
+          for (int ks = 0; ks < KSLABS_D; ++ks) {
+            sm100::mbar_wait(&full[rs.stage], rs.phase);
+            sm100::tc_fence_after();
+            issue_slab_mmas(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smB + rs.stage * B_SLAB_BYTES), idesc, ks == 0);
+            sm100::umma_commit(&empty[rs.stage]);
+            rs.advance(NSTAGE);
+          }
+          sm100::umma_commit(acc1_full);
+        }
+        if (j >= 1) {  // M2_{j-1}
+          const int c = j - 1, b = c & 1;
+          sm100::mbar_wait(&h_ready[b], (c >> 1) & 1);
+          sm100::tc_fence_after();
+          const int ns = m2_slabs(c);
+          for (int s2 = 0; s2 < ns; ++s2) {
+            sm100::mbar_wait(&full[rs.stage], rs.phase);
+            sm100::tc_fence_after();
+            issue_slab_mmas(acc2, sm100::smem_u32(smH + (b * 2 + s2) * A_SLAB_BYTES), sm100::smem_u32(smB + rs.stage * B_SLAB_BYTES), idesc,
+                            c == 0 && s2 == 0);
+            sm100::umma_commit(&empty[rs.stage]);
+            rs.advance(NSTAGE);
+          }
+          sm100::umma_commit(&h_free[b]);
+        }
+      }
+      sm100::umma_commit(acc2_full);
+    }
+  } else {
+    // ===================== 16 prologue / epilogue warps ====================================
+    const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
+    const uint32_t row = q * 32 + lane;
+    ln_prologue_tma(smH, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane);
+    sm100::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) sm100::mbar_arrive(a_ready);
+    if (etid == 0) dbg_stamp(p.dbg, 3);
+
+    // ---------- E1_j: SwiGLU of hidden chunk j into the A slabs of M2_j ----------
+    const int hs = sub >> 1, h = sub & 1;   // this warp: slab hs of the chunk, 32-column half h
+    for (int j = 0; j < T; ++j) {
+      sm100::mbar_wait(acc1_full, j & 1);
+      sm100::tc_fence_after();
+      if (etid == 0 && j < 6) dbg_stamp(p.dbg, 4 + 2 * j);
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+      uint32_t va[32], vb[32];
+      sm100::tmem_ld_32x32b_x32(taddr + hs * 64 + h * 32, va);
+      sm100::tmem_ld_32x32b_x32(taddr + 128 + hs * 64 + h * 32, vb);
+      sm100::tmem_ld_wait();
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(acc1_free);          // M1_{j+1} may overwrite acc1
+      const int b = j & 1;
+      if (j >= 2) sm100::mbar_wait(&h_free[b], ((j >> 1) - 1) & 1);   // M2_{j-2} finished reading this buffer
+      uint8_t* buf = smH + (b * 2 + hs) * A_SLAB_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float hv[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) hv[jj] = sm100::silu_tanh(__uint_as_float(va[c * 8 + jj])) * __uint_as_float(vb[c * 8 + jj]);
+        uint4 o;
+        o.x = sm100::pack_bf16x2(hv[0], hv[1]);
+        o.y = sm100::pack_bf16x2(hv[2], hv[3]);
+        o.z = sm100::pack_bf16x2(hv[4], hv[5]);
+        o.w = sm100::pack_bf16x2(hv[6], hv[7]);
+        *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, h * 4 + c)) = o;
+      }
+      sm100::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&h_ready[b]);
+      if (etid == 0 && j < 6) dbg_stamp(p.dbg, 5 + 2 * j);
+    }
+
+    // ---------- final epilogue: x += gate * acc2 ----------
+    float* smGate = reinterpret_cast<float*>(smA + STG_BYTES);   // the A tile is dead once acc2 is complete
+    const uint32_t cc = etid & 15;
+    float4 x[2][4];
+    auto load_chunk = [&](int ch, int bufi) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
+        x[bufi][it] = *reinterpret_cast<const float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + ch * 64 + cc * 4);
+      }
+    };
+    load_chunk(0, 0);
+    const int gcell = etid >> 6, gc4 = etid & 63;
+    const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod[row_tile * 8 + gcell] * p.mod_stride + p.mod_off_gate + gc4 * 4);
+    sm100::mbar_wait(acc2_full, 0);
+    sm100::tc_fence_after();
+    if (etid == 0) dbg_stamp(p.dbg, 20);
+    reinterpret_cast<float4*>(smGate)[etid] = gate_v;
+    const uint32_t taddr2 = tmem_base + ((q * 32u) << 16) + BLOCK_N;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int col = ch * 64 + cc * 4;
+      if (ch + 1 < 4) load_chunk(ch + 1, (ch + 1) & 1);
+      sm100::named_bar_sync(1, EPI_THREADS);
+      {
+        uint32_t v[16];
+        sm100::tmem_ld_32x32b_x16(taddr2 + ch * 64 + sub * 16, v);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(smA + row * 272 + (sub * 4 + c) * 16) = make_float4(
+              __uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
+      }
+      sm100::named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
+        const float4 a = *reinterpret_cast<const float4*>(smA + r * 272 + cc * 16);
+        const float4 gg = *reinterpret_cast<const float4*>(smGate + (r >> 4) * D + col);
+        float4 o = x[ch & 1][it];
+        o.x += gg.x * a.x; o.y += gg.y * a.y; o.z += gg.z * a.z; o.w += gg.w * a.w;
+        *reinterpret_cast<float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + col) = o;
+      }
+    }
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) sm100::tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 31);
+}
+
+constexpr size_t mlp_fused_smem_bytes() { return 1024 + (KSLABS_D + 4) * A_SLAB_BYTES + 3 * B_SLAB_BYTES + 256; }
+static_assert(2 * XPASS_BYTES <= 4 * A_SLAB_BYTES, "X pass buffers alias the H buffers");
 
 // ==========================================================================================
 // 16-token self attention, one warp per (slot, head), tensor cores via mma.sync m16n8k16 (bf16)

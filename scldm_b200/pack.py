@@ -12,6 +12,8 @@ Everything here is plain torch indexing and runs on CPU too (tests/test_pack.py)
 
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -105,6 +107,22 @@ class PackedDiT:
         self.w_mlp1 = dev(torch.stack(mlp1))
         self.w_mlp2 = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.mlp.c_proj.weight"), BLOCK_N)[0] for i in range(L)]))
         assert self.w_mlp2.shape[1] == self.hid_slabs
+        # fused-MLP weight stream: M1_0, M1_1, M2_0, M1_2, M2_1, ..., M2_{T-1} (csrc/dit_kernels.cuh: mlp_fused_kernel)
+        T = self.mlp1_tiles
+        streams = []
+        for i in range(L):
+            m1, m2 = self.w_mlp1[i], self.w_mlp2[i]   # [T][4][256*64], [hid_slabs][256*64]
+            parts = []
+            for j in range(T + 1):
+                if j < T:
+                    parts.append(m1[j])
+                if j >= 1:
+                    c = j - 1
+                    parts.append(m2[2 * c: min(2 * c + 2, self.hid_slabs)])
+            streams.append(torch.cat(parts, 0))
+        self.w_mlp_stream = torch.stack(streams).contiguous()
+        assert self.w_mlp_stream.shape[1] == 4 * T + self.hid_slabs
+        self.use_fused_mlp = os.environ.get("SCLDM_FUSED_MLP", "1") != "0"
         self.temb_w0t = f32(get("t_embedder.mlp.0.weight").T)
         self.temb_b0 = f32(get("t_embedder.mlp.0.bias"))
         self.temb_w2t = f32(get("t_embedder.mlp.2.weight").T)
@@ -119,6 +137,7 @@ class PackedDiT:
         s = _lib.DitWeights()
         s.n_layer, s.hidden, s.hid_slabs, s.mlp1_tiles = L, H, self.hid_slabs, self.mlp1_tiles
         s.mod_stride, s.n_class, s.eps = self.mod_stride, len(self.class_names), float(cfg.layernorm_eps)
+        s.w_mlp_stream = self.w_mlp_stream.data_ptr() if self.use_fused_mlp else None
         for name in ("w_mod", "b_mod", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_mlp1", "w_mlp2", "temb_w0t", "temb_b0",
                      "temb_w2t", "temb_b2", "w_in", "b_in", "pos", "w_out", "b_out"):
             setattr(s, name, getattr(self, name).data_ptr())

@@ -1,6 +1,10 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider 2>&1 | tail -3
-python bench.py > gpurun_out/bench_r01_default.json 2> gpurun_out/bench_r01_default.err; tail -c 1500 gpurun_out/bench_r01_default.json; tail -2 gpurun_out/bench_r01_default.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r01_reference.json 2>> gpurun_out/bench_r01_default.err; cat gpurun_out/bench_r01_reference.json | head -c 600
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2200 -c 2200 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 1 --warmup 1 --batch 784 --chunk 784 --no-cpu-baseline --no-e2e --no-prof > gpurun_out/ncu_launches.log 2>&1; tail -1 gpurun_out/ncu_launches.log; wc -l gpurun_out/r01_launches.csv
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_|attn16|mcab_decode_tc|final_step" -s 60 -c 14 -o gpurun_out/r01_prof_top python bench.py --steps 1 --warmup 1 --batch 784 --chunk 784 --no-cpu-baseline --no-e2e --no-prof > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log
+timeout 600 python -m pytest tests/test_gpu_dit.py -m gpu -q -x --timeout=240 -p no:cacheprovider -s 2>&1 | grep -E "passed|failed|stage errors|Error|error" | head
+SCLDM_FUSED_MLP=0 timeout 600 python -m pytest tests/test_gpu_dit.py -m gpu -q -x --timeout=240 -p no:cacheprovider 2>&1 | tail -1
+python tools/kernel_timeline.py 392 | grep -A1 -E "^mlp1|^proj"
+python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_v8.json 2>> gpurun_out/sweep.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_v8.json"))
+print("value", round(d["value"]), "model_tflops", d["model_tflops"], "roof", d["roofline"]["kernel"], d["roofline"]["frac"], d["roofline"]["avg_launch_us"])
+print("   ", {k:(v["share"], round(v["ms"]/v["launches"]*1000,1)) for k,v in list(d["kernel_breakdown"].items())[:10]})
+PY
