@@ -79,6 +79,9 @@ typedef struct scldm_dit_plan {
   int32_t n_mod;          /* distinct conditioning rows                                   */
   const int32_t* cls_idx; /* [n_class][n_mod_pad] embedding row per class (null = vocab)   */
   const int32_t* slot_mod;/* [slots_pad] conditioning row of every slot                    */
+  int32_t slot_mode;      /* 0: use the slot_mod table; 1: slot_mod[s] == s; 2: the shared-time CFG layout
+                             (slots [0,n_u) -> row 0; guided cell j, pass k: k==0 -> row 0, else 1 + j*(n_f-1) + k-1).
+                             Modes 1/2 let the kernels compute the row instead of loading it (no dependent load).  */
 } scldm_dit_plan;
 
 /* padded sizes the index arrays / workspace must honour (multiples of 8 slots / 128 mod rows) */

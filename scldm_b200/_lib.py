@@ -37,7 +37,7 @@ class DitWeights(C.Structure):
 class DitPlan(C.Structure):
     _fields_ = [
         ("n_u", C.c_int32), ("n_g", C.c_int32), ("n_f", C.c_int32), ("coef", C.c_float * MAX_COMBINE),
-        ("n_mod", C.c_int32), ("cls_idx", C.c_void_p), ("slot_mod", C.c_void_p),
+        ("n_mod", C.c_int32), ("cls_idx", C.c_void_p), ("slot_mod", C.c_void_p), ("slot_mode", C.c_int32),
     ]
 
 

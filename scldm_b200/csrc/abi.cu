@@ -119,6 +119,7 @@ int check_dit(const scldm_dit_weights* w, const scldm_dit_plan* plan) {
   if (plan->n_g > 0 && (plan->n_f < 1 || plan->n_f > SCLDM_MAX_COMBINE)) return fail(SCLDM_EINVAL, "n_f %d out of range", plan->n_f);
   if (plan->n_mod < 1) return fail(SCLDM_EINVAL, "n_mod must be >= 1");
   if (!plan->slot_mod || (w->n_class > 0 && !plan->cls_idx)) return fail(SCLDM_EINVAL, "null index arrays");
+  if (plan->slot_mode < 0 || plan->slot_mode > 2) return fail(SCLDM_EINVAL, "bad slot_mode %d", plan->slot_mode);
   return SCLDM_OK;
 }
 
@@ -156,6 +157,16 @@ int launch_mod(const scldm_dit_weights* w, const scldm_dit_plan* plan, const Dit
   return SCLDM_OK;
 }
 
+dit::ModIndex mod_index(const scldm_dit_plan* plan) {
+  dit::ModIndex mi{};
+  mi.table = plan->slot_mod;
+  mi.mode = plan->slot_mode;
+  mi.n_u = plan->n_u;
+  mi.n_f = plan->n_g > 0 ? plan->n_f : 1;
+  mi.n_slots = plan->n_u + plan->n_g * mi.n_f;
+  return mi;
+}
+
 // the n_layer adaLN blocks on the residual stream ws.X (reference layers.py:208-221)
 int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, cudaStream_t st) {
   const int slots_pad = scldm_dit_slots_pad(plan);
@@ -165,7 +176,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
     const int mo = l * 6 * dit::D;
     {  // LN1 + modulate + QKV
       dit::AResParams p{};
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride;
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
       p.mod_off_mul = mo + 0 * dit::D; p.mod_off_add = mo + 1 * dit::D; p.eps = w->eps;
       p.Wp = static_cast<const dit::bf16*>(w->w_qkv) + (size_t)l * 3 * tile_elems;
       p.n_tiles_total = 3; p.tiles_per_cta = 3;
@@ -179,13 +190,13 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       dit::AStreamParams p{};
       p.Ap = ws.ao; p.Wp = static_cast<const dit::bf16*>(w->w_proj) + (size_t)l * tile_elems; p.k_slabs = dit::KSLABS_D;
       p.bias = w->b_proj + (size_t)l * dit::D;
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 2 * dit::D;
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 2 * dit::D;
       p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + (1 << 17) : nullptr;
       LAUNCH("gemm_astream<proj>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
     }
     if (w->w_mlp_stream != nullptr) {  // fused MLP half: LN2 + modulate + [w1|w2] + SwiGLU + c_proj + gated residual
       dit::MlpFusedParams p{};
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride;
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
       p.mod_off_mul = mo + 3 * dit::D; p.mod_off_add = mo + 4 * dit::D; p.mod_off_gate = mo + 5 * dit::D; p.eps = w->eps;
       const size_t n_stream = (size_t)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs;
       p.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream) + (size_t)l * n_stream * dit::B_SLAB_ELEMS;
@@ -196,7 +207,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
     }
     {  // LN2 + modulate + [w1|w2] + SwiGLU
       dit::AResParams p{};
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride;
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
       p.mod_off_mul = mo + 3 * dit::D; p.mod_off_add = mo + 4 * dit::D; p.eps = w->eps;
       p.Wp = static_cast<const dit::bf16*>(w->w_mlp1) + (size_t)l * w->mlp1_tiles * tile_elems;
       p.n_tiles_total = w->mlp1_tiles; p.tiles_per_cta = w->mlp1_tiles;
@@ -208,7 +219,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       dit::AStreamParams p{};
       p.Ap = ws.hid; p.Wp = static_cast<const dit::bf16*>(w->w_mlp2) + (size_t)l * w->hid_slabs * dit::B_SLAB_ELEMS;
       p.k_slabs = w->hid_slabs; p.bias = nullptr;
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = plan->slot_mod; p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 5 * dit::D;
+      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 5 * dit::D;
       p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 3 * (1 << 17) : nullptr;
       LAUNCH("gemm_astream<mlp2>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
     }
@@ -218,7 +229,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
 
 dit::StepParams make_step(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws) {
   dit::StepParams s{};
-  s.X = ws.X; s.mod = ws.mod; s.slot_mod = plan->slot_mod; s.mod_stride = w->mod_stride;
+  s.X = ws.X; s.mod = ws.mod; s.slot_mod = mod_index(plan); s.mod_stride = w->mod_stride;
   s.mod_off_final = w->n_layer * 6 * dit::D; s.eps = w->eps;
   s.w_out = w->w_out; s.b_out = w->b_out; s.w_in = w->w_in; s.b_in = w->b_in; s.pos = w->pos;
   s.n_u = plan->n_u; s.n_g = plan->n_g; s.n_f = plan->n_g > 0 ? plan->n_f : 1;

@@ -43,11 +43,27 @@ constexpr int MAX_COMBINE = 8;
 enum { PRO_LN = 0, PRO_COND = 1 };
 enum { EPI_QKV = 0, EPI_SWIGLU = 1, EPI_MOD = 2 };
 
+// Conditioning row of a slot: table lookup, or computed (no dependent load on the critical path)
+//   mode 0: table[slot];  mode 1: identity;  mode 2: CFG layout with shared time (nnets.py:336-378 batched):
+//   slots [0,n_u) -> row 0; guided cell j owns n_f slots: pass 0 -> row 0 (unconditional), pass k -> row 1 + j*(n_f-1) + k-1
+struct ModIndex {
+  const int* table;
+  int mode, n_u, n_f, n_slots;
+  __device__ __forceinline__ int row(int slot) const {
+    if (mode == 0) return table[slot];
+    if (slot >= n_slots) return 0;
+    if (mode == 1) return slot;
+    if (slot < n_u) return 0;
+    const int j = (slot - n_u) / n_f, k = (slot - n_u) - j * n_f;
+    return k == 0 ? 0 : 1 + j * (n_f - 1) + (k - 1);
+  }
+};
+
 struct AResParams {
   // ---- A operand source -----------------------------------------------------------------
   const float* X;        // PRO_LN: residual stream [rows_pad][256] fp32
   const float* mod;      // PRO_LN: modulation table [n_mod_pad][mod_stride] fp32
-  const int* slot_mod;   // PRO_LN: [slots_pad] -> row of mod
+  ModIndex slot_mod;     // PRO_LN: slot -> row of mod
   int mod_stride;
   int mod_off_mul;       // column offset of the multiplicative chunk (h = LN(x)*(1+mul)+add)
   int mod_off_add;
@@ -76,7 +92,7 @@ struct AStreamParams {
   const float* bias;     // [256] or nullptr
   float* X;              // residual stream, updated in place
   const float* mod;
-  const int* slot_mod;
+  ModIndex slot_mod;
   int mod_stride;
   int mod_off_gate;
   long long* dbg;
@@ -116,38 +132,45 @@ __device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_d, uint32_t a_smem
 // the bf16 A tile in the swizzled UMMA layout.  No long-latency global loads sit in the warps' dependency chains.
 // ------------------------------------------------------------------------------------------
 constexpr int XPASS_ROWS = 32;
-constexpr int XPASS_BYTES = XPASS_ROWS * D * 4;   // 32 KB
+constexpr int XPASS_BYTES = XPASS_ROWS * D * 4;   // 32 KB = one weight-ring stage
 
-__device__ __forceinline__ void producer_issue_x_pass(const float* X, int row_tile, int pass, uint8_t* smX, uint64_t* x_full) {
-  sm100::mbar_arrive_expect_tx(&x_full[pass & 1], XPASS_BYTES);
-  sm100::bulk_g2s(smX + (pass & 1) * XPASS_BYTES, X + ((size_t)row_tile * BLOCK_M + pass * XPASS_ROWS) * D, XPASS_BYTES, &x_full[pass & 1]);
+// All four X passes are in flight from t=0: passes 0,1 land in a 64 KB scratch region (epilogue staging / H buffers),
+// passes 2,3 in the two weight-ring buffers that the first weight slabs do not need yet (the ring starts at physical
+// buffer 2; see ring_buf()).  x_full[p] completes when pass p landed; x_empty[p-2] when a borrowed ring buffer is free.
+__device__ __forceinline__ uint32_t ring_buf(uint32_t stage) { return (stage + 2u) % 3u; }   // logical stage -> physical buffer
+
+__device__ __forceinline__ uint8_t* x_pass_buffer(int pass, uint8_t* smScratch, uint8_t* smB) {
+  return pass < 2 ? smScratch + pass * XPASS_BYTES : smB + (pass - 2) * XPASS_BYTES;
 }
 
-__device__ __forceinline__ void ln_prologue_tma(const uint8_t* smX, uint64_t* x_full, uint64_t* x_empty, uint8_t* smA, const float* mod,
-                                                const int* slot_mod, int mod_stride, int off_mul, int off_add, float eps, int row_tile,
-                                                uint32_t ew, uint32_t lane) {
+__device__ __forceinline__ void producer_issue_x_passes(const float* X, int row_tile, uint8_t* smScratch, uint8_t* smB, uint64_t* x_full) {
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    sm100::mbar_arrive_expect_tx(&x_full[pass], XPASS_BYTES);
+    sm100::bulk_g2s(x_pass_buffer(pass, smScratch, smB), X + ((size_t)row_tile * BLOCK_M + pass * XPASS_ROWS) * D, XPASS_BYTES, &x_full[pass]);
+  }
+}
+
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int slot);
+__device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB, uint64_t* x_full, uint64_t* x_empty, uint8_t* smA,
+                                                const float* mod, const ModIndex& slot_mod, int mod_stride, int off_mul, int off_add,
+                                                float eps, int row_tile, uint32_t ew, uint32_t lane, long long* dbg = nullptr) {
   const float inv_d = 1.0f / D;
   const int half = ew >> 3;          // which of the pass's two slots this warp serves
   const int r2 = (ew & 7) * 2;       // first of this warp's two rows inside that slot
-  int mr[4];
+  // modulation vectors of this warp's 4 slots: issued before anything is waited on
+  float4 m0[4], m1[4], a0[4], a1[4];
 #pragma unroll
-  for (int pss = 0; pss < 4; ++pss) mr[pss] = slot_mod[row_tile * 8 + 2 * pss + half];
-  float4 m0, m1, a0, a1;
-  {
-    const float* mrow = mod + (size_t)mr[0] * mod_stride;
-    m0 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8); m1 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8 + 4);
-    a0 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8); a1 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8 + 4);
+  for (int pss = 0; pss < 4; ++pss) {
+    const float* mrow = mod + (size_t)slot_mod.row(row_tile * 8 + 2 * pss + half) * mod_stride;
+    m0[pss] = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8); m1[pss] = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8 + 4);
+    a0[pss] = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8); a1[pss] = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8 + 4);
   }
 #pragma unroll
   for (int pss = 0; pss < 4; ++pss) {
-    float4 nm0 = m0, nm1 = m1, na0 = a0, na1 = a1;
-    if (pss + 1 < 4) {  // prefetch the next pass's modulation vectors
-      const float* mrow = mod + (size_t)mr[pss + 1] * mod_stride;
-      nm0 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8); nm1 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8 + 4);
-      na0 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8); na1 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8 + 4);
-    }
-    sm100::mbar_wait(&x_full[pss & 1], (pss >> 1) & 1);
-    const uint8_t* xb = smX + (pss & 1) * XPASS_BYTES + (half * 16 + r2) * (D * 4) + lane * 32;
+    sm100::mbar_wait(&x_full[pss], 0);
+    if (ew == 0 && lane == 0) dbg_stamp(dbg, 22 + pss);
+    const uint8_t* xb = x_pass_buffer(pss, smScratch, smB) + (half * 16 + r2) * (D * 4) + lane * 32;
     float v[2][8];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -155,8 +178,10 @@ __device__ __forceinline__ void ln_prologue_tma(const uint8_t* smX, uint64_t* x_
       const float4 x1 = *reinterpret_cast<const float4*>(xb + i * (D * 4) + 16);
       v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w; v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
     }
-    __syncwarp();
-    if (pss < 2 && lane == 0) sm100::mbar_arrive(&x_empty[pss & 1]);   // buffer may be refilled with pass pss+2
+    if (pss >= 2) {   // hand the borrowed weight-ring buffer back to the producer
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&x_empty[pss - 2]);
+    }
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s0 += v[0][j]; s1 += v[1][j]; }
@@ -169,8 +194,9 @@ __device__ __forceinline__ void ln_prologue_tma(const uint8_t* smX, uint64_t* x_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
     const float rs[2] = {rsqrtf(q0 * inv_d + eps), rsqrtf(q1 * inv_d + eps)};
-    const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
-    const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (ew == 0 && lane == 0 && pss == 0) dbg_stamp(dbg, 26);
+    const float mul[8] = {1.f + m0[pss].x, 1.f + m0[pss].y, 1.f + m0[pss].z, 1.f + m0[pss].w, 1.f + m1[pss].x, 1.f + m1[pss].y, 1.f + m1[pss].z, 1.f + m1[pss].w};
+    const float add[8] = {a0[pss].x, a0[pss].y, a0[pss].z, a0[pss].w, a1[pss].x, a1[pss].y, a1[pss].z, a1[pss].w};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int r = pss * XPASS_ROWS + half * 16 + r2 + i;   // row within the tile
@@ -181,7 +207,6 @@ __device__ __forceinline__ void ln_prologue_tma(const uint8_t* smX, uint64_t* x_
       o.w = sm100::pack_bf16x2(v[i][6] * rs[i] * mul[6] + add[6], v[i][7] * rs[i] * mul[7] + add[7]);
       *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
     }
-    m0 = nm0; m1 = nm1; a0 = na0; a1 = na1;
   }
 }
 
@@ -195,6 +220,7 @@ __device__ __forceinline__ void ln_prologue_tma(const uint8_t* smX, uint64_t* x_
 template <int PRO, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResParams p) {
   constexpr uint32_t NSTAGE = 3;
+  constexpr int EARLY = PRO == PRO_LN ? 1 : 3;   // weight slabs issued before the setup barrier (PRO_LN lends 2 buffers to X)
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column fp32 accumulators
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -207,8 +233,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
   uint64_t* tmem_full = bars + 2 * NSTAGE;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* a_ready = tmem_empty + 2;        // [1]
-  uint64_t* x_full = a_ready + 1;            // [2]  (PRO_LN: X passes landed)
-  uint64_t* x_empty = x_full + 2;            // [2]
+  uint64_t* x_full = a_ready + 1;            // [4]  (PRO_LN: X passes landed)
+  uint64_t* x_empty = x_full + 4;            // [2]  (borrowed ring buffers handed back)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(x_empty + 2);
 
   const uint32_t warp = threadIdx.x >> 5;
@@ -228,8 +254,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
       sm100::mbar_init(&tmem_empty[i], EPI_WARPS);
     }
     sm100::mbar_init(a_ready, EPI_WARPS);
-    for (uint32_t i = 0; i < 2; ++i) { sm100::mbar_init(&x_full[i], 1); sm100::mbar_init(&x_empty[i], EPI_WARPS); }
+    for (uint32_t i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
+    for (uint32_t i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], EPI_WARPS);
     sm100::fence_barrier_init();
+    // first loads go out before the setup barrier: the X tile (all four passes) and the first weight slab(s)
+    if constexpr (PRO == PRO_LN) producer_issue_x_passes(p.X, row_tile, smStg, smB, x_full);
+    for (int i = 0; i < EARLY; ++i) {
+      sm100::mbar_arrive_expect_tx(&full[i], B_SLAB_BYTES);
+      sm100::bulk_g2s(smB + ring_buf(i) * B_SLAB_BYTES, p.Wp + ((size_t)tile0 * KSLABS_D + i) * B_SLAB_ELEMS, B_SLAB_BYTES, &full[i]);
+    }
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   sm100::tc_fence_before();
@@ -241,28 +274,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
     // ===================== TMA producer: stream packed weight slabs ======================
     if (lane == 0) {
       RingState rs;
-      if constexpr (PRO == PRO_LN) {  // the X tile goes first: the prologue is on the critical path
-        producer_issue_x_pass(p.X, row_tile, 0, smStg, x_full);
-        producer_issue_x_pass(p.X, row_tile, 1, smStg, x_full);
-      }
-      int issued = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        const bf16* wt = p.Wp + (size_t)(tile0 + t) * KSLABS_D * B_SLAB_ELEMS;
-        for (int ks = 0; ks < KSLABS_D; ++ks) {
-          if constexpr (PRO == PRO_LN) {
-            if (issued == (int)NSTAGE) {  // ring primed; refill the X buffers before blocking on the weight ring
-              for (int pss = 2; pss < 4; ++pss) {
-                sm100::mbar_wait(&x_empty[pss & 1], 0);
-                producer_issue_x_pass(p.X, row_tile, pss, smStg, x_full);
-              }
-            }
-          }
-          ++issued;
-          sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
-          sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
-          sm100::bulk_g2s(smB + rs.stage * B_SLAB_BYTES, wt + (size_t)ks * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
-          rs.advance(NSTAGE);
+      for (int i = 0; i < EARLY; ++i) rs.advance(NSTAGE);
+      for (int i = EARLY; i < ntiles * KSLABS_D; ++i) {
+        if constexpr (PRO == PRO_LN) {
+          if (i == 1 || i == 2) sm100::mbar_wait(&x_empty[i - 1], 0);   // first use of a ring buffer that carried an X pass
         }
+        sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+        sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
+        sm100::bulk_g2s(smB + ring_buf(rs.stage) * B_SLAB_BYTES, p.Wp + ((size_t)tile0 * KSLABS_D + i) * B_SLAB_ELEMS, B_SLAB_BYTES,
+                        &full[rs.stage]);
+        rs.advance(NSTAGE);
       }
     }
   } else if (warp == 1) {
@@ -282,7 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
         for (int ks = 0; ks < KSLABS_D; ++ks) {
           sm100::mbar_wait(&full[rs.stage], rs.phase);
           sm100::tc_fence_after();
-          issue_slab_mmas(tmem_d, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smB + rs.stage * B_SLAB_BYTES),
+          issue_slab_mmas(tmem_d, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smB + ring_buf(rs.stage) * B_SLAB_BYTES),
                           idesc, ks == 0);
           sm100::umma_commit(&empty[rs.stage]);  // frees the B stage when these MMAs retire
           rs.advance(NSTAGE);
@@ -299,7 +320,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
 
     // ---------- produce the A tile (128 rows x 256 K, bf16, swizzled); warp ew owns rows [8*ew, 8*ew+8) ----------
     if constexpr (PRO == PRO_LN) {
-      ln_prologue_tma(smStg, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane);
+      ln_prologue_tma(smStg, smB, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane);
     } else {
       // PRO_COND: A[m][k] = SiLU(temb[k] + cls[m][k])
 #pragma unroll 4
@@ -510,6 +531,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
     }
     sm100::mbar_init(tmem_full, 1);
     sm100::fence_barrier_init();
+    // the first ring of loads goes out before the setup barrier
+    const bf16* a_src0 = p.Ap + (size_t)row_tile * p.k_slabs * A_SLAB_ELEMS;
+    for (int i = 0; i < (int)NSTAGE && i < p.k_slabs; ++i) {
+      sm100::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
+      sm100::bulk_g2s(smStage + i * STAGE_BYTES, a_src0 + (size_t)i * A_SLAB_ELEMS, A_SLAB_BYTES, &full[i]);
+      sm100::bulk_g2s(smStage + i * STAGE_BYTES + A_SLAB_BYTES, p.Wp + (size_t)i * B_SLAB_ELEMS, B_SLAB_BYTES, &full[i]);
+    }
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   sm100::tc_fence_before();
@@ -521,7 +549,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
     if (lane == 0) {
       RingState rs;
       const bf16* a_src = p.Ap + (size_t)row_tile * p.k_slabs * A_SLAB_ELEMS;
-      for (int ks = 0; ks < p.k_slabs; ++ks) {
+      for (int i = 0; i < (int)NSTAGE && i < p.k_slabs; ++i) rs.advance(NSTAGE);
+      for (int ks = NSTAGE; ks < p.k_slabs; ++ks) {
         sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
         sm100::mbar_arrive_expect_tx(&full[rs.stage], STAGE_BYTES);
         uint8_t* st = smStage + rs.stage * STAGE_BYTES;
@@ -558,7 +587,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
     {
       // 8 cells x 64 float4 = 512 float4: one per thread
       const int cell = etid >> 6, c4 = etid & 63;
-      const int mr = p.slot_mod[row_tile * 8 + cell];
+      const int mr = p.slot_mod.row(row_tile * 8 + cell);
       reinterpret_cast<float4*>(smGate)[etid] =
           *reinterpret_cast<const float4*>(p.mod + (size_t)mr * p.mod_stride + p.mod_off_gate + c4 * 4);
       if (etid < 64)
@@ -635,7 +664,7 @@ constexpr size_t astream_smem_bytes() { return 1024 + 3 * (A_SLAB_BYTES + B_SLAB
 struct MlpFusedParams {
   float* X;               // residual stream [rows_pad][256] fp32, updated in place
   const float* mod;
-  const int* slot_mod;
+  ModIndex slot_mod;
   int mod_stride;
   int mod_off_mul, mod_off_add, mod_off_gate;
   float eps;
@@ -661,9 +690,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
   uint64_t* h_ready = bars + 9;           // [2]
   uint64_t* h_free = bars + 11;           // [2]
   uint64_t* acc2_full = bars + 13;
-  uint64_t* x_full = bars + 14;           // [2]
-  uint64_t* x_empty = bars + 16;          // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* x_full = bars + 14;           // [4]
+  uint64_t* x_empty = bars + 18;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_tile = blockIdx.x;
@@ -676,10 +705,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     sm100::mbar_init(acc1_free, EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&h_ready[i], EPI_WARPS); sm100::mbar_init(&h_free[i], 1);
-      sm100::mbar_init(&x_full[i], 1); sm100::mbar_init(&x_empty[i], EPI_WARPS);
+      sm100::mbar_init(&x_empty[i], EPI_WARPS);
     }
+    for (int i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
     sm100::mbar_init(acc2_full, 1);
     sm100::fence_barrier_init();
+    // first loads go out before the setup barrier: all four X passes (H buffers + two idle ring buffers) and weight slab 0
+    producer_issue_x_passes(p.X, row_tile, smH, smB, x_full);
+    sm100::mbar_arrive_expect_tx(&full[0], B_SLAB_BYTES);
+    sm100::bulk_g2s(smB + ring_buf(0) * B_SLAB_BYTES, p.Wstream, B_SLAB_BYTES, &full[0]);
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
   sm100::tc_fence_before();
@@ -694,18 +728,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
       int total = 0;
       for (int j = 0; j < T; ++j) total += KSLABS_D + m2_slabs(j);
       RingState rs;
-      producer_issue_x_pass(p.X, row_tile, 0, smH, x_full);   // X streams through the (still idle) H buffers
-      producer_issue_x_pass(p.X, row_tile, 1, smH, x_full);
-      for (int i = 0; i < total; ++i) {
-        if (i == (int)NSTAGE) {  // ring primed; refill the X buffers before blocking on the weight ring
-          for (int pss = 2; pss < 4; ++pss) {
-            sm100::mbar_wait(&x_empty[pss & 1], 0);
-            producer_issue_x_pass(p.X, row_tile, pss, smH, x_full);
-          }
-        }
+      rs.advance(NSTAGE);   // slab 0 was issued during setup
+      for (int i = 1; i < total; ++i) {
+        if (i == 1 || i == 2) sm100::mbar_wait(&x_empty[i - 1], 0);   // first use of a ring buffer that carried an X pass
         sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
         sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
-        sm100::bulk_g2s(smB + rs.stage * B_SLAB_BYTES, p.Wstream + (size_t)i * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
+        sm100::bulk_g2s(smB + ring_buf(rs.stage) * B_SLAB_BYTES, p.Wstream + (size_t)i * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
         rs.advance(NSTAGE);
       }
     }
@@ -725,7 +753,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
           for (int ks = 0; ks < KSLABS_D; ++ks) {
             sm100::mbar_wait(&full[rs.stage], rs.phase);
             sm100::tc_fence_after();
-            issue_slab_mmas(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smB + rs.stage * B_SLAB_BYTES), idesc, ks == 0);
+            issue_slab_mmas(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smB + ring_buf(rs.stage) * B_SLAB_BYTES), idesc, ks == 0);
             sm100::umma_commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
           }
@@ -739,7 +767,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
           for (int s2 = 0; s2 < ns; ++s2) {
             sm100::mbar_wait(&full[rs.stage], rs.phase);
             sm100::tc_fence_after();
-            issue_slab_mmas(acc2, sm100::smem_u32(smH + (b * 2 + s2) * A_SLAB_BYTES), sm100::smem_u32(smB + rs.stage * B_SLAB_BYTES), idesc,
+            issue_slab_mmas(acc2, sm100::smem_u32(smH + (b * 2 + s2) * A_SLAB_BYTES), sm100::smem_u32(smB + ring_buf(rs.stage) * B_SLAB_BYTES), idesc,
                             c == 0 && s2 == 0);
             sm100::umma_commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
@@ -753,7 +781,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     // ===================== 16 prologue / epilogue warps ====================================
     const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
-    ln_prologue_tma(smH, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane);
+    ln_prologue_tma(smH, smB, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg);
     sm100::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) sm100::mbar_arrive(a_ready);
@@ -807,7 +835,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     };
     load_chunk(0, 0);
     const int gcell = etid >> 6, gc4 = etid & 63;
-    const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod[row_tile * 8 + gcell] * p.mod_stride + p.mod_off_gate + gc4 * 4);
+    const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod.row(row_tile * 8 + gcell) * p.mod_stride + p.mod_off_gate + gc4 * 4);
     sm100::mbar_wait(acc2_full, 0);
     sm100::tc_fence_after();
     if (etid == 0) dbg_stamp(p.dbg, 20);
@@ -1008,7 +1036,7 @@ __global__ void __launch_bounds__(256) cls_kernel(const ClsParams p, float* __re
 struct StepParams {
   float* X;               // residual stream [slots_pad*16][256]
   const float* mod;       // modulation table
-  const int* slot_mod;
+  ModIndex slot_mod;
   int mod_stride;
   int mod_off_final;      // offset of the final layer's (shift | scale) chunks in a mod row
   float eps;
@@ -1080,7 +1108,7 @@ __global__ void __launch_bounds__(512) final_step_kernel(const StepParams p, int
       const float* xr = p.X + ((size_t)slot * TOK + tk) * D + lane * 8;
       const float4 x0 = *reinterpret_cast<const float4*>(xr);
       const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
-      const float* mrow = p.mod + (size_t)p.slot_mod[slot] * p.mod_stride + p.mod_off_final + lane * 8;
+      const float* mrow = p.mod + (size_t)p.slot_mod.row(slot) * p.mod_stride + p.mod_off_final + lane * 8;
       const float4 sh0 = *reinterpret_cast<const float4*>(mrow), sh1 = *reinterpret_cast<const float4*>(mrow + 4);
       const float4 sc0 = *reinterpret_cast<const float4*>(mrow + D), sc1 = *reinterpret_cast<const float4*>(mrow + D + 4);
       float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};

@@ -164,7 +164,7 @@ class DiT(nn.Module):
         n = x.shape[0]
         cls = self._cls_rows(self._active_labels(condition or {}), n, x.device)
         plan = ops.DitPlan(packed, n_u=n, n_g=0, n_f=1, coef=[1.0], cls_idx=cls,
-                           slot_mod=torch.arange(n, dtype=torch.int32, device=x.device))
+                           slot_mod=torch.arange(n, dtype=torch.int32, device=x.device), slot_mode="identity")
         return ops.dit_forward(plan, x.contiguous().float(), t.float())
 
     def cfg_layout(self, condition: dict[str, torch.Tensor] | None, cfg_scale: dict[str, float] | None, half: int, device,
@@ -208,12 +208,13 @@ class DiT(nn.Module):
             slot_g = half + ar[:, None] * n_f + torch.arange(n_f, dtype=torch.int32, device=device)[None, :]
             t_index = torch.cat([ar, (half + ar).repeat_interleave(n_f)]).long()
         slot_mod = torch.cat([slot_u, slot_g.reshape(-1)])
-        return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index)
+        return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index,
+                    slot_mode="cfg_shared" if shared_time else "identity")
 
     def cfg_plan(self, condition, cfg_scale, half: int, device, shared_time: bool):
         lay = self.cfg_layout(condition, cfg_scale, half, device, shared_time)
         plan = ops.DitPlan(self.packed(), n_u=lay["n_u"], n_g=lay["n_g"], n_f=lay["n_f"], coef=lay["coef"],
-                           cls_idx=lay["cls_idx"], slot_mod=lay["slot_mod"])
+                           cls_idx=lay["cls_idx"], slot_mod=lay["slot_mod"], slot_mode=lay["slot_mode"])
         return plan, lay["t_index"]
 
     def forward_with_cfg(self, x: torch.Tensor, t: torch.Tensor, condition: dict[str, torch.Tensor] | None = None,

@@ -30,7 +30,10 @@ class DitPlan:
     `slot_mod` maps every cell-forward slot to its conditioning row.
     """
 
-    def __init__(self, packed: PackedDiT, n_u: int, n_g: int, n_f: int, coef, cls_idx: torch.Tensor, slot_mod: torch.Tensor):
+    SLOT_MODES = {"table": 0, "identity": 1, "cfg_shared": 2}
+
+    def __init__(self, packed: PackedDiT, n_u: int, n_g: int, n_f: int, coef, cls_idx: torch.Tensor, slot_mod: torch.Tensor,
+                 slot_mode: str = "table"):
         lib = _lib.load()
         dev = packed.device
         s = _lib.DitPlan()
@@ -59,6 +62,7 @@ class DitPlan:
         sm[:n_slots] = slot_mod.to(device=dev, dtype=torch.int32)
         self.cls_idx, self.slot_mod = ci.contiguous(), sm.contiguous()
         s.cls_idx, s.slot_mod = self.cls_idx.data_ptr(), self.slot_mod.data_ptr()
+        s.slot_mode = self.SLOT_MODES[slot_mode]   # the table is always filled; modes 1/2 promise it has that closed form
         self.struct = s
         self.n_states = n_u + n_g
         self.n_slots, self.slots_pad, self.mod_pad = n_slots, slots_pad, mod_pad

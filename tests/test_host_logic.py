@@ -155,6 +155,39 @@ def test_cfg_layout_reproduces_forward_with_cfg(golden_dir, name, shared_time):
             assert torch.allclose(acc, ref[B + j], atol=5e-5, rtol=1e-3)
 
 
+def _mod_row(mode, slot, n_u, n_f, n_slots, table):
+    """python mirror of csrc/dit_kernels.cuh::ModIndex::row"""
+    if mode == 0:
+        return int(table[slot])
+    if slot >= n_slots:
+        return 0
+    if mode == 1:
+        return slot
+    if slot < n_u:
+        return 0
+    j, k = divmod(slot - n_u, n_f)
+    return 0 if k == 0 else 1 + j * (n_f - 1) + (k - 1)
+
+
+@pytest.mark.parametrize("name", list(golden_cases().keys()))
+def test_slot_mode_closed_forms_match_tables(name):
+    """the kernels may compute the conditioning row instead of loading it: the closed forms must equal the tables."""
+    from scldm_b200.nnets import DiT
+    from scldm_b200.ops import DitPlan
+
+    case = golden_cases()[name]
+    cfg, B = case["cfg"], case["B"]
+    _, _, labels = dit_inputs(name, cfg, B)
+    m = DiT(**cfg.kwargs())
+    for shared in (False, True):
+        lay = m.cfg_layout(labels, case["scales"], B, "cpu", shared)
+        mode = DitPlan.SLOT_MODES[lay["slot_mode"]]
+        n_slots = lay["slot_mod"].numel()
+        for slot in range(n_slots):
+            assert _mod_row(mode, slot, lay["n_u"], lay["n_f"], n_slots, lay["slot_mod"]) == int(lay["slot_mod"][slot])
+        assert int(lay["slot_mod"].max()) + 1 == lay["cls_idx"].shape[1]
+
+
 def test_abi_library_loads_and_exports_declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "scldm_b200.h")).read()
     declared = set(re.findall(r"\b(scldm_[a-z_0-9]+)\s*\(", hdr))
@@ -167,7 +200,7 @@ def test_abi_library_loads_and_exports_declared_symbols():
     assert lib.scldm_vae_decode_workspace_bytes(4, 1000) > 4 * 1000 * 4
     # ctypes struct sizes match the C structs (8-byte pointers, natural alignment)
     assert ctypes.sizeof(_lib.DitWeights) == 7 * 4 + 4 + 18 * 8 + 8 * 8
-    assert ctypes.sizeof(_lib.DitPlan) == 3 * 4 + 8 * 4 + 4 + 2 * 8
+    assert ctypes.sizeof(_lib.DitPlan) == 3 * 4 + 8 * 4 + 4 + 2 * 8 + 8
 
 
 def test_no_cpu_fallback():
