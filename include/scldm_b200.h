@@ -143,6 +143,33 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
                      uint64_t seed, int64_t cell_offset, int32_t precision, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Packed VAE encoder weights (device).  scldm_b200/pack.py::PackedVAEEncoder. */
+typedef struct scldm_vae_enc_weights {
+  int32_t n_layer;
+  int32_t has_pos;
+  float eps;
+  const float* emb;       /* input_layer.gene_embedding.weight [n_ids][32]                                  */
+  const void* wkv_frag;   /* encoder.ca_layer.attn.c_attn.weight (k|v) in mma.sync B-fragment order          */
+  const void* q_tbl;      /* bf16 [16][32]: c_attn_q(ln_1q(inducing_points)) -- cell invariant (layers.py:312-313) */
+  const float* ln1_w;     /* encoder.ca_layer.ln_1                                                          */
+  const float* ln1_b;
+  const float* inducing;  /* encoder.ca_layer.inducing_points [16][32]                                      */
+  const float* wproj_t;   /* encoder.ca_layer.attn.c_proj.weight^T [32][32]                                 */
+  const float* ln2_w;
+  const float* ln2_b;
+  const float* w1_t;      /* encoder.ca_layer.mlp.w1.weight^T [32][88]                                      */
+  const float* w2_t;
+  const float* w3_t;      /* encoder.ca_layer.mlp.c_proj.weight^T [88][32]                                  */
+  const float* pos;       /* encoder.pos_embed [16][32]                                                     */
+  const float* blocks;    /* n_layer packed Blocks (encoder.encoder_layers.i)                               */
+  const float* wlat_t;    /* encoder.encoder_latent_input.0.weight^T [32][16]                               */
+} scldm_vae_enc_weights;
+
+/* Replaces TransformerVAE.encode (vae.py:58-69): genes_subset [n_cells][S] int64, counts_subset [n_cells][S] fp32
+ * -> z [n_cells][16][16] fp32.  Padding tokens (id 0, count 0) are NOT masked, as in the reference.          */
+int scldm_vae_encode(const scldm_vae_enc_weights* w, const int64_t* genes_subset, const float* counts_subset, int32_t n_cells,
+                     int32_t seq_len, float* z, void* stream);
+
 /* N(0,1) draws keyed by (seed, global cell index, element): latent noise (models.py:788) and the
  * size-factor normals (models.py:585-596).                                                        */
 int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t seed, int64_t cell_offset,

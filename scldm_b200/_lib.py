@@ -17,7 +17,7 @@ DECODE_PRECISION = {"bf16": 0, "fp32": 1}
 EXPORTS = [
     "scldm_dit_slots_pad", "scldm_dit_mod_pad", "scldm_dit_workspace_bytes", "scldm_dit_workspace_layout",
     "scldm_dit_forward", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
-    "scldm_vae_decode", "scldm_randn_cells", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
+    "scldm_vae_decode", "scldm_vae_encode", "scldm_randn_cells", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
 ]
 
 
@@ -49,6 +49,12 @@ class VaeDecWeights(C.Structure):
         ("mcab_blob", C.c_void_p), ("emb", C.c_void_p), ("theta_tbl", C.c_void_p),
         ("mcab_wfrag", C.c_void_p), ("mcab_small", C.c_void_p),
     ]
+
+
+class VaeEncWeights(C.Structure):
+    _fields_ = [("n_layer", C.c_int32), ("has_pos", C.c_int32), ("eps", C.c_float)] + [
+        (n, C.c_void_p) for n in ("emb", "wkv_frag", "q_tbl", "ln1_w", "ln1_b", "inducing", "wproj_t", "ln2_w", "ln2_b", "w1_t", "w2_t",
+                                  "w3_t", "pos", "blocks", "wlat_t")]
 
 
 _lib = None
@@ -87,6 +93,8 @@ def load() -> C.CDLL:
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p,
                                      C.c_size_t, C.c_void_p]
     lib.scldm_vae_decode.restype = C.c_int
+    lib.scldm_vae_encode.argtypes = [P(VaeEncWeights), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.scldm_vae_encode.restype = C.c_int
     lib.scldm_randn_cells.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]
     lib.scldm_randn_cells.restype = C.c_int
     lib.scldm_prof_enable.argtypes = [C.c_int32, C.c_void_p]

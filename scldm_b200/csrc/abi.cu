@@ -447,6 +447,21 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
   return SCLDM_OK;
 }
 
+int scldm_vae_encode(const scldm_vae_enc_weights* w, const int64_t* genes_subset, const float* counts_subset, int32_t n_cells,
+                     int32_t seq_len, float* z, void* stream) {
+  if (!w || !genes_subset || !counts_subset || !z) return fail(SCLDM_EINVAL, "null argument");
+  if (n_cells < 1 || seq_len < 1) return fail(SCLDM_EINVAL, "empty encode: n_cells=%d seq_len=%d", n_cells, seq_len);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  vae::EncParams p{};
+  p.emb = w->emb; p.genes = reinterpret_cast<const long long*>(genes_subset); p.counts = counts_subset; p.S = seq_len; p.n_cells = n_cells;
+  p.wkv_frag = static_cast<const uint32_t*>(w->wkv_frag); p.q_tbl = static_cast<const __nv_bfloat16*>(w->q_tbl);
+  p.ln1_w = w->ln1_w; p.ln1_b = w->ln1_b; p.inducing = w->inducing; p.wproj_t = w->wproj_t; p.ln2_w = w->ln2_w; p.ln2_b = w->ln2_b;
+  p.w1_t = w->w1_t; p.w2_t = w->w2_t; p.w3_t = w->w3_t; p.pos = w->has_pos ? w->pos : nullptr; p.blocks = w->blocks; p.n_layer = w->n_layer;
+  p.wlat_t = w->wlat_t; p.eps = w->eps; p.z = z;
+  LAUNCH("mcab_encode", vae::mcab_encode_kernel<<<n_cells, 256, 0, st>>>(p));
+  return SCLDM_OK;
+}
+
 int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t seed, int64_t cell_offset, uint32_t stream_id,
                       void* stream) {
   if (!out || n_cells < 1 || per_cell < 1) return fail(SCLDM_EINVAL, "bad randn arguments");

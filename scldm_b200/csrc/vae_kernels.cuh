@@ -75,6 +75,82 @@ __device__ __forceinline__ void ln32_tokens(const float (*x)[E], float (*y)[E], 
   }
 }
 
+// n_layer non-adaLN Blocks (layers.py:222-226) on a 16 x 32 tile in shared memory; nt = threads of the CTA (>= 128)
+__device__ __forceinline__ void vae_block_stack(float (*x)[E], float (*h)[E], float (*qkv)[3 * E], float (*hid)[HID],
+                                                const float* blocks, int n_layer, float eps, int tid, int nt) {
+  for (int l = 0; l < n_layer; ++l) {
+    const float* w = blocks + (size_t)l * BLOCK_STRIDE;
+    if (tid < 128) ln32_tokens(x, h, w + BLK_LN1W, w + BLK_LN1B, eps, tid);
+    __syncthreads();
+    for (int i = tid; i < TOK * 3 * E; i += nt) {
+      const int tok = i / (3 * E), j = i % (3 * E);
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WQKV + k * 3 * E + j];
+      qkv[tok][j] = acc;
+    }
+    __syncthreads();
+    if (tid < 128) {
+      // one thread per (query token, head): head_dim 4, softmax over 16 keys, scale 1/sqrt(4)
+      const int tok = tid >> 3, hd = tid & 7;
+      float q[4], s[TOK];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) q[d] = qkv[tok][hd * 4 + d];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) a += q[d] * qkv[k][E + hd * 4 + d];
+        s[k] = a * 0.5f;
+        mx = fmaxf(mx, s[k]);
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) { s[k] = __expf(s[k] - mx); den += s[k]; }
+      const float inv = 1.0f / den;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < TOK; ++k) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) o[d] += s[k] * qkv[k][2 * E + hd * 4 + d];
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d) h[tok][hd * 4 + d] = o[d] * inv;
+    }
+    __syncthreads();
+    for (int i = tid; i < TOK * E; i += nt) {
+      const int tok = i / E, c = i % E;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WPROJ + k * E + c];
+      x[tok][c] += acc;
+    }
+    __syncthreads();
+    if (tid < 128) ln32_tokens(x, h, w + BLK_LN2W, w + BLK_LN2B, eps, tid);
+    __syncthreads();
+    for (int i = tid; i < TOK * HID; i += nt) {
+      const int tok = i / HID, j = i % HID;
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < E; ++k) {
+        a += h[tok][k] * w[BLK_W1 + k * HID + j];
+        b += h[tok][k] * w[BLK_W2 + k * HID + j];
+      }
+      hid[tok][j] = sm100::silu(a) * b;
+    }
+    __syncthreads();
+    for (int i = tid; i < TOK * E; i += nt) {
+      const int tok = i / E, c = i % E;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < HID; ++k) acc += hid[tok][k] * w[BLK_W3 + k * E + c];
+      x[tok][c] += acc;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(128) dec_latent_kernel(const DecLatentParams p, int n_cells) {
   __shared__ float x[TOK][E];
   __shared__ float h[TOK][E];
@@ -106,77 +182,7 @@ __global__ void __launch_bounds__(128) dec_latent_kernel(const DecLatentParams p
     }
     __syncthreads();
   }
-  for (int l = 0; l < p.n_layer; ++l) {
-    const float* w = p.blocks + (size_t)l * BLOCK_STRIDE;
-    ln32_tokens(x, h, w + BLK_LN1W, w + BLK_LN1B, p.eps, tid);
-    __syncthreads();
-    for (int i = tid; i < TOK * 3 * E; i += 128) {
-      const int tok = i / (3 * E), j = i % (3 * E);
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WQKV + k * 3 * E + j];
-      qkv[tok][j] = acc;
-    }
-    __syncthreads();
-    {
-      // one thread per (query token, head): head_dim 4, softmax over 16 keys, scale 1/sqrt(4)
-      const int tok = tid >> 3, hd = tid & 7;
-      float q[4], s[TOK];
-#pragma unroll
-      for (int d = 0; d < 4; ++d) q[d] = qkv[tok][hd * 4 + d];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < TOK; ++k) {
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) a += q[d] * qkv[k][E + hd * 4 + d];
-        s[k] = a * 0.5f;
-        mx = fmaxf(mx, s[k]);
-      }
-      float den = 0.f;
-#pragma unroll
-      for (int k = 0; k < TOK; ++k) { s[k] = __expf(s[k] - mx); den += s[k]; }
-      const float inv = 1.0f / den;
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < TOK; ++k) {
-#pragma unroll
-        for (int d = 0; d < 4; ++d) o[d] += s[k] * qkv[k][2 * E + hd * 4 + d];
-      }
-#pragma unroll
-      for (int d = 0; d < 4; ++d) h[tok][hd * 4 + d] = o[d] * inv;
-    }
-    __syncthreads();
-    for (int i = tid; i < TOK * E; i += 128) {
-      const int tok = i / E, c = i % E;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WPROJ + k * E + c];
-      x[tok][c] += acc;
-    }
-    __syncthreads();
-    ln32_tokens(x, h, w + BLK_LN2W, w + BLK_LN2B, p.eps, tid);
-    __syncthreads();
-    for (int i = tid; i < TOK * HID; i += 128) {
-      const int tok = i / HID, j = i % HID;
-      float a = 0.f, b = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < E; ++k) {
-        a += h[tok][k] * w[BLK_W1 + k * HID + j];
-        b += h[tok][k] * w[BLK_W2 + k * HID + j];
-      }
-      hid[tok][j] = sm100::silu(a) * b;
-    }
-    __syncthreads();
-    for (int i = tid; i < TOK * E; i += 128) {
-      const int tok = i / E, c = i % E;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < HID; ++k) acc += hid[tok][k] * w[BLK_W3 + k * E + c];
-      x[tok][c] += acc;
-    }
-    __syncthreads();
-  }
+  vae_block_stack(x, h, qkv, hid, p.blocks, p.n_layer, p.eps, tid, 128);
   // MCAB key/value projection of the latents
   ln32_tokens(x, h, p.ca_ln1_w, p.ca_ln1_b, p.eps, tid);
   __syncthreads();
@@ -407,6 +413,11 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ uint32_t movmatrix_trans_b16(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
 __device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -592,6 +603,242 @@ __global__ void __launch_bounds__(256, 2) mcab_decode_tc_kernel(const McabTcPara
     }
 #pragma unroll
     for (int h = 0; h < 4; ++h) { kb[h][0] = kn[h][0]; kb[h][1] = kn[h][1]; vb[h][0] = vn[h][0]; vb[h][1] = vn[h][1]; }
+  }
+}
+
+// ---- MCAB encode (layers.py:97-118, 305-330; nnets.py:137-144) ------------------------------------------------
+// One CTA (8 warps) per cell.  Phase 1, flash-style pooling on mma.sync: every warp walks 16-token blocks of the
+// cell's S gene tokens: gather emb[gene]*log1p(count) -> LN1 (quad shuffles) -> K,V = c_attn (16 mma) -> per-head
+// scores against the cached, cell-invariant Q = c_attn_q(LN1q(inducing points)) (m16n8k8) -> online softmax over
+// tokens (NO key masking: padding tokens keep their softmax mass) -> P V (V^T via movmatrix).
+// Phase 2 merges the warps' (max, sum, acc) states; phase 3 is the fp32 tail on the 16 x 32 latent tile:
+// c_proj, + inducing points (raw-query residual), LN2 + SwiGLU, + pos_embed, n_layer Blocks, Linear(32->16), LN.
+struct EncParams {
+  const float* emb;             // gene embedding table [n_ids][32]
+  const long long* genes;       // [cells][S]
+  const float* counts;          // [cells][S]
+  int S;
+  int n_cells;
+  const uint32_t* wkv_frag;     // c_attn (k|v) in mma B-fragment order: [2 ks][8 nt][32 lanes][2 u32]
+  const __nv_bfloat16* q_tbl;   // [16][32] bf16: c_attn_q(LN1q(inducing_points))
+  const float* ln1_w; const float* ln1_b;
+  const float* inducing;        // [16][32]
+  const float* wproj_t;         // ca_layer.attn.c_proj^T [32][32]
+  const float* ln2_w; const float* ln2_b;
+  const float* w1_t; const float* w2_t;   // [32][88]
+  const float* w3_t;            // [88][32]
+  const float* pos;             // encoder.pos_embed [16][32] or nullptr
+  const float* blocks; int n_layer;
+  const float* wlat_t;          // encoder_latent_input.0.weight^T [32][16]
+  float eps;
+  float* z;                     // [cells][16][16]
+};
+
+__global__ void __launch_bounds__(256) mcab_encode_kernel(const EncParams p) {
+  __shared__ uint2 s_wkv[16 * 32];              // 4 KB
+  __shared__ float s_state[8][4][16][10];       // per warp, head, query: m, l, acc[8]   (20 KB)
+  __shared__ float x[TOK][E];
+  __shared__ float h[TOK][E];
+  __shared__ float qkv[TOK][3 * E];
+  __shared__ float hid[TOK][HID];
+  const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 16 * 32; i += 256) s_wkv[i] = reinterpret_cast<const uint2*>(p.wkv_frag)[i];
+  __syncthreads();
+
+  // Q fragments per head (m16n8k8 A operand): a0 = (query g, dims 8h+2t,+1), a1 = (query g+8, ...)
+  uint32_t qa[4][2];
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    qa[hh][0] = *reinterpret_cast<const uint32_t*>(p.q_tbl + g * E + 8 * hh + 2 * t);
+    qa[hh][1] = *reinterpret_cast<const uint32_t*>(p.q_tbl + (g + 8) * E + 8 * hh + 2 * t);
+  }
+  // LN1 affine in A-fragment column order: columns {2t, 2t+1, 2t+8, 2t+9} + 16*ks
+  float lw[2][4], lb[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 16 * ks + 2 * t + (j & 1) + 8 * (j >> 1);
+      lw[ks][j] = p.ln1_w[c]; lb[ks][j] = p.ln1_b[c];
+    }
+  }
+  const float sc = 0.35355339059327373f * 1.4426950408889634f;  // 1/sqrt(8) * log2(e)
+  float m_run[4][2], l_run[4][2], o_acc[4][4];
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    m_run[hh][0] = m_run[hh][1] = -INFINITY; l_run[hh][0] = l_run[hh][1] = 0.f;
+    o_acc[hh][0] = o_acc[hh][1] = o_acc[hh][2] = o_acc[hh][3] = 0.f;
+  }
+  const long long* gp = p.genes + (size_t)cell * p.S;
+  const float* cp = p.counts + (size_t)cell * p.S;
+  const int n_blk = (p.S + 15) >> 4;
+  for (int blk = warp; blk < n_blk; blk += 8) {
+    // ---- tokens g and g+8 of this block: gather, scale by log1p(count), LayerNorm over 32 channels ----
+    const int t0 = blk * 16 + g, t1 = t0 + 8;
+    const bool ok0 = t0 < p.S, ok1 = t1 < p.S;
+    const long long id0 = ok0 ? gp[t0] : 0, id1 = ok1 ? gp[t1] : 0;
+    const float c0 = ok0 ? log1pf(cp[t0]) : 0.f, c1 = ok1 ? log1pf(cp[t1]) : 0.f;
+    float xv[2][2][4];  // [row g / g+8][ks][4 cols]
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const float2 e00 = *reinterpret_cast<const float2*>(p.emb + (size_t)id0 * E + 16 * ks + 2 * t);
+      const float2 e01 = *reinterpret_cast<const float2*>(p.emb + (size_t)id0 * E + 16 * ks + 2 * t + 8);
+      const float2 e10 = *reinterpret_cast<const float2*>(p.emb + (size_t)id1 * E + 16 * ks + 2 * t);
+      const float2 e11 = *reinterpret_cast<const float2*>(p.emb + (size_t)id1 * E + 16 * ks + 2 * t + 8);
+      xv[0][ks][0] = e00.x * c0; xv[0][ks][1] = e00.y * c0; xv[0][ks][2] = e01.x * c0; xv[0][ks][3] = e01.y * c0;
+      xv[1][ks][0] = e10.x * c1; xv[1][ks][1] = e10.y * c1; xv[1][ks][2] = e11.x * c1; xv[1][ks][3] = e11.y * c1;
+    }
+    uint32_t xa[2][4];  // A fragments of LN1(x): [ks]{a0 (row g, cols 2t..), a1 (row g+8), a2 (row g, cols 2t+8..), a3}
+    {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s0 += xv[0][ks][j]; s1 += xv[1][ks][j]; }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float mu0 = s0 * (1.0f / E), mu1 = s1 * (1.0f / E);
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xv[0][ks][j] -= mu0; q0 += xv[0][ks][j] * xv[0][ks][j];
+          xv[1][ks][j] -= mu1; q1 += xv[1][ks][j] * xv[1][ks][j];
+        }
+      q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      const float r0 = rsqrtf(q0 * (1.0f / E) + p.eps), r1 = rsqrtf(q1 * (1.0f / E) + p.eps);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        xa[ks][0] = sm100::pack_bf16x2(xv[0][ks][0] * r0 * lw[ks][0] + lb[ks][0], xv[0][ks][1] * r0 * lw[ks][1] + lb[ks][1]);
+        xa[ks][1] = sm100::pack_bf16x2(xv[1][ks][0] * r1 * lw[ks][0] + lb[ks][0], xv[1][ks][1] * r1 * lw[ks][1] + lb[ks][1]);
+        xa[ks][2] = sm100::pack_bf16x2(xv[0][ks][2] * r0 * lw[ks][2] + lb[ks][2], xv[0][ks][3] * r0 * lw[ks][3] + lb[ks][3]);
+        xa[ks][3] = sm100::pack_bf16x2(xv[1][ks][2] * r1 * lw[ks][2] + lb[ks][2], xv[1][ks][3] * r1 * lw[ks][3] + lb[ks][3]);
+      }
+    }
+    // ---- K (n-tiles 0-3 = heads) and V (n-tiles 4-7) of the 16 tokens: C rows = tokens g / g+8 ----
+    float kv[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      kv[nt][0] = kv[nt][1] = kv[nt][2] = kv[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint2 b = s_wkv[(ks * 8 + nt) * 32 + lane];
+        mma_16816(kv[nt], xa[ks][0], xa[ks][1], xa[ks][2], xa[ks][3], b.x, b.y);
+      }
+    }
+    // ---- per head: scores (16 queries x 16 tokens), online softmax over tokens, O += P V ----
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      // B operand of the score MMA: B[k=dim][n=token] = K[token][dim]; the K C-fragment is already in that layout
+      const uint32_t kb0 = sm100::pack_bf16x2(kv[hh][0], kv[hh][1]);   // tokens 0-7  of the block
+      const uint32_t kb1 = sm100::pack_bf16x2(kv[hh][2], kv[hh][3]);   // tokens 8-15
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_1688(s0, qa[hh][0], qa[hh][1], kb0);   // rows = queries g / g+8, cols = tokens 2t,2t+1
+      mma_1688(s1, qa[hh][0], qa[hh][1], kb1);   // cols = tokens 8+2t, 8+2t+1
+      // tokens beyond S do not exist (ragged tail of the last block) -> no softmax mass
+      const int tb = blk * 16 + 2 * t;
+      if (tb >= p.S) { s0[0] = s0[2] = -INFINITY; }
+      if (tb + 1 >= p.S) { s0[1] = s0[3] = -INFINITY; }
+      if (tb + 8 >= p.S) { s1[0] = s1[2] = -INFINITY; }
+      if (tb + 9 >= p.S) { s1[1] = s1[3] = -INFINITY; }
+      float bm0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));   // query g
+      float bm1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));   // query g+8
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float nm0 = fmaxf(m_run[hh][0], bm0), nm1 = fmaxf(m_run[hh][1], bm1);
+      const float f0 = exp2f((m_run[hh][0] - nm0) * sc), f1 = exp2f((m_run[hh][1] - nm1) * sc);   // exp2(-inf) = 0 on first use
+      m_run[hh][0] = nm0; m_run[hh][1] = nm1;
+      s0[0] = exp2f((s0[0] - nm0) * sc); s0[1] = exp2f((s0[1] - nm0) * sc); s1[0] = exp2f((s1[0] - nm0) * sc); s1[1] = exp2f((s1[1] - nm0) * sc);
+      s0[2] = exp2f((s0[2] - nm1) * sc); s0[3] = exp2f((s0[3] - nm1) * sc); s1[2] = exp2f((s1[2] - nm1) * sc); s1[3] = exp2f((s1[3] - nm1) * sc);
+      l_run[hh][0] = l_run[hh][0] * f0 + (s0[0] + s0[1]) + (s1[0] + s1[1]);   // per-lane partial sums (quad-reduced at the end)
+      l_run[hh][1] = l_run[hh][1] * f1 + (s0[2] + s0[3]) + (s1[2] + s1[3]);
+      o_acc[hh][0] *= f0; o_acc[hh][1] *= f0; o_acc[hh][2] *= f1; o_acc[hh][3] *= f1;
+      // B operand of P V: B[k=token][n=dim] = V[token][dim] -> transpose the V C-fragment 8x8 tiles in registers
+      const uint32_t vb0 = movmatrix_trans_b16(sm100::pack_bf16x2(kv[4 + hh][0], kv[4 + hh][1]));   // tokens 0-7
+      const uint32_t vb1 = movmatrix_trans_b16(sm100::pack_bf16x2(kv[4 + hh][2], kv[4 + hh][3]));   // tokens 8-15
+      mma_16816(o_acc[hh], sm100::pack_bf16x2(s0[0], s0[1]), sm100::pack_bf16x2(s0[2], s0[3]), sm100::pack_bf16x2(s1[0], s1[1]),
+                sm100::pack_bf16x2(s1[2], s1[3]), vb0, vb1);
+    }
+  }
+  // ---- phase 2: merge the 8 warps' online-softmax states ----
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    float l0 = l_run[hh][0], l1 = l_run[hh][1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    if (t == 0) {
+      s_state[warp][hh][g][0] = m_run[hh][0]; s_state[warp][hh][g][1] = l0;
+      s_state[warp][hh][g + 8][0] = m_run[hh][1]; s_state[warp][hh][g + 8][1] = l1;
+    }
+    s_state[warp][hh][g][2 + 2 * t] = o_acc[hh][0]; s_state[warp][hh][g][3 + 2 * t] = o_acc[hh][1];
+    s_state[warp][hh][g + 8][2 + 2 * t] = o_acc[hh][2]; s_state[warp][hh][g + 8][3 + 2 * t] = o_acc[hh][3];
+  }
+  __syncthreads();
+  for (int i = tid; i < TOK * E; i += 256) {   // pooled[q][8h+d] -> h
+    const int qi = i / E, c = i % E, hh = c >> 3, d = c & 7;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, s_state[w][hh][qi][0]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float mw = s_state[w][hh][qi][0];
+      const float f = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * sc);
+      L += s_state[w][hh][qi][1] * f;
+      O += s_state[w][hh][qi][2 + d] * f;
+    }
+    h[qi][c] = O / L;
+  }
+  __syncthreads();
+  // ---- phase 3: x = inducing + c_proj(pooled); x += MLP(LN2(x)); x += pos; Blocks; Linear; LN ----
+  for (int i = tid; i < TOK * E; i += 256) {
+    const int qi = i / E, c = i % E;
+    float acc = p.inducing[i];
+#pragma unroll 8
+    for (int k = 0; k < E; ++k) acc += h[qi][k] * p.wproj_t[k * E + c];
+    x[qi][c] = acc;
+  }
+  __syncthreads();
+  if (tid < 128) ln32_tokens(x, h, p.ln2_w, p.ln2_b, p.eps, tid);
+  __syncthreads();
+  for (int i = tid; i < TOK * HID; i += 256) {
+    const int qi = i / HID, j = i % HID;
+    float a = 0.f, b = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < E; ++k) { a += h[qi][k] * p.w1_t[k * HID + j]; b += h[qi][k] * p.w2_t[k * HID + j]; }
+    hid[qi][j] = sm100::silu(a) * b;
+  }
+  __syncthreads();
+  for (int i = tid; i < TOK * E; i += 256) {
+    const int qi = i / E, c = i % E;
+    float acc = p.pos ? p.pos[i] : 0.f;
+#pragma unroll 8
+    for (int k = 0; k < HID; ++k) acc += hid[qi][k] * p.w3_t[k * E + c];
+    x[qi][c] += acc;
+  }
+  __syncthreads();
+  vae_block_stack(x, h, qkv, hid, p.blocks, p.n_layer, p.eps, tid, 256);
+  // Linear(32 -> 16) + LayerNorm(16, no affine)
+  float (*zl)[LAT] = reinterpret_cast<float (*)[LAT]>(&qkv[0][0]);
+  for (int i = tid; i < TOK * LAT; i += 256) {
+    const int qi = i / LAT, c = i % LAT;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < E; ++k) acc += x[qi][k] * p.wlat_t[k * LAT + c];
+    zl[qi][c] = acc;
+  }
+  __syncthreads();
+  if (tid < TOK) {
+    float m = 0.f;
+    for (int j = 0; j < LAT; ++j) m += zl[tid][j];
+    m *= (1.0f / LAT);
+    float var = 0.f;
+    for (int j = 0; j < LAT; ++j) { const float dlt = zl[tid][j] - m; var += dlt * dlt; }
+    const float rstd = rsqrtf(var * (1.0f / LAT) + p.eps);
+    for (int j = 0; j < LAT; ++j) p.z[((size_t)cell * TOK + tid) * LAT + j] = (zl[tid][j] - m) * rstd;
   }
 }
 

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .pack import PackedDiT, PackedVAEDecoder
+from .pack import PackedDiT, PackedVAEDecoder, PackedVAEEncoder
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -184,6 +184,21 @@ def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, l
                               _lib.DECODE_PRECISION[precision], ws.data_ptr(), ws.numel(), _stream_ptr(z.device))
     _lib.check(rc, "scldm_vae_decode")
     return mu, theta, counts
+
+
+def vae_encode(packed: PackedVAEEncoder, genes_subset: torch.Tensor, counts_subset: torch.Tensor) -> torch.Tensor:
+    """genes_subset [cells,S] int64, counts_subset [cells,S] float -> z [cells,16,16] fp32."""
+    lib = _lib.load()
+    _require_cuda(genes_subset, "genes_subset")
+    _require_cuda(counts_subset, "counts_subset")
+    assert genes_subset.dtype == torch.int64 and genes_subset.dim() == 2 and genes_subset.shape == counts_subset.shape
+    counts = counts_subset.to(torch.float32).contiguous()
+    n_cells, S = genes_subset.shape
+    z = torch.empty(n_cells, 16, 16, dtype=torch.float32, device=genes_subset.device)
+    rc = lib.scldm_vae_encode(C.byref(packed.struct), genes_subset.data_ptr(), counts.data_ptr(), n_cells, S, z.data_ptr(),
+                              _stream_ptr(genes_subset.device))
+    _lib.check(rc, "scldm_vae_encode")
+    return z
 
 
 def randn_cells(n_cells: int, per_cell: int, seed: int, cell_offset: int, stream_id: int, device) -> torch.Tensor:

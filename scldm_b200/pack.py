@@ -214,3 +214,53 @@ class PackedVAEDecoder:
         self.device = torch.device(device)
         self.qp = None  # Q-side tables (fp32, bf16), filled lazily by ops.vae_qside
         self.qp_bf16 = None
+
+
+def _pack_vae_blocks(g, prefix: str, n_layer: int) -> torch.Tensor:
+    blocks = []
+    for i in range(n_layer):
+        p = f"{prefix}{i}."
+        blocks.append(torch.cat([
+            g(p + "ln_1.weight"), g(p + "ln_1.bias"), g(p + "ln_2.weight"), g(p + "ln_2.bias"),
+            g(p + "attn.c_attn.weight").T.reshape(-1), g(p + "attn.c_proj.weight").T.reshape(-1),
+            g(p + "mlp.w1.weight").T.reshape(-1), g(p + "mlp.w2.weight").T.reshape(-1), g(p + "mlp.c_proj.weight").T.reshape(-1),
+        ]))
+        assert blocks[-1].numel() == VAE_BLOCK_STRIDE
+    return torch.stack(blocks)
+
+
+class PackedVAEEncoder:
+    """Device-resident packed encoder (MCAB pooling + Blocks + latent head) for `scldm_vae_encode`."""
+
+    def __init__(self, sd: dict, cfg: VAEConfig, device):
+        if (cfg.n_embed, cfg.n_embed_latent, cfg.n_inducing_points, cfg.n_head, cfg.n_head_cross, cfg.hidden) != (32, 16, 16, 8, 4, VAE_HID):
+            raise NotImplementedError(f"sm_100a VAE kernels are specialised to the shipped vae_base dims; got {cfg}")
+        if cfg.bias or cfg.agg_func != "log1p":
+            raise NotImplementedError("encoder kernels cover bias=False, agg_func='log1p'")
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+        g = lambda n: sd[n].detach().float().cpu()  # noqa: E731
+        c = "encoder.ca_layer."
+        eps = float(cfg.layernorm_eps)
+        self.emb = f32(g("input_layer.gene_embedding.weight"))
+        self.wkv_frag = mma_b_frags(g(c + "attn.c_attn.weight")).to(device).contiguous()       # [2][8][32][4] bf16
+        # cell-invariant query side (tiny, computed once at pack time): c_attn_q(ln_1q(inducing_points))
+        ind = g(c + "inducing_points")
+        qn = torch.nn.functional.layer_norm(ind, (cfg.n_embed,), g(c + "ln_1q.weight"), g(c + "ln_1q.bias"), eps)
+        self.q_tbl = (qn @ g(c + "attn.c_attn_q.weight").T).to(torch.bfloat16).to(device).contiguous()
+        self.ln1_w, self.ln1_b = f32(g(c + "ln_1.weight")), f32(g(c + "ln_1.bias"))
+        self.inducing = f32(ind)
+        self.wproj_t = f32(g(c + "attn.c_proj.weight").T)
+        self.ln2_w, self.ln2_b = f32(g(c + "ln_2.weight")), f32(g(c + "ln_2.bias"))
+        self.w1_t, self.w2_t = f32(g(c + "mlp.w1.weight").T), f32(g(c + "mlp.w2.weight").T)
+        self.w3_t = f32(g(c + "mlp.c_proj.weight").T)
+        self.has_pos = "encoder.pos_embed" in sd
+        self.pos = f32(g("encoder.pos_embed").reshape(16, 32)) if self.has_pos else f32(torch.zeros(16, 32))
+        self.blocks = f32(_pack_vae_blocks(g, "encoder.encoder_layers.", cfg.n_layer))
+        self.wlat_t = f32(g("encoder.encoder_latent_input.0.weight").T)
+        s = _lib.VaeEncWeights()
+        s.n_layer, s.has_pos, s.eps = cfg.n_layer, int(self.has_pos), eps
+        for name in ("emb", "wkv_frag", "q_tbl", "ln1_w", "ln1_b", "inducing", "wproj_t", "ln2_w", "ln2_b", "w1_t", "w2_t", "w3_t", "pos",
+                     "blocks", "wlat_t"):
+            setattr(s, name, getattr(self, name).data_ptr())
+        self.struct = s
+        self.device = torch.device(device)

@@ -11,7 +11,7 @@ from . import ops
 from .config import VAEConfig
 from .layers import InputTransformerVAE
 from .nnets import Decoder, Encoder
-from .pack import PackedVAEDecoder
+from .pack import PackedVAEDecoder, PackedVAEEncoder
 from .stochastic_layers import NegativeBinomial, NegativeBinomialTransformerLayer
 
 
@@ -95,8 +95,22 @@ class TransformerVAE(nn.Module):
                                            out_counts=out_counts, out_mu=out_mu, precision=self.decode_precision)
         return counts, mu, theta
 
+    def packed_encoder(self) -> PackedVAEEncoder:
+        sd = self.state_dict(keep_vars=True)
+        key = tuple((p.data_ptr(), p._version) for k, p in sd.items() if k.startswith("encoder.") or k.startswith("input_layer."))
+        dev = self.input_layer.gene_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("scldm_b200.TransformerVAE runs on CUDA only (no CPU fallback): call .cuda() first")
+        if getattr(self, "_packed_enc", None) is None or self._packed_enc_key != key:
+            self._packed_enc = PackedVAEEncoder({k: v.detach() for k, v in sd.items()}, self.config(), dev)
+            self._packed_enc_key = key
+        return self._packed_enc
+
     def encode(self, counts, genes, counts_subset=None, genes_subset=None):
-        raise NotImplementedError("MCAB encode kernels are the next row of the scope table (SURVEY.md §8a row a20)")
+        """`TransformerVAE.encode` (`vae.py:58-69`): the subset tensors are used when given, else (counts, genes)."""
+        c = counts_subset if counts_subset is not None else counts
+        g = genes_subset if genes_subset is not None else genes
+        return ops.vae_encode(self.packed_encoder(), g.contiguous(), c.contiguous())
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError("VAE training forward is a later row (SURVEY.md §8f rank 3)")

@@ -214,3 +214,34 @@ def test_shard_invariance_single_gpu():
     c_cat = torch.cat([parts[0][0][:n0], parts[1][0][:n1], parts[0][0][n0:], parts[1][0][n1:]])
     z_cat = torch.cat([parts[0][1][:n0], parts[1][1][:n1], parts[0][1][n0:], parts[1][1][n1:]])
     assert torch.equal(z_cat, z_all) and torch.equal(c_cat, c_all)
+
+
+@pytest.mark.parametrize("name,G,B,S", [("vae_small", 1500, 3, 400), ("vae_dentate", 17002, 2, 600)])
+def test_encode_vs_golden(golden_dir, name, G, B, S):
+    """MCAB encode (tensor-core flash pooling, bf16 operands) vs the reference: z is LayerNorm-ed (unit variance), so
+    rel-L2 == RMS error; tolerance 2e-2.  Padding tokens (id 0, count 0) are part of the fixture (unmasked, quirk 3)."""
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    cfg = VAEConfig(n_genes=G)
+    vae, sd = make_vae(cfg)
+    _, _, _, cs, gs = vae_inputs(name, cfg, B, S)
+    assert int((gs == 0).sum()) > 0  # the fixture really contains padding
+    z = vae.encode(None, None, cs.cuda(), gs.cuda())
+    e = rel_l2(z, g["z_enc"])
+    print(name, f"encode z rel-L2 {e:.2e}")
+    assert z.shape == (B, 16, 16) and e < 2e-2
+
+
+def test_encode_ragged_lengths_vs_oracle():
+    """S not a multiple of 16 (ragged last token block), S < 128 (some warps idle), many cells."""
+    cfg = VAEConfig(n_genes=700, n_layer=2)
+    vae, sd = make_vae(cfg)
+    for S, B in ((37, 5), (250, 33), (1000, 4)):
+        gen = torch.Generator().manual_seed(S)
+        gs = torch.randint(0, 701, (B, S), generator=gen)
+        cs = torch.poisson(torch.full((B, S), 2.0), generator=gen) * (gs > 0)
+        z = vae.encode(None, None, cs.cuda(), gs.cuda())
+        with torch.no_grad():
+            zo = O.vae_encode(cs, gs, sd, cfg)
+        e = rel_l2(z, zo)
+        print("encode", S, B, f"{e:.2e}")
+        assert e < 2e-2
