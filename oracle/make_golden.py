@@ -114,6 +114,19 @@ def main() -> None:
     arrays["t0t1"] = np.asarray(t0t1, dtype=np.float64)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "ode_me1.npz"), **arrays)
 
+    # ---- flow-matching loss through the reference's Transport.training_losses (eval mode, as in shared_step) ----
+    B = 6
+    x1 = synthetic.randn("fm.x1", (B, cfg.seq_len, cfg.n_embed_input))
+    labf = {"clusters": synthetic.randint("fm.label", 14, (B,))}
+    torch.manual_seed(77)
+    x0_ref = torch.randn_like(x1)            # same draw order as Transport.sample (transport.py:103-107)
+    t_ref = torch.rand((B,))
+    torch.manual_seed(77)
+    terms = transport.training_losses(model, x1, {"condition": labf})
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "fm_loss_me1.npz"), x1=x1.numpy(), label=labf["clusters"].numpy(), x0=x0_ref.numpy(),
+                        t=t_ref.numpy(), loss=terms["loss"].numpy(), pred=terms["pred"].numpy())
+    print("fm loss", terms["loss"].tolist())
+
     # ---- VAE decode / encode ----------------------------------------------------------------
     for name, G, B, S in (("vae_small", 1500, 3, 400), ("vae_dentate", 17002, 2, 600)):
         vcfg = VAEConfig(n_genes=G)

@@ -244,6 +244,17 @@ def sample_ode(x, model_fn, num_steps=50, method="euler"):
     return odeint_fixed(fn, x, grid, method)
 
 
+def fm_training_losses(x1, t, x0, model_fn):
+    """`Transport.training_losses` for Linear path + velocity prediction, reference `transport.py:110-150` with
+    `ICPlan.plan` (`path.py:129-151`): x_t = t x1 + (1-t) x0, u_t = x1 - x0, loss = mean over (tokens, channels) of
+    (model(x_t, t) - u_t)^2 per cell.  t and x0 are passed in (the reference draws them with the global RNG)."""
+    te = t.view(-1, *([1] * (x1.dim() - 1)))
+    xt = te * x1 + (1 - te) * x0
+    ut = x1 - x0
+    out = model_fn(xt, t)
+    return {"loss": ((out - ut) ** 2).flatten(1).mean(1), "pred": out}
+
+
 # ----------------------------------------------------------------------------------------
 # VAE decoder + NB head (reference nnets.py:147-208, layers.py:267-330, stochastic_layers.py:76-116)
 # ----------------------------------------------------------------------------------------

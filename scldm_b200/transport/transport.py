@@ -44,6 +44,35 @@ class Transport:
             t0, t1 = 1 - t0, 1 - t1
         return t0, t1
 
+    def sample(self, x1: torch.Tensor):
+        """`Transport.sample` (`transport.py:97-108`): x0 ~ N(0,I), t ~ U(t0,t1) drawn on the CPU then moved (as the reference)."""
+        x0 = torch.randn_like(x1)
+        t0, t1 = self.check_interval(self.train_eps, self.sample_eps)
+        t = torch.rand((x1.shape[0],)) * (t1 - t0) + t0
+        return t.to(x1), x0, x1
+
+    def training_losses(self, model, x1: torch.Tensor, model_kwargs: dict | None = None, *, t: torch.Tensor | None = None,
+                        x0: torch.Tensor | None = None) -> dict:
+        """`Transport.training_losses` (`transport.py:110-150`) for the Linear path + velocity prediction:
+        x_t = t x1 + (1-t) x0 (`path.py:129-151`), loss = mean_flat((model(x_t, t) - (x1 - x0))^2).
+        Forward only (validation / `shared_step`, `models.py:673-704`); `t` / `x0` may be injected for parity tests."""
+        model_kwargs = model_kwargs or {}
+        if t is None or x0 is None:
+            ts, x0s, _ = self.sample(x1)
+            t = ts if t is None else t
+            x0 = x0s if x0 is None else x0
+        te = t.view(-1, *([1] * (x1.dim() - 1)))
+        xt = te * x1 + (1 - te) * x0
+        ut = x1 - x0
+        out = model(xt, t, **model_kwargs)
+        assert out.shape == xt.shape
+        return {"pred": out, "loss": mean_flat((out - ut) ** 2)}
+
+
+def mean_flat(x: torch.Tensor) -> torch.Tensor:
+    """mean over all non-batch dims (`transport/utils.py`)."""
+    return x.flatten(1).mean(1)
+
 
 def create_transport(path_type="Linear", prediction="velocity", loss_weight=None, train_eps=None, sample_eps=None) -> Transport:
     """`create_transport` (`transport/__init__.py:6-68`); velocity & Linear forces both eps to 0 (`:55-57`)."""
@@ -70,6 +99,7 @@ class Sampler:
     """`Sampler` (`transport.py:206-225, 324-369`): `sample_ode(...)` returns fn(x, model, **model_kwargs)."""
 
     FIXED = ("euler", "heun2", "midpoint")
+    ADAPTIVE = ("dopri5",)
 
     def __init__(self, transport: Transport):
         self.transport = transport
@@ -78,10 +108,8 @@ class Sampler:
         if reverse:
             raise NotImplementedError("reverse-time ODE is outside the generation path")
         method = sampling_method.lower()
-        if method not in self.FIXED:
-            raise NotImplementedError(
-                f"sampling_method='{sampling_method}': the device stepper implements the fixed-grid solvers {self.FIXED}; "
-                "the reference's default adaptive dopri5 is a later row (SURVEY.md §8f rank 4)")
+        if method not in self.FIXED + self.ADAPTIVE:
+            raise NotImplementedError(f"sampling_method='{sampling_method}': implemented: {self.FIXED + self.ADAPTIVE}")
         t0, t1 = self.transport.check_interval(self.transport.train_eps, self.transport.sample_eps, sde=False, eval=True)
         grid = torch.linspace(t0, t1, num_steps)  # `ode.__init__`, integrators.py:95
 
@@ -89,6 +117,8 @@ class Sampler:
             """Returns the trajectory end points stacked as (2, ...): [x(t0), x(t1)] (the reference returns all
             `num_steps` states but `LatentDiffusion.sample` only reads `[-1]`, `models.py:812`)."""
             x0 = x.contiguous().float()
+            if method in self.ADAPTIVE:
+                return self._sample_adaptive(x0, model, grid, atol, rtol, **model_kwargs)
             if isinstance(model, FusedCFGModel):
                 half = x0.shape[0] // 2
                 plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
@@ -111,3 +141,26 @@ class Sampler:
             return torch.stack([x0, xk])
 
         return sample
+
+    def _sample_adaptive(self, x0, model, grid, atol, rtol, **model_kwargs):
+        """dopri5 (the reference's default, `transport.py:327`): host-side step controller (as in torchdiffeq), function
+        evaluations on the GPU.  With a `FusedCFGModel` every evaluation is ONE batched launch sequence (shared-time CFG
+        plan built once); returns all `num_steps` requested states like the reference."""
+        from .adaptive import dopri5
+
+        if isinstance(model, FusedCFGModel):
+            half = x0.shape[0] // 2
+            plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
+            tm = torch.empty(plan.n_mod, dtype=torch.float32, device=x0.device)
+
+            def f(t, y):
+                tm.fill_(float(t))
+                return ops.dit_forward(plan, y.contiguous(), tm)
+        else:
+            def f(t, y):
+                tv = torch.full((y.shape[0],), float(t), dtype=torch.float32, device=y.device)
+                return model(y, tv, **model_kwargs)
+
+        traj, nfe = dopri5(f, x0, grid.tolist(), rtol=rtol, atol=atol)
+        self.last_nfe = nfe
+        return traj

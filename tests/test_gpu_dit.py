@@ -173,3 +173,49 @@ def test_large_batch_matches_oracle_sample():
         ref = O.dit_forward_with_cfg(x, t, lab, {"clusters": 1.7}, sd, cfg)
     assert rel_l2(out[rows], ref[rows]) < 2 * TOL_FWD
     assert rel_l2(out, ref) < 2 * TOL_FWD
+
+
+def test_fm_training_losses_vs_golden(golden_dir):
+    """Transport.training_losses (forward / validation loss) through the CUDA DiT vs the reference's Transport."""
+    from scldm_b200.transport import create_transport
+
+    g = load(golden_dir, "fm_loss_me1")
+    cfg = golden_cases()["dit_me1"]["cfg"]
+    dit, _ = make_dit(cfg)
+    tr = create_transport("Linear", "velocity", "velocity", 1e-5, 1e-5)
+    terms = tr.training_losses(dit, torch.from_numpy(g["x1"]).cuda(), {"condition": {"clusters": torch.from_numpy(g["label"]).cuda()}},
+                               t=torch.from_numpy(g["t"]).cuda(), x0=torch.from_numpy(g["x0"]).cuda())
+    e_pred, e_loss = rel_l2(terms["pred"], g["pred"]), rel_l2(terms["loss"], g["loss"])
+    print(f"fm loss: pred {e_pred:.2e} loss {e_loss:.2e}")
+    assert e_pred < TOL_FWD and e_loss < 5e-3
+    # RNG path (no injection): shapes and finiteness; t drawn on the CPU as the reference does
+    terms2 = tr.training_losses(dit, torch.from_numpy(g["x1"]).cuda(), {"condition": {"clusters": torch.from_numpy(g["label"]).cuda()}})
+    assert terms2["loss"].shape == (6,) and bool(torch.isfinite(terms2["loss"]).all())
+
+
+def test_dopri5_adaptive_sampler():
+    """the reference's default solver: adaptive dopri5 (host controller + CUDA function evaluations) lands on the same
+    end point as a fine fixed-grid Heun integration of the oracle, and both model-callable flavours agree."""
+    from scldm_b200.transport import Sampler, create_transport
+    from scldm_b200.transport.transport import FusedCFGModel
+
+    cfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=2)
+    dit, sd = make_dit(cfg)
+    B = 3
+    z0 = synthetic.randn("dp.z0", (B, 16, 16))
+    lab = {"clusters": synthetic.randint("dp.lab", 14, (B,))}
+    lab2 = {"clusters": torch.cat([lab["clusters"], lab["clusters"]])}
+    w = {"clusters": 1.5}
+    sampler = Sampler(create_transport("Linear", "velocity", "velocity", 1e-5, 1e-5))
+    fn = sampler.sample_ode(sampling_method="dopri5", num_steps=5, atol=1e-3, rtol=1e-3)
+    traj = fn(torch.cat([z0, z0]).cuda(), FusedCFGModel(dit, w), condition={k: v.cuda() for k, v in lab2.items()})
+    nfe = sampler.last_nfe
+    assert traj.shape == (5, 2 * B, 16, 16)  # all requested grid points, like the reference
+    with torch.no_grad():
+        ref = O.sample_ode(torch.cat([z0, z0]), lambda x, t: O.dit_forward_with_cfg(x, t, lab2, w, sd, cfg), num_steps=201, method="heun2")
+    e_end = rel_l2(traj[-1], ref[-1])
+    e_mid = rel_l2(traj[2], ref[100])
+    traj2 = fn(torch.cat([z0, z0]).cuda(), lambda x, t, **kw: dit.forward_with_cfg(x, t, **kw, cfg_scale=w),
+               condition={k: v.cuda() for k, v in lab2.items()})
+    print(f"dopri5: nfe {nfe}, end {e_end:.2e}, mid {e_mid:.2e}, generic-vs-fused {rel_l2(traj2[-1], traj[-1]):.2e}")
+    assert e_end < 1e-2 and e_mid < 1e-2 and rel_l2(traj2[-1], traj[-1]) < 1e-2 and nfe < 2000

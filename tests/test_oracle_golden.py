@@ -121,3 +121,15 @@ def test_nb_sample_moments():
     exp_v = mu[0] + mu[0] ** 2 / theta
     assert torch.allclose(m, mu[0], rtol=0.03)
     assert torch.allclose(v, exp_v, rtol=0.06)
+
+
+def test_fm_training_losses(golden_dir):
+    """oracle restatement of Transport.training_losses (Linear path, velocity) vs the reference's own Transport."""
+    g = load(golden_dir, "fm_loss_me1")
+    cfg = golden_cases()["dit_me1"]["cfg"]
+    sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    lab = {"clusters": torch.from_numpy(g["label"])}
+    with torch.no_grad():
+        out = O.fm_training_losses(torch.from_numpy(g["x1"]), torch.from_numpy(g["t"]), torch.from_numpy(g["x0"]),
+                                   lambda x, t: O.dit_forward(x, t, lab, sd, cfg))
+    assert rel_l2(out["loss"], g["loss"]) < 1e-5 and rel_l2(out["pred"], g["pred"]) < TOL
