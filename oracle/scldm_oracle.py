@@ -373,6 +373,23 @@ def sample_log_size_factors(labels: dict | None, mu_tbl: dict | None, sd_tbl: di
     return out
 
 
+def sample_joint_log_size_factors(labels: dict, components: list, joint_idx_2_classes: dict, mu_vec: dict, sd_vec: dict,
+                                  batch_size: int, eps_normal: torch.Tensor):
+    """Joint path of `_sample_log_size_factors` reference `models.py:510-550`: key "{i}_{j}" of the component labels ->
+    `joint_idx_2_classes` -> class index -> N(mu, sd); missing key or statistics leave 0."""
+    out = torch.zeros(batch_size, dtype=eps_normal.dtype)
+    for b in range(batch_size):
+        key = "_".join(str(int(labels[k][b])) for k in components)
+        if key not in joint_idx_2_classes:
+            continue
+        c = joint_idx_2_classes[key]
+        m, s = mu_vec.get(c), sd_vec.get(c)
+        if m is None or s is None:
+            continue
+        out[b] = m + s * eps_normal[b]
+    return out
+
+
 def latent_diffusion_sample(z0, labels, guidance_weight, genes, log_size_factors, dit_sd, dit_cfg, vae_sd, vae_cfg,
                             num_steps=50, method="euler"):
     """`LatentDiffusion.sample` reference `models.py:766-819` with the noise z0 (B,M,L) and the

@@ -31,7 +31,8 @@ class LatentDiffusion(nn.Module):
     def __init__(self, vae_model: TransformerVAE, diffusion_model: DiT, transport: Transport,
                  mu_size_factor: dict | None = None, sd_size_factor: dict | None = None,
                  size_factor_condition_key: str | None = None, sampling_method: str = "euler", num_steps: int = 50,
-                 seed: int = 0, cell_chunk: int = 784, **_unused_training_kwargs):
+                 seed: int = 0, cell_chunk: int = 784, joint_idx_2_classes: dict | None = None, joint_key: str | None = None,
+                 joint_components: list | None = None, **_unused_training_kwargs):
         super().__init__()
         self.vae_model = vae_model
         self.diffusion_model = diffusion_model
@@ -39,6 +40,8 @@ class LatentDiffusion(nn.Module):
         self.transport_sampler = Sampler(transport)
         self.mu_size_factor, self.sd_size_factor = mu_size_factor, sd_size_factor
         self.size_factor_condition_key = size_factor_condition_key
+        # joint statistics (`encoder.py:113-134`): "{i}_{j}" -> class index of the joint table `joint_key`
+        self.joint_idx_2_classes, self.joint_key, self.joint_components = joint_idx_2_classes, joint_key, joint_components
         self.sampling_method, self.num_steps = sampling_method, num_steps
         self.seed = seed
         self.cell_chunk = cell_chunk
@@ -59,7 +62,44 @@ class LatentDiffusion(nn.Module):
         inter = sorted(set(condition) & set(self.mu_size_factor) & set(self.sd_size_factor))
         return inter[0] if inter else None
 
+    def _use_joint(self, condition) -> bool:
+        """joint branch of `_sample_log_size_factors` (`models.py:498-550`)."""
+        return (condition is not None and self.mu_size_factor is not None and self.sd_size_factor is not None
+                and getattr(self.diffusion_model, "condition_strategy", None) == "joint" and self.joint_idx_2_classes is not None
+                and self.joint_key is not None and self.joint_key in self.mu_size_factor and self.joint_key in self.sd_size_factor)
+
+    def _sample_joint_log_size_factors(self, condition, batch_size: int, cell_offset: int) -> torch.Tensor:
+        comps = [k for k in self.joint_components if k in condition] if self.joint_components is not None else list(condition.keys())
+        if "joint" not in self._sf_tables:
+            # dense (component index tuple) -> (mu, sd) tables on the device; missing keys / stats give exactly 0
+            sizes = [self.diffusion_model.class_vocab_sizes[k] + 1 for k in comps]
+            n = 1
+            for v in sizes:
+                n *= v
+            mu, sd = torch.zeros(n), torch.zeros(n)
+            mu_vec, sd_vec = self.mu_size_factor[self.joint_key], self.sd_size_factor[self.joint_key]
+            for key, cls_idx in self.joint_idx_2_classes.items():
+                idx = [int(v) for v in key.split("_")]
+                if len(idx) != len(sizes) or any(i >= s for i, s in zip(idx, sizes)):
+                    continue
+                m, s_ = mu_vec.get(cls_idx), sd_vec.get(cls_idx)
+                if m is None or s_ is None:
+                    continue
+                flat = 0
+                for i, sz in zip(idx, sizes):
+                    flat = flat * sz + i
+                mu[flat], sd[flat] = float(m), float(s_)
+            self._sf_tables["joint"] = (mu.to(self.device), sd.to(self.device), sizes, comps)
+        mu, sd, sizes, comps = self._sf_tables["joint"]
+        flat = torch.zeros(batch_size, dtype=torch.long, device=self.device)
+        for k, sz in zip(comps, sizes):
+            flat = flat * sz + condition[k].to(self.device).long()
+        eps = ops.randn_cells(batch_size, 1, self.seed, cell_offset, STREAM_SIZE_FACTOR, self.device).reshape(-1)
+        return mu[flat] + sd[flat] * eps
+
     def _sample_log_size_factors(self, condition, batch_size: int, cell_offset: int) -> torch.Tensor:
+        if self._use_joint(condition):
+            return self._sample_joint_log_size_factors(condition, batch_size, cell_offset)
         key = self._size_factor_key(condition)
         if key is None:
             return torch.zeros(batch_size, device=self.device)

@@ -245,3 +245,39 @@ def test_encode_ragged_lengths_vs_oracle():
         e = rel_l2(z, zo)
         print("encode", S, B, f"{e:.2e}")
         assert e < 2e-2
+
+
+def test_joint_size_factors_match_oracle():
+    """joint-key size-factor statistics (`models.py:498-550`, Replogle / Parse1M configs): the device lookup uses the same
+    standard normals as the oracle's per-cell loop; missing joint keys / statistics give exactly 0."""
+    from scldm_b200 import ops
+    from scldm_b200.models import STREAM_SIZE_FACTOR, LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    dcfg = DiTConfig(class_vocab_sizes={"cell_line": 4, "gene": 7}, n_layer=1, condition_strategy="joint")
+    vcfg = VAEConfig(n_genes=200, n_layer=1)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
+    vae, _ = make_vae(vcfg)
+    j2c, mu_vec, sd_vec, c = {}, {}, {}, 0
+    for i in range(4):
+        for j in range(7):
+            if (i + j) % 5 == 0:
+                continue  # combination never seen in training: no joint key
+            j2c[f"{i}_{j}"] = c
+            if c % 6 != 1:  # a few classes lack statistics
+                mu_vec[c], sd_vec[c] = 7.0 + 0.1 * c, 0.2 + 0.01 * c
+            c += 1
+    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor={"joint": mu_vec},
+                          sd_size_factor={"joint": sd_vec}, joint_idx_2_classes=j2c, joint_key="joint",
+                          joint_components=["cell_line", "gene"], num_steps=3, seed=5)
+    B = 64
+    cond = {"cell_line": synthetic.randint("jl.a", 4, (B,)), "gene": synthetic.randint("jl.b", 7, (B,))}
+    lsf = ldm._sample_log_size_factors({k: v.cuda() for k, v in cond.items()}, B, cell_offset=100).cpu()
+    eps = ops.randn_cells(B, 1, 5, 100, STREAM_SIZE_FACTOR, "cuda").reshape(-1).cpu()
+    ref = O.sample_joint_log_size_factors(cond, ["cell_line", "gene"], j2c, mu_vec, sd_vec, B, eps)
+    assert torch.allclose(lsf, ref, atol=1e-5) and int((ref == 0).sum()) > 0 and int((ref != 0).sum()) > 0
+    counts, z = ldm.sample({k: v.cuda() for k, v in cond.items()}, {"cell_line": 1.0, "gene": 2.0}, B,
+                           torch.arange(1, 201).unsqueeze(0).repeat(B, 1).cuda())
+    assert counts.shape == (2 * B, 200) and bool(torch.isfinite(counts).all())
