@@ -895,6 +895,11 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
 }
 
 __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out_packed, int n_slots) {
+  // one CTA per slot (cell-forward), one warp per head.  The slot's q|k|v rows (16 tokens x 768 channels) are 12
+  // contiguous 2 KB segments of the packed activation slabs: stage them with 12 bulk-TMA copies, then read the mma
+  // fragments from shared memory (the swizzle is resolved per access).
+  __shared__ __align__(128) uint8_t s_qkv[12 * 2048];
+  __shared__ uint64_t s_bar;
   const int slot = blockIdx.x;
   const int head = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -902,11 +907,21 @@ __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qk
   if (slot >= n_slots) return;
   const size_t row0 = (size_t)slot * TOK;                 // first token row of this slot
   const uint8_t* tile_base = reinterpret_cast<const uint8_t*>(qkv + (row0 >> 7) * (3 * D / BLOCK_K) * A_SLAB_ELEMS);
-  const uint32_t rbase = row0 & 127;
+  const uint32_t rbase = row0 & 127;                      // multiple of 16: the 16 rows share (r & 7) patterns with r - rbase
+  if (threadIdx.x == 0) {
+    sm100::mbar_init(&s_bar, 1);
+    sm100::fence_barrier_init();
+    sm100::mbar_arrive_expect_tx(&s_bar, 12 * 2048);
+#pragma unroll
+    for (int sl = 0; sl < 12; ++sl)
+      sm100::bulk_g2s(s_qkv + sl * 2048, tile_base + (size_t)sl * A_SLAB_BYTES + rbase * 128, 2048, &s_bar);
+  }
+  __syncthreads();
+  sm100::mbar_wait(&s_bar, 0);
   auto ld2 = [&](int token, int part, int dim) -> uint32_t {
-    const uint32_t col = part * D + head * HD + dim, r = rbase + token;
-    return *reinterpret_cast<const uint32_t*>(tile_base + (size_t)(col >> 6) * A_SLAB_BYTES +
-                                              sm100::swz_chunk_offset(r, (col & 63) >> 3) + (col & 7) * 2);
+    const uint32_t col = part * D + head * HD + dim;
+    // (rbase + token) & 7 == token & 7 because rbase is a multiple of 16
+    return *reinterpret_cast<const uint32_t*>(s_qkv + (col >> 6) * 2048 + sm100::swz_chunk_offset(token, (col & 63) >> 3) + (col & 7) * 2);
   };
   // S = Q K^T : A = Q (16 tokens x 32 dims) in two k-steps; B[k=dim][n=key] = K[key][dim]
   float s[2][4] = {};
@@ -963,22 +978,25 @@ __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qk
     const uint32_t b1 = movmatrix_trans(v1);            // -> (keys 2t+8,.. ; dim nt*8+g)
     mma_bf16_16816(o[nt], pa, b0, b1);
   }
-  // write O rows (g, g+8) x dims (nt*8 + 2t, +1) into the swizzled A-tile layout
-  const size_t grow0 = (size_t)slot * TOK + g, grow1 = grow0 + 8;
+  // O rows (g, g+8) x dims (nt*8 + 2t, +1): assemble the slot's 16 x 256 output as 4 swizzled 2 KB slab segments in
+  // shared memory (reusing the q slabs, which every warp has finished reading after the barrier) and bulk-store them
+  __syncthreads();
+  uint8_t* s_out = s_qkv;   // q columns [0,256) = slabs 0..3 are dead now
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     const int col = head * HD + nt * 8 + 2 * t;
-    const int slab = col >> 6, chunk = (col & 63) >> 3, within = col & 7;
-    {
-      const size_t tile = grow0 >> 7; const uint32_t r = grow0 & 127;
-      uint8_t* dst = reinterpret_cast<uint8_t*>(out_packed + (tile * KSLABS_D + slab) * A_SLAB_ELEMS) + sm100::swz_chunk_offset(r, chunk) + within * 2;
-      *reinterpret_cast<uint32_t*>(dst) = sm100::pack_bf16x2(o[nt][0], o[nt][1]);
-    }
-    {
-      const size_t tile = grow1 >> 7; const uint32_t r = grow1 & 127;
-      uint8_t* dst = reinterpret_cast<uint8_t*>(out_packed + (tile * KSLABS_D + slab) * A_SLAB_ELEMS) + sm100::swz_chunk_offset(r, chunk) + within * 2;
-      *reinterpret_cast<uint32_t*>(dst) = sm100::pack_bf16x2(o[nt][2], o[nt][3]);
-    }
+    uint8_t* seg = s_out + (col >> 6) * 2048 + (col & 7) * 2;
+    *reinterpret_cast<uint32_t*>(seg + sm100::swz_chunk_offset(g, (col & 63) >> 3)) = sm100::pack_bf16x2(o[nt][0], o[nt][1]);
+    *reinterpret_cast<uint32_t*>(seg + sm100::swz_chunk_offset(g + 8, (col & 63) >> 3)) = sm100::pack_bf16x2(o[nt][2], o[nt][3]);
+  }
+  sm100::fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint8_t* out_base = reinterpret_cast<uint8_t*>(out_packed + (row0 >> 7) * KSLABS_D * A_SLAB_ELEMS) + rbase * 128;
+#pragma unroll
+    for (int sl = 0; sl < KSLABS_D; ++sl) sm100::bulk_s2g(out_base + (size_t)sl * A_SLAB_BYTES, s_out + sl * 2048, 2048);
+    sm100::bulk_commit();
+    sm100::bulk_wait_read<0>();
   }
 }
 

@@ -1,6 +1,6 @@
 timeout 600 python -m pytest tests/test_gpu_dit.py -m gpu -q -x --timeout=240 -p no:cacheprovider -s 2>&1 | grep -E "passed|failed|stage errors|Error|error" | head
 SCLDM_FUSED_MLP=0 timeout 600 python -m pytest tests/test_gpu_dit.py -m gpu -q -x --timeout=240 -p no:cacheprovider 2>&1 | tail -1
-python tools/kernel_timeline.py 392 | grep -A1 -E "^mlp1|^proj"
+true
 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_v8.json 2>> gpurun_out/sweep.err
 python - <<PY
 import json
