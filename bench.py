@@ -212,6 +212,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=device)
     from scldm_b200 import ops
 

@@ -65,6 +65,8 @@ typedef struct scldm_dit_weights {
   const float* pos;    /* pos_embed [16][256]                 */
   const float* w_out;  /* final_layer.linear.weight [16][256] */
   const float* b_out;  /* [16]                                */
+  const void* wout_frag; /* bf16 final_layer.linear.weight in mma.sync B-fragment order [16][2][32][4]; NULL: fp32 CUDA-core path */
+  const void* win_frag;  /* bf16 input_proj.weight in mma.sync B-fragment order [1][32][32][4]                                   */
   const float* class_tables[SCLDM_MAX_CLASSES]; /* class_embeddings.<name>.weight [(V+1)][256] */
 } scldm_dit_weights;
 

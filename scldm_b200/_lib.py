@@ -30,6 +30,7 @@ class DitWeights(C.Structure):
         ("w_mlp_stream", C.c_void_p),
         ("temb_w0t", C.c_void_p), ("temb_b0", C.c_void_p), ("temb_w2t", C.c_void_p), ("temb_b2", C.c_void_p),
         ("w_in", C.c_void_p), ("b_in", C.c_void_p), ("pos", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+        ("wout_frag", C.c_void_p), ("win_frag", C.c_void_p),
         ("class_tables", C.c_void_p * MAX_CLASSES),
     ]
 

@@ -227,6 +227,16 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
   return SCLDM_OK;
 }
 
+int launch_final(const scldm_dit_weights* w, const dit::StepParams& s, int n_states, cudaStream_t st) {
+  if (w->wout_frag != nullptr && w->win_frag != nullptr) {
+    dit::StepTcWeights tw{static_cast<const uint2*>(w->wout_frag), static_cast<const uint2*>(w->win_frag)};
+    LAUNCH("final_step_tc", dit::final_step_tc_kernel<<<ceil_div(n_states, 4), 128, 0, st>>>(s, tw, n_states));
+  } else {
+    LAUNCH("final_step", dit::final_step_kernel<<<n_states < 296 ? n_states : 296, 512, 0, st>>>(s, n_states));
+  }
+  return SCLDM_OK;
+}
+
 dit::StepParams make_step(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws) {
   dit::StepParams s{};
   s.X = ws.X; s.mod = ws.mod; s.slot_mod = mod_index(plan); s.mod_stride = w->mod_stride;
@@ -310,7 +320,7 @@ int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, co
   LAUNCH("inproj", dit::inproj_kernel<<<n_states, 256, 0, st>>>(s));
   if ((rc = launch_blocks(w, plan, ws, st))) return rc;
   s.v_out = v_out; s.do_update = 0; s.do_inproj = 0;
-  LAUNCH("final_step", dit::final_step_kernel<<<n_states < 296 ? n_states : 296, 512, 0, st>>>(s, n_states));
+  if ((rc = launch_final(w, s, n_states, st))) return rc;
   return SCLDM_OK;
 }
 
@@ -369,7 +379,7 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
       else if (method == SCLDM_ODE_HEUN2) { s.a_dt = dt; s.b_dt = 0.5f * dt; }
       else { s.a_dt = 0.5f * dt; s.b_dt = sg == 0 ? 0.f : dt; }
       s.do_inproj = !(k == n_steps - 1 && s.last_stage);
-      LAUNCH("final_step", dit::final_step_kernel<<<n_states < 296 ? n_states : 296, 512, 0, st>>>(s, n_states));
+      if ((rc = launch_final(w, s, n_states, st))) return rc;
     }
   }
   return SCLDM_OK;

@@ -1206,4 +1206,153 @@ __global__ void __launch_bounds__(512) final_step_kernel(const StepParams p, int
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core version of final_step_kernel: one warp per state, everything in mma.sync fragment layout.
+//   per slot: X tile (16 tokens x 256) loaded straight into A-fragment order -> LN (quad shuffles) -> modulate -> bf16
+//             -> 32 x m16n8k16 with the final Linear (B fragments in smem) -> + bias -> CFG combine (coef)
+//   then the ODE stage update on the 16 x 16 C fragments, and the next evaluation's input projection as
+//   2 x 32 MMAs (x split into bf16 hi + lo parts so only the bf16 weight rounding remains) written to every slot.
+// ------------------------------------------------------------------------------------------
+struct StepTcWeights {
+  const uint2* wout_frag;   // final_layer.linear.weight as B fragments [16 ks][2 nt][32 lanes]
+  const uint2* win_frag;    // input_proj.weight as B fragments [32 nt][32 lanes]   (K = 16: one k-step)
+};
+
+__device__ __forceinline__ void mma_bf16_f(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) final_step_tc_kernel(const StepParams p, const StepTcWeights w, int n_states) {
+  __shared__ uint2 s_wout[32 * 32];     // 8 KB
+  __shared__ uint2 s_win[32 * 32];      // 8 KB
+  __shared__ float s_posb[TOK * D];     // 16 KB: pos_embed + input_proj.bias
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 32 * 32; i += 128) { s_wout[i] = w.wout_frag[i]; s_win[i] = w.win_frag[i]; }
+  for (int i = tid; i < TOK * D; i += 128) s_posb[i] = p.pos[i] + (p.b_in ? p.b_in[i & (D - 1)] : 0.f);
+  __syncthreads();
+  const int state = blockIdx.x * 4 + warp;
+  if (state >= n_states) return;
+  int slot0, ns;
+  state_slots(p, state, slot0, ns);
+  float coef[MAX_COMBINE];
+#pragma unroll
+  for (int k = 0; k < MAX_COMBINE; ++k) coef[k] = p.coef[k];
+  const float bo[2][2] = {{p.b_out ? p.b_out[2 * t] : 0.f, p.b_out ? p.b_out[2 * t + 1] : 0.f},
+                          {p.b_out ? p.b_out[8 + 2 * t] : 0.f, p.b_out ? p.b_out[8 + 2 * t + 1] : 0.f}};
+  float vsum[2][4] = {};
+  const float inv_d = 1.0f / D;
+#pragma unroll 1
+  for (int k = 0; k < ns; ++k) {
+    const int slot = slot0 + k;
+    const float* x0p = p.X + ((size_t)slot * TOK + g) * D + 2 * t;   // row g
+    const float* x1p = x0p + 8 * D;                                  // row g+8
+    float2 xa[16][4];   // [ks]{(g, 2t), (g+8, 2t), (g, 2t+8), (g+8, 2t+8)}
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      xa[ks][0] = *reinterpret_cast<const float2*>(x0p + 16 * ks);
+      xa[ks][1] = *reinterpret_cast<const float2*>(x1p + 16 * ks);
+      xa[ks][2] = *reinterpret_cast<const float2*>(x0p + 16 * ks + 8);
+      xa[ks][3] = *reinterpret_cast<const float2*>(x1p + 16 * ks + 8);
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      s0 += (xa[ks][0].x + xa[ks][0].y) + (xa[ks][2].x + xa[ks][2].y);
+      s1 += (xa[ks][1].x + xa[ks][1].y) + (xa[ks][3].x + xa[ks][3].y);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float m0 = s0 * inv_d, m1 = s1 * inv_d;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      xa[ks][0].x -= m0; xa[ks][0].y -= m0; xa[ks][2].x -= m0; xa[ks][2].y -= m0;
+      xa[ks][1].x -= m1; xa[ks][1].y -= m1; xa[ks][3].x -= m1; xa[ks][3].y -= m1;
+      q0 += xa[ks][0].x * xa[ks][0].x + xa[ks][0].y * xa[ks][0].y + xa[ks][2].x * xa[ks][2].x + xa[ks][2].y * xa[ks][2].y;
+      q1 += xa[ks][1].x * xa[ks][1].x + xa[ks][1].y * xa[ks][1].y + xa[ks][3].x * xa[ks][3].x + xa[ks][3].y * xa[ks][3].y;
+    }
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    const float r0 = rsqrtf(q0 * inv_d + p.eps), r1 = rsqrtf(q1 * inv_d + p.eps);
+    const float* mrow = p.mod + (size_t)p.slot_mod.row(slot) * p.mod_stride + p.mod_off_final + 2 * t;   // shift | scale
+    float acc[2][4] = {};
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      const float2 shA = *reinterpret_cast<const float2*>(mrow + 16 * ks), shB = *reinterpret_cast<const float2*>(mrow + 16 * ks + 8);
+      const float2 scA = *reinterpret_cast<const float2*>(mrow + D + 16 * ks), scB = *reinterpret_cast<const float2*>(mrow + D + 16 * ks + 8);
+      const float gAx = 1.f + scA.x, gAy = 1.f + scA.y, gBx = 1.f + scB.x, gBy = 1.f + scB.y;
+      const uint32_t a0 = sm100::pack_bf16x2(xa[ks][0].x * r0 * gAx + shA.x, xa[ks][0].y * r0 * gAy + shA.y);
+      const uint32_t a1 = sm100::pack_bf16x2(xa[ks][1].x * r1 * gAx + shA.x, xa[ks][1].y * r1 * gAy + shA.y);
+      const uint32_t a2 = sm100::pack_bf16x2(xa[ks][2].x * r0 * gBx + shB.x, xa[ks][2].y * r0 * gBy + shB.y);
+      const uint32_t a3 = sm100::pack_bf16x2(xa[ks][3].x * r1 * gBx + shB.x, xa[ks][3].y * r1 * gBy + shB.y);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const uint2 b = s_wout[(ks * 2 + nt) * 32 + lane];
+        mma_bf16_f(acc[nt], a0, a1, a2, a3, b.x, b.y);
+      }
+    }
+    const float ck = (ns == 1) ? 1.0f : coef[k];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      vsum[nt][0] += ck * (acc[nt][0] + bo[nt][0]); vsum[nt][1] += ck * (acc[nt][1] + bo[nt][1]);
+      vsum[nt][2] += ck * (acc[nt][2] + bo[nt][0]); vsum[nt][3] += ck * (acc[nt][3] + bo[nt][1]);
+    }
+  }
+  // ---- v / ODE stage update in C-fragment layout: (token g | g+8, channels 8nt+2t, +1) ----
+  float xe[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const size_t idx = ((size_t)state * TOK + g + 8 * hr) * LAT + 8 * nt + 2 * t;
+      const float2 v = make_float2(vsum[nt][2 * hr], vsum[nt][2 * hr + 1]);
+      if (p.v_out) *reinterpret_cast<float2*>(p.v_out + idx) = v;
+      float2 xev = make_float2(0.f, 0.f);
+      if (p.do_update) {
+        float2 ac = p.first_stage ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(p.acc + idx);
+        ac.x += p.b_dt * v.x; ac.y += p.b_dt * v.y;
+        const float2 xb = *reinterpret_cast<const float2*>(p.x_base + idx);
+        if (p.last_stage) {
+          xev = make_float2(xb.x + ac.x, xb.y + ac.y);
+          *reinterpret_cast<float2*>(p.x_base + idx) = xev;
+        } else {
+          *reinterpret_cast<float2*>(p.acc + idx) = ac;
+          xev = make_float2(xb.x + p.a_dt * v.x, xb.y + p.a_dt * v.y);
+        }
+      }
+      xe[nt][2 * hr] = xev.x; xe[nt][2 * hr + 1] = xev.y;
+    }
+  }
+  if (!p.do_inproj) return;
+  // ---- input projection of the next evaluation point: h = x_eval Win^T + b + pos, x_eval = hi + lo (both bf16) ----
+  uint32_t ah[4], al[4];
+  {
+    const float e[4][2] = {{xe[0][0], xe[0][1]}, {xe[0][2], xe[0][3]}, {xe[1][0], xe[1][1]}, {xe[1][2], xe[1][3]}};  // a0..a3
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16 h0 = __float2bfloat16(e[i][0]), h1 = __float2bfloat16(e[i][1]);
+      ah[i] = sm100::pack_bf16x2(e[i][0], e[i][1]);
+      al[i] = sm100::pack_bf16x2(e[i][0] - __bfloat162float(h0), e[i][1] - __bfloat162float(h1));
+    }
+  }
+#pragma unroll 4
+  for (int nt = 0; nt < 32; ++nt) {
+    const float2 p0 = *reinterpret_cast<const float2*>(s_posb + g * D + 8 * nt + 2 * t);
+    const float2 p1 = *reinterpret_cast<const float2*>(s_posb + (g + 8) * D + 8 * nt + 2 * t);
+    float c[4] = {p0.x, p0.y, p1.x, p1.y};
+    const uint2 b = s_win[nt * 32 + lane];
+    mma_bf16_f(c, ah[0], ah[1], ah[2], ah[3], b.x, b.y);
+    mma_bf16_f(c, al[0], al[1], al[2], al[3], b.x, b.y);
+    for (int k = 0; k < ns; ++k) {
+      float* dst = p.X + ((size_t)(slot0 + k) * TOK + g) * D + 8 * nt + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(c[0], c[1]);
+      *reinterpret_cast<float2*>(dst + 8 * D) = make_float2(c[2], c[3]);
+    }
+  }
+}
+
 }  // namespace dit

@@ -133,11 +133,17 @@ class PackedDiT:
         self.w_out = f32(get("final_layer.linear.weight"))
         self.b_out = f32(get("final_layer.linear.bias", (cfg.n_embed_input,)))
         self.class_tables = [f32(get(f"class_embeddings.{n}.weight")) for n in self.class_names]
+        # tensor-core final step (csrc/dit_kernels.cuh: final_step_tc_kernel)
+        self.wout_frag = dev(mma_b_frags(get("final_layer.linear.weight")))   # [16][2][32][4]
+        self.win_frag = dev(mma_b_frags(get("input_proj.weight")))            # [1][32][32][4]
+        self.use_tc_final = os.environ.get("SCLDM_TC_FINAL", "1") != "0"
 
         s = _lib.DitWeights()
         s.n_layer, s.hidden, s.hid_slabs, s.mlp1_tiles = L, H, self.hid_slabs, self.mlp1_tiles
         s.mod_stride, s.n_class, s.eps = self.mod_stride, len(self.class_names), float(cfg.layernorm_eps)
         s.w_mlp_stream = self.w_mlp_stream.data_ptr() if self.use_fused_mlp else None
+        s.wout_frag = self.wout_frag.data_ptr() if self.use_tc_final else None
+        s.win_frag = self.win_frag.data_ptr() if self.use_tc_final else None
         for name in ("w_mod", "b_mod", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_mlp1", "w_mlp2", "temb_w0t", "temb_b0",
                      "temb_w2t", "temb_b2", "w_in", "b_in", "pos", "w_out", "b_out"):
             setattr(s, name, getattr(self, name).data_ptr())
