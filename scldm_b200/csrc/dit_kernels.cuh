@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
   constexpr int EARLY = PRO == PRO_LN ? 1 : 3;   // weight slabs issued before the setup barrier (PRO_LN lends 2 buffers to X)
   constexpr uint32_t TMEM_COLS = 512;  // two 256-column fp32 accumulators
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;   // keep shared-space provenance (LDS/STS, not generic LD/ST); alignment is checked below
+  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smA = smem;                                     // 4 x 16 KB
   uint8_t* smB = smem + KSLABS_D * A_SLAB_BYTES;           // NSTAGE x 32 KB
   uint8_t* smStg = smB + NSTAGE * B_SLAB_BYTES;            // 64 KB
@@ -508,7 +509,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
   constexpr uint32_t STAGE_BYTES = A_SLAB_BYTES + B_SLAB_BYTES;  // 48 KB
   constexpr uint32_t TMEM_COLS = 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;   // keep shared-space provenance (LDS/STS, not generic LD/ST); alignment is checked below
+  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smStage = smem;                              // NSTAGE x (A 16 KB | B 32 KB)
   uint8_t* smStg = smem + NSTAGE * STAGE_BYTES;
   float* smGate = reinterpret_cast<float*>(smStg + STG_BYTES);   // [8 cells][256]
@@ -677,7 +679,8 @@ struct MlpFusedParams {
 __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFusedParams p) {
   constexpr uint32_t NSTAGE = 3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;   // keep shared-space provenance (LDS/STS, not generic LD/ST); alignment is checked below
+  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smA = smem;                                     // 4 x 16 KB (later: epilogue staging + gates)
   uint8_t* smH = smA + KSLABS_D * A_SLAB_BYTES;            // 2 x (2 x 16 KB); first the X pass buffers
   uint8_t* smB = smH + 4 * A_SLAB_BYTES;                   // NSTAGE x 32 KB
