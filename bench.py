@@ -126,6 +126,8 @@ def kernel_flops(name: str, rows: int, mod_rows: int) -> float | None:
         "gemm_astream<mlp2>": 2.0 * rows * H * D,
         "gemm_ares<COND,MOD>": 2.0 * mod_rows * D * (8 * 6 * D + 2 * D),
         "attn16": 4.0 * rows * 16 * D,
+        "mlp_fused": 2.0 * rows * D * 2 * H + 2.0 * rows * H * D,
+        "attn_block": 2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D,
     }.get(name)
 
 
@@ -302,7 +304,7 @@ def main():
                      sorted(prof.items(), key=lambda kv: -kv[1][1])}
         chunk = min(ldm.cell_chunk, B)
         rows = 3 * chunk * 16  # slots of a full chunk x 16 tokens (CFG: 3 forwards per cell)
-        gemm = {k: v for k, v in prof.items() if k.startswith("gemm_")}
+        gemm = {k: v for k, v in prof.items() if kernel_flops(k, 1, 1) is not None}
         top = max(gemm.items(), key=lambda kv: kv[1][1])
         name, (cnt, tms) = top
         fl = kernel_flops(name, rows, 1 + chunk)

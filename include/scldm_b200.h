@@ -56,6 +56,12 @@ typedef struct scldm_dit_weights {
   const void* w_mlp_stream; /* bf16 [n_layer][mlp1_tiles*4 + hid_slabs][256x64]: the same [w1|w2] tiles and c_proj slabs
                                in the consumption order of the fused MLP kernel (M1_0, M1_1, M2_0, M1_2, M2_1, ...);
                                NULL selects the unfused pair of kernels                                              */
+  const void* w_attn_stream; /* bf16 [n_layer][262144]: attn.c_attn + attn.c_proj in the consumption order of the fused
+                                attention-block kernel.  Per head pair hp (heads 2hp, 2hp+1) a "Q item" is the 192 x 64 K-major
+                                swizzled slab [Wq rows 64hp.. | Wk rows 64hp.. | Wv rows 64hp..] for one 64-wide K slab, a
+                                "P item" the 128 x 64 slab c_proj.weight[128*half.., 64hp..64hp+64]; order Q_0 (4 items),
+                                Q_1, P_0 (2 items), Q_2, P_1, Q_3, P_2, P_3.  NULL selects the three unfused kernels          */
+  const float* b_qkv_hp;     /* [n_layer][4][192]: attn.c_attn.bias in the same q|k|v-per-head-pair order (with w_attn_stream) */
   const float* temb_w0t; /* t_embedder.mlp.0.weight^T [256][256] */
   const float* temb_b0;
   const float* temb_w2t; /* t_embedder.mlp.2.weight^T [256][256] */

@@ -103,7 +103,15 @@ struct AStreamParams {
 // ==========================================================================================
 // debug timeline: slot i of CTA b lives at dbg[b*32 + i]
 __device__ __forceinline__ void dbg_stamp(long long* dbg, int slot) {
-  if (dbg != nullptr) dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 + slot] = clock64();
+  if (dbg != nullptr) {
+    long long* d = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32;
+    d[slot] = clock64();
+    if (slot == 0 || slot == 31) {   // wall-clock (ns) twins of the CTA start/end stamps + SM id
+      unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      d[slot == 0 ? 29 : 30] = (long long)g;
+      if (slot == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); d[28] = sm; }
+    }
+  }
 }
 
 struct RingState {
@@ -133,6 +141,7 @@ __device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_d, uint32_t a_smem
 // ------------------------------------------------------------------------------------------
 constexpr int XPASS_ROWS = 32;
 constexpr int XPASS_BYTES = XPASS_ROWS * D * 4;   // 32 KB = one weight-ring stage
+constexpr int XPASS_WARPS = XPASS_ROWS / 8;       // prologue warps reading each pass (8 rows per warp)
 
 // All four X passes are in flight from t=0: passes 0,1 land in a 64 KB scratch region (epilogue staging / H buffers),
 // passes 2,3 in the two weight-ring buffers that the first weight slabs do not need yet (the ring starts at physical
@@ -155,57 +164,71 @@ __device__ __forceinline__ void dbg_stamp(long long* dbg, int slot);
 __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB, uint64_t* x_full, uint64_t* x_empty, uint8_t* smA,
                                                 const float* mod, const ModIndex& slot_mod, int mod_stride, int off_mul, int off_add,
                                                 float eps, int row_tile, uint32_t ew, uint32_t lane, long long* dbg = nullptr) {
+  // Warp ew owns rows [8 ew, 8 ew + 8) of the tile: one X pass (ew / 4), one slot (ew / 2) -> one set of modulation
+  // vectors.  Four rows are normalised at a time so that four independent reduction chains overlap.  Lane l holds
+  // channels [4l, 4l+4) and [128 + 4l, 128 + 4l + 4) of a row (conflict-free 16 B shared-memory reads).
   const float inv_d = 1.0f / D;
-  const int half = ew >> 3;          // which of the pass's two slots this warp serves
-  const int r2 = (ew & 7) * 2;       // first of this warp's two rows inside that slot
-  // modulation vectors of this warp's 4 slots: issued before anything is waited on
-  float4 m0[4], m1[4], a0[4], a1[4];
+  const int pss = ew >> 2;
+  const float* mrow = mod + (size_t)slot_mod.row(row_tile * 8 + (ew >> 1)) * mod_stride;
+  const float4 m0 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 4), m1 = *reinterpret_cast<const float4*>(mrow + off_mul + 128 + lane * 4);
+  const float4 a0 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 4), a1 = *reinterpret_cast<const float4*>(mrow + off_add + 128 + lane * 4);
+  sm100::mbar_wait(&x_full[pss], 0);
+  if ((ew & 3) == 0 && lane == 0) dbg_stamp(dbg, 22 + pss);
+  const uint8_t* xb = x_pass_buffer(pss, smScratch, smB) + (ew & 3) * 8 * (D * 4) + lane * 16;
+  uint8_t* a_lo = smA + (lane >> 4) * A_SLAB_BYTES + (lane & 1) * 8;
 #pragma unroll
-  for (int pss = 0; pss < 4; ++pss) {
-    const float* mrow = mod + (size_t)slot_mod.row(row_tile * 8 + 2 * pss + half) * mod_stride;
-    m0[pss] = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8); m1[pss] = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 8 + 4);
-    a0[pss] = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8); a1[pss] = *reinterpret_cast<const float4*>(mrow + off_add + lane * 8 + 4);
-  }
+  for (int rnd = 0; rnd < 2; ++rnd) {
+    float v[4][8];
 #pragma unroll
-  for (int pss = 0; pss < 4; ++pss) {
-    sm100::mbar_wait(&x_full[pss], 0);
-    if (ew == 0 && lane == 0) dbg_stamp(dbg, 22 + pss);
-    const uint8_t* xb = x_pass_buffer(pss, smScratch, smB) + (half * 16 + r2) * (D * 4) + lane * 32;
-    float v[2][8];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float4 x0 = *reinterpret_cast<const float4*>(xb + i * (D * 4));
-      const float4 x1 = *reinterpret_cast<const float4*>(xb + i * (D * 4) + 16);
+    for (int i = 0; i < 4; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xb + (rnd * 4 + i) * (D * 4));
+      const float4 x1 = *reinterpret_cast<const float4*>(xb + (rnd * 4 + i) * (D * 4) + 512);
       v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w; v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
     }
-    if (pss >= 2) {   // hand the borrowed weight-ring buffer back to the producer
+    if (rnd == 1 && pss >= 2) {   // hand the borrowed weight-ring buffer back to the producer
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(&x_empty[pss - 2]);
     }
-    float s0 = 0.f, s1 = 0.f;
+    float sm_[4], sq[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s0 += v[0][j]; s1 += v[1][j]; }
+    for (int i = 0; i < 4; ++i) {
+      sm_[i] = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-    const float mean0 = s0 * inv_d, mean1 = s1 * inv_d;
-    float q0 = 0.f, q1 = 0.f;
+      for (int j = 0; j < 8; ++j) sm_[i] += v[i][j];
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { v[0][j] -= mean0; q0 += v[0][j] * v[0][j]; v[1][j] -= mean1; q1 += v[1][j] * v[1][j]; }
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
-    const float rs[2] = {rsqrtf(q0 * inv_d + eps), rsqrtf(q1 * inv_d + eps)};
-    if (ew == 0 && lane == 0 && pss == 0) dbg_stamp(dbg, 26);
-    const float mul[8] = {1.f + m0[pss].x, 1.f + m0[pss].y, 1.f + m0[pss].z, 1.f + m0[pss].w, 1.f + m1[pss].x, 1.f + m1[pss].y, 1.f + m1[pss].z, 1.f + m1[pss].w};
-    const float add[8] = {a0[pss].x, a0[pss].y, a0[pss].z, a0[pss].w, a1[pss].x, a1[pss].y, a1[pss].z, a1[pss].w};
+      for (int i = 0; i < 4; ++i) sm_[i] += __shfl_xor_sync(0xffffffffu, sm_[i], o);
+    }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = pss * XPASS_ROWS + half * 16 + r2 + i;   // row within the tile
-      uint4 o;
-      o.x = sm100::pack_bf16x2(v[i][0] * rs[i] * mul[0] + add[0], v[i][1] * rs[i] * mul[1] + add[1]);
-      o.y = sm100::pack_bf16x2(v[i][2] * rs[i] * mul[2] + add[2], v[i][3] * rs[i] * mul[3] + add[3]);
-      o.z = sm100::pack_bf16x2(v[i][4] * rs[i] * mul[4] + add[4], v[i][5] * rs[i] * mul[5] + add[5]);
-      o.w = sm100::pack_bf16x2(v[i][6] * rs[i] * mul[6] + add[6], v[i][7] * rs[i] * mul[7] + add[7]);
-      *reinterpret_cast<uint4*>(smA + (lane >> 3) * A_SLAB_BYTES + sm100::swz_chunk_offset(r, lane & 7)) = o;
+    for (int i = 0; i < 4; ++i) {
+      const float mean = sm_[i] * inv_d;
+      sq[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[i][j] -= mean; sq[i] += v[i][j] * v[i][j]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+    }
+    if (ew == 0 && lane == 0 && rnd == 0) dbg_stamp(dbg, 26);
+    // first use of the modulation vectors: their (two dependent) global loads have been in flight since kernel entry
+    const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
+    const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float rs = rsqrtf(sq[i] * inv_d + eps);
+      const int r = ew * 8 + rnd * 4 + i;   // row within the tile
+      uint2 lo, hi;
+      lo.x = sm100::pack_bf16x2(v[i][0] * rs * mul[0] + add[0], v[i][1] * rs * mul[1] + add[1]);
+      lo.y = sm100::pack_bf16x2(v[i][2] * rs * mul[2] + add[2], v[i][3] * rs * mul[3] + add[3]);
+      hi.x = sm100::pack_bf16x2(v[i][4] * rs * mul[4] + add[4], v[i][5] * rs * mul[5] + add[5]);
+      hi.y = sm100::pack_bf16x2(v[i][6] * rs * mul[6] + add[6], v[i][7] * rs * mul[7] + add[7]);
+      const uint32_t off = sm100::swz_chunk_offset(r, (lane & 15) >> 1);
+      *reinterpret_cast<uint2*>(a_lo + off) = lo;                       // channels [4l, 4l+4)       -> slab l/16
+      *reinterpret_cast<uint2*>(a_lo + 2 * A_SLAB_BYTES + off) = hi;    // channels [128+4l, +4)     -> slab 2 + l/16
     }
   }
 }
@@ -256,7 +279,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
     }
     sm100::mbar_init(a_ready, EPI_WARPS);
     for (uint32_t i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
-    for (uint32_t i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], EPI_WARPS);
+    for (uint32_t i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], XPASS_WARPS);
     sm100::fence_barrier_init();
     // first loads go out before the setup barrier: the X tile (all four passes) and the first weight slab(s)
     if constexpr (PRO == PRO_LN) producer_issue_x_passes(p.X, row_tile, smStg, smB, x_full);
@@ -502,6 +525,59 @@ constexpr size_t ares_smem_bytes() {
 static_assert(2 * XPASS_BYTES <= STG_ARES_BYTES, "X pass buffers alias the epilogue staging");
 
 // ==========================================================================================
+// Residual epilogue, one warp at a time and without CTA-wide barriers:
+//   X[32q + r][64*sub + c] += gate[slot(r)][c] * (acc[r][c] + bias[c])      r < 32, c < 64
+// The accumulator arrives row-per-lane (tcgen05.ld 32x32b); a 2 KB warp-private staging block (XOR-swizzled, bank
+// conflict free both ways) turns it into the row-contiguous order of the global read-modify-write (8 rows x 64 B per
+// warp instruction).  The residual rows are prefetched two sub-chunks ahead, the first two before the accumulator wait.
+// ==========================================================================================
+constexpr int RESID_WARP_STG = 2048;
+constexpr int RESID_STG_BYTES = EPI_WARPS * RESID_WARP_STG;   // 32 KB
+template <bool HAS_BIAS, typename WaitAcc>
+__device__ __forceinline__ void resid_epilogue_warp(float* __restrict__ Xtile, uint32_t taddr_q, uint8_t* stg_warp, const float* smGate,
+                                                    const float* smBias, uint32_t q, uint32_t sub, uint32_t lane, WaitAcc&& wait_acc) {
+  const uint32_t rg = lane >> 2, cchunk = lane & 3;          // global side: row within an 8-row group, 16 B chunk
+  float* xp = Xtile + (size_t)(q * 32 + rg) * D + sub * 64 + cchunk * 4;
+  float4 xr[2][4];
+  auto ldx = [&](int sc, int b) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) xr[b][it] = *reinterpret_cast<const float4*>(xp + (size_t)it * 8 * D + sc * 16);
+  };
+  ldx(0, 0);
+  ldx(1, 1);
+  wait_acc();
+  const uint32_t wsw = (lane >> 1) & 3;                      // staging swizzle of the row this lane writes
+#pragma unroll
+  for (int sc = 0; sc < 4; ++sc) {
+    {
+      uint32_t v[16];
+      sm100::tmem_ld_32x32b_x16(taddr_q + sub * 64 + sc * 16, v);
+      sm100::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(stg_warp + lane * 64 + ((c ^ wsw) << 4)) = make_float4(
+            __uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
+    }
+    __syncwarp();
+    const int col = sub * 64 + sc * 16 + cchunk * 4;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (HAS_BIAS) bb = *reinterpret_cast<const float4*>(smBias + col);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const uint32_t r = it * 8 + rg;
+      const float4 a = *reinterpret_cast<const float4*>(stg_warp + r * 64 + ((cchunk ^ ((r >> 1) & 3)) << 4));
+      const float4 gg = *reinterpret_cast<const float4*>(smGate + ((q * 32 + r) >> 4) * D + col);
+      float4 o = xr[sc & 1][it];
+      o.x += gg.x * (a.x + bb.x); o.y += gg.y * (a.y + bb.y);
+      o.z += gg.z * (a.z + bb.z); o.w += gg.w * (a.w + bb.w);
+      *reinterpret_cast<float4*>(xp + (size_t)it * 8 * D + sc * 16) = o;
+    }
+    __syncwarp();                                            // staging is rewritten by the next sub-chunk
+    if (sc + 2 < 4) ldx(sc + 2, sc & 1);
+  }
+}
+
+// ==========================================================================================
 // GEMM with both operands streamed by bulk TMA; epilogue x += gate * (acc + bias)
 // ==========================================================================================
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(const AStreamParams p) {
@@ -582,10 +658,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
     const uint32_t q = warp & 3;
     const uint32_t sub = ew >> 2;
     const uint32_t etid = threadIdx.x - 64;
-    const uint32_t row = q * 32 + lane;
-    // while the MMAs run: stage the 8 cells' gate vectors (8 x 256 fp32) and the bias in shared memory, and start
-    // fetching the residual rows.  thread -> items idx = it*512 + etid -> (row r = idx/16, float4 column cc) per chunk
-    const uint32_t cc = etid & 15;
+    // while the MMAs run: stage the 8 cells' gate vectors (8 x 256 fp32) and the bias in shared memory
     {
       // 8 cells x 64 float4 = 512 float4: one per thread
       const int cell = etid >> 6, c4 = etid & 63;
@@ -597,48 +670,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
             p.bias != nullptr ? *reinterpret_cast<const float4*>(p.bias + etid * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (etid == 0) dbg_stamp(p.dbg, 3);
-    float4 x[2][4];
-    auto load_chunk = [&](int ch, int buf) {
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
-        x[buf][it] = *reinterpret_cast<const float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + ch * 64 + cc * 4);
-      }
-    };
-    load_chunk(0, 0);
-    sm100::mbar_wait(tmem_full, 0);
-    sm100::tc_fence_after();
-    if (etid == 0) dbg_stamp(p.dbg, 4);
-    const uint32_t taddr = tmem_base + ((q * 32u) << 16);
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      if (etid == 0) dbg_stamp(p.dbg, 5 + ch);
-      const int col = ch * 64 + cc * 4;
-      if (ch + 1 < 4) load_chunk(ch + 1, (ch + 1) & 1);
-      sm100::named_bar_sync(1, EPI_THREADS);   // staging free (and, for ch = 0, gate/bias staged)
-      {
-        uint32_t v[16];
-        sm100::tmem_ld_32x32b_x16(taddr + ch * 64 + sub * 16, v);
-        sm100::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(smStg + row * 272 + (sub * 4 + c) * 16) = make_float4(
-              __uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
-      }
-      sm100::named_bar_sync(1, EPI_THREADS);   // staging full
-      const float4 bb = *reinterpret_cast<const float4*>(smBias + col);
-      // coalesced read-modify-write of the residual stream: 2 rows x 256 B per warp instruction
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
-        const float4 a = *reinterpret_cast<const float4*>(smStg + r * 272 + cc * 16);
-        const float4 gg = *reinterpret_cast<const float4*>(smGate + (r >> 4) * D + col);
-        float4 o = x[ch & 1][it];
-        o.x += gg.x * (a.x + bb.x); o.y += gg.y * (a.y + bb.y);
-        o.z += gg.z * (a.z + bb.z); o.w += gg.w * (a.w + bb.w);
-        *reinterpret_cast<float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + col) = o;
-      }
-    }
+    sm100::named_bar_sync(1, EPI_THREADS);   // gates + bias staged (the MMAs are still running)
+    resid_epilogue_warp<true>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16), smStg + ew * RESID_WARP_STG, smGate, smBias,
+                              q, sub, lane, [&] {
+                                sm100::mbar_wait(tmem_full, 0);
+                                sm100::tc_fence_after();
+                                if (etid == 0) dbg_stamp(p.dbg, 4);
+                              });
   }
 
   sm100::tc_fence_before();
@@ -708,7 +746,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     sm100::mbar_init(acc1_free, EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&h_ready[i], EPI_WARPS); sm100::mbar_init(&h_free[i], 1);
-      sm100::mbar_init(&x_empty[i], EPI_WARPS);
+      sm100::mbar_init(&x_empty[i], XPASS_WARPS);
     }
     for (int i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
     sm100::mbar_init(acc2_full, 1);
@@ -826,49 +864,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     }
 
     // ---------- final epilogue: x += gate * acc2 ----------
-    float* smGate = reinterpret_cast<float*>(smA + STG_BYTES);   // the A tile is dead once acc2 is complete
-    const uint32_t cc = etid & 15;
-    float4 x[2][4];
-    auto load_chunk = [&](int ch, int bufi) {
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
-        x[bufi][it] = *reinterpret_cast<const float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + ch * 64 + cc * 4);
-      }
-    };
-    load_chunk(0, 0);
+    float* smGate = reinterpret_cast<float*>(smA + RESID_STG_BYTES);   // the A tile is dead once acc2 is complete
     const int gcell = etid >> 6, gc4 = etid & 63;
     const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod.row(row_tile * 8 + gcell) * p.mod_stride + p.mod_off_gate + gc4 * 4);
-    sm100::mbar_wait(acc2_full, 0);
-    sm100::tc_fence_after();
-    if (etid == 0) dbg_stamp(p.dbg, 20);
-    reinterpret_cast<float4*>(smGate)[etid] = gate_v;
-    const uint32_t taddr2 = tmem_base + ((q * 32u) << 16) + BLOCK_N;
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const int col = ch * 64 + cc * 4;
-      if (ch + 1 < 4) load_chunk(ch + 1, (ch + 1) & 1);
-      sm100::named_bar_sync(1, EPI_THREADS);
-      {
-        uint32_t v[16];
-        sm100::tmem_ld_32x32b_x16(taddr2 + ch * 64 + sub * 16, v);
-        sm100::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(smA + row * 272 + (sub * 4 + c) * 16) = make_float4(
-              __uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
-      }
-      sm100::named_bar_sync(1, EPI_THREADS);
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const uint32_t r = (it * EPI_THREADS + etid) >> 4;
-        const float4 a = *reinterpret_cast<const float4*>(smA + r * 272 + cc * 16);
-        const float4 gg = *reinterpret_cast<const float4*>(smGate + (r >> 4) * D + col);
-        float4 o = x[ch & 1][it];
-        o.x += gg.x * a.x; o.y += gg.y * a.y; o.z += gg.z * a.z; o.w += gg.w * a.w;
-        *reinterpret_cast<float4*>(p.X + ((size_t)row_tile * BLOCK_M + r) * D + col) = o;
-      }
-    }
+    resid_epilogue_warp<false>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16) + BLOCK_N, smA + ew * RESID_WARP_STG, smGate,
+                               nullptr, q, sub, lane, [&] {
+                                 sm100::mbar_wait(acc2_full, 0);
+                                 sm100::tc_fence_after();
+                                 if (etid == 0) dbg_stamp(p.dbg, 20);
+                                 reinterpret_cast<float4*>(smGate)[etid] = gate_v;
+                                 sm100::named_bar_sync(1, EPI_THREADS);
+                               });
   }
   sm100::tc_fence_before();
   __syncthreads();
@@ -897,35 +903,11 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
   return y;
 }
 
-__global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out_packed, int n_slots) {
-  // one CTA per slot (cell-forward), one warp per head.  The slot's q|k|v rows (16 tokens x 768 channels) are 12
-  // contiguous 2 KB segments of the packed activation slabs: stage them with 12 bulk-TMA copies, then read the mma
-  // fragments from shared memory (the swizzle is resolved per access).
-  __shared__ __align__(128) uint8_t s_qkv[12 * 2048];
-  __shared__ uint64_t s_bar;
-  const int slot = blockIdx.x;
-  const int head = threadIdx.x >> 5;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t g = lane >> 2, t = lane & 3;
-  if (slot >= n_slots) return;
-  const size_t row0 = (size_t)slot * TOK;                 // first token row of this slot
-  const uint8_t* tile_base = reinterpret_cast<const uint8_t*>(qkv + (row0 >> 7) * (3 * D / BLOCK_K) * A_SLAB_ELEMS);
-  const uint32_t rbase = row0 & 127;                      // multiple of 16: the 16 rows share (r & 7) patterns with r - rbase
-  if (threadIdx.x == 0) {
-    sm100::mbar_init(&s_bar, 1);
-    sm100::fence_barrier_init();
-    sm100::mbar_arrive_expect_tx(&s_bar, 12 * 2048);
-#pragma unroll
-    for (int sl = 0; sl < 12; ++sl)
-      sm100::bulk_g2s(s_qkv + sl * 2048, tile_base + (size_t)sl * A_SLAB_BYTES + rbase * 128, 2048, &s_bar);
-  }
-  __syncthreads();
-  sm100::mbar_wait(&s_bar, 0);
-  auto ld2 = [&](int token, int part, int dim) -> uint32_t {
-    const uint32_t col = part * D + head * HD + dim;
-    // (rbase + token) & 7 == token & 7 because rbase is a multiple of 16
-    return *reinterpret_cast<const uint32_t*>(s_qkv + (col >> 6) * 2048 + sm100::swz_chunk_offset(token, (col & 63) >> 3) + (col & 7) * 2);
-  };
+// softmax(Q K^T / sqrt(32)) V for one (slot, head) on one warp.  ld2(token, part, dim) returns the bf16 pair
+// (dim, dim+1) of q (part 0), k (1) or v (2) for that token and head; the result is the C fragment layout of
+// m16n8k16: o[nt] = rows (g, g+8) x dims (8 nt + 2t, +1).
+template <typename LD2>
+__device__ __forceinline__ void attn16_core(LD2&& ld2, uint32_t g, uint32_t t, float (&o)[4][4]) {
   // S = Q K^T : A = Q (16 tokens x 32 dims) in two k-steps; B[k=dim][n=key] = K[key][dim]
   float s[2][4] = {};
 #pragma unroll
@@ -972,7 +954,8 @@ __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qk
   pa[2] = sm100::pack_bf16x2(s[1][0] * r0, s[1][1] * r0);
   pa[3] = sm100::pack_bf16x2(s[1][2] * r1, s[1][3] * r1);
   // B[k=key][n=dim] = V[key][dim]: load V as 8x8 (token, dim-pair) tiles and transpose in registers
-  float o[4][4] = {};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     const uint32_t v0 = ld2(g, 2, nt * 8 + 2 * t);      // tokens 0-7 , dims nt*8 + (2t, 2t+1)
@@ -981,6 +964,39 @@ __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qk
     const uint32_t b1 = movmatrix_trans(v1);            // -> (keys 2t+8,.. ; dim nt*8+g)
     mma_bf16_16816(o[nt], pa, b0, b1);
   }
+}
+
+__global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out_packed, int n_slots) {
+  // one CTA per slot (cell-forward), one warp per head.  The slot's q|k|v rows (16 tokens x 768 channels) are 12
+  // contiguous 2 KB segments of the packed activation slabs: stage them with 12 bulk-TMA copies, then read the mma
+  // fragments from shared memory (the swizzle is resolved per access).
+  __shared__ __align__(128) uint8_t s_qkv[12 * 2048];
+  __shared__ uint64_t s_bar;
+  const int slot = blockIdx.x;
+  const int head = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t g = lane >> 2, t = lane & 3;
+  if (slot >= n_slots) return;
+  const size_t row0 = (size_t)slot * TOK;                 // first token row of this slot
+  const uint8_t* tile_base = reinterpret_cast<const uint8_t*>(qkv + (row0 >> 7) * (3 * D / BLOCK_K) * A_SLAB_ELEMS);
+  const uint32_t rbase = row0 & 127;                      // multiple of 16: the 16 rows share (r & 7) patterns with r - rbase
+  if (threadIdx.x == 0) {
+    sm100::mbar_init(&s_bar, 1);
+    sm100::fence_barrier_init();
+    sm100::mbar_arrive_expect_tx(&s_bar, 12 * 2048);
+#pragma unroll
+    for (int sl = 0; sl < 12; ++sl)
+      sm100::bulk_g2s(s_qkv + sl * 2048, tile_base + (size_t)sl * A_SLAB_BYTES + rbase * 128, 2048, &s_bar);
+  }
+  __syncthreads();
+  sm100::mbar_wait(&s_bar, 0);
+  auto ld2 = [&](int token, int part, int dim) -> uint32_t {
+    const uint32_t col = part * D + head * HD + dim;
+    // (rbase + token) & 7 == token & 7 because rbase is a multiple of 16
+    return *reinterpret_cast<const uint32_t*>(s_qkv + (col >> 6) * 2048 + sm100::swz_chunk_offset(token, (col & 63) >> 3) + (col & 7) * 2);
+  };
+  float o[4][4];
+  attn16_core(ld2, g, t, o);
   // O rows (g, g+8) x dims (nt*8 + 2t, +1): assemble the slot's 16 x 256 output as 4 swizzled 2 KB slab segments in
   // shared memory (reusing the q slabs, which every warp has finished reading after the barrier) and bulk-store them
   __syncthreads();
@@ -1001,6 +1017,243 @@ __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qk
     sm100::bulk_commit();
     sm100::bulk_wait_read<0>();
   }
+}
+
+// ==========================================================================================
+// Fused attention half of a DiT block (layers.py:213-218):
+//     x += gate * c_proj( attention( c_attn( LN(x) * (1 + c0) + c1 ) ) )
+// One CTA per 128-row tile (8 slots).  q/k/v and the attention output never leave the SM:
+//
+//   prologue    LN + modulate -> A tile (4 swizzled slabs, smem); X rows arrive by bulk TMA (ln_prologue_tma)
+//   per head pair hp (heads 2hp, 2hp+1; 4 of them):
+//     Q_hp      accq[128 x 192] = A x [Wq_hp | Wk_hp | Wv_hp]^T              (TMEM cols 0-191)
+//     E_hp      accq + bias -> bf16 q|k|v slabs in smem -> 16 (slot, head) attention jobs, one per warp (mma.sync)
+//               -> AO_hp slab (smem) = K slab hp of the c_proj A operand
+//     P_hp      accp[128 x 256] += AO_hp x Wproj[:, 64hp:64hp+64]^T          (TMEM cols 256-511, two N=128 halves)
+//   epilogue    x += gate * (accp + bias)   (resid_epilogue_warp)
+//
+// MMA issue order Q_0, Q_1, P_0, Q_2, P_1, Q_3, P_2, P_3 (the tensor pipe works on Q_{hp+1} while the warps run E_hp);
+// the weights are packed in exactly that order (pack.py: attn stream), 24 KB per Q item (192 x 64 slab, one per K
+// slab) and 16 KB per P item (128 x 64).
+// ==========================================================================================
+struct AttnBlockParams {
+  float* X;               // residual stream [rows_pad][256] fp32, updated in place
+  const float* mod;
+  ModIndex slot_mod;
+  int mod_stride;
+  int mod_off_mul, mod_off_add, mod_off_gate;
+  float eps;
+  const bf16* Wstream;    // one layer of the attention weight stream (512 KB)
+  const float* bias_qkv;  // [4 head pairs][192] in accumulator column order (q | k | v of the pair)
+  const float* bias_proj; // [256]
+  long long* dbg;
+};
+
+constexpr int AB_HP = 4;                        // head pairs
+constexpr int AB_QN = 192;                      // accumulator columns per head pair: q | k | v, 64 each
+constexpr uint32_t AB_NSTAGE = 3;
+constexpr int AB_STAGE_BYTES = AB_QN * BLOCK_K * 2;     // 24 KB
+constexpr int AB_Q_ITEM_BYTES = AB_QN * BLOCK_K * 2;    // 24 KB
+constexpr int AB_P_ITEM_BYTES = 128 * BLOCK_K * 2;      // 16 KB
+constexpr int AB_OFF_QKV = KSLABS_D * A_SLAB_BYTES;               // 64 KB
+constexpr int AB_OFF_AO = AB_OFF_QKV + 3 * A_SLAB_BYTES;          // +48 KB
+constexpr int AB_OFF_W = AB_OFF_AO + A_SLAB_BYTES;                // +16 KB = 128 KB
+constexpr int AB_OFF_GATE = AB_OFF_W + AB_NSTAGE * AB_STAGE_BYTES;
+constexpr int AB_OFF_BIASP = AB_OFF_GATE + 8 * D * 4;
+constexpr int AB_OFF_BIASQ = AB_OFF_BIASP + D * 4;
+constexpr int AB_OFF_BARS = AB_OFF_BIASQ + AB_HP * AB_QN * 4;
+constexpr size_t attn_block_smem_bytes() { return AB_OFF_BARS + 256; }
+static_assert(2 * XPASS_BYTES <= 4 * A_SLAB_BYTES, "X passes 0,1 alias the q/k/v + AO staging");
+static_assert(2 * XPASS_BYTES <= AB_NSTAGE * AB_STAGE_BYTES, "X passes 2,3 alias the weight ring");
+static_assert(RESID_STG_BYTES <= 3 * A_SLAB_BYTES, "residual staging aliases the q/k/v slabs");
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBlockParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* smA = smem;
+  uint8_t* smQKV = smem + AB_OFF_QKV;     // q | k | v slabs of the current head pair; first X passes 0,1
+  uint8_t* smAO = smem + AB_OFF_AO;
+  uint8_t* smW = smem + AB_OFF_W;         // weight ring; first X passes 2,3
+  float* smGate = reinterpret_cast<float*>(smem + AB_OFF_GATE);
+  float* smBiasP = reinterpret_cast<float*>(smem + AB_OFF_BIASP);
+  float* smBiasQ = reinterpret_cast<float*>(smem + AB_OFF_BIASQ);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_OFF_BARS);
+  uint64_t* full = bars;                  // [3]
+  uint64_t* empty = bars + 3;             // [3]
+  uint64_t* a_ready = bars + 6;
+  uint64_t* accq_full = bars + 7;
+  uint64_t* accq_free = bars + 8;
+  uint64_t* ao_ready = bars + 9;
+  uint64_t* ao_free = bars + 10;
+  uint64_t* accp_full = bars + 11;
+  uint64_t* x_full = bars + 12;           // [4]
+  uint64_t* x_empty = bars + 16;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_tile = blockIdx.x;
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 0);
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < AB_NSTAGE; ++i) { sm100::mbar_init(&full[i], 1); sm100::mbar_init(&empty[i], 1); }
+    sm100::mbar_init(a_ready, EPI_WARPS);
+    sm100::mbar_init(accq_full, 1);
+    sm100::mbar_init(accq_free, EPI_WARPS);
+    sm100::mbar_init(ao_ready, EPI_WARPS);
+    sm100::mbar_init(ao_free, 1);
+    sm100::mbar_init(accp_full, 1);
+    for (int i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
+    for (int i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], XPASS_WARPS);
+    sm100::fence_barrier_init();
+    producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
+  }
+  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== producer: one linear stream of weight items ======================
+    if (lane == 0) {
+      sm100::mbar_wait(&x_empty[0], 0);   // the ring carried X passes 2 and 3
+      sm100::mbar_wait(&x_empty[1], 0);
+      RingState rs;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wstream);
+      auto issue = [&](uint32_t bytes) {
+        sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+        sm100::mbar_arrive_expect_tx(&full[rs.stage], bytes);
+        sm100::bulk_g2s(smW + rs.stage * AB_STAGE_BYTES, src, bytes, &full[rs.stage]);
+        src += bytes;
+        rs.advance(AB_NSTAGE);
+      };
+      for (int step = 0; step <= AB_HP; ++step) {
+        if (step < AB_HP)
+          for (int ks = 0; ks < KSLABS_D; ++ks) issue(AB_Q_ITEM_BYTES);
+        if (step >= 1)
+          for (int half = 0; half < 2; ++half) issue(AB_P_ITEM_BYTES);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =======================================================
+    if (lane == 0) {
+      const uint32_t idesc_q = sm100::make_idesc_bf16(BLOCK_M, AB_QN);
+      const uint32_t idesc_p = sm100::make_idesc_bf16(BLOCK_M, 128);
+      const uint32_t accq = tmem_base, accp = tmem_base + 256;
+      dbg_stamp(p.dbg, 1);
+      sm100::mbar_wait(a_ready, 0);
+      sm100::tc_fence_after();
+      dbg_stamp(p.dbg, 2);
+      RingState rs;
+      for (int step = 0; step <= AB_HP; ++step) {
+        if (step < AB_HP) {  // Q_step
+          if (step > 0) { sm100::mbar_wait(accq_free, (step - 1) & 1); sm100::tc_fence_after(); }
+          for (int ks = 0; ks < KSLABS_D; ++ks) {
+            sm100::mbar_wait(&full[rs.stage], rs.phase);
+            sm100::tc_fence_after();
+            issue_slab_mmas(accq, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smW + rs.stage * AB_STAGE_BYTES), idesc_q, ks == 0);
+            sm100::umma_commit(&empty[rs.stage]);
+            rs.advance(AB_NSTAGE);
+          }
+          sm100::umma_commit(accq_full);
+        }
+        if (step >= 1) {  // P_{step-1}
+          const int hp = step - 1;
+          sm100::mbar_wait(ao_ready, hp & 1);
+          sm100::tc_fence_after();
+          for (int half = 0; half < 2; ++half) {
+            sm100::mbar_wait(&full[rs.stage], rs.phase);
+            sm100::tc_fence_after();
+            issue_slab_mmas(accp + half * 128, sm100::smem_u32(smAO), sm100::smem_u32(smW + rs.stage * AB_STAGE_BYTES), idesc_p, hp == 0);
+            sm100::umma_commit(&empty[rs.stage]);
+            rs.advance(AB_NSTAGE);
+          }
+          sm100::umma_commit(ao_free);
+        }
+      }
+      sm100::umma_commit(accp_full);
+    }
+  } else {
+    // ===================== 16 worker warps ==================================================
+    const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
+    const uint32_t row = q * 32 + lane;
+    // gate / bias vectors: issue the global loads now, park them in shared memory after the prologue
+    const int gcell = etid >> 6, gc4 = etid & 63;
+    const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod.row(row_tile * 8 + gcell) * p.mod_stride + p.mod_off_gate + gc4 * 4);
+    float4 bias_v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (etid < 64) bias_v = *reinterpret_cast<const float4*>(p.bias_proj + etid * 4);
+    else if (etid < 64 + AB_HP * AB_QN / 4) bias_v = *reinterpret_cast<const float4*>(p.bias_qkv + (etid - 64) * 4);
+    ln_prologue_tma(smQKV, smW, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg);
+    sm100::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) sm100::mbar_arrive(a_ready);
+    reinterpret_cast<float4*>(smGate)[etid] = gate_v;
+    if (etid < 64) reinterpret_cast<float4*>(smBiasP)[etid] = bias_v;
+    else if (etid < 64 + AB_HP * AB_QN / 4) reinterpret_cast<float4*>(smBiasQ)[etid - 64] = bias_v;
+    if (etid == 0) dbg_stamp(p.dbg, 3);
+
+    const uint32_t taddr_q = tmem_base + ((q * 32u) << 16);
+    const uint32_t slot = ew >> 1, h = ew & 1;        // this warp's attention job within a head pair
+    const uint32_t g = lane >> 2, t = lane & 3;
+    for (int hp = 0; hp < AB_HP; ++hp) {
+      sm100::mbar_wait(accq_full, hp & 1);
+      sm100::tc_fence_after();
+      if (etid == 0) dbg_stamp(p.dbg, 4 + 3 * hp);
+      uint32_t v0[32], v1[16];
+      sm100::tmem_ld_32x32b_x32(taddr_q + sub * 48, v0);
+      sm100::tmem_ld_32x32b_x16(taddr_q + sub * 48 + 32, v1);
+      sm100::tmem_ld_wait();
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(accq_free);          // Q_{hp+1} may overwrite the accumulator
+      sm100::named_bar_sync(1, EPI_THREADS);                 // every warp is done reading the previous pair's q/k/v (and, hp = 0, biases staged)
+#pragma unroll
+      for (int c8 = 0; c8 < 6; ++c8) {
+        const uint32_t gcol = sub * 48 + c8 * 8;             // accumulator column: [0,64) q, [64,128) k, [128,192) v
+        const float4 b0 = *reinterpret_cast<const float4*>(smBiasQ + hp * AB_QN + gcol);
+        const float4 b1 = *reinterpret_cast<const float4*>(smBiasQ + hp * AB_QN + gcol + 4);
+        const uint32_t* vv = c8 < 4 ? &v0[c8 * 8] : &v1[(c8 - 4) * 8];
+        uint4 o;
+        o.x = sm100::pack_bf16x2(__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y);
+        o.y = sm100::pack_bf16x2(__uint_as_float(vv[2]) + b0.z, __uint_as_float(vv[3]) + b0.w);
+        o.z = sm100::pack_bf16x2(__uint_as_float(vv[4]) + b1.x, __uint_as_float(vv[5]) + b1.y);
+        o.w = sm100::pack_bf16x2(__uint_as_float(vv[6]) + b1.z, __uint_as_float(vv[7]) + b1.w);
+        *reinterpret_cast<uint4*>(smQKV + (gcol >> 6) * A_SLAB_BYTES + sm100::swz_chunk_offset(row, (gcol & 63) >> 3)) = o;
+      }
+      sm100::named_bar_sync(1, EPI_THREADS);                 // q/k/v of this head pair staged
+      if (etid == 0) dbg_stamp(p.dbg, 5 + 3 * hp);
+      auto ld2 = [&](int token, int part, int dim) -> uint32_t {
+        const uint32_t col = h * HD + dim;
+        return *reinterpret_cast<const uint32_t*>(smQKV + part * A_SLAB_BYTES + sm100::swz_chunk_offset(slot * TOK + token, col >> 3) + (col & 7) * 2);
+      };
+      float o[4][4];
+      attn16_core(ld2, g, t, o);
+      if (hp > 0) sm100::mbar_wait(ao_free, (hp - 1) & 1);   // P_{hp-1} finished reading the AO slab
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t col = h * HD + nt * 8 + 2 * t;
+        uint8_t* dst = smAO + (col & 7) * 2;
+        *reinterpret_cast<uint32_t*>(dst + sm100::swz_chunk_offset(slot * TOK + g, col >> 3)) = sm100::pack_bf16x2(o[nt][0], o[nt][1]);
+        *reinterpret_cast<uint32_t*>(dst + sm100::swz_chunk_offset(slot * TOK + g + 8, col >> 3)) = sm100::pack_bf16x2(o[nt][2], o[nt][3]);
+      }
+      sm100::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(ao_ready);
+      if (etid == 0) dbg_stamp(p.dbg, 6 + 3 * hp);
+    }
+
+    // ---------- final epilogue: x += gate * (accp + bias) ----------
+    resid_epilogue_warp<true>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16) + 256, smQKV + ew * RESID_WARP_STG, smGate, smBiasP,
+                              q, sub, lane, [&] {
+                                sm100::mbar_wait(accp_full, 0);
+                                sm100::tc_fence_after();
+                                if (etid == 0) dbg_stamp(p.dbg, 20);
+                              });
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) sm100::tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 31);
 }
 
 // ==========================================================================================

@@ -93,6 +93,27 @@ class PackedDiT:
         self.b_qkv = f32(torch.stack([get(f"blocks.{i}.attn.c_attn.bias", (3 * D,)) for i in range(L)]))
         self.w_proj = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.attn.c_proj.weight"), BLOCK_N) for i in range(L)]))
         self.b_proj = f32(torch.stack([get(f"blocks.{i}.attn.c_proj.bias", (D,)) for i in range(L)]))
+        # fused attention-block weight stream (csrc/dit_kernels.cuh: attn_block_kernel): per head pair hp the items
+        # Q_hp = [Wq | Wk | Wv rows 64hp..64hp+63] as four 192 x 64 slabs, P_hp = c_proj[:, 64hp..] as two 128 x 64 slabs
+        streams, biases = [], []
+        for i in range(L):
+            wqkv, wp = get(f"blocks.{i}.attn.c_attn.weight"), get(f"blocks.{i}.attn.c_proj.weight")
+            bq = get(f"blocks.{i}.attn.c_attn.bias", (3 * D,))
+            sel = lambda hp: torch.cat([torch.arange(part * D + 64 * hp, part * D + 64 * hp + 64) for part in range(3)])  # noqa: E731
+            q_items = [pack_kmajor_tiles(wqkv[sel(hp)], 192)[0].reshape(-1) for hp in range(4)]            # 4 x [4*192*64]
+            p_items = [pack_kmajor_tiles(wp[:, 64 * hp: 64 * hp + 64], 128)[:, 0].reshape(-1) for hp in range(4)]  # 4 x [2*128*64]
+            parts = []
+            for step in range(5):
+                if step < 4:
+                    parts.append(q_items[step])
+                if step >= 1:
+                    parts.append(p_items[step - 1])
+            streams.append(torch.cat(parts))
+            biases.append(torch.cat([bq[sel(hp)] for hp in range(4)]))
+        self.w_attn_stream = dev(torch.stack(streams))
+        assert self.w_attn_stream.shape[1] == 4 * D * D
+        self.b_qkv_hp = f32(torch.stack(biases))
+        self.use_fused_attn = os.environ.get("SCLDM_FUSED_ATTN", "1") != "0"
         self.mlp1_tiles = -(-H // 128)
         self.hid_slabs = -(-H // 64)
         mlp1 = []
@@ -142,6 +163,8 @@ class PackedDiT:
         s.n_layer, s.hidden, s.hid_slabs, s.mlp1_tiles = L, H, self.hid_slabs, self.mlp1_tiles
         s.mod_stride, s.n_class, s.eps = self.mod_stride, len(self.class_names), float(cfg.layernorm_eps)
         s.w_mlp_stream = self.w_mlp_stream.data_ptr() if self.use_fused_mlp else None
+        s.w_attn_stream = self.w_attn_stream.data_ptr() if self.use_fused_attn else None
+        s.b_qkv_hp = self.b_qkv_hp.data_ptr() if self.use_fused_attn else None
         s.wout_frag = self.wout_frag.data_ptr() if self.use_tc_final else None
         s.win_frag = self.win_frag.data_ptr() if self.use_tc_final else None
         for name in ("w_mod", "b_mod", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_mlp1", "w_mlp2", "temb_w0t", "temb_b0",

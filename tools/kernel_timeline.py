@@ -34,14 +34,31 @@ _lib.load().scldm_debug_timeline(None, -1)
 b = buf.cpu().view(4, -1, 32)
 n_cta = (3 * cells + 7) // 8
 names = ["qkv", "proj", "mlp1", "mlp2"]
+spans = {}
 for k, name in enumerate(names):
+    tt = b[k, :n_cta]
+    if (tt[:, 29] > 0).any():
+        spans[name] = (int(tt[:, 29].min()), int(tt[:, 30].max()))
+print("wall ns (last layer): ", {k: v[1] - v[0] for k, v in spans.items()})
+if "proj" in spans:
+    print(" qkv end -> proj start (attn + 2 gaps)", spans["proj"][0] - spans["qkv"][1], " proj end -> mlp start", spans["mlp1"][0] - spans["proj"][1])
+else:
+    print(" attn_block end -> mlp start", spans["mlp1"][0] - spans["qkv"][1])
+for k, name in enumerate(names):
+    if name not in spans:
+        continue
     t = b[k, :n_cta]
     t0 = t[:, 0:1]
     rel = (t - t0).float()
     rel[t == 0] = float("nan")
     med = rel.nanmedian(0).values
     print(name, "n_cta", n_cta, "median cycles since CTA start per stamp:")
-    print("   ", [(i, int(v)) for i, v in enumerate(med.tolist()) if v == v and i > 0])
+    print("   ", [(i, int(v)) for i, v in enumerate(med.tolist()) if v == v and i > 0 and not 28 <= i <= 30])
     start_spread = (t[:, 0] - t[:, 0].min()).float()
     end = (t[:, 31] - t[:, 0].min()).float()
-    print("    CTA start spread max", int(start_spread.max()), "kernel span (first start -> last end)", int(end.max()))
+    g0, g1 = t[:, 29], t[:, 30]
+    life = (g1 - g0).float()
+    print("    wall ns: kernel span (first CTA start -> last CTA end)", int(g1.max() - g0.min()), " CTA life median", int(life.median()),
+          "max", int(life.max()), " start spread: first-wave", int((g0.sort().values[min(147, n_cta - 1)] - g0.min())), "last", int(g0.max() - g0.min()))
+    sm = t[:, 28]
+    print("    CTAs per SM: max", int(torch.bincount(sm).max()), "SMs used", int((torch.bincount(sm) > 0).sum()))
