@@ -61,7 +61,9 @@ typedef struct scldm_dit_weights {
                                 swizzled slab [Wq rows 64hp.. | Wk rows 64hp.. | Wv rows 64hp..] for one 64-wide K slab, a
                                 "P item" the 128 x 64 slab c_proj.weight[128*half.., 64hp..64hp+64]; order Q_0 (4 items),
                                 Q_1, P_0 (2 items), Q_2, P_1, Q_3, P_2, P_3.  NULL selects the three unfused kernels          */
-  const float* b_qkv_hp;     /* [n_layer][4][192]: attn.c_attn.bias in the same q|k|v-per-head-pair order (with w_attn_stream) */
+  const float* b_proj_fused; /* [n_layer][256] = c_proj.bias + c_proj.weight @ c_attn.bias[512:768] (with w_attn_stream): the v bias
+                                passes through softmax-weighted averaging unchanged, the k bias cancels in the softmax, so the
+                                fused kernel adds only the q bias (b_qkv[:, 0:256]) before the attention                      */
   const float* temb_w0t; /* t_embedder.mlp.0.weight^T [256][256] */
   const float* temb_b0;
   const float* temb_w2t; /* t_embedder.mlp.2.weight^T [256][256] */

@@ -174,13 +174,13 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
   const size_t tile_elems = (size_t)dit::KSLABS_D * dit::B_SLAB_ELEMS;
   for (int l = 0; l < w->n_layer; ++l) {
     const int mo = l * 6 * dit::D;
-    if (w->w_attn_stream != nullptr && w->b_qkv_hp != nullptr) {  // fused attention half: LN1 + QKV + attention + c_proj + gated residual
+    if (w->w_attn_stream != nullptr && w->b_proj_fused != nullptr) {  // fused attention half: LN1 + QKV + attention + c_proj + gated residual
       dit::AttnBlockParams p{};
       p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
       p.mod_off_mul = mo + 0 * dit::D; p.mod_off_add = mo + 1 * dit::D; p.mod_off_gate = mo + 2 * dit::D; p.eps = w->eps;
       p.Wstream = static_cast<const dit::bf16*>(w->w_attn_stream) + (size_t)l * 4 * dit::D * dit::D;
-      p.bias_qkv = w->b_qkv_hp + (size_t)l * 3 * dit::D;
-      p.bias_proj = w->b_proj + (size_t)l * dit::D;
+      p.bias_q = w->b_qkv + (size_t)l * 3 * dit::D;
+      p.bias_proj = w->b_proj_fused + (size_t)l * dit::D;
       p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk : nullptr;
       LAUNCH("attn_block", dit::attn_block_kernel<<<row_tiles, dit::NUM_THREADS, dit::attn_block_smem_bytes(), st>>>(p));
     } else {

@@ -903,66 +903,83 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
   return y;
 }
 
-// softmax(Q K^T / sqrt(32)) V for one (slot, head) on one warp.  ld2(token, part, dim) returns the bf16 pair
-// (dim, dim+1) of q (part 0), k (1) or v (2) for that token and head; the result is the C fragment layout of
-// m16n8k16: o[nt] = rows (g, g+8) x dims (8 nt + 2t, +1).
-template <typename LD2>
-__device__ __forceinline__ void attn16_core(LD2&& ld2, uint32_t g, uint32_t t, float (&o)[4][4]) {
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// softmax(Q K^T / sqrt(32)) V for one (slot, head) on one warp.  chunk_addr(token, part, dim) returns the shared-memory
+// address (u32) of the 16-byte chunk holding dims [dim, dim+8) (dim a multiple of 8) of q (part 0), k (1) or v (2) for
+// that token and this head; all mma fragments come from six ldmatrix.x4 (V transposed on the fly).  The result is the
+// C fragment layout of m16n8k16: o[nt] = rows (g, g+8) x dims (8 nt + 2t, +1), g = lane / 4, t = lane % 4.
+template <typename ADDR>
+__device__ __forceinline__ void attn16_core(ADDR&& chunk_addr, uint32_t lane, float (&o)[4][4], long long* dbg = nullptr) {
+  const uint32_t l7 = lane & 7, m = lane >> 3;     // ldmatrix: this lane supplies row l7 of 8x8 matrix m
   // S = Q K^T : A = Q (16 tokens x 32 dims) in two k-steps; B[k=dim][n=key] = K[key][dim]
   float s[2][4] = {};
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
-    uint32_t a[4];
-    a[0] = ld2(g, 0, ks * 16 + 2 * t);
-    a[1] = ld2(g + 8, 0, ks * 16 + 2 * t);
-    a[2] = ld2(g, 0, ks * 16 + 2 * t + 8);
-    a[3] = ld2(g + 8, 0, ks * 16 + 2 * t + 8);
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const uint32_t b0 = ld2(nt * 8 + g, 1, ks * 16 + 2 * t);
-      const uint32_t b1 = ld2(nt * 8 + g, 1, ks * 16 + 2 * t + 8);
-      mma_bf16_16816(s[nt], a, b0, b1);
-    }
+    uint32_t a[4], kb[4];
+    ldmatrix_x4(a, chunk_addr(l7 + 8 * (m & 1), 0, ks * 16 + 8 * (m >> 1)));          // a0..a3
+    ldmatrix_x4(kb, chunk_addr((m >> 1) * 8 + l7, 1, ks * 16 + 8 * (m & 1)));         // (nt0: b0, b1), (nt1: b0, b1)
+    mma_bf16_16816(s[0], a, kb[0], kb[1]);
+    mma_bf16_16816(s[1], a, kb[2], kb[3]);
   }
+  if (dbg) dbg_stamp(dbg, 16);
   // softmax over the 16 keys of rows g (c0,c1) and g+8 (c2,c3); a row lives in the 4 lanes of a quad
   const float scale_log2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
   float m0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
   float m1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
   m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  const float ms0 = m0 * scale_log2, ms1 = m1 * scale_log2;
   float l0 = 0.f, l1 = 0.f;
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - m0) * scale_log2);
-    s[nt][1] = exp2f((s[nt][1] - m0) * scale_log2);
-    s[nt][2] = exp2f((s[nt][2] - m1) * scale_log2);
-    s[nt][3] = exp2f((s[nt][3] - m1) * scale_log2);
+    s[nt][0] = fast_exp2(fmaf(s[nt][0], scale_log2, -ms0));
+    s[nt][1] = fast_exp2(fmaf(s[nt][1], scale_log2, -ms0));
+    s[nt][2] = fast_exp2(fmaf(s[nt][2], scale_log2, -ms1));
+    s[nt][3] = fast_exp2(fmaf(s[nt][3], scale_log2, -ms1));
     l0 += s[nt][0] + s[nt][1];
     l1 += s[nt][2] + s[nt][3];
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float r0 = 1.0f / l0, r1 = 1.0f / l1;
+  const float r0 = fast_rcp(l0), r1 = fast_rcp(l1);
   // P (normalised, bf16) as the A operand of O = P V : C-fragment layout == A-fragment layout
   uint32_t pa[4];
   pa[0] = sm100::pack_bf16x2(s[0][0] * r0, s[0][1] * r0);
   pa[1] = sm100::pack_bf16x2(s[0][2] * r1, s[0][3] * r1);
   pa[2] = sm100::pack_bf16x2(s[1][0] * r0, s[1][1] * r0);
   pa[3] = sm100::pack_bf16x2(s[1][2] * r1, s[1][3] * r1);
-  // B[k=key][n=dim] = V[key][dim]: load V as 8x8 (token, dim-pair) tiles and transpose in registers
+  if (dbg) dbg_stamp(dbg, 17);
+  // B[k=key][n=dim] = V[key][dim]: 8x8 (key, dim) tiles loaded transposed
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+  for (int np = 0; np < 2; ++np) {
+    uint32_t vb[4];
+    ldmatrix_x4_trans(vb, chunk_addr((m & 1) * 8 + l7, 2, (np * 2 + (m >> 1)) * 8));   // (nt: keys 0-7, keys 8-15), (nt+1: ...)
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    const uint32_t v0 = ld2(g, 2, nt * 8 + 2 * t);      // tokens 0-7 , dims nt*8 + (2t, 2t+1)
-    const uint32_t v1 = ld2(g + 8, 2, nt * 8 + 2 * t);  // tokens 8-15
-    const uint32_t b0 = movmatrix_trans(v0);            // -> (keys 2t,2t+1 ; dim nt*8+g)
-    const uint32_t b1 = movmatrix_trans(v1);            // -> (keys 2t+8,.. ; dim nt*8+g)
-    mma_bf16_16816(o[nt], pa, b0, b1);
+    for (int j = 0; j < 2; ++j) {
+      float (&oo)[4] = o[np * 2 + j];
+      oo[0] = 0.f; oo[1] = 0.f; oo[2] = 0.f; oo[3] = 0.f;
+      mma_bf16_16816(oo, pa, vb[2 * j], vb[2 * j + 1]);
+    }
   }
 }
 
@@ -990,13 +1007,14 @@ __global__ void __launch_bounds__(256) attn16_kernel(const bf16* __restrict__ qk
   }
   __syncthreads();
   sm100::mbar_wait(&s_bar, 0);
-  auto ld2 = [&](int token, int part, int dim) -> uint32_t {
+  const uint32_t s_base = sm100::smem_u32(s_qkv);
+  auto chunk_addr = [&](uint32_t token, uint32_t part, uint32_t dim) -> uint32_t {
     const uint32_t col = part * D + head * HD + dim;
     // (rbase + token) & 7 == token & 7 because rbase is a multiple of 16
-    return *reinterpret_cast<const uint32_t*>(s_qkv + (col >> 6) * 2048 + sm100::swz_chunk_offset(token, (col & 63) >> 3) + (col & 7) * 2);
+    return s_base + (col >> 6) * 2048 + sm100::swz_chunk_offset(token, (col & 63) >> 3);
   };
   float o[4][4];
-  attn16_core(ld2, g, t, o);
+  attn16_core(chunk_addr, lane, o);
   // O rows (g, g+8) x dims (nt*8 + 2t, +1): assemble the slot's 16 x 256 output as 4 swizzled 2 KB slab segments in
   // shared memory (reusing the q slabs, which every warp has finished reading after the barrier) and bulk-store them
   __syncthreads();
@@ -1044,28 +1062,34 @@ struct AttnBlockParams {
   int mod_off_mul, mod_off_add, mod_off_gate;
   float eps;
   const bf16* Wstream;    // one layer of the attention weight stream (512 KB)
-  const float* bias_qkv;  // [4 head pairs][192] in accumulator column order (q | k | v of the pair)
-  const float* bias_proj; // [256]
+  const float* bias_q;    // [256] c_attn.bias[0:256].  The k bias cancels in the softmax (a per-query constant shift of the
+                          // scores) and the v bias passes through the attention (rows of P sum to 1), so it is folded into
+  const float* bias_proj; // [256] = c_proj.bias + c_proj.weight @ c_attn.bias[512:768]   (pack.py: b_proj_fused)
   long long* dbg;
 };
 
 constexpr int AB_HP = 4;                        // head pairs
 constexpr int AB_QN = 192;                      // accumulator columns per head pair: q | k | v, 64 each
-constexpr uint32_t AB_NSTAGE = 3;
+#ifndef DBG_HP
+#define DBG_HP 0
+#endif
+constexpr uint32_t AB_NSTAGE = 4;
 constexpr int AB_STAGE_BYTES = AB_QN * BLOCK_K * 2;     // 24 KB
 constexpr int AB_Q_ITEM_BYTES = AB_QN * BLOCK_K * 2;    // 24 KB
 constexpr int AB_P_ITEM_BYTES = 128 * BLOCK_K * 2;      // 16 KB
 constexpr int AB_OFF_QKV = KSLABS_D * A_SLAB_BYTES;               // 64 KB
 constexpr int AB_OFF_AO = AB_OFF_QKV + 3 * A_SLAB_BYTES;          // +48 KB
 constexpr int AB_OFF_W = AB_OFF_AO + A_SLAB_BYTES;                // +16 KB = 128 KB
-constexpr int AB_OFF_GATE = AB_OFF_W + AB_NSTAGE * AB_STAGE_BYTES;
-constexpr int AB_OFF_BIASP = AB_OFF_GATE + 8 * D * 4;
-constexpr int AB_OFF_BIASQ = AB_OFF_BIASP + D * 4;
-constexpr int AB_OFF_BARS = AB_OFF_BIASQ + AB_HP * AB_QN * 4;
+constexpr int AB_OFF_BIASQ = AB_OFF_W + AB_NSTAGE * AB_STAGE_BYTES;   // 224 KB
+constexpr int AB_OFF_BARS = AB_OFF_BIASQ + D * 4;
 constexpr size_t attn_block_smem_bytes() { return AB_OFF_BARS + 256; }
+static_assert(attn_block_smem_bytes() <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 static_assert(2 * XPASS_BYTES <= 4 * A_SLAB_BYTES, "X passes 0,1 alias the q/k/v + AO staging");
-static_assert(2 * XPASS_BYTES <= AB_NSTAGE * AB_STAGE_BYTES, "X passes 2,3 alias the weight ring");
+static_assert(2 * XPASS_BYTES <= (AB_NSTAGE - 1) * AB_STAGE_BYTES, "X passes 2,3 alias ring buffers 0-2; buffer 3 is free from the start");
 static_assert(RESID_STG_BYTES <= 3 * A_SLAB_BYTES, "residual staging aliases the q/k/v slabs");
+static_assert(9 * D * 4 <= AB_STAGE_BYTES, "gate vectors + c_proj bias are parked in the (then idle) weight ring");
+// logical ring stage -> physical buffer: the first item lands in buffer 3, which carries no X pass
+__device__ __forceinline__ uint32_t ab_ring_buf(uint32_t stage) { return (stage + 3u) & 3u; }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBlockParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1075,21 +1099,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
   uint8_t* smQKV = smem + AB_OFF_QKV;     // q | k | v slabs of the current head pair; first X passes 0,1
   uint8_t* smAO = smem + AB_OFF_AO;
   uint8_t* smW = smem + AB_OFF_W;         // weight ring; first X passes 2,3
-  float* smGate = reinterpret_cast<float*>(smem + AB_OFF_GATE);
-  float* smBiasP = reinterpret_cast<float*>(smem + AB_OFF_BIASP);
+  float* smGate = reinterpret_cast<float*>(smW);   // parked here once every weight item has been consumed
+  float* smBiasP = smGate + 8 * D;
   float* smBiasQ = reinterpret_cast<float*>(smem + AB_OFF_BIASQ);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_OFF_BARS);
-  uint64_t* full = bars;                  // [3]
-  uint64_t* empty = bars + 3;             // [3]
-  uint64_t* a_ready = bars + 6;
-  uint64_t* accq_full = bars + 7;
-  uint64_t* accq_free = bars + 8;
-  uint64_t* ao_ready = bars + 9;
-  uint64_t* ao_free = bars + 10;
-  uint64_t* accp_full = bars + 11;
-  uint64_t* x_full = bars + 12;           // [4]
-  uint64_t* x_empty = bars + 16;          // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* full = bars;                  // [4]
+  uint64_t* empty = bars + 4;             // [4]
+  uint64_t* a_ready = bars + 8;
+  uint64_t* accq_full = bars + 9;
+  uint64_t* accq_free = bars + 10;
+  uint64_t* ao_ready = bars + 11;
+  uint64_t* ao_free = bars + 12;
+  uint64_t* accp_full = bars + 13;
+  uint64_t* x_full = bars + 14;           // [4]
+  uint64_t* x_empty = bars + 18;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_tile = blockIdx.x;
@@ -1106,6 +1130,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
     for (int i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], XPASS_WARPS);
     sm100::fence_barrier_init();
     producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
+    // weight item 0 goes out with them, into the ring buffer that carries no X pass
+    sm100::mbar_arrive_expect_tx(&full[0], AB_Q_ITEM_BYTES);
+    sm100::bulk_g2s(smW + ab_ring_buf(0) * AB_STAGE_BYTES, p.Wstream, AB_Q_ITEM_BYTES, &full[0]);
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
   sm100::tc_fence_before();
@@ -1116,15 +1143,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
   if (warp == 0) {
     // ===================== producer: one linear stream of weight items ======================
     if (lane == 0) {
-      sm100::mbar_wait(&x_empty[0], 0);   // the ring carried X passes 2 and 3
-      sm100::mbar_wait(&x_empty[1], 0);
       RingState rs;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wstream);
+      int item = 0;
       auto issue = [&](uint32_t bytes) {
-        sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
-        sm100::mbar_arrive_expect_tx(&full[rs.stage], bytes);
-        sm100::bulk_g2s(smW + rs.stage * AB_STAGE_BYTES, src, bytes, &full[rs.stage]);
+        if (item == 1) {                      // buffers 0-2 carried X passes 2 and 3
+          sm100::mbar_wait(&x_empty[0], 0);
+          sm100::mbar_wait(&x_empty[1], 0);
+        }
+        if (item > 0) {                       // item 0 was issued during setup
+          sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+          sm100::mbar_arrive_expect_tx(&full[rs.stage], bytes);
+          sm100::bulk_g2s(smW + ab_ring_buf(rs.stage) * AB_STAGE_BYTES, src, bytes, &full[rs.stage]);
+        }
         src += bytes;
+        ++item;
         rs.advance(AB_NSTAGE);
       };
       for (int step = 0; step <= AB_HP; ++step) {
@@ -1151,7 +1184,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
           for (int ks = 0; ks < KSLABS_D; ++ks) {
             sm100::mbar_wait(&full[rs.stage], rs.phase);
             sm100::tc_fence_after();
-            issue_slab_mmas(accq, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smW + rs.stage * AB_STAGE_BYTES), idesc_q, ks == 0);
+            issue_slab_mmas(accq, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smW + ab_ring_buf(rs.stage) * AB_STAGE_BYTES), idesc_q, ks == 0);
             sm100::umma_commit(&empty[rs.stage]);
             rs.advance(AB_NSTAGE);
           }
@@ -1164,7 +1197,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
           for (int half = 0; half < 2; ++half) {
             sm100::mbar_wait(&full[rs.stage], rs.phase);
             sm100::tc_fence_after();
-            issue_slab_mmas(accp + half * 128, sm100::smem_u32(smAO), sm100::smem_u32(smW + rs.stage * AB_STAGE_BYTES), idesc_p, hp == 0);
+            issue_slab_mmas(accp + half * 128, sm100::smem_u32(smAO), sm100::smem_u32(smW + ab_ring_buf(rs.stage) * AB_STAGE_BYTES), idesc_p, hp == 0);
             sm100::umma_commit(&empty[rs.stage]);
             rs.advance(AB_NSTAGE);
           }
@@ -1177,24 +1210,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
     // ===================== 16 worker warps ==================================================
     const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
-    // gate / bias vectors: issue the global loads now, park them in shared memory after the prologue
-    const int gcell = etid >> 6, gc4 = etid & 63;
-    const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod.row(row_tile * 8 + gcell) * p.mod_stride + p.mod_off_gate + gc4 * 4);
-    float4 bias_v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (etid < 64) bias_v = *reinterpret_cast<const float4*>(p.bias_proj + etid * 4);
-    else if (etid < 64 + AB_HP * AB_QN / 4) bias_v = *reinterpret_cast<const float4*>(p.bias_qkv + (etid - 64) * 4);
     ln_prologue_tma(smQKV, smW, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg);
     sm100::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) sm100::mbar_arrive(a_ready);
-    reinterpret_cast<float4*>(smGate)[etid] = gate_v;
-    if (etid < 64) reinterpret_cast<float4*>(smBiasP)[etid] = bias_v;
-    else if (etid < 64 + AB_HP * AB_QN / 4) reinterpret_cast<float4*>(smBiasQ)[etid - 64] = bias_v;
+    // gate / bias vectors: needed by the final epilogue only; the loads are issued now and parked in shared memory then
+    const int gcell = etid >> 6, gc4 = etid & 63;
+    const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod.row(row_tile * 8 + gcell) * p.mod_stride + p.mod_off_gate + gc4 * 4);
+    float4 bias_v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (etid < 64) bias_v = *reinterpret_cast<const float4*>(p.bias_proj + etid * 4);
+    else if (etid < 128) reinterpret_cast<float4*>(smBiasQ)[etid - 64] = *reinterpret_cast<const float4*>(p.bias_q + (etid - 64) * 4);
     if (etid == 0) dbg_stamp(p.dbg, 3);
 
     const uint32_t taddr_q = tmem_base + ((q * 32u) << 16);
     const uint32_t slot = ew >> 1, h = ew & 1;        // this warp's attention job within a head pair
     const uint32_t g = lane >> 2, t = lane & 3;
+    const uint32_t qkv_base = sm100::smem_u32(smQKV);
     for (int hp = 0; hp < AB_HP; ++hp) {
       sm100::mbar_wait(accq_full, hp & 1);
       sm100::tc_fence_after();
@@ -1206,12 +1237,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
       sm100::tc_fence_before();
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(accq_free);          // Q_{hp+1} may overwrite the accumulator
-      sm100::named_bar_sync(1, EPI_THREADS);                 // every warp is done reading the previous pair's q/k/v (and, hp = 0, biases staged)
+      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 21);
+      sm100::named_bar_sync(1, EPI_THREADS);
+      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 27);                 // every warp is done reading the previous pair's q/k/v (and, hp = 0, biases staged)
 #pragma unroll
       for (int c8 = 0; c8 < 6; ++c8) {
         const uint32_t gcol = sub * 48 + c8 * 8;             // accumulator column: [0,64) q, [64,128) k, [128,192) v
-        const float4 b0 = *reinterpret_cast<const float4*>(smBiasQ + hp * AB_QN + gcol);
-        const float4 b1 = *reinterpret_cast<const float4*>(smBiasQ + hp * AB_QN + gcol + 4);
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (gcol < 64) {                                      // q columns carry a bias (see AttnBlockParams)
+          b0 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + gcol);
+          b1 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + gcol + 4);
+        }
         const uint32_t* vv = c8 < 4 ? &v0[c8 * 8] : &v1[(c8 - 4) * 8];
         uint4 o;
         o.x = sm100::pack_bf16x2(__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y);
@@ -1222,13 +1258,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
       }
       sm100::named_bar_sync(1, EPI_THREADS);                 // q/k/v of this head pair staged
       if (etid == 0) dbg_stamp(p.dbg, 5 + 3 * hp);
-      auto ld2 = [&](int token, int part, int dim) -> uint32_t {
-        const uint32_t col = h * HD + dim;
-        return *reinterpret_cast<const uint32_t*>(smQKV + part * A_SLAB_BYTES + sm100::swz_chunk_offset(slot * TOK + token, col >> 3) + (col & 7) * 2);
+      auto chunk_addr = [&](uint32_t token, uint32_t part, uint32_t dim) -> uint32_t {
+        return qkv_base + part * A_SLAB_BYTES + sm100::swz_chunk_offset(slot * TOK + token, (h * HD + dim) >> 3);
       };
       float o[4][4];
-      attn16_core(ld2, g, t, o);
+      attn16_core(chunk_addr, lane, o, (etid == 0 && hp == DBG_HP) ? p.dbg : nullptr);
+      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 18);
       if (hp > 0) sm100::mbar_wait(ao_free, (hp - 1) & 1);   // P_{hp-1} finished reading the AO slab
+      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 19);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const uint32_t col = h * HD + nt * 8 + 2 * t;
@@ -1248,6 +1285,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
                                 sm100::mbar_wait(accp_full, 0);
                                 sm100::tc_fence_after();
                                 if (etid == 0) dbg_stamp(p.dbg, 20);
+                                reinterpret_cast<float4*>(smGate)[etid] = gate_v;   // every MMA has retired: the ring is idle
+                                if (etid < 64) reinterpret_cast<float4*>(smBiasP)[etid] = bias_v;
+                                sm100::named_bar_sync(1, EPI_THREADS);
                               });
   }
   sm100::tc_fence_before();

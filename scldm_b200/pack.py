@@ -109,10 +109,11 @@ class PackedDiT:
                 if step >= 1:
                     parts.append(p_items[step - 1])
             streams.append(torch.cat(parts))
-            biases.append(torch.cat([bq[sel(hp)] for hp in range(4)]))
+            # v bias: rows of softmax(.) sum to 1, so attention(q, k, v + b_v) = attention(q, k, v) + b_v -> into the c_proj bias
+            biases.append(get(f"blocks.{i}.attn.c_proj.bias", (D,)).double() + wp.double() @ bq[2 * D:].double())
         self.w_attn_stream = dev(torch.stack(streams))
         assert self.w_attn_stream.shape[1] == 4 * D * D
-        self.b_qkv_hp = f32(torch.stack(biases))
+        self.b_proj_fused = f32(torch.stack(biases).float())
         self.use_fused_attn = os.environ.get("SCLDM_FUSED_ATTN", "1") != "0"
         self.mlp1_tiles = -(-H // 128)
         self.hid_slabs = -(-H // 64)
@@ -164,7 +165,7 @@ class PackedDiT:
         s.mod_stride, s.n_class, s.eps = self.mod_stride, len(self.class_names), float(cfg.layernorm_eps)
         s.w_mlp_stream = self.w_mlp_stream.data_ptr() if self.use_fused_mlp else None
         s.w_attn_stream = self.w_attn_stream.data_ptr() if self.use_fused_attn else None
-        s.b_qkv_hp = self.b_qkv_hp.data_ptr() if self.use_fused_attn else None
+        s.b_proj_fused = self.b_proj_fused.data_ptr() if self.use_fused_attn else None
         s.wout_frag = self.wout_frag.data_ptr() if self.use_tc_final else None
         s.win_frag = self.win_frag.data_ptr() if self.use_tc_final else None
         for name in ("w_mod", "b_mod", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_mlp1", "w_mlp2", "temb_w0t", "temb_b0",

@@ -1,10 +1,9 @@
 timeout 900 python -m pytest tests/test_gpu_dit.py -m gpu -q -x --timeout=240 -p no:cacheprovider 2>&1 | tail -3
-SCLDM_FUSED_ATTN=0 timeout 900 python -m pytest tests/test_gpu_dit.py -m gpu -q -x --timeout=240 -p no:cacheprovider -k "intermediates or golden" 2>&1 | tail -2
-python tools/kernel_timeline.py 784 2>&1 | grep -v "^\[\]" | head -14
-python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_v11.json 2>> gpurun_out/sweep.err
+python tools/kernel_timeline.py 784 2>&1 | grep -A3 "^qkv"
+python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_v12.json 2>> gpurun_out/sweep.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_v11.json"))
+d=json.load(open("gpurun_out/bench_v12.json"))
 print("value", round(d["value"]), "model_tflops", d["model_tflops"], "roof", d["roofline"]["kernel"], d["roofline"]["frac"], d["roofline"]["avg_launch_us"])
 print("   ", {k:(v["share"], round(v["ms"]/v["launches"]*1000,1)) for k,v in list(d["kernel_breakdown"].items())[:10]})
 PY
