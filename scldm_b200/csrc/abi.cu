@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <cstring>
 #include <map>
 #include <string>
@@ -37,6 +39,7 @@ struct ProfRec { const char* name; cudaEvent_t a, b; };
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_prof_pool;
 bool g_prof_on = false;
+const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
 cudaStream_t g_prof_stream = nullptr;
 
 cudaEvent_t prof_event() {
@@ -65,6 +68,20 @@ inline void prof_end() {
     cudaError_t _e = cudaPeekAtLastError();                                                    \
     if (_e != cudaSuccess) return fail(SCLDM_ECUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
+
+// Launch with programmatic stream serialization: the kernel's CTAs may become resident (barrier init, TMEM allocation,
+// first weight loads) while the preceding kernel drains; the kernel itself orders its dependent accesses with
+// griddepcontrol.wait.  Plain launch while per-kernel event timing is on.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (g_prof_on || !g_use_pdl) ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -153,7 +170,7 @@ int launch_mod(const scldm_dit_weights* w, const scldm_dit_plan* plan, const Dit
   p.out_f32 = ws.mod;
   p.out_ld = w->mod_stride;
   dim3 grid(row_tiles, ceil_div(p.n_tiles_total, p.tiles_per_cta));
-  LAUNCH("gemm_ares<COND,MOD>", dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD><<<grid, dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
+  LAUNCH("gemm_ares<COND,MOD>", launch_pdl(dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD>, grid, dim3(dit::NUM_THREADS), dit::ares_smem_bytes(), st, p));
   return SCLDM_OK;
 }
 
@@ -182,7 +199,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.bias_q = w->b_qkv + (size_t)l * 3 * dit::D;
       p.bias_proj = w->b_proj_fused + (size_t)l * dit::D;
       p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk : nullptr;
-      LAUNCH("attn_block", dit::attn_block_kernel<<<row_tiles, dit::NUM_THREADS, dit::attn_block_smem_bytes(), st>>>(p));
+      LAUNCH("attn_block", launch_pdl(dit::attn_block_kernel, dim3(row_tiles), dim3(dit::NUM_THREADS), dit::attn_block_smem_bytes(), st, p));
     } else {
     {  // LN1 + modulate + QKV
       dit::AResParams p{};
@@ -213,7 +230,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
       p.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream) + (size_t)l * n_stream * dit::B_SLAB_ELEMS;
       p.n_chunks = w->mlp1_tiles; p.hid_slabs = w->hid_slabs;
       p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 2 * (1 << 17) : nullptr;
-      LAUNCH("mlp_fused", dit::mlp_fused_kernel<<<row_tiles, dit::NUM_THREADS, dit::mlp_fused_smem_bytes(), st>>>(p));
+      LAUNCH("mlp_fused", launch_pdl(dit::mlp_fused_kernel, dim3(row_tiles), dim3(dit::NUM_THREADS), dit::mlp_fused_smem_bytes(), st, p));
       continue;
     }
     {  // LN2 + modulate + [w1|w2] + SwiGLU
@@ -241,7 +258,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
 int launch_final(const scldm_dit_weights* w, const dit::StepParams& s, int n_states, cudaStream_t st) {
   if (w->wout_frag != nullptr && w->win_frag != nullptr) {
     dit::StepTcWeights tw{static_cast<const uint2*>(w->wout_frag), static_cast<const uint2*>(w->win_frag)};
-    LAUNCH("final_step_tc", dit::final_step_tc_kernel<<<ceil_div(n_states, 4), 128, 0, st>>>(s, tw, n_states));
+    LAUNCH("final_step_tc", launch_pdl(dit::final_step_tc_kernel, dim3(ceil_div(n_states, 4)), dim3(128), 0, st, s, tw, n_states));
   } else {
     LAUNCH("final_step", dit::final_step_kernel<<<n_states < 296 ? n_states : 296, 512, 0, st>>>(s, n_states));
   }

@@ -281,14 +281,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
     for (uint32_t i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
     for (uint32_t i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], XPASS_WARPS);
     sm100::fence_barrier_init();
-    // first loads go out before the setup barrier: the X tile (all four passes) and the first weight slab(s)
-    if constexpr (PRO == PRO_LN) producer_issue_x_passes(p.X, row_tile, smStg, smB, x_full);
+    // first loads go out before the setup barrier: the first weight slab(s), then (once the preceding kernel's output is
+    // visible) the X tile (all four passes)
     for (int i = 0; i < EARLY; ++i) {
       sm100::mbar_arrive_expect_tx(&full[i], B_SLAB_BYTES);
       sm100::bulk_g2s(smB + ring_buf(i) * B_SLAB_BYTES, p.Wp + ((size_t)tile0 * KSLABS_D + i) * B_SLAB_ELEMS, B_SLAB_BYTES, &full[i]);
     }
+    sm100::grid_dep_wait();
+    if constexpr (PRO == PRO_LN) producer_issue_x_passes(p.X, row_tile, smStg, smB, x_full);
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  sm100::grid_dep_launch();
+  sm100::grid_dep_wait();
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
@@ -751,12 +755,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     for (int i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
     sm100::mbar_init(acc2_full, 1);
     sm100::fence_barrier_init();
-    // first loads go out before the setup barrier: all four X passes (H buffers + two idle ring buffers) and weight slab 0
-    producer_issue_x_passes(p.X, row_tile, smH, smB, x_full);
+    // first loads go out before the setup barrier: weight slab 0, then (once the preceding kernel's X is visible) all
+    // four X passes (H buffers + two idle ring buffers)
     sm100::mbar_arrive_expect_tx(&full[0], B_SLAB_BYTES);
     sm100::bulk_g2s(smB + ring_buf(0) * B_SLAB_BYTES, p.Wstream, B_SLAB_BYTES, &full[0]);
+    sm100::grid_dep_wait();
+    producer_issue_x_passes(p.X, row_tile, smH, smB, x_full);
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
+  sm100::grid_dep_launch();
+  sm100::grid_dep_wait();
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
@@ -925,7 +933,7 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // that token and this head; all mma fragments come from six ldmatrix.x4 (V transposed on the fly).  The result is the
 // C fragment layout of m16n8k16: o[nt] = rows (g, g+8) x dims (8 nt + 2t, +1), g = lane / 4, t = lane % 4.
 template <typename ADDR>
-__device__ __forceinline__ void attn16_core(ADDR&& chunk_addr, uint32_t lane, float (&o)[4][4], long long* dbg = nullptr) {
+__device__ __forceinline__ void attn16_core(ADDR&& chunk_addr, uint32_t lane, float (&o)[4][4]) {
   const uint32_t l7 = lane & 7, m = lane >> 3;     // ldmatrix: this lane supplies row l7 of 8x8 matrix m
   // S = Q K^T : A = Q (16 tokens x 32 dims) in two k-steps; B[k=dim][n=key] = K[key][dim]
   float s[2][4] = {};
@@ -937,7 +945,6 @@ __device__ __forceinline__ void attn16_core(ADDR&& chunk_addr, uint32_t lane, fl
     mma_bf16_16816(s[0], a, kb[0], kb[1]);
     mma_bf16_16816(s[1], a, kb[2], kb[3]);
   }
-  if (dbg) dbg_stamp(dbg, 16);
   // softmax over the 16 keys of rows g (c0,c1) and g+8 (c2,c3); a row lives in the 4 lanes of a quad
   const float scale_log2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
   float m0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
@@ -968,7 +975,6 @@ __device__ __forceinline__ void attn16_core(ADDR&& chunk_addr, uint32_t lane, fl
   pa[1] = sm100::pack_bf16x2(s[0][2] * r1, s[0][3] * r1);
   pa[2] = sm100::pack_bf16x2(s[1][0] * r0, s[1][1] * r0);
   pa[3] = sm100::pack_bf16x2(s[1][2] * r1, s[1][3] * r1);
-  if (dbg) dbg_stamp(dbg, 17);
   // B[k=key][n=dim] = V[key][dim]: 8x8 (key, dim) tiles loaded transposed
 #pragma unroll
   for (int np = 0; np < 2; ++np) {
@@ -1070,9 +1076,6 @@ struct AttnBlockParams {
 
 constexpr int AB_HP = 4;                        // head pairs
 constexpr int AB_QN = 192;                      // accumulator columns per head pair: q | k | v, 64 each
-#ifndef DBG_HP
-#define DBG_HP 0
-#endif
 constexpr uint32_t AB_NSTAGE = 4;
 constexpr int AB_STAGE_BYTES = AB_QN * BLOCK_K * 2;     // 24 KB
 constexpr int AB_Q_ITEM_BYTES = AB_QN * BLOCK_K * 2;    // 24 KB
@@ -1129,12 +1132,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
     for (int i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
     for (int i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], XPASS_WARPS);
     sm100::fence_barrier_init();
-    producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
-    // weight item 0 goes out with them, into the ring buffer that carries no X pass
+    // weight item 0 (independent of the previous kernel) goes into the ring buffer that carries no X pass
     sm100::mbar_arrive_expect_tx(&full[0], AB_Q_ITEM_BYTES);
     sm100::bulk_g2s(smW + ab_ring_buf(0) * AB_STAGE_BYTES, p.Wstream, AB_Q_ITEM_BYTES, &full[0]);
+    sm100::grid_dep_wait();                 // X and the modulation table come from the preceding kernels
+    producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
+  sm100::grid_dep_launch();
+  sm100::grid_dep_wait();
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
@@ -1237,9 +1243,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
       sm100::tc_fence_before();
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(accq_free);          // Q_{hp+1} may overwrite the accumulator
-      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 21);
       sm100::named_bar_sync(1, EPI_THREADS);
-      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 27);                 // every warp is done reading the previous pair's q/k/v (and, hp = 0, biases staged)
 #pragma unroll
       for (int c8 = 0; c8 < 6; ++c8) {
         const uint32_t gcol = sub * 48 + c8 * 8;             // accumulator column: [0,64) q, [64,128) k, [128,192) v
@@ -1262,10 +1266,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
         return qkv_base + part * A_SLAB_BYTES + sm100::swz_chunk_offset(slot * TOK + token, (h * HD + dim) >> 3);
       };
       float o[4][4];
-      attn16_core(chunk_addr, lane, o, (etid == 0 && hp == DBG_HP) ? p.dbg : nullptr);
-      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 18);
+      attn16_core(chunk_addr, lane, o);
       if (hp > 0) sm100::mbar_wait(ao_free, (hp - 1) & 1);   // P_{hp-1} finished reading the AO slab
-      if (etid == 0 && hp == DBG_HP) dbg_stamp(p.dbg, 19);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const uint32_t col = h * HD + nt * 8 + 2 * t;
@@ -1522,6 +1524,8 @@ __device__ __forceinline__ void mma_bf16_f(float (&c)[4], uint32_t a0, uint32_t 
 }
 
 __global__ void __launch_bounds__(128) final_step_tc_kernel(const StepParams p, const StepTcWeights w, int n_states) {
+  sm100::grid_dep_launch();
+  sm100::grid_dep_wait();   // programmatic dependent launch: X comes from the last MLP kernel
   __shared__ uint2 s_wout[32 * 32];     // 8 KB
   __shared__ uint2 s_win[32 * 32];      // 8 KB
   __shared__ float s_posb[TOK * D];     // 16 KB: pos_embed + input_proj.bias

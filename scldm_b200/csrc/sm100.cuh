@@ -79,6 +79,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch: `grid_dep_launch` lets the next kernel in the stream start its CTAs (and run whatever
+// does not depend on this grid's output) as soon as every CTA of this grid has issued it; `grid_dep_wait` blocks until
+// the preceding grid has completed and its global writes are visible.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -91,6 +91,7 @@ class DiT(nn.Module):
                                 dropout=dropout, bias=bias, norm_layer=norm_layer, multiple_of=multiple_of,
                                 layernorm_eps=layernorm_eps, class_vocab_sizes=dict(class_vocab_sizes),
                                 cfg_dropout_prob=cfg_dropout_prob, condition_strategy=condition_strategy)
+        self.dedup_conditions = True   # ODE path: one adaLN row per distinct label combination instead of one per cell
         self._packed: PackedDiT | None = None
         self._packed_key = None
         self.initialize_weights()
@@ -189,7 +190,18 @@ class DiT(nn.Module):
         n_f = 1 + len(passes)
         null_rows = lambda n: self._cls_rows({}, n, device)  # noqa: E731
         ar = torch.arange(half, dtype=torch.int32, device=device)
-        if shared_time:
+        slot_mode = "identity"
+        if shared_time and self.dedup_conditions and passes:
+            # all rows share t, so the adaLN vectors depend on the label combination only: row 0 = unconditional, then
+            # one row per distinct combination (14 for the dentate clusters instead of one per cell and pass)
+            cols = torch.cat([self._cls_rows(p, half, device) for p in passes], 1)       # [n_class, n_c*half], pass-major
+            uniq, inv = torch.unique(cols, dim=1, return_inverse=True)
+            cls_idx = torch.cat([null_rows(1), uniq.to(torch.int32)], 1)
+            slot_u = torch.zeros(half, dtype=torch.int32, device=device)
+            slot_g = torch.zeros(half, n_f, dtype=torch.int32, device=device)
+            slot_g[:, 1:] = 1 + inv.view(len(passes), half).T.to(torch.int32)
+            t_index, slot_mode = None, "table"
+        elif shared_time:
             # row 0 = unconditional; row 1 + j*n_c + k = guided cell j, conditional pass k
             n_c = len(passes)
             cls = [null_rows(1)] + ([torch.stack([self._cls_rows(p, half, device) for p in passes], 2).reshape(-1, half * n_c)] if n_c else [])
@@ -198,7 +210,7 @@ class DiT(nn.Module):
             slot_g = torch.zeros(half, n_f, dtype=torch.int32, device=device)
             for k in range(n_c):
                 slot_g[:, 1 + k] = 1 + ar * n_c + k
-            t_index = None
+            t_index, slot_mode = None, "cfg_shared"
         else:
             # rows [0,half): unconditional first half; then per guided cell j: n_f rows (uncond, cond passes)
             per = [null_rows(half)] + [self._cls_rows(p, half, device) for p in passes]  # each [n_class, half]
@@ -208,8 +220,7 @@ class DiT(nn.Module):
             slot_g = half + ar[:, None] * n_f + torch.arange(n_f, dtype=torch.int32, device=device)[None, :]
             t_index = torch.cat([ar, (half + ar).repeat_interleave(n_f)]).long()
         slot_mod = torch.cat([slot_u, slot_g.reshape(-1)])
-        return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index,
-                    slot_mode="cfg_shared" if shared_time else "identity")
+        return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index, slot_mode=slot_mode)
 
     def cfg_plan(self, condition, cfg_scale, half: int, device, shared_time: bool):
         lay = self.cfg_layout(condition, cfg_scale, half, device, shared_time)

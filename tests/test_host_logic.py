@@ -188,6 +188,26 @@ def test_slot_mode_closed_forms_match_tables(name):
         assert int(lay["slot_mod"].max()) + 1 == lay["cls_idx"].shape[1]
 
 
+@pytest.mark.parametrize("name", list(golden_cases().keys()))
+def test_deduplicated_conditioning_rows_are_equivalent(name):
+    """shared-time plans keep one adaLN row per distinct label combination: every slot must still see its own labels."""
+    from scldm_b200.nnets import DiT
+
+    case = golden_cases()[name]
+    cfg, B = case["cfg"], case["B"]
+    _, _, labels = dit_inputs(name, cfg, B)
+    m = DiT(**cfg.kwargs())
+    lay_d = m.cfg_layout(labels, case["scales"], B, "cpu", True)
+    m.dedup_conditions = False
+    lay_f = m.cfg_layout(labels, case["scales"], B, "cpu", True)
+    assert lay_d["slot_mode"] == "table" and lay_f["slot_mode"] == "cfg_shared"
+    per_slot_d = lay_d["cls_idx"][:, lay_d["slot_mod"].long()]
+    per_slot_f = lay_f["cls_idx"][:, lay_f["slot_mod"].long()]
+    assert torch.equal(per_slot_d, per_slot_f)
+    assert lay_d["cls_idx"].shape[1] <= lay_f["cls_idx"].shape[1]
+    assert torch.unique(lay_d["cls_idx"][:, 1:], dim=1).shape[1] == lay_d["cls_idx"].shape[1] - 1
+
+
 def test_abi_library_loads_and_exports_declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "scldm_b200.h")).read()
     declared = set(re.findall(r"\b(scldm_[a-z_0-9]+)\s*\(", hdr))
