@@ -128,6 +128,7 @@ def kernel_flops(name: str, rows: int, mod_rows: int) -> float | None:
         "attn16": 4.0 * rows * 16 * D,
         "mlp_fused": 2.0 * rows * D * 2 * H + 2.0 * rows * H * D,
         "attn_block": 2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D,
+        "dit_blocks": 8 * (2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D + 2.0 * rows * D * 2 * H + 2.0 * rows * H * D),
     }.get(name)
 
 
@@ -191,7 +192,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=2352, help="cells per step per GPU (2x rows are generated)")
+    ap.add_argument("--batch", type=int, default=2368, help="cells per step per GPU (2x rows are generated)")
     ap.add_argument("--chunk", type=int, default=0, help="cells per ODE chunk (0 = library default)")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--cpu-batch", type=int, default=8)

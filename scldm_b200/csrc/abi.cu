@@ -39,6 +39,9 @@ struct ProfRec { const char* name; cudaEvent_t a, b; };
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_prof_pool;
 bool g_prof_on = false;
+const bool g_use_mega = []{ const char* e = getenv("SCLDM_MEGA"); return !(e && e[0] == '0'); }();  // SCLDM_MEGA=0: one kernel per block half
+int g_num_sms = 148;
+const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? atoi(e) : 4500; }();   // start offset step of the persistent CTAs (cycles)
 const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
 cudaStream_t g_prof_stream = nullptr;
 
@@ -189,6 +192,25 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
   const int slots_pad = scldm_dit_slots_pad(plan);
   const int row_tiles = slots_pad * dit::TOK / dit::BLOCK_M;
   const size_t tile_elems = (size_t)dit::KSLABS_D * dit::B_SLAB_ELEMS;
+  if (g_use_mega && w->w_attn_stream != nullptr && w->b_proj_fused != nullptr && w->w_mlp_stream != nullptr) {
+    // the whole block stack as one persistent kernel (one CTA per SM, tiles walk through all layers without grid syncs)
+    dit::BlocksParams bp{};
+    dit::AttnBlockParams& a = bp.attn;
+    a.X = ws.X; a.mod = ws.mod; a.slot_mod = mod_index(plan); a.mod_stride = w->mod_stride;
+    a.mod_off_mul = 0; a.mod_off_add = dit::D; a.mod_off_gate = 2 * dit::D; a.eps = w->eps;
+    a.Wstream = static_cast<const dit::bf16*>(w->w_attn_stream); a.bias_q = w->b_qkv; a.bias_proj = w->b_proj_fused;
+    dit::MlpFusedParams& m = bp.mlp;
+    m.X = ws.X; m.mod = ws.mod; m.slot_mod = mod_index(plan); m.mod_stride = w->mod_stride;
+    m.mod_off_mul = 3 * dit::D; m.mod_off_add = 4 * dit::D; m.mod_off_gate = 5 * dit::D; m.eps = w->eps;
+    m.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream); m.n_chunks = w->mlp1_tiles; m.hid_slabs = w->hid_slabs;
+    bp.n_layer = w->n_layer; bp.n_tiles = row_tiles;
+    bp.dbg = g_dbg_clk; bp.dbg_layer = g_dbg_layer; bp.stagger_cycles = g_stagger;
+    bp.attn_w_stride = 4LL * dit::D * dit::D;
+    bp.mlp_w_stride = ((long long)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs) * dit::B_SLAB_ELEMS;
+    const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
+    LAUNCH("dit_blocks", launch_pdl(dit::dit_blocks_kernel, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, bp));
+    return SCLDM_OK;
+  }
   for (int l = 0; l < w->n_layer; ++l) {
     const int mo = l * 6 * dit::D;
     if (w->w_attn_stream != nullptr && w->b_proj_fused != nullptr) {  // fused attention half: LN1 + QKV + attention + c_proj + gated residual
@@ -295,6 +317,13 @@ int prepare_kernels() {
   if ((rc = set_smem(dit::gemm_astream_resid_kernel, dit::astream_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::mlp_fused_kernel, dit::mlp_fused_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::attn_block_kernel, dit::attn_block_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::dit_blocks_kernel, dit::phase_smem_bytes()))) return rc;
+  {
+    int dev = 0, n = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (n > 0) g_num_sms = n;
+  }
   if ((rc = set_smem(vae::mcab_decode_kernel, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float)))) return rc;
   done.store(1);
   return SCLDM_OK;

@@ -163,7 +163,10 @@ __device__ __forceinline__ void producer_issue_x_passes(const float* X, int row_
 __device__ __forceinline__ void dbg_stamp(long long* dbg, int slot);
 __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB, uint64_t* x_full, uint64_t* x_empty, uint8_t* smA,
                                                 const float* mod, const ModIndex& slot_mod, int mod_stride, int off_mul, int off_add,
-                                                float eps, int row_tile, uint32_t ew, uint32_t lane, long long* dbg = nullptr) {
+                                                float eps, int row_tile, uint32_t ew, uint32_t lane, long long* dbg = nullptr,
+                                                bool stashed = false, uint32_t x_parity = 0) {
+  // `stashed`: the rows were left in the pass buffers by the previous phase's residual epilogue (resid_epilogue_warp
+  // <.., OUT_STASH>) instead of arriving by TMA: nothing to wait for.
   // Warp ew owns rows [8 ew, 8 ew + 8) of the tile: one X pass (ew / 4), one slot (ew / 2) -> one set of modulation
   // vectors.  Four rows are normalised at a time so that four independent reduction chains overlap.  Lane l holds
   // channels [4l, 4l+4) and [128 + 4l, 128 + 4l + 4) of a row (conflict-free 16 B shared-memory reads).
@@ -172,17 +175,19 @@ __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB
   const float* mrow = mod + (size_t)slot_mod.row(row_tile * 8 + (ew >> 1)) * mod_stride;
   const float4 m0 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 4), m1 = *reinterpret_cast<const float4*>(mrow + off_mul + 128 + lane * 4);
   const float4 a0 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 4), a1 = *reinterpret_cast<const float4*>(mrow + off_add + 128 + lane * 4);
-  sm100::mbar_wait(&x_full[pss], 0);
+  if (!stashed) sm100::mbar_wait(&x_full[pss], x_parity);
   if ((ew & 3) == 0 && lane == 0) dbg_stamp(dbg, 22 + pss);
-  const uint8_t* xb = x_pass_buffer(pss, smScratch, smB) + (ew & 3) * 8 * (D * 4) + lane * 16;
+  const uint8_t* xb = x_pass_buffer(pss, smScratch, smB) + (ew & 3) * 8 * (D * 4);
+  const uint32_t xoff_even = lane * 16, xoff_odd = lane * 16;
   uint8_t* a_lo = smA + (lane >> 4) * A_SLAB_BYTES + (lane & 1) * 8;
 #pragma unroll
   for (int rnd = 0; rnd < 2; ++rnd) {
     float v[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 x0 = *reinterpret_cast<const float4*>(xb + (rnd * 4 + i) * (D * 4));
-      const float4 x1 = *reinterpret_cast<const float4*>(xb + (rnd * 4 + i) * (D * 4) + 512);
+      const uint32_t xo = (i & 1) ? xoff_odd : xoff_even;
+      const float4 x0 = *reinterpret_cast<const float4*>(xb + (rnd * 4 + i) * (D * 4) + xo);
+      const float4 x1 = *reinterpret_cast<const float4*>(xb + (rnd * 4 + i) * (D * 4) + 512 + xo);
       v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w; v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
     }
     if (rnd == 1 && pss >= 2) {   // hand the borrowed weight-ring buffer back to the producer
@@ -531,54 +536,63 @@ static_assert(2 * XPASS_BYTES <= STG_ARES_BYTES, "X pass buffers alias the epilo
 // ==========================================================================================
 // Residual epilogue, one warp at a time and without CTA-wide barriers:
 //   X[32q + r][64*sub + c] += gate[slot(r)][c] * (acc[r][c] + bias[c])      r < 32, c < 64
-// The accumulator arrives row-per-lane (tcgen05.ld 32x32b); a 2 KB warp-private staging block (XOR-swizzled, bank
-// conflict free both ways) turns it into the row-contiguous order of the global read-modify-write (8 rows x 64 B per
-// warp instruction).  The residual rows are prefetched two sub-chunks ahead, the first two before the accumulator wait.
+// The accumulator arrives row-per-lane (tcgen05.ld 32x32b); a 4 KB warp-private staging block (128 B rows, the usual
+// 16-byte XOR swizzle: conflict free both ways) turns two 32-column halves into row-contiguous order: 4 rows x 128 B per
+// warp instruction, i.e. whole cache lines on the global side and conflict-free rows on the shared-memory side.
+//   OUT_GLOBAL  st.global of the updated rows (stand-alone kernels)
+//   OUT_STASH   the updated rows go to shared memory only (row r at stash + 1024 r, the layout of the TMA X passes that
+//               ln_prologue_tma reads): the next phase normalises them from there and the producer thread writes them
+//               back with one bulk-TMA store that overlaps that prologue (dit_blocks_kernel)
 // ==========================================================================================
-constexpr int RESID_WARP_STG = 2048;
-constexpr int RESID_STG_BYTES = EPI_WARPS * RESID_WARP_STG;   // 32 KB
-template <bool HAS_BIAS, typename WaitAcc>
+constexpr int RESID_WARP_STG = 4096;
+constexpr int RESID_STG_BYTES = EPI_WARPS * RESID_WARP_STG;   // 64 KB
+enum { OUT_GLOBAL = 0, OUT_STASH = 1 };
+#ifndef SCLDM_WB_ITEM
+#define SCLDM_WB_ITEM 8
+#endif
+template <bool HAS_BIAS, int OUT, typename WaitAcc>
 __device__ __forceinline__ void resid_epilogue_warp(float* __restrict__ Xtile, uint32_t taddr_q, uint8_t* stg_warp, const float* smGate,
-                                                    const float* smBias, uint32_t q, uint32_t sub, uint32_t lane, WaitAcc&& wait_acc) {
-  const uint32_t rg = lane >> 2, cchunk = lane & 3;          // global side: row within an 8-row group, 16 B chunk
-  float* xp = Xtile + (size_t)(q * 32 + rg) * D + sub * 64 + cchunk * 4;
-  float4 xr[2][4];
-  auto ldx = [&](int sc, int b) {
+                                                    const float* smBias, uint32_t q, uint32_t sub, uint32_t lane, WaitAcc&& wait_acc,
+                                                    uint8_t* stash = nullptr) {
+  const uint32_t rg = lane >> 3, cchunk = lane & 7;          // row-contiguous side: row within a 4-row group, 16 B chunk
+  const float* xp = Xtile + (size_t)(q * 32 + rg) * D + sub * 64 + cchunk * 4;
+  float4 xr[2][8];
+  auto ldx = [&](int half) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) xr[b][it] = *reinterpret_cast<const float4*>(xp + (size_t)it * 8 * D + sc * 16);
+    for (int it = 0; it < 8; ++it) xr[half][it] = __ldcg(reinterpret_cast<const float4*>(xp + (size_t)it * 4 * D + half * 32));
   };
-  ldx(0, 0);
-  ldx(1, 1);
+  ldx(0);
   wait_acc();
-  const uint32_t wsw = (lane >> 1) & 3;                      // staging swizzle of the row this lane writes
 #pragma unroll
-  for (int sc = 0; sc < 4; ++sc) {
+  for (int half = 0; half < 2; ++half) {
     {
-      uint32_t v[16];
-      sm100::tmem_ld_32x32b_x16(taddr_q + sub * 64 + sc * 16, v);
+      uint32_t v[32];
+      sm100::tmem_ld_32x32b_x32(taddr_q + sub * 64 + half * 32, v);
       sm100::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(stg_warp + lane * 64 + ((c ^ wsw) << 4)) = make_float4(
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(stg_warp + sm100::swz_chunk_offset(lane, c)) = make_float4(
             __uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
     }
     __syncwarp();
-    const int col = sub * 64 + sc * 16 + cchunk * 4;
+    if (half == 0) ldx(1);                                   // the accumulator registers are dead: fetch the second half's rows
+    const int col = sub * 64 + half * 32 + cchunk * 4;
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (HAS_BIAS) bb = *reinterpret_cast<const float4*>(smBias + col);
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const uint32_t r = it * 8 + rg;
-      const float4 a = *reinterpret_cast<const float4*>(stg_warp + r * 64 + ((cchunk ^ ((r >> 1) & 3)) << 4));
+    for (int it = 0; it < 8; ++it) {
+      const uint32_t r = it * 4 + rg;
+      const float4 a = *reinterpret_cast<const float4*>(stg_warp + sm100::swz_chunk_offset(r, cchunk));
       const float4 gg = *reinterpret_cast<const float4*>(smGate + ((q * 32 + r) >> 4) * D + col);
-      float4 o = xr[sc & 1][it];
+      float4 o = xr[half][it];
       o.x += gg.x * (a.x + bb.x); o.y += gg.y * (a.y + bb.y);
       o.z += gg.z * (a.z + bb.z); o.w += gg.w * (a.w + bb.w);
-      *reinterpret_cast<float4*>(xp + (size_t)it * 8 * D + sc * 16) = o;
+      if constexpr (OUT == OUT_GLOBAL) *reinterpret_cast<float4*>(Xtile + (size_t)(q * 32 + r) * D + col) = o;
+      else *reinterpret_cast<float4*>(stash + (q * 32 + r) * (D * 4) + col * 4) = o;
     }
-    __syncwarp();                                            // staging is rewritten by the next sub-chunk
-    if (sc + 2 < 4) ldx(sc + 2, sc & 1);
+    __syncwarp();                                            // staging is rewritten by the second half
   }
+  if constexpr (OUT == OUT_STASH) sm100::fence_proxy_async_smem();   // the stash is read by a bulk-TMA store next
 }
 
 // ==========================================================================================
@@ -593,7 +607,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
   if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smStage = smem;                              // NSTAGE x (A 16 KB | B 32 KB)
   uint8_t* smStg = smem + NSTAGE * STAGE_BYTES;
-  float* smGate = reinterpret_cast<float*>(smStg + STG_BYTES);   // [8 cells][256]
+  float* smGate = reinterpret_cast<float*>(smStg + RESID_STG_BYTES);   // [8 cells][256]
   float* smBias = smGate + 8 * D;                                // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smBias + D);
   uint64_t* full = bars;
@@ -675,7 +689,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
     }
     if (etid == 0) dbg_stamp(p.dbg, 3);
     sm100::named_bar_sync(1, EPI_THREADS);   // gates + bias staged (the MMAs are still running)
-    resid_epilogue_warp<true>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16), smStg + ew * RESID_WARP_STG, smGate, smBias,
+    resid_epilogue_warp<true, OUT_GLOBAL>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16), smStg + ew * RESID_WARP_STG, smGate, smBias,
                               q, sub, lane, [&] {
                                 sm100::mbar_wait(tmem_full, 0);
                                 sm100::tc_fence_after();
@@ -689,7 +703,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_astream_resid_kernel(cons
   if (threadIdx.x == 0) dbg_stamp(p.dbg, 31);
 }
 
-constexpr size_t astream_smem_bytes() { return 1024 + 3 * (A_SLAB_BYTES + B_SLAB_BYTES) + STG_BYTES + 9 * D * 4 + 256; }
+constexpr size_t astream_smem_bytes() { return 3 * (A_SLAB_BYTES + B_SLAB_BYTES) + RESID_STG_BYTES + 9 * D * 4 + 256; }
 
 // ==========================================================================================
 // Fused MLP half of a DiT block (layers.py:219-221): x += gate * c_proj( silu(w1 h) * (w2 h) ),  h = LN(x)*(1+c3)+c4
@@ -718,15 +732,70 @@ struct MlpFusedParams {
   long long* dbg;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFusedParams p) {
+// Shared-memory map common to both fused phases (attention half / MLP half) so that they can alternate inside one
+// persistent kernel (dit_blocks_kernel):  [0,64K) A tile | [64K,128K) q/k/v + AO slabs or H buffers | [128K,224K) weight
+// ring | 1 KB q bias | mbarriers.  The residual rows of a tile pass through [64K,192K) (TMA passes or the stash).
+constexpr int PH_OFF_MID = KSLABS_D * A_SLAB_BYTES;       // 64 KB
+constexpr int PH_OFF_RING = PH_OFF_MID + 4 * A_SLAB_BYTES; // 128 KB
+constexpr int PH_OFF_BIASQ = PH_OFF_RING + 96 * 1024;      // 224 KB
+constexpr int PH_OFF_BARS = PH_OFF_BIASQ + D * 4;
+constexpr int PH_BARS_PER_SET = 20;
+constexpr int PH_OFF_TMEMPTR = PH_OFF_BARS + 2 * PH_BARS_PER_SET * 8;   // set 0: attention phase, set 1: MLP phase
+constexpr size_t phase_smem_bytes() { return PH_OFF_TMEMPTR + 64; }
+static_assert(phase_smem_bytes() <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+constexpr int PH_OFF_GATE = PH_OFF_RING + 80 * 1024;   // gates + c_proj bias: parked in the (then idle) tail of the weight ring
+static_assert(RESID_STG_BYTES <= KSLABS_D * A_SLAB_BYTES, "residual staging lives in the dead A tile");
+static_assert(PH_OFF_GATE + 9 * D * 4 <= PH_OFF_BIASQ, "gates + bias fit in the ring tail");
+
+// Write the stashed residual rows of the tile back to global memory (issued by the producer thread at the start of the
+// phase that consumes the stash).  Two bulk groups: rows 64-127 first (they sit in the weight ring, which the producer
+// needs back soonest: cp.async.bulk.wait_group.read 1), then rows 0-63.
+__device__ __forceinline__ void stash_write_back(float* Xtile, const uint8_t* stash) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int half = 1 - g;
+    sm100::bulk_s2g(Xtile + (size_t)half * 64 * D, stash + half * 64 * D * 4, 32 * D * 4);
+    sm100::bulk_s2g(Xtile + (size_t)(half * 64 + 32) * D, stash + (half * 64 + 32) * D * 4, 32 * D * 4);
+    sm100::bulk_commit();
+  }
+}
+
+// The mbarriers of both phase types are initialised ONCE per kernel (warp 0, one barrier per lane) and never
+// re-initialised: a phase that runs for the n-th time waits with parities shifted by how often each barrier has completed
+// before.  Per execution every barrier completes an even number of times, except the single-shot ones (a_ready, the final
+// accumulator, x_empty, and the MLP's h_ready / h_free, 3 uses each), whose parity therefore alternates with (n & 1);
+// x_full completes only in executions whose rows come by TMA.  The MLP weight ring is padded with hand-made completions
+// up to an even number of rounds (mlp_phase).
+struct PhaseSeq {
+  uint32_t odd;     // (previous executions of this phase type) & 1
+  uint32_t tma;     // (previous executions with x_tma) & 1
+};
+__device__ __forceinline__ void phase_barriers_init(uint8_t* smem) {
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS);
+  const uint32_t lane = threadIdx.x & 31;
+  if ((threadIdx.x >> 5) == 0) {
+    if (lane < PH_BARS_PER_SET) {
+      // attention set: full[4] empty[4] a_ready accq_full accq_free ao_ready ao_free accp_full x_full[4] x_empty[2]
+      const uint32_t ca = (lane == 8 || lane == 10 || lane == 11) ? EPI_WARPS : (lane >= 18 ? XPASS_WARPS : 1);
+      sm100::mbar_init(&bars[lane], ca);
+      // MLP set: full[3] empty[3] a_ready acc1_full acc1_free h_ready[2] h_free[2] acc2_full x_full[4] x_empty[2]
+      const uint32_t cm = (lane == 6 || lane == 8 || lane == 9 || lane == 10) ? EPI_WARPS : (lane >= 18 ? XPASS_WARPS : 1);
+      sm100::mbar_init(&bars[PH_BARS_PER_SET + lane], cm);
+    }
+    sm100::fence_barrier_init();
+  }
+}
+
+// One MLP half on the CTA's tile.  Entry: every thread of the CTA, previous phase complete (CTA-wide barrier passed),
+// TMEM allocated.  x_tma: the tile's rows are fetched by TMA (otherwise the previous phase stashed them).  STASH: leave
+// the updated rows in shared memory for the next phase.  Exit: CTA-wide barrier passed, all async work retired.
+template <bool STASH>
+__device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile, uint8_t* smem, uint32_t tmem_base, bool x_tma, PhaseSeq seq) {
   constexpr uint32_t NSTAGE = 3;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;   // keep shared-space provenance (LDS/STS, not generic LD/ST); alignment is checked below
-  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smA = smem;                                     // 4 x 16 KB (later: epilogue staging + gates)
-  uint8_t* smH = smA + KSLABS_D * A_SLAB_BYTES;            // 2 x (2 x 16 KB); first the X pass buffers
-  uint8_t* smB = smH + 4 * A_SLAB_BYTES;                   // NSTAGE x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + NSTAGE * B_SLAB_BYTES);
+  uint8_t* smH = smem + PH_OFF_MID;                        // 2 x (2 x 16 KB); first the X pass buffers / stash
+  uint8_t* smB = smem + PH_OFF_RING;                       // NSTAGE x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS) + PH_BARS_PER_SET;
   uint64_t* full = bars;                  // [3]
   uint64_t* empty = bars + 3;             // [3]
   uint64_t* a_ready = bars + 6;
@@ -737,52 +806,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
   uint64_t* acc2_full = bars + 13;
   uint64_t* x_full = bars + 14;           // [4]
   uint64_t* x_empty = bars + 18;          // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_tile = blockIdx.x;
   const int T = p.n_chunks;
   if (threadIdx.x == 0) dbg_stamp(p.dbg, 0);
+  const uint32_t po = seq.odd, px = seq.tma;
+  // parity shifts of the barriers that complete T (acc1) or about T/2 (H buffer b) times per execution
+  const uint32_t pt = po & (uint32_t)(T & 1);
+  const uint32_t ph[2] = {po & (uint32_t)(((T + 1) >> 1) & 1), po & (uint32_t)((T >> 1) & 1)};
   if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < NSTAGE; ++i) { sm100::mbar_init(&full[i], 1); sm100::mbar_init(&empty[i], 1); }
-    sm100::mbar_init(a_ready, EPI_WARPS);
-    sm100::mbar_init(acc1_full, 1);
-    sm100::mbar_init(acc1_free, EPI_WARPS);
-    for (int i = 0; i < 2; ++i) {
-      sm100::mbar_init(&h_ready[i], EPI_WARPS); sm100::mbar_init(&h_free[i], 1);
-      sm100::mbar_init(&x_empty[i], XPASS_WARPS);
-    }
-    for (int i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
-    sm100::mbar_init(acc2_full, 1);
-    sm100::fence_barrier_init();
-    // first loads go out before the setup barrier: weight slab 0, then (once the preceding kernel's X is visible) all
-    // four X passes (H buffers + two idle ring buffers)
+    // first loads: weight slab 0 into the ring buffer that carries no residual rows, then (x_tma) all four X passes
     sm100::mbar_arrive_expect_tx(&full[0], B_SLAB_BYTES);
     sm100::bulk_g2s(smB + ring_buf(0) * B_SLAB_BYTES, p.Wstream, B_SLAB_BYTES, &full[0]);
-    sm100::grid_dep_wait();
-    producer_issue_x_passes(p.X, row_tile, smH, smB, x_full);
+    if (x_tma) producer_issue_x_passes(p.X, row_tile, smH, smB, x_full);
+    else stash_write_back(p.X + (size_t)row_tile * BLOCK_M * D, smH);
   }
-  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
-  sm100::grid_dep_launch();
-  sm100::grid_dep_wait();
-  sm100::tc_fence_before();
   __syncthreads();
-  sm100::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
   auto m2_slabs = [&](int j) { return min(2, p.hid_slabs - 2 * j); };
+  const int total = KSLABS_D * T + p.hid_slabs;               // weight slabs of the phase
+  int rounds = (total + (int)NSTAGE - 1) / (int)NSTAGE;
+  rounds += rounds & 1;
+  const int padded = rounds * (int)NSTAGE;                     // ring completions incl. the hand-made ones
 
   if (warp == 0) {
     // ===================== producer: X passes, then one linear stream of weight slabs =======
     if (lane == 0) {
-      int total = 0;
-      for (int j = 0; j < T; ++j) total += KSLABS_D + m2_slabs(j);
       RingState rs;
       rs.advance(NSTAGE);   // slab 0 was issued during setup
       for (int i = 1; i < total; ++i) {
-        if (i == 1 || i == 2) sm100::mbar_wait(&x_empty[i - 1], 0);   // first use of a ring buffer that carried an X pass
+        if (i == 1 || i == 2) sm100::mbar_wait(&x_empty[i - 1], po);  // first use of a ring buffer that carried residual rows
+        if (i == 1 && !x_tma) sm100::bulk_wait_read<1>();             // ... and the write-back has read rows 64-127 too
+        if (i == 3 && !x_tma) sm100::bulk_wait_read<0>();             // rows 0-63 (H buffers) read before E1_0 can be reached
+        if (i == SCLDM_WB_ITEM && !x_tma) sm100::bulk_wait<0>();      // write-back complete long before this phase's epilogue re-reads X
         sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
         sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
         sm100::bulk_g2s(smB + ring_buf(rs.stage) * B_SLAB_BYTES, p.Wstream + (size_t)i * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
+        rs.advance(NSTAGE);
+      }
+      for (int i = total; i < padded; ++i) {   // hand-made completions: every ring barrier ends the phase at parity 0
+        sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+        sm100::mbar_arrive(&full[rs.stage]);
         rs.advance(NSTAGE);
       }
     }
@@ -792,13 +855,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
       const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
       const uint32_t acc1 = tmem_base, acc2 = tmem_base + BLOCK_N;
       dbg_stamp(p.dbg, 1);
-      sm100::mbar_wait(a_ready, 0);
+      sm100::mbar_wait(a_ready, po);
       sm100::tc_fence_after();
       dbg_stamp(p.dbg, 2);
       RingState rs;
       for (int j = 0; j <= T; ++j) {
         if (j < T) {  // M1_j
-          if (j > 0) { sm100::mbar_wait(acc1_free, (j - 1) & 1); sm100::tc_fence_after(); }
+          if (j > 0) { sm100::mbar_wait(acc1_free, ((j - 1) & 1) ^ pt); sm100::tc_fence_after(); }
           for (int ks = 0; ks < KSLABS_D; ++ks) {
             sm100::mbar_wait(&full[rs.stage], rs.phase);
             sm100::tc_fence_after();
@@ -810,7 +873,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
         }
         if (j >= 1) {  // M2_{j-1}
           const int c = j - 1, b = c & 1;
-          sm100::mbar_wait(&h_ready[b], (c >> 1) & 1);
+          sm100::mbar_wait(&h_ready[b], ((c >> 1) & 1) ^ ph[b]);
           sm100::tc_fence_after();
           const int ns = m2_slabs(c);
           for (int s2 = 0; s2 < ns; ++s2) {
@@ -825,12 +888,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
         }
       }
       sm100::umma_commit(acc2_full);
+      for (int i = total; i < padded; ++i) {   // consume the hand-made ring completions
+        sm100::mbar_wait(&full[rs.stage], rs.phase);
+        sm100::mbar_arrive(&empty[rs.stage]);
+        rs.advance(NSTAGE);
+      }
     }
   } else {
     // ===================== 16 prologue / epilogue warps ====================================
     const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
-    ln_prologue_tma(smH, smB, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg);
+    ln_prologue_tma(smH, smB, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px);
     sm100::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) sm100::mbar_arrive(a_ready);
@@ -839,7 +907,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     // ---------- E1_j: SwiGLU of hidden chunk j into the A slabs of M2_j ----------
     const int hs = sub >> 1, h = sub & 1;   // this warp: slab hs of the chunk, 32-column half h
     for (int j = 0; j < T; ++j) {
-      sm100::mbar_wait(acc1_full, j & 1);
+      sm100::mbar_wait(acc1_full, (j & 1) ^ pt);
       sm100::tc_fence_after();
       if (etid == 0 && j < 6) dbg_stamp(p.dbg, 4 + 2 * j);
       const uint32_t taddr = tmem_base + ((q * 32u) << 16);
@@ -851,7 +919,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(acc1_free);          // M1_{j+1} may overwrite acc1
       const int b = j & 1;
-      if (j >= 2) sm100::mbar_wait(&h_free[b], ((j >> 1) - 1) & 1);   // M2_{j-2} finished reading this buffer
+      if (j >= 2) sm100::mbar_wait(&h_free[b], (((j >> 1) - 1) & 1) ^ ph[b]);   // M2_{j-2} finished reading this buffer
       uint8_t* buf = smH + (b * 2 + hs) * A_SLAB_BYTES;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -872,25 +940,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
     }
 
     // ---------- final epilogue: x += gate * acc2 ----------
-    float* smGate = reinterpret_cast<float*>(smA + RESID_STG_BYTES);   // the A tile is dead once acc2 is complete
+    float* smGate = reinterpret_cast<float*>(smem + PH_OFF_GATE);   // every weight slab has been consumed: the ring is idle
     const int gcell = etid >> 6, gc4 = etid & 63;
     const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod.row(row_tile * 8 + gcell) * p.mod_stride + p.mod_off_gate + gc4 * 4);
-    resid_epilogue_warp<false>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16) + BLOCK_N, smA + ew * RESID_WARP_STG, smGate,
-                               nullptr, q, sub, lane, [&] {
-                                 sm100::mbar_wait(acc2_full, 0);
-                                 sm100::tc_fence_after();
-                                 if (etid == 0) dbg_stamp(p.dbg, 20);
-                                 reinterpret_cast<float4*>(smGate)[etid] = gate_v;
-                                 sm100::named_bar_sync(1, EPI_THREADS);
-                               });
+    resid_epilogue_warp<false, STASH ? OUT_STASH : OUT_GLOBAL>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16) + BLOCK_N, smA + ew * RESID_WARP_STG, smGate,
+                                      nullptr, q, sub, lane, [&] {
+                                        sm100::mbar_wait(acc2_full, po);
+                                        sm100::tc_fence_after();
+                                        if (etid == 0) dbg_stamp(p.dbg, 20);
+                                        reinterpret_cast<float4*>(smGate)[etid] = gate_v;
+                                        sm100::named_bar_sync(1, EPI_THREADS);
+                                      }, smH);
   }
   sm100::tc_fence_before();
   __syncthreads();
-  if (warp == 1) sm100::tmem_dealloc(tmem_base, 512);
   if (threadIdx.x == 0) dbg_stamp(p.dbg, 31);
 }
 
-constexpr size_t mlp_fused_smem_bytes() { return 1024 + (KSLABS_D + 4) * A_SLAB_BYTES + 3 * B_SLAB_BYTES + 256; }
+__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // keep shared-space provenance (LDS/STS, not generic LD/ST); alignment is checked below
+  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
+  if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
+  phase_barriers_init(smem);
+  sm100::grid_dep_launch();
+  sm100::grid_dep_wait();   // X and the modulation table come from the preceding kernels
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  mlp_phase<false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
+  if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
+}
+
+constexpr size_t mlp_fused_smem_bytes() { return phase_smem_bytes(); }
 static_assert(2 * XPASS_BYTES <= 4 * A_SLAB_BYTES, "X pass buffers alias the H buffers");
 
 // ==========================================================================================
@@ -1080,32 +1164,23 @@ constexpr uint32_t AB_NSTAGE = 4;
 constexpr int AB_STAGE_BYTES = AB_QN * BLOCK_K * 2;     // 24 KB
 constexpr int AB_Q_ITEM_BYTES = AB_QN * BLOCK_K * 2;    // 24 KB
 constexpr int AB_P_ITEM_BYTES = 128 * BLOCK_K * 2;      // 16 KB
-constexpr int AB_OFF_QKV = KSLABS_D * A_SLAB_BYTES;               // 64 KB
-constexpr int AB_OFF_AO = AB_OFF_QKV + 3 * A_SLAB_BYTES;          // +48 KB
-constexpr int AB_OFF_W = AB_OFF_AO + A_SLAB_BYTES;                // +16 KB = 128 KB
-constexpr int AB_OFF_BIASQ = AB_OFF_W + AB_NSTAGE * AB_STAGE_BYTES;   // 224 KB
-constexpr int AB_OFF_BARS = AB_OFF_BIASQ + D * 4;
-constexpr size_t attn_block_smem_bytes() { return AB_OFF_BARS + 256; }
-static_assert(attn_block_smem_bytes() <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-static_assert(2 * XPASS_BYTES <= 4 * A_SLAB_BYTES, "X passes 0,1 alias the q/k/v + AO staging");
-static_assert(2 * XPASS_BYTES <= (AB_NSTAGE - 1) * AB_STAGE_BYTES, "X passes 2,3 alias ring buffers 0-2; buffer 3 is free from the start");
-static_assert(RESID_STG_BYTES <= 3 * A_SLAB_BYTES, "residual staging aliases the q/k/v slabs");
-static_assert(9 * D * 4 <= AB_STAGE_BYTES, "gate vectors + c_proj bias are parked in the (then idle) weight ring");
-// logical ring stage -> physical buffer: the first item lands in buffer 3, which carries no X pass
+constexpr size_t attn_block_smem_bytes() { return phase_smem_bytes(); }
+static_assert(AB_NSTAGE * AB_STAGE_BYTES == PH_OFF_BIASQ - PH_OFF_RING, "weight ring fills [128K, 224K)");
+static_assert(2 * XPASS_BYTES <= (AB_NSTAGE - 1) * AB_STAGE_BYTES, "residual rows alias ring buffers 0-2; buffer 3 is free from the start");
+// logical ring stage -> physical buffer: the first item lands in buffer 3, which carries no residual rows
 __device__ __forceinline__ uint32_t ab_ring_buf(uint32_t stage) { return (stage + 3u) & 3u; }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBlockParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
+// One attention half on the CTA's tile; same entry / exit contract as mlp_phase.
+template <bool STASH>
+__device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_tile, uint8_t* smem, uint32_t tmem_base, bool x_tma, PhaseSeq seq) {
   uint8_t* smA = smem;
-  uint8_t* smQKV = smem + AB_OFF_QKV;     // q | k | v slabs of the current head pair; first X passes 0,1
-  uint8_t* smAO = smem + AB_OFF_AO;
-  uint8_t* smW = smem + AB_OFF_W;         // weight ring; first X passes 2,3
-  float* smGate = reinterpret_cast<float*>(smW);   // parked here once every weight item has been consumed
+  uint8_t* smQKV = smem + PH_OFF_MID;     // q | k | v slabs of the current head pair; first residual rows 0-63
+  uint8_t* smAO = smQKV + 3 * A_SLAB_BYTES;
+  uint8_t* smW = smem + PH_OFF_RING;      // weight ring; first residual rows 64-127
+  float* smGate = reinterpret_cast<float*>(smem + PH_OFF_GATE);       // parked once every weight item has been consumed
   float* smBiasP = smGate + 8 * D;
-  float* smBiasQ = reinterpret_cast<float*>(smem + AB_OFF_BIASQ);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_OFF_BARS);
+  float* smBiasQ = reinterpret_cast<float*>(smem + PH_OFF_BIASQ);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS);
   uint64_t* full = bars;                  // [4]
   uint64_t* empty = bars + 4;             // [4]
   uint64_t* a_ready = bars + 8;
@@ -1116,36 +1191,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
   uint64_t* accp_full = bars + 13;
   uint64_t* x_full = bars + 14;           // [4]
   uint64_t* x_empty = bars + 18;          // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_tile = blockIdx.x;
   if (threadIdx.x == 0) dbg_stamp(p.dbg, 0);
+  const uint32_t po = seq.odd, px = seq.tma;
   if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < AB_NSTAGE; ++i) { sm100::mbar_init(&full[i], 1); sm100::mbar_init(&empty[i], 1); }
-    sm100::mbar_init(a_ready, EPI_WARPS);
-    sm100::mbar_init(accq_full, 1);
-    sm100::mbar_init(accq_free, EPI_WARPS);
-    sm100::mbar_init(ao_ready, EPI_WARPS);
-    sm100::mbar_init(ao_free, 1);
-    sm100::mbar_init(accp_full, 1);
-    for (int i = 0; i < 4; ++i) sm100::mbar_init(&x_full[i], 1);
-    for (int i = 0; i < 2; ++i) sm100::mbar_init(&x_empty[i], XPASS_WARPS);
-    sm100::fence_barrier_init();
-    // weight item 0 (independent of the previous kernel) goes into the ring buffer that carries no X pass
+    // weight item 0 goes into the ring buffer that carries no residual rows; then (x_tma) all four X passes
     sm100::mbar_arrive_expect_tx(&full[0], AB_Q_ITEM_BYTES);
     sm100::bulk_g2s(smW + ab_ring_buf(0) * AB_STAGE_BYTES, p.Wstream, AB_Q_ITEM_BYTES, &full[0]);
-    sm100::grid_dep_wait();                 // X and the modulation table come from the preceding kernels
-    producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
+    if (x_tma) producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
+    else stash_write_back(p.X + (size_t)row_tile * BLOCK_M * D, smQKV);
   }
-  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
-  sm100::grid_dep_launch();
-  sm100::grid_dep_wait();
-  sm100::tc_fence_before();
   __syncthreads();
-  sm100::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
   if (warp == 0) {
     // ===================== producer: one linear stream of weight items ======================
     if (lane == 0) {
@@ -1153,10 +1210,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wstream);
       int item = 0;
       auto issue = [&](uint32_t bytes) {
-        if (item == 1) {                      // buffers 0-2 carried X passes 2 and 3
-          sm100::mbar_wait(&x_empty[0], 0);
-          sm100::mbar_wait(&x_empty[1], 0);
+        if (item == 1) {                      // buffers 0-2 carried residual rows 64-127
+          sm100::mbar_wait(&x_empty[0], po);
+          sm100::mbar_wait(&x_empty[1], po);
+          if (!x_tma) sm100::bulk_wait_read<1>();   // ... and the write-back has read them too
         }
+        if (item == 3 && !x_tma) sm100::bulk_wait_read<0>();   // rows 0-63 (q/k/v staging) read before the first head pair can be staged
+        if (item == SCLDM_WB_ITEM && !x_tma) sm100::bulk_wait<0>();   // write-back complete long before this phase's epilogue re-reads X
         if (item > 0) {                       // item 0 was issued during setup
           sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
           sm100::mbar_arrive_expect_tx(&full[rs.stage], bytes);
@@ -1180,7 +1240,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
       const uint32_t idesc_p = sm100::make_idesc_bf16(BLOCK_M, 128);
       const uint32_t accq = tmem_base, accp = tmem_base + 256;
       dbg_stamp(p.dbg, 1);
-      sm100::mbar_wait(a_ready, 0);
+      sm100::mbar_wait(a_ready, po);
       sm100::tc_fence_after();
       dbg_stamp(p.dbg, 2);
       RingState rs;
@@ -1216,7 +1276,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
     // ===================== 16 worker warps ==================================================
     const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
-    ln_prologue_tma(smQKV, smW, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg);
+    ln_prologue_tma(smQKV, smW, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px);
     sm100::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) sm100::mbar_arrive(a_ready);
@@ -1282,20 +1342,110 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
     }
 
     // ---------- final epilogue: x += gate * (accp + bias) ----------
-    resid_epilogue_warp<true>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16) + 256, smQKV + ew * RESID_WARP_STG, smGate, smBiasP,
-                              q, sub, lane, [&] {
-                                sm100::mbar_wait(accp_full, 0);
-                                sm100::tc_fence_after();
-                                if (etid == 0) dbg_stamp(p.dbg, 20);
-                                reinterpret_cast<float4*>(smGate)[etid] = gate_v;   // every MMA has retired: the ring is idle
-                                if (etid < 64) reinterpret_cast<float4*>(smBiasP)[etid] = bias_v;
-                                sm100::named_bar_sync(1, EPI_THREADS);
-                              });
+    resid_epilogue_warp<true, STASH ? OUT_STASH : OUT_GLOBAL>(p.X + (size_t)row_tile * BLOCK_M * D, tmem_base + ((q * 32u) << 16) + 256, smA + ew * RESID_WARP_STG, smGate, smBiasP,
+                                     q, sub, lane, [&] {
+                                       sm100::mbar_wait(accp_full, po);
+                                       sm100::tc_fence_after();
+                                       if (etid == 0) dbg_stamp(p.dbg, 20);
+                                       reinterpret_cast<float4*>(smGate)[etid] = gate_v;   // every MMA has retired: the A tile is dead
+                                       if (etid < 64) reinterpret_cast<float4*>(smBiasP)[etid] = bias_v;
+                                       sm100::named_bar_sync(1, EPI_THREADS);
+                                     }, smQKV);
   }
   sm100::tc_fence_before();
   __syncthreads();
-  if (warp == 1) sm100::tmem_dealloc(tmem_base, 512);
   if (threadIdx.x == 0) dbg_stamp(p.dbg, 31);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBlockParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
+  if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
+  phase_barriers_init(smem);
+  sm100::grid_dep_launch();
+  sm100::grid_dep_wait();   // X and the modulation table come from the preceding kernels
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  attn_phase<false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
+  if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
+}
+
+// ==========================================================================================
+// The whole block stack of one DiT evaluation as ONE persistent kernel: tiles are independent through all layers, so
+// each CTA walks its tiles through attention half / MLP half of every layer without ever synchronising with other CTAs.
+// Between phases the residual rows stay in shared memory (stash), TMEM stays allocated, and CTAs drift out of lock-step,
+// which spreads the L2-bound residual read-modify-write over time.
+// ==========================================================================================
+struct BlocksParams {
+  AttnBlockParams attn;   // layer 0; layer l adds the strides below
+  MlpFusedParams mlp;
+  int n_layer, n_tiles;
+  long long attn_w_stride, mlp_w_stride;   // elements per layer in the two weight streams
+  long long* dbg;                          // optional phase timeline of (second tile, layer dbg_layer) per CTA
+  int dbg_layer;
+  int stagger_cycles;                      // CTA b starts (b % 8) * stagger_cycles late: see dit_blocks_kernel
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const BlocksParams bp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
+  if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
+  phase_barriers_init(smem);
+  sm100::grid_dep_launch();
+  sm100::grid_dep_wait();
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // Every tile costs the same, so CTAs launched together would stay in lock-step and hit the L2-bound stretches (the
+  // residual read-modify-write above all) at the same moment on all SMs.  A one-off start offset per CTA keeps them
+  // out of phase for the rest of the kernel.
+  if (bp.stagger_cycles > 0) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64(), d = (long long)(blockIdx.x & 7) * bp.stagger_cycles;
+      while (clock64() - t0 < d) {}
+    }
+    __syncthreads();
+  }
+  int* smRows = reinterpret_cast<int*>(smem + PH_OFF_TMEMPTR + 16);   // conditioning row of each of the tile's 8 slots
+  uint32_t n_attn = 0, n_mlp = 0, n_tma = 0;                          // executions so far (mbarrier parities, see PhaseSeq)
+  for (int tile = blockIdx.x; tile < bp.n_tiles; tile += gridDim.x) {
+    // resolve the tile's slot -> conditioning-row indices once, so that the per-phase loads of the modulation vectors are
+    // not behind a second dependent global load (visible to all warps after the first phase's setup barrier; the previous
+    // tile's last phase ended with a CTA-wide barrier)
+    if (threadIdx.x < 8) smRows[threadIdx.x] = bp.attn.slot_mod.row(tile * 8 + threadIdx.x);
+    ModIndex tile_rows{};
+    tile_rows.table = smRows - tile * 8;
+    tile_rows.mode = 0;
+    for (int l = 0; l < bp.n_layer; ++l) {
+      AttnBlockParams ap = bp.attn;
+      ap.slot_mod = tile_rows;
+      ap.Wstream += (size_t)l * bp.attn_w_stride;
+      ap.bias_q += (size_t)l * 3 * D;
+      ap.bias_proj += (size_t)l * D;
+      ap.mod_off_mul += l * 6 * D; ap.mod_off_add += l * 6 * D; ap.mod_off_gate += l * 6 * D;
+      const bool dbg_on = bp.dbg != nullptr && l == bp.dbg_layer && tile == (int)(blockIdx.x + gridDim.x);
+      ap.dbg = dbg_on ? bp.dbg : nullptr;
+      attn_phase<true>(ap, tile, smem, tmem_base, l == 0, PhaseSeq{n_attn & 1, n_tma & 1});
+      ++n_attn;
+      if (l == 0) ++n_tma;
+      MlpFusedParams mp = bp.mlp;
+      mp.slot_mod = tile_rows;
+      mp.Wstream += (size_t)l * bp.mlp_w_stride;
+      mp.mod_off_mul += l * 6 * D; mp.mod_off_add += l * 6 * D; mp.mod_off_gate += l * 6 * D;
+      mp.dbg = dbg_on ? bp.dbg + 2 * (1 << 17) : nullptr;
+      if (l + 1 < bp.n_layer) mlp_phase<true>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
+      else mlp_phase<false>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
+      ++n_mlp;
+    }
+  }
+  if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
 }
 
 // ==========================================================================================

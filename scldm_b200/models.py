@@ -31,7 +31,7 @@ class LatentDiffusion(nn.Module):
     def __init__(self, vae_model: TransformerVAE, diffusion_model: DiT, transport: Transport,
                  mu_size_factor: dict | None = None, sd_size_factor: dict | None = None,
                  size_factor_condition_key: str | None = None, sampling_method: str = "euler", num_steps: int = 50,
-                 seed: int = 0, cell_chunk: int = 784, joint_idx_2_classes: dict | None = None, joint_key: str | None = None,
+                 seed: int = 0, cell_chunk: int = 1184, joint_idx_2_classes: dict | None = None, joint_key: str | None = None,
                  joint_components: list | None = None, **_unused_training_kwargs):
         super().__init__()
         self.vae_model = vae_model

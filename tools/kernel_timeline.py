@@ -33,6 +33,8 @@ torch.cuda.synchronize()
 _lib.load().scldm_debug_timeline(None, -1)
 b = buf.cpu().view(4, -1, 32)
 n_cta = (3 * cells + 7) // 8
+if os.environ.get("SCLDM_MEGA", "1") != "0":
+    n_cta = min(n_cta, 148)   # persistent kernel: one CTA per SM, stamps of its second tile
 names = ["qkv", "proj", "mlp1", "mlp2"]
 spans = {}
 for k, name in enumerate(names):
