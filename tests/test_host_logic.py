@@ -55,6 +55,42 @@ def test_dit_pack_layout_cpu():
     assert torch.equal(m2[:, :684], sd["blocks.0.mlp.c_proj.weight"].to(torch.bfloat16))
 
 
+def test_attention_stream_pack_layout_cpu():
+    """The fused attention-block kernel walks one linear weight stream: per head pair hp four 192x64 [Wq|Wk|Wv] slabs
+    (Q items) and two 128x64 c_proj slabs (P items), in the MMA issue order Q0 Q1 P0 Q2 P1 Q3 P2 P3; the v bias is
+    folded into the c_proj bias (rows of softmax sum to 1) and the k bias is dropped (cancels in the softmax)."""
+    cfg = DiTConfig(class_vocab_sizes={"a": 3}, n_layer=2)
+    sd = synthetic.dit_state_dict(cfg, 1)
+    pk = pack.PackedDiT(sd, cfg, "cpu")
+    stream = pk.w_attn_stream[1]                       # layer 1
+    assert stream.numel() == 4 * 256 * 256
+    q_item, p_item = 192 * 64, 128 * 64
+    order = [("q", 0), ("q", 1), ("p", 0), ("q", 2), ("p", 1), ("q", 3), ("p", 2), ("p", 3)]
+    wqkv = sd["blocks.1.attn.c_attn.weight"].to(torch.bfloat16)
+    wp = sd["blocks.1.attn.c_proj.weight"].to(torch.bfloat16)
+    off = 0
+    for kind, hp in order:
+        if kind == "q":
+            tile = pack.unpack_kmajor_tiles(stream[off: off + 4 * q_item].view(1, 4, q_item), 192)   # [192, 256]
+            rows = torch.cat([torch.arange(part * 256 + 64 * hp, part * 256 + 64 * hp + 64) for part in range(3)])
+            assert torch.equal(tile, wqkv[rows])
+            off += 4 * q_item
+        else:
+            tile = pack.unpack_kmajor_tiles(stream[off: off + 2 * p_item].view(2, 1, p_item), 128)   # [256, 64]
+            assert torch.equal(tile, wp[:, 64 * hp: 64 * hp + 64])
+            off += 2 * p_item
+    assert off == stream.numel()
+    bqkv = sd["blocks.1.attn.c_attn.bias"].double()
+    want = sd["blocks.1.attn.c_proj.bias"].double() + sd["blocks.1.attn.c_proj.weight"].double() @ bqkv[512:]
+    assert torch.allclose(pk.b_proj_fused[1].double(), want, atol=1e-6)
+    # attention is invariant to the k bias and shifts by the v bias: softmax(q(k+bk)^T)(v+bv) = softmax(q k^T) v + bv
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(16, 32, generator=g, dtype=torch.float64) for _ in range(3))
+    bk, bv = torch.randn(32, generator=g, dtype=torch.float64), torch.randn(32, generator=g, dtype=torch.float64)
+    att = lambda q, k, v: torch.softmax(q @ k.T / 32 ** 0.5, -1) @ v  # noqa: E731
+    assert torch.allclose(att(q, k + bk, v + bv), att(q, k, v) + bv, atol=1e-12)
+
+
 def test_vae_pack_layout_cpu():
     cfg = VAEConfig(n_genes=50, n_layer=2)
     sd = synthetic.vae_state_dict(cfg, 1)
