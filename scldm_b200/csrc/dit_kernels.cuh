@@ -579,11 +579,14 @@ __device__ __forceinline__ void resid_epilogue_warp(float* __restrict__ Xtile, u
     const int col = sub * 64 + half * 32 + cchunk * 4;
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (HAS_BIAS) bb = *reinterpret_cast<const float4*>(smBias + col);
+    // rows 4 it + rg of this quadrant belong to slot 2q + it / 4: two gate vectors per half, kept in registers
+    const float4 g_lo = *reinterpret_cast<const float4*>(smGate + (q * 2) * D + col);
+    const float4 g_hi = *reinterpret_cast<const float4*>(smGate + (q * 2 + 1) * D + col);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const uint32_t r = it * 4 + rg;
       const float4 a = *reinterpret_cast<const float4*>(stg_warp + sm100::swz_chunk_offset(r, cchunk));
-      const float4 gg = *reinterpret_cast<const float4*>(smGate + ((q * 32 + r) >> 4) * D + col);
+      const float4 gg = it < 4 ? g_lo : g_hi;
       float4 o = xr[half][it];
       o.x += gg.x * (a.x + bb.x); o.y += gg.y * (a.y + bb.y);
       o.z += gg.z * (a.z + bb.z); o.w += gg.w * (a.w + bb.w);

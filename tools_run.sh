@@ -1,7 +1,8 @@
-set -x
-timeout 1200 python -m pytest tests -m gpu -q -x --timeout=600 -p no:cacheprovider 2>&1 | tail -3
-timeout 900 python bench.py > gpurun_out/bench_r02_default.json 2> gpurun_out/bench_r02_default.err; tail -c 600 gpurun_out/bench_r02_default.json
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r02_reference.json 2> gpurun_out/bench_r02_reference.err; tail -c 400 gpurun_out/bench_r02_reference.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/r02_ncu_launches.csv python bench.py --batch 1184 --chunk 1184 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-prof > gpurun_out/ncu_b1.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none --cache-control none -k regex:dit_blocks --launch-skip 60 --launch-count 1 -o gpurun_out/r02_prof_dit_blocks -f python bench.py --batch 1184 --chunk 1184 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-prof > gpurun_out/ncu_b2.log 2>&1
-ls -la gpurun_out | tail -8
+timeout 900 python -m pytest tests/test_gpu_dit.py -m gpu -q -x --timeout=300 -p no:cacheprovider 2>&1 | tail -2
+timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-prof > gpurun_out/bench_mega1.json 2>> gpurun_out/sweep.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_mega1.json"))
+print("mega value", round(d["value"]), "ms", d["ms_per_step"])
+PY
+python tools/kernel_timeline.py 1184 2>&1 | grep -A1 "^mlp1\|^qkv" | grep "\["
