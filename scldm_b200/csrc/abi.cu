@@ -41,6 +41,7 @@ std::vector<cudaEvent_t> g_prof_pool;
 bool g_prof_on = false;
 const bool g_use_mega = []{ const char* e = getenv("SCLDM_MEGA"); return !(e && e[0] == '0'); }();  // SCLDM_MEGA=0: one kernel per block half
 int g_num_sms = 148;
+const bool g_use_pair = []{ const char* e = getenv("SCLDM_PAIR"); return e && e[0] == '1'; }();   // SCLDM_PAIR=1: cta_group::2 CTA pairs
 const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? atoi(e) : 4500; }();   // start offset step of the persistent CTAs (cycles)
 const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
 cudaStream_t g_prof_stream = nullptr;
@@ -76,14 +77,27 @@ inline void prof_end() {
 // first weight loads) while the preceding kernel drains; the kernel itself orders its dependent accesses with
 // griddepcontrol.wait.  Plain launch while per-kernel event timing is on.
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline void launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = (g_prof_on || !g_use_pdl) ? 0 : 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {   // thread-block clusters (CTA pairs for cta_group::2)
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (!g_prof_on && g_use_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_ex(kern, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -207,8 +221,14 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
     bp.dbg = g_dbg_clk; bp.dbg_layer = g_dbg_layer; bp.stagger_cycles = g_stagger;
     bp.attn_w_stride = 4LL * dit::D * dit::D;
     bp.mlp_w_stride = ((long long)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs) * dit::B_SLAB_ELEMS;
+    if (g_use_pair && row_tiles % 2 == 0) {   // CTA pairs share every weight slab (cta_group::2)
+      int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
+      grid &= ~1;
+      LAUNCH("dit_blocks", launch_ex(dit::dit_blocks_kernel<true>, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, 2, bp));
+      return SCLDM_OK;
+    }
     const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
-    LAUNCH("dit_blocks", launch_pdl(dit::dit_blocks_kernel, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, bp));
+    LAUNCH("dit_blocks", launch_pdl(dit::dit_blocks_kernel<false>, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, bp));
     return SCLDM_OK;
   }
   for (int l = 0; l < w->n_layer; ++l) {
@@ -317,7 +337,8 @@ int prepare_kernels() {
   if ((rc = set_smem(dit::gemm_astream_resid_kernel, dit::astream_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::mlp_fused_kernel, dit::mlp_fused_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::attn_block_kernel, dit::attn_block_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::dit_blocks_kernel, dit::phase_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::dit_blocks_kernel<false>, dit::phase_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::dit_blocks_kernel<true>, dit::phase_smem_bytes()))) return rc;
   {
     int dev = 0, n = 0;
     CUDA_OK(cudaGetDevice(&dev));

@@ -742,7 +742,7 @@ constexpr int PH_OFF_MID = KSLABS_D * A_SLAB_BYTES;       // 64 KB
 constexpr int PH_OFF_RING = PH_OFF_MID + 4 * A_SLAB_BYTES; // 128 KB
 constexpr int PH_OFF_BIASQ = PH_OFF_RING + 96 * 1024;      // 224 KB
 constexpr int PH_OFF_BARS = PH_OFF_BIASQ + D * 4;
-constexpr int PH_BARS_PER_SET = 20;
+constexpr int PH_BARS_PER_SET = 40;
 constexpr int PH_OFF_TMEMPTR = PH_OFF_BARS + 2 * PH_BARS_PER_SET * 8;   // set 0: attention phase, set 1: MLP phase
 constexpr size_t phase_smem_bytes() { return PH_OFF_TMEMPTR + 64; }
 static_assert(phase_smem_bytes() <= 232448, "exceeds the 227 KB dynamic shared memory limit");
@@ -773,42 +773,88 @@ struct PhaseSeq {
   uint32_t odd;     // (previous executions of this phase type) & 1
   uint32_t tma;     // (previous executions with x_tma) & 1
 };
+// Barrier indices inside a set (40 slots): ring full[8] | empty[8] | pfull[8] (pair mode: "the peer's half of the stage
+// landed", forwarded to the leader), then the phase's own barriers.
+enum { BI_FULL = 0, BI_EMPTY = 8, BI_PFULL = 16,
+       BA_A_READY = 24, BA_ACCQ_FULL = 25, BA_ACCQ_FREE = 26, BA_AO_READY = 27, BA_AO_FREE = 28, BA_ACCP_FULL = 29, BA_X_FULL = 30, BA_X_EMPTY = 34,
+       BM_A_READY = 24, BM_ACC1_FULL = 25, BM_ACC1_FREE = 26, BM_H_READY = 27, BM_H_FREE = 29, BM_ACC2_FULL = 31, BM_X_FULL = 32, BM_X_EMPTY = 36 };
+
+// Synchronisation policy of a phase: one CTA per tile (cta_group::1) or a CTA pair sharing every weight slab (cta_group::2,
+// see sm100.cuh).  In pair mode the warps of both CTAs arrive on the LEADER's worker->MMA barriers and the leader's commits
+// arrive on the MMA->worker barriers of both CTAs.
+template <bool PAIR>
+struct Cg {
+  static constexpr uint32_t WORKER_ARRIVALS = PAIR ? 2 * EPI_WARPS : EPI_WARPS;
+  __device__ static __forceinline__ void commit(uint64_t* bar) {
+    if constexpr (PAIR) sm100::umma_commit2(bar); else sm100::umma_commit(bar);
+  }
+  __device__ static __forceinline__ void arrive_mma(uint64_t* bar) {      // a worker warp (one lane) -> the MMA issuer
+    if constexpr (PAIR) sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(bar), 0)); else sm100::mbar_arrive(bar);
+  }
+  __device__ static __forceinline__ void arrive_both(uint64_t* bar) {     // the MMA issuer -> this barrier in every CTA of the group
+    if constexpr (PAIR) { sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(bar), 0)); sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(bar), 1)); }
+    else sm100::mbar_arrive(bar);
+  }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if constexpr (PAIR) sm100::umma_bf16_ss2(d, a, b, idesc, acc); else sm100::umma_bf16_ss(d, a, b, idesc, acc);
+  }
+  __device__ static __forceinline__ uint32_t rank() { if constexpr (PAIR) return sm100::cluster_ctarank(); else return 0; }
+};
+
+template <bool PAIR>
+__device__ __forceinline__ void issue_slab_mmas_cg(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool first_slab) {
+  const uint64_t a_desc = sm100::make_kmajor_sw128_desc(a_smem);
+  const uint64_t b_desc = sm100::make_kmajor_sw128_desc(b_smem);
+#pragma unroll
+  for (uint32_t k = 0; k < BLOCK_K / 16; ++k) Cg<PAIR>::mma(tmem_d, a_desc + 2ull * k, b_desc + 2ull * k, idesc, (first_slab && k == 0) ? 0u : 1u);
+}
+
+template <bool PAIR>
 __device__ __forceinline__ void phase_barriers_init(uint8_t* smem) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS);
   const uint32_t lane = threadIdx.x & 31;
   if ((threadIdx.x >> 5) == 0) {
-    if (lane < PH_BARS_PER_SET) {
-      // attention set: full[4] empty[4] a_ready accq_full accq_free ao_ready ao_free accp_full x_full[4] x_empty[2]
-      const uint32_t ca = (lane == 8 || lane == 10 || lane == 11) ? EPI_WARPS : (lane >= 18 ? XPASS_WARPS : 1);
-      sm100::mbar_init(&bars[lane], ca);
-      // MLP set: full[3] empty[3] a_ready acc1_full acc1_free h_ready[2] h_free[2] acc2_full x_full[4] x_empty[2]
-      const uint32_t cm = (lane == 6 || lane == 8 || lane == 9 || lane == 10) ? EPI_WARPS : (lane >= 18 ? XPASS_WARPS : 1);
-      sm100::mbar_init(&bars[PH_BARS_PER_SET + lane], cm);
+    for (uint32_t i = lane; i < PH_BARS_PER_SET; i += 32) {
+      const uint32_t W = Cg<PAIR>::WORKER_ARRIVALS;
+      const uint32_t ca = (i == BA_A_READY || i == BA_ACCQ_FREE || i == BA_AO_READY) ? W : ((i == BA_X_EMPTY || i == BA_X_EMPTY + 1) ? XPASS_WARPS : 1);
+      sm100::mbar_init(&bars[i], ca);
+      const uint32_t cm = (i == BM_A_READY || i == BM_ACC1_FREE || i == BM_H_READY || i == BM_H_READY + 1) ? W
+                                                                                                         : ((i == BM_X_EMPTY || i == BM_X_EMPTY + 1) ? XPASS_WARPS : 1);
+      sm100::mbar_init(&bars[PH_BARS_PER_SET + i], cm);
     }
     sm100::fence_barrier_init();
   }
 }
 
+// Weight-ring geometry of a phase.  Pair mode: every item is half as big (this CTA's half of the B rows), so the 96 KB ring
+// holds six 16 KB stages in both phases; buffers 4,5 carry no residual rows and take the items issued during setup.
+template <bool PAIR> struct MlpRing { static constexpr uint32_t NST = PAIR ? 6 : 3, STAGE = PAIR ? 16384 : 32768, FREE0 = PAIR ? 4 : 2, EARLY = PAIR ? 2 : 1; };
+template <bool PAIR> struct AttnRing { static constexpr uint32_t NST = PAIR ? 6 : 4, STAGE = PAIR ? 16384 : 24576, FREE0 = PAIR ? 4 : 3, EARLY = PAIR ? 2 : 1; };
+
 // One MLP half on the CTA's tile.  Entry: every thread of the CTA, previous phase complete (CTA-wide barrier passed),
 // TMEM allocated.  x_tma: the tile's rows are fetched by TMA (otherwise the previous phase stashed them).  STASH: leave
 // the updated rows in shared memory for the next phase.  Exit: CTA-wide barrier passed, all async work retired.
-template <bool STASH>
+template <bool STASH, bool PAIR>
 __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile, uint8_t* smem, uint32_t tmem_base, bool x_tma, PhaseSeq seq) {
-  constexpr uint32_t NSTAGE = 3;
-  uint8_t* smA = smem;                                     // 4 x 16 KB (later: epilogue staging + gates)
+  using R = MlpRing<PAIR>;
+  using G = Cg<PAIR>;
+  constexpr uint32_t NSTAGE = R::NST;
+  uint8_t* smA = smem;                                     // 4 x 16 KB (later: epilogue staging)
   uint8_t* smH = smem + PH_OFF_MID;                        // 2 x (2 x 16 KB); first the X pass buffers / stash
-  uint8_t* smB = smem + PH_OFF_RING;                       // NSTAGE x 32 KB
+  uint8_t* smB = smem + PH_OFF_RING;                       // NSTAGE stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS) + PH_BARS_PER_SET;
-  uint64_t* full = bars;                  // [3]
-  uint64_t* empty = bars + 3;             // [3]
-  uint64_t* a_ready = bars + 6;
-  uint64_t* acc1_full = bars + 7;
-  uint64_t* acc1_free = bars + 8;
-  uint64_t* h_ready = bars + 9;           // [2]
-  uint64_t* h_free = bars + 11;           // [2]
-  uint64_t* acc2_full = bars + 13;
-  uint64_t* x_full = bars + 14;           // [4]
-  uint64_t* x_empty = bars + 18;          // [2]
+  uint64_t* full = bars + BI_FULL;
+  uint64_t* empty = bars + BI_EMPTY;
+  uint64_t* pfull = bars + BI_PFULL;
+  uint64_t* a_ready = bars + BM_A_READY;
+  uint64_t* acc1_full = bars + BM_ACC1_FULL;
+  uint64_t* acc1_free = bars + BM_ACC1_FREE;
+  uint64_t* h_ready = bars + BM_H_READY;           // [2]
+  uint64_t* h_free = bars + BM_H_FREE;             // [2]
+  uint64_t* acc2_full = bars + BM_ACC2_FULL;
+  uint64_t* x_full = bars + BM_X_FULL;             // [4]
+  uint64_t* x_empty = bars + BM_X_EMPTY;           // [2]
+  auto ring_ptr = [&](uint32_t stage) { return smB + ((stage + R::FREE0) % NSTAGE) * R::STAGE; };
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.n_chunks;
@@ -816,11 +862,15 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
   const uint32_t po = seq.odd, px = seq.tma;
   // parity shifts of the barriers that complete T (acc1) or about T/2 (H buffer b) times per execution
   const uint32_t pt = po & (uint32_t)(T & 1);
-  const uint32_t ph[2] = {po & (uint32_t)(((T + 1) >> 1) & 1), po & (uint32_t)((T >> 1) & 1)};
+  const uint32_t ph0 = po & (uint32_t)(((T + 1) >> 1) & 1), ph1 = po & (uint32_t)((T >> 1) & 1);
+  // this CTA's share of weight slab i (pair mode: rows [128 rank, 128 rank + 128) = the rank-th half of its bytes)
+  auto slab_src = [&](int i) { return reinterpret_cast<const uint8_t*>(p.Wstream) + (size_t)i * B_SLAB_BYTES + G::rank() * R::STAGE; };
   if (threadIdx.x == 0) {
-    // first loads: weight slab 0 into the ring buffer that carries no residual rows, then (x_tma) all four X passes
-    sm100::mbar_arrive_expect_tx(&full[0], B_SLAB_BYTES);
-    sm100::bulk_g2s(smB + ring_buf(0) * B_SLAB_BYTES, p.Wstream, B_SLAB_BYTES, &full[0]);
+    // first loads: the first slab(s) into the ring buffers that carry no residual rows, then (x_tma) all four X passes
+    for (uint32_t i = 0; i < R::EARLY; ++i) {
+      sm100::mbar_arrive_expect_tx(&full[i], R::STAGE);
+      sm100::bulk_g2s(ring_ptr(i), slab_src(i), R::STAGE, &full[i]);
+    }
     if (x_tma) producer_issue_x_passes(p.X, row_tile, smH, smB, x_full);
     else stash_write_back(p.X + (size_t)row_tile * BLOCK_M * D, smH);
   }
@@ -832,18 +882,21 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
   const int padded = rounds * (int)NSTAGE;                     // ring completions incl. the hand-made ones
 
   if (warp == 0) {
-    // ===================== producer: X passes, then one linear stream of weight slabs =======
+    // ===================== producer: one linear stream of weight slabs =======================
     if (lane == 0) {
       RingState rs;
-      rs.advance(NSTAGE);   // slab 0 was issued during setup
-      for (int i = 1; i < total; ++i) {
-        if (i == 1 || i == 2) sm100::mbar_wait(&x_empty[i - 1], po);  // first use of a ring buffer that carried residual rows
-        if (i == 1 && !x_tma) sm100::bulk_wait_read<1>();             // ... and the write-back has read rows 64-127 too
-        if (i == 3 && !x_tma) sm100::bulk_wait_read<0>();             // rows 0-63 (H buffers) read before E1_0 can be reached
-        if (i == SCLDM_WB_ITEM && !x_tma) sm100::bulk_wait<0>();      // write-back complete long before this phase's epilogue re-reads X
+      for (uint32_t i = 0; i < R::EARLY; ++i) rs.advance(NSTAGE);   // issued during setup
+      for (int i = R::EARLY; i < total; ++i) {
+        if (i == (int)R::EARLY) {                                   // first use of ring buffers that carried residual rows
+          sm100::mbar_wait(&x_empty[0], po);
+          sm100::mbar_wait(&x_empty[1], po);
+          if (!x_tma) sm100::bulk_wait_read<1>();                   // ... and the write-back has read rows 64-127 too
+        }
+        if (i == KSLABS_D - 1 && !x_tma) sm100::bulk_wait_read<0>();   // rows 0-63 (H buffers) read before M1_0 can complete, i.e. before E1_0
+        if (i == SCLDM_WB_ITEM && !x_tma) sm100::bulk_wait<0>();       // write-back complete long before the epilogue re-reads X
         sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
-        sm100::mbar_arrive_expect_tx(&full[rs.stage], B_SLAB_BYTES);
-        sm100::bulk_g2s(smB + ring_buf(rs.stage) * B_SLAB_BYTES, p.Wstream + (size_t)i * B_SLAB_ELEMS, B_SLAB_BYTES, &full[rs.stage]);
+        sm100::mbar_arrive_expect_tx(&full[rs.stage], R::STAGE);
+        sm100::bulk_g2s(ring_ptr(rs.stage), slab_src(i), R::STAGE, &full[rs.stage]);
         rs.advance(NSTAGE);
       }
       for (int i = total; i < padded; ++i) {   // hand-made completions: every ring barrier ends the phase at parity 0
@@ -853,47 +906,58 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =======================================================
-    if (lane == 0) {
-      const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && G::rank() == 0) {
+      // ===================== MMA issuer (pair mode: the leader CTA, for both CTAs) ==========
+      const uint32_t idesc = sm100::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       const uint32_t acc1 = tmem_base, acc2 = tmem_base + BLOCK_N;
       dbg_stamp(p.dbg, 1);
       sm100::mbar_wait(a_ready, po);
       sm100::tc_fence_after();
       dbg_stamp(p.dbg, 2);
       RingState rs;
+      auto wait_stage = [&]() {
+        sm100::mbar_wait(&full[rs.stage], rs.phase);
+        if constexpr (PAIR) sm100::mbar_wait(&pfull[rs.stage], rs.phase);
+        sm100::tc_fence_after();
+      };
       for (int j = 0; j <= T; ++j) {
         if (j < T) {  // M1_j
           if (j > 0) { sm100::mbar_wait(acc1_free, ((j - 1) & 1) ^ pt); sm100::tc_fence_after(); }
           for (int ks = 0; ks < KSLABS_D; ++ks) {
-            sm100::mbar_wait(&full[rs.stage], rs.phase);
-            sm100::tc_fence_after();
-            issue_slab_mmas(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smB + ring_buf(rs.stage) * B_SLAB_BYTES), idesc, ks == 0);
-            sm100::umma_commit(&empty[rs.stage]);
+            wait_stage();
+            issue_slab_mmas_cg<PAIR>(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc, ks == 0);
+            G::commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
           }
-          sm100::umma_commit(acc1_full);
+          G::commit(acc1_full);
         }
         if (j >= 1) {  // M2_{j-1}
           const int c = j - 1, b = c & 1;
-          sm100::mbar_wait(&h_ready[b], ((c >> 1) & 1) ^ ph[b]);
+          sm100::mbar_wait(&h_ready[b], ((c >> 1) & 1) ^ (b ? ph1 : ph0));
           sm100::tc_fence_after();
           const int ns = m2_slabs(c);
           for (int s2 = 0; s2 < ns; ++s2) {
-            sm100::mbar_wait(&full[rs.stage], rs.phase);
-            sm100::tc_fence_after();
-            issue_slab_mmas(acc2, sm100::smem_u32(smH + (b * 2 + s2) * A_SLAB_BYTES), sm100::smem_u32(smB + ring_buf(rs.stage) * B_SLAB_BYTES), idesc,
-                            c == 0 && s2 == 0);
-            sm100::umma_commit(&empty[rs.stage]);
+            wait_stage();
+            issue_slab_mmas_cg<PAIR>(acc2, sm100::smem_u32(smH + (b * 2 + s2) * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc,
+                                     c == 0 && s2 == 0);
+            G::commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
           }
-          sm100::umma_commit(&h_free[b]);
+          G::commit(&h_free[b]);
         }
       }
-      sm100::umma_commit(acc2_full);
+      G::commit(acc2_full);
       for (int i = total; i < padded; ++i) {   // consume the hand-made ring completions
+        wait_stage();
+        G::arrive_both(&empty[rs.stage]);
+        rs.advance(NSTAGE);
+      }
+    } else if (PAIR && lane == 0) {
+      // ===================== pair mode, second CTA: tell the leader when this CTA's half of a stage has landed ====
+      RingState rs;
+      for (int i = 0; i < padded; ++i) {
         sm100::mbar_wait(&full[rs.stage], rs.phase);
-        sm100::mbar_arrive(&empty[rs.stage]);
+        sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(&pfull[rs.stage]), 0));
         rs.advance(NSTAGE);
       }
     }
@@ -904,7 +968,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
     ln_prologue_tma(smH, smB, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px);
     sm100::fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) sm100::mbar_arrive(a_ready);
+    if (lane == 0) G::arrive_mma(a_ready);
     if (etid == 0) dbg_stamp(p.dbg, 3);
 
     // ---------- E1_j: SwiGLU of hidden chunk j into the A slabs of M2_j ----------
@@ -920,9 +984,9 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
       sm100::tmem_ld_wait();
       sm100::tc_fence_before();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(acc1_free);          // M1_{j+1} may overwrite acc1
+      if (lane == 0) G::arrive_mma(acc1_free);               // M1_{j+1} may overwrite acc1
       const int b = j & 1;
-      if (j >= 2) sm100::mbar_wait(&h_free[b], (((j >> 1) - 1) & 1) ^ ph[b]);   // M2_{j-2} finished reading this buffer
+      if (j >= 2) sm100::mbar_wait(&h_free[b], (((j >> 1) - 1) & 1) ^ (b ? ph1 : ph0));   // M2_{j-2} finished reading this buffer
       uint8_t* buf = smH + (b * 2 + hs) * A_SLAB_BYTES;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -938,7 +1002,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
       }
       sm100::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&h_ready[b]);
+      if (lane == 0) G::arrive_mma(&h_ready[b]);
       if (etid == 0 && j < 6) dbg_stamp(p.dbg, 5 + 2 * j);
     }
 
@@ -966,14 +1030,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
   if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
   if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
-  phase_barriers_init(smem);
+  phase_barriers_init<false>(smem);
   sm100::grid_dep_launch();
   sm100::grid_dep_wait();   // X and the modulation table come from the preceding kernels
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  mlp_phase<false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
+  mlp_phase<false, false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
   if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
 }
 
@@ -1163,19 +1227,19 @@ struct AttnBlockParams {
 
 constexpr int AB_HP = 4;                        // head pairs
 constexpr int AB_QN = 192;                      // accumulator columns per head pair: q | k | v, 64 each
-constexpr uint32_t AB_NSTAGE = 4;
-constexpr int AB_STAGE_BYTES = AB_QN * BLOCK_K * 2;     // 24 KB
 constexpr int AB_Q_ITEM_BYTES = AB_QN * BLOCK_K * 2;    // 24 KB
 constexpr int AB_P_ITEM_BYTES = 128 * BLOCK_K * 2;      // 16 KB
 constexpr size_t attn_block_smem_bytes() { return phase_smem_bytes(); }
-static_assert(AB_NSTAGE * AB_STAGE_BYTES == PH_OFF_BIASQ - PH_OFF_RING, "weight ring fills [128K, 224K)");
-static_assert(2 * XPASS_BYTES <= (AB_NSTAGE - 1) * AB_STAGE_BYTES, "residual rows alias ring buffers 0-2; buffer 3 is free from the start");
-// logical ring stage -> physical buffer: the first item lands in buffer 3, which carries no residual rows
-__device__ __forceinline__ uint32_t ab_ring_buf(uint32_t stage) { return (stage + 3u) & 3u; }
 
 // One attention half on the CTA's tile; same entry / exit contract as mlp_phase.
-template <bool STASH>
+template <bool STASH, bool PAIR>
 __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_tile, uint8_t* smem, uint32_t tmem_base, bool x_tma, PhaseSeq seq) {
+  using R = AttnRing<PAIR>;
+  using G = Cg<PAIR>;
+  constexpr uint32_t NSTAGE = R::NST;
+  constexpr uint32_t Q_BYTES = AB_Q_ITEM_BYTES / (PAIR ? 2 : 1), P_BYTES = AB_P_ITEM_BYTES / (PAIR ? 2 : 1);   // this CTA's share of an item
+  constexpr int N_ITEMS = AB_HP * (KSLABS_D + 2);
+  static_assert(N_ITEMS % NSTAGE == 0 && ((N_ITEMS / NSTAGE) & 1) == 0, "every ring barrier must complete an even number of times per phase");
   uint8_t* smA = smem;
   uint8_t* smQKV = smem + PH_OFF_MID;     // q | k | v slabs of the current head pair; first residual rows 0-63
   uint8_t* smAO = smQKV + 3 * A_SLAB_BYTES;
@@ -1184,24 +1248,31 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
   float* smBiasP = smGate + 8 * D;
   float* smBiasQ = reinterpret_cast<float*>(smem + PH_OFF_BIASQ);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS);
-  uint64_t* full = bars;                  // [4]
-  uint64_t* empty = bars + 4;             // [4]
-  uint64_t* a_ready = bars + 8;
-  uint64_t* accq_full = bars + 9;
-  uint64_t* accq_free = bars + 10;
-  uint64_t* ao_ready = bars + 11;
-  uint64_t* ao_free = bars + 12;
-  uint64_t* accp_full = bars + 13;
-  uint64_t* x_full = bars + 14;           // [4]
-  uint64_t* x_empty = bars + 18;          // [2]
+  uint64_t* full = bars + BI_FULL;
+  uint64_t* empty = bars + BI_EMPTY;
+  uint64_t* pfull = bars + BI_PFULL;
+  uint64_t* a_ready = bars + BA_A_READY;
+  uint64_t* accq_full = bars + BA_ACCQ_FULL;
+  uint64_t* accq_free = bars + BA_ACCQ_FREE;
+  uint64_t* ao_ready = bars + BA_AO_READY;
+  uint64_t* ao_free = bars + BA_AO_FREE;
+  uint64_t* accp_full = bars + BA_ACCP_FULL;
+  uint64_t* x_full = bars + BA_X_FULL;             // [4]
+  uint64_t* x_empty = bars + BA_X_EMPTY;           // [2]
+  auto ring_ptr = [&](uint32_t stage) { return smW + ((stage + R::FREE0) % NSTAGE) * R::STAGE; };
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) dbg_stamp(p.dbg, 0);
   const uint32_t po = seq.odd, px = seq.tma;
+  // item i of the stream: Q items (4 per head pair) and P items (2 per head pair) in the order Q0 Q1 P0 Q2 P1 Q3 P2 P3.
+  // The producer walks them with a running source pointer; in pair mode it takes the rank-th half of every item.
   if (threadIdx.x == 0) {
-    // weight item 0 goes into the ring buffer that carries no residual rows; then (x_tma) all four X passes
-    sm100::mbar_arrive_expect_tx(&full[0], AB_Q_ITEM_BYTES);
-    sm100::bulk_g2s(smW + ab_ring_buf(0) * AB_STAGE_BYTES, p.Wstream, AB_Q_ITEM_BYTES, &full[0]);
+    // the first item(s) go into the ring buffers that carry no residual rows; then (x_tma) all four X passes
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wstream);
+    for (uint32_t i = 0; i < R::EARLY; ++i) {   // R::EARLY <= 4: these are Q items of head pair 0
+      sm100::mbar_arrive_expect_tx(&full[i], Q_BYTES);
+      sm100::bulk_g2s(ring_ptr(i), src + (size_t)i * AB_Q_ITEM_BYTES + G::rank() * Q_BYTES, Q_BYTES, &full[i]);
+    }
     if (x_tma) producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
     else stash_write_back(p.X + (size_t)row_tile * BLOCK_M * D, smQKV);
   }
@@ -1210,70 +1281,82 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
     // ===================== producer: one linear stream of weight items ======================
     if (lane == 0) {
       RingState rs;
+      const uint32_t rank = G::rank();
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wstream);
       int item = 0;
-      auto issue = [&](uint32_t bytes) {
-        if (item == 1) {                      // buffers 0-2 carried residual rows 64-127
+      auto issue = [&](uint32_t item_bytes, uint32_t my_bytes) {
+        if (item == (int)R::EARLY) {          // first use of ring buffers that carried residual rows 64-127
           sm100::mbar_wait(&x_empty[0], po);
           sm100::mbar_wait(&x_empty[1], po);
           if (!x_tma) sm100::bulk_wait_read<1>();   // ... and the write-back has read them too
         }
-        if (item == 3 && !x_tma) sm100::bulk_wait_read<0>();   // rows 0-63 (q/k/v staging) read before the first head pair can be staged
-        if (item == SCLDM_WB_ITEM && !x_tma) sm100::bulk_wait<0>();   // write-back complete long before this phase's epilogue re-reads X
-        if (item > 0) {                       // item 0 was issued during setup
+        if (item == KSLABS_D - 1 && !x_tma) sm100::bulk_wait_read<0>();   // rows 0-63 (q/k/v staging) read before Q_0 can complete
+        if (item == SCLDM_WB_ITEM && !x_tma) sm100::bulk_wait<0>();       // write-back complete long before this phase's epilogue re-reads X
+        if (item >= (int)R::EARLY) {          // the first items were issued during setup
           sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
-          sm100::mbar_arrive_expect_tx(&full[rs.stage], bytes);
-          sm100::bulk_g2s(smW + ab_ring_buf(rs.stage) * AB_STAGE_BYTES, src, bytes, &full[rs.stage]);
+          sm100::mbar_arrive_expect_tx(&full[rs.stage], my_bytes);
+          sm100::bulk_g2s(ring_ptr(rs.stage), src + rank * my_bytes, my_bytes, &full[rs.stage]);
         }
-        src += bytes;
+        src += item_bytes;
         ++item;
-        rs.advance(AB_NSTAGE);
+        rs.advance(NSTAGE);
       };
       for (int step = 0; step <= AB_HP; ++step) {
         if (step < AB_HP)
-          for (int ks = 0; ks < KSLABS_D; ++ks) issue(AB_Q_ITEM_BYTES);
+          for (int ks = 0; ks < KSLABS_D; ++ks) issue(AB_Q_ITEM_BYTES, Q_BYTES);
         if (step >= 1)
-          for (int half = 0; half < 2; ++half) issue(AB_P_ITEM_BYTES);
+          for (int half = 0; half < 2; ++half) issue(AB_P_ITEM_BYTES, P_BYTES);
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =======================================================
-    if (lane == 0) {
-      const uint32_t idesc_q = sm100::make_idesc_bf16(BLOCK_M, AB_QN);
-      const uint32_t idesc_p = sm100::make_idesc_bf16(BLOCK_M, 128);
+    if (lane == 0 && G::rank() == 0) {
+      // ===================== MMA issuer (pair mode: the leader CTA, for both CTAs) ==========
+      const uint32_t idesc_q = sm100::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, AB_QN);
+      const uint32_t idesc_p = sm100::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, 128);
       const uint32_t accq = tmem_base, accp = tmem_base + 256;
       dbg_stamp(p.dbg, 1);
       sm100::mbar_wait(a_ready, po);
       sm100::tc_fence_after();
       dbg_stamp(p.dbg, 2);
       RingState rs;
+      auto wait_stage = [&]() {
+        sm100::mbar_wait(&full[rs.stage], rs.phase);
+        if constexpr (PAIR) sm100::mbar_wait(&pfull[rs.stage], rs.phase);
+        sm100::tc_fence_after();
+      };
       for (int step = 0; step <= AB_HP; ++step) {
         if (step < AB_HP) {  // Q_step
           if (step > 0) { sm100::mbar_wait(accq_free, (step - 1) & 1); sm100::tc_fence_after(); }
           for (int ks = 0; ks < KSLABS_D; ++ks) {
-            sm100::mbar_wait(&full[rs.stage], rs.phase);
-            sm100::tc_fence_after();
-            issue_slab_mmas(accq, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(smW + ab_ring_buf(rs.stage) * AB_STAGE_BYTES), idesc_q, ks == 0);
-            sm100::umma_commit(&empty[rs.stage]);
-            rs.advance(AB_NSTAGE);
+            wait_stage();
+            issue_slab_mmas_cg<PAIR>(accq, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc_q, ks == 0);
+            G::commit(&empty[rs.stage]);
+            rs.advance(NSTAGE);
           }
-          sm100::umma_commit(accq_full);
+          G::commit(accq_full);
         }
         if (step >= 1) {  // P_{step-1}
           const int hp = step - 1;
           sm100::mbar_wait(ao_ready, hp & 1);
           sm100::tc_fence_after();
           for (int half = 0; half < 2; ++half) {
-            sm100::mbar_wait(&full[rs.stage], rs.phase);
-            sm100::tc_fence_after();
-            issue_slab_mmas(accp + half * 128, sm100::smem_u32(smAO), sm100::smem_u32(smW + ab_ring_buf(rs.stage) * AB_STAGE_BYTES), idesc_p, hp == 0);
-            sm100::umma_commit(&empty[rs.stage]);
-            rs.advance(AB_NSTAGE);
+            wait_stage();
+            issue_slab_mmas_cg<PAIR>(accp + half * 128, sm100::smem_u32(smAO), sm100::smem_u32(ring_ptr(rs.stage)), idesc_p, hp == 0);
+            G::commit(&empty[rs.stage]);
+            rs.advance(NSTAGE);
           }
-          sm100::umma_commit(ao_free);
+          G::commit(ao_free);
         }
       }
-      sm100::umma_commit(accp_full);
+      G::commit(accp_full);
+    } else if (PAIR && lane == 0) {
+      // ===================== pair mode, second CTA: tell the leader when this CTA's half of a stage has landed ====
+      RingState rs;
+      for (int i = 0; i < N_ITEMS; ++i) {
+        sm100::mbar_wait(&full[rs.stage], rs.phase);
+        sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(&pfull[rs.stage]), 0));
+        rs.advance(NSTAGE);
+      }
     }
   } else {
     // ===================== 16 worker warps ==================================================
@@ -1282,7 +1365,7 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
     ln_prologue_tma(smQKV, smW, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px);
     sm100::fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) sm100::mbar_arrive(a_ready);
+    if (lane == 0) G::arrive_mma(a_ready);
     // gate / bias vectors: needed by the final epilogue only; the loads are issued now and parked in shared memory then
     const int gcell = etid >> 6, gc4 = etid & 63;
     const float4 gate_v = *reinterpret_cast<const float4*>(p.mod + (size_t)p.slot_mod.row(row_tile * 8 + gcell) * p.mod_stride + p.mod_off_gate + gc4 * 4);
@@ -1305,7 +1388,7 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
       sm100::tmem_ld_wait();
       sm100::tc_fence_before();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(accq_free);          // Q_{hp+1} may overwrite the accumulator
+      if (lane == 0) G::arrive_mma(accq_free);               // Q_{hp+1} may overwrite the accumulator
       sm100::named_bar_sync(1, EPI_THREADS);
 #pragma unroll
       for (int c8 = 0; c8 < 6; ++c8) {
@@ -1340,7 +1423,7 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
       }
       sm100::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(ao_ready);
+      if (lane == 0) G::arrive_mma(ao_ready);
       if (etid == 0) dbg_stamp(p.dbg, 6 + 3 * hp);
     }
 
@@ -1366,14 +1449,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
   if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
   if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
-  phase_barriers_init(smem);
+  phase_barriers_init<false>(smem);
   sm100::grid_dep_launch();
   sm100::grid_dep_wait();   // X and the modulation table come from the preceding kernels
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  attn_phase<false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
+  attn_phase<false, false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
   if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
 }
 
@@ -1393,32 +1476,39 @@ struct BlocksParams {
   int stagger_cycles;                      // CTA b starts (b % 8) * stagger_cycles late: see dit_blocks_kernel
 };
 
+// PAIR: launched as clusters of two CTAs (cudaLaunchAttributeClusterDimension = 2); the pair works on two adjacent tiles
+// with cta_group::2 MMAs, so every weight slab is fetched once per pair (half per SM).  Needs an even number of tiles.
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const BlocksParams bp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
-  if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
-  phase_barriers_init(smem);
+  if ((threadIdx.x >> 5) == 1) {
+    if constexpr (PAIR) sm100::tmem_alloc2(tmem_ptr_smem, 512); else sm100::tmem_alloc(tmem_ptr_smem, 512);
+  }
+  phase_barriers_init<PAIR>(smem);
   sm100::grid_dep_launch();
   sm100::grid_dep_wait();
   sm100::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) sm100::cluster_sync_all(); else __syncthreads();   // barriers of both CTAs exist before any remote arrive
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // Every tile costs the same, so CTAs launched together would stay in lock-step and hit the L2-bound stretches (the
-  // residual read-modify-write above all) at the same moment on all SMs.  A one-off start offset per CTA keeps them
-  // out of phase for the rest of the kernel.
+  // Every tile costs the same, so CTAs launched together would stay in lock-step and hit the L2-bound stretches at the same
+  // moment on all SMs.  An optional one-off start offset per CTA (pair) keeps them out of phase for the rest of the kernel.
+  const int group = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, n_groups = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int per_group = PAIR ? 2 : 1, rank = (int)Cg<PAIR>::rank();
   if (bp.stagger_cycles > 0) {
     if (threadIdx.x == 0) {
-      const long long t0 = clock64(), d = (long long)(blockIdx.x & 7) * bp.stagger_cycles;
+      const long long t0 = clock64(), d = (long long)(group & 7) * bp.stagger_cycles;
       while (clock64() - t0 < d) {}
     }
     __syncthreads();
   }
   int* smRows = reinterpret_cast<int*>(smem + PH_OFF_TMEMPTR + 16);   // conditioning row of each of the tile's 8 slots
   uint32_t n_attn = 0, n_mlp = 0, n_tma = 0;                          // executions so far (mbarrier parities, see PhaseSeq)
-  for (int tile = blockIdx.x; tile < bp.n_tiles; tile += gridDim.x) {
+  for (int t0 = group * per_group; t0 < bp.n_tiles; t0 += n_groups * per_group) {
+    const int tile = t0 + rank;
     // resolve the tile's slot -> conditioning-row indices once, so that the per-phase loads of the modulation vectors are
     // not behind a second dependent global load (visible to all warps after the first phase's setup barrier; the previous
     // tile's last phase ended with a CTA-wide barrier)
@@ -1433,9 +1523,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const Blocks
       ap.bias_q += (size_t)l * 3 * D;
       ap.bias_proj += (size_t)l * D;
       ap.mod_off_mul += l * 6 * D; ap.mod_off_add += l * 6 * D; ap.mod_off_gate += l * 6 * D;
-      const bool dbg_on = bp.dbg != nullptr && l == bp.dbg_layer && tile == (int)(blockIdx.x + gridDim.x);
+      const bool dbg_on = bp.dbg != nullptr && l == bp.dbg_layer && t0 == (group + n_groups) * per_group;
       ap.dbg = dbg_on ? bp.dbg : nullptr;
-      attn_phase<true>(ap, tile, smem, tmem_base, l == 0, PhaseSeq{n_attn & 1, n_tma & 1});
+      attn_phase<true, PAIR>(ap, tile, smem, tmem_base, l == 0, PhaseSeq{n_attn & 1, n_tma & 1});
       ++n_attn;
       if (l == 0) ++n_tma;
       MlpFusedParams mp = bp.mlp;
@@ -1443,12 +1533,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const Blocks
       mp.Wstream += (size_t)l * bp.mlp_w_stride;
       mp.mod_off_mul += l * 6 * D; mp.mod_off_add += l * 6 * D; mp.mod_off_gate += l * 6 * D;
       mp.dbg = dbg_on ? bp.dbg + 2 * (1 << 17) : nullptr;
-      if (l + 1 < bp.n_layer) mlp_phase<true>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
-      else mlp_phase<false>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
+      if (l + 1 < bp.n_layer) mlp_phase<true, PAIR>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
+      else mlp_phase<false, PAIR>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
       ++n_mlp;
     }
   }
-  if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
+  if constexpr (PAIR) sm100::cluster_sync_all();   // the peer's tensor core may still be reading this CTA's shared memory
+  if ((threadIdx.x >> 5) == 1) {
+    if constexpr (PAIR) sm100::tmem_dealloc2(tmem_base, 512); else sm100::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ==========================================================================================

@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "one_kernel_per_block_half": {"SCLDM_MEGA": "0"},
     "unfused_no_pdl": {"SCLDM_MEGA": "0", "SCLDM_FUSED_ATTN": "0", "SCLDM_FUSED_MLP": "0", "SCLDM_TC_FINAL": "0", "SCLDM_PDL": "0"},
+    # CTA pairs (cta_group::2 MMAs, every weight slab split over the two SMs of a cluster); used when the tile count is even
+    "cta_pairs": {"SCLDM_PAIR": "1"},
 }
 
 
@@ -20,7 +22,7 @@ VARIANTS = {
 def test_kernel_variant_matches_golden(name):
     env = dict(os.environ, **VARIANTS[name])
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_dit.py"), "-m", "gpu", "-q", "-x",
-                          "-p", "no:cacheprovider", "-k", "golden or intermediates or ode"],
+                          "-p", "no:cacheprovider", "-k", "golden or intermediates or ode or large_batch or batch_invariance"],
                          env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert " passed" in res.stdout

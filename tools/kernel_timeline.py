@@ -56,6 +56,10 @@ for k, name in enumerate(names):
     med = rel.nanmedian(0).values
     print(name, "n_cta", n_cta, "median cycles since CTA start per stamp:")
     print("   ", [(i, int(v)) for i, v in enumerate(med.tolist()) if v == v and i > 0 and not 28 <= i <= 30])
+    if os.environ.get("SCLDM_PAIR") == "1":   # stamps of a pair are relative to each CTA's own phase start: show leader / peer
+        for r, nm in ((0, "leader"), (1, "peer  ")):
+            m2 = rel[r::2].nanmedian(0).values
+            print("    ", nm, [(i, int(v)) for i, v in enumerate(m2.tolist()) if v == v and i > 0 and not 28 <= i <= 30])
     start_spread = (t[:, 0] - t[:, 0].min()).float()
     end = (t[:, 31] - t[:, 0].min()).float()
     g0, g1 = t[:, 29], t[:, 30]
