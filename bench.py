@@ -215,8 +215,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
+        # keep stdout to the single JSON line: NCCL prints its version banner (NCCL_DEBUG >= VERSION) to stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     from scldm_b200 import ops
 
