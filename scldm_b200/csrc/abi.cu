@@ -42,7 +42,7 @@ bool g_prof_on = false;
 const bool g_use_mega = []{ const char* e = getenv("SCLDM_MEGA"); return !(e && e[0] == '0'); }();  // SCLDM_MEGA=0: one kernel per block half
 int g_num_sms = 148;
 const bool g_use_pair = []{ const char* e = getenv("SCLDM_PAIR"); return e && e[0] == '1'; }();   // SCLDM_PAIR=1: cta_group::2 CTA pairs
-const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? atoi(e) : 4500; }();   // start offset step of the persistent CTAs (cycles)
+const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? atoi(e) : 0; }();   // optional start offset step of the persistent CTAs (cycles); measured: no gain
 const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
 cudaStream_t g_prof_stream = nullptr;
 
