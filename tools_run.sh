@@ -1,2 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_r02_2gpu.json 2> gpurun_out/bench_r02_2gpu.err
-tail -c 1500 gpurun_out/bench_r02_2gpu.json; tail -3 gpurun_out/bench_r02_2gpu.err
+python tools/kernel_timeline.py 1184 2>&1 | grep -A1 "^mlp1" | grep "\["
