@@ -185,6 +185,14 @@ int scldm_vae_encode(const scldm_vae_enc_weights* w, const int64_t* genes_subset
 int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t seed, int64_t cell_offset,
                       uint32_t stream_id, void* stream);
 
+/* Device-side CSR of a dense (rows, G) fp32 count matrix: the arrays scipy.sparse.csr_matrix(dense) would hold
+ * (reference: process_generation_output builds them on the host from the dense D2H copy, src/scldm/_utils.py:186-200).
+ *   scldm_csr_count: row_nnz [rows] int32 scratch, indptr [rows+1] int64 -> the caller reads indptr[rows] (= nnz) to size
+ *                    the outputs of
+ *   scldm_csr_fill : indices [nnz] int32 (ascending within a row), data [nnz] fp32.                              */
+int scldm_csr_count(const float* dense, int32_t rows, int32_t G, int32_t* row_nnz, int64_t* indptr, void* stream);
+int scldm_csr_fill(const float* dense, int32_t rows, int32_t G, const int64_t* indptr, int32_t* indices, float* data, void* stream);
+
 /* Live per-kernel timing for bench.py: when enabled every launch is bracketed by CUDA events recorded on
  * `stream` (must be the stream the calls run on; disables CUDA-graph capturability while on).
  * scldm_prof_summary synchronises the device and writes "name count total_ms\n" lines.            */

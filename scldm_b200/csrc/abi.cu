@@ -12,6 +12,7 @@
 #include "../../include/scldm_b200.h"
 #include "dit_kernels.cuh"
 #include "vae_kernels.cuh"
+#include "csr_kernels.cuh"
 
 namespace {
 
@@ -557,6 +558,23 @@ int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t se
   const long long n = (long long)n_cells * per_cell;
   LAUNCH("randn_cells", vae::randn_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n_cells, per_cell, seed,
                                                                                                       cell_offset, stream_id));
+  return SCLDM_OK;
+}
+
+int scldm_csr_count(const float* dense, int32_t rows, int32_t G, int32_t* row_nnz, int64_t* indptr, void* stream) {
+  if (!dense || !row_nnz || !indptr || rows < 0 || G < 1) return fail(SCLDM_EINVAL, "bad csr_count arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows > 0) LAUNCH("csr_count", csr::count_kernel<<<rows, csr::THREADS, 0, st>>>(dense, G, row_nnz));
+  LAUNCH("csr_scan", csr::scan_kernel<<<1, 1024, 0, st>>>(row_nnz, rows, reinterpret_cast<long long*>(indptr)));
+  return SCLDM_OK;
+}
+
+int scldm_csr_fill(const float* dense, int32_t rows, int32_t G, const int64_t* indptr, int32_t* indices, float* data, void* stream) {
+  if (!dense || !indptr || rows < 0 || G < 1) return fail(SCLDM_EINVAL, "bad csr_fill arguments");
+  if (rows == 0) return SCLDM_OK;
+  // indices / data may be NULL only when the matrix has no non-zero at all (nothing is written then)
+  LAUNCH("csr_fill", csr::fill_kernel<<<rows, csr::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(dense, G, reinterpret_cast<const long long*>(indptr),
+                                                                                           indices, data));
   return SCLDM_OK;
 }
 

@@ -1,0 +1,99 @@
+// Device-side sparsification of the generated count matrix.
+// The reference copies the dense (rows, G) fp32 counts to the host and builds scipy.sparse.csr_matrix per batch
+// (src/scldm/_utils.py:186-200); counts are > 90 % zeros, so building the CSR arrays on the GPU cuts the D2H
+// transfer roughly 10x.  Output is exactly what scipy.sparse.csr_matrix(dense) holds: indptr (rows+1), column indices
+// ascending within a row, data = the non-zero values (fp32).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace csr {
+
+constexpr int THREADS = 256;
+
+// nnz per row: one CTA per row, coalesced 4-byte loads (rows are only 4-byte aligned in general: G need not be even)
+__global__ void __launch_bounds__(THREADS) count_kernel(const float* __restrict__ dense, int G, int* __restrict__ row_nnz) {
+  __shared__ int s_part[THREADS / 32];
+  const float* r = dense + (size_t)blockIdx.x * G;
+  int c = 0;
+  for (int g = threadIdx.x; g < G; g += THREADS) c += r[g] != 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) t += s_part[i];
+    row_nnz[blockIdx.x] = t;
+  }
+}
+
+// indptr[0] = 0, indptr[i+1] = sum_{j<=i} row_nnz[j]: one CTA, rows walked in chunks of 1024 with a carried total
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ row_nnz, int rows, long long* __restrict__ indptr) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) { s_carry = 0; indptr[0] = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < rows; base += 1024) {
+    const int i = base + threadIdx.x;
+    long long v = i < rows ? (long long)row_nnz[i] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const long long incl = v + (warp > 0 ? s_warp[warp - 1] : 0) + s_carry;
+    if (i < rows) indptr[i + 1] = incl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+}
+
+// ordered compaction of one row per CTA: chunks of 256 genes, ballot + warp prefix + block prefix keep ascending order
+__global__ void __launch_bounds__(THREADS) fill_kernel(const float* __restrict__ dense, int G, const long long* __restrict__ indptr,
+                                                       int* __restrict__ indices, float* __restrict__ data) {
+  __shared__ int s_warp[THREADS / 32];
+  const float* r = dense + (size_t)blockIdx.x * G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long out = indptr[blockIdx.x];
+  for (int base = 0; base < G; base += THREADS) {
+    const int g = base + threadIdx.x;
+    const float v = g < G ? r[g] : 0.0f;
+    const bool nz = v != 0.0f;
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    const int before = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int warp_off = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) {
+      const int c = s_warp[i];
+      if (i < warp) warp_off += c;
+      total += c;
+    }
+    if (nz) {
+      const long long o = out + warp_off + before;
+      indices[o] = g;
+      data[o] = v;
+    }
+    out += total;
+    __syncthreads();
+  }
+}
+
+}  // namespace csr

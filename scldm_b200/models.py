@@ -169,3 +169,19 @@ class LatentDiffusion(nn.Module):
         if return_mu:
             return counts, z_out, mu_out
         return counts, z_out
+
+    def sample_csr(self, condition, guidance_weight, batch_size: int, genes: torch.Tensor, timesteps: int = 50, **kw):
+        """`sample` with the count matrix sparsified on the device: returns `((indptr, indices, data), z)` where the triple is
+        what `scipy.sparse.csr_matrix(counts)` holds (the reference builds it on the host from the dense copy in
+        `process_generation_output`, `_utils.py:186-200`).  Use `csr_to_scipy` for the host object."""
+        counts, z = self.sample(condition, guidance_weight, batch_size, genes, timesteps, **kw)
+        return ops.counts_to_csr(counts), z
+
+
+def csr_to_scipy(csr: tuple[torch.Tensor, torch.Tensor, torch.Tensor], n_genes: int):
+    """Host `scipy.sparse.csr_matrix` from the device arrays of `LatentDiffusion.sample_csr` (the D2H copy moves
+    8 bytes per non-zero instead of 4 bytes per matrix entry)."""
+    from scipy import sparse
+
+    indptr, indices, data = (t.cpu().numpy() for t in csr)
+    return sparse.csr_matrix((data, indices, indptr), shape=(len(indptr) - 1, n_genes))

@@ -209,6 +209,27 @@ def randn_cells(n_cells: int, per_cell: int, seed: int, cell_offset: int, stream
     return out
 
 
+def counts_to_csr(counts: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Dense (rows, G) fp32 counts -> the arrays of `scipy.sparse.csr_matrix(counts)` built on the device:
+    `indptr` int64 [rows+1], `indices` int32 [nnz] (ascending within a row), `data` fp32 [nnz].  The reference builds
+    them on the host from the dense copy (`_utils.py:186-200`); one 8-byte D2H read (nnz) sizes the outputs here."""
+    if counts.device.type != "cuda" or counts.dtype != torch.float32 or counts.dim() != 2:
+        raise RuntimeError("counts_to_csr expects a 2-D float32 CUDA tensor (no CPU fallback)")
+    lib = _lib.load()
+    counts = counts.contiguous()
+    rows, G = counts.shape
+    dev = counts.device
+    row_nnz = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
+    indptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
+    _lib.check(lib.scldm_csr_count(counts.data_ptr(), rows, G, row_nnz.data_ptr(), indptr.data_ptr(), _stream_ptr(dev)), "scldm_csr_count")
+    nnz = int(indptr[-1].item())
+    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    data = torch.empty(nnz, dtype=torch.float32, device=dev)
+    _lib.check(lib.scldm_csr_fill(counts.data_ptr(), rows, G, indptr.data_ptr(), indices.data_ptr(), data.data_ptr(), _stream_ptr(dev)),
+               "scldm_csr_fill")
+    return indptr, indices, data
+
+
 def prof_enable(on: bool, device=None) -> None:
     """Bracket every library launch with CUDA events on the current stream (bench.py roofline timing)."""
     dev = device if device is not None else torch.cuda.current_device()

@@ -281,3 +281,52 @@ def test_joint_size_factors_match_oracle():
     counts, z = ldm.sample({k: v.cuda() for k, v in cond.items()}, {"cell_line": 1.0, "gene": 2.0}, B,
                            torch.arange(1, 201).unsqueeze(0).repeat(B, 1).cuda())
     assert counts.shape == (2 * B, 200) and bool(torch.isfinite(counts).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,G,density", [(37, 17002, 0.08), (5, 1500, 0.5), (3, 129, 0.0), (64, 2000, 1.0), (1, 7, 0.3)])
+def test_device_csr_matches_scipy(rows, G, density):
+    """counts_to_csr builds exactly what scipy.sparse.csr_matrix(dense) holds (the reference's host-side step,
+    _utils.py:186-200): bit-exact indptr / indices / data, including empty rows, ragged G and a full matrix."""
+    from scipy import sparse
+
+    from scldm_b200 import ops
+
+    g = torch.Generator().manual_seed(rows * 1000 + G)
+    dense = torch.poisson(torch.full((rows, G), 3.0), generator=g) + 1.0
+    dense = dense * (torch.rand(rows, G, generator=g) < density)
+    if rows > 2:
+        dense[1] = 0.0                      # an all-zero row
+    ref = sparse.csr_matrix(dense.numpy())
+    indptr, indices, data = ops.counts_to_csr(dense.cuda())
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int32 and data.dtype == torch.float32
+    assert np.array_equal(indptr.cpu().numpy(), ref.indptr.astype(np.int64))
+    assert np.array_equal(indices.cpu().numpy(), ref.indices.astype(np.int32))
+    assert np.array_equal(data.cpu().numpy(), ref.data)
+
+
+@pytest.mark.gpu
+def test_sample_csr_equals_dense_sample():
+    from scldm_b200.models import csr_to_scipy
+
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=1)
+    vcfg = VAEConfig(n_genes=300, n_layer=1)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
+    vae, _ = make_vae(vcfg)
+    mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes)
+    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t, sd_size_factor=sd_t,
+                          num_steps=5, seed=3)
+    B = 6
+    lab = {"clusters": synthetic.randint("csr.lab", 14, (B,)).cuda()}
+    genes = torch.arange(1, vcfg.n_genes + 1, device="cuda").unsqueeze(0).expand(B, -1)
+    counts, z = ldm.sample(lab, {"clusters": 2.0}, B, genes, cell_offset=0)
+    csr, z2 = ldm.sample_csr(lab, {"clusters": 2.0}, B, genes, cell_offset=0)
+    m = csr_to_scipy(csr, vcfg.n_genes)
+    assert torch.equal(z, z2)
+    assert np.array_equal(m.toarray(), counts.cpu().numpy())
+    assert m.nnz == int((counts != 0).sum())

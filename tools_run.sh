@@ -1,3 +1,6 @@
-# scratch script for gpurun sessions: GPU tests, then one bench line
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout=900 -p no:cacheprovider 2>&1 | tail -3
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_latest.json 2>> gpurun_out/sweep.err; tail -c 400 gpurun_out/bench_latest.json
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-prof > gpurun_out/bench_latest.json 2>> gpurun_out/sweep.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_latest.json"))
+print("value", round(d["value"]), "e2e", d["e2e"], "e2e_csr", d.get("e2e_csr"))
+PY
