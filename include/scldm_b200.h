@@ -193,6 +193,13 @@ int scldm_randn_cells(float* out, int32_t n_cells, int32_t per_cell, uint64_t se
 int scldm_csr_count(const float* dense, int32_t rows, int32_t G, int32_t* row_nnz, int64_t* indptr, void* stream);
 int scldm_csr_fill(const float* dense, int32_t rows, int32_t G, const int64_t* indptr, int32_t* indices, float* data, void* stream);
 
+/* "expressed" tokenizer on the device (reference: tokenize_cells(sample_genes="expressed"), src/scldm/datamodule.py:708-731):
+ * dense (rows, G) counts -> genes_subset / counts_subset (rows, S): per cell the expressed genes packed left in gene order
+ * (token = gene_ids[g]), padded with mask_idx / 0; library [rows] = row sums.  *overflow (device int32, zeroed by the
+ * caller) receives the largest expressed-gene count that exceeded S (the reference raises ValueError in that case).  */
+int scldm_tokenize_expressed(const float* dense, int32_t rows, int32_t G, const int64_t* gene_ids, int32_t S, int64_t mask_idx,
+                             int64_t* genes_subset, float* counts_subset, float* library, int32_t* overflow, void* stream);
+
 /* Live per-kernel timing for bench.py: when enabled every launch is bracketed by CUDA events recorded on
  * `stream` (must be the stream the calls run on; disables CUDA-graph capturability while on).
  * scldm_prof_summary synchronises the device and writes "name count total_ms\n" lines.            */

@@ -407,3 +407,39 @@ def latent_diffusion_sample(z0, labels, guidance_weight, genes, log_size_factors
     lib2 = torch.cat([lib, lib], dim=0)
     mu, theta = vae_decode(z_final, genes2, lib2, vae_sd, vae_cfg)
     return mu, theta, z_final
+
+
+# ----------------------------------------------------------------------------------------
+# data formats either side of the path: numpy restatements, test infrastructure only
+# ----------------------------------------------------------------------------------------
+
+
+def tokenize_cells_expressed(counts, gene_idx_row, genes_seq_len: int, mask_idx: int = 0):
+    """`tokenize_cells(..., sample_genes="expressed")` (`src/scldm/datamodule.py:708-731`): per cell the expressed genes
+    (count > 0) packed left in gene order, padded with the mask token / zero counts; raises when a cell expresses more
+    than `genes_seq_len` genes.  counts (N, G) float, gene_idx_row (G,) int64 -> dict as the reference returns."""
+    import numpy as np
+
+    counts = np.asarray(counts)
+    gene_idx = np.tile(np.asarray(gene_idx_row), (len(counts), 1))
+    library_size = counts.sum(1, keepdims=True)
+    N, _ = counts.shape
+    expressed = counts > 0
+    if (expressed.sum(axis=1) > genes_seq_len).any():
+        raise ValueError("genes_seq_len is smaller than number of expressed genes")
+    pos_order = expressed.cumsum(axis=1) - 1
+    genes_out = np.full((N, genes_seq_len), mask_idx, dtype=gene_idx.dtype)
+    counts_out = np.zeros((N, genes_seq_len), dtype=counts.dtype)
+    ii, jj = np.where(expressed)
+    pp = pos_order[expressed]
+    genes_out[ii, pp] = gene_idx[ii, jj]
+    counts_out[ii, pp] = counts[ii, jj]
+    return {"genes": gene_idx, "counts": counts, "genes_subset": genes_out, "counts_subset": counts_out, "library_size": library_size}
+
+
+def counts_to_csr(counts):
+    """`sparse.csr_matrix(counts.numpy())` as used by `process_generation_output` (`src/scldm/_utils.py:186-200`)."""
+    from scipy import sparse
+
+    m = sparse.csr_matrix(counts)
+    return m.indptr, m.indices, m.data

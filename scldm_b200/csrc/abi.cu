@@ -578,6 +578,17 @@ int scldm_csr_fill(const float* dense, int32_t rows, int32_t G, const int64_t* i
   return SCLDM_OK;
 }
 
+int scldm_tokenize_expressed(const float* dense, int32_t rows, int32_t G, const int64_t* gene_ids, int32_t S, int64_t mask_idx,
+                             int64_t* genes_subset, float* counts_subset, float* library, int32_t* overflow, void* stream) {
+  if (!dense || !gene_ids || !genes_subset || !counts_subset || !library || !overflow || rows < 0 || G < 1 || S < 1)
+    return fail(SCLDM_EINVAL, "bad tokenize_expressed arguments");
+  if (rows == 0) return SCLDM_OK;
+  LAUNCH("tokenize_expressed", csr::tokenize_expressed_kernel<<<rows, csr::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+                                   dense, G, reinterpret_cast<const long long*>(gene_ids), S, (long long)mask_idx,
+                                   reinterpret_cast<long long*>(genes_subset), counts_subset, library, overflow));
+  return SCLDM_OK;
+}
+
 uint64_t scldm_launch_count(void) { return g_launches.load(); }
 
 void scldm_debug_timeline(long long* device_buf, int32_t layer) {

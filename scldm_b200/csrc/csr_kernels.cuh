@@ -96,4 +96,58 @@ __global__ void __launch_bounds__(THREADS) fill_kernel(const float* __restrict__
   }
 }
 
+// "expressed" tokenizer (reference: tokenize_cells(sample_genes="expressed"), src/scldm/datamodule.py:708-731): per cell the
+// expressed genes (count > 0) packed left in gene order into (rows, S) token / count arrays, padded with the mask token and
+// zeros; library size = row sum.  One CTA per cell; a cell with more than S expressed genes sets *overflow (the reference
+// raises) and is truncated.
+__global__ void __launch_bounds__(THREADS) tokenize_expressed_kernel(const float* __restrict__ dense, int G, const long long* __restrict__ gene_ids,
+                                                                    int S, long long mask_idx, long long* __restrict__ genes_out,
+                                                                    float* __restrict__ counts_out, float* __restrict__ library,
+                                                                    int* __restrict__ overflow) {
+  __shared__ int s_warp[THREADS / 32];
+  __shared__ float s_sum[THREADS / 32];
+  const float* r = dense + (size_t)blockIdx.x * G;
+  long long* go = genes_out + (size_t)blockIdx.x * S;
+  float* co = counts_out + (size_t)blockIdx.x * S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int out = 0;
+  float sum = 0.0f;
+  for (int base = 0; base < G; base += THREADS) {
+    const int g = base + threadIdx.x;
+    const float v = g < G ? r[g] : 0.0f;
+    sum += v;
+    const bool nz = v > 0.0f;
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    const int before = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int warp_off = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) {
+      const int c = s_warp[i];
+      if (i < warp) warp_off += c;
+      total += c;
+    }
+    if (nz) {
+      const int o = out + warp_off + before;
+      if (o < S) { go[o] = gene_ids[g]; co[o] = v; }
+    }
+    out += total;
+    __syncthreads();
+  }
+  for (int o = min(out, S) + threadIdx.x; o < S; o += THREADS) { go[o] = mask_idx; co[o] = 0.0f; }
+  // library size: the row sum in a fixed (lane-strided, then tree) order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_sum[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) t += s_sum[i];
+    library[blockIdx.x] = t;
+    if (out > S) atomicMax(overflow, out);
+  }
+}
+
 }  // namespace csr

@@ -230,6 +230,31 @@ def counts_to_csr(counts: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, tor
     return indptr, indices, data
 
 
+def tokenize_expressed(counts: torch.Tensor, gene_ids: torch.Tensor, genes_seq_len: int, mask_idx: int = 0) -> dict[str, torch.Tensor]:
+    """`tokenize_cells(..., sample_genes="expressed")` (`datamodule.py:708-731`) on the device: dense (N, G) counts and the
+    (G,) gene-token row -> `genes_subset` int64 / `counts_subset` fp32 (N, genes_seq_len) with the expressed genes packed
+    left, plus `library_size` (N, 1).  Raises ValueError like the reference when a cell expresses more genes than fit."""
+    if counts.device.type != "cuda" or counts.dtype != torch.float32 or counts.dim() != 2:
+        raise RuntimeError("tokenize_expressed expects a 2-D float32 CUDA tensor (no CPU fallback)")
+    lib = _lib.load()
+    counts = counts.contiguous()
+    rows, G = counts.shape
+    dev = counts.device
+    gene_ids = gene_ids.to(device=dev, dtype=torch.int64).contiguous()
+    if gene_ids.numel() != G:
+        raise ValueError("gene_ids must hold one token per column of counts")
+    genes_out = torch.empty(rows, genes_seq_len, dtype=torch.int64, device=dev)
+    counts_out = torch.empty(rows, genes_seq_len, dtype=torch.float32, device=dev)
+    library = torch.empty(rows, 1, dtype=torch.float32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = lib.scldm_tokenize_expressed(counts.data_ptr(), rows, G, gene_ids.data_ptr(), genes_seq_len, mask_idx, genes_out.data_ptr(),
+                                      counts_out.data_ptr(), library.data_ptr(), overflow.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "scldm_tokenize_expressed")
+    if int(overflow.item()) > 0:
+        raise ValueError("genes_seq_len is smaller than number of expressed genes")
+    return {"genes_subset": genes_out, "counts_subset": counts_out, "library_size": library}
+
+
 def prof_enable(on: bool, device=None) -> None:
     """Bracket every library launch with CUDA events on the current stream (bench.py roofline timing)."""
     dev = device if device is not None else torch.cuda.current_device()

@@ -330,3 +330,25 @@ def test_sample_csr_equals_dense_sample():
     assert torch.equal(z, z2)
     assert np.array_equal(m.toarray(), counts.cpu().numpy())
     assert m.nnz == int((counts != 0).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,G,S,density", [(33, 17002, 6147, 0.2), (4, 300, 300, 1.0), (3, 129, 16, 0.0), (7, 2000, 512, 0.1)])
+def test_device_tokenizer_matches_reference_expressed_mode(rows, G, S, density):
+    """ops.tokenize_expressed == the numpy restatement of tokenize_cells(sample_genes="expressed") (datamodule.py:708-731):
+    bit-exact token / count arrays (padding included) and row sums; too many expressed genes raises like the reference."""
+    from scldm_b200 import ops
+
+    g = torch.Generator().manual_seed(rows + G + S)
+    dense = (torch.poisson(torch.full((rows, G), 2.0), generator=g) + 1.0) * (torch.rand(rows, G, generator=g) < density)
+    gene_ids = torch.randperm(G, generator=g) + 1
+    ref = O.tokenize_cells_expressed(dense.numpy(), gene_ids.numpy(), S, mask_idx=0)
+    out = ops.tokenize_expressed(dense.cuda(), gene_ids.cuda(), S, mask_idx=0)
+    assert np.array_equal(out["genes_subset"].cpu().numpy(), ref["genes_subset"])
+    assert np.array_equal(out["counts_subset"].cpu().numpy(), ref["counts_subset"])
+    assert np.allclose(out["library_size"].cpu().numpy(), ref["library_size"], rtol=1e-6)
+    if density > 0:
+        with pytest.raises(ValueError):
+            ops.tokenize_expressed(dense.cuda(), gene_ids.cuda(), max(1, int((dense > 0).sum(1).max()) - 1))
+        with pytest.raises(ValueError):
+            O.tokenize_cells_expressed(dense.numpy(), gene_ids.numpy(), max(1, int((dense > 0).sum(1).max()) - 1))

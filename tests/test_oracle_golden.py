@@ -133,3 +133,24 @@ def test_fm_training_losses(golden_dir):
         out = O.fm_training_losses(torch.from_numpy(g["x1"]), torch.from_numpy(g["t"]), torch.from_numpy(g["x0"]),
                                    lambda x, t: O.dit_forward(x, t, lab, sd, cfg))
     assert rel_l2(out["loss"], g["loss"]) < 1e-5 and rel_l2(out["pred"], g["pred"]) < TOL
+
+
+def test_oracle_tokenizer_and_csr_small_cases():
+    """hand-checkable cases for the numpy restatements of the data-format steps either side of the path
+    (datamodule.py:708-731, _utils.py:186-200)."""
+    import numpy as np
+
+    from oracle import scldm_oracle as O
+
+    counts = np.array([[0, 3, 0, 1, 0], [0, 0, 0, 0, 0], [2, 2, 2, 0, 0]], dtype=np.float32)
+    genes = np.array([11, 12, 13, 14, 15], dtype=np.int64)
+    t = O.tokenize_cells_expressed(counts, genes, 3, mask_idx=0)
+    assert t["genes_subset"].tolist() == [[12, 14, 0], [0, 0, 0], [11, 12, 13]]
+    assert t["counts_subset"].tolist() == [[3, 1, 0], [0, 0, 0], [2, 2, 2]]
+    assert t["library_size"].ravel().tolist() == [4, 0, 6]
+    import pytest
+
+    with pytest.raises(ValueError):
+        O.tokenize_cells_expressed(counts, genes, 2)
+    indptr, indices, data = O.counts_to_csr(counts)
+    assert indptr.tolist() == [0, 2, 2, 5] and indices.tolist() == [1, 3, 0, 1, 2] and data.tolist() == [3, 1, 2, 2, 2]
