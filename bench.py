@@ -153,6 +153,13 @@ def cpu_sample(B: int, dcfg, vcfg, threads: int):
     return step
 
 
+def workload_name(dataset, dcfg, vcfg) -> str:
+    cls = ", ".join(f"{k}:{v}" for k, v in dcfg.class_vocab_sizes.items())
+    tag = " (BASELINE configs[1])" if dataset == "dentate_gyrus" else ""
+    return (f"{dataset}-shaped generation with CFG{tag}: G={vcfg.n_genes}, classes {{{cls}}} {dcfg.condition_strategy}, "
+            f"sample_ode('euler', num_steps={NUM_STEPS}) = {NUM_STEPS - 1} evals, guidance {GUIDANCE}, decode + NB draw")
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle port; the
     reference tree itself does not exist on the GPU box).  Rank 0 only."""
@@ -161,7 +168,7 @@ def run_reference(args):
         return
     from scldm_b200.config import dataset_configs
 
-    dcfg, vcfg = dataset_configs(DATASET)
+    dcfg, vcfg = dataset_configs(args.dataset)
     threads = os.cpu_count() or 1
     B = args.ref_batch
     step = cpu_sample(B, dcfg, vcfg, threads)
@@ -176,7 +183,7 @@ def run_reference(args):
         "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{DATASET}-shaped generation with CFG: G=17002, 49-eval Euler, guidance {GUIDANCE}",
+        "config": {"workload": workload_name(args.dataset, dcfg, vcfg),
                    "cells_per_step": B, "rows_per_step": 2 * B, "note": "bounded sample of the GPU arm's workload; CPU only"},
         "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} x sample() of {B} cells (2B={2 * B} rows), oracle port of the reference modules"},
@@ -199,6 +206,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
+    ap.add_argument("--dataset", default=DATASET, choices=["dentate_gyrus", "hlca", "tabula_muris", "parse1m", "replogle"],
+                    help="gene-vocabulary / class-table shape (BASELINE configs 2-4); the headline line is dentate_gyrus")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -220,7 +229,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from scldm_b200 import ops
 
-    ldm, dcfg, vcfg = build_models(device)
+    ldm, dcfg, vcfg = build_models(device, args.dataset)
     if args.chunk > 0:
         ldm.cell_chunk = args.chunk
     B, G = args.batch, vcfg.n_genes
@@ -247,9 +256,7 @@ def main():
     def step_e2e():
         lab = {k: v.to(device, non_blocking=True) for k, v in labels_h.items()}
         genes = genes_row_h.to(device, non_blocking=True).unsqueeze(0).expand(B, -1)
-        counts, z = ldm.sample(lab, gw, B, genes)
-        counts_h.copy_(counts, non_blocking=True)
-        z_h.copy_(z, non_blocking=True)
+        ldm.sample(lab, gw, B, genes, host_out=(counts_h, z_h))   # rows are copied out chunk by chunk, overlapping the next chunk's ODE
         torch.cuda.current_stream().synchronize()
         return counts_h, z_h
 
@@ -323,11 +330,12 @@ def main():
         breakdown = {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot, 4)} for k, v in
                      sorted(prof.items(), key=lambda kv: -kv[1][1])}
         chunk = min(ldm.cell_chunk, B)
-        rows = 3 * chunk * 16  # slots of a full chunk x 16 tokens (CFG: 3 forwards per cell)
+        chunks = [min(chunk, B - c0) for c0 in range(0, B, chunk)]   # the last chunk of a step may be ragged
         gemm = {k: v for k, v in prof.items() if kernel_flops(k, 1, 1) is not None}
         top = max(gemm.items(), key=lambda kv: kv[1][1])
         name, (cnt, tms) = top
-        fl = kernel_flops(name, rows, 1 + chunk)
+        # 3 forwards per cell (CFG) x 16 tokens; every chunk launches the kernel the same number of times
+        fl = sum(kernel_flops(name, 3 * c * 16, 1 + c) for c in chunks) / len(chunks)   # mean algorithmic FLOPs per launch
         ach = fl / (tms / cnt * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         traffic = None
@@ -357,8 +365,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{DATASET}-shaped generation with CFG (BASELINE configs[1]): G={G}, 14 clusters, "
-                                   f"sample_ode('euler', num_steps=50) = 49 evals, guidance {GUIDANCE}, decode + NB draw",
+            "config": {"workload": workload_name(args.dataset, dcfg, vcfg),
                        "cells_per_step_per_gpu": B, "rows_per_step": rows_per_step, "ode_chunk_cells": min(ldm.cell_chunk, B),
                        "l2": "256 MB flush buffer written between timed steps", "parallelism": f"cells sharded over {world} GPU(s), no collective",
                        "algorithmic_gflop_per_row": round(fl["row_cfg"] / 1e9, 3)},
@@ -377,6 +384,10 @@ def main():
         if roofline:
             line["roofline"] = roofline
             line["kernel_breakdown"] = breakdown
+            dec_ms = sum(v["ms"] for k, v in breakdown.items() if k in ("mcab_decode_tc", "mcab_decode", "nb_finalize", "dec_latent", "qside"))
+            ode_ms = sum(v["ms"] for k, v in breakdown.items()) - dec_ms
+            line["stages"] = {"ode_only_cells_per_s": round(2 * B / (ode_ms / 1e3), 1), "decode_only_cells_per_s": round(2 * B / (dec_ms / 1e3), 1),
+                              "note": "per GPU, from the per-kernel CUDA-event times of one profiled step (rows per second of kernel time)"}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

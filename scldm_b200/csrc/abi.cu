@@ -44,6 +44,9 @@ const bool g_use_mega = []{ const char* e = getenv("SCLDM_MEGA"); return !(e && 
 int g_num_sms = 148;
 const bool g_use_pair = []{ const char* e = getenv("SCLDM_PAIR"); return e && e[0] == '1'; }();   // SCLDM_PAIR=1: cta_group::2 CTA pairs
 const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? atoi(e) : 0; }();   // optional start offset step of the persistent CTAs (cycles); measured: no gain
+// dit_blocks_kernel switches (bit mask, SCLDM_EXP): 1 = hand the MLP accumulator over before M2 is queued (measured slower: 971 vs 942 us),
+// 2 = no setup barrier in phases whose rows come from the stash (927 vs 942 us), 4 = butterfly LayerNorm reductions (937 vs 942 us)
+const int g_exp = []{ const char* e = getenv("SCLDM_EXP"); return e ? atoi(e) : 6; }();
 const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
 cudaStream_t g_prof_stream = nullptr;
 
@@ -117,8 +120,21 @@ struct DitWs {
   size_t total;
 };
 
+// ODE solves on a fixed grid know every evaluation time in advance: when the table fits MOD_BATCH_BYTES, the adaLN vectors of
+// ALL evaluations come from one GEMM before the loop (rows = evaluation x conditioning row) instead of one 20 us launch per
+// evaluation.  Returns the padded row count of that table, or 0 when the per-evaluation path is used.
+constexpr size_t MOD_BATCH_BYTES = 192u << 20;
+const bool g_mod_batch = []{ const char* e = getenv("SCLDM_MOD_BATCH"); return !(e && e[0] == '0'); }();
+size_t mod_batch_rows(const scldm_dit_weights* w, const scldm_dit_plan* plan, int n_evals) {
+  if (!g_mod_batch || n_evals < 2) return 0;
+  const size_t rows = align_up((size_t)n_evals * plan->n_mod, dit::BLOCK_M);
+  return rows * (size_t)w->mod_stride * 4 <= MOD_BATCH_BYTES ? rows : 0;
+}
+
 DitWs carve_dit(void* base, const scldm_dit_weights* w, const scldm_dit_plan* plan, int n_evals) {
-  const size_t slots_pad = scldm_dit_slots_pad(plan), mod_pad = scldm_dit_mod_pad(plan);
+  const size_t slots_pad = scldm_dit_slots_pad(plan);
+  const size_t batch_rows = mod_batch_rows(w, plan, n_evals);
+  const size_t mod_pad = scldm_dit_mod_pad(plan), mod_rows = batch_rows > mod_pad ? batch_rows : mod_pad;
   const size_t rows = slots_pad * dit::TOK, row_tiles = rows / dit::BLOCK_M;
   const size_t n_states = (size_t)plan->n_u + plan->n_g;
   const size_t temb_rows = (size_t)n_evals > mod_pad ? (size_t)n_evals : mod_pad;
@@ -134,7 +150,7 @@ DitWs carve_dit(void* base, const scldm_dit_weights* w, const scldm_dit_plan* pl
   ws.qkv = reinterpret_cast<dit::bf16*>(b + take(rows * 3 * dit::D * 2));
   ws.ao = reinterpret_cast<dit::bf16*>(b + take(rows * dit::D * 2));
   ws.hid = reinterpret_cast<dit::bf16*>(b + take(row_tiles * w->hid_slabs * dit::A_SLAB_BYTES));
-  ws.mod = reinterpret_cast<float*>(b + take(mod_pad * (size_t)w->mod_stride * 4));
+  ws.mod = reinterpret_cast<float*>(b + take(mod_rows * (size_t)w->mod_stride * 4));
   ws.cls = reinterpret_cast<float*>(b + take(mod_pad * dit::D * 4));
   ws.temb = reinterpret_cast<float*>(b + take(temb_rows * dit::D * 4));
   ws.acc = reinterpret_cast<float*>(b + take(n_states * dit::TOK * dit::LAT * 4));
@@ -171,12 +187,13 @@ __global__ void set_times_kernel(float* dst, TimeArgs a, int n) {
 
 // adaLN modulation vectors of every block + final layer for all conditioning rows
 int launch_mod(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, const float* temb, long long temb_stride,
-               cudaStream_t st) {
-  const int mod_pad = scldm_dit_mod_pad(plan);
+               cudaStream_t st, int batch_rows = 0, int n_evals = 0) {
+  const int mod_pad = batch_rows > 0 ? batch_rows : scldm_dit_mod_pad(plan);
   dit::AResParams p{};
   p.temb = temb;
   p.temb_row_stride = temb_stride;
   p.cls = ws.cls;
+  if (batch_rows > 0) { p.cond_group = plan->n_mod; p.cond_rows = n_evals * plan->n_mod; p.temb_row_stride = dit::D; }
   p.Wp = static_cast<const dit::bf16*>(w->w_mod);
   p.n_tiles_total = w->mod_stride / dit::BLOCK_N;
   const int row_tiles = mod_pad / dit::BLOCK_M;
@@ -218,6 +235,7 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
     m.X = ws.X; m.mod = ws.mod; m.slot_mod = mod_index(plan); m.mod_stride = w->mod_stride;
     m.mod_off_mul = 3 * dit::D; m.mod_off_add = 4 * dit::D; m.mod_off_gate = 5 * dit::D; m.eps = w->eps;
     m.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream); m.n_chunks = w->mlp1_tiles; m.hid_slabs = w->hid_slabs;
+    a.exp = g_exp; m.exp = g_exp;
     bp.n_layer = w->n_layer; bp.n_tiles = row_tiles;
     bp.dbg = g_dbg_clk; bp.dbg_layer = g_dbg_layer; bp.stagger_cycles = g_stagger;
     bp.attn_w_stride = 4LL * dit::D * dit::D;
@@ -447,12 +465,18 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
   s.x_base = x;
   LAUNCH("inproj", dit::inproj_kernel<<<n_states, 256, 0, st>>>(s));
   s.do_update = 1;
+  const int batch_rows = (int)mod_batch_rows(w, plan, n_evals);
+  if (batch_rows > 0 && (rc = launch_mod(w, plan, ws, ws.temb, dit::D, st, batch_rows, n_evals))) return rc;
   for (int k = 0; k < n_steps; ++k) {
     const float dt = t_grid_host[k + 1] - t_grid_host[k];
     for (int sg = 0; sg < stages; ++sg) {
       const int e = k * stages + sg;
-      if ((rc = launch_mod(w, plan, ws, ws.temb + (size_t)e * dit::D, 0, st))) return rc;
-      if ((rc = launch_blocks(w, plan, ws, st))) return rc;
+      DitWs wse = ws;
+      if (batch_rows > 0) {   // this evaluation's rows of the precomputed table
+        wse.mod = ws.mod + (size_t)e * plan->n_mod * w->mod_stride;
+        s.mod = wse.mod;
+      } else if ((rc = launch_mod(w, plan, ws, ws.temb + (size_t)e * dit::D, 0, st))) return rc;
+      if ((rc = launch_blocks(w, plan, wse, st))) return rc;
       s.first_stage = sg == 0;
       s.last_stage = sg == stages - 1;
       if (method == SCLDM_ODE_EULER) { s.a_dt = 0.f; s.b_dt = dt; }

@@ -71,6 +71,8 @@ struct AResParams {
   const float* temb;     // PRO_COND: [*, 256] timestep embedding rows
   long long temb_row_stride;  // PRO_COND: 0 => one shared row (sampling), 256 => one row per mod row
   const float* cls;      // PRO_COND: [n_mod_pad][256] summed class embeddings
+  int cond_group;        // PRO_COND: > 0 => row m pairs temb row m / cond_group with cls row m % cond_group (the tables of all
+  int cond_rows;         //           evaluations of an ODE solve in one GEMM); rows >= cond_rows repeat the last valid row
   // ---- B operand ------------------------------------------------------------------------
   const bf16* Wp;        // packed [n_tiles][4 slabs][256 x 64 swizzled]
   int n_tiles_total;
@@ -161,10 +163,27 @@ __device__ __forceinline__ void producer_issue_x_passes(const float* X, int row_
 }
 
 __device__ __forceinline__ void dbg_stamp(long long* dbg, int slot);
+// Row totals of four per-lane partials with a transposing butterfly: 10 shuffles instead of 20 (the prologue is bound by the
+// shared-memory / shuffle pipe).  Lanes fold rows pairwise (xor 16, xor 8), finish one row each over 8 lanes, then broadcast.
+__device__ __forceinline__ void reduce4_bfly(float (&s)[4], uint32_t lane) {
+  const bool b4 = (lane & 16u) != 0, b3 = (lane & 8u) != 0;
+  float k0 = b4 ? s[2] : s[0], k1 = b4 ? s[3] : s[1];
+  k0 += __shfl_xor_sync(0xffffffffu, b4 ? s[0] : s[2], 16);
+  k1 += __shfl_xor_sync(0xffffffffu, b4 ? s[1] : s[3], 16);
+  float k = b3 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  s[0] = __shfl_sync(0xffffffffu, k, 0);
+  s[1] = __shfl_sync(0xffffffffu, k, 8);
+  s[2] = __shfl_sync(0xffffffffu, k, 16);
+  s[3] = __shfl_sync(0xffffffffu, k, 24);
+}
 __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB, uint64_t* x_full, uint64_t* x_empty, uint8_t* smA,
                                                 const float* mod, const ModIndex& slot_mod, int mod_stride, int off_mul, int off_add,
                                                 float eps, int row_tile, uint32_t ew, uint32_t lane, long long* dbg = nullptr,
-                                                bool stashed = false, uint32_t x_parity = 0) {
+                                                bool stashed = false, uint32_t x_parity = 0, int exp = 0) {
   // `stashed`: the rows were left in the pass buffers by the previous phase's residual epilogue (resid_epilogue_warp
   // <.., OUT_STASH>) instead of arriving by TMA: nothing to wait for.
   // Warp ew owns rows [8 ew, 8 ew + 8) of the tile: one X pass (ew / 4), one slot (ew / 2) -> one set of modulation
@@ -172,6 +191,7 @@ __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB
   // channels [4l, 4l+4) and [128 + 4l, 128 + 4l + 4) of a row (conflict-free 16 B shared-memory reads).
   const float inv_d = 1.0f / D;
   const int pss = ew >> 2;
+  if (ew == 0 && lane == 0) dbg_stamp(dbg, 16);
   const float* mrow = mod + (size_t)slot_mod.row(row_tile * 8 + (ew >> 1)) * mod_stride;
   const float4 m0 = *reinterpret_cast<const float4*>(mrow + off_mul + lane * 4), m1 = *reinterpret_cast<const float4*>(mrow + off_mul + 128 + lane * 4);
   const float4 a0 = *reinterpret_cast<const float4*>(mrow + off_add + lane * 4), a1 = *reinterpret_cast<const float4*>(mrow + off_add + 128 + lane * 4);
@@ -201,10 +221,13 @@ __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB
 #pragma unroll
       for (int j = 0; j < 8; ++j) sm_[i] += v[i][j];
     }
+    if (exp & 4) reduce4_bfly(sm_, lane);
+    else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) sm_[i] += __shfl_xor_sync(0xffffffffu, sm_[i], o);
+        for (int i = 0; i < 4; ++i) sm_[i] += __shfl_xor_sync(0xffffffffu, sm_[i], o);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -213,12 +236,15 @@ __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB
 #pragma unroll
       for (int j = 0; j < 8; ++j) { v[i][j] -= mean; sq[i] += v[i][j] * v[i][j]; }
     }
+    if (exp & 4) reduce4_bfly(sq, lane);
+    else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+        for (int i = 0; i < 4; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+      }
     }
-    if (ew == 0 && lane == 0 && rnd == 0) dbg_stamp(dbg, 26);
+    if (ew == 0 && lane == 0) dbg_stamp(dbg, rnd == 0 ? 26 : 18);
     // first use of the modulation vectors: their (two dependent) global loads have been in flight since kernel entry
     const float mul[8] = {1.f + m0.x, 1.f + m0.y, 1.f + m0.z, 1.f + m0.w, 1.f + m1.x, 1.f + m1.y, 1.f + m1.z, 1.f + m1.w};
     const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -235,6 +261,7 @@ __device__ __forceinline__ void ln_prologue_tma(uint8_t* smScratch, uint8_t* smB
       *reinterpret_cast<uint2*>(a_lo + off) = lo;                       // channels [4l, 4l+4)       -> slab l/16
       *reinterpret_cast<uint2*>(a_lo + 2 * A_SLAB_BYTES + off) = hi;    // channels [128+4l, +4)     -> slab 2 + l/16
     }
+    if (ew == 0 && lane == 0) dbg_stamp(dbg, 17 + 2 * rnd);
   }
 }
 
@@ -359,9 +386,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
 #pragma unroll 4
       for (int i = 0; i < 8; ++i) {
         const int r = ew * 8 + i;
-        const size_t m = (size_t)row_tile * BLOCK_M + r;
-        const float* tr = p.temb + m * p.temb_row_stride + lane * 8;
-        const float* cr = p.cls + m * D + lane * 8;
+        size_t m = (size_t)row_tile * BLOCK_M + r;
+        size_t mt = m, mc = m;
+        if (p.cond_group > 0) {
+          if (m >= (size_t)p.cond_rows) m = (size_t)p.cond_rows - 1;
+          mt = m / (size_t)p.cond_group;
+          mc = m % (size_t)p.cond_group;
+        }
+        const float* tr = p.temb + mt * p.temb_row_stride + lane * 8;
+        const float* cr = p.cls + mc * D + lane * 8;
         const float4 t0 = *reinterpret_cast<const float4*>(tr);
         const float4 t1 = *reinterpret_cast<const float4*>(tr + 4);
         const float4 c0 = *reinterpret_cast<const float4*>(cr);
@@ -733,6 +766,7 @@ struct MlpFusedParams {
   int n_chunks;           // ceil(hidden/128)
   int hid_slabs;          // ceil(hidden/64)
   long long* dbg;
+  int exp;                // experiment switches (SCLDM_EXP bit mask), see abi.cu
 };
 
 // Shared-memory map common to both fused phases (attention half / MLP half) so that they can alternate inside one
@@ -874,7 +908,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
     if (x_tma) producer_issue_x_passes(p.X, row_tile, smH, smB, x_full);
     else stash_write_back(p.X + (size_t)row_tile * BLOCK_M * D, smH);
   }
-  __syncthreads();
+  if (x_tma || !(p.exp & 2)) __syncthreads();   // stash mode: nobody depends on thread 0's issue work (consumers wait on mbarriers)
   auto m2_slabs = [&](int j) { return min(2, p.hid_slabs - 2 * j); };
   const int total = KSLABS_D * T + p.hid_slabs;               // weight slabs of the phase
   int rounds = (total + (int)NSTAGE - 1) / (int)NSTAGE;
@@ -922,7 +956,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
       };
       for (int j = 0; j <= T; ++j) {
         if (j < T) {  // M1_j
-          if (j > 0) { sm100::mbar_wait(acc1_free, ((j - 1) & 1) ^ pt); sm100::tc_fence_after(); }
+          if (j > 0 && !(p.exp & 1)) { sm100::mbar_wait(acc1_free, ((j - 1) & 1) ^ pt); sm100::tc_fence_after(); }
           for (int ks = 0; ks < KSLABS_D; ++ks) {
             wait_stage();
             issue_slab_mmas_cg<PAIR>(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc, ks == 0);
@@ -930,6 +964,9 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
             rs.advance(NSTAGE);
           }
           G::commit(acc1_full);
+          // exp bit 0: hand the accumulator over while the tensor pipe is idle (tcgen05.ld is several times faster without
+          // MMAs in flight), then queue M2_{j-1} and M1_{j+1} back to back
+          if ((p.exp & 1) && j + 1 < T) { sm100::mbar_wait(acc1_free, (j & 1) ^ pt); sm100::tc_fence_after(); }
         }
         if (j >= 1) {  // M2_{j-1}
           const int c = j - 1, b = c & 1;
@@ -965,7 +1002,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
     // ===================== 16 prologue / epilogue warps ====================================
     const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
-    ln_prologue_tma(smH, smB, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px);
+    ln_prologue_tma(smH, smB, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px, p.exp);
     sm100::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) G::arrive_mma(a_ready);
@@ -1223,6 +1260,7 @@ struct AttnBlockParams {
                           // scores) and the v bias passes through the attention (rows of P sum to 1), so it is folded into
   const float* bias_proj; // [256] = c_proj.bias + c_proj.weight @ c_attn.bias[512:768]   (pack.py: b_proj_fused)
   long long* dbg;
+  int exp;                // experiment switches (SCLDM_EXP bit mask), see abi.cu
 };
 
 constexpr int AB_HP = 4;                        // head pairs
@@ -1276,7 +1314,7 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
     if (x_tma) producer_issue_x_passes(p.X, row_tile, smQKV, smW, x_full);
     else stash_write_back(p.X + (size_t)row_tile * BLOCK_M * D, smQKV);
   }
-  __syncthreads();
+  if (x_tma || !(p.exp & 2)) __syncthreads();
   if (warp == 0) {
     // ===================== producer: one linear stream of weight items ======================
     if (lane == 0) {
@@ -1362,7 +1400,7 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
     // ===================== 16 worker warps ==================================================
     const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2, etid = threadIdx.x - 64;
     const uint32_t row = q * 32 + lane;
-    ln_prologue_tma(smQKV, smW, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px);
+    ln_prologue_tma(smQKV, smW, x_full, x_empty, smA, p.mod, p.slot_mod, p.mod_stride, p.mod_off_mul, p.mod_off_add, p.eps, row_tile, ew, lane, p.dbg, !x_tma, px, p.exp);
     sm100::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) G::arrive_mma(a_ready);

@@ -119,10 +119,16 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def sample(self, condition: dict[str, torch.Tensor] | None, guidance_weight: dict[str, float] | None, batch_size: int,
                genes: torch.Tensor, timesteps: int = 50, *, z0: torch.Tensor | None = None,
-               log_size_factors: torch.Tensor | None = None, return_mu: bool = False, cell_offset: int | None = None):
+               log_size_factors: torch.Tensor | None = None, return_mu: bool = False, cell_offset: int | None = None,
+               host_out: tuple[torch.Tensor, torch.Tensor] | None = None):
         """Generation (`models.py:766-819`).  `timesteps` is accepted and ignored exactly as in the reference
         (`models.py:773,793`); the grid is `self.num_steps` points.  `z0` / `log_size_factors` may be injected
-        (parity tests share them with the oracle); otherwise they are drawn on device."""
+        (parity tests share them with the oracle); otherwise they are drawn on device.
+
+        `host_out=(counts_host (2B,G), z_host (2B,M,L))`, pinned: every chunk's rows are copied to the host on a side
+        stream as soon as they are decoded, so the device-to-host transfer (the reference's `.cpu()` in
+        `predict_step`, `models.py:742`) overlaps the ODE of the next chunk; the copies are complete when this call's
+        stream is synchronised (the side stream is joined before returning)."""
         if len(genes) != batch_size:
             raise ValueError(f"genes batch dimension ({genes.shape[0]}) must match batch_size ({batch_size})")
         if condition is not None:
@@ -152,6 +158,17 @@ class LatentDiffusion(nn.Module):
         counts = torch.empty(2 * batch_size, G, dtype=torch.float32, device=dev)
         mu_out = torch.empty(2 * batch_size, G, dtype=torch.float32, device=dev) if return_mu else None
         z_out = torch.empty(2 * batch_size, dit.seq_len, dit.config.n_embed_input, dtype=torch.float32, device=dev)
+        copy_stream = None
+        if host_out is not None:
+            counts_host, z_host = host_out
+            if tuple(counts_host.shape) != (2 * batch_size, G) or tuple(z_host.shape) != tuple(z_out.shape):
+                raise ValueError("host_out shapes must be (2B, G) and (2B, seq_len, n_embed_input)")
+            if not (counts_host.is_pinned() and z_host.is_pinned()):
+                raise ValueError("host_out buffers must be pinned host memory")
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            copy_stream = self._copy_stream
+            copy_stream.wait_stream(torch.cuda.current_stream(dev))   # earlier readers of the host buffers are ordered before us
         # cells are independent: run the ODE + decode chunk by chunk so the working set stays L2-sized
         for c0 in range(0, batch_size, self.cell_chunk):
             c1 = min(c0 + self.cell_chunk, batch_size)
@@ -166,6 +183,16 @@ class LatentDiffusion(nn.Module):
                                              cell_offset=offset + c0 + half * (1 << 40), want_mu=return_mu,
                                              out_counts=counts[rows], out_mu=mu_out[rows] if return_mu else None)
                 z_out[rows] = zh
+            if copy_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                copy_stream.wait_event(ev)
+                with torch.cuda.stream(copy_stream):
+                    for rows in (slice(c0, c1), slice(batch_size + c0, batch_size + c1)):
+                        counts_host[rows].copy_(counts[rows], non_blocking=True)
+                        z_host[rows].copy_(z_out[rows], non_blocking=True)
+        if copy_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(copy_stream)
         if return_mu:
             return counts, z_out, mu_out
         return counts, z_out
