@@ -200,6 +200,12 @@ int scldm_csr_fill(const float* dense, int32_t rows, int32_t G, const int64_t* i
 int scldm_tokenize_expressed(const float* dense, int32_t rows, int32_t G, const int64_t* gene_ids, int32_t S, int64_t mask_idx,
                              int64_t* genes_subset, float* counts_subset, float* library, int32_t* overflow, void* stream);
 
+/* NB reconstruction loss per cell: nll[r] = -sum_g log_nb_positive(x[r][g], mu[r][g], theta[..][g]) with eps = 1e-8
+ * (reference: src/scldm/distributions.py:6-42, summed over genes as VAE.loss does, src/scldm/models.py:233-247).
+ * theta_row_stride = G for a (rows, G) theta, 0 for one shared (G,) row.                                          */
+int scldm_nb_nll(const float* x, const float* mu, const float* theta, int64_t theta_row_stride, int32_t rows, int32_t G, float* nll,
+                 void* stream);
+
 /* Live per-kernel timing for bench.py: when enabled every launch is bracketed by CUDA events recorded on
  * `stream` (must be the stream the calls run on; disables CUDA-graph capturability while on).
  * scldm_prof_summary synchronises the device and writes "name count total_ms\n" lines.            */

@@ -443,3 +443,19 @@ def counts_to_csr(counts):
 
     m = sparse.csr_matrix(counts)
     return m.indptr, m.indices, m.data
+
+
+def log_nb_positive(x, mu, theta, eps: float = 1e-8):
+    """NB log-likelihood per entry (`src/scldm/distributions.py:6-42`)."""
+    log_theta_mu_eps = torch.log(theta + mu + eps)
+    return (theta * (torch.log(theta + eps) - log_theta_mu_eps) + x * (torch.log(mu + eps) - log_theta_mu_eps)
+            + torch.lgamma(x + theta) - torch.lgamma(theta) - torch.lgamma(x + 1))
+
+
+def vae_forward_loss(counts, genes, library_size, counts_subset, genes_subset, sd, cfg):
+    """`TransformerVAE.forward` (`src/scldm/vae.py:29-56`) followed by `VAE.loss` for the NB head
+    (`src/scldm/models.py:233-247`): returns (mu, theta, h_z, per-cell NLL, llh = mean over cells)."""
+    h_z = vae_encode(counts_subset, genes_subset, sd, cfg)
+    mu, theta = vae_decode(h_z, genes, library_size, sd, cfg)
+    per_cell = (-log_nb_positive(counts, mu, theta)).sum(dim=1)
+    return mu, theta, h_z, per_cell, per_cell.mean()

@@ -47,6 +47,7 @@ const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? at
 // dit_blocks_kernel switches (bit mask, SCLDM_EXP): 1 = hand the MLP accumulator over before M2 is queued (measured slower: 971 vs 942 us),
 // 2 = no setup barrier in phases whose rows come from the stash (927 vs 942 us), 4 = butterfly LayerNorm reductions (937 vs 942 us)
 const int g_exp = []{ const char* e = getenv("SCLDM_EXP"); return e ? atoi(e) : 6; }();
+const int g_dec_occ = []{ const char* e = getenv("SCLDM_DEC_OCC"); return e ? atoi(e) : 2; }();   // resident CTAs per SM the MCAB decode kernel is compiled for (2: 128 registers, 3: 80 registers + spills)
 const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
 cudaStream_t g_prof_stream = nullptr;
 
@@ -542,7 +543,8 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
     mp.G = n_genes; mp.kvb = kvb; mp.n_cells = n_cells; mp.cells_per_block = cpb;
     mp.wfrag = static_cast<const uint32_t*>(w->mcab_wfrag); mp.small = w->mcab_small; mp.eps = w->eps;
     mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
-    LAUNCH("mcab_decode_tc", vae::mcab_decode_tc_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 256, 0, st>>>(mp));
+    if (g_dec_occ == 3) LAUNCH("mcab_decode_tc", vae::mcab_decode_tc_kernel<3><<<dim3(tiles, ceil_div(n_cells, cpb)), 256, 0, st>>>(mp));
+    else LAUNCH("mcab_decode_tc", vae::mcab_decode_tc_kernel<2><<<dim3(tiles, ceil_div(n_cells, cpb)), 256, 0, st>>>(mp));
   } else {
     vae::McabParams mp{};
     mp.emb = w->emb; mp.qp = qp; mp.genes = reinterpret_cast<const long long*>(genes); mp.G = n_genes; mp.kv = kv; mp.n_cells = n_cells;
@@ -599,6 +601,15 @@ int scldm_csr_fill(const float* dense, int32_t rows, int32_t G, const int64_t* i
   // indices / data may be NULL only when the matrix has no non-zero at all (nothing is written then)
   LAUNCH("csr_fill", csr::fill_kernel<<<rows, csr::THREADS, 0, static_cast<cudaStream_t>(stream)>>>(dense, G, reinterpret_cast<const long long*>(indptr),
                                                                                            indices, data));
+  return SCLDM_OK;
+}
+
+int scldm_nb_nll(const float* x, const float* mu, const float* theta, int64_t theta_row_stride, int32_t rows, int32_t G, float* nll,
+                 void* stream) {
+  if (!x || !mu || !theta || !nll || rows < 0 || G < 1 || (theta_row_stride != 0 && theta_row_stride < G))
+    return fail(SCLDM_EINVAL, "bad nb_nll arguments");
+  if (rows == 0) return SCLDM_OK;
+  LAUNCH("nb_nll", vae::nb_nll_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, mu, theta, (long long)theta_row_stride, G, nll));
   return SCLDM_OK;
 }
 

@@ -110,8 +110,26 @@ __device__ __forceinline__ float poisson(Philox& g, float lam) {
   return floorf(lam);
 }
 
-// NB(mu, theta) as Poisson(Gamma(theta, rate = theta/mu)), gamma draw clamped to 1e8 (scvi semantics)
+// NB(mu, theta) as Poisson(Gamma(theta, rate = theta/mu)), gamma draw clamped to 1e8 (scvi semantics).
+// Small means (the bulk of a count matrix: mean count per gene << 1) take the Gamma-Poisson MIXTURE's own law instead of
+// the two-stage draw: pmf(0) = (theta/(theta+mu))^theta, pmf(k+1) = pmf(k) (k+theta)/(k+1) mu/(theta+mu), inverted with one
+// uniform (same distribution, one Philox block instead of two or more and no rejection loops).
+constexpr float NB_INVERSION_MAX_MU = 4.0f;
 __device__ __forceinline__ float negative_binomial(Philox& g, float mu, float theta) {
+  if (mu < NB_INVERSION_MAX_MU && theta > 1e-3f) {
+    if (!(mu > 0.0f)) return 0.0f;
+    const float u = g.uniform();                       // (0, 1]
+    const float q = mu / (theta + mu);
+    float p = __expf(-theta * log1pf(mu / theta));     // pmf(0)
+    float c = p;
+    int k = 0;
+    while (u > c && k < 256) {
+      p *= ((float)k + theta) / (float)(k + 1) * q;
+      c += p;
+      ++k;
+    }
+    return (float)k;
+  }
   const float lam = fminf(gamma_mt(g, theta) * (mu / theta), 1e8f);
   return poisson(g, lam);
 }

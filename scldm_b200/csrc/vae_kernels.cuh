@@ -425,7 +425,8 @@ __device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(b0));
 }
 
-__global__ void __launch_bounds__(256, 2) mcab_decode_tc_kernel(const McabTcParams p) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const McabTcParams p) {
   __shared__ uint2 s_frag[TC_NFRAG * 32];   // 20 KB
   __shared__ float s_small[100];
   __shared__ float red_m[2][8], red_s[2][8];
@@ -603,6 +604,44 @@ __global__ void __launch_bounds__(256, 2) mcab_decode_tc_kernel(const McabTcPara
     }
 #pragma unroll
     for (int h = 0; h < 4; ++h) { kb[h][0] = kn[h][0]; kb[h][1] = kn[h][1]; vb[h][0] = vn[h][0]; vb[h][1] = vn[h][1]; }
+  }
+}
+
+// ---- NB reconstruction loss (distributions.py:6-42 log_nb_positive; models.py:233-247 VAE.loss) ---------------------
+// nll[cell] = -sum_g log NB(x | mu, theta), the per-cell term of `recon_loss.sum(dim=1)`; eps = 1e-8 as the reference.
+// One CTA per cell, coalesced float4 rows; HBM-bound: 12 B per (cell, gene) when theta is per cell, 8 B when it is the
+// shared (G,) row.  Zero counts (the bulk of a count matrix) skip the three lgamma terms, which cancel exactly there.
+__device__ __forceinline__ float nb_logp(float x, float mu, float th) {
+  const float eps = 1e-8f;
+  const float l_tm = logf(th + mu + eps);
+  float r = th * (logf(th + eps) - l_tm);
+  if (x != 0.f) r += x * (logf(mu + eps) - l_tm) + lgammaf(x + th) - lgammaf(th) - lgammaf(x + 1.f);
+  return r;
+}
+__global__ void __launch_bounds__(256) nb_nll_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ theta,
+                                                      long long theta_row_stride, int G, float* __restrict__ nll) {
+  __shared__ float red[8];
+  const size_t cell = blockIdx.x;
+  const float* xr = x + cell * (size_t)G;
+  const float* mr = mu + cell * (size_t)G;
+  const float* tr = theta + cell * (size_t)theta_row_stride;
+  float acc = 0.f;
+  if ((G & 3) == 0 && (theta_row_stride & 3) == 0) {
+    for (int g = threadIdx.x * 4; g < G; g += 1024) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + g), b = *reinterpret_cast<const float4*>(mr + g), c = *reinterpret_cast<const float4*>(tr + g);
+      acc += (nb_logp(a.x, b.x, c.x) + nb_logp(a.y, b.y, c.y)) + (nb_logp(a.z, b.z, c.z) + nb_logp(a.w, b.w, c.w));
+    }
+  } else {
+    for (int g = threadIdx.x; g < G; g += 256) acc += nb_logp(xr[g], mr[g], tr[g]);
+  }
+  acc = sm100::warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    nll[cell] = -t;
   }
 }
 

@@ -45,6 +45,7 @@ class LatentDiffusion(nn.Module):
         self.sampling_method, self.num_steps = sampling_method, num_steps
         self.seed = seed
         self.cell_chunk = cell_chunk
+        self.decode_piece = 296  # cells per decode launch when results stream to the host (`sample(host_out=...)`)
         self.cells_generated = 0  # global cell counter -> RNG offsets independent of batching / sharding
         self._sf_tables: dict = {}
 
@@ -177,20 +178,25 @@ class LatentDiffusion(nn.Module):
             zf = sample_fn(torch.cat([zc, zc]), model_fn, condition=cc)[-1]
             n = c1 - c0
             libc = torch.cat([lib[c0:c1], lib[c0:c1]])
-            for half, rows in ((0, slice(c0, c1)), (1, slice(batch_size + c0, batch_size + c1))):
-                zh = zf[half * n:(half + 1) * n]
-                self.vae_model.decode_counts(zh, gvec, libc[half * n:(half + 1) * n], seed=self.seed,
-                                             cell_offset=offset + c0 + half * (1 << 40), want_mu=return_mu,
-                                             out_counts=counts[rows], out_mu=mu_out[rows] if return_mu else None)
-                z_out[rows] = zh
-            if copy_stream is not None:
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(dev))
-                copy_stream.wait_event(ev)
-                with torch.cuda.stream(copy_stream):
-                    for rows in (slice(c0, c1), slice(batch_size + c0, batch_size + c1)):
-                        counts_host[rows].copy_(counts[rows], non_blocking=True)
-                        z_host[rows].copy_(z_out[rows], non_blocking=True)
+            # decode in pieces; with host_out every piece is copied out behind its decode, so only the last piece's transfer
+            # is left when the final chunk finishes
+            piece = self.decode_piece if copy_stream is not None else n
+            for half in (0, 1):
+                for p0 in range(0, n, piece):
+                    p1 = min(p0 + piece, n)
+                    rows = slice(half * batch_size + c0 + p0, half * batch_size + c0 + p1)
+                    zh = zf[half * n + p0:half * n + p1]
+                    self.vae_model.decode_counts(zh, gvec, libc[half * n + p0:half * n + p1], seed=self.seed,
+                                                 cell_offset=offset + c0 + p0 + half * (1 << 40), want_mu=return_mu,
+                                                 out_counts=counts[rows], out_mu=mu_out[rows] if return_mu else None)
+                    z_out[rows] = zh
+                    if copy_stream is not None:
+                        ev = torch.cuda.Event()
+                        ev.record(torch.cuda.current_stream(dev))
+                        copy_stream.wait_event(ev)
+                        with torch.cuda.stream(copy_stream):
+                            counts_host[rows].copy_(counts[rows], non_blocking=True)
+                            z_host[rows].copy_(z_out[rows], non_blocking=True)
         if copy_stream is not None:
             torch.cuda.current_stream(dev).wait_stream(copy_stream)
         if return_mu:

@@ -230,6 +230,27 @@ def counts_to_csr(counts: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, tor
     return indptr, indices, data
 
 
+def nb_nll(counts: torch.Tensor, mu: torch.Tensor, theta: torch.Tensor) -> torch.Tensor:
+    """Per-cell NB reconstruction loss `(-log_nb_positive(counts, mu, theta)).sum(dim=1)` (`distributions.py:6-42`,
+    `models.py:233-247`): counts / mu (N, G) fp32, theta (N, G) or a shared (G,) row -> (N,) fp32."""
+    for name, t in (("counts", counts), ("mu", mu), ("theta", theta)):
+        if t.device.type != "cuda" or t.dtype != torch.float32:
+            raise RuntimeError(f"nb_nll: {name} must be a float32 CUDA tensor (no CPU fallback)")
+    if counts.dim() != 2 or mu.shape != counts.shape or theta.shape[-1] != counts.shape[1] or theta.dim() not in (1, 2):
+        raise ValueError(f"nb_nll: shape mismatch counts {tuple(counts.shape)} mu {tuple(mu.shape)} theta {tuple(theta.shape)}")
+    if theta.dim() == 2 and theta.shape[0] not in (1, counts.shape[0]):
+        raise ValueError("nb_nll: theta must have one row or one row per cell")
+    if theta.dim() == 2 and (theta.shape[0] == 1 or theta.stride(0) == 0):
+        theta = theta[0]   # one shared row (the expanded view `decode` returns for shared_theta)
+    counts, mu, theta = counts.contiguous(), mu.contiguous(), theta.contiguous()
+    rows, G = counts.shape
+    stride = G if theta.dim() == 2 else 0
+    out = torch.empty(rows, dtype=torch.float32, device=counts.device)
+    _lib.check(_lib.load().scldm_nb_nll(counts.data_ptr(), mu.data_ptr(), theta.data_ptr(), stride, rows, G, out.data_ptr(),
+                                        _stream_ptr(counts.device)), "scldm_nb_nll")
+    return out
+
+
 def tokenize_expressed(counts: torch.Tensor, gene_ids: torch.Tensor, genes_seq_len: int, mask_idx: int = 0) -> dict[str, torch.Tensor]:
     """`tokenize_cells(..., sample_genes="expressed")` (`datamodule.py:708-731`) on the device: dense (N, G) counts and the
     (G,) gene-token row -> `genes_subset` int64 / `counts_subset` fp32 (N, genes_seq_len) with the expressed genes packed

@@ -112,5 +112,17 @@ class TransformerVAE(nn.Module):
         g = genes_subset if genes_subset is not None else genes
         return ops.vae_encode(self.packed_encoder(), g.contiguous(), c.contiguous())
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("VAE training forward is a later row (SURVEY.md §8f rank 3)")
+    @torch.no_grad()
+    def forward(self, counts, genes, library_size, counts_subset=None, genes_subset=None):
+        """`TransformerVAE.forward` (`vae.py:29-56`), inference only: encode the (subset) tokens, decode every gene ->
+        `({"mu", "theta"}, h_z)`.  No autograd graph is built (the backward pass / VAE training step is SURVEY.md 8f rank 3)."""
+        h_z = self.encode(counts, genes, counts_subset, genes_subset)
+        dist = self.decode(h_z, genes, library_size)
+        return {"mu": dist.mu, "theta": dist.theta}, h_z
+
+    @staticmethod
+    def reconstruction_loss(counts: torch.Tensor, params: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        """`VAE.loss` for the NB head (`models.py:233-247`): `{"llh": (-log_nb_positive(...)).sum(dim=1).mean()}`
+        (`LossEnum.LLH_LOSS`, `constants.py:35`); the per-cell sums come from one fused device pass (`ops.nb_nll`)."""
+        per_cell = ops.nb_nll(counts.float(), params["mu"], params["theta"])
+        return {"llh": per_cell.mean(), "per_cell": per_cell}

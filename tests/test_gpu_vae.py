@@ -352,3 +352,66 @@ def test_device_tokenizer_matches_reference_expressed_mode(rows, G, S, density):
             ops.tokenize_expressed(dense.cuda(), gene_ids.cuda(), max(1, int((dense > 0).sum(1).max()) - 1))
         with pytest.raises(ValueError):
             O.tokenize_cells_expressed(dense.numpy(), gene_ids.numpy(), max(1, int((dense > 0).sum(1).max()) - 1))
+
+
+def test_sample_streams_to_pinned_host_buffers():
+    """`sample(host_out=...)`: rows are copied out piece by piece on a side stream behind their decode; the host buffers must
+    hold exactly what the call returns on the device (several ODE chunks and ragged decode pieces), and bad buffers raise."""
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=1)
+    vcfg = VAEConfig(n_genes=700, n_layer=1)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
+    vae, _ = make_vae(vcfg)
+    mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes)
+    B = 53
+    lab = {"clusters": synthetic.randint("ho.lab", 14, (B,)).cuda()}
+    genes = torch.arange(1, 701).unsqueeze(0).repeat(B, 1).cuda()
+    mk = lambda: LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t,  # noqa: E731
+                                 sd_size_factor=sd_t, num_steps=4, seed=11, cell_chunk=24)
+    c_ref, z_ref = mk().sample(lab, {"clusters": 2.0}, B, genes)
+    ldm = mk()
+    ldm.decode_piece = 7
+    counts_h = torch.full((2 * B, 700), -1.0).pin_memory()
+    z_h = torch.full((2 * B, 16, 16), -1.0).pin_memory()
+    c_dev, z_dev = ldm.sample(lab, {"clusters": 2.0}, B, genes, host_out=(counts_h, z_h))
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(c_dev, c_ref) and torch.equal(z_dev, z_ref)
+    assert torch.equal(counts_h, c_ref.cpu()) and torch.equal(z_h, z_ref.cpu())
+    with pytest.raises(ValueError):
+        mk().sample(lab, {"clusters": 2.0}, B, genes, host_out=(torch.empty(2 * B, 700), z_h))          # not pinned
+    with pytest.raises(ValueError):
+        mk().sample(lab, {"clusters": 2.0}, B, genes, host_out=(counts_h[:B], z_h))                     # wrong shape
+
+
+def test_nb_nll_and_vae_forward_vs_golden(golden_dir):
+    """fused NB reconstruction loss and the inference `TransformerVAE.forward` against the reference's outputs
+    (tests/golden/vae_loss_small.npz).  The loss kernel is fp32 throughout: per-cell sums agree to 1e-5 relative on the
+    reference's own (mu, theta); through the bf16 tensor-core encode/decode the loss moves by < 1e-3 relative."""
+    from scldm_b200 import ops
+
+    g = dict(np.load(os.path.join(golden_dir, "vae_loss_small.npz")))
+    counts, mu, theta = (torch.from_numpy(g[k]).cuda() for k in ("counts", "mu", "theta"))
+    per_cell = ops.nb_nll(counts, mu, theta)                       # (B, G) theta
+    assert rel_l2(per_cell, g["per_cell"]) < 1e-5
+    per_cell_shared = ops.nb_nll(counts, mu, theta[0])             # theta is one row for shared_theta
+    assert torch.allclose(per_cell_shared, per_cell, rtol=1e-6)
+    odd = ops.nb_nll(counts[:, :1499].contiguous(), mu[:, :1499].contiguous(), theta[:, :1499].contiguous())   # G % 4 != 0: scalar path
+    ref_odd = (-torch.from_numpy(g["log_nb"])[:, :1499]).sum(1)
+    assert rel_l2(odd, ref_odd) < 1e-5
+    cfg = VAEConfig(n_genes=1500)
+    vae, _ = make_vae(cfg)
+    B = counts.shape[0]
+    genes = torch.arange(1, cfg.n_genes + 1).unsqueeze(0).repeat(B, 1).cuda()
+    params, h_z = vae(counts, genes, torch.from_numpy(g["lib"]).cuda(), torch.from_numpy(g["counts_subset"]).cuda(),
+                      torch.from_numpy(g["genes_subset"]).cuda())
+    loss = vae.reconstruction_loss(counts, params)
+    e_mu, e_z = rel_l2(params["mu"], g["mu"]), rel_l2(h_z, g["h_z"])
+    e_l = abs(float(loss["llh"]) - float(g["llh"])) / abs(float(g["llh"]))
+    print(f"vae forward: mu {e_mu:.2e} h_z {e_z:.2e} llh rel {e_l:.2e}")
+    assert e_mu < 3e-2 and e_z < 2e-2 and e_l < 1e-3
+    with pytest.raises(RuntimeError):
+        ops.nb_nll(counts.cpu(), mu.cpu(), theta.cpu())            # no CPU fallback

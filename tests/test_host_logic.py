@@ -278,3 +278,27 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("with the oracle", ""), f
+
+
+def test_abi_argument_errors_are_reported_not_undefined():
+    """Error behaviour of the C-ABI (include/scldm_b200.h): bad arguments return SCLDM_EINVAL (-1) with a message in
+    scldm_last_error(), before any CUDA work - so this runs without a GPU.  No exceptions cross the boundary."""
+    lib = _lib.load()
+    none = None
+    calls = {
+        "scldm_csr_count": lambda: lib.scldm_csr_count(none, 1, 1, none, none, none),
+        "scldm_csr_fill": lambda: lib.scldm_csr_fill(none, 1, 1, none, none, none, none),
+        "scldm_nb_nll": lambda: lib.scldm_nb_nll(none, none, none, 0, 1, 1, none, none),
+        "scldm_tokenize_expressed": lambda: lib.scldm_tokenize_expressed(none, 1, 1, none, 1, 0, none, none, none, none, none),
+    }
+    for name, call in calls.items():
+        rc = call()
+        msg = lib.scldm_last_error().decode()
+        assert rc == -1 and len(msg) > 0, (name, rc, msg)
+    # theta stride shorter than a row is rejected (would read across rows)
+    buf = (ctypes.c_float * 8)()
+    rc = lib.scldm_nb_nll(buf, buf, buf, 2, 1, 4, buf, none)
+    assert rc == -1 and "nb_nll" in lib.scldm_last_error().decode()
+    # _lib.check turns a negative code into a RuntimeError that carries the library's message
+    with pytest.raises(RuntimeError, match="nb_nll"):
+        _lib.check(rc, "scldm_nb_nll")

@@ -154,3 +154,28 @@ def test_oracle_tokenizer_and_csr_small_cases():
         O.tokenize_cells_expressed(counts, genes, 2)
     indptr, indices, data = O.counts_to_csr(counts)
     assert indptr.tolist() == [0, 2, 2, 5] and indices.tolist() == [1, 3, 0, 1, 2] and data.tolist() == [3, 1, 2, 2, 2]
+
+
+def test_vae_forward_nb_loss(golden_dir):
+    """oracle `log_nb_positive` / `TransformerVAE.forward` + `VAE.loss` vs the reference's own outputs
+    (distributions.py:6-42, vae.py:29-56, models.py:233-247)."""
+    import numpy as np
+    import torch
+
+    from oracle import scldm_oracle as O
+    from oracle.make_golden import WEIGHT_SEED
+    from scldm_b200 import synthetic
+    from scldm_b200.config import VAEConfig
+
+    g = dict(np.load(os.path.join(golden_dir, "vae_loss_small.npz")))
+    cfg = VAEConfig(n_genes=1500)
+    sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
+    counts, mu, theta = (torch.from_numpy(g[k]) for k in ("counts", "mu", "theta"))
+    ll = O.log_nb_positive(counts, mu, theta)
+    assert torch.allclose(ll, torch.from_numpy(g["log_nb"]), rtol=1e-5, atol=1e-5)
+    genes = torch.arange(1, cfg.n_genes + 1).unsqueeze(0).repeat(counts.shape[0], 1)
+    with torch.no_grad():
+        mu_o, th_o, hz_o, per_cell, llh = O.vae_forward_loss(counts, genes, torch.from_numpy(g["lib"]), torch.from_numpy(g["counts_subset"]),
+                                                            torch.from_numpy(g["genes_subset"]), sd, cfg)
+    assert rel_l2(mu_o, g["mu"]) < TOL and rel_l2(hz_o, g["h_z"]) < TOL and rel_l2(th_o, g["theta"]) < 1e-6
+    assert rel_l2(per_cell, g["per_cell"]) < 1e-5 and abs(float(llh) - float(g["llh"])) < 1e-3 * abs(float(g["llh"]))
