@@ -160,6 +160,29 @@ def workload_name(dataset, dcfg, vcfg) -> str:
             f"sample_ode('euler', num_steps={NUM_STEPS}) = {NUM_STEPS - 1} evals, guidance {GUIDANCE}, decode + NB draw")
 
 
+def gpu_eager_sample(B: int, dcfg, vcfg, device):
+    """The same oracle port as `cpu_sample`, with every tensor on the GPU: what the reference's eager PyTorch generation
+    costs on this device (library kernels, TF32 matmuls as `experiments/scripts/inference.py:26` sets them).  A reported
+    comparator only - never part of `value` / `e2e`."""
+    from oracle import scldm_oracle as O
+    from scldm_b200 import synthetic
+
+    dsd = {k: v.to(device) for k, v in synthetic.dit_state_dict(dcfg, 1234).items()}
+    vsd = {k: v.to(device) for k, v in synthetic.vae_state_dict(vcfg, 1234).items()}
+    z0 = synthetic.randn("cpu.z0", (B, 16, 16)).to(device)
+    lab = {k: synthetic.randint("cpu.lab." + k, v, (B,)).to(device) for k, v in dcfg.class_vocab_sizes.items()}
+    w = {k: GUIDANCE for k in dcfg.class_vocab_sizes}
+    lsf = (8.0 + 0.3 * synthetic.randn("cpu.lsf", (B,))).to(device)
+    genes = torch.arange(1, vcfg.n_genes + 1, device=device).unsqueeze(0).expand(B, -1)
+
+    def step():
+        with torch.no_grad():
+            mu, theta, z = O.latent_diffusion_sample(z0, lab, w, genes, lsf, dsd, dcfg, vsd, vcfg, num_steps=NUM_STEPS, method="euler")
+            return O.nb_sample(mu, theta)
+
+    return step
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle port; the
     reference tree itself does not exist on the GPU box).  Rank 0 only."""
@@ -206,6 +229,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU comparator (oracle port on the same device)")
+    ap.add_argument("--eager-batch", type=int, default=1024)
     ap.add_argument("--dataset", default=DATASET, choices=["dentate_gyrus", "hlca", "tabula_muris", "parse1m", "replogle"],
                     help="gene-vocabulary / class-table shape (BASELINE configs 2-4); the headline line is dentate_gyrus")
     args = ap.parse_args()
@@ -359,6 +384,25 @@ def main():
                         "sample": f"1 x sample() of {args.cpu_batch} cells ({2 * args.cpu_batch} rows): same model, 49-eval Euler + CFG + decode + NB draw, fp32 oracle port",
                         "seconds": round(dtc, 2)}
 
+    gpu_eager = None
+    if rank == 0 and not args.no_gpu_eager:
+        prev = torch.get_float32_matmul_precision()
+        try:
+            torch.set_float32_matmul_precision("high")
+            stepg = gpu_eager_sample(args.eager_batch, dcfg, vcfg, device)
+            stepg()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); stepg(); b.record(); b.synchronize()
+            gpu_eager = {"value": 2 * args.eager_batch / (a.elapsed_time(b) / 1e3), "unit": "cells/s", "kind": "port",
+                         "sample": f"1 x sample() of {args.eager_batch} cells: oracle port of the reference modules run eagerly on the same GPU "
+                                   "(PyTorch library kernels, float32 matmul precision 'high' as the reference's inference script)"}
+        except Exception as e:  # a comparator must never take the bench line down
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        finally:
+            torch.set_float32_matmul_precision(prev)
+            torch.cuda.empty_cache()
+
     if rank == 0:
         fl = algorithmic_flops_per_row(G)
         line = {
@@ -390,6 +434,8 @@ def main():
                               "note": "per GPU, from the per-kernel CUDA-event times of one profiled step (rows per second of kernel time)"}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if gpu_eager:
+            line["gpu_eager_baseline"] = gpu_eager
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

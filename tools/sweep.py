@@ -11,7 +11,7 @@ runs = [("dentate_gyrus", b) for b in (64, 256, 1024, 4096, 16384)] + [(d, 2368)
 with open(out, "w") as f:
     for dataset, batch in runs:
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--dataset", dataset, "--batch", str(batch), "--steps", "3", "--warmup", "3",
-               "--no-cpu-baseline"]
+               "--no-cpu-baseline", "--no-gpu-eager"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
         try:
