@@ -129,11 +129,11 @@ typedef struct scldm_vae_dec_weights {
   const float* ca_ln1q_w;  /* decoder_cross_attention.ln_1q                                   */
   const float* ca_ln1q_b;
   const float* ca_wq;      /* decoder_cross_attention.attn.c_attn_q.weight [32][32]           */
-  const float* mcab_blob;  /* c_proj | ln_2 | mlp.w1 | mlp.w2 | mlp.c_proj^T | head w | head b */
+  const float* mcab_blob;  /* c_proj | ln_2 | mlp.w1 | mlp.w2 | mlp.c_proj^T | head w | head b | theta-head w | theta-head b */
   const float* emb;        /* input_layer.gene_embedding.weight [n_ids][32]                   */
-  const float* theta_tbl;  /* decoder_head.theta.weight [n_ids]                               */
+  const float* theta_tbl;  /* decoder_head.theta.weight [n_ids]; NULL = unshared-theta head   */
   const void* mcab_wfrag;  /* bf16 MCAB weights in mma.sync B-fragment order (80 x 64 u32)    */
-  const float* mcab_small; /* ln_2.weight[32] | ln_2.bias[32] | head w[32] | head b           */
+  const float* mcab_small; /* ln_2.weight[32] | ln_2.bias[32] | head w[32] | head b | pad[3] | theta-head w[32] | b | pad[3] */
 } scldm_vae_dec_weights;
 
 #define SCLDM_DECODE_TC 0   /* MCAB on tensor cores (bf16 operands, fp32 accumulate): default   */
@@ -147,7 +147,8 @@ size_t scldm_vae_decode_workspace_bytes(int32_t n_cells, int32_t n_genes);
 
 /* Replaces TransformerVAE.decode (vae.py:71-87) [+ NegativeBinomial.sample, models.py:819].
  *   z [n_cells][16][16]; genes [n_genes] int64 vocabulary ids shared by all cells; lib [n_cells]
- *   mu [n_cells][n_genes] / theta [n_genes] / counts [n_cells][n_genes]: any may be NULL           */
+ *   mu [n_cells][n_genes] / theta [n_genes] / counts [n_cells][n_genes]: any may be NULL.
+ *   Unshared-theta head (theta_tbl == NULL; stochastic_layers.py:111-113): theta is [n_cells][n_genes] and required. */
 int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void* qp_bf16, const float* z, int32_t n_cells,
                      const int64_t* genes, int32_t n_genes, const float* lib, float* mu, float* theta, float* counts,
                      uint64_t seed, int64_t cell_offset, int32_t precision, void* workspace, size_t workspace_bytes,

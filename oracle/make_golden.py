@@ -194,9 +194,24 @@ def nb_loss_golden() -> None:
     print("vae_loss_small", float(per_cell.mean()), per_cell.tolist())
 
 
+@torch.no_grad()
+def unshared_theta_golden() -> None:
+    """`TransformerVAE.decode` with an unshared-theta NB head (`shared_theta=False`: `params` is Linear(E->2) and theta =
+    exp(second channel), stochastic_layers.py:91-98,106-113) from the reference: tests/golden/vae_unshared_theta.npz."""
+    cfg, B, S = VAEConfig(n_genes=1500, shared_theta=False), 3, 400
+    sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
+    vae = ref_loader.build_reference_vae(cfg, sd)
+    z, genes, lib, _, _ = vae_inputs("vae_unshared", cfg, B, S)
+    d = vae.decode(z, genes, lib)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "vae_unshared_theta.npz"), z=z.numpy(), lib=lib.numpy(), mu=d.mu.numpy(), theta=d.theta.numpy())
+    print("vae_unshared_theta", d.mu.shape, d.theta.shape, float(d.theta.min()), float(d.theta.max()))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "nb_loss":   # mint only the fixture added later; the others stay byte-identical
-        nb_loss_golden()
+    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden}   # fixtures added after the first set; minted
+    if len(sys.argv) > 1 and sys.argv[1] in later:                                 # alone so the others stay byte-identical
+        later[sys.argv[1]]()
     else:
         main()
-        nb_loss_golden()
+        for fn in later.values():
+            fn()

@@ -512,6 +512,8 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
   if (precision == SCLDM_DECODE_FP32 && !qp) return fail(SCLDM_EINVAL, "fp32 decode needs the fp32 Q-side table");
   if (n_cells < 1 || n_genes < 1) return fail(SCLDM_EINVAL, "empty decode: n_cells=%d n_genes=%d", n_cells, n_genes);
   if (workspace_bytes < scldm_vae_decode_workspace_bytes(n_cells, n_genes)) return fail(SCLDM_ENOMEM, "workspace too small");
+  const bool unshared = w->theta_tbl == nullptr;   // unshared-theta head: theta is [n_cells][n_genes] and always needed (the NB draw reads it)
+  if (unshared && !theta) return fail(SCLDM_EINVAL, "unshared-theta head: a theta buffer [n_cells][n_genes] is required");
   int rc;
   if ((rc = prepare_kernels())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -542,7 +544,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
     mp.emb = w->emb; mp.qp = static_cast<const __nv_bfloat16*>(qp_bf16); mp.genes = reinterpret_cast<const long long*>(genes);
     mp.G = n_genes; mp.kvb = kvb; mp.n_cells = n_cells; mp.cells_per_block = cpb;
     mp.wfrag = static_cast<const uint32_t*>(w->mcab_wfrag); mp.small = w->mcab_small; mp.eps = w->eps;
-    mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
+    mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles; mp.log_theta = unshared ? theta : nullptr;
     if (g_dec_occ == 3) LAUNCH("mcab_decode_tc", vae::mcab_decode_tc_kernel<3><<<dim3(tiles, ceil_div(n_cells, cpb)), 256, 0, st>>>(mp));
     else LAUNCH("mcab_decode_tc", vae::mcab_decode_tc_kernel<2><<<dim3(tiles, ceil_div(n_cells, cpb)), 256, 0, st>>>(mp));
   } else {
@@ -550,6 +552,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
     mp.emb = w->emb; mp.qp = qp; mp.genes = reinterpret_cast<const long long*>(genes); mp.G = n_genes; mp.kv = kv; mp.n_cells = n_cells;
     mp.cells_per_block = cpb;
     mp.wblob = w->mcab_blob; mp.eps = w->eps; mp.logits = logits; mp.partials = partials; mp.gene_tiles = tiles;
+    mp.log_theta = unshared ? theta : nullptr;
     LAUNCH("mcab_decode", vae::mcab_decode_kernel<<<dim3(tiles, ceil_div(n_cells, cpb)), 128, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float), st>>>(mp));
   }
 

@@ -254,15 +254,17 @@ struct McabParams {
   int n_cells;
   int cells_per_block;
   // smem-resident weights, one contiguous fp32 blob:
-  //   wproj [32][32] (out,in) | ln2_w[32] | ln2_b[32] | w1 [88][32] | w2 [88][32] | w3_t [88][32] | head_w[32] | head_b
+  //   wproj [32][32] (out,in) | ln2_w[32] | ln2_b[32] | w1 [88][32] | w2 [88][32] | w3_t [88][32] | head_w[32] | head_b |
+  //   pad[3] | theta-head w[32] | theta-head b | pad[3]     (second output channel of an unshared-theta head, else zeros)
   const float* wblob;
   float eps;
+  float* log_theta;       // [cells][G] log theta of an unshared-theta head (stochastic_layers.py:111-113), or nullptr
   float* logits;          // [cells][G]
   float2* partials;       // [cells][gene_tiles] (max, sum exp(l - max))
   int gene_tiles;
 };
 constexpr int MW_PROJ = 0, MW_LN2W = 1024, MW_LN2B = 1056, MW_W1 = 1088, MW_W2 = MW_W1 + HID * E, MW_W3T = MW_W2 + HID * E,
-              MW_HW = MW_W3T + HID * E, MW_HB = MW_HW + E, MW_TOTAL = MW_HB + 4;
+              MW_HW = MW_W3T + HID * E, MW_HB = MW_HW + E, MW_HW2 = MW_HB + 4, MW_HB2 = MW_HW2 + E, MW_TOTAL = MW_HB2 + 4;
 
 __global__ void __launch_bounds__(128) mcab_decode_kernel(const McabParams p) {
   extern __shared__ __align__(16) float smf[];
@@ -371,6 +373,12 @@ __global__ void __launch_bounds__(128) mcab_decode_kernel(const McabParams p) {
 #pragma unroll
     for (int c = 0; c < E; ++c) logit += x[c] * sw[MW_HW + c];
     if (valid) p.logits[(size_t)cell * p.G + gi] = logit;
+    if (p.log_theta != nullptr) {   // unshared theta: second output channel of the head
+      float lt = sw[MW_HB2];
+#pragma unroll
+      for (int c = 0; c < E; ++c) lt += x[c] * sw[MW_HW2 + c];
+      if (valid) p.log_theta[(size_t)cell * p.G + gi] = lt;
+    }
     const float lm = valid ? logit : -INFINITY;
     const float wm = sm100::warp_max(lm);
     if ((tid & 31) == 0) red_m[tid >> 5] = wm;
@@ -399,8 +407,9 @@ struct McabTcParams {
   int n_cells;
   int cells_per_block;
   const uint32_t* wfrag;       // 80 fragments x 64 u32: proj (2x4) | per hidden chunk c<6: w1 (2x2) | w2 (2x2) | w3 (4)
-  const float* small;          // ln2_w[32] | ln2_b[32] | head_w[32] | head_b
+  const float* small;          // ln2_w[32] | ln2_b[32] | head_w[32] | head_b | pad[3] | theta-head w[32] | theta-head b | pad[3]
   float eps;
+  float* log_theta;            // [cells][G] (unshared-theta head) or nullptr
   float* logits;
   float2* partials;
   int gene_tiles;
@@ -428,12 +437,12 @@ __device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const McabTcParams p) {
   __shared__ uint2 s_frag[TC_NFRAG * 32];   // 20 KB
-  __shared__ float s_small[100];
+  __shared__ float s_small[136];
   __shared__ float red_m[2][8], red_s[2][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   for (int i = tid; i < TC_NFRAG * 32; i += 256) s_frag[i] = reinterpret_cast<const uint2*>(p.wfrag)[i];
-  if (tid < 97) s_small[tid] = p.small[tid];
+  if (tid < 136) s_small[tid] = p.small[tid];
   __syncthreads();
 
   // ---- gene-side operands of this warp's 16 genes (cell invariant) ----
@@ -585,6 +594,21 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const M
     if (t == 0) {
       if (v0) p.logits[(size_t)cell * p.G + gi0] = la;
       if (v1) p.logits[(size_t)cell * p.G + gi1] = lb2;
+    }
+    if (p.log_theta != nullptr) {   // unshared theta: second output channel of the head (weights read from shared memory: rare path)
+      float ta = 0.f, tb = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float w0 = s_small[100 + nt * 8 + 2 * t], w1 = s_small[100 + nt * 8 + 2 * t + 1];
+        ta += x[nt][0] * w0 + x[nt][1] * w1;
+        tb += x[nt][2] * w0 + x[nt][3] * w1;
+      }
+      ta += __shfl_xor_sync(0xffffffffu, ta, 1); ta += __shfl_xor_sync(0xffffffffu, ta, 2);
+      tb += __shfl_xor_sync(0xffffffffu, tb, 1); tb += __shfl_xor_sync(0xffffffffu, tb, 2);
+      if (t == 0) {
+        if (v0) p.log_theta[(size_t)cell * p.G + gi0] = ta + s_small[132];
+        if (v1) p.log_theta[(size_t)cell * p.G + gi1] = tb + s_small[132];
+      }
     }
     const float lm = fmaxf(v0 ? la : -INFINITY, v1 ? lb2 : -INFINITY);
     const float wm = sm100::warp_max(lm);
@@ -889,7 +913,8 @@ struct NbParams {
   int G;
   int n_cells;
   const float* lib;        // [cells] library size
-  const float* theta_tbl;  // decoder_head.theta.weight [n_ids] (log theta)
+  const float* theta_tbl;  // decoder_head.theta.weight [n_ids] (log theta); nullptr for an unshared-theta head, whose log theta
+                           // the MCAB kernel left in `theta` [cells][G] (exponentiated in place here)
   const long long* genes;  // [G]
   float* mu;               // [cells][G] or nullptr
   float* theta;            // [G] or nullptr (written by cell 0 blocks)
@@ -933,9 +958,15 @@ __global__ void __launch_bounds__(256) nb_finalize_kernel(const NbParams p) {
   const long long gcell = p.cell_offset + cell;
   for (int gi = blockIdx.y * 256 + tid; gi < p.G; gi += gridDim.y * 256) {
     const float muv = __expf(p.logits[(size_t)cell * p.G + gi] - gm) * scale;
-    const float th = __expf(p.theta_tbl[p.genes[gi]]);
+    float th;
+    if (p.theta_tbl != nullptr) {
+      th = __expf(p.theta_tbl[p.genes[gi]]);
+      if (p.theta && cell == 0) p.theta[gi] = th;
+    } else {
+      th = __expf(p.theta[(size_t)cell * p.G + gi]);
+      p.theta[(size_t)cell * p.G + gi] = th;
+    }
     if (p.mu) p.mu[(size_t)cell * p.G + gi] = muv;
-    if (p.theta && cell == 0) p.theta[gi] = th;
     if (p.counts) {
       rng::Philox g(p.seed, (uint32_t)gi, (uint32_t)gcell, (uint32_t)(gcell >> 32) ^ 0x4E42u);
       p.counts[(size_t)cell * p.G + gi] = rng::negative_binomial(g, muv, th);

@@ -160,7 +160,7 @@ def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, l
                want_counts=False, seed: int = 0, cell_offset: int = 0, out_mu: torch.Tensor | None = None,
                out_counts: torch.Tensor | None = None, precision: str = "bf16"):
     """z [cells,16,16] fp32, genes [G] int64 (shared by all cells), lib_size [cells] fp32 ->
-    (mu [cells,G] | None, theta [G], counts [cells,G] | None)."""
+    (mu [cells,G] | None, theta [G] (shared table) or [cells,G] (unshared-theta head), counts [cells,G] | None)."""
     lib = _lib.load()
     _require_cuda(z, "z")
     n_cells, G = z.shape[0], genes.numel()
@@ -175,7 +175,7 @@ def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, l
     mu = out_mu if out_mu is not None else (torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_mu else None)
     counts = out_counts if out_counts is not None else (
         torch.empty(n_cells, G, dtype=torch.float32, device=z.device) if want_counts else None)
-    theta = torch.empty(G, dtype=torch.float32, device=z.device)
+    theta = torch.empty(G if getattr(packed, "shared_theta", True) else (n_cells, G), dtype=torch.float32, device=z.device)
     nbytes = int(lib.scldm_vae_decode_workspace_bytes(n_cells, G))
     ws = _workspace(z.device, nbytes, "vae")
     rc = lib.scldm_vae_decode(C.byref(packed.struct), qp.data_ptr(), qpb.data_ptr(), z.data_ptr(), n_cells, genes.data_ptr(), G,

@@ -180,7 +180,7 @@ class PackedDiT:
 # offsets inside one packed VAE Block / the MCAB blob: must match csrc/vae_kernels.cuh
 VAE_HID = 88
 VAE_BLOCK_STRIDE = 128 + 32 * 96 + 32 * 32 + 2 * 32 * VAE_HID + VAE_HID * 32
-MCAB_TOTAL = 1024 + 64 + 3 * VAE_HID * 32 + 32 + 4
+MCAB_TOTAL = 1024 + 64 + 3 * VAE_HID * 32 + 2 * (32 + 4)
 
 
 class PackedVAEDecoder:
@@ -189,8 +189,8 @@ class PackedVAEDecoder:
     def __init__(self, sd: dict, cfg: VAEConfig, device):
         if (cfg.n_embed, cfg.n_embed_latent, cfg.n_inducing_points, cfg.n_head, cfg.n_head_cross, cfg.hidden) != (32, 16, 16, 8, 4, VAE_HID):
             raise NotImplementedError(f"sm_100a VAE kernels are specialised to the shipped vae_base dims; got {cfg}")
-        if cfg.bias or cfg.use_adaln or not cfg.shared_embedding or not cfg.shared_theta:
-            raise NotImplementedError("decoder kernels cover bias=False, use_adaln=False, shared_embedding, shared_theta")
+        if cfg.bias or cfg.use_adaln or not cfg.shared_embedding:
+            raise NotImplementedError("decoder kernels cover bias=False, use_adaln=False, shared_embedding")
         self.cfg = cfg
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
         g = lambda n: sd[n].detach().float().cpu()  # noqa: E731  (pack on the host once, then upload)
@@ -213,7 +213,7 @@ class PackedVAEDecoder:
         blob = torch.cat([
             g(c + "attn.c_proj.weight").reshape(-1), g(c + "ln_2.weight"), g(c + "ln_2.bias"),
             g(c + "mlp.w1.weight").reshape(-1), g(c + "mlp.w2.weight").reshape(-1), g(c + "mlp.c_proj.weight").T.reshape(-1),
-            g("decoder_head.params.weight").reshape(-1), g("decoder_head.params.bias").reshape(-1), torch.zeros(3),
+            *self._head_rows(g, cfg),
         ])
         assert blob.numel() == MCAB_TOTAL
         self.mcab_blob = f32(blob)
@@ -231,19 +231,33 @@ class PackedVAEDecoder:
             frags += [f3[ch, nt] for nt in range(4)]
         self.mcab_wfrag = torch.stack(frags).to(device).contiguous()   # [80][32][4] bf16
         assert self.mcab_wfrag.shape == (80, 32, 4)
-        self.mcab_small = f32(torch.cat([g(c + "ln_2.weight"), g(c + "ln_2.bias"), g("decoder_head.params.weight").reshape(-1),
-                                         g("decoder_head.params.bias").reshape(-1), torch.zeros(3)]))
+        self.mcab_small = f32(torch.cat([g(c + "ln_2.weight"), g(c + "ln_2.bias"), *self._head_rows(g, cfg)]))
+        assert self.mcab_small.numel() == 136
         self.emb = f32(g("input_layer.gene_embedding.weight"))
-        self.theta_tbl = f32(g("decoder_head.theta.weight").reshape(-1))
+        self.shared_theta = bool(cfg.shared_theta)
+        self.theta_tbl = f32(g("decoder_head.theta.weight").reshape(-1)) if cfg.shared_theta else None
         s = _lib.VaeDecWeights()
         s.n_layer, s.n_ids, s.eps = cfg.n_layer, self.emb.shape[0], float(cfg.layernorm_eps)
         for name in ("win_t", "blocks", "ca_ln1_w", "ca_ln1_b", "ca_wkv_t", "ca_ln1q_w", "ca_ln1q_b", "ca_wq", "mcab_blob", "emb",
                      "theta_tbl", "mcab_wfrag", "mcab_small"):
-            setattr(s, name, getattr(self, name).data_ptr())
+            t = getattr(self, name)
+            setattr(s, name, t.data_ptr() if t is not None else None)   # theta_tbl is NULL for an unshared-theta head
         self.struct = s
         self.device = torch.device(device)
         self.qp = None  # Q-side tables (fp32, bf16), filled lazily by ops.vae_qside
         self.qp_bf16 = None
+
+
+def _head_rows_impl(g, cfg) -> list:
+    """NB head rows of the packed blobs: logit w[32] | b | pad[3] | log-theta w[32] | b | pad[3].  `params` is Linear(E->1) for a
+    shared theta table and Linear(E->2) = (logit, log theta) otherwise (`stochastic_layers.py:91-98,106-113`)."""
+    w, b = g("decoder_head.params.weight"), g("decoder_head.params.bias")
+    if cfg.shared_theta:
+        return [w.reshape(-1), b.reshape(-1), torch.zeros(3), torch.zeros(32 + 4)]
+    return [w[0], b[0:1], torch.zeros(3), w[1], b[1:2], torch.zeros(3)]
+
+
+PackedVAEDecoder._head_rows = staticmethod(_head_rows_impl)
 
 
 def _pack_vae_blocks(g, prefix: str, n_layer: int) -> torch.Tensor:

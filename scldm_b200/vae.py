@@ -75,7 +75,7 @@ class TransformerVAE(nn.Module):
         zc = z.contiguous().float()
         prec = self.decode_precision
         mu, theta, _ = ops.vae_decode(packed, zc, gvec, library_size, want_mu=True, want_counts=False, precision=prec)
-        theta_full = theta.unsqueeze(0).expand(z.shape[0], -1)
+        theta_full = theta.unsqueeze(0).expand(z.shape[0], -1) if theta.dim() == 1 else theta
         seed, offset = self.sample_seed, self.sample_offset
 
         def sampler():

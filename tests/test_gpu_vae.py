@@ -415,3 +415,31 @@ def test_nb_nll_and_vae_forward_vs_golden(golden_dir):
     assert e_mu < 3e-2 and e_z < 2e-2 and e_l < 1e-3
     with pytest.raises(RuntimeError):
         ops.nb_nll(counts.cpu(), mu.cpu(), theta.cpu())            # no CPU fallback
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decode_unshared_theta_vs_golden(golden_dir, precision):
+    """NB head with `shared_theta=False` (`params` = Linear(E->2), theta = exp(second channel), stochastic_layers.py:106-113):
+    mu and the per-cell theta (B, G) against the reference; the NB draw uses that per-cell theta."""
+    g = dict(np.load(os.path.join(golden_dir, "vae_unshared_theta.npz")))
+    cfg = VAEConfig(n_genes=1500, shared_theta=False)
+    vae, _ = make_vae(cfg, precision)
+    B = g["z"].shape[0]
+    genes = torch.arange(1, cfg.n_genes + 1).unsqueeze(0).repeat(B, 1).cuda()
+    lib = torch.from_numpy(g["lib"]).cuda()
+    d = vae.decode(torch.from_numpy(g["z"]).cuda(), genes, lib)
+    e_mu, e_th = rel_l2(d.mu, g["mu"]), rel_l2(d.theta, g["theta"])
+    print(f"unshared theta [{precision}]: mu {e_mu:.2e} theta {e_th:.2e}")
+    assert d.theta.shape == (B, cfg.n_genes)
+    assert e_mu < MU_TOL[precision] and e_th < MU_TOL[precision]
+    assert torch.allclose(d.mu.sum(1).cpu(), torch.from_numpy(g["lib"]).reshape(-1), rtol=1e-4)
+    counts = d.sample()
+    assert counts.shape == (B, cfg.n_genes) and bool((counts >= 0).all()) and bool((counts == counts.round()).all())
+    # total count vs total mean within 5 standard deviations of the NB sum (var = mu + mu^2 / theta; theta spans 0.006 ... 112 here)
+    sd_total = float((d.mu + d.mu**2 / d.theta).double().sum().sqrt())
+    assert abs(float(counts.double().sum()) - float(d.mu.double().sum())) < 5 * sd_total
+    # and the over-dispersed genes really are drawn with their own theta: zero fraction matches (theta/(theta+mu))^theta on average
+    p0 = (d.theta / (d.theta + d.mu)).pow(d.theta).double().mean()
+    assert abs(float((counts == 0).double().mean()) - float(p0)) < 0.03
+    c2, _, _ = vae.decode_counts(torch.from_numpy(g["z"]).cuda(), genes, lib.reshape(-1), seed=3)
+    assert c2.shape == (B, cfg.n_genes)

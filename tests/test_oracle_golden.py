@@ -179,3 +179,24 @@ def test_vae_forward_nb_loss(golden_dir):
                                                             torch.from_numpy(g["genes_subset"]), sd, cfg)
     assert rel_l2(mu_o, g["mu"]) < TOL and rel_l2(hz_o, g["h_z"]) < TOL and rel_l2(th_o, g["theta"]) < 1e-6
     assert rel_l2(per_cell, g["per_cell"]) < 1e-5 and abs(float(llh) - float(g["llh"])) < 1e-3 * abs(float(g["llh"]))
+
+
+def test_vae_decode_unshared_theta(golden_dir):
+    """oracle decode with the unshared-theta NB head (stochastic_layers.py:91-98,106-113) vs the reference's output."""
+    import numpy as np
+    import torch
+
+    from oracle import scldm_oracle as O
+    from oracle.make_golden import WEIGHT_SEED
+    from scldm_b200 import synthetic
+    from scldm_b200.config import VAEConfig
+
+    g = dict(np.load(os.path.join(golden_dir, "vae_unshared_theta.npz")))
+    cfg = VAEConfig(n_genes=1500, shared_theta=False)
+    sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
+    B = g["z"].shape[0]
+    genes = torch.arange(1, cfg.n_genes + 1).unsqueeze(0).repeat(B, 1)
+    with torch.no_grad():
+        mu, theta = O.vae_decode(torch.from_numpy(g["z"]), genes, torch.from_numpy(g["lib"]), sd, cfg)
+    assert theta.shape == (B, cfg.n_genes)
+    assert rel_l2(mu, g["mu"]) < TOL and rel_l2(theta, g["theta"]) < TOL
