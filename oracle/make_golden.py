@@ -207,8 +207,30 @@ def unshared_theta_golden() -> None:
     print("vae_unshared_theta", d.mu.shape, d.theta.shape, float(d.theta.min()), float(d.theta.max()))
 
 
+@torch.no_grad()
+def label_dropout_golden() -> None:
+    """Training-mode CFG label dropout of the reference (`nnets.py:389-456`): the summed class embedding the reference DiT
+    builds in train mode under a fixed CPU seed, for the mutually-exclusive 2-class and the joint model:
+    tests/golden/dit_label_dropout.npz."""
+    arrays = {}
+    for name in ("dit_me2", "dit_joint"):
+        case = golden_cases()[name]
+        cfg = case["cfg"]
+        sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+        model = ref_loader.build_reference_dit(cfg, sd).train()
+        labels = {k: synthetic.randint(f"drop.{name}.{k}", v, (64,)) for k, v in cfg.class_vocab_sizes.items()}
+        for rep in range(3):
+            torch.manual_seed(1000 + rep)
+            emb = model._get_condition_embedding(labels, force_drop_ids=True)
+            arrays[f"{name}.emb{rep}"] = emb.squeeze(1).numpy()
+        for k, v in labels.items():
+            arrays[f"{name}.label.{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "dit_label_dropout.npz"), **arrays)
+    print("dit_label_dropout", {k: v.shape for k, v in arrays.items()})
+
+
 if __name__ == "__main__":
-    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden}   # fixtures added after the first set; minted
+    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden}   # fixtures added after the first set; minted
     if len(sys.argv) > 1 and sys.argv[1] in later:                                 # alone so the others stay byte-identical
         later[sys.argv[1]]()
     else:

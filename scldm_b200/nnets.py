@@ -146,24 +146,41 @@ class DiT(nn.Module):
             return torch.zeros(0, n, dtype=torch.int32, device=device)
         return torch.stack(rows)
 
-    def _active_labels(self, condition: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
-        """Which labels enter the embedding in eval mode (`nnets.py:389-456`): joint -> all given classes;
-        mutually_exclusive -> ONE class, picked with torch.randint when several are given (as the reference)."""
+    def _active_labels(self, condition: dict[str, torch.Tensor], force_drop_ids: bool = False) -> dict[str, torch.Tensor]:
+        """Which labels enter the embedding (`nnets.py:380-456`), with the reference's sequence of RNG calls on the labels' device:
+        mutually_exclusive -> ONE class picked with `torch.randint` (even when only one is given), and with `force_drop_ids`
+        (training) the picked class's labels are replaced by the null token where `torch.rand(B) < cfg_dropout_prob`;
+        joint -> all given classes, all dropped together by one mask whenever the module is in training mode (the reference
+        ignores `force_drop_ids` on this branch, `nnets.py:441-447`)."""
         avail = [n for n in sorted(self.class_vocab_sizes.keys()) if n in condition]
-        if self.condition_strategy == "joint" or len(avail) <= 1:
-            return {n: condition[n] for n in avail}
-        pick = int(torch.randint(0, len(avail), ()).item())
-        return {avail[pick]: condition[avail[pick]]}
+        if not avail:
+            return {}
+        first = condition[avail[0]]
+        n, device = first.shape[0], first.device
+        if self.condition_strategy == "joint":
+            if not self.training:
+                return {k: condition[k] for k in avail}
+            drop = torch.rand(n, device=device) < self.cfg_dropout_prob
+            return {k: torch.where(drop, torch.full_like(condition[k], self._null(k)), condition[k]) for k in avail}
+        r = torch.randint(0, len(avail), (), device=device)      # drawn even for one class, as the reference (same RNG consumption)
+        pick = int(r.item()) if len(avail) > 1 else 0
+        if not self.training and force_drop_ids:
+            raise AssertionError("force_drop_ids must be False when not training")   # nnets.py:399-400
+        name = avail[pick]
+        vals = condition[name]
+        if force_drop_ids:
+            drop = torch.rand(n, device=device) < self.cfg_dropout_prob
+            vals = torch.where(drop, torch.full_like(vals, self._null(name)), vals)
+        return {name: vals}
 
     def forward(self, x: torch.Tensor, t: torch.Tensor, condition: dict[str, torch.Tensor], force_drop_ids: bool | None = None):
-        """`DiT.forward` (`nnets.py:273-297`), eval semantics (no CFG label dropout)."""
+        """`DiT.forward` (`nnets.py:273-297`).  In training mode the CFG label dropout of the reference is applied to the labels
+        on the host side (the kernels only ever see label rows); no autograd graph is built (forward only)."""
         if force_drop_ids is None:
             force_drop_ids = self.training
-        if force_drop_ids:
-            raise NotImplementedError("training-mode CFG label dropout: the training step is a later row (SURVEY.md §8f)")
         packed = self.packed()
         n = x.shape[0]
-        cls = self._cls_rows(self._active_labels(condition or {}), n, x.device)
+        cls = self._cls_rows(self._active_labels(condition or {}, force_drop_ids), n, x.device)
         plan = ops.DitPlan(packed, n_u=n, n_g=0, n_f=1, coef=[1.0], cls_idx=cls,
                            slot_mod=torch.arange(n, dtype=torch.int32, device=x.device), slot_mode="identity")
         return ops.dit_forward(plan, x.contiguous().float(), t.float())

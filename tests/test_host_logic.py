@@ -302,3 +302,37 @@ def test_abi_argument_errors_are_reported_not_undefined():
     # _lib.check turns a negative code into a RuntimeError that carries the library's message
     with pytest.raises(RuntimeError, match="nb_nll"):
         _lib.check(rc, "scldm_nb_nll")
+
+
+@pytest.mark.parametrize("name", ["dit_me2", "dit_joint"])
+def test_training_mode_label_dropout_matches_reference(golden_dir, name):
+    """Training-mode CFG label dropout (`nnets.py:389-456`) is host logic here: under the same CPU seed the label rows the
+    kernels would receive reproduce the summed class embedding the reference DiT builds in train mode (same sequence of
+    `torch.randint` / `torch.rand` draws; the golden holds three seeds so both the class pick and the drop mask vary)."""
+    import numpy as np
+
+    from scldm_b200.nnets import DiT
+
+    g = dict(np.load(os.path.join(golden_dir, "dit_label_dropout.npz")))
+    cfg = golden_cases()[name]["cfg"]
+    sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    m = DiT(**cfg.kwargs())
+    m.load_state_dict(sd)
+    m.train()
+    labels = {k: torch.from_numpy(g[f"{name}.label.{k}"]) for k in cfg.class_vocab_sizes}
+    n = 64
+    seen = set()
+    for rep in range(3):
+        torch.manual_seed(1000 + rep)
+        rows = m._cls_rows(m._active_labels(labels, force_drop_ids=True), n, "cpu")        # [n_class, n] table rows
+        emb = sum(sd[f"class_embeddings.{cname}.weight"][rows[i].long()] for i, cname in enumerate(sorted(cfg.class_vocab_sizes)))
+        assert torch.allclose(emb, torch.from_numpy(g[f"{name}.emb{rep}"]), atol=1e-6)
+        seen.add(tuple(rows.reshape(-1).tolist()))
+    assert len(seen) == 3                                     # the three seeds really gave different masks
+    m.eval()
+    if cfg.condition_strategy != "joint":
+        with pytest.raises(AssertionError):
+            m._active_labels(labels, force_drop_ids=True)     # the reference asserts this too (nnets.py:399-400)
+    rows = m._cls_rows(m._active_labels(labels, force_drop_ids=False), n, "cpu")
+    nulls = torch.tensor([cfg.class_vocab_sizes[c] for c in sorted(cfg.class_vocab_sizes)])
+    assert int((rows != nulls[:, None]).any(1).sum()) == (len(labels) if cfg.condition_strategy == "joint" else 1)
