@@ -1,2 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_vae.py tests/test_gpu_datasets.py -m gpu -q -x --timeout=600 -p no:cacheprovider -s 2>&1 | grep -E "unshared|passed|failed|Error|error" | tail -12
-python bench.py --no-cpu-baseline --steps 3 --warmup 3 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('bench', round(j['value']), round(j['e2e']['value']), j['roofline']['avg_launch_us'], j.get('gpu_eager_baseline'))"
+python __graft_entry__.py --smoke 2>&1 | tail -2
+for n in 2 4; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/bench_r04_${n}gpu.json 2> gpurun_out/bench_r04_${n}gpu.err
+python -c "
+import json; j=json.loads(open('gpurun_out/bench_r04_${n}gpu.json').read().strip().splitlines()[-1]); print(j['n_gpus'], round(j['value']), round(j['e2e']['value']), j['ms_per_step'], j['clocks'])"
+done
