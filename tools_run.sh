@@ -1,6 +1,4 @@
-python __graft_entry__.py --smoke 2>&1 | tail -2
-for n in 2 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/bench_r04_${n}gpu.json 2> gpurun_out/bench_r04_${n}gpu.err
-python -c "
-import json; j=json.loads(open('gpurun_out/bench_r04_${n}gpu.json').read().strip().splitlines()[-1]); print(j['n_gpus'], round(j['value']), round(j['e2e']['value']), j['ms_per_step'], j['clocks'])"
+for e in 6 14; do
+  echo "EXP=$e"; SCLDM_EXP=$e python bench.py --no-cpu-baseline --no-e2e --no-gpu-eager --steps 3 --warmup 3 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read()); print(round(j['value']), j['roofline']['avg_launch_us'], j['roofline']['frac'])"
 done
+SCLDM_EXP=14 python tools/kernel_timeline.py 1184 2>&1 | grep -A1 "median cycles" | grep "\["
