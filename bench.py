@@ -89,7 +89,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def build_models(device, dataset=DATASET, seed=1234):
+def build_models(device, dataset=DATASET, seed=1234, method="euler"):
     from scldm_b200 import synthetic
     from scldm_b200.config import dataset_configs
     from scldm_b200.models import LatentDiffusion
@@ -104,16 +104,16 @@ def build_models(device, dataset=DATASET, seed=1234):
     vae.load_state_dict(synthetic.vae_state_dict(vcfg, seed))
     mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes, seed)
     ldm = LatentDiffusion(vae.to(device).eval(), dit.to(device).eval(), create_transport("Linear", "velocity", "velocity"),
-                          mu_size_factor=mu_t, sd_size_factor=sd_t, sampling_method="euler", num_steps=NUM_STEPS, seed=4321)
+                          mu_size_factor=mu_t, sd_size_factor=sd_t, sampling_method=method, num_steps=NUM_STEPS, seed=4321)
     return ldm, dcfg, vcfg
 
 
-def algorithmic_flops_per_row(G: int) -> dict:
-    """DiT forward 210.8 MFLOP/cell; 49 evals; CFG => 1.5 forwards per output row; decode 2.2M + G*23104."""
+def algorithmic_flops_per_row(G: int, evals: int = 49) -> dict:
+    """DiT forward 210.8 MFLOP/cell; 49 evals (Euler); CFG => 1.5 forwards per output row; decode 2.2M + G*23104."""
     D, H, M, L, N = 256, 684, 16, 16, 8
     dit = M * (N * (8 * D * D + 6 * D * H + 4 * M * D) + 4 * L * D) + N * 12 * D * D + 4 * D * D + 2 * (256 * D + D * D)
     dec = 2.2e6 + G * 23104
-    return {"dit_forward": dit, "decode": dec, "row_cfg": 1.5 * 49 * dit + dec}
+    return {"dit_forward": dit, "decode": dec, "row_cfg": 1.5 * evals * dit + dec}
 
 
 # per-launch algorithmic FLOPs of the GEMM kernel classes (rows = slots*16 actual, unpadded N/K)
@@ -153,11 +153,13 @@ def cpu_sample(B: int, dcfg, vcfg, threads: int):
     return step
 
 
-def workload_name(dataset, dcfg, vcfg) -> str:
+def workload_name(dataset, dcfg, vcfg, method="euler") -> str:
     cls = ", ".join(f"{k}:{v}" for k, v in dcfg.class_vocab_sizes.items())
-    tag = " (BASELINE configs[1])" if dataset == "dentate_gyrus" else ""
+    tag = " (BASELINE configs[1])" if dataset == "dentate_gyrus" and method == "euler" else ""
+    evals = {"euler": f"{NUM_STEPS - 1} evals", "heun2": f"{2 * (NUM_STEPS - 1)} evals", "midpoint": f"{2 * (NUM_STEPS - 1)} evals",
+             "dopri5": "adaptive, atol = rtol = 1e-5 (the reference's default solver)"}[method]
     return (f"{dataset}-shaped generation with CFG{tag}: G={vcfg.n_genes}, classes {{{cls}}} {dcfg.condition_strategy}, "
-            f"sample_ode('euler', num_steps={NUM_STEPS}) = {NUM_STEPS - 1} evals, guidance {GUIDANCE}, decode + NB draw")
+            f"sample_ode('{method}', num_steps={NUM_STEPS}) = {evals}, guidance {GUIDANCE}, decode + NB draw")
 
 
 def gpu_eager_sample(B: int, dcfg, vcfg, device):
@@ -229,6 +231,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
+    ap.add_argument("--method", default="euler", choices=["euler", "heun2", "midpoint", "dopri5"],
+                    help="ODE solver of sample_ode; the headline line is the fixed-grid Euler of BASELINE configs[1]")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU comparator (oracle port on the same device)")
     ap.add_argument("--eager-batch", type=int, default=1024)
     ap.add_argument("--dataset", default=DATASET, choices=["dentate_gyrus", "hlca", "tabula_muris", "parse1m", "replogle"],
@@ -254,7 +258,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from scldm_b200 import ops
 
-    ldm, dcfg, vcfg = build_models(device, args.dataset)
+    ldm, dcfg, vcfg = build_models(device, args.dataset, method=args.method)
     if args.chunk > 0:
         ldm.cell_chunk = args.chunk
     B, G = args.batch, vcfg.n_genes
@@ -404,15 +408,18 @@ def main():
             torch.cuda.empty_cache()
 
     if rank == 0:
-        fl = algorithmic_flops_per_row(G)
+        evals = {"euler": NUM_STEPS - 1, "heun2": 2 * (NUM_STEPS - 1), "midpoint": 2 * (NUM_STEPS - 1)}.get(args.method)
+        if evals is None:   # adaptive: function evaluations of the last solve
+            evals = int(getattr(ldm.transport_sampler, "last_nfe", 0))
+        fl = algorithmic_flops_per_row(G, evals)
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.dataset, dcfg, vcfg),
+            "config": {"workload": workload_name(args.dataset, dcfg, vcfg, args.method),
                        "cells_per_step_per_gpu": B, "rows_per_step": rows_per_step, "ode_chunk_cells": min(ldm.cell_chunk, B),
                        "l2": "256 MB flush buffer written between timed steps", "parallelism": f"cells sharded over {world} GPU(s), no collective",
-                       "algorithmic_gflop_per_row": round(fl["row_cfg"] / 1e9, 3)},
+                       "algorithmic_gflop_per_row": round(fl["row_cfg"] / 1e9, 3), "dit_evaluations_per_solve": evals},
             "clocks": clocks,
             "gpu_launches": int(launches),
             "model_tflops": round(value * fl["row_cfg"] / 1e12, 1),

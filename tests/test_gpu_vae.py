@@ -443,3 +443,51 @@ def test_decode_unshared_theta_vs_golden(golden_dir, precision):
     assert abs(float((counts == 0).double().mean()) - float(p0)) < 0.03
     c2, _, _ = vae.decode_counts(torch.from_numpy(g["z"]).cuda(), genes, lib.reshape(-1), seed=3)
     assert c2.shape == (B, cfg.n_genes)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decode_is_invariant_to_latent_token_order(precision):
+    """The decoder treats the 16 latents as a SET (no positional encoding in `Decoder.forward`, nnets.py:200-208; self-attention and
+    the MCAB softmax over keys are permutation-equivariant / -invariant): decoding a permuted latent set gives the same NB means.
+    Checked at the full dentate_gyrus vocabulary (G = 17 002)."""
+    cfg = VAEConfig(n_genes=17002)
+    vae, _ = make_vae(cfg, precision)
+    B = 24
+    z = synthetic.randn("perm.z", (B, 16, 16)).cuda()
+    lib = torch.exp(8.0 + 0.3 * synthetic.randn("perm.lsf", (B, 1))).cuda()
+    genes = torch.arange(1, cfg.n_genes + 1).cuda().unsqueeze(0).expand(B, -1)
+    perm = torch.from_numpy(np.random.default_rng(3).permutation(16)).cuda()
+    mu_a = vae.decode(z, genes, lib).mu
+    mu_b = vae.decode(z[:, perm].contiguous(), genes, lib).mu
+    e = rel_l2(mu_b, mu_a)
+    print(f"latent permutation [{precision}]: mu rel-L2 {e:.2e}")
+    assert e < (1e-5 if precision == "fp32" else 5e-3)
+
+
+def test_full_size_generation_properties():
+    """BASELINE configs[1] at the bench's size (2368 cells -> 4736 rows, G = 17 002, 49-eval Euler + CFG): properties that do not need
+    the CPU oracle - shapes, finiteness, integer counts, sum_g mu = library size per row, unconditional and guided halves share the
+    library sizes, and chunking invariance of the latents (cells are independent, RNG keyed by the global cell index)."""
+    import bench
+
+    ldm, dcfg, vcfg = bench.build_models(torch.device("cuda"))
+    B, G = 2368, vcfg.n_genes
+    lab = {"clusters": torch.randint(0, 14, (B,), generator=torch.Generator().manual_seed(5)).cuda()}
+    genes = torch.arange(1, G + 1).cuda().unsqueeze(0).expand(B, -1)
+    ldm.cells_generated = 0
+    counts, z, mu = ldm.sample(lab, {"clusters": 2.0}, B, genes, return_mu=True)
+    assert counts.shape == (2 * B, G) and z.shape == (2 * B, 16, 16) and mu.shape == (2 * B, G)
+    assert bool(torch.isfinite(z).all()) and bool(torch.isfinite(mu).all()) and bool((mu > 0).all())
+    assert bool((counts >= 0).all()) and bool((counts == counts.round()).all())
+    lib = mu.sum(1)
+    assert torch.allclose(lib[:B], lib[B:], rtol=1e-4)                      # same library size for the unconditional / guided twin
+    assert 6.0 < float(lib.log().mean()) < 10.0                             # synthetic tables: mu_c ~ U(7,9) on the log scale
+    theta = torch.exp(ldm.vae_model.decoder_head.theta.weight.detach()[1:, 0]).double()
+    sd_total = float((mu.double() + mu.double() ** 2 / theta[None, :]).sum().sqrt())
+    assert abs(float(counts.double().sum()) - float(mu.double().sum())) < 5 * sd_total      # 80 M NB draws: total within 5 sd
+    assert float((z[:B] - z[B:]).abs().max()) > 1e-3                        # guidance 2.0 moves the guided half
+    assert 0.5 < float(z.std()) < 2.0
+    ldm.cells_generated = 0
+    ldm.cell_chunk = 592
+    _, z2 = ldm.sample(lab, {"clusters": 2.0}, B, genes)
+    assert torch.equal(z2, z)

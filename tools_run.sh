@@ -1,4 +1,5 @@
-for e in 6 14; do
-  echo "EXP=$e"; SCLDM_EXP=$e python bench.py --no-cpu-baseline --no-e2e --no-gpu-eager --steps 3 --warmup 3 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read()); print(round(j['value']), j['roofline']['avg_launch_us'], j['roofline']['frac'])"
+timeout 900 python -m pytest tests/test_gpu_vae.py -m gpu -q -x --timeout=600 -p no:cacheprovider -s -k "latent_token_order or full_size" 2>&1 | grep -E "latent|passed|failed|Error|assert" | tail -8
+for m in heun2 dopri5; do
+python bench.py --method $m --no-cpu-baseline --no-gpu-eager --steps 2 --warmup 3 > gpurun_out/bench_r04_$m.json 2>gpurun_out/bench_r04_$m.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_r04_$m.json')); print('$m', round(j['value']), round(j['e2e']['value']), j['config']['dit_evaluations_per_solve'], j['roofline']['frac'], j['model_tflops'])" || tail -3 gpurun_out/bench_r04_$m.err
 done
-SCLDM_EXP=14 python tools/kernel_timeline.py 1184 2>&1 | grep -A1 "median cycles" | grep "\["
