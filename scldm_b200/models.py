@@ -30,7 +30,7 @@ STREAM_SIZE_FACTOR = 0x5A02
 class LatentDiffusion(nn.Module):
     def __init__(self, vae_model: TransformerVAE, diffusion_model: DiT, transport: Transport,
                  mu_size_factor: dict | None = None, sd_size_factor: dict | None = None,
-                 size_factor_condition_key: str | None = None, sampling_method: str = "euler", num_steps: int = 50,
+                 size_factor_condition_key: str | None = None, sampling_method: str = "dopri5", num_steps: int = 50,
                  seed: int = 0, cell_chunk: int = 1184, joint_idx_2_classes: dict | None = None, joint_key: str | None = None,
                  joint_components: list | None = None, **_unused_training_kwargs):
         super().__init__()
@@ -42,7 +42,11 @@ class LatentDiffusion(nn.Module):
         self.size_factor_condition_key = size_factor_condition_key
         # joint statistics (`encoder.py:113-134`): "{i}_{j}" -> class index of the joint table `joint_key`
         self.joint_idx_2_classes, self.joint_key, self.joint_components = joint_idx_2_classes, joint_key, joint_components
+        # `sample` in the reference always calls `sample_ode()` with its defaults (`models.py:793`, `transport.py:324-332`):
+        # adaptive dopri5, 50 output points, atol = rtol = 1e-5.  That is the default here too; the fixed-grid solvers
+        # ("euler" = BASELINE's 49-step configuration, "heun2", "midpoint") run the whole loop in one C-ABI call.
         self.sampling_method, self.num_steps = sampling_method, num_steps
+        self.atol, self.rtol = 1e-5, 1e-5
         self.seed = seed
         self.cell_chunk = cell_chunk
         self.decode_piece = 296  # cells per decode launch when results stream to the host (`sample(host_out=...)`)
@@ -149,7 +153,8 @@ class LatentDiffusion(nn.Module):
             z0 = ops.randn_cells(batch_size, dit.seq_len * dit.config.n_embed_input, self.seed, offset, STREAM_NOISE, dev)
             z0 = z0.view(batch_size, dit.seq_len, dit.config.n_embed_input)
         z0 = z0.to(dev).float()
-        sample_fn = self.transport_sampler.sample_ode(sampling_method=self.sampling_method, num_steps=self.num_steps)
+        sample_fn = self.transport_sampler.sample_ode(sampling_method=self.sampling_method, num_steps=self.num_steps,
+                                                      atol=self.atol, rtol=self.rtol)
         model_fn = FusedCFGModel(dit, guidance_weight)
         cond = {k: v.to(dev) for k, v in (condition or {}).items()}
         gvec = genes[0] if genes.dim() == 2 else genes

@@ -170,7 +170,7 @@ def test_sample_rng_path_and_size_factors():
     genes = torch.arange(1, 501).unsqueeze(0).repeat(B, 1).cuda()
     outs = []
     for _ in range(2):
-        ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t,
+        ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), sampling_method="euler", mu_size_factor=mu_t,
                               sd_size_factor=sd_t, num_steps=5, seed=3, cell_chunk=24)
         outs.append(ldm.sample(lab, {"clusters": 1.0}, B, genes, return_mu=True))
     (c1, z1, m1), (c2, z2, m2) = outs
@@ -179,7 +179,7 @@ def test_sample_rng_path_and_size_factors():
     want = torch.tensor([mu_t["clusters"][int(c)] for c in lab["clusters"].cpu()])
     assert float((lib - want).abs().max()) < 6 * 0.5  # within 6 sd of the class mean
     # chunking invariance: one big chunk gives the same cells
-    ldm = LatentDiffusion(vae, dit, create_transport("Linear", "velocity"), mu_size_factor=mu_t, sd_size_factor=sd_t,
+    ldm = LatentDiffusion(vae, dit, create_transport("Linear", "velocity"), sampling_method="euler", mu_size_factor=mu_t, sd_size_factor=sd_t,
                           num_steps=5, seed=3, cell_chunk=4096)
     c3, z3, _ = ldm.sample(lab, {"clusters": 1.0}, B, genes, return_mu=True)
     assert torch.equal(z3, z1) and torch.equal(c3, c1)
@@ -199,7 +199,7 @@ def test_shard_invariance_single_gpu():
     dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
     vae, _ = make_vae(vcfg)
     mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes)
-    mk = lambda: LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t,  # noqa: E731
+    mk = lambda: LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), sampling_method="euler", mu_size_factor=mu_t,  # noqa: E731
                                  sd_size_factor=sd_t, num_steps=4, seed=9)
     B = 10
     lab = {"clusters": synthetic.randint("si.lab", 14, (B,)).cuda()}
@@ -269,7 +269,7 @@ def test_joint_size_factors_match_oracle():
             if c % 6 != 1:  # a few classes lack statistics
                 mu_vec[c], sd_vec[c] = 7.0 + 0.1 * c, 0.2 + 0.01 * c
             c += 1
-    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor={"joint": mu_vec},
+    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), sampling_method="euler", mu_size_factor={"joint": mu_vec},
                           sd_size_factor={"joint": sd_vec}, joint_idx_2_classes=j2c, joint_key="joint",
                           joint_components=["cell_line", "gene"], num_steps=3, seed=5)
     B = 64
@@ -319,7 +319,7 @@ def test_sample_csr_equals_dense_sample():
     dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
     vae, _ = make_vae(vcfg)
     mu_t, sd_t = synthetic.size_factor_tables(dcfg.class_vocab_sizes)
-    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t, sd_size_factor=sd_t,
+    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), sampling_method="euler", mu_size_factor=mu_t, sd_size_factor=sd_t,
                           num_steps=5, seed=3)
     B = 6
     lab = {"clusters": synthetic.randint("csr.lab", 14, (B,)).cuda()}
@@ -370,7 +370,7 @@ def test_sample_streams_to_pinned_host_buffers():
     B = 53
     lab = {"clusters": synthetic.randint("ho.lab", 14, (B,)).cuda()}
     genes = torch.arange(1, 701).unsqueeze(0).repeat(B, 1).cuda()
-    mk = lambda: LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), mu_size_factor=mu_t,  # noqa: E731
+    mk = lambda: LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), sampling_method="euler", mu_size_factor=mu_t,  # noqa: E731
                                  sd_size_factor=sd_t, num_steps=4, seed=11, cell_chunk=24)
     c_ref, z_ref = mk().sample(lab, {"clusters": 2.0}, B, genes)
     ldm = mk()
@@ -491,3 +491,37 @@ def test_full_size_generation_properties():
     ldm.cell_chunk = 592
     _, z2 = ldm.sample(lab, {"clusters": 2.0}, B, genes)
     assert torch.equal(z2, z)
+
+
+def test_default_solver_is_the_references_dopri5():
+    """`LatentDiffusion.sample` of the reference always integrates with `sample_ode()`'s defaults (models.py:793: adaptive dopri5,
+    50 points, atol = rtol = 1e-5).  A default-constructed drop-in does the same: its latents agree with a very fine fixed-grid
+    Heun solve of the oracle far better than the 49-step Euler configuration does."""
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=2)
+    vcfg = VAEConfig(n_genes=300, n_layer=1)
+    dsd = synthetic.dit_state_dict(dcfg, WEIGHT_SEED)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(dsd)
+    vae, _ = make_vae(vcfg)
+    B = 3
+    z0 = synthetic.randn("dd.z0", (B, 16, 16))
+    lab = {"clusters": synthetic.randint("dd.lab", 14, (B,))}
+    w = {"clusters": 1.5}
+    genes = torch.arange(1, 301).unsqueeze(0).repeat(B, 1).cuda()
+    lsf = torch.full((B,), 7.0)
+    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"))
+    assert ldm.sampling_method == "dopri5" and ldm.num_steps == 50 and ldm.atol == 1e-5 and ldm.rtol == 1e-5
+    _, z_def = ldm.sample({k: v.cuda() for k, v in lab.items()}, w, B, genes, z0=z0.cuda(), log_size_factors=lsf.cuda())
+    nfe = ldm.transport_sampler.last_nfe
+    ldm_e = LatentDiffusion(vae, dit, create_transport("Linear", "velocity"), sampling_method="euler")
+    _, z_eul = ldm_e.sample({k: v.cuda() for k, v in lab.items()}, w, B, genes, z0=z0.cuda(), log_size_factors=lsf.cuda())
+    lab2 = {"clusters": torch.cat([lab["clusters"], lab["clusters"]])}
+    with torch.no_grad():
+        ref = O.sample_ode(torch.cat([z0, z0]), lambda x, t: O.dit_forward_with_cfg(x, t, lab2, w, dsd, dcfg), num_steps=401, method="heun2")[-1]
+    e_def, e_eul = rel_l2(z_def, ref), rel_l2(z_eul, ref)
+    print(f"default (dopri5, nfe {nfe}) vs fine Heun: {e_def:.2e}; 49-step Euler vs fine Heun: {e_eul:.2e}")
+    assert e_def < 5e-3 and nfe > 49
