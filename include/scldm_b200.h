@@ -110,6 +110,12 @@ int32_t scldm_dit_workspace_layout(const scldm_dit_weights* w, const scldm_dit_p
 int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, const float* t_mod,
                       float* v_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same evaluation when every conditioning row shares one time t (what an ODE solver's drift call passes:
+ * `th.ones(x.size(0)) * t`, integrators.py:105): one timestep-embedding row instead of one per conditioning row.
+ * Used by the adaptive dopri5 sampler, whose evaluation times are not known in advance.                          */
+int scldm_dit_forward_shared_t(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, float t, float* v_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* Replaces Sampler.sample_ode(...)(x, model) -> [-1] for fixed-grid solvers
  * (transport.py:324-369, integrators.py:100-112 + torchdiffeq fixed-grid step).  x is advanced in
  * place over t_grid_host[0..n_grid) (n_grid points => n_grid-1 steps); all rows share t.         */

@@ -16,7 +16,7 @@ DECODE_PRECISION = {"bf16": 0, "fp32": 1}
 
 EXPORTS = [
     "scldm_dit_slots_pad", "scldm_dit_mod_pad", "scldm_dit_workspace_bytes", "scldm_dit_workspace_layout",
-    "scldm_dit_forward", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
+    "scldm_dit_forward", "scldm_dit_forward_shared_t", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
     "scldm_vae_decode", "scldm_vae_encode", "scldm_randn_cells", "scldm_csr_count", "scldm_csr_fill", "scldm_tokenize_expressed", "scldm_nb_nll", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
 ]
 
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     lib.scldm_dit_workspace_layout.restype = C.c_int32
     lib.scldm_dit_forward.argtypes = [P(DitWeights), P(DitPlan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.scldm_dit_forward.restype = C.c_int
+    lib.scldm_dit_forward_shared_t.argtypes = [P(DitWeights), P(DitPlan), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_dit_forward_shared_t.restype = C.c_int
     lib.scldm_dit_sample_ode.argtypes = [P(DitWeights), P(DitPlan), C.c_void_p, P(C.c_float), C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_size_t, C.c_void_p]
     lib.scldm_dit_sample_ode.restype = C.c_int

@@ -397,11 +397,13 @@ int32_t scldm_dit_workspace_layout(const scldm_dit_weights* w, const scldm_dit_p
   return n;
 }
 
-int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, const float* t_mod, float* v_out,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+namespace {
+// one evaluation; t_mod != nullptr: one time per conditioning row, else every row shares the time `t_shared`
+int dit_forward_impl(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, const float* t_mod, float t_shared, float* v_out,
+                     void* workspace, size_t workspace_bytes, void* stream) {
   int rc;
   if ((rc = check_dit(w, plan))) return rc;
-  if (!x || !t_mod || !v_out || !workspace) return fail(SCLDM_EINVAL, "null buffer");
+  if (!x || !v_out || !workspace) return fail(SCLDM_EINVAL, "null buffer");
   if (workspace_bytes < scldm_dit_workspace_bytes(w, plan, 0)) return fail(SCLDM_ENOMEM, "workspace too small");
   if ((rc = prepare_kernels())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -411,8 +413,16 @@ int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, co
   const int n_states = plan->n_u + plan->n_g;
 
   if ((rc = launch_cls(w, plan, ws, st))) return rc;
-  LAUNCH("temb", dit::temb_kernel<<<mod_pad, 256, 0, st>>>(t_mod, mod_pad, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
-  if ((rc = launch_mod(w, plan, ws, ws.temb, dit::D, st))) return rc;
+  if (t_mod) {
+    LAUNCH("temb", dit::temb_kernel<<<mod_pad, dit::TEMB_THREADS, 0, st>>>(t_mod, mod_pad, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
+    if ((rc = launch_mod(w, plan, ws, ws.temb, dit::D, st))) return rc;
+  } else {   // shared time: one embedding row, broadcast by the adaLN GEMM's prologue (row stride 0)
+    TimeArgs ta{};
+    ta.t[0] = t_shared;
+    LAUNCH("set_times", set_times_kernel<<<1, 64, 0, st>>>(ws.tvals, ta, 1));
+    LAUNCH("temb", dit::temb_kernel<<<1, dit::TEMB_THREADS, 0, st>>>(ws.tvals, 1, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
+    if ((rc = launch_mod(w, plan, ws, ws.temb, 0, st))) return rc;
+  }
 
   dit::StepParams s = make_step(w, plan, ws);
   s.x_base = const_cast<float*>(x);  // read only in inproj
@@ -421,6 +431,18 @@ int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, co
   s.v_out = v_out; s.do_update = 0; s.do_inproj = 0;
   if ((rc = launch_final(w, s, n_states, st))) return rc;
   return SCLDM_OK;
+}
+}  // namespace
+
+int scldm_dit_forward(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, const float* t_mod, float* v_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!t_mod) return fail(SCLDM_EINVAL, "null buffer");
+  return dit_forward_impl(w, plan, x, t_mod, 0.f, v_out, workspace, workspace_bytes, stream);
+}
+
+int scldm_dit_forward_shared_t(const scldm_dit_weights* w, const scldm_dit_plan* plan, const float* x, float t, float* v_out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  return dit_forward_impl(w, plan, x, nullptr, t, v_out, workspace, workspace_bytes, stream);
 }
 
 int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan, float* x, const float* t_grid_host, int32_t n_grid,
@@ -459,7 +481,7 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
       e += n;
     }
   }
-  LAUNCH("temb", dit::temb_kernel<<<n_evals, 256, 0, st>>>(ws.tvals, n_evals, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
+  LAUNCH("temb", dit::temb_kernel<<<n_evals, dit::TEMB_THREADS, 0, st>>>(ws.tvals, n_evals, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
   if ((rc = launch_cls(w, plan, ws, st))) return rc;
 
   dit::StepParams s = make_step(w, plan, ws);

@@ -1586,31 +1586,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const Blocks
 // small fp32 kernels: timestep embedding, class-embedding sum, input projection
 // ==========================================================================================
 // temb[i] = W2 * SiLU(W0 * [cos(t f) | sin(t f)] + b0) + b2  (layers.py:351-364). Weights transposed [in][out].
-__global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, int n_t, const float* __restrict__ w0t,
-                                                    const float* __restrict__ b0, const float* __restrict__ w2t,
-                                                    const float* __restrict__ b2, float* __restrict__ temb) {
+// 1024 threads: output channel d = tid % 256, K split four ways (64 inputs each, 16 loads in flight per thread) - a single
+// 256-thread CTA streaming the two 256 KB matrices was latency-bound at 40 us, which the adaptive solver pays per evaluation.
+constexpr int TEMB_THREADS = 1024;
+__global__ void __launch_bounds__(TEMB_THREADS) temb_kernel(const float* __restrict__ t, int n_t, const float* __restrict__ w0t,
+                                                             const float* __restrict__ b0, const float* __restrict__ w2t,
+                                                             const float* __restrict__ b2, float* __restrict__ temb) {
   __shared__ float f[256];
   __shared__ float h[256];
+  __shared__ float part[4][256];
   const int i = blockIdx.x;
   if (i >= n_t) return;
-  const int d = threadIdx.x;
+  const int d = threadIdx.x & 255, kq = threadIdx.x >> 8;
   const float tv = t[i];
-  {
+  if (kq == 0) {
     const int k = d & 127;
     const float freq = expf(-9.210340371976184f * (float)k / 128.0f);  // exp(-ln(1e4) k / half)
     const float arg = tv * freq;
     f[d] = (d < 128) ? cosf(arg) : sinf(arg);
   }
   __syncthreads();
-  float acc = b0[d];
-#pragma unroll 8
-  for (int k = 0; k < 256; ++k) acc += f[k] * w0t[k * D + d];
-  h[d] = sm100::silu(acc);
+  float acc = 0.f;
+#pragma unroll 16
+  for (int k = kq * 64; k < kq * 64 + 64; ++k) acc += f[k] * w0t[k * D + d];
+  part[kq][d] = acc;
   __syncthreads();
-  float acc2 = b2[d];
-#pragma unroll 8
-  for (int k = 0; k < D; ++k) acc2 += h[k] * w2t[k * D + d];
-  temb[(size_t)i * D + d] = acc2;
+  if (kq == 0) h[d] = sm100::silu(b0[d] + ((part[0][d] + part[1][d]) + (part[2][d] + part[3][d])));
+  __syncthreads();
+  float acc2 = 0.f;
+#pragma unroll 16
+  for (int k = kq * 64; k < kq * 64 + 64; ++k) acc2 += h[k] * w2t[k * D + d];
+  part[kq][d] = acc2;
+  __syncthreads();
+  if (kq == 0) temb[(size_t)i * D + d] = b2[d] + ((part[0][d] + part[1][d]) + (part[2][d] + part[3][d]));
 }
 
 // cls[m] = sum over class tables of emb_c[idx[c][m]]   (nnets.py:403-426, 447-456)

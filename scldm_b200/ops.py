@@ -99,6 +99,20 @@ def dit_forward(plan: DitPlan, x: torch.Tensor, t_mod: torch.Tensor, workspace: 
     return v
 
 
+def dit_forward_shared_t(plan: DitPlan, x: torch.Tensor, t: float, workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """`dit_forward` when every conditioning row shares the scalar time `t` (an ODE drift evaluation): one timestep-embedding
+    row, no per-row time vector."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.shape == (plan.n_states, 16, 16), x.shape
+    ws = workspace if workspace is not None else _workspace(x.device, plan.workspace_bytes(0), "dit")
+    v = torch.empty_like(x)
+    rc = lib.scldm_dit_forward_shared_t(C.byref(plan.packed.struct), C.byref(plan.struct), x.data_ptr(), float(t), v.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream_ptr(x.device))
+    _lib.check(rc, "scldm_dit_forward_shared_t")
+    return v
+
+
 def dit_sample_ode(plan: DitPlan, x: torch.Tensor, t_grid: torch.Tensor, method: str = "euler",
                    workspace: torch.Tensor | None = None) -> torch.Tensor:
     """Integrates x (in place) over the fixed time grid; returns x."""

@@ -151,11 +151,9 @@ class Sampler:
         if isinstance(model, FusedCFGModel):
             half = x0.shape[0] // 2
             plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
-            tm = torch.empty(plan.n_mod, dtype=torch.float32, device=x0.device)
 
             def f(t, y):
-                tm.fill_(float(t))
-                return ops.dit_forward(plan, y.contiguous(), tm)
+                return ops.dit_forward_shared_t(plan, y.contiguous(), float(t))
         else:
             def f(t, y):
                 tv = torch.full((y.shape[0],), float(t), dtype=torch.float32, device=y.device)
