@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_ares_kernel(const AResPar
             float hv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              hv[j] = sm100::silu_tanh(__uint_as_float(va[c * 8 + j])) * __uint_as_float(vb[c * 8 + j]);
+              hv[j] = sm100::silu_from_half(__uint_as_float(va[c * 8 + j])) * __uint_as_float(vb[c * 8 + j]);
             uint4 o;
             o.x = sm100::pack_bf16x2(hv[0], hv[1]);
             o.y = sm100::pack_bf16x2(hv[2], hv[3]);
@@ -1029,7 +1029,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
       for (int c = 0; c < 4; ++c) {
         float hv[8];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) hv[jj] = sm100::silu_tanh(__uint_as_float(va[c * 8 + jj])) * __uint_as_float(vb[c * 8 + jj]);
+        for (int jj = 0; jj < 8; ++jj) hv[jj] = sm100::silu_from_half(__uint_as_float(va[c * 8 + jj])) * __uint_as_float(vb[c * 8 + jj]);
         uint4 o;
         o.x = sm100::pack_bf16x2(hv[0], hv[1]);
         o.y = sm100::pack_bf16x2(hv[2], hv[3]);

@@ -276,6 +276,24 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, th, h);
 }
 
+// The same with the halving folded into the producer: the packers store 0.5 * w1 (exact in bf16), so the accumulator already
+// holds h = x/2 and SiLU(x) = h + h*tanh(h) costs one SFU op and one FMA.
+__device__ __forceinline__ float silu_from_half(float h) {
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

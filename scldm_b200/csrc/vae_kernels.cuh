@@ -505,15 +505,21 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const M
       float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));   // row g+8
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      s0[0] = exp2f((s0[0] - m0) * sc); s0[1] = exp2f((s0[1] - m0) * sc); s1[0] = exp2f((s1[0] - m0) * sc); s1[1] = exp2f((s1[1] - m0) * sc);
-      s0[2] = exp2f((s0[2] - m1) * sc); s0[3] = exp2f((s0[3] - m1) * sc); s1[2] = exp2f((s1[2] - m1) * sc); s1[3] = exp2f((s1[3] - m1) * sc);
+      const float n0 = -m0 * sc, n1 = -m1 * sc;      // exp2(s*sc - m*sc): one FMA + one SFU op per score
+      s0[0] = sm100::ex2_approx(fmaf(s0[0], sc, n0)); s0[1] = sm100::ex2_approx(fmaf(s0[1], sc, n0));
+      s1[0] = sm100::ex2_approx(fmaf(s1[0], sc, n0)); s1[1] = sm100::ex2_approx(fmaf(s1[1], sc, n0));
+      s0[2] = sm100::ex2_approx(fmaf(s0[2], sc, n1)); s0[3] = sm100::ex2_approx(fmaf(s0[3], sc, n1));
+      s1[2] = sm100::ex2_approx(fmaf(s1[2], sc, n1)); s1[3] = sm100::ex2_approx(fmaf(s1[3], sc, n1));
       float l0 = (s0[0] + s0[1]) + (s1[0] + s1[1]), l1 = (s0[2] + s0[3]) + (s1[2] + s1[3]);
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      const float r0 = __fdividef(1.0f, l0), r1 = __fdividef(1.0f, l1);
+      const float r0 = sm100::rcp_approx(l0), r1 = sm100::rcp_approx(l1);
+      // unnormalised probabilities (<= 1, exact in the softmax sense) go through the PV MMA; the 1/l scaling is applied to the
+      // four output values of a row instead of its eight probabilities
       o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
-      mma_16816(o[h], sm100::pack_bf16x2(s0[0] * r0, s0[1] * r0), sm100::pack_bf16x2(s0[2] * r1, s0[3] * r1),
-                sm100::pack_bf16x2(s1[0] * r0, s1[1] * r0), sm100::pack_bf16x2(s1[2] * r1, s1[3] * r1), vb[h][0], vb[h][1]);
+      mma_16816(o[h], sm100::pack_bf16x2(s0[0], s0[1]), sm100::pack_bf16x2(s0[2], s0[3]),
+                sm100::pack_bf16x2(s1[0], s1[1]), sm100::pack_bf16x2(s1[2], s1[3]), vb[h][0], vb[h][1]);
+      o[h][0] *= r0; o[h][1] *= r0; o[h][2] *= r1; o[h][3] *= r1;
     }
     // ---- x = q + c_proj(attn): A k-step 0 = heads (0,1), k-step 1 = heads (2,3) ----
     float x[4][4];
@@ -571,10 +577,10 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const M
           mma_16816(a2[n2], ha[ks][0], ha[ks][1], ha[ks][2], ha[ks][3], b2.x, b2.y);
         }
       }
-      const uint32_t h0 = sm100::pack_bf16x2(sm100::silu_tanh(a1[0][0]) * a2[0][0], sm100::silu_tanh(a1[0][1]) * a2[0][1]);
-      const uint32_t h1 = sm100::pack_bf16x2(sm100::silu_tanh(a1[0][2]) * a2[0][2], sm100::silu_tanh(a1[0][3]) * a2[0][3]);
-      const uint32_t h2 = sm100::pack_bf16x2(sm100::silu_tanh(a1[1][0]) * a2[1][0], sm100::silu_tanh(a1[1][1]) * a2[1][1]);
-      const uint32_t h3 = sm100::pack_bf16x2(sm100::silu_tanh(a1[1][2]) * a2[1][2], sm100::silu_tanh(a1[1][3]) * a2[1][3]);
+      const uint32_t h0 = sm100::pack_bf16x2(sm100::silu_from_half(a1[0][0]) * a2[0][0], sm100::silu_from_half(a1[0][1]) * a2[0][1]);
+      const uint32_t h1 = sm100::pack_bf16x2(sm100::silu_from_half(a1[0][2]) * a2[0][2], sm100::silu_from_half(a1[0][3]) * a2[0][3]);
+      const uint32_t h2 = sm100::pack_bf16x2(sm100::silu_from_half(a1[1][0]) * a2[1][0], sm100::silu_from_half(a1[1][1]) * a2[1][1]);
+      const uint32_t h3 = sm100::pack_bf16x2(sm100::silu_from_half(a1[1][2]) * a2[1][2], sm100::silu_from_half(a1[1][3]) * a2[1][3]);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const uint2 b3 = fr[(8 + nt) * 32];

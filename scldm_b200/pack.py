@@ -121,7 +121,7 @@ class PackedDiT:
         for i in range(L):
             w1 = torch.zeros(self.mlp1_tiles * 128, D)
             w2 = torch.zeros(self.mlp1_tiles * 128, D)
-            w1[:H] = get(f"blocks.{i}.mlp.w1.weight")
+            w1[:H] = 0.5 * get(f"blocks.{i}.mlp.w1.weight")   # halved (exact in bf16): the SwiGLU epilogue computes SiLU(2h) = h + h tanh(h)
             w2[:H] = get(f"blocks.{i}.mlp.w2.weight")
             # N tile j = [w1 rows 128j..128j+127 | w2 rows 128j..128j+127] so SwiGLU pairs share an accumulator tile
             inter = torch.stack([w1.view(self.mlp1_tiles, 128, D), w2.view(self.mlp1_tiles, 128, D)], 1).reshape(-1, D)
@@ -219,7 +219,7 @@ class PackedVAEDecoder:
         self.mcab_blob = f32(blob)
         # tensor-core MCAB: fragments in the order csrc/vae_kernels.cuh::mcab_decode_tc_kernel walks them
         fp = mma_b_frags(g(c + "attn.c_proj.weight"))                 # [2][4]
-        f1 = mma_b_frags(g(c + "mlp.w1.weight"))                      # [2][11 -> 12 n-tiles after padding below]
+        f1 = mma_b_frags(0.5 * g(c + "mlp.w1.weight"))                # [2][11 -> 12 n-tiles]; halved: see sm100::silu_from_half
         f2 = mma_b_frags(g(c + "mlp.w2.weight"))
         f3 = mma_b_frags(g(c + "mlp.c_proj.weight"))                  # [6][4]  (K = 88 -> 96)
         pad = lambda f: torch.cat([f, torch.zeros(f.shape[0], 12 - f.shape[1], 32, 4, dtype=f.dtype)], 1)  # noqa: E731

@@ -47,9 +47,9 @@ def test_dit_pack_layout_cpu():
     assert torch.equal(mod[1536:3072], sd["blocks.1.adaln_modulation.1.weight"].to(torch.bfloat16))
     assert torch.equal(mod[3072:3584], sd["final_layer.adaln_modulation.1.weight"].to(torch.bfloat16))
     m1 = pack.unpack_kmajor_tiles(pk.w_mlp1[1], 256)  # layer 1: [6*256, 256]
-    assert torch.equal(m1[256:256 + 128], sd["blocks.1.mlp.w1.weight"][128:256].to(torch.bfloat16))
+    assert torch.equal(m1[256:256 + 128], (0.5 * sd["blocks.1.mlp.w1.weight"][128:256]).to(torch.bfloat16))   # stored halved (silu_from_half)
     assert torch.equal(m1[256 + 128:512], sd["blocks.1.mlp.w2.weight"][128:256].to(torch.bfloat16))
-    assert torch.equal(m1[5 * 256:5 * 256 + 44], sd["blocks.1.mlp.w1.weight"][640:684].to(torch.bfloat16))
+    assert torch.equal(m1[5 * 256:5 * 256 + 44], (0.5 * sd["blocks.1.mlp.w1.weight"][640:684]).to(torch.bfloat16))
     assert float(m1[5 * 256 + 44:5 * 256 + 128].abs().max()) == 0
     m2 = pack.unpack_kmajor_tiles(pk.w_mlp2[0].unsqueeze(0), 256)
     assert torch.equal(m2[:, :684], sd["blocks.0.mlp.c_proj.weight"].to(torch.bfloat16))

@@ -1,5 +1,3 @@
-python bench.py > gpurun_out/bench_r04_default.json 2> gpurun_out/bench_r04_default.err; python -c "
-import json; j=json.load(open('gpurun_out/bench_r04_default.json')); print(round(j['value']), round(j['e2e']['value']), j['roofline']['frac'], j['gpu_eager_baseline']['value'], j['cpu_baseline']['value'], j['clocks'], j['gpu_launches'])"
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r04_reference.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r04_ncu_launches.csv python bench.py --batch 1184 --chunk 1184 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-prof --no-gpu-eager > /dev/null 2>&1
-wc -l gpurun_out/r04_ncu_launches.csv
+timeout 900 python -m pytest tests -m gpu -q -x --timeout=600 -p no:cacheprovider 2>&1 | tail -3
+python bench.py --no-cpu-baseline --no-gpu-eager --steps 3 --warmup 3 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('bench', round(j['value']), round(j['e2e']['value']), j['roofline']['avg_launch_us'], {k:v['ms'] for k,v in j['kernel_breakdown'].items() if k in ('mcab_decode_tc','dit_blocks')})"
+python tools/bench_vae.py census 1024 2>&1 | tail -1 | cut -c1-400
