@@ -233,7 +233,10 @@ def main():
     ap.add_argument("--no-prof", action="store_true")
     ap.add_argument("--method", default="euler", choices=["euler", "heun2", "midpoint", "dopri5"],
                     help="ODE solver of sample_ode; the headline line is the fixed-grid Euler of BASELINE configs[1]")
-    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU comparator (oracle port on the same device)")
+    ap.add_argument("--gpu-eager", action="store_true",
+                    help="also time the oracle port run eagerly on the GPU (PyTorch library kernels) as a comparator; off by default: "
+                         "the default run executes oracle/ only in the cpu_baseline leg")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="(default) kept for older command lines")
     ap.add_argument("--eager-batch", type=int, default=1024)
     ap.add_argument("--dataset", default=DATASET, choices=["dentate_gyrus", "hlca", "tabula_muris", "parse1m", "replogle"],
                     help="gene-vocabulary / class-table shape (BASELINE configs 2-4); the headline line is dentate_gyrus")
@@ -389,7 +392,7 @@ def main():
                         "seconds": round(dtc, 2)}
 
     gpu_eager = None
-    if rank == 0 and not args.no_gpu_eager:
+    if rank == 0 and args.gpu_eager and not args.no_gpu_eager:
         prev = torch.get_float32_matmul_precision()
         try:
             torch.set_float32_matmul_precision("high")
