@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN_DIR
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The C-ABI tests need libscldm_b200.so; build it in-tree when it is missing or older than its sources (nvcc cross-compiles
+    for sm_100a without a GPU, ~20 s; a no-op when the library is fresh, e.g. on the GPU box where the built .so travels)."""
+    from scldm_b200 import build
+
+    build.build()
