@@ -226,8 +226,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2368, help="cells per step per GPU (2x rows are generated)")
     ap.add_argument("--chunk", type=int, default=0, help="cells per ODE chunk (0 = library default)")
-    ap.add_argument("--ref-batch", type=int, default=8)
-    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--ref-batch", type=int, default=32, help="cells per step of the CPU reference arm (the oracle port saturates its matmuls from ~32 cells)")
+    ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
