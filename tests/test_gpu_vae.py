@@ -525,3 +525,30 @@ def test_default_solver_is_the_references_dopri5():
     e_def, e_eul = rel_l2(z_def, ref), rel_l2(z_eul, ref)
     print(f"default (dopri5, nfe {nfe}) vs fine Heun: {e_def:.2e}; 49-step Euler vs fine Heun: {e_eul:.2e}")
     assert e_def < 5e-3 and nfe > 49
+
+
+def test_unconditional_sample_without_labels():
+    """`sample(condition=None, guidance_weight=None, ...)` (models.py:776-819 with no labels): size factors are zeros
+    (library size 1), every forward is unconditional, so the two halves of the output carry the same latents."""
+    from scldm_b200.models import LatentDiffusion
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import create_transport
+
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=1)
+    vcfg = VAEConfig(n_genes=200, n_layer=1)
+    dsd = synthetic.dit_state_dict(dcfg, WEIGHT_SEED)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(dsd)
+    vae, _ = make_vae(vcfg)
+    B = 5
+    genes = torch.arange(1, 201).unsqueeze(0).repeat(B, 1).cuda()
+    z0 = synthetic.randn("un.z0", (B, 16, 16))
+    ldm = LatentDiffusion(vae, dit.cuda().eval(), create_transport("Linear", "velocity"), sampling_method="euler", num_steps=6)
+    counts, z, mu = ldm.sample(None, None, B, genes, z0=z0.cuda(), return_mu=True)
+    assert counts.shape == (2 * B, 200) and torch.equal(z[:B], z[B:])
+    assert torch.allclose(mu.sum(1), torch.ones(2 * B, device="cuda"), rtol=1e-4)      # exp(0) library size
+    with torch.no_grad():
+        z_o = O.sample_ode(torch.cat([z0, z0]), lambda x, t: O.dit_forward_with_cfg(x, t, None, None, dsd, dcfg), num_steps=6, method="euler")[-1]
+    assert rel_l2(z, z_o) < 3e-2
+    with pytest.raises(ValueError):
+        ldm.sample(None, None, B, genes[:2])                                           # genes batch dimension must match (models.py:777)
