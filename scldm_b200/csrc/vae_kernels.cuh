@@ -742,22 +742,47 @@ __global__ void __launch_bounds__(256) mcab_encode_kernel(const EncParams p) {
   const long long* gp = p.genes + (size_t)cell * p.S;
   const float* cp = p.counts + (size_t)cell * p.S;
   const int n_blk = (p.S + 15) >> 4;
-  for (int blk = warp; blk < n_blk; blk += 8) {
-    // ---- tokens g and g+8 of this block: gather, scale by log1p(count), LayerNorm over 32 channels ----
+  // Software pipeline over this warp's token blocks: the gene ids / counts are fetched two blocks ahead and the embedding rows
+  // they point to one block ahead, so the two dependent global loads (id -> embedding row) of a block are in flight while the
+  // previous block is normalised, projected and pooled (the kernel is latency-bound: one CTA walks a cell's S tokens).
+  struct TokIds { long long id0, id1; float c0, c1; };
+  auto load_ids = [&](int blk) {
+    TokIds r;
     const int t0 = blk * 16 + g, t1 = t0 + 8;
-    const bool ok0 = t0 < p.S, ok1 = t1 < p.S;
-    const long long id0 = ok0 ? gp[t0] : 0, id1 = ok1 ? gp[t1] : 0;
-    const float c0 = ok0 ? log1pf(cp[t0]) : 0.f, c1 = ok1 ? log1pf(cp[t1]) : 0.f;
+    const bool ok0 = blk < n_blk && t0 < p.S, ok1 = blk < n_blk && t1 < p.S;
+    r.id0 = ok0 ? gp[t0] : 0; r.id1 = ok1 ? gp[t1] : 0;
+    r.c0 = ok0 ? cp[t0] : 0.f; r.c1 = ok1 ? cp[t1] : 0.f;
+    return r;
+  };
+  auto gather = [&](const TokIds& r, float2 (&e)[2][4]) {   // [ks]{row g cols 2t, row g cols 2t+8, row g+8 cols 2t, row g+8 cols 2t+8}
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      e[ks][0] = *reinterpret_cast<const float2*>(p.emb + (size_t)r.id0 * E + 16 * ks + 2 * t);
+      e[ks][1] = *reinterpret_cast<const float2*>(p.emb + (size_t)r.id0 * E + 16 * ks + 2 * t + 8);
+      e[ks][2] = *reinterpret_cast<const float2*>(p.emb + (size_t)r.id1 * E + 16 * ks + 2 * t);
+      e[ks][3] = *reinterpret_cast<const float2*>(p.emb + (size_t)r.id1 * E + 16 * ks + 2 * t + 8);
+    }
+  };
+  TokIds ids_cur = load_ids(warp), ids_nxt = load_ids(warp + 8);
+  float2 emb_cur[2][4], emb_nxt[2][4];
+  gather(ids_cur, emb_cur);
+  for (int blk = warp; blk < n_blk; blk += 8) {
+    gather(ids_nxt, emb_nxt);                       // rows of block blk + 8 (row 0 of the table when that block does not exist)
+    const TokIds ids_nn = load_ids(blk + 16);
+    // ---- tokens g and g+8 of this block: scale by log1p(count), LayerNorm over 32 channels ----
+    const float c0 = log1pf(ids_cur.c0), c1 = log1pf(ids_cur.c1);   // absent tokens: id 0 / count 0 -> zero rows, masked below
     float xv[2][2][4];  // [row g / g+8][ks][4 cols]
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      const float2 e00 = *reinterpret_cast<const float2*>(p.emb + (size_t)id0 * E + 16 * ks + 2 * t);
-      const float2 e01 = *reinterpret_cast<const float2*>(p.emb + (size_t)id0 * E + 16 * ks + 2 * t + 8);
-      const float2 e10 = *reinterpret_cast<const float2*>(p.emb + (size_t)id1 * E + 16 * ks + 2 * t);
-      const float2 e11 = *reinterpret_cast<const float2*>(p.emb + (size_t)id1 * E + 16 * ks + 2 * t + 8);
-      xv[0][ks][0] = e00.x * c0; xv[0][ks][1] = e00.y * c0; xv[0][ks][2] = e01.x * c0; xv[0][ks][3] = e01.y * c0;
-      xv[1][ks][0] = e10.x * c1; xv[1][ks][1] = e10.y * c1; xv[1][ks][2] = e11.x * c1; xv[1][ks][3] = e11.y * c1;
+      xv[0][ks][0] = emb_cur[ks][0].x * c0; xv[0][ks][1] = emb_cur[ks][0].y * c0; xv[0][ks][2] = emb_cur[ks][1].x * c0; xv[0][ks][3] = emb_cur[ks][1].y * c0;
+      xv[1][ks][0] = emb_cur[ks][2].x * c1; xv[1][ks][1] = emb_cur[ks][2].y * c1; xv[1][ks][2] = emb_cur[ks][3].x * c1; xv[1][ks][3] = emb_cur[ks][3].y * c1;
     }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) emb_cur[ks][j] = emb_nxt[ks][j];
+    ids_cur = ids_nxt;
+    ids_nxt = ids_nn;
     uint32_t xa[2][4];  // A fragments of LN1(x): [ks]{a0 (row g, cols 2t..), a1 (row g+8), a2 (row g, cols 2t+8..), a3}
     {
       float s0 = 0.f, s1 = 0.f;
@@ -818,10 +843,14 @@ __global__ void __launch_bounds__(256) mcab_encode_kernel(const EncParams p) {
       bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
       bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
       const float nm0 = fmaxf(m_run[hh][0], bm0), nm1 = fmaxf(m_run[hh][1], bm1);
-      const float f0 = exp2f((m_run[hh][0] - nm0) * sc), f1 = exp2f((m_run[hh][1] - nm1) * sc);   // exp2(-inf) = 0 on first use
+      // nm0 / nm1 are finite (every block a warp visits holds at least one real token), so the folded form is safe
+      const float n0 = -nm0 * sc, n1 = -nm1 * sc;
+      const float f0 = sm100::ex2_approx(fmaf(m_run[hh][0], sc, n0)), f1 = sm100::ex2_approx(fmaf(m_run[hh][1], sc, n1));   // ex2(-inf) = 0 on first use
       m_run[hh][0] = nm0; m_run[hh][1] = nm1;
-      s0[0] = exp2f((s0[0] - nm0) * sc); s0[1] = exp2f((s0[1] - nm0) * sc); s1[0] = exp2f((s1[0] - nm0) * sc); s1[1] = exp2f((s1[1] - nm0) * sc);
-      s0[2] = exp2f((s0[2] - nm1) * sc); s0[3] = exp2f((s0[3] - nm1) * sc); s1[2] = exp2f((s1[2] - nm1) * sc); s1[3] = exp2f((s1[3] - nm1) * sc);
+      s0[0] = sm100::ex2_approx(fmaf(s0[0], sc, n0)); s0[1] = sm100::ex2_approx(fmaf(s0[1], sc, n0));
+      s1[0] = sm100::ex2_approx(fmaf(s1[0], sc, n0)); s1[1] = sm100::ex2_approx(fmaf(s1[1], sc, n0));
+      s0[2] = sm100::ex2_approx(fmaf(s0[2], sc, n1)); s0[3] = sm100::ex2_approx(fmaf(s0[3], sc, n1));
+      s1[2] = sm100::ex2_approx(fmaf(s1[2], sc, n1)); s1[3] = sm100::ex2_approx(fmaf(s1[3], sc, n1));
       l_run[hh][0] = l_run[hh][0] * f0 + (s0[0] + s0[1]) + (s1[0] + s1[1]);   // per-lane partial sums (quad-reduced at the end)
       l_run[hh][1] = l_run[hh][1] * f1 + (s0[2] + s0[3]) + (s1[2] + s1[3]);
       o_acc[hh][0] *= f0; o_acc[hh][1] *= f0; o_acc[hh][2] *= f1; o_acc[hh][3] *= f1;
