@@ -175,12 +175,17 @@ class LatentDiffusion(nn.Module):
                 self._copy_stream = torch.cuda.Stream(device=dev)
             copy_stream = self._copy_stream
             copy_stream.wait_stream(torch.cuda.current_stream(dev))   # earlier readers of the host buffers are ordered before us
-        # cells are independent: run the ODE + decode chunk by chunk so the working set stays L2-sized
-        for c0 in range(0, batch_size, self.cell_chunk):
-            c1 = min(c0 + self.cell_chunk, batch_size)
+        # cells are independent: run the ODE + decode chunk by chunk so the working set stays L2-sized.  The evaluation plans
+        # of ALL chunks are built first: deduplicating label combinations synchronises with the device, and doing that between
+        # chunks would leave the GPU idle while the host prepares the next chunk's launches.
+        chunks = [(c0, min(c0 + self.cell_chunk, batch_size)) for c0 in range(0, batch_size, self.cell_chunk)]
+        conds = [{k: torch.cat([v[c0:c1], v[c0:c1]]) for k, v in cond.items()} for c0, c1 in chunks]
+        plans = [None] * len(chunks)
+        if self.sampling_method.lower() in Sampler.FIXED:
+            plans = [dit.cfg_plan(cc if cond else None, guidance_weight, c1 - c0, dev, shared_time=True)[0] for (c0, c1), cc in zip(chunks, conds)]
+        for (c0, c1), cc, plan in zip(chunks, conds, plans):
             zc = z0[c0:c1]
-            cc = {k: torch.cat([v[c0:c1], v[c0:c1]]) for k, v in cond.items()}
-            zf = sample_fn(torch.cat([zc, zc]), model_fn, condition=cc)[-1]
+            zf = sample_fn(torch.cat([zc, zc]), model_fn, condition=cc, **({"_plan": plan} if plan is not None else {}))[-1]
             n = c1 - c0
             libc = torch.cat([lib[c0:c1], lib[c0:c1]])
             # decode in pieces; with host_out every piece is copied out behind its decode, so only the last piece's transfer

@@ -121,7 +121,9 @@ class Sampler:
                 return self._sample_adaptive(x0, model, grid, atol, rtol, **model_kwargs)
             if isinstance(model, FusedCFGModel):
                 half = x0.shape[0] // 2
-                plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
+                plan = model_kwargs.get("_plan")   # prebuilt by LatentDiffusion.sample (plan building synchronises with the device)
+                if plan is None:
+                    plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
                 xf = ops.dit_sample_ode(plan, x0.clone(), grid, method)
                 return torch.stack([x0, xf])
             # generic callable: host-driven loop with the same fixed-grid formulas (slow path, still CUDA model calls)
