@@ -239,6 +239,22 @@ class DiT(nn.Module):
         slot_mod = torch.cat([slot_u, slot_g.reshape(-1)])
         return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index, slot_mode=slot_mode)
 
+    def forward_plan(self, condition: dict[str, torch.Tensor] | None, n: int, device):
+        """Evaluation plan of a plain conditional `forward(x, t, condition, force_drop_ids=False)` on n cells that all share the
+        time (an ODE drift call without guidance, BASELINE configs[0]): one slot per cell, one conditioning row per distinct label
+        combination.  Returns None when the reference's forward is not a pure function of its inputs (several mutually-exclusive
+        classes: `torch.randint` picks the active class anew at every call, `nnets.py:395`) - callers then loop on the host."""
+        avail = [k for k in sorted(self.class_vocab_sizes.keys()) if condition and k in condition]
+        if self.condition_strategy != "joint" and len(avail) > 1:
+            return None
+        cols = self._cls_rows({k: condition[k] for k in avail}, n, device)
+        if cols.shape[0] == 0:
+            return ops.DitPlan(self.packed(), n_u=n, n_g=0, n_f=1, coef=[1.0], cls_idx=cols[:, :1],
+                               slot_mod=torch.zeros(n, dtype=torch.int32, device=device), slot_mode="table")
+        uniq, inv = torch.unique(cols, dim=1, return_inverse=True)
+        return ops.DitPlan(self.packed(), n_u=n, n_g=0, n_f=1, coef=[1.0], cls_idx=uniq.to(torch.int32), slot_mod=inv.to(torch.int32),
+                           slot_mode="table")
+
     def cfg_plan(self, condition, cfg_scale, half: int, device, shared_time: bool):
         lay = self.cfg_layout(condition, cfg_scale, half, device, shared_time)
         plan = ops.DitPlan(self.packed(), n_u=lay["n_u"], n_g=lay["n_g"], n_f=lay["n_f"], coef=lay["coef"],

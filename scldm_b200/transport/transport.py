@@ -95,6 +95,17 @@ class FusedCFGModel:
         return self.dit.forward_with_cfg(x, t, condition=condition, cfg_scale=self.cfg_scale)
 
 
+class FusedForwardModel:
+    """Callable for sampling WITHOUT guidance: `lambda x, t, **kw: dit.forward(x, t, **kw, force_drop_ids=False)` as a recognisable
+    object, so that fixed-grid solvers run the whole loop in one C-ABI call (BASELINE configs[0]: plain conditional sampling)."""
+
+    def __init__(self, dit):
+        self.dit = dit
+
+    def __call__(self, x, t, condition=None):
+        return self.dit.forward(x, t, condition, force_drop_ids=False)
+
+
 class Sampler:
     """`Sampler` (`transport.py:206-225, 324-369`): `sample_ode(...)` returns fn(x, model, **model_kwargs)."""
 
@@ -126,6 +137,11 @@ class Sampler:
                     plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
                 xf = ops.dit_sample_ode(plan, x0.clone(), grid, method)
                 return torch.stack([x0, xf])
+            if isinstance(model, FusedForwardModel):
+                plan = model.dit.forward_plan(model_kwargs.get("condition"), x0.shape[0], x0.device)
+                if plan is not None:
+                    xf = ops.dit_sample_ode(plan, x0.clone(), grid, method)
+                    return torch.stack([x0, xf])
             # generic callable: host-driven loop with the same fixed-grid formulas (slow path, still CUDA model calls)
             xk = x0
             for k in range(num_steps - 1):

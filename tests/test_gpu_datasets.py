@@ -91,3 +91,39 @@ def test_census_vocabulary_decode_and_encode_match_oracle():
     e = rel_l2(z_enc, z_o)
     print(f"census encode: z {e:.2e}")
     assert z_enc.shape == (B, 16, 16) and e < 2e-2   # tensor-core pooling with bf16 operands; z is LayerNorm-ed (unit variance)
+
+
+def test_baseline_config0_plain_sampling_no_cfg():
+    """BASELINE.json configs[0] at full size: dentate_gyrus-shaped model, batch 64, `sample_ode('euler', num_steps=50)` with the plain
+    conditional `DiT.forward` as the model (no classifier-free guidance), then decode.  The fused loop (`FusedForwardModel`: one
+    C-ABI call) and the generic host loop over an opaque lambda agree, and both match the oracle run on the CPU."""
+    from scldm_b200.nnets import DiT
+    from scldm_b200.transport import Sampler, create_transport
+    from scldm_b200.transport.transport import FusedForwardModel
+    from scldm_b200.vae import TransformerVAE
+
+    dcfg, vcfg = dataset_configs("dentate_gyrus")
+    dsd, vsd = synthetic.dit_state_dict(dcfg, WEIGHT_SEED), synthetic.vae_state_dict(vcfg, WEIGHT_SEED)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(dsd, strict=True)
+    dit = dit.cuda().eval()
+    vae = TransformerVAE.from_config(vcfg)
+    vae.load_state_dict(vsd, strict=True)
+    vae = vae.cuda().eval()
+    B = 64
+    z0 = synthetic.randn("c0.z0", (B, 16, 16))
+    lab = {"clusters": synthetic.randint("c0.lab", 14, (B,))}
+    lib = torch.exp(8.0 + 0.3 * synthetic.randn("c0.lsf", (B, 1)))
+    genes = torch.arange(1, vcfg.n_genes + 1).unsqueeze(0).repeat(B, 1)
+    fn = Sampler(create_transport("Linear", "velocity")).sample_ode(sampling_method="euler", num_steps=50)
+    cond = {"clusters": lab["clusters"].cuda()}
+    z_fused = fn(z0.cuda(), FusedForwardModel(dit), condition=cond)[-1]
+    z_loop = fn(z0.cuda(), lambda x, t, **kw: dit.forward(x, t, **kw, force_drop_ids=False), condition=cond)[-1]
+    mu = vae.decode(z_fused, genes.cuda(), lib.cuda()).mu
+    with torch.no_grad():
+        z_o = O.sample_ode(z0, lambda x, t: O.dit_forward(x, t, lab, dsd, dcfg), num_steps=50, method="euler")[-1]
+        mu_o, _ = O.vae_decode(z_o, genes, lib, vsd, vcfg)
+    e_z, e_l, e_mu = rel_l2(z_fused, z_o), rel_l2(z_loop, z_fused), rel_l2(mu, mu_o)
+    print(f"configs[0]: z fused-vs-oracle {e_z:.2e}, host-loop-vs-fused {e_l:.2e}, mu {e_mu:.2e}")
+    assert e_z < 3e-2 and e_l < 1e-3 and e_mu < 6e-2
+    assert torch.allclose(mu.sum(1).cpu(), lib.reshape(-1), rtol=1e-4)
