@@ -125,5 +125,5 @@ def test_baseline_config0_plain_sampling_no_cfg():
         mu_o, _ = O.vae_decode(z_o, genes, lib, vsd, vcfg)
     e_z, e_l, e_mu = rel_l2(z_fused, z_o), rel_l2(z_loop, z_fused), rel_l2(mu, mu_o)
     print(f"configs[0]: z fused-vs-oracle {e_z:.2e}, host-loop-vs-fused {e_l:.2e}, mu {e_mu:.2e}")
-    assert e_z < 3e-2 and e_l < 1e-3 and e_mu < 6e-2
+    assert e_z < 3e-2 and e_l < 5e-3 and e_mu < 6e-2   # the two loops differ in how the next input projection is evaluated (fp32 kernel vs hi/lo bf16 tensor-core form)
     assert torch.allclose(mu.sum(1).cpu(), lib.reshape(-1), rtol=1e-4)
