@@ -641,11 +641,26 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const M
 // nll[cell] = -sum_g log NB(x | mu, theta), the per-cell term of `recon_loss.sum(dim=1)`; eps = 1e-8 as the reference.
 // One CTA per cell, coalesced float4 rows; HBM-bound: 12 B per (cell, gene) when theta is per cell, 8 B when it is the
 // shared (G,) row.  Zero counts (the bulk of a count matrix) skip the three lgamma terms, which cancel exactly there.
+// log(k!) for k <= 16: lgamma(x + 1) of the small integer counts that make up almost all non-zero entries
+__constant__ float c_log_factorial[17] = {0.f, 0.f, 0.6931471806f, 1.7917594692f, 3.1780538303f, 4.7874917428f, 6.5792512120f,
+                                          8.5251613611f, 10.6046029027f, 12.8018274801f, 15.1044125730f, 17.5023078459f,
+                                          19.9872144957f, 22.5521638531f, 25.1912211827f, 27.8992713838f, 30.6718601061f};
 __device__ __forceinline__ float nb_logp(float x, float mu, float th) {
   const float eps = 1e-8f;
-  const float l_tm = logf(th + mu + eps);
-  float r = th * (logf(th + eps) - l_tm);
-  if (x != 0.f) r += x * (logf(mu + eps) - l_tm) + lgammaf(x + th) - lgammaf(th) - lgammaf(x + 1.f);
+  const float l_tm = __logf(th + mu + eps);
+  float r = th * (__logf(th + eps) - l_tm);
+  if (x != 0.f) {
+    r += x * (__logf(mu + eps) - l_tm);
+    const int k = (int)x;
+    if ((float)k == x && k <= 16) {
+      // integer count: lgamma(x + theta) - lgamma(theta) = sum_{i<x} log(theta + i) (exact identity), lgamma(x + 1) = log(x!)
+      float acc = 0.f;
+      for (int i = 0; i < k; ++i) acc += __logf(th + (float)i);
+      r += acc - c_log_factorial[k];
+    } else {
+      r += lgammaf(x + th) - lgammaf(th) - lgammaf(x + 1.f);
+    }
+  }
   return r;
 }
 __global__ void __launch_bounds__(256) nb_nll_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ theta,

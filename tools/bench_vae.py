@@ -52,6 +52,9 @@ ms_enc = timed(lambda: vae.encode(None, None, cs, gs))
 ms_dec = timed(lambda: vae.decode(z, gene_row.unsqueeze(0).expand(B, -1), lib))
 counts_out = torch.empty(B, G, device=dev)
 ms_decs = timed(lambda: vae.decode_counts(z, gene_row, lib.reshape(-1), seed=1, out_counts=counts_out))
+mu_d = vae.decode(z, gene_row.unsqueeze(0).expand(B, -1), lib)
+ms_nll = timed(lambda: ops.nb_nll(counts_dense, mu_d.mu, mu_d.theta))
+ms_csr = timed(lambda: ops.counts_to_csr(counts_out))
 E, H, M = 32, 88, 16
 dec_flop = 2.2e6 + G * 23104
 enc_flop = S * (4 * E * E + 4 * M * E) + 2.0e6        # pooling over S tokens + tail blocks
@@ -61,6 +64,8 @@ line = {
     "decode_mu_theta_cells_per_s": round(B / ms_dec * 1e3), "decode_sample_counts_cells_per_s": round(B / ms_decs * 1e3),
     "encode_tflops": round(B * enc_flop / ms_enc / 1e9, 1), "decode_tflops": round(B * dec_flop / ms_dec / 1e9, 1),
     "decode_hbm_gbs_algorithmic": round(B * G * 8 / ms_decs / 1e6, 1),
+    "nb_nll_cells_per_s": round(B / ms_nll * 1e3), "nb_nll_hbm_gbs": round(B * G * 8 / ms_nll / 1e6, 1),      # reads counts + mu (theta row is shared)
+    "csr_cells_per_s": round(B / ms_csr * 1e3), "csr_hbm_gbs": round(B * G * 8 / ms_csr / 1e6, 1),            # two reads of the dense matrix (+ nnz writes)
     "note": "CUDA events, L2 flushed between steps; decode_mu_theta returns the NB distribution (mu, theta), decode_sample_counts the Gamma-Poisson draw only",
 }
 print(json.dumps(line))
