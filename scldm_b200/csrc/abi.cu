@@ -522,7 +522,7 @@ int scldm_vae_qside(const scldm_vae_dec_weights* w, float* qp, void* qp_bf16, vo
 size_t scldm_vae_decode_workspace_bytes(int32_t n_cells, int32_t n_genes) {
   const size_t tiles = ceil_div(n_genes, 128);
   return align_up((size_t)n_cells * vae::TOK * vae::KV * 4, 1024) + align_up((size_t)n_cells * n_genes * 4, 1024) +
-         align_up((size_t)n_cells * tiles * 8, 1024) + align_up((size_t)n_cells * 1024 * 2, 1024) + 1024;
+         align_up((size_t)n_cells * tiles * 8 * 8, 1024) + align_up((size_t)n_cells * 1024 * 2, 1024) + 1024;   // 8 softmax partials per gene tile
 }
 
 int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void* qp_bf16, const float* z, int32_t n_cells,
@@ -546,7 +546,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
   float* logits_ws = reinterpret_cast<float*>(b);
   b += align_up((size_t)n_cells * n_genes * 4, 1024);
   float2* partials = reinterpret_cast<float2*>(b);
-  b += align_up((size_t)n_cells * tiles * 8, 1024);
+  b += align_up((size_t)n_cells * tiles * 8 * 8, 1024);
   __nv_bfloat16* kvb = reinterpret_cast<__nv_bfloat16*>(b);
   float* logits = mu ? mu : logits_ws;  // finalised in place when mu is requested
   const bool tc = precision == SCLDM_DECODE_TC;
@@ -579,7 +579,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
   }
 
   vae::NbParams np{};
-  np.logits = logits; np.partials = partials; np.gene_tiles = tiles; np.G = n_genes; np.n_cells = n_cells; np.lib = lib;
+  np.logits = logits; np.partials = partials; np.gene_tiles = tc ? tiles * 8 : tiles; np.G = n_genes; np.n_cells = n_cells; np.lib = lib;
   np.theta_tbl = w->theta_tbl; np.genes = reinterpret_cast<const long long*>(genes); np.mu = mu; np.theta = theta; np.counts = counts;
   np.seed = seed; np.cell_offset = cell_offset;
   int gx = ceil_div(n_genes, 256 * 4);

@@ -438,7 +438,6 @@ template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const McabTcParams p) {
   __shared__ uint2 s_frag[TC_NFRAG * 32];   // 20 KB
   __shared__ float s_small[136];
-  __shared__ float red_m[2][8], red_s[2][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   for (int i = tid; i < TC_NFRAG * 32; i += 256) s_frag[i] = reinterpret_cast<const uint2*>(p.wfrag)[i];
@@ -620,18 +619,9 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) mcab_decode_tc_kernel(const M
     const float wm = sm100::warp_max(lm);
     const float ev = (t == 0) ? ((v0 ? __expf(la - wm) : 0.f) + (v1 ? __expf(lb2 - wm) : 0.f)) : 0.f;
     const float wsum = sm100::warp_sum(ev);
-    const int par = cell & 1;
-    if (lane == 0) { red_m[par][warp] = wm; red_s[par][warp] = wsum; }
-    __syncthreads();
-    if (tid == 0) {
-      float bm = red_m[par][0];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) bm = fmaxf(bm, red_m[par][w]);
-      float bs = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) bs += red_m[par][w] == -INFINITY ? 0.f : red_s[par][w] * __expf(red_m[par][w] - bm);
-      p.partials[(size_t)cell * p.gene_tiles + blockIdx.x] = make_float2(bm, bs);
-    }
+    // one (max, sum) partial per warp (16 genes): no CTA barrier in the per-cell loop, so the eight warps drift freely and hide
+    // each other's latencies; nb_finalize_kernel merges 8 x gene_tiles partials per cell
+    if (lane == 0) p.partials[(size_t)cell * p.gene_tiles * 8 + blockIdx.x * 8 + warp] = make_float2(wm, wsum);
 #pragma unroll
     for (int h = 0; h < 4; ++h) { kb[h][0] = kn[h][0]; kb[h][1] = kn[h][1]; vb[h][0] = vn[h][0]; vb[h][1] = vn[h][1]; }
   }
@@ -958,7 +948,7 @@ __global__ void __launch_bounds__(256) mcab_encode_kernel(const EncParams p) {
 // ---- softmax-over-genes finalisation + optional NB sampling --------------------------------
 struct NbParams {
   const float* logits;     // [cells][G]
-  const float2* partials;  // [cells][gene_tiles]
+  const float2* partials;  // [cells][gene_tiles] (max, sum) pairs; gene_tiles = partials per cell (8 per 128-gene tile on the tensor-core path)
   int gene_tiles;
   int G;
   int n_cells;
