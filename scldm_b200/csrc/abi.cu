@@ -47,6 +47,7 @@ const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? at
 // dit_blocks_kernel switches (bit mask, SCLDM_EXP): 1 = hand the MLP accumulator over before M2 is queued (measured slower: 971 vs 942 us),
 // 2 = no setup barrier in phases whose rows come from the stash (927 vs 942 us), 4 = butterfly LayerNorm reductions (937 vs 942 us)
 const int g_exp = []{ const char* e = getenv("SCLDM_EXP"); return e ? atoi(e) : 6; }();
+const int g_dec_cpb = []{ const char* e = getenv("SCLDM_DEC_CPB"); return e ? atoi(e) : 0; }();   // cells per MCAB decode CTA (0: heuristic)
 const int g_dec_occ = []{ const char* e = getenv("SCLDM_DEC_OCC"); return e ? atoi(e) : 2; }();   // resident CTAs per SM the MCAB decode kernel is compiled for (2: 128 registers, 3: 80 registers + spills)
 const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
 cudaStream_t g_prof_stream = nullptr;
@@ -561,6 +562,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
   int cpb = (int)(((long long)tiles * n_cells) / (148LL * 2 * 4));
   if (cpb < 1) cpb = 1;
   if (cpb > 32) cpb = 32;
+  if (g_dec_cpb > 0) cpb = g_dec_cpb;
   if (tc) {
     vae::McabTcParams mp{};
     mp.emb = w->emb; mp.qp = static_cast<const __nv_bfloat16*>(qp_bf16); mp.genes = reinterpret_cast<const long long*>(genes);
