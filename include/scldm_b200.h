@@ -213,6 +213,90 @@ int scldm_tokenize_expressed(const float* dense, int32_t rows, int32_t G, const 
 int scldm_nb_nll(const float* x, const float* mu, const float* theta, int64_t theta_row_stride, int32_t rows, int32_t G, float* nll,
                  void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * DiT training step (reference: LatentDiffusion.training_step, src/scldm/models.py:634-666; Transport.training_losses,
+ * src/scldm/transport/transport.py:110-150; DiT.forward in training mode, src/scldm/nnets.py:273-297; torch autograd;
+ * torch.optim.AdamW, experiments/configs/model/ldm_base.yaml:36-40; gradient_clip_val, configs/training/default.yaml:15).
+ *
+ * All trainable DiT parameters live in ONE flat fp32 buffer (`params`), their gradients in a second one with the same
+ * layout (`grads`) - the buffer DDP all-reduces.  The layout is ordered by when a gradient is complete during the backward
+ * pass (final layer, blocks n_layer-1 .. 0, then the conditioning / input tensors), so contiguous ranges can be all-reduced
+ * while earlier blocks are still being differentiated.  bf16 copies of the GEMM weights in UMMA tile order (`pk_*`) are
+ * refreshed by the optimizer step.
+ * --------------------------------------------------------------------------------------------------------------- */
+#define SCLDM_MAX_LAYERS 32
+
+typedef struct scldm_dit_train_layout {   /* element offsets into params / grads */
+  int64_t w_qkv[SCLDM_MAX_LAYERS];   /* blocks.i.attn.c_attn.weight [768][256]           */
+  int64_t b_qkv[SCLDM_MAX_LAYERS];   /* blocks.i.attn.c_attn.bias   [768]                */
+  int64_t w_proj[SCLDM_MAX_LAYERS];  /* blocks.i.attn.c_proj.weight [256][256]           */
+  int64_t b_proj[SCLDM_MAX_LAYERS];  /* blocks.i.attn.c_proj.bias   [256]                */
+  int64_t w1[SCLDM_MAX_LAYERS];      /* blocks.i.mlp.w1.weight      [hidden][256]        */
+  int64_t w2[SCLDM_MAX_LAYERS];      /* blocks.i.mlp.w2.weight      [hidden][256]        */
+  int64_t w3[SCLDM_MAX_LAYERS];      /* blocks.i.mlp.c_proj.weight  [256][hidden]        */
+  int64_t w_mod[SCLDM_MAX_LAYERS];   /* blocks.i.adaln_modulation.1.weight [1536][256]   */
+  int64_t b_mod;                     /* all adaLN biases, contiguous: blocks 0..n_layer-1 [1536] each, then the final layer's [512] */
+  int64_t w_mod_final;               /* final_layer.adaln_modulation.1.weight [512][256] */
+  int64_t w_out, b_out;              /* final_layer.linear [16][256], [16]               */
+  int64_t temb_w0, temb_b0, temb_w2, temb_b2;   /* t_embedder.mlp.{0,2} [256][256], [256] */
+  int64_t w_in, b_in;                /* input_proj [256][16], [256]                      */
+  int64_t class_tab[SCLDM_MAX_CLASSES];          /* class_embeddings.<name>.weight [(V+1)][256], sorted by class name */
+  int64_t n_params;
+} scldm_dit_train_layout;
+
+typedef struct scldm_dit_train {
+  int32_t n_layer, hidden, n_class;
+  float eps;
+  scldm_dit_train_layout off;
+  float* params;       /* flat fp32 master weights                                            */
+  float* grads;        /* flat fp32 gradients (same layout)                                   */
+  const float* pos;    /* pos_embed [16][256] (requires_grad=False in the reference)           */
+  /* bf16 GEMM weights as 128B-swizzled K-major tiles [n_tile][k_slab][256 x 64] (T = ceil(hidden/128)):               */
+  const void* pk_qkv;  /* [n_layer][3][4]                                                      */
+  const void* pk_proj; /* [n_layer][1][4]                                                      */
+  const void* pk_w12;  /* [n_layer][T][4]   tile j rows 0-127 = w1[128j..], rows 128-255 = w2[128j..] (zero padded)     */
+  const void* pk_w3;   /* [n_layer][1][2T]  K (= hidden) zero padded to 128 T                   */
+  const void* pk_mod;  /* [6 n_layer + 2][4]                                                   */
+} scldm_dit_train;
+
+size_t scldm_dit_train_workspace_bytes(const scldm_dit_train* tr, int32_t n_cells);
+
+/* DiT.forward in training mode with every activation the backward pass needs kept in `workspace`.
+ *   x [n_cells][16][16] fp32, t [n_cells] fp32, cls_idx [n_class][n_cells] int32 embedding rows (label dropout already
+ *   applied by the caller: dropped labels = the class's null row), v_out [n_cells][16][16].  n_cells % 8 == 0.          */
+int scldm_dit_train_forward(const scldm_dit_train* tr, const float* x, const float* t, const int32_t* cls_idx, int32_t n_cells,
+                            float* v_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the call above: dv [n_cells][16][16] = dLoss/dv_out.  Gradients are ACCUMULATED into tr->grads unless
+ * zero_grads != 0 (then the buffer is cleared first); dx (nullable) receives dLoss/dx.
+ * events: n_events cudaEvent_t handles; events[k] is recorded on `stream` once the backward of block ev_after_layer[k]
+ * (and of everything after it in the network) has been enqueued - the gradients of the flat-buffer prefix ending with
+ * that block are then final, so the caller can start their all-reduce on another stream.                               */
+int scldm_dit_train_backward(const scldm_dit_train* tr, const float* dv, float* dx, int32_t n_cells, int32_t zero_grads,
+                             void* const* events, const int32_t* ev_after_layer, int32_t n_events, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Fused optimizer step over flat buffers: g *= grad_scale; clip by global norm (max_norm <= 0: off; Lightning /
+ * torch.nn.utils.clip_grad_norm_ semantics); AdamW (torch.optim.AdamW: decoupled weight decay, bias correction with
+ * `step` >= 1); then the bf16 packed copy pk[pk_dst[i]] of every parameter with pk_dst[i] >= 0 is refreshed.
+ * scratch: one device float.                                                                                          */
+int scldm_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int32_t step, float max_norm, float grad_scale, float* scratch,
+                     const int32_t* pk_dst, void* pk, void* stream);
+/* pk[pk_dst[i]] = bf16(params[i]) (initial pack, after load_state_dict) */
+int scldm_repack(const float* params, const int32_t* pk_dst, void* pk, int64_t n, void* stream);
+/* ema += (1 - decay) * (params - ema)   (ema_pytorch update with the decay the caller scheduled) */
+int scldm_ema_update(float* ema, const float* params, int64_t n, float decay, void* stream);
+
+/* Stand-alone access to the slab GEMM for unit tests: mode 0 forward  out[M][N]  = A[M][K] W[N][K]^T (+bias[N]),
+ * mode 1 dgrad out[M][K] = dY[M][N] W[N][K], mode 2 wgrad out[N][K] += dY[M][N]^T A[M][K].  a_f32 / dy_f32 are fp32
+ * row-major inputs (converted to bf16 slab tensors in `workspace`), w_packed = bf16 [N/256][K/64][256 x 64] tiles.
+ * M % 128 == 0, N % 256 == 0, K % 256 == 0.                                                                            */
+int scldm_test_gemm(int32_t mode, const float* a_f32, const float* dy_f32, const void* w_packed, const float* bias, int32_t M,
+                    int32_t N, int32_t K, int32_t split_k, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* unit-test probe of the small-mean NB sampler: k[i] = inverse CDF of NB(mu[i], theta[i]) at u[i] */
+int scldm_test_nb_invert(const float* u, const float* mu, const float* theta, float* k, int32_t n, void* stream);
+
 /* Live per-kernel timing for bench.py: when enabled every launch is bracketed by CUDA events recorded on
  * `stream` (must be the stream the calls run on; disables CUDA-graph capturability while on).
  * scldm_prof_summary synchronises the device and writes "name count total_ms\n" lines.            */

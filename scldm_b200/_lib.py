@@ -17,7 +17,8 @@ DECODE_PRECISION = {"bf16": 0, "fp32": 1}
 EXPORTS = [
     "scldm_dit_slots_pad", "scldm_dit_mod_pad", "scldm_dit_workspace_bytes", "scldm_dit_workspace_layout",
     "scldm_dit_forward", "scldm_dit_forward_shared_t", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
-    "scldm_vae_decode", "scldm_vae_encode", "scldm_randn_cells", "scldm_csr_count", "scldm_csr_fill", "scldm_tokenize_expressed", "scldm_nb_nll", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
+    "scldm_vae_decode", "scldm_vae_encode", "scldm_randn_cells", "scldm_csr_count", "scldm_csr_fill", "scldm_tokenize_expressed", "scldm_nb_nll", "scldm_dit_train_workspace_bytes", "scldm_dit_train_forward", "scldm_dit_train_backward", "scldm_adamw_step", "scldm_repack",
+    "scldm_ema_update", "scldm_test_gemm", "scldm_test_nb_invert", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
 ]
 
 
@@ -56,6 +57,21 @@ class VaeEncWeights(C.Structure):
     _fields_ = [("n_layer", C.c_int32), ("has_pos", C.c_int32), ("eps", C.c_float)] + [
         (n, C.c_void_p) for n in ("emb", "wkv_frag", "q_tbl", "ln1_w", "ln1_b", "inducing", "wproj_t", "ln2_w", "ln2_b", "w1_t", "w2_t",
                                   "w3_t", "pos", "blocks", "wlat_t")]
+
+
+MAX_LAYERS = 32
+
+
+class DitTrainLayout(C.Structure):
+    _fields_ = [(n, C.c_int64 * MAX_LAYERS) for n in ("w_qkv", "b_qkv", "w_proj", "b_proj", "w1", "w2", "w3", "w_mod")] + [
+        (n, C.c_int64) for n in ("b_mod", "w_mod_final", "w_out", "b_out", "temb_w0", "temb_b0", "temb_w2", "temb_b2", "w_in", "b_in")] + [
+        ("class_tab", C.c_int64 * MAX_CLASSES), ("n_params", C.c_int64)]
+
+
+class DitTrain(C.Structure):
+    _fields_ = [("n_layer", C.c_int32), ("hidden", C.c_int32), ("n_class", C.c_int32), ("eps", C.c_float), ("off", DitTrainLayout),
+                ("params", C.c_void_p), ("grads", C.c_void_p), ("pos", C.c_void_p),
+                ("pk_qkv", C.c_void_p), ("pk_proj", C.c_void_p), ("pk_w12", C.c_void_p), ("pk_w3", C.c_void_p), ("pk_mod", C.c_void_p)]
 
 
 _lib = None
@@ -109,6 +125,25 @@ def load() -> C.CDLL:
     lib.scldm_tokenize_expressed.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p]
     lib.scldm_tokenize_expressed.restype = C.c_int
+    lib.scldm_dit_train_workspace_bytes.argtypes = [P(DitTrain), C.c_int32]
+    lib.scldm_dit_train_workspace_bytes.restype = C.c_size_t
+    lib.scldm_dit_train_forward.argtypes = [P(DitTrain), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_dit_train_forward.restype = C.c_int
+    lib.scldm_dit_train_backward.argtypes = [P(DitTrain), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, P(C.c_void_p), P(C.c_int32), C.c_int32,
+                                             C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_dit_train_backward.restype = C.c_int
+    lib.scldm_adamw_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.scldm_adamw_step.restype = C.c_int
+    lib.scldm_repack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.scldm_repack.restype = C.c_int
+    lib.scldm_ema_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+    lib.scldm_ema_update.restype = C.c_int
+    lib.scldm_test_gemm.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_test_gemm.restype = C.c_int
+    lib.scldm_test_nb_invert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.scldm_test_nb_invert.restype = C.c_int
     lib.scldm_prof_enable.argtypes = [C.c_int32, C.c_void_p]
     lib.scldm_prof_enable.restype = None
     lib.scldm_prof_summary.argtypes = [C.c_char_p, C.c_int32]

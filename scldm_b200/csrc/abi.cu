@@ -13,6 +13,7 @@
 #include "dit_kernels.cuh"
 #include "vae_kernels.cuh"
 #include "csr_kernels.cuh"
+#include "train_kernels.cuh"
 
 namespace {
 
@@ -690,3 +691,5 @@ const char* scldm_last_error(void) { return g_err; }
 const char* scldm_version(void) { return "scldm_b200 0.1 (sm_100a)"; }
 
 }  // extern "C"
+
+#include "train_abi.inc"

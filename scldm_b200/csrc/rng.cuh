@@ -115,20 +115,28 @@ __device__ __forceinline__ float poisson(Philox& g, float lam) {
 // the two-stage draw: pmf(0) = (theta/(theta+mu))^theta, pmf(k+1) = pmf(k) (k+theta)/(k+1) mu/(theta+mu), inverted with one
 // uniform (same distribution, one Philox block instead of two or more and no rejection loops).
 constexpr float NB_INVERSION_MAX_MU = 4.0f;
+// inversion of the NB(mu, theta) CDF at u in (0, 1] (the small-mean path of `negative_binomial`; exposed for the u = 1.0 unit test)
+__device__ __forceinline__ float nb_invert(float u, float mu, float theta) {
+  const float q = mu / (theta + mu);
+  float p = __expf(-theta * log1pf(mu / theta));     // pmf(0)
+  float c = p;
+  int k = 0;
+  // The fp32 CDF saturates just below 1 (e.g. 0.99999994 for mu = 0.01, theta = 1) while u may be exactly 1.0: once a term no
+  // longer changes c the tail is exhausted in fp32, and the scan must stop THERE - running on to the loop cap would turn
+  // u in (c_final, 1] (probability ~1e-7 per draw, several draws per 4736 x 17002 step) into spurious counts of 256.
+  while (u > c && k < 256) {
+    p *= ((float)k + theta) / (float)(k + 1) * q;
+    const float c_next = c + p;
+    if (c_next == c) break;
+    c = c_next;
+    ++k;
+  }
+  return (float)k;
+}
 __device__ __forceinline__ float negative_binomial(Philox& g, float mu, float theta) {
   if (mu < NB_INVERSION_MAX_MU && theta > 1e-3f) {
     if (!(mu > 0.0f)) return 0.0f;
-    const float u = g.uniform();                       // (0, 1]
-    const float q = mu / (theta + mu);
-    float p = __expf(-theta * log1pf(mu / theta));     // pmf(0)
-    float c = p;
-    int k = 0;
-    while (u > c && k < 256) {
-      p *= ((float)k + theta) / (float)(k + 1) * q;
-      c += p;
-      ++k;
-    }
-    return (float)k;
+    return nb_invert(g.uniform(), mu, theta);          // u in (0, 1]
   }
   const float lam = fminf(gamma_mt(g, theta) * (mu / theta), 1e8f);
   return poisson(g, lam);

@@ -1,6 +1,6 @@
 """Drop-in replacements for `scldm.nnets.{DiT, Encoder, Decoder}`: same constructor kwargs, same
 `state_dict` layout, same call signatures -- the arithmetic runs in hand-written sm_100a kernels
-through the C-ABI (`include/scldm_b200.h`).  Inference (eval-mode) semantics only in this round.
+through the C-ABI (`include/scldm_b200.h`).  `DiT.forward` is differentiable once a `training.DiTTrainer` is attached.
 """
 
 from __future__ import annotations
@@ -178,8 +178,15 @@ class DiT(nn.Module):
         on the host side (the kernels only ever see label rows); no autograd graph is built (forward only)."""
         if force_drop_ids is None:
             force_drop_ids = self.training
-        packed = self.packed()
         n = x.shape[0]
+        trainer = getattr(self, "trainer", None)
+        if self.training and torch.is_grad_enabled() and trainer is not None:
+            # differentiable path (`scldm_b200.training.DiTTrainer`): activations are kept and `loss.backward()` runs the backward
+            # kernels, leaving the gradients in the parameters' `.grad` (views of the trainer's flat buffer)
+            from .training import differentiable_forward
+            cls = self._cls_rows(self._active_labels(condition or {}, force_drop_ids), n, x.device)
+            return differentiable_forward(trainer, x.contiguous().float(), t.float(), cls)
+        packed = self.packed()
         cls = self._cls_rows(self._active_labels(condition or {}, force_drop_ids), n, x.device)
         plan = ops.DitPlan(packed, n_u=n, n_g=0, n_f=1, coef=[1.0], cls_idx=cls,
                            slot_mod=torch.arange(n, dtype=torch.int32, device=x.device), slot_mode="identity")
