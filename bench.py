@@ -218,6 +218,302 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ==================================================================================================================
+# --mode train: one LDM training step (BASELINE configs[4]): frozen census-vocabulary VAE encode -> flow-matching loss ->
+# DiT forward/backward -> DDP gradient all-reduce (NCCL, bucketed, overlapped with the backward) -> clip + AdamW.
+# Reference: LatentDiffusion.training_step (src/scldm/models.py:634-666), per-GPU batch 128 (ldm_base.yaml:58).
+# ==================================================================================================================
+TRAIN_METRIC = "LDM training cells/sec (frozen MCAB encode + FM loss + DiT fwd/bwd + DDP all-reduce + AdamW)"
+TRAIN_CLASSES = {"cell_type": 50}
+TRAIN_S = 8000   # census genes_seq_len (datamodule/default.yaml:130)
+
+
+def train_flops_per_cell() -> float:
+    return 3.0 * algorithmic_flops_per_row(1)["dit_forward"]   # forward + backward (dgrad + wgrad) of the DiT; the frozen encode adds 52.9 MFLOP
+
+
+def encoder_inputs(B: int, G: int, S: int, seed: int):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    gs = np.zeros((B, S), dtype=np.int64)
+    cs = np.zeros((B, S), dtype=np.float32)
+    for b in range(B):
+        n = int(rng.integers(int(0.05 * G), min(S, int(0.3 * G))))
+        gs[b, :n] = np.sort(rng.choice(np.arange(1, G + 1), size=n, replace=False))
+        cs[b, :n] = 1 + rng.poisson(2.0, size=n)
+    return torch.from_numpy(cs), torch.from_numpy(gs)
+
+
+def oracle_train_step_fn(B: int, dcfg, device, threads: int | None = None, use_reference_modules: bool = False):
+    """fwd + bwd + clip + AdamW of the same DiT in eager PyTorch: the oracle port (CPU: the reference's flex_attention has no CPU
+    backward) or the staged reference modules themselves (GPU).  Baseline / comparator only."""
+    from oracle import scldm_oracle as O
+    from scldm_b200 import synthetic
+
+    if threads:
+        torch.set_num_threads(threads)
+    sd = synthetic.dit_state_dict(dcfg, 1234)
+    z = synthetic.randn("trainb.z", (B, 16, 16)).to(device)
+    lab = {k: synthetic.randint("trainb.lab." + k, v, (B,)).to(device) for k, v in dcfg.class_vocab_sizes.items()}
+    if use_reference_modules:
+        from oracle import ref_loader
+
+        ref = ref_loader.load_reference()
+        model = ref_loader.build_reference_dit(dcfg, sd).to(device).train()
+        params = [p for p in model.parameters() if p.requires_grad]
+        transport = ref.transport.create_transport(path_type="Linear", prediction="velocity", loss_weight="velocity", train_eps=1e-5, sample_eps=1e-5)
+
+        def loss_fn():
+            return transport.training_losses(model, z, {"condition": lab})["loss"].mean()
+    else:
+        sdg = {k: v.clone().to(device).requires_grad_(k != "pos_embed") for k, v in sd.items()}
+        params = [v for v in sdg.values() if v.requires_grad]
+
+        def loss_fn():
+            x0 = torch.randn_like(z)
+            t = torch.rand(B).to(device)
+            return O.fm_training_losses(z, t, x0, lambda xt, tt: O.dit_forward(xt, tt, lab, sdg, dcfg))["loss"].mean()
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.0)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+        return loss
+
+    return step
+
+
+def run_train(args):
+    from scldm_b200.config import DiTConfig, VAEConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dcfg = DiTConfig(class_vocab_sizes=dict(TRAIN_CLASSES))
+    vcfg = VAEConfig(n_genes=36130)
+    B = args.train_batch
+    workload = (f"census-vocabulary LDM training step (BASELINE configs[4]): frozen TransformerVAE.encode G={vcfg.n_genes} S={TRAIN_S} -> FM loss "
+                f"-> DiT (8 layers, D=256, classes {TRAIN_CLASSES}) fwd/bwd -> DDP all-reduce of {9.7:.1f} M fp32 grads -> clip 10 + AdamW; per-GPU batch {B}")
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        Bc = args.ref_batch
+        step = oracle_train_step_fn(Bc, dcfg, torch.device("cpu"), threads)
+        step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+        val = Bc * args.steps / dt
+        print(json.dumps({
+            "metric": TRAIN_METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference", "config": {"workload": workload, "cells_per_step": Bc,
+                                            "note": "DiT fwd/bwd + clip + AdamW of the oracle port with torch autograd on the host cores (the reference's flex_attention has no CPU backward; frozen encode not included)"},
+            "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port", "sample": f"{args.steps} training steps of {Bc} cells"},
+            "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (scldm_b200 has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+    from scldm_b200 import ops, synthetic
+    from scldm_b200.nnets import DiT
+    from scldm_b200.training import DiTTrainer, wsd_schedule
+    from scldm_b200.transport import create_transport
+    from scldm_b200.vae import TransformerVAE
+
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, 1234))   # identical replicas on every rank
+    dit = dit.to(device).train()
+    vae = TransformerVAE.from_config(vcfg)
+    vae.load_state_dict(synthetic.vae_state_dict(vcfg, 1234))
+    vae = vae.to(device).eval()
+    trainer = DiTTrainer(dit, lr=5e-4 * world, max_grad_norm=10.0, lr_lambda=wsd_schedule(100_000, num_warmup_steps=1000),
+                         ema_decay=0.9999, ema_update_every=10, ema_update_after_step=10_000, n_buckets=args.buckets)
+    transport = create_transport("Linear", "velocity", "velocity")
+    cs_h, gs_h = encoder_inputs(B, vcfg.n_genes, TRAIN_S, 500 + rank)
+    cs_h, gs_h = cs_h.pin_memory(), gs_h.pin_memory()
+    lab_h = {k: torch.randint(0, v, (B,), generator=torch.Generator().manual_seed(900 + rank)).pin_memory() for k, v in TRAIN_CLASSES.items()}
+    cs_d, gs_d = cs_h.to(device), gs_h.to(device)
+    lab_d = {k: v.to(device) for k, v in lab_h.items()}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        z = vae.encode(None, None, cs_d, gs_d)
+        return trainer.fm_step(z, lab_d, transport)
+
+    def step_e2e():
+        cs, gs = cs_h.to(device, non_blocking=True), gs_h.to(device, non_blocking=True)
+        lab = {k: v.to(device, non_blocking=True) for k, v in lab_h.items()}
+        z = vae.encode(None, None, cs, gs)
+        return float(trainer.fm_step(z, lab, transport))     # D2H read of the loss
+
+    def timed(fn, steps):
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            total += a.elapsed_time(b)
+        return total
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = ops.launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ar_ms = None
+    if world > 1 and getattr(trainer, "_ar_events", None):
+        ar_ms = trainer._ar_events[0].elapsed_time(trainer._ar_events[1])
+    # exposed all-reduce time: the same steps with the collective switched off (gradients stay rank-local; timing only)
+    noar_ms = None
+    if world > 1:
+        saved = trainer.world
+        trainer.world = 1
+        barrier()
+        noar_ms = timed(step_device, args.steps)
+        trainer.world = saved
+        barrier()
+    step_e2e()
+    barrier()
+    e2e_ms = timed(step_e2e, args.steps)
+    barrier()
+    t = torch.tensor([ms, e2e_ms, noar_ms or 0.0, ar_ms or 0.0], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, noar_ms, ar_ms = (float(v) for v in t)
+
+    breakdown, roofline = None, None
+    peaks = measured_peaks()
+    if rank == 0 and not args.no_prof:
+        saved_world, trainer.world = trainer.world, 1      # rank-0-only step: no collective (the other ranks are not in it)
+        ops.prof_enable(True, device)
+        step_device()
+        prof = ops.prof_summary()
+        ops.prof_enable(False, device)
+        trainer.world = saved_world
+        tot = sum(v[1] for v in prof.values())
+        breakdown = {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        gemm_ms = sum(v[1] for k, v in prof.items() if k.startswith("trn_gemm") or k.startswith("trn_dgrad") or k.startswith("trn_wgrad"))
+        gemm_n = sum(v[0] for k, v in prof.items() if k.startswith("trn_gemm") or k.startswith("trn_dgrad") or k.startswith("trn_wgrad"))
+        rows, D, H, L = B * 16, 256, 684, 8
+        blk = 2.0 * rows * (D * 3 * D + D * D + D * 2 * H + H * D)            # the four GEMMs of a block, forward
+        modf = 2.0 * B * D * (L * 6 * D + 2 * D)
+        fl = 3.0 * (L * blk + modf)                                           # forward + dgrad + wgrad
+        ach = fl / (gemm_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "trn::gemm_kernel (all forward / dgrad / wgrad launches of a step)", "achieved": round(ach, 2),
+                    "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 4), "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "avg_launch_us": round(1e3 * gemm_ms / max(gemm_n, 1), 2),
+                    "flops_per_step": fl, "launches_per_step": gemm_n,
+                    "note": "2048-row GEMMs (batch 128 x 16 tokens): 16 row tiles per launch, latency-bound; the step is bounded by its ~260 dependent launches"}
+
+    cpu_baseline, gpu_eager = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        stepc = oracle_train_step_fn(args.cpu_batch, dcfg, torch.device("cpu"), threads)
+        stepc()
+        t0 = time.perf_counter()
+        stepc()
+        dtc = time.perf_counter() - t0
+        cpu_baseline = {"value": args.cpu_batch / dtc, "unit": "cells/s", "cores": threads, "kind": "port", "seconds": round(dtc, 2),
+                        "sample": f"1 training step (DiT fwd/bwd + clip + AdamW, torch autograd through the oracle port) of {args.cpu_batch} cells"}
+    if rank == 0 and not args.no_gpu_eager_train:
+        prev = torch.get_float32_matmul_precision()
+        try:
+            torch.set_float32_matmul_precision("high")   # as experiments/scripts/train_ldm.py:18
+            try:
+                stepg = oracle_train_step_fn(B, dcfg, device, use_reference_modules=True)
+                kind = "reference"
+            except Exception:
+                stepg = oracle_train_step_fn(B, dcfg, device)
+                kind = "port"
+            for _ in range(3):
+                stepg()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                stepg()
+            b.record(); b.synchronize()
+            gpu_eager = {"value": 5 * B / (a.elapsed_time(b) / 1e3), "unit": "cells/s", "kind": kind, "ms_per_step": a.elapsed_time(b) / 5,
+                         "sample": f"5 eager PyTorch training steps of {B} cells on the same GPU (DiT fwd/bwd + clip + AdamW, TF32 'high'; no encode, no DDP)"}
+        except Exception as e:
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        finally:
+            torch.set_float32_matmul_precision(prev)
+
+    if rank == 0:
+        cells = B * world
+        line = {
+            "metric": TRAIN_METRIC, "value": cells * args.steps / (ms / 1e3), "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "steps_per_s": args.steps / (ms / 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "mode": "train",
+            "config": {"workload": workload, "cells_per_step_per_gpu": B, "l2": "256 MB flush buffer written between timed steps",
+                       "parallelism": f"dp{world}: replicated DiT, flat fp32 gradient buffer all-reduced in {len(trainer.bucket_bounds) - 1} buckets on a side stream",
+                       "grad_bytes": trainer.n_params * 4, "algorithmic_gflop_per_cell": round(train_flops_per_cell() / 1e9, 4)},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "model_tflops": round(cells * args.steps / (ms / 1e3) * train_flops_per_cell() / 1e12, 2),
+            "e2e": {"value": cells * args.steps / (e2e_ms / 1e3), "unit": "cells/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": cs_h.numel() * 4 + gs_h.numel() * 8 + sum(v.numel() * 8 for v in lab_h.values()), "d2h_bytes_per_step": 4},
+        }
+        if world > 1:
+            exposed = max(ms - noar_ms, 0.0) / args.steps
+            line["allreduce"] = {"ms_per_step": ar_ms, "exposed_ms_per_step": exposed, "overlap_frac": (1.0 - exposed / ar_ms) if ar_ms else None,
+                                 "ms_per_step_without_collective": noar_ms / args.steps,
+                                 "note": "ms_per_step = first bucket start to last bucket end on the side stream (includes waiting for the backward); exposed = step time minus the same step with the collective switched off"}
+        if roofline:
+            line["roofline"] = roofline
+            line["kernel_breakdown"] = breakdown
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if gpu_eager:
+            line["gpu_eager_baseline"] = gpu_eager
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def quiet_stdout():
+    """Multi-rank runs: NCCL writes its version banner to fd 1 at the first collective.  Point fd 1 at stderr for the whole run and
+    return a file object on the original stdout for the single JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,8 +536,21 @@ def main():
     ap.add_argument("--eager-batch", type=int, default=1024)
     ap.add_argument("--dataset", default=DATASET, choices=["dentate_gyrus", "hlca", "tabula_muris", "parse1m", "replogle"],
                     help="gene-vocabulary / class-table shape (BASELINE configs 2-4); the headline line is dentate_gyrus")
+    ap.add_argument("--mode", default="generate", choices=["generate", "train"], help="generate: the headline generation step; train: one LDM training step (BASELINE configs[4])")
+    ap.add_argument("--train-batch", type=int, default=128, help="cells per training step per GPU (ldm_base.yaml:58)")
+    ap.add_argument("--buckets", type=int, default=3, help="gradient all-reduce buckets of the training step")
+    ap.add_argument("--no-gpu-eager-train", action="store_true")
     args = ap.parse_args()
 
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        out = quiet_stdout()
+        _print = print
+        import builtins
+
+        builtins.print = lambda *a, **k: _print(*a, **{**k, "file": k.get("file") or out, "flush": True})
+    if args.mode == "train":
+        run_train(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

@@ -279,7 +279,7 @@ int scldm_dit_train_backward(const scldm_dit_train* tr, const float* dv, float* 
 /* Fused optimizer step over flat buffers: g *= grad_scale; clip by global norm (max_norm <= 0: off; Lightning /
  * torch.nn.utils.clip_grad_norm_ semantics); AdamW (torch.optim.AdamW: decoupled weight decay, bias correction with
  * `step` >= 1); then the bf16 packed copy pk[pk_dst[i]] of every parameter with pk_dst[i] >= 0 is refreshed.
- * scratch: one device float.                                                                                          */
+ * scratch: 512 device floats (deterministic two-stage norm: identical clip coefficient on every data-parallel rank).  */
 int scldm_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int32_t step, float max_norm, float grad_scale, float* scratch,
                      const int32_t* pk_dst, void* pk, void* stream);

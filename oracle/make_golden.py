@@ -229,8 +229,70 @@ def label_dropout_golden() -> None:
     print("dit_label_dropout", {k: v.shape for k, v in arrays.items()})
 
 
+TRAIN_GOLDEN_FULL = ("final_layer.linear.weight", "final_layer.linear.bias", "blocks.0.attn.c_attn.bias", "blocks.1.attn.c_proj.bias",
+                     "class_embeddings.clusters.weight", "input_proj.weight", "t_embedder.mlp.2.bias", "blocks.0.adaln_modulation.1.bias")
+
+
+def train_step_golden() -> None:
+    """One LDM training step of the REFERENCE (`LatentDiffusion.training_step`, models.py:634-666, minus the Lightning shell):
+    `Transport.training_losses(DiT.train(), z, {"condition": labels})` under a fixed CPU seed -> `loss.mean().backward()` through
+    the unmodified reference modules -> `clip_grad_norm_(10)` (training/default.yaml:15) -> `torch.optim.AdamW(lr=5e-4)`
+    (ldm_base.yaml:36-40).  Stores the RNG draws (x0, t, label-dropout mask, re-derived by replaying the reference's sequence of
+    RNG calls), the loss, every gradient's norm, a few gradients in full, strided slices of the rest, and the same for the
+    updated weights: tests/golden/train_step_me1.npz."""
+    ref = ref_loader.load_reference()
+    # torch's flex_attention has no CPU backward ("FlexAttention does not support backward on CPU"), so this fixture is minted on the
+    # GPU box from the staged reference modules (oracle/build_ref.py):  SCLDM_GOLDEN_DEVICE=cuda SCLDM_GOLDEN_DIR=gpurun_out/golden
+    dev = torch.device(os.environ.get("SCLDM_GOLDEN_DEVICE", "cuda" if torch.cuda.is_available() else "cpu"))
+    out_dir = os.environ.get("SCLDM_GOLDEN_DIR", GOLDEN_DIR)
+    os.makedirs(out_dir, exist_ok=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    cfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=2)
+    sd = synthetic.dit_state_dict(cfg, WEIGHT_SEED)
+    model = ref_loader.build_reference_dit(cfg, sd).to(dev).train()
+    for p in model.parameters():
+        p.requires_grad_(True)
+    model.pos_embed.requires_grad_(False)
+    B = 8
+    z = synthetic.randn("train.z", (B, cfg.seq_len, cfg.n_embed_input)).to(dev)
+    lab = {"clusters": synthetic.randint("train.lab", 14, (B,)).to(dev)}
+    transport = ref.transport.create_transport(path_type="Linear", prediction="velocity", loss_weight="velocity", train_eps=1e-5, sample_eps=1e-5)
+    # replay of the reference's RNG calls: Transport.sample (randn_like on the data's device, rand on the CPU: transport.py:104-106),
+    # then DiT's randint + rand on the labels' device (nnets.py:395,402)
+    torch.manual_seed(4242)
+    x0 = torch.randn_like(z)
+    t = torch.rand((B,))
+    torch.randint(0, 1, (), device=dev)
+    drop = torch.rand(B, device=dev) < cfg.cfg_dropout_prob
+    torch.manual_seed(4242)
+    terms = transport.training_losses(model, z, {"condition": lab})
+    loss = terms["loss"].mean()
+    loss.backward()
+    c = lambda a: a.detach().cpu().numpy().copy()  # noqa: E731
+    arrays = dict(z=c(z), label=c(lab["clusters"]), x0=c(x0), t=c(t), drop=c(drop), loss=np.float32(loss.item()),
+                  loss_per_cell=c(terms["loss"]), pred=c(terms["pred"]), device=np.array(str(dev)))
+    params = dict(model.named_parameters())
+    names = [n for n, p in params.items() if p.requires_grad]
+    arrays["names"] = np.array(names)
+    arrays["grad_norms"] = np.array([float(params[n].grad.norm()) for n in names], dtype=np.float64)
+    for n in names:
+        g = params[n].grad
+        arrays["grad." + n] = c(g) if n in TRAIN_GOLDEN_FULL else c(g.reshape(-1)[::97])
+    total = torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 10.0)
+    arrays["total_norm"] = np.float64(float(total))
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=5e-4, weight_decay=0.0)
+    opt.step()
+    for n in names:
+        w = params[n].detach()
+        arrays["new." + n] = c(w) if n in TRAIN_GOLDEN_FULL else c(w.reshape(-1)[::97])
+    np.savez_compressed(os.path.join(out_dir, "train_step_me1.npz"), **arrays)
+    print("train_step_me1 loss", float(loss), "total grad norm", float(total), "dropped", int(drop.sum()))
+
+
 if __name__ == "__main__":
-    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden}   # fixtures added after the first set; minted
+    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden}   # fixtures added after the first set; minted
     if len(sys.argv) > 1 and sys.argv[1] in later:                                 # alone so the others stay byte-identical
         later[sys.argv[1]]()
     else:

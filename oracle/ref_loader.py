@@ -1,9 +1,10 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.
 
 Loads the *unmodified* reference modules from `/root/reference/src/scldm` in-process so that
-golden vectors can be minted from the reference itself (dev container only: the reference
-tree does not exist on the GPU box, and nothing in `-m gpu` tests, `smoke()` or `bench.py`
-may call this at run time).
+golden vectors can be minted from the reference itself.  On the GPU box `/root/reference` does not
+exist; the byte-identical copies staged by `oracle/build_ref.py` under `oracle/_ref/` (git-ignored,
+shipped with the snapshot) are loaded instead - as the checker in tests and as the thing timed by
+`bench.py --impl reference`, never on the product path.
 
 `scldm/__init__.py` cannot be imported (it pulls `scvi` and package metadata), so a namespace
 stub is registered instead and the submodules are imported directly.  Two third-party
@@ -21,7 +22,8 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = os.environ.get("SCLDM_REFERENCE_SRC", "/root/reference/src/scldm")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "scldm")   # oracle/build_ref.py (travels to the GPU box)
+REFERENCE_SRC = os.environ.get("SCLDM_REFERENCE_SRC") or ("/root/reference/src/scldm" if os.path.isdir("/root/reference/src/scldm") else _STAGED)
 
 
 def reference_available() -> bool:

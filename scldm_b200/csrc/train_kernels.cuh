@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(dit::NUM_THREADS, 1) gemm_kernel(const GemmPar
     sm100::fence_barrier_init();
   }
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 256);
+  sm100::grid_dep_launch();   // barrier init / TMEM allocation above overlap the tail of the preceding kernel (PDL)
+  sm100::grid_dep_wait();
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
@@ -209,6 +211,8 @@ struct LnModParams {
   bf16* h; float* h_f32; int rows;
 };
 __global__ void __launch_bounds__(256) lnmod_fwd_kernel(const LnModParams p) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= p.rows) return;
@@ -236,15 +240,19 @@ __global__ void __launch_bounds__(256) lnmod_fwd_kernel(const LnModParams p) {
 // backward of the above for one cell (16 rows): dX (+)= LN-backward(dh * (1 + mul)); dmul = sum_tok dh * xhat; dadd = sum_tok dh
 struct LnModBwdParams {
   const float* X; const float* mod; long long mod_stride; int off_mul, off_add; float eps;
-  const float* dh; float* dX; int accumulate; float* dmod; long long dmod_stride;
+  float* dh; float* dX; int accumulate; float* dmod; long long dmod_stride;
+  int clear_dh;   // 1: zero dh after reading it (the next split-K dgrad accumulates into it with atomics)
 };
 __global__ void __launch_bounds__(512) lnmod_bwd_kernel(const LnModBwdParams p) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float red[2][TOK][D];   // 32 KB
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x, row = cell * TOK + warp, c0 = lane * 8;
   float x[8], dh[8], mul[8];
   load8(p.X + (size_t)row * D + c0, x);
   load8(p.dh + (size_t)row * D + c0, dh);
+  if (p.clear_dh) { const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; store8(p.dh + (size_t)row * D + c0, z8); }
   load8(p.mod + (size_t)cell * p.mod_stride + p.off_mul + c0, mul);
   float s = 0.f;
 #pragma unroll
@@ -289,6 +297,8 @@ __global__ void __launch_bounds__(512) lnmod_bwd_kernel(const LnModBwdParams p) 
 // x_out = x_in + gate[cell] * y   (layers.py:218,221)
 __global__ void __launch_bounds__(256) resid_fwd_kernel(const float* __restrict__ Xin, const float* __restrict__ y, const float* __restrict__ mod,
                                                         long long mod_stride, int off_gate, float* __restrict__ Xout, int rows) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)rows * (D / 4)) return;
   const int row = (int)(idx >> 6), c = (int)(idx & 63) * 4;
@@ -302,6 +312,8 @@ __global__ void __launch_bounds__(256) resid_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(512) resid_bwd_kernel(const float* __restrict__ dX, const float* __restrict__ y, const float* __restrict__ mod,
                                                         long long mod_stride, int off_gate, bf16* __restrict__ dy, float* __restrict__ dmod,
                                                         long long dmod_stride) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float red[TOK][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x, row = cell * TOK + warp, c0 = lane * 8;
@@ -324,6 +336,8 @@ __global__ void __launch_bounds__(512) resid_bwd_kernel(const float* __restrict_
 // SwiGLU (layers.py:161-174).  ab [rows][T*256]: per 128-hidden tile j the columns [256j, +128) = w1 x, [256j+128, +128) = w2 x.
 // s[rows][T*128] = silu(a) * b as a slab tensor.
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const float* __restrict__ ab, int n_tiles, bf16* __restrict__ s, int rows) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int per_row = n_tiles * 16;   // 8-wide groups per row
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)rows * per_row) return;
@@ -337,8 +351,10 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const float* __restrict
   *reinterpret_cast<uint4*>(slab_chunk(s, n_tiles * 128, row, g8)) = pack8(o);
 }
 // ds [rows][T*128] -> dab slab tensor [rows][T*256] in the same interleaved column order as `ab`
-__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ ab, int n_tiles,
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(float* __restrict__ ds, const float* __restrict__ ab, int n_tiles,
                                                          bf16* __restrict__ dab, int rows) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int per_row = n_tiles * 16;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)rows * per_row) return;
@@ -348,6 +364,7 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const float* __restrict
   load8(ab + (size_t)row * n_tiles * 256 + j * 256 + off, a);
   load8(ab + (size_t)row * n_tiles * 256 + j * 256 + 128 + off, b);
   load8(ds + (size_t)row * n_tiles * 128 + g8, d);
+  { const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; store8(ds + (size_t)row * n_tiles * 128 + g8, z8); }   // consumed: the next split-K dgrad accumulates into zeros
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float sg = sigmoidf_(a[k]);
@@ -364,6 +381,8 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 constexpr int ATT_LD = D + 4;   // padded row stride of the shared tiles (floats)
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__ qkv, bf16* __restrict__ ao) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float sK[TOK][ATT_LD];
   __shared__ float sV[TOK][ATT_LD];
   const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -416,7 +435,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
 // backward: dao [rows][256] fp32, qkv [rows][768] fp32 -> dqkv slab tensor [rows][768]
 constexpr int ATT_PS = 17;
 constexpr size_t attn_bwd_smem_bytes() { return (4 * TOK * ATT_LD + 2 * NHEAD * TOK * ATT_PS) * sizeof(float); }
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dao, bf16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__ qkv, float* __restrict__ dao, bf16* __restrict__ dqkv) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   extern __shared__ __align__(16) float sm_att[];
   float (*sQ)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(sm_att);
   float (*sK)[ATT_LD] = sQ + TOK;
@@ -432,6 +453,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     *reinterpret_cast<float4*>(&sK[r][c]) = *reinterpret_cast<const float4*>(src + D + c);
     *reinterpret_cast<float4*>(&sV[r][c]) = *reinterpret_cast<const float4*>(src + 2 * D + c);
     *reinterpret_cast<float4*>(&sO[r][c]) = *reinterpret_cast<const float4*>(dao + (size_t)(cell * TOK + r) * D + c);
+    *reinterpret_cast<float4*>(dao + (size_t)(cell * TOK + r) * D + c) = make_float4(0.f, 0.f, 0.f, 0.f);   // consumed (see lnmod_bwd_kernel)
   }
   __syncthreads();
   const int h = warp * 2 + (lane >> 4), i = lane & 15, row = cell * TOK + i;
@@ -529,6 +551,8 @@ __device__ __forceinline__ void matvec256(const float* __restrict__ W, const flo
   }
 }
 __global__ void __launch_bounds__(256) cond_fwd_kernel(const CondParams p) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float f[D], h[D], te[D];
   const int cell = blockIdx.x, d = threadIdx.x, warp = d >> 5, lane = d & 31;
   const float tv = p.t[cell];
@@ -569,6 +593,8 @@ struct CondBwdParams {
   float* dc; float* dh0;
 };
 __global__ void __launch_bounds__(256) cond_bwd_kernel(const CondBwdParams p) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float sdc[D];
   const int cell = blockIdx.x, d = threadIdx.x;
   const float c = p.c[(size_t)cell * D + d];
@@ -589,6 +615,8 @@ __global__ void __launch_bounds__(256) cond_bwd_kernel(const CondBwdParams p) {
 // dW[o][k] += sum_n dy[n][o] * x[n][k]   (small Linear layers: t_embedder, input_proj, final linear); grid (ceil(O*K/256), n chunks)
 __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ dy, int O, const float* __restrict__ x, int K, int n, int n_chunk,
                                                           float* __restrict__ dW) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= O * K) return;
   const int o = idx / K, k = idx % K;
@@ -599,6 +627,8 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restric
 }
 // db[c] += sum_n y[n][c]; grid (ceil(C/256), n chunks)
 __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ y, int C, long long ld, int n, int n_chunk, float* __restrict__ db) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   const int n0 = blockIdx.y * n_chunk, n1 = min(n, n0 + n_chunk);
@@ -608,6 +638,8 @@ __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict
 }
 // db[c] += sum over the rows of a slab tensor [rows][C] (bf16); grid (C/64, row tiles), 64 threads... one thread per column
 __global__ void __launch_bounds__(64) colsum_slab_kernel(const bf16* __restrict__ t, int C, float* __restrict__ db) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int slab = blockIdx.x, rt = blockIdx.y, c = threadIdx.x;
   const bf16* base = t + ((size_t)rt * (C >> 6) + slab) * SLAB_ELEMS;
   float acc = 0.f;
@@ -618,6 +650,8 @@ __global__ void __launch_bounds__(64) colsum_slab_kernel(const bf16* __restrict_
 // fp32 [n][ld] columns [col0, col0 + ncols) -> slab tensor [.][C_dst] columns [dcol0, ...); one thread per 8 columns
 __global__ void __launch_bounds__(256) f32_to_slab_kernel(const float* __restrict__ src, long long ld, int col0, int ncols, int n, bf16* __restrict__ dst,
                                                           int C_dst, int dcol0) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int per_row = ncols >> 3;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)n * per_row) return;
@@ -630,6 +664,8 @@ __global__ void __launch_bounds__(256) f32_to_slab_kernel(const float* __restric
 // input projection (nnets.py:290-291): X0[row][c] = sum_k x[row][k] w_in[c][k] + b_in[c] + pos[row % 16][c]
 __global__ void __launch_bounds__(256) inproj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_in, const float* __restrict__ b_in,
                                                          const float* __restrict__ pos, float* __restrict__ X0) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float xs[LAT];
   const int row = blockIdx.x, c = threadIdx.x;
   if (c < LAT) xs[c] = x[(size_t)row * LAT + c];
@@ -641,6 +677,8 @@ __global__ void __launch_bounds__(256) inproj_fwd_kernel(const float* __restrict
 }
 // dx[row][k] = sum_c dX0[row][c] w_in[c][k]   (only when the caller wants the gradient wrt the noisy latents)
 __global__ void __launch_bounds__(256) inproj_dx_kernel(const float* __restrict__ dX0, const float* __restrict__ w_in, float* __restrict__ dx) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float part[16][LAT];
   const int row = blockIdx.x, k = threadIdx.x & 15, g = threadIdx.x >> 4;
   float acc = 0.f;
@@ -658,6 +696,8 @@ __global__ void __launch_bounds__(256) inproj_dx_kernel(const float* __restrict_
 // final Linear 256 -> 16 (layers.py:401): v[row][o] = sum_c hf[row][c] w_out[o][c] + b_out[o]; warp per row
 __global__ void __launch_bounds__(256) final_lin_fwd_kernel(const float* __restrict__ hf, const float* __restrict__ w_out, const float* __restrict__ b_out,
                                                             float* __restrict__ v, int rows) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -678,6 +718,8 @@ __global__ void __launch_bounds__(256) final_lin_fwd_kernel(const float* __restr
 }
 // dhf[row][c] = sum_o dv[row][o] w_out[o][c]
 __global__ void __launch_bounds__(256) final_lin_dh_kernel(const float* __restrict__ dv, const float* __restrict__ w_out, float* __restrict__ dhf) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float s[LAT];
   const int row = blockIdx.x, c = threadIdx.x;
   if (c < LAT) s[c] = dv[(size_t)row * LAT + c];
@@ -691,7 +733,12 @@ __global__ void __launch_bounds__(256) final_lin_dh_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 // optimizer: global gradient norm, AdamW (torch.optim.AdamW semantics) with norm clipping, refresh of the bf16 packed weights
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// deterministic two-stage sum of squares (the clip coefficient must be bit-identical on every data-parallel rank, or the replicas
+// drift apart by an ulp per step): partial[block] in a fixed thread order, then one block folds the partials in a fixed order
+constexpr int SUMSQ_BLOCKS = 296;
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * 1024) {
@@ -708,8 +755,16 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[i];
-    atomicAdd(out, s);
+    partial[1 + blockIdx.x] = s;
   }
+}
+__global__ void __launch_bounds__(32) sumsq_final_kernel(float* __restrict__ partial, int n_blocks) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_blocks; i += 32) acc += partial[1 + i];
+  acc = sm100::warp_sum(acc);
+  if (threadIdx.x == 0) partial[0] = acc;
 }
 struct AdamParams {
   float* p; const float* g; float* m; float* v; long long n;
@@ -719,6 +774,8 @@ struct AdamParams {
   const int* pk_dst; bf16* pk;                           // packed bf16 position of every parameter (-1: not a GEMM weight)
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= a.n) return;
   float coef = a.grad_scale;
@@ -740,6 +797,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
 }
 // packed[dst[i]] = bf16(p[i]) for every GEMM weight (initial pack / after load_state_dict)
 __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ p, const int* __restrict__ pk_dst, bf16* __restrict__ pk, long long n) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const int dst = pk_dst[i];
@@ -747,6 +806,8 @@ __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ p
 }
 // EMA of the parameters (ema_pytorch semantics as configured by ldm_base.yaml:51-53): ema += (1 - decay) * (p - ema)
 __global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ ema, const float* __restrict__ p, long long n, float one_minus_decay) {
+  sm100::grid_dep_launch();   // programmatic dependent launch: let the next kernel's CTAs become resident ...
+  sm100::grid_dep_wait();     // ... and do not touch global memory before the preceding kernel has completed
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i < n) ema[i] += one_minus_decay * (p[i] - ema[i]);
 }

@@ -161,7 +161,7 @@ class DiTTrainer:
         self.grad = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
-        self.scratch = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros(512, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for name in order:
                 p = sd[name]

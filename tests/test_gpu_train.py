@@ -171,7 +171,7 @@ def test_fused_adamw_matches_torch():
     ref = torch.nn.Parameter(p0.clone())
     opt = torch.optim.AdamW([ref], lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
     p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
-    scratch = torch.zeros(4, device="cuda")
+    scratch = torch.zeros(512, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for step, gr in enumerate(grads, 1):
         ref.grad = gr.clone()
@@ -224,3 +224,49 @@ def test_nb_inversion_never_returns_the_loop_cap():
     torch.cuda.synchronize()
     print("nb_invert(u=1):", k.tolist())
     assert float(k.max()) < 200 and float(k[0]) < 16 and float(k[4]) < 8, k.tolist()
+
+
+def test_training_step_vs_reference_minted_golden(golden_dir):
+    """The whole step against the UNMODIFIED reference (tests/golden/train_step_me1.npz, minted on a B200 by
+    `oracle.make_golden train_step` from the staged reference modules): loss, every gradient, and the weights after
+    clip_grad_norm_(10) + AdamW(lr=5e-4)."""
+    import os
+
+    import numpy as np
+
+    from scldm_b200.training import DiTTrainer
+
+    g = dict(np.load(os.path.join(golden_dir, "train_step_me1.npz")))
+    cfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=2)
+    dit, sd = make(cfg)
+    tr = DiTTrainer(dit, lr=5e-4, max_grad_norm=10.0)
+    z, x0, t = (torch.from_numpy(g[k]).cuda() for k in ("z", "x0", "t"))
+    lab = torch.from_numpy(g["label"]).clone()
+    lab[torch.from_numpy(g["drop"])] = 14
+    B = z.shape[0]
+    te = t.view(-1, 1, 1)
+    v = tr.forward(te * z + (1 - te) * x0, t, tr.cls_rows({"clusters": lab.cuda()}, B))
+    diff = v - (z - x0)
+    loss = float((diff * diff).flatten(1).mean(1).mean())
+    tr.backward(diff * (2.0 / (B * 256)))
+    torch.cuda.synchronize()
+    assert abs(loss - float(g["loss"])) < 1e-3 * float(g["loss"])
+    assert rel_l2(v, g["pred"]) < TOL_V
+    params = dict(dit.named_parameters())
+    for n, gn in zip([str(x) for x in g["names"]], g["grad_norms"]):
+        ref = g["grad." + n]
+        mine = params[n].grad if ref.shape == tuple(params[n].shape) else params[n].grad.reshape(-1)[::97]
+        assert rel_l2(mine, ref) < TOL_GRAD, n
+        assert abs(float(params[n].grad.norm()) - gn) < 1e-2 * gn, n
+    old = {n: p.detach().clone() for n, p in params.items()}
+    tr.optimizer_step()
+    torch.cuda.synchronize()
+    for n in [str(x) for x in g["names"]]:
+        ref = torch.from_numpy(g["new." + n]).cuda()
+        w, w0 = params[n].detach(), old[n]
+        mine, before = (w, w0) if ref.shape == tuple(w.shape) else (w.reshape(-1)[::97], w0.reshape(-1)[::97])
+        # compare the UPDATE (new - old, ~lr per element) where the gradient is not rounding noise
+        gref = torch.from_numpy(g["grad." + n]).cuda()
+        big = gref.abs() > 1e-4 * gref.abs().max()
+        du, dr = (mine - before)[big], (ref - before)[big]
+        assert float((du - dr).norm() / dr.norm()) < 5e-2, n

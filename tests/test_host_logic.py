@@ -336,3 +336,48 @@ def test_training_mode_label_dropout_matches_reference(golden_dir, name):
     rows = m._cls_rows(m._active_labels(labels, force_drop_ids=False), n, "cpu")
     nulls = torch.tensor([cfg.class_vocab_sizes[c] for c in sorted(cfg.class_vocab_sizes)])
     assert int((rows != nulls[:, None]).any(1).sum()) == (len(labels) if cfg.condition_strategy == "joint" else 1)
+
+
+def test_training_flat_layout_and_pack_map():
+    """Host logic of `scldm_b200.training`: the flat buffer is ordered by gradient completion (final layer, blocks L-1..0, tail), the
+    adaLN biases are contiguous in block order, and the bf16 tile arena is a pure gather of the flat buffer that reproduces
+    `pack.pack_kmajor_tiles` of every GEMM weight."""
+    import torch
+
+    from scldm_b200 import synthetic
+    from scldm_b200.config import DiTConfig
+    from scldm_b200.pack import pack_kmajor_tiles
+    from scldm_b200.training import flat_layout, pack_sources, wsd_schedule
+
+    cfg = DiTConfig(class_vocab_sizes={"b": 3, "a": 5}, n_layer=3, condition_strategy="joint")
+    sd = synthetic.dit_state_dict(cfg)
+    shapes = {k: tuple(v.shape) for k, v in sd.items() if k != "pos_embed"}
+    names, off, layer_end, n = flat_layout(cfg, shapes)
+    assert set(names) == set(shapes) and len(names) == len(shapes)
+    assert names[0].startswith("final_layer") and names.index("blocks.2.attn.c_attn.weight") < names.index("blocks.0.attn.c_attn.weight")
+    assert layer_end[2] < layer_end[1] < layer_end[0] < n
+    assert all(o % 4 == 0 for o in off.values())
+    for l in range(3):
+        assert off[f"blocks.{l}.adaln_modulation.1.bias"] == off["blocks.0.adaln_modulation.1.bias"] + l * 1536
+    assert names.index("class_embeddings.a.weight") < names.index("class_embeddings.b.weight")   # sorted class names
+    flat = torch.zeros(n)
+    for k in names:
+        flat[off[k]: off[k] + sd[k].numel()] = sd[k].reshape(-1)
+    src, pko = pack_sources(cfg, off, shapes)
+    pk = torch.where(src >= 0, flat[src.clamp_min(0)], torch.zeros(())).to(torch.bfloat16)
+    H, T = cfg.hidden, -(-cfg.hidden // 128)
+    ref_qkv = torch.stack([pack_kmajor_tiles(sd[f"blocks.{l}.attn.c_attn.weight"], 256) for l in range(3)]).reshape(-1)
+    assert torch.equal(pk[pko["qkv"]: pko["qkv"] + ref_qkv.numel()], ref_qkv)
+    w3 = torch.zeros(256, T * 128)
+    w3[:, :H] = sd["blocks.1.mlp.c_proj.weight"]
+    ref_w3 = pack_kmajor_tiles(w3, 256).reshape(-1)
+    o = pko["w3"] + ref_w3.numel()
+    assert torch.equal(pk[o: o + ref_w3.numel()], ref_w3)
+    mod = torch.cat([sd[f"blocks.{l}.adaln_modulation.1.weight"] for l in range(3)] + [sd["final_layer.adaln_modulation.1.weight"]], 0)
+    assert torch.equal(pk[pko["mod"]:], pack_kmajor_tiles(mod, 256).reshape(-1))
+    # every GEMM weight element appears exactly once in the arena
+    used = src[src >= 0]
+    assert used.numel() == used.unique().numel()
+    # the reference's LR schedule (scldm/_utils.py:19-60)
+    f = wsd_schedule(1000, final_lr_factor=0.1, num_warmup_steps=100, init_div_factor=100, fract_decay=0.1)
+    assert abs(f(0) - 0.01) < 1e-12 and f(100) == 1.0 and f(899) == 1.0 and 0.1 < f(950) < 1.0 and f(1000) == 0.1
