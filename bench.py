@@ -132,18 +132,35 @@ def kernel_flops(name: str, rows: int, mod_rows: int) -> float | None:
     }.get(name)
 
 
-def cpu_sample(B: int, dcfg, vcfg, threads: int):
-    """The reference's CPU path (oracle restatement of the reference modules), fp32, `threads` host threads."""
+def reference_kind() -> str:
+    """"reference": the reference's own modules are staged under oracle/_ref (oracle/build_ref.py; they travel to the GPU box);
+    "port": only the oracle restatement is available."""
+    from oracle import ref_loader
+
+    return "reference" if ref_loader.reference_available() else "port"
+
+
+def cpu_sample(B: int, dcfg, vcfg, threads: int, device="cpu"):
+    """The reference's generation path in eager PyTorch, fp32: its OWN modules (oracle/_ref, `kind: "reference"`) composed as
+    `LatentDiffusion.sample` composes them, or - when they are not staged - the oracle restatement (`kind: "port"`)."""
     from oracle import scldm_oracle as O
     from scldm_b200 import synthetic
 
-    torch.set_num_threads(threads)
+    if device == "cpu":
+        torch.set_num_threads(threads)
     dsd, vsd = synthetic.dit_state_dict(dcfg, 1234), synthetic.vae_state_dict(vcfg, 1234)
-    z0 = synthetic.randn("cpu.z0", (B, 16, 16))
-    lab = {k: synthetic.randint("cpu.lab." + k, v, (B,)) for k, v in dcfg.class_vocab_sizes.items()}
+    z0 = synthetic.randn("cpu.z0", (B, 16, 16)).to(device)
+    lab = {k: synthetic.randint("cpu.lab." + k, v, (B,)).to(device) for k, v in dcfg.class_vocab_sizes.items()}
     w = {k: GUIDANCE for k in dcfg.class_vocab_sizes}
-    lsf = 8.0 + 0.3 * synthetic.randn("cpu.lsf", (B,))
-    genes = torch.arange(1, vcfg.n_genes + 1).unsqueeze(0).expand(B, -1)
+    lsf = (8.0 + 0.3 * synthetic.randn("cpu.lsf", (B,))).to(device)
+    genes = torch.arange(1, vcfg.n_genes + 1, device=device).unsqueeze(0).expand(B, -1)
+    if reference_kind() == "reference":
+        from oracle import ref_loader
+
+        ref_step = ref_loader.reference_sample_fn(dcfg, vcfg, dsd, vsd, device=device, num_steps=NUM_STEPS, method="euler")
+        return lambda: ref_step(z0, lab, w, genes, lsf)
+    dsd = {k: v.to(device) for k, v in dsd.items()}
+    vsd = {k: v.to(device) for k, v in vsd.items()}
 
     def step():
         with torch.no_grad():
@@ -163,31 +180,15 @@ def workload_name(dataset, dcfg, vcfg, method="euler") -> str:
 
 
 def gpu_eager_sample(B: int, dcfg, vcfg, device):
-    """The same oracle port as `cpu_sample`, with every tensor on the GPU: what the reference's eager PyTorch generation
-    costs on this device (library kernels, TF32 matmuls as `experiments/scripts/inference.py:26` sets them).  A reported
-    comparator only - never part of `value` / `e2e`."""
-    from oracle import scldm_oracle as O
-    from scldm_b200 import synthetic
-
-    dsd = {k: v.to(device) for k, v in synthetic.dit_state_dict(dcfg, 1234).items()}
-    vsd = {k: v.to(device) for k, v in synthetic.vae_state_dict(vcfg, 1234).items()}
-    z0 = synthetic.randn("cpu.z0", (B, 16, 16)).to(device)
-    lab = {k: synthetic.randint("cpu.lab." + k, v, (B,)).to(device) for k, v in dcfg.class_vocab_sizes.items()}
-    w = {k: GUIDANCE for k in dcfg.class_vocab_sizes}
-    lsf = (8.0 + 0.3 * synthetic.randn("cpu.lsf", (B,))).to(device)
-    genes = torch.arange(1, vcfg.n_genes + 1, device=device).unsqueeze(0).expand(B, -1)
-
-    def step():
-        with torch.no_grad():
-            mu, theta, z = O.latent_diffusion_sample(z0, lab, w, genes, lsf, dsd, dcfg, vsd, vcfg, num_steps=NUM_STEPS, method="euler")
-            return O.nb_sample(mu, theta)
-
-    return step
+    """The same reference path as `cpu_sample` with every tensor on the GPU: what the reference's eager PyTorch generation costs on
+    this device (library kernels, TF32 matmuls as `experiments/scripts/inference.py:26` sets them).  A reported comparator only -
+    never part of `value` / `e2e`."""
+    return cpu_sample(B, dcfg, vcfg, 0, device=device)
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle port; the
-    reference tree itself does not exist on the GPU box).  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores - its unmodified modules staged under
+    oracle/_ref by oracle/build_ref.py (the oracle port only if they are absent).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -210,8 +211,8 @@ def run_reference(args):
         "data": "synthetic", "impl": "reference",
         "config": {"workload": workload_name(args.dataset, dcfg, vcfg),
                    "cells_per_step": B, "rows_per_step": 2 * B, "note": "bounded sample of the GPU arm's workload; CPU only"},
-        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} x sample() of {B} cells (2B={2 * B} rows), oracle port of the reference modules"},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": reference_kind(),
+                         "sample": f"{args.steps} x sample() of {B} cells (2B={2 * B} rows), " + ("the reference's own modules (oracle/_ref)" if reference_kind() == "reference" else "oracle port of the reference modules")},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -522,18 +523,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2368, help="cells per step per GPU (2x rows are generated)")
     ap.add_argument("--chunk", type=int, default=0, help="cells per ODE chunk (0 = library default)")
-    ap.add_argument("--ref-batch", type=int, default=32, help="cells per step of the CPU reference arm (the oracle port saturates its matmuls from ~32 cells)")
+    ap.add_argument("--ref-batch", type=int, default=64, help="cells per step of the CPU reference arm (BASELINE configs[0]: batch 64)")
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
     ap.add_argument("--method", default="euler", choices=["euler", "heun2", "midpoint", "dopri5"],
                     help="ODE solver of sample_ode; the headline line is the fixed-grid Euler of BASELINE configs[1]")
-    ap.add_argument("--gpu-eager", action="store_true",
-                    help="also time the oracle port run eagerly on the GPU (PyTorch library kernels) as a comparator; off by default: "
-                         "the default run executes oracle/ only in the cpu_baseline leg")
-    ap.add_argument("--no-gpu-eager", action="store_true", help="(default) kept for older command lines")
-    ap.add_argument("--eager-batch", type=int, default=1024)
+    ap.add_argument("--gpu-eager", action="store_true", help="(default) kept for older command lines")
+    ap.add_argument("--no-gpu-eager", action="store_true",
+                    help="skip the reference modules run eagerly on the same GPU (PyTorch library kernels, TF32 'high'): the honest library-call comparator")
+    ap.add_argument("--eager-batch", type=int, default=128, help="cells per eager step (the reference's default generation batch, generation.yaml:16)")
     ap.add_argument("--dataset", default=DATASET, choices=["dentate_gyrus", "hlca", "tabula_muris", "parse1m", "replogle"],
                     help="gene-vocabulary / class-table shape (BASELINE configs 2-4); the headline line is dentate_gyrus")
     ap.add_argument("--mode", default="generate", choices=["generate", "train"], help="generate: the headline generation step; train: one LDM training step (BASELINE configs[4])")
@@ -575,11 +575,20 @@ def main():
         ldm.cell_chunk = args.chunk
     B, G = args.batch, vcfg.n_genes
     gw = {k: GUIDANCE for k in dcfg.class_vocab_sizes}
-    gen = torch.Generator().manual_seed(100 + rank)
-    labels_h = {k: torch.randint(0, v, (B,), generator=gen).pin_memory() for k, v in dcfg.class_vocab_sizes.items()}
+    # the GLOBAL batch (B cells per GPU, weak scaling) is described once, identically on every rank; `dist.sample_sharded` - the
+    # product's multi-GPU call - makes every rank generate its contiguous slice (Philox streams keyed by the global cell index)
+    from scldm_b200 import dist as sdist
+
+    Bg = B * world
+    gen = torch.Generator().manual_seed(100)
+    labels_gh = {k: torch.randint(0, v, (Bg,), generator=gen) for k, v in dcfg.class_vocab_sizes.items()}
+    a0, a1 = sdist.shard_range(Bg, rank, world)
+    labels_h = {k: v[a0:a1].clone().pin_memory() for k, v in labels_gh.items()}
     genes_row_h = torch.arange(1, G + 1, dtype=torch.int64).pin_memory()
-    labels_d = {k: v.to(device) for k, v in labels_h.items()}
-    genes_d = genes_row_h.to(device).unsqueeze(0).expand(B, -1)  # (B,G) view of one row, as the tokenizer tiles it
+    labels_g = {k: v.to(device) for k, v in labels_gh.items()}
+    labels_d = {k: v[a0:a1] for k, v in labels_g.items()}
+    genes_g = genes_row_h.to(device).unsqueeze(0).expand(Bg, -1)   # (B,G) view of one row, as the tokenizer tiles it
+    genes_d = genes_g[a0:a1]
     counts_h = torch.empty(2 * B, G, dtype=torch.float32).pin_memory()
     z_h = torch.empty(2 * B, 16, 16, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -592,7 +601,10 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        return ldm.sample(labels_d, gw, B, genes_d)
+        return sdist.sample_sharded(ldm, labels_g, gw, Bg, genes_g, gather=False)
+
+    def step_gather():
+        return sdist.sample_sharded(ldm, labels_g, gw, Bg, genes_g, gather=True)    # + NCCL all_gather of counts and z to every rank
 
     def step_e2e():
         lab = {k: v.to(device, non_blocking=True) for k, v in labels_h.items()}
@@ -650,12 +662,18 @@ def main():
         barrier()
         e2e_csr_ms = timed(step_e2e_csr, args.steps)
         barrier()
-    t = torch.tensor([ms, e2e_ms or 0.0], device=device, dtype=torch.float64)
+    gather_ms = None
+    if world > 1:
+        step_gather()
+        barrier()
+        gather_ms = timed(step_gather, args.steps)
+        barrier()
+    t = torch.tensor([ms, e2e_ms or 0.0, gather_ms or 0.0], device=device, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms_max = float(t[0]), float(t[1])
+    ms, e2e_ms_max, gather_ms = float(t[0]), float(t[1]), float(t[2])
     rows_per_step = 2 * B * world
     value = rows_per_step * args.steps / (ms / 1e3)
 
@@ -696,12 +714,13 @@ def main():
         t0 = time.perf_counter()
         stepc()
         dtc = time.perf_counter() - t0
-        cpu_baseline = {"value": 2 * args.cpu_batch / dtc, "unit": "cells/s", "cores": threads, "kind": "port",
-                        "sample": f"1 x sample() of {args.cpu_batch} cells ({2 * args.cpu_batch} rows): same model, 49-eval Euler + CFG + decode + NB draw, fp32 oracle port",
+        cpu_baseline = {"value": 2 * args.cpu_batch / dtc, "unit": "cells/s", "cores": threads, "kind": reference_kind(),
+                        "sample": f"1 x sample() of {args.cpu_batch} cells ({2 * args.cpu_batch} rows): same model, 49-eval Euler + CFG + decode + NB draw, fp32, "
+                                  + ("the reference's own modules (oracle/_ref)" if reference_kind() == "reference" else "oracle port"),
                         "seconds": round(dtc, 2)}
 
     gpu_eager = None
-    if rank == 0 and args.gpu_eager and not args.no_gpu_eager:
+    if rank == 0 and not args.no_gpu_eager:
         prev = torch.get_float32_matmul_precision()
         try:
             torch.set_float32_matmul_precision("high")
@@ -710,8 +729,8 @@ def main():
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); stepg(); b.record(); b.synchronize()
-            gpu_eager = {"value": 2 * args.eager_batch / (a.elapsed_time(b) / 1e3), "unit": "cells/s", "kind": "port",
-                         "sample": f"1 x sample() of {args.eager_batch} cells: oracle port of the reference modules run eagerly on the same GPU "
+            gpu_eager = {"value": 2 * args.eager_batch / (a.elapsed_time(b) / 1e3), "unit": "cells/s", "kind": reference_kind(),
+                         "sample": f"1 x sample() of {args.eager_batch} cells: the reference modules ({reference_kind()}) run eagerly on the same GPU "
                                    "(PyTorch library kernels, float32 matmul precision 'high' as the reference's inference script)"}
         except Exception as e:  # a comparator must never take the bench line down
             gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
@@ -730,7 +749,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args.dataset, dcfg, vcfg, args.method),
                        "cells_per_step_per_gpu": B, "rows_per_step": rows_per_step, "ode_chunk_cells": min(ldm.cell_chunk, B),
-                       "l2": "256 MB flush buffer written between timed steps", "parallelism": f"cells sharded over {world} GPU(s), no collective",
+                       "l2": "256 MB flush buffer written between timed steps", "parallelism": f"dist.sample_sharded: global batch of {Bg} cells split contiguously over {world} GPU(s), no collective in the step (outputs stay rank-local)",
                        "algorithmic_gflop_per_row": round(fl["row_cfg"] / 1e9, 3), "dit_evaluations_per_solve": evals},
             "clocks": clocks,
             "gpu_launches": int(launches),
@@ -744,6 +763,10 @@ def main():
             if e2e_csr_ms is not None:   # rank-0 time; informational (the contract's `e2e` keeps the reference's dense return)
                 line["e2e_csr"] = {"value": 2 * B * args.steps / (e2e_csr_ms / 1e3) * world, "unit": "cells/s", "d2h_bytes_per_step": csr_bytes[0],
                                    "note": "LatentDiffusion.sample_csr: CSR built on the device, pageable D2H of indptr/indices/data"}
+        if world > 1:
+            line["gathered"] = {"value": rows_per_step * args.steps / (gather_ms / 1e3), "unit": "cells/s", "ms_per_step": gather_ms / args.steps,
+                                "allgather_bytes_per_rank": rows_per_step * (G + 256) * 4,
+                                "note": "same step through dist.sample_sharded(gather=True): NCCL all_gather of counts (2B x G fp32) and z to every rank"}
         if roofline:
             line["roofline"] = roofline
             line["kernel_breakdown"] = breakdown

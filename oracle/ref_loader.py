@@ -120,3 +120,26 @@ def build_reference_vae(cfg, state_dict):
     )
     vae.load_state_dict(state_dict, strict=True)
     return vae.eval()
+
+
+def reference_sample_fn(dit_cfg, vae_cfg, dit_sd, vae_sd, device="cpu", num_steps=50, method="euler"):
+    """`LatentDiffusion.sample` (`models.py:766-819`) composed from the reference's OWN modules (its Lightning class is not
+    importable): `Sampler.sample_ode(method, num_steps)` driving `DiT.forward_with_cfg`, then `TransformerVAE.decode(...).sample()`.
+    Returns step(z0, labels, guidance_weight, genes, log_size_factors) -> (counts (2B,G), z (2B,16,16))."""
+    import torch
+
+    ref = load_reference()
+    dit = build_reference_dit(dit_cfg, dit_sd).to(device)
+    vae = build_reference_vae(vae_cfg, vae_sd).to(device)
+    transport = ref.transport.create_transport(path_type="Linear", prediction="velocity", loss_weight="velocity", train_eps=1e-5, sample_eps=1e-5)
+    fn = ref.transport.Sampler(transport).sample_ode(sampling_method=method, num_steps=num_steps)
+
+    @torch.no_grad()
+    def step(z0, labels, guidance_weight, genes, log_size_factors):
+        model_fn = lambda x, t, **kw: dit.forward_with_cfg(x, t, **kw, cfg_scale=guidance_weight)  # noqa: E731
+        z = fn(torch.cat([z0, z0]), model_fn, condition={k: torch.cat([v, v]) for k, v in labels.items()})[-1]
+        lib = torch.exp(log_size_factors).view(-1, 1)
+        nb = vae.decode(z, torch.cat([genes, genes]), torch.cat([lib, lib]))
+        return nb.sample(), z
+
+    return step

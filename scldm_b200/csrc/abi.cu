@@ -349,9 +349,16 @@ int launch_cls(const scldm_dit_weights* w, const scldm_dit_plan* plan, const Dit
   return SCLDM_OK;
 }
 
+// cudaFuncSetAttribute and the SM count are per DEVICE: prepared once for every device a call is made on (the caller makes the
+// tensors' device current, ops.py::_on_arg_device)
+constexpr int MAX_DEVICES = 64;
+int g_sms_of[MAX_DEVICES];
 int prepare_kernels() {
-  static std::atomic<int> done{0};
-  if (done.load()) return SCLDM_OK;
+  static std::atomic<int> done[MAX_DEVICES];
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(SCLDM_EINVAL, "device index %d out of range", dev);
+  if (done[dev].load()) { g_num_sms = g_sms_of[dev]; return SCLDM_OK; }
   int rc;
   if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV>, dit::ares_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU>, dit::ares_smem_bytes()))) return rc;
@@ -362,13 +369,13 @@ int prepare_kernels() {
   if ((rc = set_smem(dit::dit_blocks_kernel<false>, dit::phase_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::dit_blocks_kernel<true>, dit::phase_smem_bytes()))) return rc;
   {
-    int dev = 0, n = 0;
-    CUDA_OK(cudaGetDevice(&dev));
+    int n = 0;
     CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    if (n > 0) g_num_sms = n;
+    g_sms_of[dev] = n > 0 ? n : 148;
+    g_num_sms = g_sms_of[dev];
   }
   if ((rc = set_smem(vae::mcab_decode_kernel, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float)))) return rc;
-  done.store(1);
+  done[dev].store(1);
   return SCLDM_OK;
 }
 

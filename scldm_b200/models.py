@@ -157,8 +157,9 @@ class LatentDiffusion(nn.Module):
                                                       atol=self.atol, rtol=self.rtol)
         model_fn = FusedCFGModel(dit, guidance_weight)
         cond = {k: v.to(dev) for k, v in (condition or {}).items()}
-        gvec = genes[0] if genes.dim() == 2 else genes
-        gvec = gvec.to(dev).contiguous()
+        from .vae import shared_gene_vector
+
+        gvec = shared_gene_vector(genes).to(device=dev, dtype=torch.int64).contiguous()   # one row; differing rows are rejected loudly
         lib = torch.exp(lsf)
         G = gvec.numel()
         counts = torch.empty(2 * batch_size, G, dtype=torch.float32, device=dev)

@@ -4,6 +4,7 @@ current stream; all arithmetic happens in libscldm_b200.so.  No CPU path exists.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import torch
 
@@ -20,6 +21,37 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
 
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def _cuda_device_of(a):
+    if isinstance(a, torch.Tensor):
+        return a.device if a.is_cuda else None
+    d = getattr(a, "device", None)                       # PackedDiT / PackedVAE*
+    if d is None and hasattr(a, "packed"):
+        d = a.packed.device                              # DitPlan
+    if d is None and isinstance(a, (str, torch.device)):
+        try:
+            d = torch.device(a)
+        except (RuntimeError, TypeError):
+            return None
+    return d if isinstance(d, torch.device) and d.type == "cuda" else None
+
+
+def _on_arg_device(fn):
+    """Run the wrapped op with the CUDA device of its tensors / packed weights current: kernel launches, `cudaFuncSetAttribute` and
+    the SM count all belong to the CURRENT device, which need not be the tensors' device in a multi-GPU process.  Mixing devices in
+    one call is an error, not undefined behaviour."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        devs = [d for d in (_cuda_device_of(a) for a in list(args) + list(kw.values())) if d is not None]
+        devs = [d if d.index is not None else torch.device("cuda", torch.cuda.current_device()) for d in devs]
+        if not devs:
+            return fn(*args, **kw)
+        if any(d != devs[0] for d in devs):
+            raise RuntimeError(f"scldm_b200.{fn.__name__}: arguments live on different CUDA devices {sorted({str(d) for d in devs})}")
+        with torch.cuda.device(devs[0]):
+            return fn(*args, **kw)
+    return wrapper
 
 
 class DitPlan:
@@ -76,7 +108,8 @@ _ws_cache: dict = {}
 
 
 def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
-    key = (str(device), tag)
+    # one scratch buffer per (device, purpose, stream): calls on different streams must not share scratch memory
+    key = (str(device), tag, torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)  # zero-filled: padded slots stay finite
@@ -84,6 +117,7 @@ def _workspace(device, nbytes: int, tag: str) -> torch.Tensor:
     return buf
 
 
+@_on_arg_device
 def dit_forward(plan: DitPlan, x: torch.Tensor, t_mod: torch.Tensor, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """v = combine(DiT(x, t, cond)) for the states of `plan`.  x [n_states,16,16] fp32, t_mod [n_mod] fp32."""
     lib = _lib.load()
@@ -99,6 +133,7 @@ def dit_forward(plan: DitPlan, x: torch.Tensor, t_mod: torch.Tensor, workspace: 
     return v
 
 
+@_on_arg_device
 def dit_forward_shared_t(plan: DitPlan, x: torch.Tensor, t: float, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """`dit_forward` when every conditioning row shares the scalar time `t` (an ODE drift evaluation): one timestep-embedding
     row, no per-row time vector."""
@@ -113,6 +148,7 @@ def dit_forward_shared_t(plan: DitPlan, x: torch.Tensor, t: float, workspace: to
     return v
 
 
+@_on_arg_device
 def dit_sample_ode(plan: DitPlan, x: torch.Tensor, t_grid: torch.Tensor, method: str = "euler",
                    workspace: torch.Tensor | None = None) -> torch.Tensor:
     """Integrates x (in place) over the fixed time grid; returns x."""
@@ -158,6 +194,7 @@ def dit_workspace_views(plan: DitPlan, ws: torch.Tensor, n_evals: int = 0) -> di
     }
 
 
+@_on_arg_device
 def vae_qside(packed: PackedVAEDecoder):
     """Cell-invariant MCAB query projections for the whole vocabulary, fp32 and bf16 (cached on `packed`)."""
     if packed.qp is None:
@@ -170,6 +207,7 @@ def vae_qside(packed: PackedVAEDecoder):
     return packed.qp, packed.qp_bf16
 
 
+@_on_arg_device
 def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, lib_size: torch.Tensor, want_mu=True,
                want_counts=False, seed: int = 0, cell_offset: int = 0, out_mu: torch.Tensor | None = None,
                out_counts: torch.Tensor | None = None, precision: str = "bf16"):
@@ -200,6 +238,7 @@ def vae_decode(packed: PackedVAEDecoder, z: torch.Tensor, genes: torch.Tensor, l
     return mu, theta, counts
 
 
+@_on_arg_device
 def vae_encode(packed: PackedVAEEncoder, genes_subset: torch.Tensor, counts_subset: torch.Tensor) -> torch.Tensor:
     """genes_subset [cells,S] int64, counts_subset [cells,S] float -> z [cells,16,16] fp32."""
     lib = _lib.load()
@@ -215,6 +254,7 @@ def vae_encode(packed: PackedVAEEncoder, genes_subset: torch.Tensor, counts_subs
     return z
 
 
+@_on_arg_device
 def randn_cells(n_cells: int, per_cell: int, seed: int, cell_offset: int, stream_id: int, device) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(n_cells, per_cell, dtype=torch.float32, device=device)
@@ -223,6 +263,7 @@ def randn_cells(n_cells: int, per_cell: int, seed: int, cell_offset: int, stream
     return out
 
 
+@_on_arg_device
 def counts_to_csr(counts: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Dense (rows, G) fp32 counts -> the arrays of `scipy.sparse.csr_matrix(counts)` built on the device:
     `indptr` int64 [rows+1], `indices` int32 [nnz] (ascending within a row), `data` fp32 [nnz].  The reference builds
@@ -244,6 +285,7 @@ def counts_to_csr(counts: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, tor
     return indptr, indices, data
 
 
+@_on_arg_device
 def nb_nll(counts: torch.Tensor, mu: torch.Tensor, theta: torch.Tensor) -> torch.Tensor:
     """Per-cell NB reconstruction loss `(-log_nb_positive(counts, mu, theta)).sum(dim=1)` (`distributions.py:6-42`,
     `models.py:233-247`): counts / mu (N, G) fp32, theta (N, G) or a shared (G,) row -> (N,) fp32."""
@@ -265,6 +307,7 @@ def nb_nll(counts: torch.Tensor, mu: torch.Tensor, theta: torch.Tensor) -> torch
     return out
 
 
+@_on_arg_device
 def tokenize_expressed(counts: torch.Tensor, gene_ids: torch.Tensor, genes_seq_len: int, mask_idx: int = 0) -> dict[str, torch.Tensor]:
     """`tokenize_cells(..., sample_genes="expressed")` (`datamodule.py:708-731`) on the device: dense (N, G) counts and the
     (G,) gene-token row -> `genes_subset` int64 / `counts_subset` fp32 (N, genes_seq_len) with the expressed genes packed

@@ -23,6 +23,10 @@ class NegativeBinomialTransformerLayer(nn.Module):
             self.theta = None
             self.params = nn.Linear(n_embed, 2, bias=True)
         self.eps_ = eps_
+        if t != 1.0:
+            # the reference computes softmax(logit / t) (`stochastic_layers.py:86,115`); the fused head has no temperature input and
+            # every shipped config uses the default - refuse rather than return wrong means
+            raise NotImplementedError("NegativeBinomialTransformerLayer: softmax temperature t != 1.0 is not implemented in the fused NB head")
         self.t = t
 
     def forward(self, counts, genes, library_size):
@@ -47,6 +51,9 @@ class NegativeBinomial:
         return self.mu + self.mu**2 / self.theta
 
     def sample(self, sample_shape=torch.Size()):
+        """One draw per (cell, gene); every call uses fresh Philox counters (as scvi's sampler uses fresh randomness)."""
         if self._sampler is None:
             raise RuntimeError("this NegativeBinomial was not produced by TransformerVAE.decode")
+        if len(tuple(sample_shape)) != 0:
+            raise NotImplementedError("NegativeBinomial.sample: only sample_shape=() (one draw per entry) is implemented")
         return self._sampler()

@@ -10,6 +10,8 @@ Only function evaluations run on the GPU (the CUDA DiT); the controller is host 
 
 from __future__ import annotations
 
+import math
+
 import torch
 
 # Dormand-Prince tableau
@@ -95,6 +97,12 @@ def dopri5(f, y0: torch.Tensor, t_eval, rtol: float = 1e-5, atol: float = 1e-5, 
                 ymid = ymid + (dt * cm) * kj
         tol = atol + rtol * torch.maximum(y.abs(), y1.abs())
         ratio = _rms(err / tol)
+        if not math.isfinite(ratio):
+            # a NaN / Inf drift would be "rejected" for ever while min(10, max(nan, 0.2)) keeps GROWING the step: fail loudly instead
+            # (torchdiffeq asserts on the same condition)
+            raise RuntimeError(f"dopri5: non-finite error estimate at t = {t} (dt = {dt}): the model returned NaN or Inf")
+        if t + dt == t:
+            raise RuntimeError(f"dopri5: step size underflow at t = {t} (dt = {dt})")
         accept = ratio <= 1.0
         if accept:
             prev = (t, t + dt, y, y1, ymid, f0, k[-1])

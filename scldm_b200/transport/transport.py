@@ -115,7 +115,10 @@ class Sampler:
     def __init__(self, transport: Transport):
         self.transport = transport
 
-    def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-5, rtol=1e-5, reverse=False):
+    def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-5, rtol=1e-5, reverse=False, return_trajectory=False):
+        """`return_trajectory=True` returns all `num_steps` states `(T, ...)` like the reference (`integrators.py:100-112` stacks
+        every grid point); the default keeps only the end points `(2, ...)`, because `LatentDiffusion.sample` reads `[-1]` alone
+        (`models.py:812`) and the whole solve then runs in ONE C-ABI call."""
         if reverse:
             raise NotImplementedError("reverse-time ODE is outside the generation path")
         method = sampling_method.lower()
@@ -124,9 +127,20 @@ class Sampler:
         t0, t1 = self.transport.check_interval(self.transport.train_eps, self.transport.sample_eps, sde=False, eval=True)
         grid = torch.linspace(t0, t1, num_steps)  # `ode.__init__`, integrators.py:95
 
+        def solve_fixed(plan, x0):
+            if not return_trajectory:
+                return torch.stack([x0, ops.dit_sample_ode(plan, x0.clone(), grid, method)])
+            # one C-ABI call per grid interval (same kernels and fp32 step sizes; each call starts from the fp32 input projection)
+            states, xk = [x0], x0.clone()
+            for k in range(num_steps - 1):
+                xk = ops.dit_sample_ode(plan, xk, grid[k:k + 2], method)
+                states.append(xk.clone())
+            return torch.stack(states)
+
         def sample(x, model, **model_kwargs):
-            """Returns the trajectory end points stacked as (2, ...): [x(t0), x(t1)] (the reference returns all
-            `num_steps` states but `LatentDiffusion.sample` only reads `[-1]`, `models.py:812`)."""
+            """Returns the trajectory end points stacked as (2, ...): [x(t0), x(t1)], or all `num_steps` states with
+            `return_trajectory=True` (the reference returns all of them but `LatentDiffusion.sample` only reads `[-1]`,
+            `models.py:812`)."""
             x0 = x.contiguous().float()
             if method in self.ADAPTIVE:
                 return self._sample_adaptive(x0, model, grid, atol, rtol, **model_kwargs)
@@ -135,15 +149,14 @@ class Sampler:
                 plan = model_kwargs.get("_plan")   # prebuilt by LatentDiffusion.sample (plan building synchronises with the device)
                 if plan is None:
                     plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, half, x0.device, shared_time=True)
-                xf = ops.dit_sample_ode(plan, x0.clone(), grid, method)
-                return torch.stack([x0, xf])
+                return solve_fixed(plan, x0)
             if isinstance(model, FusedForwardModel):
                 plan = model.dit.forward_plan(model_kwargs.get("condition"), x0.shape[0], x0.device)
                 if plan is not None:
-                    xf = ops.dit_sample_ode(plan, x0.clone(), grid, method)
-                    return torch.stack([x0, xf])
+                    return solve_fixed(plan, x0)
             # generic callable: host-driven loop with the same fixed-grid formulas (slow path, still CUDA model calls)
             xk = x0
+            states = [x0]
             for k in range(num_steps - 1):
                 ta, tb = grid[k].item(), grid[k + 1].item()
                 dt = torch.tensor(tb, dtype=torch.float32) - torch.tensor(ta, dtype=torch.float32)
@@ -156,7 +169,8 @@ class Sampler:
                     xk = xk + dt * 0.5 * (k1 + model(xk + dt * k1, tv(tb), **model_kwargs))
                 else:
                     xk = xk + dt * model(xk + 0.5 * dt * k1, tv(ta + 0.5 * dt), **model_kwargs)
-            return torch.stack([x0, xk])
+                states.append(xk)
+            return torch.stack(states if return_trajectory else [x0, xk])
 
         return sample
 

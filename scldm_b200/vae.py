@@ -76,10 +76,14 @@ class TransformerVAE(nn.Module):
         prec = self.decode_precision
         mu, theta, _ = ops.vae_decode(packed, zc, gvec, library_size, want_mu=True, want_counts=False, precision=prec)
         theta_full = theta.unsqueeze(0).expand(z.shape[0], -1) if theta.dim() == 1 else theta
-        seed, offset = self.sample_seed, self.sample_offset
+        n_cells = z.shape[0]
 
         def sampler():
-            _, _, counts = ops.vae_decode(packed, zc, gvec, library_size, want_mu=False, want_counts=True, seed=seed,
+            # Philox streams are keyed by (sample_seed, cell offset): every `.sample()` call - of this or of any other `decode()` -
+            # takes the next `n_cells` offsets, so repeated draws are independent; set `vae.sample_seed` / `vae.sample_offset` to replay
+            offset = self.sample_offset
+            self.sample_offset = offset + n_cells
+            _, _, counts = ops.vae_decode(packed, zc, gvec, library_size, want_mu=False, want_counts=True, seed=self.sample_seed,
                                           cell_offset=offset, precision=prec)
             return counts
 

@@ -4,7 +4,8 @@
 library sizes.  Small batches / few ODE steps keep the CPU oracle at seconds; the kernels and code paths are those of
 the full-size run (vocabulary-sized tables, joint vs mutually-exclusive conditioning, G-sized softmax).
 
-Tolerances: latents rel-L2 <= 3e-2 (bf16 tensor-core DiT, fp32 residual stream), NB mean rel-L2 <= 6e-2 on the bf16 decode path,
+Tolerances (<= ~3x the errors measured on B200: latents 2.3e-3, NB means 3.3e-3): latents rel-L2 <= 5e-3 (bf16 tensor-core DiT, fp32 residual
+stream), NB mean rel-L2 <= 1e-2 on the bf16 decode path,
 |sum_g mu - library| / library <= 1e-4 (fp32 softmax over genes)."""
 
 import pytest
@@ -52,7 +53,7 @@ def test_sample_matches_oracle_at_dataset_shape(dataset):
     e_z, e_mu = rel_l2(z, z_o), rel_l2(mu, mu_o)
     print(f"{dataset}: G={vcfg.n_genes} classes={dcfg.class_vocab_sizes} {dcfg.condition_strategy}: z {e_z:.2e} mu {e_mu:.2e}")
     assert counts.shape == (2 * B, vcfg.n_genes) and bool(torch.isfinite(counts).all()) and bool((counts >= 0).all())
-    assert e_z < 3e-2 and e_mu < 6e-2, (e_z, e_mu)
+    assert e_z < 5e-3 and e_mu < 1e-2, (e_z, e_mu)
     lib = torch.exp(lsf)
     assert torch.allclose(mu.sum(1).cpu(), torch.cat([lib, lib]), rtol=1e-4)
 
@@ -75,7 +76,7 @@ def test_census_vocabulary_decode_and_encode_match_oracle():
         mu_o, th_o = O.vae_decode(z, genes, lib, vsd, vcfg)
     e_mu, e_th = rel_l2(dist.mu, mu_o), rel_l2(dist.theta, th_o)
     print(f"census decode: mu {e_mu:.2e} theta {e_th:.2e}")
-    assert e_mu < 2e-2 and e_th < 1e-5
+    assert e_mu < 1e-2 and e_th < 1e-5, (e_mu, e_th)
     assert torch.allclose(dist.mu.sum(1).cpu(), lib.reshape(-1), rtol=1e-4)
     # encode: S = 8000 tokens per cell, ragged numbers of expressed genes, mask-padded (gene 0 / count 0) as the tokenizer does
     gs = torch.zeros(B, S, dtype=torch.int64)
@@ -90,7 +91,7 @@ def test_census_vocabulary_decode_and_encode_match_oracle():
         z_o = O.vae_encode(cs, gs, vsd, vcfg)
     e = rel_l2(z_enc, z_o)
     print(f"census encode: z {e:.2e}")
-    assert z_enc.shape == (B, 16, 16) and e < 2e-2   # tensor-core pooling with bf16 operands; z is LayerNorm-ed (unit variance)
+    assert z_enc.shape == (B, 16, 16) and e < 1e-2, e   # tensor-core pooling with bf16 operands; z is LayerNorm-ed (unit variance)
 
 
 def test_baseline_config0_plain_sampling_no_cfg():
@@ -125,5 +126,5 @@ def test_baseline_config0_plain_sampling_no_cfg():
         mu_o, _ = O.vae_decode(z_o, genes, lib, vsd, vcfg)
     e_z, e_l, e_mu = rel_l2(z_fused, z_o), rel_l2(z_loop, z_fused), rel_l2(mu, mu_o)
     print(f"configs[0]: z fused-vs-oracle {e_z:.2e}, host-loop-vs-fused {e_l:.2e}, mu {e_mu:.2e}")
-    assert e_z < 3e-2 and e_l < 5e-3 and e_mu < 6e-2   # the two loops differ in how the next input projection is evaluated (fp32 kernel vs hi/lo bf16 tensor-core form)
+    assert e_z < 5e-3 and e_l < 5e-3 and e_mu < 1e-2, (e_z, e_l, e_mu)   # the two loops differ in how the next input projection is evaluated (fp32 kernel vs hi/lo bf16 tensor-core form)
     assert torch.allclose(mu.sum(1).cpu(), lib.reshape(-1), rtol=1e-4)

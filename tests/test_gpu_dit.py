@@ -2,8 +2,8 @@
 
 Tolerances (stated per SURVEY.md §7): the GEMMs take bf16 operands with fp32 accumulation, the
 residual stream / LayerNorm statistics / softmax are fp32:
-  * single DiT forward: rel-L2 <= 1e-2 vs the fp32 reference
-  * 49-step trajectory end point: rel-L2 <= 3e-2 (error compounds through the loop)
+  * single DiT forward: rel-L2 <= 5e-3 vs the fp32 reference (measured 1.6e-3)
+  * 49-step trajectory end point: rel-L2 <= 4e-3 (measured 1.1e-3; the velocity errors largely average out along the path)
 """
 
 import os
@@ -20,8 +20,8 @@ from scldm_b200.config import DiTConfig
 
 pytestmark = pytest.mark.gpu
 
-TOL_FWD = 1e-2
-TOL_TRAJ = 3e-2
+TOL_FWD = 5e-3
+TOL_TRAJ = 4e-3
 
 
 def rel_l2(a, b):
@@ -121,7 +121,7 @@ def test_forward_and_cfg_vs_golden(golden_dir, name):
         out_none = dit.forward_with_cfg(xc, tc, None, None)
         e_none = rel_l2(out_none, g["out_cfg_none"])
     print(name, f"forward {e_fwd:.2e} cfg {e_cfg:.2e} cfg_none {e_none:.2e}")
-    assert e_fwd < TOL_FWD and e_cfg < 2 * TOL_FWD and e_none < TOL_FWD
+    assert e_fwd < TOL_FWD and e_cfg < 2 * TOL_FWD and e_none < TOL_FWD, (e_fwd, e_cfg, e_none)
 
 
 @pytest.mark.parametrize("method,steps,w", [("euler", 50, 2.0), ("euler", 50, 1.0), ("heun2", 10, 2.0), ("midpoint", 10, 2.0)])
@@ -143,7 +143,36 @@ def test_sample_ode_vs_golden(golden_dir, method, steps, w):
                condition={"clusters": torch.cat([lab, lab])})
     e2 = rel_l2(traj2[-1], traj[-1])
     print(method, steps, w, f"vs golden {e:.2e}; host-loop vs fused {e2:.2e}")
-    assert e < TOL_TRAJ and e2 < TOL_TRAJ
+    assert e < TOL_TRAJ and e2 < TOL_TRAJ, (e, e2)
+
+
+def test_sample_ode_can_return_every_state_like_the_reference(golden_dir):
+    """`return_trajectory=True`: (T, ...) states as the reference's `ode.sample` stacks them; the last one agrees with the one-call
+    solve and every state matches the oracle's trajectory."""
+    from scldm_b200.transport import Sampler, create_transport
+    from scldm_b200.transport.transport import FusedCFGModel
+
+    g = load(golden_dir, "ode_me1")
+    cfg = golden_cases()["dit_me1"]["cfg"]
+    dit, sd = make_dit(cfg)
+    z0 = torch.from_numpy(g["z0"]).cuda()
+    lab = torch.from_numpy(g["label"]).cuda()
+    sampler = Sampler(create_transport("Linear", "velocity"))
+    kw = dict(condition={"clusters": torch.cat([lab, lab])})
+    model = FusedCFGModel(dit, {"clusters": 2.0})
+    full = sampler.sample_ode(sampling_method="heun2", num_steps=10, return_trajectory=True)(torch.cat([z0, z0]), model, **kw)
+    ends = sampler.sample_ode(sampling_method="heun2", num_steps=10)(torch.cat([z0, z0]), model, **kw)
+    assert full.shape == (10, 4, 16, 16) and ends.shape == (2, 4, 16, 16)
+    # not bit-identical to the one-call solve: a call starts with the fp32 input projection, inside a solve the next projection is
+    # evaluated by the fused final-step kernel in its hi/lo bf16 tensor-core form
+    assert torch.equal(full[0], ends[0]) and rel_l2(full[-1], ends[-1]) < TOL_TRAJ, rel_l2(full[-1], ends[-1])
+    assert rel_l2(full[-1], g["z_heun2_10_w2.0"]) < TOL_TRAJ
+    labs = {"clusters": torch.cat([lab, lab]).cpu()}
+    with torch.no_grad():
+        ref = O.sample_ode(torch.cat([z0, z0]).cpu(), lambda x, t: O.dit_forward_with_cfg(x, t, labs, {"clusters": 2.0}, sd, cfg), num_steps=10, method="heun2")
+    assert ref.shape == full.shape
+    for k in range(10):
+        assert rel_l2(full[k], ref[k]) < TOL_TRAJ, k
 
 
 def test_batch_invariance_and_padding():
@@ -188,7 +217,7 @@ def test_fm_training_losses_vs_golden(golden_dir):
                                t=torch.from_numpy(g["t"]).cuda(), x0=torch.from_numpy(g["x0"]).cuda())
     e_pred, e_loss = rel_l2(terms["pred"], g["pred"]), rel_l2(terms["loss"], g["loss"])
     print(f"fm loss: pred {e_pred:.2e} loss {e_loss:.2e}")
-    assert e_pred < TOL_FWD and e_loss < 5e-3
+    assert e_pred < TOL_FWD and e_loss < 5e-3, (e_pred, e_loss)
     # RNG path (no injection): shapes and finiteness; t drawn on the CPU as the reference does
     terms2 = tr.training_losses(dit, torch.from_numpy(g["x1"]).cuda(), {"condition": {"clusters": torch.from_numpy(g["label"]).cuda()}})
     assert terms2["loss"].shape == (6,) and bool(torch.isfinite(terms2["loss"]).all())

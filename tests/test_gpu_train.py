@@ -265,8 +265,9 @@ def test_training_step_vs_reference_minted_golden(golden_dir):
         ref = torch.from_numpy(g["new." + n]).cuda()
         w, w0 = params[n].detach(), old[n]
         mine, before = (w, w0) if ref.shape == tuple(w.shape) else (w.reshape(-1)[::97], w0.reshape(-1)[::97])
-        # compare the UPDATE (new - old, ~lr per element) where the gradient is not rounding noise
+        # compare the UPDATE (new - old).  The first Adam step is lr * g / (|g| + eps) ~ lr * sign(g): it only pins the SIGN of a
+        # gradient, so restrict to elements whose sign the bf16 GEMMs cannot flip (|g| above 5 % of the tensor's largest)
         gref = torch.from_numpy(g["grad." + n]).cuda()
-        big = gref.abs() > 1e-4 * gref.abs().max()
+        big = gref.abs() > 5e-2 * gref.abs().max()
         du, dr = (mine - before)[big], (ref - before)[big]
         assert float((du - dr).norm() / dr.norm()) < 5e-2, n

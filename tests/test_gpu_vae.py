@@ -3,7 +3,7 @@
 Two MCAB variants share every other kernel:
   precision="fp32": CUDA-core fp32 throughout      -> mu rel-L2 <= 1e-4
   precision="bf16": tensor cores (mma.sync), bf16 operands / fp32 accumulate / fp32 residual (default)
-                                                    -> mu rel-L2 <= 2e-2 (SURVEY.md section 7 starting tolerance)
+                                                    -> mu rel-L2 <= 1e-2 (measured 2.8e-3)
 Both: |sum_g mu - library| / library <= 1e-4; theta (fp32 exp of a table) rel <= 1e-5.
 Sampled counts: distributional agreement only (moments within Monte-Carlo error)."""
 
@@ -26,7 +26,7 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-MU_TOL = {"fp32": 1e-4, "bf16": 2e-2}
+MU_TOL = {"fp32": 1e-4, "bf16": 1e-2}   # measured on B200: 8e-7 / 2.8e-3
 
 
 def make_vae(cfg, precision="bf16"):
@@ -52,7 +52,7 @@ def test_decode_vs_golden(golden_dir, name, G, B, S, precision):
     big = torch.from_numpy(g["mu"]) >= 1e-3 * float(g["mu"].max())
     e_rel = float(((nb.mu.cpu() - torch.from_numpy(g["mu"])).abs() / torch.from_numpy(g["mu"]))[big].max())
     print(name, precision, f"mu rel-L2 {e_mu:.2e} max-rel(big) {e_rel:.2e} theta {e_th:.2e} |sum/lib-1| {tot:.2e}")
-    assert e_mu < MU_TOL[precision] and e_th < 1e-5 and tot < 1e-4
+    assert e_mu < MU_TOL[precision] and e_th < 1e-5 and tot < 1e-4, (e_mu, e_th, tot)
     assert e_rel < 5 * MU_TOL[precision]
     assert nb.mu.shape == (B, G) and nb.theta.shape == (B, G)
 
@@ -147,7 +147,7 @@ def test_full_sample_vs_golden(golden_dir):
                                return_mu=True)
     e_z, e_mu = rel_l2(z, g["z_final"]), rel_l2(mu, g["mu"])
     print(f"sample: z {e_z:.2e} mu {e_mu:.2e}")
-    assert e_z < 3e-2 and e_mu < 6e-2
+    assert e_z < 5e-3 and e_mu < 1e-2, (e_z, e_mu)
     assert counts.shape == (2 * B, vcfg.n_genes) and z.shape == (2 * B, 16, 16)
     lib = torch.exp(torch.from_numpy(g["log_size_factors"]))
     assert torch.allclose(mu.sum(1).cpu(), torch.cat([lib, lib]), rtol=1e-4)
@@ -228,7 +228,7 @@ def test_encode_vs_golden(golden_dir, name, G, B, S):
     z = vae.encode(None, None, cs.cuda(), gs.cuda())
     e = rel_l2(z, g["z_enc"])
     print(name, f"encode z rel-L2 {e:.2e}")
-    assert z.shape == (B, 16, 16) and e < 2e-2
+    assert z.shape == (B, 16, 16) and e < 1e-2, e
 
 
 def test_encode_ragged_lengths_vs_oracle():
@@ -244,7 +244,7 @@ def test_encode_ragged_lengths_vs_oracle():
             zo = O.vae_encode(cs, gs, sd, cfg)
         e = rel_l2(z, zo)
         print("encode", S, B, f"{e:.2e}")
-        assert e < 2e-2
+        assert e < 1e-2, e
 
 
 def test_joint_size_factors_match_oracle():
@@ -412,7 +412,7 @@ def test_nb_nll_and_vae_forward_vs_golden(golden_dir):
     e_mu, e_z = rel_l2(params["mu"], g["mu"]), rel_l2(h_z, g["h_z"])
     e_l = abs(float(loss["llh"]) - float(g["llh"])) / abs(float(g["llh"]))
     print(f"vae forward: mu {e_mu:.2e} h_z {e_z:.2e} llh rel {e_l:.2e}")
-    assert e_mu < 3e-2 and e_z < 2e-2 and e_l < 1e-3
+    assert e_mu < 1.5e-2 and e_z < 1e-2 and e_l < 1e-3, (e_mu, e_z, e_l)
     with pytest.raises(RuntimeError):
         ops.nb_nll(counts.cpu(), mu.cpu(), theta.cpu())            # no CPU fallback
 
@@ -491,6 +491,22 @@ def test_full_size_generation_properties():
     ldm.cell_chunk = 592
     _, z2 = ldm.sample(lab, {"clusters": 2.0}, B, genes)
     assert torch.equal(z2, z)
+    # 16 random cells (32 of the 4736 rows: unconditional + guided twins) against the fp32 oracle on the CPU, from the same noise and
+    # size factors (re-derived from the Philox streams the call used)
+    from scldm_b200 import ops
+    from scldm_b200.models import STREAM_NOISE
+
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(9))[:16]
+    z0 = ops.randn_cells(B, 256, ldm.seed, 0, STREAM_NOISE, torch.device("cuda")).view(B, 16, 16)[idx.cuda()].cpu()
+    lsf = ldm._sample_log_size_factors(lab, B, 0)[idx.cuda()].cpu()
+    dsd, vsd = synthetic.dit_state_dict(dcfg, 1234), synthetic.vae_state_dict(vcfg, 1234)
+    with torch.no_grad():
+        mu_o, _, z_o = O.latent_diffusion_sample(z0, {"clusters": lab["clusters"][idx.cuda()].cpu()}, {"clusters": 2.0}, genes[:16].cpu(), lsf, dsd, dcfg, vsd, vcfg,
+                                                 num_steps=50)
+    rows = torch.cat([idx, B + idx]).cuda()
+    e_z, e_mu = rel_l2(z[rows], z_o), rel_l2(mu[rows], mu_o)
+    print(f"full size, 32 sampled rows vs oracle: z {e_z:.2e}, mu {e_mu:.2e}")
+    assert e_z < 5e-3 and e_mu < 1e-2, (e_z, e_mu)
 
 
 def test_default_solver_is_the_references_dopri5():
@@ -549,6 +565,6 @@ def test_unconditional_sample_without_labels():
     assert torch.allclose(mu.sum(1), torch.ones(2 * B, device="cuda"), rtol=1e-4)      # exp(0) library size
     with torch.no_grad():
         z_o = O.sample_ode(torch.cat([z0, z0]), lambda x, t: O.dit_forward_with_cfg(x, t, None, None, dsd, dcfg), num_steps=6, method="euler")[-1]
-    assert rel_l2(z, z_o) < 3e-2
+    assert rel_l2(z, z_o) < 5e-3, rel_l2(z, z_o)
     with pytest.raises(ValueError):
         ldm.sample(None, None, B, genes[:2])                                           # genes batch dimension must match (models.py:777)
