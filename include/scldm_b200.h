@@ -297,6 +297,58 @@ int scldm_test_gemm(int32_t mode, const float* a_f32, const float* dy_f32, const
 /* unit-test probe of the small-mean NB sampler: k[i] = inverse CDF of NB(mu[i], theta[i]) at u[i] */
 int scldm_test_nb_invert(const float* u, const float* mu, const float* theta, float* k, int32_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Census-scale VAE, n_embed = 256 (8 self-attention heads x 32, 4 cross heads x 64, SwiGLU hidden 684; bias = False,
+ * use_adaln = False, shared theta): the same reference entry points as scldm_vae_decode / scldm_vae_encode
+ * (TransformerVAE.decode, src/scldm/vae.py:71-87; .encode, vae.py:58-69; CrossAttentionBlock, layers.py:267-330) with every
+ * MCAB contraction on tcgen05 (rows = gene tokens / count tokens) and the latent Blocks on the DiT block-stack kernel.
+ * One struct describes either side (decoder: decoder.* / decoder_head.*, encoder: encoder.*); unused members are NULL.
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct scldm_vae256_weights {
+  int32_t n_layer;            /* latent Blocks                                                                       */
+  int32_t n_ids;              /* rows of the gene-embedding table (n_genes + 1)                                        */
+  int32_t mlp_tiles;          /* T = ceil(hidden / 128)                                                                */
+  int32_t has_pos;            /* encoder: add pos_embed after the MCAB                                                 */
+  float eps;
+  float head_b;               /* decoder_head.params.bias                                                              */
+  const float* emb;           /* input_layer.gene_embedding.weight [n_ids][256]                                        */
+  scldm_dit_weights blocks;   /* the latent Blocks packed like DiT blocks (w_attn_stream, w_mlp_stream, zero biases)    */
+  const float* blocks_mod;    /* [n_layer*1536 + 512]: per Block (ln_1.weight - 1 | ln_1.bias | 1 | ln_2.weight - 1 | ln_2.bias | 1) */
+  const float* ln1_mod;       /* MCAB ln_1 as a modulation row [512]: (weight - 1 | bias)                               */
+  const void* w_kv;           /* MCAB attn.c_attn.weight  (k | v)  bf16 tiles [2][4][256 x 64]                          */
+  const float* ln1q_w;        /* decoder: ln_1q.weight / bias [256] (Q side, per vocabulary)                            */
+  const float* ln1q_b;
+  const void* w_q;            /* decoder: attn.c_attn_q.weight tiles [1][4]                                             */
+  const void* w_proj;         /* MCAB attn.c_proj.weight tiles [1][4]                                                   */
+  const float* ln2_w;         /* MCAB ln_2 [256]                                                                        */
+  const float* ln2_b;
+  const float* ln2_mod;       /* encoder: ln_2 as a modulation row [512]                                                */
+  const void* w_12;           /* MCAB mlp [w1 | w2] tiles [T][4] (tile j rows 0-127 = w1[128j..], 128-255 = w2[128j..])  */
+  const void* w_3;            /* encoder: mlp.c_proj tiles [1][2T]                                                      */
+  const float* lat_w;         /* decoder_latent_input.1.weight [256][16]                                                */
+  const float* head_w;        /* decoder_head.params.weight [256]                                                       */
+  const float* head_v;        /* [128 T] = mlp.c_proj.weight^T head_w: the NB-head Linear folded through the last MLP projection */
+  const float* theta_tbl;     /* decoder_head.theta.weight [n_ids]                                                      */
+  const float* q_tbl;         /* encoder: c_attn_q(ln_1q(inducing_points)) [16][256]                                    */
+  const float* inducing;      /* encoder: ca_layer.inducing_points [16][256]                                            */
+  const float* pos;           /* encoder: pos_embed [16][256]                                                           */
+  const float* ones;          /* [256] ones (unit gate of the MLP residual)                                             */
+  const float* out_w;         /* encoder_latent_input.0.weight [16][256]                                                */
+} scldm_vae256_weights;
+
+/* qp_bf16 [n_ids][256] = c_attn_q(ln_1q(emb)) for the whole vocabulary (cell invariant; cache it per vocabulary) */
+size_t scldm_vae256_qside_workspace_bytes(int32_t n_ids);
+int scldm_vae256_qside(const scldm_vae256_weights* w, void* qp_bf16, void* workspace, size_t workspace_bytes, void* stream);
+/* same contract as scldm_vae_decode (genes shared by all cells; mu / theta / counts nullable) */
+size_t scldm_vae256_decode_workspace_bytes(int32_t n_cells, int32_t n_genes);
+int scldm_vae256_decode(const scldm_vae256_weights* w, const void* qp_bf16, const float* z, int32_t n_cells, const int64_t* genes,
+                        int32_t n_genes, const float* lib, float* mu, float* theta, float* counts, uint64_t seed, int64_t cell_offset,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* same contract as scldm_vae_encode */
+size_t scldm_vae256_encode_workspace_bytes(int32_t n_cells, int32_t seq_len);
+int scldm_vae256_encode(const scldm_vae256_weights* w, const int64_t* genes_subset, const float* counts_subset, int32_t n_cells,
+                        int32_t seq_len, float* z, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Live per-kernel timing for bench.py: when enabled every launch is bracketed by CUDA events recorded on
  * `stream` (must be the stream the calls run on; disables CUDA-graph capturability while on).
  * scldm_prof_summary synchronises the device and writes "name count total_ms\n" lines.            */

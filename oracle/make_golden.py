@@ -291,8 +291,26 @@ def train_step_golden() -> None:
     print("train_step_me1 loss", float(loss), "total grad norm", float(total), "dropped", int(drop.sum()))
 
 
+@torch.no_grad()
+def vae256_golden() -> None:
+    """Census-scale VAE width (n_embed = 256: 8 heads, 4 cross heads, SwiGLU hidden 684) through the REFERENCE modules:
+    decode + encode at G = 1500 (B = 3, S = 400) and decode at the census vocabulary G = 36 130 (B = 1):
+    tests/golden/vae256_small.npz, vae256_census.npz."""
+    for name, G, B, S in (("vae256_small", 1500, 3, 400), ("vae256_census", 36130, 1, 0)):
+        vcfg = VAEConfig(n_genes=G, n_embed=256)
+        vsd = synthetic.vae_state_dict(vcfg, WEIGHT_SEED)
+        vae = ref_loader.build_reference_vae(vcfg, vsd)
+        z, genes, lib, cs, gs = vae_inputs(name, vcfg, B, max(S, 8))
+        nb = vae.decode(z, genes, lib)
+        arrays = dict(z=z.numpy(), lib=lib.numpy(), mu=nb.mu.numpy(), theta=nb.theta[0].numpy())
+        if S > 0:
+            arrays.update(counts_subset=cs.numpy(), genes_subset=gs.numpy(), z_enc=vae.encode(None, None, cs, gs).numpy())
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
+        print(name, {k: v.shape for k, v in arrays.items()}, "mu.sum/lib", (nb.mu.sum(1) / lib[:, 0]).tolist())
+
+
 if __name__ == "__main__":
-    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden}   # fixtures added after the first set; minted
+    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden, "vae256": vae256_golden}   # fixtures added after the first set; minted
     if len(sys.argv) > 1 and sys.argv[1] in later:                                 # alone so the others stay byte-identical
         later[sys.argv[1]]()
     else:

@@ -14,6 +14,7 @@
 #include "vae_kernels.cuh"
 #include "csr_kernels.cuh"
 #include "train_kernels.cuh"
+#include "vae256_kernels.cuh"
 
 namespace {
 
@@ -700,3 +701,4 @@ const char* scldm_version(void) { return "scldm_b200 0.1 (sm_100a)"; }
 }  // extern "C"
 
 #include "train_abi.inc"
+#include "vae256_abi.inc"

@@ -73,6 +73,11 @@ struct GemmParams {
   int valid_rows, valid_cols;
   const float* bias;              // [valid_cols] or nullptr (added by the blockIdx.z == 0 share only)
   int atomic;                     // 1: accumulate into `out` with vector atomics (split-K, gradient accumulation)
+  int n_loop;                     // > 1: the CTA walks n_loop consecutive N tiles (two TMEM accumulators: epilogue t overlaps MMAs t + 1)
+  int swap_xy;                    // 1: blockIdx.x walks the N tiles and blockIdx.y the M tiles (CTAs that share an A tile are scheduled together: L2 reuse)
+  int epi;                        // 0: fp32 store / atomic accumulate;  1: SwiGLU . v epilogue (no `out`):
+  const float* vdot;              //    the tile's columns are [w1 h (128) | w2 h (128)] of hidden units [128 n, 128 n + 128);
+  float* dot_out;                 //    dot_out[row] += sum_i silu(a_i) * b_i * vdot[128 n + i]   (atomic = 0 and n_loop = all tiles: one plain update per row)
 };
 
 constexpr int G_STAGE_BYTES = 48 * 1024;
@@ -99,10 +104,13 @@ __global__ void __launch_bounds__(dit::NUM_THREADS, 1) gemm_kernel(const GemmPar
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BARS);
   uint64_t* full = bars;
   uint64_t* empty = bars + G_NSTAGE;
-  uint64_t* tmem_full = bars + 2 * G_NSTAGE;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = bars + 2 * G_NSTAGE;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_loop = p.n_loop > 1 ? p.n_loop : 1;
+  const int bm = p.swap_xy ? blockIdx.y : blockIdx.x, bn0 = (p.swap_xy ? blockIdx.x : blockIdx.y) * n_loop;
   const int per = (p.n_steps + (int)gridDim.z - 1) / (int)gridDim.z;
   const int s0 = (int)blockIdx.z * per;
   const int s1 = min(p.n_steps, s0 + per);
@@ -112,10 +120,10 @@ __global__ void __launch_bounds__(dit::NUM_THREADS, 1) gemm_kernel(const GemmPar
   if (threadIdx.x == 0) {
     if (a_bytes + b_bytes > (uint32_t)G_STAGE_BYTES) __trap();
     for (int i = 0; i < G_NSTAGE; ++i) { sm100::mbar_init(&full[i], 1); sm100::mbar_init(&empty[i], 1); }
-    sm100::mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { sm100::mbar_init(&tmem_full[i], 1); sm100::mbar_init(&tmem_empty[i], dit::EPI_WARPS); }
     sm100::fence_barrier_init();
   }
-  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 256);
+  if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);   // two 256-column accumulators: the epilogue of N tile t overlaps the MMAs of tile t + 1
   sm100::grid_dep_launch();   // barrier init / TMEM allocation above overlap the tail of the preceding kernel (PDL)
   sm100::grid_dep_wait();
   sm100::tc_fence_before();
@@ -126,78 +134,120 @@ __global__ void __launch_bounds__(dit::NUM_THREADS, 1) gemm_kernel(const GemmPar
   if (warp == 0) {
     if (lane == 0) {
       dit::RingState rs;
-      const bf16* a0 = p.a.base + (long long)blockIdx.x * p.a.tile_stride;
-      const bf16* b0 = p.b.base + (long long)blockIdx.y * p.b.tile_stride;
-      for (int s = s0; s < s1; ++s) {
-        sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
-        sm100::mbar_arrive_expect_tx(&full[rs.stage], a_bytes + b_bytes);
-        uint8_t* st = smem + rs.stage * G_STAGE_BYTES;
-        const bf16* as = a0 + (long long)(s / p.a.step_div) * p.a.step_hi + (long long)(s % p.a.step_div) * p.a.step_lo;
-        for (int c = 0; c < p.a.n_copies; ++c) sm100::bulk_g2s(st + c * p.a.copy_bytes, as + c * p.a.copy_stride, p.a.copy_bytes, &full[rs.stage]);
-        const bf16* bs = b0 + (long long)(s / p.b.step_div) * p.b.step_hi + (long long)(s % p.b.step_div) * p.b.step_lo;
-        for (int c = 0; c < p.b.n_copies; ++c) sm100::bulk_g2s(st + a_bytes + c * p.b.copy_bytes, bs + c * p.b.copy_stride, p.b.copy_bytes, &full[rs.stage]);
-        rs.advance(G_NSTAGE);
+      const bf16* a0 = p.a.base + (long long)bm * p.a.tile_stride;
+      for (int t = 0; t < n_loop; ++t) {
+        const bf16* b0 = p.b.base + (long long)(bn0 + t) * p.b.tile_stride;
+        for (int s = s0; s < s1; ++s) {
+          sm100::mbar_wait(&empty[rs.stage], rs.phase ^ 1);
+          sm100::mbar_arrive_expect_tx(&full[rs.stage], a_bytes + b_bytes);
+          uint8_t* st = smem + rs.stage * G_STAGE_BYTES;
+          const bf16* as = a0 + (long long)(s / p.a.step_div) * p.a.step_hi + (long long)(s % p.a.step_div) * p.a.step_lo;
+          for (int c = 0; c < p.a.n_copies; ++c) sm100::bulk_g2s(st + c * p.a.copy_bytes, as + c * p.a.copy_stride, p.a.copy_bytes, &full[rs.stage]);
+          const bf16* bs = b0 + (long long)(s / p.b.step_div) * p.b.step_hi + (long long)(s % p.b.step_div) * p.b.step_lo;
+          for (int c = 0; c < p.b.n_copies; ++c) sm100::bulk_g2s(st + a_bytes + c * p.b.copy_bytes, bs + c * p.b.copy_stride, p.b.copy_bytes, &full[rs.stage]);
+          rs.advance(G_NSTAGE);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = sm100::make_idesc_bf16(128, 256) | ((uint32_t)(p.a.major & 1) << 15) | ((uint32_t)(p.b.major & 1) << 16);
       dit::RingState rs;
-      for (int s = s0; s < s1; ++s) {
-        sm100::mbar_wait(&full[rs.stage], rs.phase);
+      for (int t = 0; t < n_loop; ++t) {
+        const uint32_t acc = t & 1;
+        sm100::mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1);
         sm100::tc_fence_after();
-        const uint32_t st = sm100::smem_u32(smem + rs.stage * G_STAGE_BYTES);
-        const uint64_t ad = make_sw128_desc(st, p.a.lbo, p.a.sbo), bd = make_sw128_desc(st + a_bytes, p.b.lbo, p.b.sbo);
-        for (int k = 0; k < p.mmas_per_step; ++k)
-          sm100::umma_bf16_ss(tmem_base, ad + (uint64_t)((k * p.a.mma_adv) >> 4), bd + (uint64_t)((k * p.b.mma_adv) >> 4), idesc,
-                              (s == s0 && k == 0) ? 0u : 1u);
-        sm100::umma_commit(&empty[rs.stage]);
-        rs.advance(G_NSTAGE);
+        for (int s = s0; s < s1; ++s) {
+          sm100::mbar_wait(&full[rs.stage], rs.phase);
+          sm100::tc_fence_after();
+          const uint32_t st = sm100::smem_u32(smem + rs.stage * G_STAGE_BYTES);
+          const uint64_t ad = make_sw128_desc(st, p.a.lbo, p.a.sbo), bd = make_sw128_desc(st + a_bytes, p.b.lbo, p.b.sbo);
+          for (int k = 0; k < p.mmas_per_step; ++k)
+            sm100::umma_bf16_ss(tmem_base + acc * 256, ad + (uint64_t)((k * p.a.mma_adv) >> 4), bd + (uint64_t)((k * p.b.mma_adv) >> 4), idesc,
+                                (s == s0 && k == 0) ? 0u : 1u);
+          sm100::umma_commit(&empty[rs.stage]);
+          rs.advance(G_NSTAGE);
+        }
+        sm100::umma_commit(&tmem_full[acc]);
       }
-      sm100::umma_commit(tmem_full);
     }
   } else {
     // 16 epilogue warps: lane quadrant q (TMEM lanes 32q..), column quarter sub (64 columns)
     const uint32_t ew = warp - 2, q = warp & 3, sub = ew >> 2;
     uint8_t* stg = smStg + ew * dit::RESID_WARP_STG;
     const uint32_t rg = lane >> 3, cchunk = lane & 7;
-    sm100::mbar_wait(tmem_full, 0);
-    sm100::tc_fence_after();
-    const uint32_t taddr = tmem_base + ((q * 32u) << 16);
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int col0 = (int)blockIdx.y * 256 + sub * 64 + half * 32;
-      if (col0 < p.valid_cols) {   // warp-uniform
-        uint32_t v[32];
-        sm100::tmem_ld_32x32b_x32(taddr + sub * 64 + half * 32, v);
+    float part = 0.f;   // epi 1: this thread's share of the row's SwiGLU . v dot product, accumulated over the N tiles of the CTA
+    for (int t = 0; t < n_loop; ++t) {
+      const uint32_t acc = t & 1;
+      const int bn = bn0 + t;
+      sm100::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
+      sm100::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * 256;
+      if (p.epi == 1) {
+        // SwiGLU . v: this warp owns rows [32 q, 32 q + 32) (one per lane) and hidden units [32 sub, 32 sub + 32) of the tile
+        uint32_t va[32], vb[32];
+        sm100::tmem_ld_32x32b_x32(taddr + sub * 32, va);
+        sm100::tmem_ld_32x32b_x32(taddr + 128 + sub * 32, vb);
         sm100::tmem_ld_wait();
+        const float* vv = p.vdot + bn * 128 + sub * 32;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<float4*>(stg + sm100::swz_chunk_offset(lane, c)) =
-              make_float4(__uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
-        __syncwarp();
-        const int col = col0 + cchunk * 4;
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && blockIdx.z == 0 && col < p.valid_cols) bb = *reinterpret_cast<const float4*>(p.bias + col);
+        for (int i = 0; i < 32; ++i) {
+          const float a = __uint_as_float(va[i]);
+          part += a * sigmoidf_(a) * __uint_as_float(vb[i]) * vv[i];
+        }
+      } else {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int col0 = bn * 256 + sub * 64 + half * 32;
+          if (col0 < p.valid_cols) {   // warp-uniform
+            uint32_t v[32];
+            sm100::tmem_ld_32x32b_x32(taddr + sub * 64 + half * 32, v);
+            sm100::tmem_ld_wait();
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const uint32_t r = it * 4 + rg;
-          const int row = (int)blockIdx.x * 128 + q * 32 + r;
-          float4 a = *reinterpret_cast<const float4*>(stg + sm100::swz_chunk_offset(r, cchunk));
-          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-          if (row < p.valid_rows && col < p.valid_cols) {
-            float* dst = p.out + (long long)row * p.out_ld + col;
-            if (p.atomic) atomicAdd(reinterpret_cast<float4*>(dst), a);
-            else *reinterpret_cast<float4*>(dst) = a;
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(stg + sm100::swz_chunk_offset(lane, c)) =
+                  make_float4(__uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]), __uint_as_float(v[c * 4 + 3]));
+            __syncwarp();
+            const int col = col0 + cchunk * 4;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && blockIdx.z == 0 && col < p.valid_cols) bb = *reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const uint32_t r = it * 4 + rg;
+              const int row = bm * 128 + q * 32 + r;
+              float4 a = *reinterpret_cast<const float4*>(stg + sm100::swz_chunk_offset(r, cchunk));
+              a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+              if (row < p.valid_rows && col < p.valid_cols) {
+                float* dst = p.out + (long long)row * p.out_ld + col;
+                if (p.atomic) atomicAdd(reinterpret_cast<float4*>(dst), a);
+                else *reinterpret_cast<float4*>(dst) = a;
+              }
+            }
+            __syncwarp();
           }
         }
-        __syncwarp();
+      }
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);     // the MMA warp may overwrite this accumulator (tile t + 2)
+    }
+    if (p.epi == 1) {
+      float* red = reinterpret_cast<float*>(smStg);            // [4 sub][128 rows]
+      red[sub * 128 + q * 32 + lane] = part;
+      sm100::named_bar_sync(1, dit::EPI_THREADS);
+      if (sub == 0) {
+        const int r = q * 32 + lane, row = bm * 128 + r;
+        if (row < p.valid_rows) {
+          const float tot = (red[r] + red[128 + r]) + (red[256 + r] + red[384 + r]);
+          if (p.atomic) atomicAdd(p.dot_out + row, tot);
+          else p.dot_out[row] += tot;                          // single writer per row (all N tiles in this CTA): deterministic
+        }
       }
     }
   }
   sm100::tc_fence_before();
   __syncthreads();
-  if (warp == 1) sm100::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) sm100::tmem_dealloc(tmem_base, 512);
 }
 
 // ==========================================================================================

@@ -947,7 +947,8 @@ __global__ void __launch_bounds__(256) mcab_encode_kernel(const EncParams p) {
 
 // ---- softmax-over-genes finalisation + optional NB sampling --------------------------------
 struct NbParams {
-  const float* logits;     // [cells][G]
+  const float* logits;     // [cells][G] (row stride logit_stride when that is non-zero)
+  long long logit_stride;
   const float2* partials;  // [cells][gene_tiles] (max, sum) pairs; gene_tiles = partials per cell (8 per 128-gene tile on the tensor-core path)
   int gene_tiles;
   int G;
@@ -997,7 +998,7 @@ __global__ void __launch_bounds__(256) nb_finalize_kernel(const NbParams p) {
   const float scale = p.lib[cell] / s_s;
   const long long gcell = p.cell_offset + cell;
   for (int gi = blockIdx.y * 256 + tid; gi < p.G; gi += gridDim.y * 256) {
-    const float muv = __expf(p.logits[(size_t)cell * p.G + gi] - gm) * scale;
+    const float muv = __expf(p.logits[(size_t)cell * (p.logit_stride ? p.logit_stride : (long long)p.G) + gi] - gm) * scale;
     float th;
     if (p.theta_tbl != nullptr) {
       th = __expf(p.theta_tbl[p.genes[gi]]);

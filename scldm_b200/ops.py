@@ -255,6 +255,62 @@ def vae_encode(packed: PackedVAEEncoder, genes_subset: torch.Tensor, counts_subs
 
 
 @_on_arg_device
+def vae256_decode(packed, z: torch.Tensor, genes: torch.Tensor, lib_size: torch.Tensor, want_mu=True, want_counts=False, seed: int = 0,
+                  cell_offset: int = 0, out_mu: torch.Tensor | None = None, out_counts: torch.Tensor | None = None, max_rows: int = 1 << 21):
+    """`vae_decode` for the n_embed = 256 VAE (`pack256.PackedVAE256Decoder`).  The cells are processed in chunks of at most
+    `max_rows` gene rows (cells x padded G) so that the (rows, 256) intermediates of the tensor-core MCAB stay a few GB."""
+    lib = _lib.load()
+    _require_cuda(z, "z")
+    n_cells, G = z.shape[0], genes.numel()
+    assert z.dtype == torch.float32 and z.shape[1:] == (16, 16) and genes.dtype == torch.int64 and genes.is_cuda and genes.dim() == 1
+    assert int(lib_size.numel()) == n_cells
+    lib_size = lib_size.reshape(-1).to(torch.float32).contiguous()
+    dev = z.device
+    if packed.qp_bf16 is None:      # cell-invariant query side, once per vocabulary
+        qp = torch.empty(packed.emb.shape[0], 256, dtype=torch.bfloat16, device=dev)
+        ws = _workspace(dev, int(lib.scldm_vae256_qside_workspace_bytes(packed.emb.shape[0])), "vae256q")
+        _lib.check(lib.scldm_vae256_qside(C.byref(packed.struct), qp.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "scldm_vae256_qside")
+        packed.qp_bf16 = qp
+    mu = out_mu if out_mu is not None else (torch.empty(n_cells, G, dtype=torch.float32, device=dev) if want_mu else None)
+    counts = out_counts if out_counts is not None else (torch.empty(n_cells, G, dtype=torch.float32, device=dev) if want_counts else None)
+    theta = torch.empty(G, dtype=torch.float32, device=dev)
+    g_pad = -(-G // 128) * 128
+    per = max(8, (max_rows // g_pad) // 8 * 8)
+    ws = _workspace(dev, int(lib.scldm_vae256_decode_workspace_bytes(min(per, n_cells), G)), "vae256d")
+    for c0 in range(0, n_cells, per):
+        c1 = min(c0 + per, n_cells)
+        rc = lib.scldm_vae256_decode(C.byref(packed.struct), packed.qp_bf16.data_ptr(), z[c0:c1].data_ptr(), c1 - c0, genes.data_ptr(), G,
+                                     lib_size[c0:c1].data_ptr(), mu[c0:c1].data_ptr() if mu is not None else None, theta.data_ptr(),
+                                     counts[c0:c1].data_ptr() if counts is not None else None, seed & (2**64 - 1), cell_offset + c0,
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _lib.check(rc, "scldm_vae256_decode")
+    return mu, theta, counts
+
+
+@_on_arg_device
+def vae256_encode(packed, genes_subset: torch.Tensor, counts_subset: torch.Tensor, max_rows: int = 1 << 20) -> torch.Tensor:
+    """`vae_encode` for the n_embed = 256 VAE (`pack256.PackedVAE256Encoder`), in chunks of at most `max_rows` token rows."""
+    lib = _lib.load()
+    _require_cuda(genes_subset, "genes_subset")
+    _require_cuda(counts_subset, "counts_subset")
+    assert genes_subset.dtype == torch.int64 and genes_subset.dim() == 2 and genes_subset.shape == counts_subset.shape
+    counts = counts_subset.to(torch.float32).contiguous()
+    genes_subset = genes_subset.contiguous()
+    n_cells, S = genes_subset.shape
+    dev = genes_subset.device
+    z = torch.empty(n_cells, 16, 16, dtype=torch.float32, device=dev)
+    s_pad = -(-S // 128) * 128
+    per = max(8, (max_rows // s_pad) // 8 * 8)
+    ws = _workspace(dev, int(lib.scldm_vae256_encode_workspace_bytes(min(per, n_cells), S)), "vae256e")
+    for c0 in range(0, n_cells, per):
+        c1 = min(c0 + per, n_cells)
+        rc = lib.scldm_vae256_encode(C.byref(packed.struct), genes_subset[c0:c1].data_ptr(), counts[c0:c1].data_ptr(), c1 - c0, S, z[c0:c1].data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _lib.check(rc, "scldm_vae256_encode")
+    return z
+
+
+@_on_arg_device
 def randn_cells(n_cells: int, per_cell: int, seed: int, cell_offset: int, stream_id: int, device) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(n_cells, per_cell, dtype=torch.float32, device=device)

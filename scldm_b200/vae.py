@@ -12,6 +12,7 @@ from .config import VAEConfig
 from .layers import InputTransformerVAE
 from .nnets import Decoder, Encoder
 from .pack import PackedVAEDecoder, PackedVAEEncoder
+from .pack256 import PackedVAE256Decoder, PackedVAE256Encoder
 from .stochastic_layers import NegativeBinomial, NegativeBinomialTransformerLayer
 
 
@@ -61,9 +62,17 @@ class TransformerVAE(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("scldm_b200.TransformerVAE runs on CUDA only (no CPU fallback): call .cuda() first")
         if self._packed_dec is None or self._packed_key != key:
-            self._packed_dec = PackedVAEDecoder({k: v.detach() for k, v in sd.items()}, self.config(), dev)
+            cfg = self.config()
+            cls = PackedVAE256Decoder if cfg.n_embed == 256 else PackedVAEDecoder      # kernels exist for n_embed 32 (vae_base.yaml) and 256 (census scale)
+            self._packed_dec = cls({k: v.detach() for k, v in sd.items()}, cfg, dev)
             self._packed_key = key
         return self._packed_dec
+
+    def _decode_op(self, packed):
+        """The decode entry point of the packed weights' kernel family (same contract)."""
+        if isinstance(packed, PackedVAE256Decoder):
+            return lambda z, g, lib, precision="bf16", **kw: ops.vae256_decode(packed, z, g, lib, **kw)     # tensor cores only at n_embed = 256
+        return lambda z, g, lib, **kw: ops.vae_decode(packed, z, g, lib, **kw)
 
     def decode(self, z: torch.Tensor, genes: torch.Tensor, library_size: torch.Tensor,
                condition: dict[str, torch.Tensor] | None = None) -> NegativeBinomial:
@@ -74,7 +83,8 @@ class TransformerVAE(nn.Module):
         gvec = shared_gene_vector(genes)
         zc = z.contiguous().float()
         prec = self.decode_precision
-        mu, theta, _ = ops.vae_decode(packed, zc, gvec, library_size, want_mu=True, want_counts=False, precision=prec)
+        dec = self._decode_op(packed)
+        mu, theta, _ = dec(zc, gvec, library_size, want_mu=True, want_counts=False, precision=prec)
         theta_full = theta.unsqueeze(0).expand(z.shape[0], -1) if theta.dim() == 1 else theta
         n_cells = z.shape[0]
 
@@ -83,8 +93,7 @@ class TransformerVAE(nn.Module):
             # takes the next `n_cells` offsets, so repeated draws are independent; set `vae.sample_seed` / `vae.sample_offset` to replay
             offset = self.sample_offset
             self.sample_offset = offset + n_cells
-            _, _, counts = ops.vae_decode(packed, zc, gvec, library_size, want_mu=False, want_counts=True, seed=self.sample_seed,
-                                          cell_offset=offset, precision=prec)
+            _, _, counts = dec(zc, gvec, library_size, want_mu=False, want_counts=True, seed=self.sample_seed, cell_offset=offset, precision=prec)
             return counts
 
         return NegativeBinomial(mu, theta_full, _sampler=sampler)
@@ -94,9 +103,9 @@ class TransformerVAE(nn.Module):
         """Fast path of `decode(...).sample()` (`models.py:818-819`): one pass, counts only (+mu on request),
         optionally written straight into caller-provided output rows."""
         packed = self.packed_decoder()
-        mu, theta, counts = ops.vae_decode(packed, z.contiguous().float(), shared_gene_vector(genes), library_size,
-                                           want_mu=want_mu, want_counts=True, seed=seed, cell_offset=cell_offset,
-                                           out_counts=out_counts, out_mu=out_mu, precision=self.decode_precision)
+        mu, theta, counts = self._decode_op(packed)(z.contiguous().float(), shared_gene_vector(genes), library_size,
+                                                    want_mu=want_mu, want_counts=True, seed=seed, cell_offset=cell_offset,
+                                                    out_counts=out_counts, out_mu=out_mu, precision=self.decode_precision)
         return counts, mu, theta
 
     def packed_encoder(self) -> PackedVAEEncoder:
@@ -106,7 +115,9 @@ class TransformerVAE(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("scldm_b200.TransformerVAE runs on CUDA only (no CPU fallback): call .cuda() first")
         if getattr(self, "_packed_enc", None) is None or self._packed_enc_key != key:
-            self._packed_enc = PackedVAEEncoder({k: v.detach() for k, v in sd.items()}, self.config(), dev)
+            cfg = self.config()
+            cls = PackedVAE256Encoder if cfg.n_embed == 256 else PackedVAEEncoder
+            self._packed_enc = cls({k: v.detach() for k, v in sd.items()}, cfg, dev)
             self._packed_enc_key = key
         return self._packed_enc
 
@@ -114,7 +125,10 @@ class TransformerVAE(nn.Module):
         """`TransformerVAE.encode` (`vae.py:58-69`): the subset tensors are used when given, else (counts, genes)."""
         c = counts_subset if counts_subset is not None else counts
         g = genes_subset if genes_subset is not None else genes
-        return ops.vae_encode(self.packed_encoder(), g.contiguous(), c.contiguous())
+        packed = self.packed_encoder()
+        if isinstance(packed, PackedVAE256Encoder):
+            return ops.vae256_encode(packed, g.contiguous(), c.contiguous())
+        return ops.vae_encode(packed, g.contiguous(), c.contiguous())
 
     @torch.no_grad()
     def forward(self, counts, genes, library_size, counts_subset=None, genes_subset=None):

