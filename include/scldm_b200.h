@@ -349,6 +349,29 @@ size_t scldm_vae256_encode_workspace_bytes(int32_t n_cells, int32_t seq_len);
 int scldm_vae256_encode(const scldm_vae256_weights* w, const int64_t* genes_subset, const float* counts_subset, int32_t n_cells,
                         int32_t seq_len, float* z, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- generation evaluation (src/scldm/evaluations.py) and the SDE sampler (transport/integrators.py:7-75) ------------------- */
+/* out [4][nx][ny] fp32: per pair (i, j) of rows of x [nx][D] and y [ny][D]: sum x*y, sum |x - y|, sum |x + y|, sum min(x, y) -
+ * the sufficient statistics of RBFKernel / BrayCurtisKernel / TanimotoKernel / RuzickaKernel (evaluations.py:10-69) and of the
+ * torch.cdist cost matrix of `wasserstein` (evaluations.py:100). */
+int scldm_pair_stats(const float* x, int32_t nx, const float* y, int32_t ny, int32_t D, float* out, void* stream);
+/* n_iter Sinkhorn-Knopp iterations on the Gibbs kernel K [n][m] (POT sinkhorn_knopp: v = b / K^T u; u = a / K v), then
+ * res[0] = <u K v, M> and res[1] = || v * K^T u - b ||_1 (res: 2 device floats, zeroed here). */
+int scldm_sinkhorn(const float* K, const float* M, const float* a, const float* b, int32_t n, int32_t m, float* u, float* v, int32_t n_iter,
+                   float* res, void* stream);
+#define SCLDM_DIFFUSION_CONSTANT 0
+#define SCLDM_DIFFUSION_SBDM 1
+#define SCLDM_DIFFUSION_SIGMA 2
+#define SCLDM_DIFFUSION_LINEAR 3
+#define SCLDM_DIFFUSION_DECREASING 4
+#define SCLDM_DIFFUSION_INCDEC 5
+/* SDE drift of the Linear path with a velocity model: drift = v + D(t) (t v - x) / (1 - t)   (transport.py:231-233, path.py:52-95) */
+int scldm_sde_drift(const float* v, const float* x, float t, int32_t diffusion_form, float diffusion_norm, float* drift, int64_t n, void* stream);
+/* out = x + sqrt(2 D(t)) sqrt(dt) w; w = noise[n] when non-NULL, else Philox N(0,1) keyed by (seed, cell_offset + i / per_cell, i % per_cell, step) */
+int scldm_sde_kick(const float* x, const float* noise, float t, float dt, int32_t diffusion_form, float diffusion_norm, uint64_t seed, int64_t cell_offset,
+                   int32_t per_cell, uint32_t step, float* out, int64_t n, void* stream);
+/* out = a + c1 d1 (+ c2 d2 when d2 != NULL) */
+int scldm_axpy2(const float* a, float c1, const float* d1, float c2, const float* d2, float* out, int64_t n, void* stream);
+
 /* Live per-kernel timing for bench.py: when enabled every launch is bracketed by CUDA events recorded on
  * `stream` (must be the stream the calls run on; disables CUDA-graph capturability while on).
  * scldm_prof_summary synchronises the device and writes "name count total_ms\n" lines.            */

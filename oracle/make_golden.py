@@ -309,8 +309,48 @@ def vae256_golden() -> None:
         print(name, {k: v.shape for k, v in arrays.items()}, "mu.sum/lib", (nb.mu.sum(1) / lib[:, 0]).tolist())
 
 
+@torch.no_grad()
+def sde_golden() -> None:
+    """`Sampler.sample_sde` of the REFERENCE (`transport.py:269-322`, `integrators.py:7-75`) on the me1 DiT with classifier-free
+    guidance: Euler-Maruyama and Heun, diffusion_form="sigma" (the default "SBDM" is infinite at t0 = 0 for the eps = 0 that
+    `create_transport` forces), 10 grid points, last_step="Mean".  The Brownian increments the reference drew (torch.randn on the
+    CPU) are recorded by wrapping torch.randn for the duration of the call: tests/golden/sde_me1.npz."""
+    ref = ref_loader.load_reference()
+    case = golden_cases()["dit_me1"]
+    cfg = case["cfg"]
+    model = ref_loader.build_reference_dit(cfg, synthetic.dit_state_dict(cfg, WEIGHT_SEED))
+    transport = ref.transport.create_transport(path_type="Linear", prediction="velocity", loss_weight="velocity", train_eps=1e-5, sample_eps=1e-5)
+    sampler = ref.transport.Sampler(transport)
+    B = 2
+    z0 = synthetic.randn("sde.z0", (B, cfg.seq_len, cfg.n_embed_input))
+    lab = synthetic.randint("sde.label", 14, (B,))
+    w = {"clusters": 2.0}
+    model_fn = lambda x, t, **kw: model.forward_with_cfg(x, t, **kw, cfg_scale=w)  # noqa: E731
+    arrays = dict(z0=z0.numpy(), label=lab.numpy())
+    for method in ("Euler", "Heun"):
+        fn = sampler.sample_sde(sampling_method=method, diffusion_form="sigma", diffusion_norm=1.0, last_step="Mean", last_step_size=0.04, num_steps=10)
+        drawn, orig = [], torch.randn
+        import scldm.transport.integrators as integ
+
+        def rec(*a, **k):
+            t = orig(*a, **k)
+            drawn.append(t.clone())
+            return t
+
+        integ.th.randn = rec
+        try:
+            torch.manual_seed(31)
+            xs = fn(torch.cat([z0, z0]), model_fn, condition={"clusters": torch.cat([lab, lab])})
+        finally:
+            integ.th.randn = orig
+        arrays[f"{method}.noise"] = torch.stack(drawn).numpy()
+        arrays[f"{method}.states"] = torch.stack(xs).numpy()
+        print("sde", method, len(drawn), torch.stack(xs).shape, float(xs[-1].abs().mean()))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "sde_me1.npz"), **arrays)
+
+
 if __name__ == "__main__":
-    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden, "vae256": vae256_golden}   # fixtures added after the first set; minted
+    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden, "vae256": vae256_golden, "sde": sde_golden}   # fixtures added after the first set; minted
     if len(sys.argv) > 1 and sys.argv[1] in later:                                 # alone so the others stay byte-identical
         later[sys.argv[1]]()
     else:

@@ -19,7 +19,7 @@ EXPORTS = [
     "scldm_dit_forward", "scldm_dit_forward_shared_t", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
     "scldm_vae_decode", "scldm_vae_encode", "scldm_randn_cells", "scldm_csr_count", "scldm_csr_fill", "scldm_tokenize_expressed", "scldm_nb_nll", "scldm_dit_train_workspace_bytes", "scldm_dit_train_forward", "scldm_dit_train_backward", "scldm_adamw_step", "scldm_repack",
     "scldm_ema_update", "scldm_vae256_qside_workspace_bytes", "scldm_vae256_qside", "scldm_vae256_decode_workspace_bytes", "scldm_vae256_decode",
-    "scldm_vae256_encode_workspace_bytes", "scldm_vae256_encode", "scldm_test_gemm", "scldm_test_nb_invert", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
+    "scldm_vae256_encode_workspace_bytes", "scldm_vae256_encode", "scldm_pair_stats", "scldm_sinkhorn", "scldm_sde_drift", "scldm_sde_kick", "scldm_axpy2", "scldm_test_gemm", "scldm_test_nb_invert", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
 ]
 
 
@@ -161,6 +161,17 @@ def load() -> C.CDLL:
     lib.scldm_vae256_encode_workspace_bytes.restype = C.c_size_t
     lib.scldm_vae256_encode.argtypes = [P(Vae256Weights), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.scldm_vae256_encode.restype = C.c_int
+    lib.scldm_pair_stats.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.scldm_pair_stats.restype = C.c_int
+    lib.scldm_sinkhorn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.scldm_sinkhorn.restype = C.c_int
+    lib.scldm_sde_drift.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.scldm_sde_drift.restype = C.c_int
+    lib.scldm_sde_kick.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p,
+                                   C.c_int64, C.c_void_p]
+    lib.scldm_sde_kick.restype = C.c_int
+    lib.scldm_axpy2.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.scldm_axpy2.restype = C.c_int
     lib.scldm_test_gemm.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]
     lib.scldm_test_gemm.restype = C.c_int

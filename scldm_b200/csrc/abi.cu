@@ -15,6 +15,7 @@
 #include "csr_kernels.cuh"
 #include "train_kernels.cuh"
 #include "vae256_kernels.cuh"
+#include "eval_kernels.cuh"
 
 namespace {
 
@@ -702,3 +703,46 @@ const char* scldm_version(void) { return "scldm_b200 0.1 (sm_100a)"; }
 
 #include "train_abi.inc"
 #include "vae256_abi.inc"
+
+extern "C" {
+
+int scldm_pair_stats(const float* x, int32_t nx, const float* y, int32_t ny, int32_t D, float* out, void* stream) {
+  if (!x || !y || !out || nx < 1 || ny < 1 || D < 1) return fail(SCLDM_EINVAL, "bad pair_stats arguments");
+  LAUNCH("pair_stats", evk::pair_stats_kernel<<<dim3(ceil_div(ny, evk::PT), ceil_div(nx, evk::PT)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, nx, y, ny, D, out));
+  return SCLDM_OK;
+}
+
+int scldm_sinkhorn(const float* K, const float* M, const float* a, const float* b, int32_t n, int32_t m, float* u, float* v, int32_t n_iter, float* res,
+                   void* stream) {
+  if (!K || !M || !a || !b || !u || !v || !res || n < 1 || m < 1 || n_iter < 0) return fail(SCLDM_EINVAL, "bad sinkhorn arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int it = 0; it < n_iter; ++it) {
+    LAUNCH("sinkhorn_ktu", evk::sinkhorn_ktu_kernel<<<ceil_div(m, 256), 256, 0, st>>>(K, u, b, n, m, v));
+    LAUNCH("sinkhorn_kv", evk::sinkhorn_kv_kernel<<<ceil_div(n, 8), 256, 0, st>>>(K, v, a, n, m, u));
+  }
+  CUDA_OK(cudaMemsetAsync(res, 0, 8, st));
+  LAUNCH("sinkhorn_eval", evk::sinkhorn_eval_kernel<<<ceil_div(m, 256), 256, 0, st>>>(K, M, u, v, b, n, m, res));
+  return SCLDM_OK;
+}
+
+int scldm_sde_drift(const float* v, const float* x, float t, int32_t form, float norm, float* drift, int64_t n, void* stream) {
+  if (!v || !x || !drift || n < 1 || form < 0 || form > 5) return fail(SCLDM_EINVAL, "bad sde_drift arguments");
+  LAUNCH("sde_drift", evk::sde_drift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, x, t, form, norm, drift, (long long)n));
+  return SCLDM_OK;
+}
+
+int scldm_sde_kick(const float* x, const float* noise, float t, float dt, int32_t form, float norm, uint64_t seed, int64_t cell_offset, int32_t per_cell,
+                   uint32_t step, float* out, int64_t n, void* stream) {
+  if (!x || !out || n < 1 || per_cell < 1 || form < 0 || form > 5) return fail(SCLDM_EINVAL, "bad sde_kick arguments");
+  LAUNCH("sde_kick", evk::sde_kick_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, noise, t, dt, form, norm, seed, (long long)cell_offset,
+                                                                                                         per_cell, step, out, (long long)n));
+  return SCLDM_OK;
+}
+
+int scldm_axpy2(const float* a, float c1, const float* d1, float c2, const float* d2, float* out, int64_t n, void* stream) {
+  if (!a || !d1 || !out || n < 1) return fail(SCLDM_EINVAL, "bad axpy2 arguments");
+  LAUNCH("axpy2", evk::axpy2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, c1, d1, c2, d2, out, (long long)n));
+  return SCLDM_OK;
+}
+
+}  // extern "C"

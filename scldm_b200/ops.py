@@ -389,6 +389,41 @@ def tokenize_expressed(counts: torch.Tensor, gene_ids: torch.Tensor, genes_seq_l
     return {"genes_subset": genes_out, "counts_subset": counts_out, "library_size": library}
 
 
+@_on_arg_device
+def sde_drift(v: torch.Tensor, x: torch.Tensor, t: float, form: int, norm: float) -> torch.Tensor:
+    """v + D(t) (t v - x) / (1 - t): SDE drift of the Linear path with a velocity model (`transport.py:231-233`)."""
+    _require_cuda(v, "v")
+    _require_cuda(x, "x")
+    out = torch.empty_like(v)
+    _lib.check(_lib.load().scldm_sde_drift(v.data_ptr(), x.data_ptr(), float(t), int(form), float(norm), out.data_ptr(), v.numel(), _stream_ptr(v.device)), "scldm_sde_drift")
+    return out
+
+
+@_on_arg_device
+def sde_kick(x: torch.Tensor, noise: torch.Tensor | None, t: float, dt: float, form: int, norm: float, seed: int, cell_offset: int, per_cell: int, step: int,
+             x_for_diffusion: torch.Tensor | None = None) -> torch.Tensor:
+    """x + sqrt(2 D(t)) sqrt(dt) w with w = `noise` or Philox normals keyed by (seed, global cell, element, step)."""
+    _require_cuda(x, "x")
+    out = torch.empty_like(x)
+    if noise is not None:
+        noise = noise.contiguous().float()
+    rc = _lib.load().scldm_sde_kick(x.data_ptr(), noise.data_ptr() if noise is not None else None, float(t), float(dt), int(form), float(norm), seed & (2**64 - 1),
+                                    int(cell_offset), int(per_cell), int(step), out.data_ptr(), x.numel(), _stream_ptr(x.device))
+    _lib.check(rc, "scldm_sde_kick")
+    return out
+
+
+@_on_arg_device
+def axpy2(a: torch.Tensor, c1: float, d1: torch.Tensor, c2: float = 0.0, d2: torch.Tensor | None = None) -> torch.Tensor:
+    """a + c1 d1 (+ c2 d2)."""
+    _require_cuda(a, "a")
+    out = torch.empty_like(a)
+    rc = _lib.load().scldm_axpy2(a.data_ptr(), float(c1), d1.contiguous().data_ptr(), float(c2), d2.contiguous().data_ptr() if d2 is not None else None, out.data_ptr(),
+                                 a.numel(), _stream_ptr(a.device))
+    _lib.check(rc, "scldm_axpy2")
+    return out
+
+
 def prof_enable(on: bool, device=None) -> None:
     """Bracket every library launch with CUDA events on the current stream (bench.py roofline timing)."""
     dev = device if device is not None else torch.cuda.current_device()

@@ -37,9 +37,11 @@ class Transport:
     def check_interval(self, train_eps, sample_eps, *, diffusion_form="SBDM", sde=False, reverse=False, eval=False,
                        last_step_size=0.0):
         """`Transport.check_interval` (`transport.py:69-95`) for the velocity/Linear ODE case: t0=0, t1=1."""
-        if sde:
-            raise NotImplementedError("SDE sampling is outside the hot path (SURVEY.md §8f rank 4)")
         t0, t1 = 0, 1
+        if sde:   # ICPlan branch of the reference (`transport.py:85-89`): a first semi-implicit step for SBDM, the last step held back
+            eps = train_eps if not eval else sample_eps
+            t0 = eps if diffusion_form == "SBDM" else 0
+            t1 = 1 - eps if last_step_size == 0 else 1 - last_step_size
         if reverse:
             t0, t1 = 1 - t0, 1 - t1
         return t0, t1
@@ -173,6 +175,69 @@ class Sampler:
             return torch.stack(states if return_trajectory else [x0, xk])
 
         return sample
+
+    DIFFUSION_FORMS = {"constant": 0, "SBDM": 1, "sigma": 2, "linear": 3, "decreasing": 4, "inccreasing-decreasing": 5}
+
+    def sample_sde(self, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean", last_step_size=0.04, num_steps=250,
+                   seed: int = 0):
+        """`Sampler.sample_sde` (`transport.py:269-322`) for the Linear path with a velocity model: Euler-Maruyama / Heun steps of
+        `integrators.sde` (`integrators.py:7-75`) on the uniform grid linspace(t0, t1, num_steps), then the last step ("Mean", "Euler",
+        "Tweedie" or None).  Returns fn(init, model, **model_kwargs) -> list of `num_steps` states like the reference.  Every model
+        evaluation is one batched launch sequence on the device; drift / noise / update run in the library's own kernels.  The
+        Brownian increments come from Philox streams keyed by (seed, cell, step) - pass `noise=[...]` (num_steps - 1 tensors) to inject
+        them.  NOTE (reference behaviour): with the eps = 0 that `create_transport` forces for Linear + velocity, the default
+        diffusion_form="SBDM" = (1-t)/t is infinite at t0 = 0, in the reference as here; use "sigma", "linear", "constant", ..."""
+        if sampling_method not in ("Euler", "Heun"):
+            raise NotImplementedError("Sampler type not implemented.")
+        if diffusion_form not in self.DIFFUSION_FORMS:
+            raise NotImplementedError(f"Diffusion form {diffusion_form} not implemented")
+        if last_step not in (None, "Mean", "Tweedie", "Euler"):
+            raise NotImplementedError()
+        if last_step is None:
+            last_step_size = 0.0
+        form = self.DIFFUSION_FORMS[diffusion_form]
+        t0, t1 = self.transport.check_interval(self.transport.train_eps, self.transport.sample_eps, diffusion_form=diffusion_form, sde=True, eval=True,
+                                               reverse=False, last_step_size=last_step_size)
+        assert t0 < t1, "SDE sampler has to be in forward time"
+        grid = torch.linspace(t0, t1, num_steps)
+        dt = float(grid[1] - grid[0])
+
+        def _sample(init, model, noise=None, cell_offset: int = 0, **model_kwargs):
+            x = init.contiguous().float()
+            per_cell = x[0].numel()
+            if isinstance(model, FusedCFGModel):
+                plan, _ = model.dit.cfg_plan(model_kwargs.get("condition"), model.cfg_scale, x.shape[0] // 2, x.device, shared_time=True)
+                velocity = lambda xx, t: ops.dit_forward_shared_t(plan, xx.contiguous(), float(t))  # noqa: E731
+            else:
+                velocity = lambda xx, t: model(xx, torch.full((xx.shape[0],), float(t), dtype=torch.float32, device=xx.device), **model_kwargs)  # noqa: E731
+            drift = lambda xx, t: ops.sde_drift(velocity(xx, t), xx, float(t), form, diffusion_norm)  # noqa: E731
+            xs = []
+            for k in range(num_steps - 1):
+                t = float(grid[k])
+                w = None if noise is None else noise[k].to(x)
+                if sampling_method == "Euler":      # x' = x + drift dt + sqrt(2 D) dW     (integrators.py:27-35)
+                    x = ops.sde_kick(ops.axpy2(x, dt, drift(x, t)), w, t, dt, form, diffusion_norm, seed, cell_offset, per_cell, k, x_for_diffusion=x)
+                else:                               # Heun (integrators.py:37-46)
+                    xhat = ops.sde_kick(x, w, t, dt, form, diffusion_norm, seed, cell_offset, per_cell, k)
+                    k1 = drift(xhat, t)
+                    k2 = drift(ops.axpy2(xhat, dt, k1), t + dt)
+                    x = ops.axpy2(xhat, 0.5 * dt, k1, 0.5 * dt, k2)
+                xs.append(x)
+            if last_step == "Mean":
+                x = ops.axpy2(xs[-1], last_step_size, drift(xs[-1], t1))
+            elif last_step == "Euler":
+                x = ops.axpy2(xs[-1], last_step_size, velocity(xs[-1], t1))
+            elif last_step == "Tweedie":            # x / alpha + sigma^2 / alpha * score, alpha = t1, sigma = 1 - t1
+                v = velocity(xs[-1], t1)
+                score = (t1 * v - xs[-1]) / (1 - t1)
+                x = xs[-1] / t1 + (1 - t1) ** 2 / t1 * score
+            else:
+                x = xs[-1]
+            xs.append(x)
+            assert len(xs) == num_steps, "Samples does not match the number of steps"
+            return xs
+
+        return _sample
 
     def _sample_adaptive(self, x0, model, grid, atol, rtol, **model_kwargs):
         """dopri5 (the reference's default, `transport.py:327`): host-side step controller (as in torchdiffeq), function
