@@ -382,6 +382,13 @@ int32_t scldm_prof_summary(char* buf, int32_t cap);
  * device_buf (4 regions of 2^17 int64: qkv, proj, mlp1, mlp2; 32 stamps per CTA).  NULL disables.      */
 void scldm_debug_timeline(long long* device_buf, int32_t layer);
 
+/* Runtime options (cross-checks / profiling; the defaults are the product path).  name: "mega" (1: one persistent block-stack kernel per
+ * evaluation, 0: one kernel per block half), "pdl" (programmatic dependent launch), "mod_batch" (adaLN table of a whole solve from one
+ * GEMM), "exp" (bit mask of dit_blocks_kernel micro-variants), "dec_cpb" / "dec_occ" (MCAB decode launch shape).  The SCLDM_<NAME>
+ * environment variables give the initial values only.  scldm_get_option returns -1 for an unknown name. */
+int scldm_set_option(const char* name, int32_t value);
+int32_t scldm_get_option(const char* name);
+
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 uint64_t scldm_launch_count(void);
 const char* scldm_last_error(void);

@@ -19,7 +19,7 @@ EXPORTS = [
     "scldm_dit_forward", "scldm_dit_forward_shared_t", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
     "scldm_vae_decode", "scldm_vae_encode", "scldm_randn_cells", "scldm_csr_count", "scldm_csr_fill", "scldm_tokenize_expressed", "scldm_nb_nll", "scldm_dit_train_workspace_bytes", "scldm_dit_train_forward", "scldm_dit_train_backward", "scldm_adamw_step", "scldm_repack",
     "scldm_ema_update", "scldm_vae256_qside_workspace_bytes", "scldm_vae256_qside", "scldm_vae256_decode_workspace_bytes", "scldm_vae256_decode",
-    "scldm_vae256_encode_workspace_bytes", "scldm_vae256_encode", "scldm_pair_stats", "scldm_sinkhorn", "scldm_sde_drift", "scldm_sde_kick", "scldm_axpy2", "scldm_test_gemm", "scldm_test_nb_invert", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_launch_count", "scldm_last_error", "scldm_version",
+    "scldm_vae256_encode_workspace_bytes", "scldm_vae256_encode", "scldm_pair_stats", "scldm_sinkhorn", "scldm_sde_drift", "scldm_sde_kick", "scldm_axpy2", "scldm_test_gemm", "scldm_test_nb_invert", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_set_option", "scldm_get_option", "scldm_launch_count", "scldm_last_error", "scldm_version",
 ]
 
 
@@ -183,6 +183,10 @@ def load() -> C.CDLL:
     lib.scldm_prof_summary.restype = C.c_int32
     lib.scldm_debug_timeline.argtypes = [C.c_void_p, C.c_int32]
     lib.scldm_debug_timeline.restype = None
+    lib.scldm_set_option.argtypes = [C.c_char_p, C.c_int32]
+    lib.scldm_set_option.restype = C.c_int
+    lib.scldm_get_option.argtypes = [C.c_char_p]
+    lib.scldm_get_option.restype = C.c_int32
     lib.scldm_launch_count.argtypes = []
     lib.scldm_launch_count.restype = C.c_uint64
     lib.scldm_last_error.argtypes = []

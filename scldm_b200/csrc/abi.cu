@@ -43,16 +43,26 @@ struct ProfRec { const char* name; cudaEvent_t a, b; };
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_prof_pool;
 bool g_prof_on = false;
-const bool g_use_mega = []{ const char* e = getenv("SCLDM_MEGA"); return !(e && e[0] == '0'); }();  // SCLDM_MEGA=0: one kernel per block half
+// Runtime options (scldm_set_option / scldm_get_option).  The SCLDM_* environment variables only provide the initial values.
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+int g_opt_mega = env_int("SCLDM_MEGA", 1);            // 1: the whole block stack of an evaluation is one persistent kernel; 0: one kernel per block half
 int g_num_sms = 148;
-const bool g_use_pair = []{ const char* e = getenv("SCLDM_PAIR"); return e && e[0] == '1'; }();   // SCLDM_PAIR=1: cta_group::2 CTA pairs
-const int g_stagger = []{ const char* e = getenv("SCLDM_STAGGER"); return e ? atoi(e) : 0; }();   // optional start offset step of the persistent CTAs (cycles); measured: no gain
-// dit_blocks_kernel switches (bit mask, SCLDM_EXP): 1 = hand the MLP accumulator over before M2 is queued (measured slower: 971 vs 942 us),
+// dit_blocks_kernel micro-variants (bit mask): 1 = hand the MLP accumulator over before M2 is queued (measured slower: 971 vs 942 us),
 // 2 = no setup barrier in phases whose rows come from the stash (927 vs 942 us), 4 = butterfly LayerNorm reductions (937 vs 942 us)
-const int g_exp = []{ const char* e = getenv("SCLDM_EXP"); return e ? atoi(e) : 6; }();
-const int g_dec_cpb = []{ const char* e = getenv("SCLDM_DEC_CPB"); return e ? atoi(e) : 0; }();   // cells per MCAB decode CTA (0: heuristic)
-const int g_dec_occ = []{ const char* e = getenv("SCLDM_DEC_OCC"); return e ? atoi(e) : 2; }();   // resident CTAs per SM the MCAB decode kernel is compiled for (2: 128 registers, 3: 80 registers + spills)
-const bool g_use_pdl = []{ const char* e = getenv("SCLDM_PDL"); return !(e && e[0] == '0'); }();   // SCLDM_PDL=0: plain launches
+int g_opt_exp = env_int("SCLDM_EXP", 6);
+int g_opt_dec_cpb = env_int("SCLDM_DEC_CPB", 0);      // cells per MCAB decode CTA (0: heuristic)
+int g_opt_dec_occ = env_int("SCLDM_DEC_OCC", 2);      // resident CTAs per SM the MCAB decode kernel is compiled for (2: 128 registers, 3: 80 registers + spills)
+int g_opt_pdl = env_int("SCLDM_PDL", 1);              // programmatic dependent launch between the kernels of a call
+int g_opt_mod_batch = env_int("SCLDM_MOD_BATCH", 1);  // adaLN vectors of all evaluations of a fixed-grid solve from ONE GEMM
+#define g_use_mega (g_opt_mega != 0)
+#define g_exp g_opt_exp
+#define g_dec_cpb g_opt_dec_cpb
+#define g_dec_occ g_opt_dec_occ
+#define g_use_pdl (g_opt_pdl != 0)
+#define g_mod_batch (g_opt_mod_batch != 0)
+struct OptionEntry { const char* name; int* value; };
+const OptionEntry g_options[] = {{"mega", &g_opt_mega}, {"exp", &g_opt_exp}, {"dec_cpb", &g_opt_dec_cpb}, {"dec_occ", &g_opt_dec_occ},
+                                 {"pdl", &g_opt_pdl}, {"mod_batch", &g_opt_mod_batch}};
 cudaStream_t g_prof_stream = nullptr;
 
 cudaEvent_t prof_event() {
@@ -129,7 +139,6 @@ struct DitWs {
 // ALL evaluations come from one GEMM before the loop (rows = evaluation x conditioning row) instead of one 20 us launch per
 // evaluation.  Returns the padded row count of that table, or 0 when the per-evaluation path is used.
 constexpr size_t MOD_BATCH_BYTES = 192u << 20;
-const bool g_mod_batch = []{ const char* e = getenv("SCLDM_MOD_BATCH"); return !(e && e[0] == '0'); }();
 size_t mod_batch_rows(const scldm_dit_weights* w, const scldm_dit_plan* plan, int n_evals) {
   if (!g_mod_batch || n_evals < 2) return 0;
   const size_t rows = align_up((size_t)n_evals * plan->n_mod, dit::BLOCK_M);
@@ -242,17 +251,11 @@ int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const 
     m.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream); m.n_chunks = w->mlp1_tiles; m.hid_slabs = w->hid_slabs;
     a.exp = g_exp; m.exp = g_exp;
     bp.n_layer = w->n_layer; bp.n_tiles = row_tiles;
-    bp.dbg = g_dbg_clk; bp.dbg_layer = g_dbg_layer; bp.stagger_cycles = g_stagger;
+    bp.dbg = g_dbg_clk; bp.dbg_layer = g_dbg_layer; bp.stagger_cycles = 0;
     bp.attn_w_stride = 4LL * dit::D * dit::D;
     bp.mlp_w_stride = ((long long)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs) * dit::B_SLAB_ELEMS;
-    if (g_use_pair && row_tiles % 2 == 0) {   // CTA pairs share every weight slab (cta_group::2)
-      int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
-      grid &= ~1;
-      LAUNCH("dit_blocks", launch_ex(dit::dit_blocks_kernel<true>, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, 2, bp));
-      return SCLDM_OK;
-    }
     const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
-    LAUNCH("dit_blocks", launch_pdl(dit::dit_blocks_kernel<false>, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, bp));
+    LAUNCH("dit_blocks", launch_pdl(dit::dit_blocks_kernel, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, bp));
     return SCLDM_OK;
   }
   for (int l = 0; l < w->n_layer; ++l) {
@@ -368,8 +371,7 @@ int prepare_kernels() {
   if ((rc = set_smem(dit::gemm_astream_resid_kernel, dit::astream_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::mlp_fused_kernel, dit::mlp_fused_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::attn_block_kernel, dit::attn_block_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::dit_blocks_kernel<false>, dit::phase_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::dit_blocks_kernel<true>, dit::phase_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::dit_blocks_kernel, dit::phase_smem_bytes()))) return rc;
   {
     int n = 0;
     CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
@@ -662,6 +664,19 @@ int scldm_tokenize_expressed(const float* dense, int32_t rows, int32_t G, const 
 }
 
 uint64_t scldm_launch_count(void) { return g_launches.load(); }
+
+int scldm_set_option(const char* name, int32_t value) {
+  if (!name) return fail(SCLDM_EINVAL, "null option name");
+  for (const OptionEntry& o : g_options)
+    if (strcmp(o.name, name) == 0) { *o.value = value; return SCLDM_OK; }
+  return fail(SCLDM_EINVAL, "unknown option '%s' (mega, exp, dec_cpb, dec_occ, pdl, mod_batch)", name);
+}
+int32_t scldm_get_option(const char* name) {
+  if (name)
+    for (const OptionEntry& o : g_options)
+      if (strcmp(o.name, name) == 0) return *o.value;
+  return -1;
+}
 
 void scldm_debug_timeline(long long* device_buf, int32_t layer) {
   g_dbg_clk = device_buf;

@@ -807,49 +807,36 @@ struct PhaseSeq {
   uint32_t odd;     // (previous executions of this phase type) & 1
   uint32_t tma;     // (previous executions with x_tma) & 1
 };
-// Barrier indices inside a set (40 slots): ring full[8] | empty[8] | pfull[8] (pair mode: "the peer's half of the stage
-// landed", forwarded to the leader), then the phase's own barriers.
+// Barrier indices inside a set (40 slots): ring full[8] | empty[8] | 8 unused, then the phase's own barriers.
 enum { BI_FULL = 0, BI_EMPTY = 8, BI_PFULL = 16,
        BA_A_READY = 24, BA_ACCQ_FULL = 25, BA_ACCQ_FREE = 26, BA_AO_READY = 27, BA_AO_FREE = 28, BA_ACCP_FULL = 29, BA_X_FULL = 30, BA_X_EMPTY = 34,
        BM_A_READY = 24, BM_ACC1_FULL = 25, BM_ACC1_FREE = 26, BM_H_READY = 27, BM_H_FREE = 29, BM_ACC2_FULL = 31, BM_X_FULL = 32, BM_X_EMPTY = 36 };
 
-// Synchronisation policy of a phase: one CTA per tile (cta_group::1) or a CTA pair sharing every weight slab (cta_group::2,
-// see sm100.cuh).  In pair mode the warps of both CTAs arrive on the LEADER's worker->MMA barriers and the leader's commits
-// arrive on the MMA->worker barriers of both CTAs.
-template <bool PAIR>
+// Synchronisation helpers of a phase (one CTA per tile, cta_group::1).  A CTA-pair variant (cta_group::2 MMAs, every weight slab
+// split over the two SMs of a cluster) was built and measured in round 1 - 38.6k vs 41.8k cells/s, the accumulator hand-off became
+// the critical path - and removed in round 2 (git history: `dit_blocks_kernel<true>`).
 struct Cg {
-  static constexpr uint32_t WORKER_ARRIVALS = PAIR ? 2 * EPI_WARPS : EPI_WARPS;
-  __device__ static __forceinline__ void commit(uint64_t* bar) {
-    if constexpr (PAIR) sm100::umma_commit2(bar); else sm100::umma_commit(bar);
-  }
-  __device__ static __forceinline__ void arrive_mma(uint64_t* bar) {      // a worker warp (one lane) -> the MMA issuer
-    if constexpr (PAIR) sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(bar), 0)); else sm100::mbar_arrive(bar);
-  }
-  __device__ static __forceinline__ void arrive_both(uint64_t* bar) {     // the MMA issuer -> this barrier in every CTA of the group
-    if constexpr (PAIR) { sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(bar), 0)); sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(bar), 1)); }
-    else sm100::mbar_arrive(bar);
-  }
-  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    if constexpr (PAIR) sm100::umma_bf16_ss2(d, a, b, idesc, acc); else sm100::umma_bf16_ss(d, a, b, idesc, acc);
-  }
-  __device__ static __forceinline__ uint32_t rank() { if constexpr (PAIR) return sm100::cluster_ctarank(); else return 0; }
+  static constexpr uint32_t WORKER_ARRIVALS = EPI_WARPS;
+  __device__ static __forceinline__ void commit(uint64_t* bar) { sm100::umma_commit(bar); }
+  __device__ static __forceinline__ void arrive_mma(uint64_t* bar) { sm100::mbar_arrive(bar); }      // a worker warp (one lane) -> the MMA issuer
+  __device__ static __forceinline__ void arrive_both(uint64_t* bar) { sm100::mbar_arrive(bar); }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { sm100::umma_bf16_ss(d, a, b, idesc, acc); }
+  __device__ static __forceinline__ uint32_t rank() { return 0; }
 };
 
-template <bool PAIR>
 __device__ __forceinline__ void issue_slab_mmas_cg(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool first_slab) {
   const uint64_t a_desc = sm100::make_kmajor_sw128_desc(a_smem);
   const uint64_t b_desc = sm100::make_kmajor_sw128_desc(b_smem);
 #pragma unroll
-  for (uint32_t k = 0; k < BLOCK_K / 16; ++k) Cg<PAIR>::mma(tmem_d, a_desc + 2ull * k, b_desc + 2ull * k, idesc, (first_slab && k == 0) ? 0u : 1u);
+  for (uint32_t k = 0; k < BLOCK_K / 16; ++k) Cg::mma(tmem_d, a_desc + 2ull * k, b_desc + 2ull * k, idesc, (first_slab && k == 0) ? 0u : 1u);
 }
 
-template <bool PAIR>
 __device__ __forceinline__ void phase_barriers_init(uint8_t* smem) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS);
   const uint32_t lane = threadIdx.x & 31;
   if ((threadIdx.x >> 5) == 0) {
     for (uint32_t i = lane; i < PH_BARS_PER_SET; i += 32) {
-      const uint32_t W = Cg<PAIR>::WORKER_ARRIVALS;
+      const uint32_t W = Cg::WORKER_ARRIVALS;
       const uint32_t ca = (i == BA_A_READY || i == BA_ACCQ_FREE || i == BA_AO_READY) ? W : ((i == BA_X_EMPTY || i == BA_X_EMPTY + 1) ? XPASS_WARPS : 1);
       sm100::mbar_init(&bars[i], ca);
       const uint32_t cm = (i == BM_A_READY || i == BM_ACC1_FREE || i == BM_H_READY || i == BM_H_READY + 1) ? W
@@ -860,18 +847,17 @@ __device__ __forceinline__ void phase_barriers_init(uint8_t* smem) {
   }
 }
 
-// Weight-ring geometry of a phase.  Pair mode: every item is half as big (this CTA's half of the B rows), so the 96 KB ring
-// holds six 16 KB stages in both phases; buffers 4,5 carry no residual rows and take the items issued during setup.
-template <bool PAIR> struct MlpRing { static constexpr uint32_t NST = PAIR ? 6 : 3, STAGE = PAIR ? 16384 : 32768, FREE0 = PAIR ? 4 : 2, EARLY = PAIR ? 2 : 1; };
-template <bool PAIR> struct AttnRing { static constexpr uint32_t NST = PAIR ? 6 : 4, STAGE = PAIR ? 16384 : 24576, FREE0 = PAIR ? 4 : 3, EARLY = PAIR ? 2 : 1; };
+// Weight-ring geometry of a phase (96 KB ring).
+struct MlpRing { static constexpr uint32_t NST = 3, STAGE = 32768, FREE0 = 2, EARLY = 1; };
+struct AttnRing { static constexpr uint32_t NST = 4, STAGE = 24576, FREE0 = 3, EARLY = 1; };
 
 // One MLP half on the CTA's tile.  Entry: every thread of the CTA, previous phase complete (CTA-wide barrier passed),
 // TMEM allocated.  x_tma: the tile's rows are fetched by TMA (otherwise the previous phase stashed them).  STASH: leave
 // the updated rows in shared memory for the next phase.  Exit: CTA-wide barrier passed, all async work retired.
-template <bool STASH, bool PAIR>
+template <bool STASH>
 __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile, uint8_t* smem, uint32_t tmem_base, bool x_tma, PhaseSeq seq) {
-  using R = MlpRing<PAIR>;
-  using G = Cg<PAIR>;
+  using R = MlpRing;
+  using G = Cg;
   constexpr uint32_t NSTAGE = R::NST;
   uint8_t* smA = smem;                                     // 4 x 16 KB (later: epilogue staging)
   uint8_t* smH = smem + PH_OFF_MID;                        // 2 x (2 x 16 KB); first the X pass buffers / stash
@@ -879,7 +865,6 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS) + PH_BARS_PER_SET;
   uint64_t* full = bars + BI_FULL;
   uint64_t* empty = bars + BI_EMPTY;
-  uint64_t* pfull = bars + BI_PFULL;
   uint64_t* a_ready = bars + BM_A_READY;
   uint64_t* acc1_full = bars + BM_ACC1_FULL;
   uint64_t* acc1_free = bars + BM_ACC1_FREE;
@@ -942,7 +927,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
   } else if (warp == 1) {
     if (lane == 0 && G::rank() == 0) {
       // ===================== MMA issuer (pair mode: the leader CTA, for both CTAs) ==========
-      const uint32_t idesc = sm100::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+      const uint32_t idesc = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
       const uint32_t acc1 = tmem_base, acc2 = tmem_base + BLOCK_N;
       dbg_stamp(p.dbg, 1);
       sm100::mbar_wait(a_ready, po);
@@ -951,7 +936,6 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
       RingState rs;
       auto wait_stage = [&]() {
         sm100::mbar_wait(&full[rs.stage], rs.phase);
-        if constexpr (PAIR) sm100::mbar_wait(&pfull[rs.stage], rs.phase);
         sm100::tc_fence_after();
       };
       for (int j = 0; j <= T; ++j) {
@@ -959,7 +943,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
           if (j > 0 && !(p.exp & 1)) { sm100::mbar_wait(acc1_free, ((j - 1) & 1) ^ pt); sm100::tc_fence_after(); }
           for (int ks = 0; ks < KSLABS_D; ++ks) {
             wait_stage();
-            issue_slab_mmas_cg<PAIR>(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc, ks == 0);
+            issue_slab_mmas_cg(acc1, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc, ks == 0);
             G::commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
           }
@@ -975,7 +959,7 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
           const int ns = m2_slabs(c);
           for (int s2 = 0; s2 < ns; ++s2) {
             wait_stage();
-            issue_slab_mmas_cg<PAIR>(acc2, sm100::smem_u32(smH + (b * 2 + s2) * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc,
+            issue_slab_mmas_cg(acc2, sm100::smem_u32(smH + (b * 2 + s2) * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc,
                                      c == 0 && s2 == 0);
             G::commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
@@ -987,14 +971,6 @@ __device__ __forceinline__ void mlp_phase(const MlpFusedParams& p, int row_tile,
       for (int i = total; i < padded; ++i) {   // consume the hand-made ring completions
         wait_stage();
         G::arrive_both(&empty[rs.stage]);
-        rs.advance(NSTAGE);
-      }
-    } else if (PAIR && lane == 0) {
-      // ===================== pair mode, second CTA: tell the leader when this CTA's half of a stage has landed ====
-      RingState rs;
-      for (int i = 0; i < padded; ++i) {
-        sm100::mbar_wait(&full[rs.stage], rs.phase);
-        sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(&pfull[rs.stage]), 0));
         rs.advance(NSTAGE);
       }
     }
@@ -1067,14 +1043,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const MlpFuse
   if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
   if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
-  phase_barriers_init<false>(smem);
+  phase_barriers_init(smem);
   sm100::grid_dep_launch();
   sm100::grid_dep_wait();   // X and the modulation table come from the preceding kernels
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  mlp_phase<false, false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
+  mlp_phase<false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
   if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
 }
 
@@ -1270,12 +1246,12 @@ constexpr int AB_P_ITEM_BYTES = 128 * BLOCK_K * 2;      // 16 KB
 constexpr size_t attn_block_smem_bytes() { return phase_smem_bytes(); }
 
 // One attention half on the CTA's tile; same entry / exit contract as mlp_phase.
-template <bool STASH, bool PAIR>
+template <bool STASH>
 __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_tile, uint8_t* smem, uint32_t tmem_base, bool x_tma, PhaseSeq seq) {
-  using R = AttnRing<PAIR>;
-  using G = Cg<PAIR>;
+  using R = AttnRing;
+  using G = Cg;
   constexpr uint32_t NSTAGE = R::NST;
-  constexpr uint32_t Q_BYTES = AB_Q_ITEM_BYTES / (PAIR ? 2 : 1), P_BYTES = AB_P_ITEM_BYTES / (PAIR ? 2 : 1);   // this CTA's share of an item
+  constexpr uint32_t Q_BYTES = AB_Q_ITEM_BYTES, P_BYTES = AB_P_ITEM_BYTES;   // this CTA's share of an item
   constexpr int N_ITEMS = AB_HP * (KSLABS_D + 2);
   static_assert(N_ITEMS % NSTAGE == 0 && ((N_ITEMS / NSTAGE) & 1) == 0, "every ring barrier must complete an even number of times per phase");
   uint8_t* smA = smem;
@@ -1288,7 +1264,6 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PH_OFF_BARS);
   uint64_t* full = bars + BI_FULL;
   uint64_t* empty = bars + BI_EMPTY;
-  uint64_t* pfull = bars + BI_PFULL;
   uint64_t* a_ready = bars + BA_A_READY;
   uint64_t* accq_full = bars + BA_ACCQ_FULL;
   uint64_t* accq_free = bars + BA_ACCQ_FREE;
@@ -1349,8 +1324,8 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
   } else if (warp == 1) {
     if (lane == 0 && G::rank() == 0) {
       // ===================== MMA issuer (pair mode: the leader CTA, for both CTAs) ==========
-      const uint32_t idesc_q = sm100::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, AB_QN);
-      const uint32_t idesc_p = sm100::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, 128);
+      const uint32_t idesc_q = sm100::make_idesc_bf16(BLOCK_M, AB_QN);
+      const uint32_t idesc_p = sm100::make_idesc_bf16(BLOCK_M, 128);
       const uint32_t accq = tmem_base, accp = tmem_base + 256;
       dbg_stamp(p.dbg, 1);
       sm100::mbar_wait(a_ready, po);
@@ -1359,7 +1334,6 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
       RingState rs;
       auto wait_stage = [&]() {
         sm100::mbar_wait(&full[rs.stage], rs.phase);
-        if constexpr (PAIR) sm100::mbar_wait(&pfull[rs.stage], rs.phase);
         sm100::tc_fence_after();
       };
       for (int step = 0; step <= AB_HP; ++step) {
@@ -1367,7 +1341,7 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
           if (step > 0) { sm100::mbar_wait(accq_free, (step - 1) & 1); sm100::tc_fence_after(); }
           for (int ks = 0; ks < KSLABS_D; ++ks) {
             wait_stage();
-            issue_slab_mmas_cg<PAIR>(accq, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc_q, ks == 0);
+            issue_slab_mmas_cg(accq, sm100::smem_u32(smA + ks * A_SLAB_BYTES), sm100::smem_u32(ring_ptr(rs.stage)), idesc_q, ks == 0);
             G::commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
           }
@@ -1379,7 +1353,7 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
           sm100::tc_fence_after();
           for (int half = 0; half < 2; ++half) {
             wait_stage();
-            issue_slab_mmas_cg<PAIR>(accp + half * 128, sm100::smem_u32(smAO), sm100::smem_u32(ring_ptr(rs.stage)), idesc_p, hp == 0);
+            issue_slab_mmas_cg(accp + half * 128, sm100::smem_u32(smAO), sm100::smem_u32(ring_ptr(rs.stage)), idesc_p, hp == 0);
             G::commit(&empty[rs.stage]);
             rs.advance(NSTAGE);
           }
@@ -1387,14 +1361,6 @@ __device__ __forceinline__ void attn_phase(const AttnBlockParams& p, int row_til
         }
       }
       G::commit(accp_full);
-    } else if (PAIR && lane == 0) {
-      // ===================== pair mode, second CTA: tell the leader when this CTA's half of a stage has landed ====
-      RingState rs;
-      for (int i = 0; i < N_ITEMS; ++i) {
-        sm100::mbar_wait(&full[rs.stage], rs.phase);
-        sm100::mbar_arrive_remote(sm100::mapa(sm100::smem_u32(&pfull[rs.stage]), 0));
-        rs.advance(NSTAGE);
-      }
     }
   } else {
     // ===================== 16 worker warps ==================================================
@@ -1487,14 +1453,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_block_kernel(const AttnBl
   if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
   if ((threadIdx.x >> 5) == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
-  phase_barriers_init<false>(smem);
+  phase_barriers_init(smem);
   sm100::grid_dep_launch();
   sm100::grid_dep_wait();   // X and the modulation table come from the preceding kernels
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  attn_phase<false, false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
+  attn_phase<false>(p, blockIdx.x, smem, tmem_base, true, PhaseSeq{0, 0});
   if ((threadIdx.x >> 5) == 1) sm100::tmem_dealloc(tmem_base, 512);
 }
 
@@ -1514,28 +1480,25 @@ struct BlocksParams {
   int stagger_cycles;                      // CTA b starts (b % 8) * stagger_cycles late: see dit_blocks_kernel
 };
 
-// PAIR: launched as clusters of two CTAs (cudaLaunchAttributeClusterDimension = 2); the pair works on two adjacent tiles
-// with cta_group::2 MMAs, so every weight slab is fetched once per pair (half per SM).  Needs an even number of tiles.
-template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const BlocksParams bp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (threadIdx.x == 0 && (sm100::smem_u32(smem) & 1023u) != 0) __trap();
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + PH_OFF_TMEMPTR);
   if ((threadIdx.x >> 5) == 1) {
-    if constexpr (PAIR) sm100::tmem_alloc2(tmem_ptr_smem, 512); else sm100::tmem_alloc(tmem_ptr_smem, 512);
+    sm100::tmem_alloc(tmem_ptr_smem, 512);
   }
-  phase_barriers_init<PAIR>(smem);
+  phase_barriers_init(smem);
   sm100::grid_dep_launch();
   sm100::grid_dep_wait();
   sm100::tc_fence_before();
-  if constexpr (PAIR) sm100::cluster_sync_all(); else __syncthreads();   // barriers of both CTAs exist before any remote arrive
+  __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Every tile costs the same, so CTAs launched together would stay in lock-step and hit the L2-bound stretches at the same
   // moment on all SMs.  An optional one-off start offset per CTA (pair) keeps them out of phase for the rest of the kernel.
-  const int group = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, n_groups = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int per_group = PAIR ? 2 : 1, rank = (int)Cg<PAIR>::rank();
+  const int group = (int)blockIdx.x, n_groups = (int)gridDim.x;
+  constexpr int per_group = 1, rank = 0;
   if (bp.stagger_cycles > 0) {
     if (threadIdx.x == 0) {
       const long long t0 = clock64(), d = (long long)(group & 7) * bp.stagger_cycles;
@@ -1563,7 +1526,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const Blocks
       ap.mod_off_mul += l * 6 * D; ap.mod_off_add += l * 6 * D; ap.mod_off_gate += l * 6 * D;
       const bool dbg_on = bp.dbg != nullptr && l == bp.dbg_layer && t0 == (group + n_groups) * per_group;
       ap.dbg = dbg_on ? bp.dbg : nullptr;
-      attn_phase<true, PAIR>(ap, tile, smem, tmem_base, l == 0, PhaseSeq{n_attn & 1, n_tma & 1});
+      attn_phase<true>(ap, tile, smem, tmem_base, l == 0, PhaseSeq{n_attn & 1, n_tma & 1});
       ++n_attn;
       if (l == 0) ++n_tma;
       MlpFusedParams mp = bp.mlp;
@@ -1571,14 +1534,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dit_blocks_kernel(const Blocks
       mp.Wstream += (size_t)l * bp.mlp_w_stride;
       mp.mod_off_mul += l * 6 * D; mp.mod_off_add += l * 6 * D; mp.mod_off_gate += l * 6 * D;
       mp.dbg = dbg_on ? bp.dbg + 2 * (1 << 17) : nullptr;
-      if (l + 1 < bp.n_layer) mlp_phase<true, PAIR>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
-      else mlp_phase<false, PAIR>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
+      if (l + 1 < bp.n_layer) mlp_phase<true>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
+      else mlp_phase<false>(mp, tile, smem, tmem_base, false, PhaseSeq{n_mlp & 1, 0});
       ++n_mlp;
     }
   }
-  if constexpr (PAIR) sm100::cluster_sync_all();   // the peer's tensor core may still be reading this CTA's shared memory
   if ((threadIdx.x >> 5) == 1) {
-    if constexpr (PAIR) sm100::tmem_dealloc2(tmem_base, 512); else sm100::tmem_dealloc(tmem_base, 512);
+    sm100::tmem_dealloc(tmem_base, 512);
   }
 }
 

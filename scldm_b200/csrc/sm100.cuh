@@ -154,54 +154,6 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       : "memory");
 }
 
-// ------------------------------------------------------------------------------------------
-// CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC execute ONE tcgen05.mma with M = 256.  Each
-// CTA owns 128 rows of A and of the accumulator (its own shared memory / TMEM) and HALF of the B rows, so a weight ring of
-// a given size covers twice as many K steps and each SM pulls half the weight bytes from L2.  Only the leader (cluster
-// rank 0) issues MMAs; completion is multicast to the mbarriers of both CTAs.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {   // every thread of both CTAs
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local` (a shared::cta address of this CTA's layout) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");   // default .release.cta, as CUTLASS
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {  // whole warp, in both CTAs
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {  // whole warp
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// arrives on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ss2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B, one 64-element (128 B) K slab:
 //   start address >> 4 | LBO (ignored for swizzled K-major, 1) | SBO = 1024 B (8-row group stride)
 //   | version = 1 (sm_100) | layout_type = 2 (SWIZZLE_128B)

@@ -219,7 +219,7 @@ class DiT(nn.Module):
             # all rows share t, so the adaLN vectors depend on the label combination only: row 0 = unconditional, then
             # one row per distinct combination (14 for the dentate clusters instead of one per cell and pass)
             cols = torch.cat([self._cls_rows(p, half, device) for p in passes], 1)       # [n_class, n_c*half], pass-major
-            uniq, inv = torch.unique(cols, dim=1, return_inverse=True)
+            uniq, inv = self._label_combinations(cols)
             cls_idx = torch.cat([null_rows(1), uniq.to(torch.int32)], 1)
             slot_u = torch.zeros(half, dtype=torch.int32, device=device)
             slot_g = torch.zeros(half, n_f, dtype=torch.int32, device=device)
@@ -245,6 +245,32 @@ class DiT(nn.Module):
             t_index = torch.cat([ar, (half + ar).repeat_interleave(n_f)]).long()
         slot_mod = torch.cat([slot_u, slot_g.reshape(-1)])
         return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index, slot_mode=slot_mode)
+
+    def _label_combinations(self, cols: torch.Tensor):
+        """Distinct columns of `cols` [n_class, n] (embedding rows per class, null = vocab size) and the column -> combination map.
+        Small label spaces (prod (V_c + 1) <= 256: dentate_gyrus 15, tabula_muris 17, hlca 51) are enumerated in
+        mixed radix on the device - no `torch.unique`, hence no host synchronisation while a plan is built; larger ones use
+        `torch.unique` (one sync)."""
+        names = sorted(self.class_vocab_sizes.keys())
+        radix = [self.class_vocab_sizes[n] + 1 for n in names]
+        total = 1
+        for r in radix:
+            total *= r
+        if cols.shape[0] == 0 or total > 256:
+            return torch.unique(cols, dim=1, return_inverse=True)
+        key = (tuple(radix), str(cols.device))
+        if getattr(self, "_combo_cache_key", None) != key:
+            ids = torch.arange(total, device=cols.device)
+            table, div = [], 1
+            for r in radix:
+                table.append((ids // div) % r)
+                div *= r
+            self._combo_table, self._combo_cache_key = torch.stack(table).to(torch.int32), key
+        inv, div = torch.zeros(cols.shape[1], dtype=torch.int64, device=cols.device), 1
+        for c, r in enumerate(radix):
+            inv = inv + cols[c].long() * div
+            div *= r
+        return self._combo_table, inv
 
     def forward_plan(self, condition: dict[str, torch.Tensor] | None, n: int, device):
         """Evaluation plan of a plain conditional `forward(x, t, condition, force_drop_ids=False)` on n cells that all share the

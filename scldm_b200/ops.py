@@ -441,5 +441,14 @@ def prof_summary() -> dict[str, tuple[int, float]]:
     return out
 
 
+def set_option(name: str, value: int) -> None:
+    """Runtime switch of the library (`scldm_set_option`): "mega", "pdl", "mod_batch", "exp", "dec_cpb", "dec_occ"."""
+    _lib.check(_lib.load().scldm_set_option(name.encode(), int(value)), "scldm_set_option")
+
+
+def get_option(name: str) -> int:
+    return int(_lib.load().scldm_get_option(name.encode()))
+
+
 def launch_count() -> int:
     return int(_lib.load().scldm_launch_count())

@@ -568,3 +568,36 @@ def test_unconditional_sample_without_labels():
     assert rel_l2(z, z_o) < 5e-3, rel_l2(z, z_o)
     with pytest.raises(ValueError):
         ldm.sample(None, None, B, genes[:2])                                           # genes batch dimension must match (models.py:777)
+
+
+def test_torch_library_ops_run_the_same_kernels():
+    """`torch.ops.scldm_b200.vae_decode / vae_encode / dit_sample_ode` (scldm_b200/torch_ops.py) return exactly what the Python API does."""
+    from scldm_b200 import ops, torch_ops
+    from scldm_b200.nnets import DiT
+
+    cfg = VAEConfig(n_genes=500, n_layer=2)
+    vae, _ = make_vae(cfg)
+    B = 6
+    z = synthetic.randn("to.z", (B, 16, 16)).cuda()
+    lib = torch.full((B,), 2000.0).cuda()
+    genes = torch.arange(1, 501).cuda()
+    hd = torch_ops.register(vae.packed_decoder())
+    mu, theta, counts = torch.ops.scldm_b200.vae_decode(z, genes, lib, 7, 0, hd)
+    mu2, theta2, counts2 = ops.vae_decode(vae.packed_decoder(), z, genes, lib, want_mu=True, want_counts=True, seed=7, cell_offset=0)
+    assert torch.equal(mu, mu2) and torch.equal(theta, theta2) and torch.equal(counts, counts2)
+    gs = torch.randint(1, 501, (B, 64), generator=torch.Generator().manual_seed(1)).cuda()
+    cs = torch.ones(B, 64).cuda()
+    he = torch_ops.register(vae.packed_encoder())
+    assert torch.equal(torch.ops.scldm_b200.vae_encode(gs, cs, he), vae.encode(None, None, cs, gs))
+    dcfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=2)
+    dit = DiT(**dcfg.kwargs())
+    dit.load_state_dict(synthetic.dit_state_dict(dcfg, WEIGHT_SEED))
+    dit = dit.cuda().eval()
+    lab = {"clusters": synthetic.randint("to.lab", 14, (2 * B,)).cuda()}
+    plan, _ = dit.cfg_plan(lab, {"clusters": 2.0}, B, torch.device("cuda"), shared_time=True)
+    hp = torch_ops.register(plan)
+    x = torch.cat([z, z])
+    grid = torch.linspace(0, 1, 6)
+    assert torch.equal(torch.ops.scldm_b200.dit_sample_ode(x, grid, "euler", hp), ops.dit_sample_ode(plan, x.clone(), grid, "euler"))
+    assert ops.get_option("mega") == 1 and ops.get_option("nonexistent") == -1
+    torch_ops.release(hd), torch_ops.release(he), torch_ops.release(hp)

@@ -12,8 +12,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "one_kernel_per_block_half": {"SCLDM_MEGA": "0"},
     "unfused_no_pdl": {"SCLDM_MEGA": "0", "SCLDM_FUSED_ATTN": "0", "SCLDM_FUSED_MLP": "0", "SCLDM_TC_FINAL": "0", "SCLDM_PDL": "0"},
-    # CTA pairs (cta_group::2 MMAs, every weight slab split over the two SMs of a cluster); used when the tile count is even
-    "cta_pairs": {"SCLDM_PAIR": "1"},
 }
 
 
