@@ -129,6 +129,7 @@ def kernel_flops(name: str, rows: int, mod_rows: int) -> float | None:
         "mlp_fused": 2.0 * rows * D * 2 * H + 2.0 * rows * H * D,
         "attn_block": 2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D,
         "dit_blocks": 8 * (2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D + 2.0 * rows * D * 2 * H + 2.0 * rows * H * D),
+        "dit_stack": 8 * (2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D + 2.0 * rows * D * 2 * H + 2.0 * rows * H * D),
     }.get(name)
 
 

@@ -11,6 +11,7 @@
 
 #include "../../include/scldm_b200.h"
 #include "dit_kernels.cuh"
+#include "dit_stack.cuh"
 #include "vae_kernels.cuh"
 #include "csr_kernels.cuh"
 #include "train_kernels.cuh"
@@ -45,7 +46,7 @@ std::vector<cudaEvent_t> g_prof_pool;
 bool g_prof_on = false;
 // Runtime options (scldm_set_option / scldm_get_option).  The SCLDM_* environment variables only provide the initial values.
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-int g_opt_mega = env_int("SCLDM_MEGA", 1);            // 1: the whole block stack of an evaluation is one persistent kernel; 0: one kernel per block half
+int g_opt_mega = env_int("SCLDM_MEGA", 2);            // 2: dit_stack_kernel (fused residual / LayerNorm boundaries, blocked residual layout); 1: dit_blocks_kernel; 0: one kernel per block half
 int g_num_sms = 148;
 // dit_blocks_kernel micro-variants (bit mask): 1 = hand the MLP accumulator over before M2 is queued (measured slower: 971 vs 942 us),
 // 2 = no setup barrier in phases whose rows come from the stash (927 vs 942 us), 4 = butterfly LayerNorm reductions (937 vs 942 us)
@@ -120,6 +121,11 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// CTA-private blocked storage of dit_stack_kernel when its input / output is row-major (one 128 x 256 fp32 tile per CTA)
+inline size_t stack_scratch_bytes(size_t rows16) {
+  const size_t tiles = (rows16 + 127) / 128;
+  return (tiles < 160 ? tiles : 160) * (size_t)(128 * 256 * 4);
+}
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 struct DitWs {
@@ -233,11 +239,31 @@ dit::ModIndex mod_index(const scldm_dit_plan* plan) {
   return mi;
 }
 
+// dit_stack_kernel needs the fused weight streams; with it the residual stream is tile-blocked (x_index)
+bool use_stack(const scldm_dit_weights* w) {
+  return g_opt_mega == 2 && w->w_attn_stream != nullptr && w->b_proj_fused != nullptr && w->w_mlp_stream != nullptr;
+}
+
 // the n_layer adaLN blocks on the residual stream ws.X (reference layers.py:208-221)
-int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, cudaStream_t st) {
+// `rowmajor_scratch` (dit_stack_kernel only): ws.X is row-major and this buffer (scldm_stack_scratch_bytes) holds the blocked interior
+int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, cudaStream_t st, float* rowmajor_scratch = nullptr) {
   const int slots_pad = scldm_dit_slots_pad(plan);
   const int row_tiles = slots_pad * dit::TOK / dit::BLOCK_M;
   const size_t tile_elems = (size_t)dit::KSLABS_D * dit::B_SLAB_ELEMS;
+  if (use_stack(w)) {
+    dit::StackParams sp{};
+    sp.X = ws.X; sp.mod = ws.mod; sp.slot_mod = mod_index(plan); sp.mod_stride = w->mod_stride; sp.eps = w->eps;
+    sp.w_attn = static_cast<const dit::bf16*>(w->w_attn_stream); sp.attn_w_stride = 4LL * dit::D * dit::D;
+    sp.w_mlp = static_cast<const dit::bf16*>(w->w_mlp_stream);
+    sp.mlp_w_stride = ((long long)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs) * dit::B_SLAB_ELEMS;
+    sp.bias_q = w->b_qkv; sp.bias_proj = w->b_proj_fused;
+    sp.n_layer = w->n_layer; sp.n_tiles = row_tiles; sp.n_chunks = w->mlp1_tiles; sp.hid_slabs = w->hid_slabs;
+    sp.dbg = g_dbg_clk; sp.dbg_layer = g_dbg_layer;
+    sp.io_blocked = rowmajor_scratch == nullptr; sp.scratch = rowmajor_scratch;
+    const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
+    LAUNCH("dit_stack", launch_pdl(dit::dit_stack_kernel, dim3(grid), dim3(dit::S2_THREADS), dit::stack_smem_bytes(), st, sp));
+    return SCLDM_OK;
+  }
   if (g_use_mega && w->w_attn_stream != nullptr && w->b_proj_fused != nullptr && w->w_mlp_stream != nullptr) {
     // the whole block stack as one persistent kernel (one CTA per SM, tiles walk through all layers without grid syncs)
     dit::BlocksParams bp{};
@@ -342,6 +368,7 @@ dit::StepParams make_step(const scldm_dit_weights* w, const scldm_dit_plan* plan
   s.n_u = plan->n_u; s.n_g = plan->n_g; s.n_f = plan->n_g > 0 ? plan->n_f : 1;
   for (int i = 0; i < SCLDM_MAX_COMBINE; ++i) s.coef[i] = plan->coef[i];
   s.acc = ws.acc;
+  s.x_blocked = use_stack(w) ? 1 : 0;
   return s;
 }
 
@@ -372,6 +399,7 @@ int prepare_kernels() {
   if ((rc = set_smem(dit::mlp_fused_kernel, dit::mlp_fused_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::attn_block_kernel, dit::attn_block_smem_bytes()))) return rc;
   if ((rc = set_smem(dit::dit_blocks_kernel, dit::phase_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::dit_stack_kernel, dit::stack_smem_bytes()))) return rc;
   {
     int n = 0;
     CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));

@@ -40,6 +40,13 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;            // 512
 constexpr int NUM_THREADS = 64 + EPI_THREADS;          // warp0 TMA, warp1 MMA, warps 2-17 prologue/epilogue
 constexpr int MAX_COMBINE = 8;
 
+// Element (row, col) of the residual stream.  blocked = 0: row-major [rows][256].  blocked = 1: the tile-blocked layout of
+// dit_stack_kernel (dit_stack.cuh): X[tile = row / 128][c4 = col / 4][row % 128][4 floats].
+__host__ __device__ __forceinline__ size_t x_index(size_t row, int col, int blocked) {
+  if (!blocked) return row * (size_t)D + col;
+  return (row >> 7) * (size_t)(BLOCK_M * D) + ((((size_t)(col >> 2)) * BLOCK_M + (row & 127)) << 2) + (size_t)(col & 3);
+}
+
 enum { PRO_LN = 0, PRO_COND = 1 };
 enum { EPI_QKV = 0, EPI_SWIGLU = 1, EPI_MOD = 2 };
 
@@ -1626,6 +1633,7 @@ struct StepParams {
   int first_stage, last_stage;
   int do_update;          // 0: only v_out
   int do_inproj;          // project x_eval for the next evaluation
+  int x_blocked;          // layout of X (x_index)
 };
 
 __device__ __forceinline__ void state_slots(const StepParams& p, int state, int& slot0, int& nslots) {
@@ -1649,7 +1657,7 @@ __global__ void __launch_bounds__(256) inproj_kernel(const StepParams p) {
     float acc = b + p.pos[tk * D + d];
 #pragma unroll
     for (int o = 0; o < LAT; ++o) acc += xs[tk * LAT + o] * w[o];
-    for (int k = 0; k < ns; ++k) p.X[((size_t)(slot0 + k) * TOK + tk) * D + d] = acc;
+    for (int k = 0; k < ns; ++k) p.X[x_index((size_t)(slot0 + k) * TOK + tk, d, p.x_blocked)] = acc;
   }
 }
 
@@ -1675,9 +1683,8 @@ __global__ void __launch_bounds__(512) final_step_kernel(const StepParams p, int
 #pragma unroll 1
     for (int k = 0; k < ns; ++k) {
       const int slot = slot0 + k;
-      const float* xr = p.X + ((size_t)slot * TOK + tk) * D + lane * 8;
-      const float4 x0 = *reinterpret_cast<const float4*>(xr);
-      const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(p.X + x_index((size_t)slot * TOK + tk, lane * 8, p.x_blocked));
+      const float4 x1 = *reinterpret_cast<const float4*>(p.X + x_index((size_t)slot * TOK + tk, lane * 8 + 4, p.x_blocked));
       const float* mrow = p.mod + (size_t)p.slot_mod.row(slot) * p.mod_stride + p.mod_off_final + lane * 8;
       const float4 sh0 = *reinterpret_cast<const float4*>(mrow), sh1 = *reinterpret_cast<const float4*>(mrow + 4);
       const float4 sc0 = *reinterpret_cast<const float4*>(mrow + D), sc1 = *reinterpret_cast<const float4*>(mrow + D + 4);
@@ -1750,9 +1757,8 @@ __global__ void __launch_bounds__(512) final_step_kernel(const StepParams p, int
         h[4] += xo * w1.x; h[5] += xo * w1.y; h[6] += xo * w1.z; h[7] += xo * w1.w;
       }
       for (int k = 0; k < ns; ++k) {
-        float* dst = p.X + ((size_t)(slot0 + k) * TOK + tk) * D + lane * 8;
-        *reinterpret_cast<float4*>(dst) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<float4*>(p.X + x_index((size_t)(slot0 + k) * TOK + tk, lane * 8, p.x_blocked)) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(p.X + x_index((size_t)(slot0 + k) * TOK + tk, lane * 8 + 4, p.x_blocked)) = make_float4(h[4], h[5], h[6], h[7]);
       }
     }
   }
@@ -1802,15 +1808,16 @@ __global__ void __launch_bounds__(128) final_step_tc_kernel(const StepParams p, 
 #pragma unroll 1
   for (int k = 0; k < ns; ++k) {
     const int slot = slot0 + k;
-    const float* x0p = p.X + ((size_t)slot * TOK + g) * D + 2 * t;   // row g
-    const float* x1p = x0p + 8 * D;                                  // row g+8
+    // element (row g, col 2t) of the slot; a step of 8 rows / 8 columns is a fixed stride in either layout
+    const float* x0p = p.X + x_index((size_t)slot * TOK + g, 2 * t, p.x_blocked);
+    const int rs8 = p.x_blocked ? 8 * 4 : 8 * D, cs8 = p.x_blocked ? 2 * BLOCK_M * 4 : 8;
     float2 xa[16][4];   // [ks]{(g, 2t), (g+8, 2t), (g, 2t+8), (g+8, 2t+8)}
 #pragma unroll
     for (int ks = 0; ks < 16; ++ks) {
-      xa[ks][0] = *reinterpret_cast<const float2*>(x0p + 16 * ks);
-      xa[ks][1] = *reinterpret_cast<const float2*>(x1p + 16 * ks);
-      xa[ks][2] = *reinterpret_cast<const float2*>(x0p + 16 * ks + 8);
-      xa[ks][3] = *reinterpret_cast<const float2*>(x1p + 16 * ks + 8);
+      xa[ks][0] = *reinterpret_cast<const float2*>(x0p + 2 * ks * cs8);
+      xa[ks][1] = *reinterpret_cast<const float2*>(x0p + 2 * ks * cs8 + rs8);
+      xa[ks][2] = *reinterpret_cast<const float2*>(x0p + (2 * ks + 1) * cs8);
+      xa[ks][3] = *reinterpret_cast<const float2*>(x0p + (2 * ks + 1) * cs8 + rs8);
     }
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -1902,9 +1909,9 @@ __global__ void __launch_bounds__(128) final_step_tc_kernel(const StepParams p, 
     mma_bf16_f(c, ah[0], ah[1], ah[2], ah[3], b.x, b.y);
     mma_bf16_f(c, al[0], al[1], al[2], al[3], b.x, b.y);
     for (int k = 0; k < ns; ++k) {
-      float* dst = p.X + ((size_t)(slot0 + k) * TOK + g) * D + 8 * nt + 2 * t;
+      float* dst = p.X + x_index((size_t)(slot0 + k) * TOK + g, 8 * nt + 2 * t, p.x_blocked);
       *reinterpret_cast<float2*>(dst) = make_float2(c[0], c[1]);
-      *reinterpret_cast<float2*>(dst + 8 * D) = make_float2(c[2], c[3]);
+      *reinterpret_cast<float2*>(dst + (p.x_blocked ? 8 * 4 : 8 * D)) = make_float2(c[2], c[3]);
     }
   }
 }

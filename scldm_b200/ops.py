@@ -183,8 +183,12 @@ def dit_workspace_views(plan: DitPlan, ws: torch.Tensor, n_evals: int = 0) -> di
     def view(off, nbytes, dtype, shape):
         return ws[off: off + nbytes].view(dtype).view(*shape)
 
+    X = view(o["X"], rows * 256 * 4, torch.float32, (rows, 256))
+    if get_option("mega") == 2 and w.use_fused_attn and w.use_fused_mlp:
+        # dit_stack_kernel keeps the residual stream tile-blocked: [tile][col / 4][row % 128][4] (csrc/dit_kernels.cuh: x_index)
+        X = X.view(rows // 128, 64, 128, 4).permute(0, 2, 1, 3).reshape(rows, 256)
     return {
-        "X": view(o["X"], rows * 256 * 4, torch.float32, (rows, 256)),
+        "X": X,
         "qkv": view(o["qkv"], rows * 768 * 2, torch.bfloat16, (rows // 128, 12, 128 * 64)),
         "ao": view(o["ao"], rows * 256 * 2, torch.bfloat16, (rows // 128, 4, 128 * 64)),
         "hid": view(o["hid"], (rows // 128) * w.hid_slabs * 16384, torch.bfloat16, (rows // 128, w.hid_slabs, 128 * 64)),

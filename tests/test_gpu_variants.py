@@ -10,6 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 VARIANTS = {
+    "first_generation_block_stack_kernel": {"SCLDM_MEGA": "1"},
     "one_kernel_per_block_half": {"SCLDM_MEGA": "0"},
     "unfused_no_pdl": {"SCLDM_MEGA": "0", "SCLDM_FUSED_ATTN": "0", "SCLDM_FUSED_MLP": "0", "SCLDM_TC_FINAL": "0", "SCLDM_PDL": "0"},
 }
