@@ -78,9 +78,10 @@ constexpr int S2_STAGE = 32768;
 constexpr int S2_OFF_MID = KSLABS_D * A_SLAB_BYTES;             // 64 KB: q|k|v + AO slabs / H buffers / boundary park
 constexpr int S2_OFF_RING = S2_OFF_MID + 4 * A_SLAB_BYTES;      // 128 KB
 constexpr int S2_OFF_BIASQ = S2_OFF_RING + S2_NST * S2_STAGE;   // 224 KB
-constexpr int S2_OFF_BARS = S2_OFF_BIASQ + D * 4;
+constexpr int S2_OFF_BIASP = S2_OFF_BIASQ + D * 4;             // c_proj bias of the attention half (boundary pass 1)
+constexpr int S2_OFF_BARS = S2_OFF_BIASP + D * 4;
 enum { SB_FULL = 0, SB_EMPTY = 3, SB_A_READY = 6, SB_ACCA_FULL = 7, SB_ACCA_FREE = 8, SB_AO_READY = 9, SB_AO_FREE = 10,
-       SB_H_READY = 11, SB_H_FREE = 13, SB_ACCB_FULL = 15, SB_PARK_READY = 16, SB_PARK_DRAINED = 17, SB_COUNT = 18 };
+       SB_H_READY = 11, SB_H_FREE = 13, SB_ACCB_FULL = 15, SB_PARK_READY = 16, SB_PARK_DRAINED = 17, SB_XFULL = 18, SB_COUNT = 19 };
 constexpr int S2_WARPS = 24, S2_THREADS = S2_WARPS * 32, S2_WORKER_WARP0 = 8, S2_DRAIN_WARP0 = 4;
 constexpr int S2_REGS_LAUNCH = 80, S2_REGS_IDLE = 56, S2_REGS_DRAIN = 40, S2_REGS_WORKER = 96;
 static_assert(S2_THREADS * S2_REGS_LAUNCH >= 128 * S2_REGS_IDLE + 128 * S2_REGS_DRAIN + 512 * S2_REGS_WORKER, "setmaxnreg budget");
@@ -91,7 +92,7 @@ constexpr int S2_OFF_ROWS = S2_OFF_TMEMPTR + 16;
 constexpr size_t stack_smem_bytes() { return S2_OFF_ROWS + 8 * 4 + 16; }
 static_assert(stack_smem_bytes() <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 // boundary park (inside the mid region): per-slot vectors of the tile's 8 slots + the LayerNorm partials
-constexpr int PK_GATE = 0, PK_MUL = 8192, PK_ADD = 16384, PK_EXCH = 24576, PK_BIAS = 32768;
+constexpr int PK_GATE = 0, PK_MUL = 8192, PK_ADD = 16384, PK_EXCH = 24576;   // 32 KB = one H buffer
 
 enum { B_FIRST = 0, B_MID = 1, B_LAST = 2 };
 
@@ -105,6 +106,8 @@ struct BoundaryArgs {
   const float* bias;     // c_proj bias of the finishing phase (attention half) or unused
   int off_mul, off_add;  // LayerNorm modulation of the starting phase                  (B_FIRST, B_MID)
   float eps;
+  const float* next_bias_q;   // q bias of the attention half that starts after this boundary (nullptr: an MLP half starts)
+  float* sm_bias_q;
 };
 
 struct BoundarySync {
@@ -150,7 +153,10 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
     *reinterpret_cast<float4*>(park + PK_MUL + etid * 16) = make_float4(1.f + mul_v.x, 1.f + mul_v.y, 1.f + mul_v.z, 1.f + mul_v.w);
     *reinterpret_cast<float4*>(park + PK_ADD + etid * 16) = add_v;
   }
-  if constexpr (HAS_BIAS) { if (etid < 64) *reinterpret_cast<float4*>(park + PK_BIAS + etid * 16) = bias_v; }
+  if constexpr (HAS_BIAS) { if (etid < 64) *reinterpret_cast<float4*>(smem + S2_OFF_BIASP + etid * 16) = bias_v; }
+  if constexpr (KIND != B_LAST) {
+    if (b.next_bias_q != nullptr && etid < 64) reinterpret_cast<float4*>(b.sm_bias_q)[etid] = *reinterpret_cast<const float4*>(b.next_bias_q + etid * 4);
+  }
   const uint32_t taddrA = tmem_base + ((q * 32u) << 16) + sub * 64;   // dead chunk accumulator: staging of x_old
   const uint32_t taddr = taddrA + 256;                                // c_proj accumulator, then the park of x_new
   if constexpr (KIND != B_FIRST) {
@@ -206,7 +212,7 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
         const float4 g = *reinterpret_cast<const float4*>(park + PK_GATE + (slot * D + col0 + i * 4) * 4);
         sm100::f32x2 a0 = sm100::pack2u(v[4 * i + 0], v[4 * i + 1]), a1 = sm100::pack2u(v[4 * i + 2], v[4 * i + 3]);
         if constexpr (HAS_BIAS) {
-          const float4 bb = *reinterpret_cast<const float4*>(park + PK_BIAS + (col0 + i * 4) * 4);
+          const float4 bb = *reinterpret_cast<const float4*>(smem + S2_OFF_BIASP + (col0 + i * 4) * 4);
           a0 = sm100::add2(a0, sm100::pack2(bb.x, bb.y));
           a1 = sm100::add2(a1, sm100::pack2(bb.z, bb.w));
         }
@@ -328,6 +334,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
   uint64_t* accB_full = bars + SB_ACCB_FULL;
   uint64_t* park_ready = bars + SB_PARK_READY;
   uint64_t* park_drained = bars + SB_PARK_DRAINED;
+  uint64_t* xfull = bars + SB_XFULL;
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
@@ -345,6 +352,14 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int T = p.n_chunks;
   const int mlp_items = KSLABS_D * T + p.hid_slabs;
+  // Before an attention half the boundary park lives in H buffer (T & 1) (the one the last MLP chunk does not use), before an
+  // MLP half in the (dead) q/k/v staging.  The OTHER 32 KB of the mid region is free from the finishing phase's last MMA until
+  // the starting phase's first chunk epilogue: the 4th weight item of the starting phase is prefetched there (the ring holds
+  // three), so the first MMA group of a phase never waits for a weight slab.
+  uint8_t* const park_pre_attn = smMid + (T & 1) * 2 * A_SLAB_BYTES;
+  uint8_t* const x_attn = smMid + ((T & 1) ^ 1) * 2 * A_SLAB_BYTES;
+  uint8_t* const park_pre_mlp = smMid;
+  uint8_t* const x_mlp = smMid + 2 * A_SLAB_BYTES;
   // blocked interior storage of a tile: its own rows of X, or this CTA's scratch tile when X is row-major
   auto interior = [&](int tile) { return p.io_blocked ? p.X + (size_t)tile * BLOCK_M * D : p.scratch + (size_t)blockIdx.x * BLOCK_M * D; };
 
@@ -359,16 +374,32 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         sm100::bulk_g2s(smRing + rs.stage * S2_STAGE, src, bytes, &full[rs.stage]);
         rs.advance(S2_NST);
       };
+      uint32_t n_phase = 0;
+      auto put_x = [&](const uint8_t* src, uint32_t bytes, uint8_t* dst) {   // the extra slot is free once the previous phase's MMAs have retired
+        if (n_phase > 0) sm100::mbar_wait(accB_full, (n_phase - 1) & 1);
+        sm100::mbar_arrive_expect_tx(xfull, bytes);
+        sm100::bulk_g2s(dst, src, bytes, xfull);
+      };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int l = 0; l < p.n_layer; ++l) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_attn + (size_t)l * p.attn_w_stride);
           for (int step = 0; step <= AB_HP; ++step) {
             if (step < AB_HP)
-              for (int ks = 0; ks < KSLABS_D; ++ks) { put(src, AB_Q_ITEM_BYTES); src += AB_Q_ITEM_BYTES; }
+              for (int ks = 0; ks < KSLABS_D; ++ks) {
+                if (step == 0 && ks == KSLABS_D - 1) put_x(src, AB_Q_ITEM_BYTES, x_attn);
+                else put(src, AB_Q_ITEM_BYTES);
+                src += AB_Q_ITEM_BYTES;
+              }
             if (step >= 1) { put(src, 2 * AB_P_ITEM_BYTES); src += 2 * AB_P_ITEM_BYTES; }
           }
+          ++n_phase;
           src = reinterpret_cast<const uint8_t*>(p.w_mlp + (size_t)l * p.mlp_w_stride);
-          for (int i = 0; i < mlp_items; ++i) { put(src, B_SLAB_BYTES); src += B_SLAB_BYTES; }
+          for (int i = 0; i < mlp_items; ++i) {
+            if (i == KSLABS_D - 1) put_x(src, B_SLAB_BYTES, x_mlp);
+            else put(src, B_SLAB_BYTES);
+            src += B_SLAB_BYTES;
+          }
+          ++n_phase;
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -378,7 +409,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
       const uint32_t accA = tmem_base, accB = tmem_base + 256;
       const uint32_t a_base = sm100::smem_u32(smA), ao_base = sm100::smem_u32(smMid + 3 * A_SLAB_BYTES), h_base = sm100::smem_u32(smMid);
       RingState rs;
-      uint32_t n_ar = 0, u_accA = 0, n_aor = 0, n_hr0 = 0, n_hr1 = 0, n_dr = 0;
+      uint32_t n_ar = 0, u_accA = 0, n_aor = 0, n_hr0 = 0, n_hr1 = 0, n_dr = 0, n_ph = 0;
       auto wait_stage = [&]() -> uint32_t {
         sm100::mbar_wait(&full[rs.stage], rs.phase);
         sm100::tc_fence_after();
@@ -401,6 +432,12 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
             if (step < AB_HP) {
               if (step > 0) { sm100::mbar_wait(accA_free, (u_accA - 1) & 1); sm100::tc_fence_after(); }
               for (int ks = 0; ks < KSLABS_D; ++ks) {
+                if (step == 0 && ks == KSLABS_D - 1) {   // prefetched into the extra slot
+                  sm100::mbar_wait(xfull, n_ph & 1);
+                  sm100::tc_fence_after();
+                  issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, sm100::smem_u32(x_attn), idesc_q, false);
+                  continue;
+                }
                 const uint32_t bs = wait_stage();
                 issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, bs, idesc_q, ks == 0);
                 done_stage();
@@ -418,7 +455,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
             }
           }
           sm100::umma_commit(accB_full);
-          ++n_dr;   // the attention -> MLP boundary
+          ++n_dr; ++n_ph;   // the attention -> MLP boundary
           // ---- MLP half: M1_0 M1_1 M2_0 M1_2 M2_1 ... ----
           sm100::mbar_wait(a_ready, n_ar & 1); ++n_ar;
           sm100::tc_fence_after();
@@ -426,6 +463,12 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
             if (j < T) {
               if (j > 0) { sm100::mbar_wait(accA_free, (u_accA - 1) & 1); sm100::tc_fence_after(); }
               for (int ks = 0; ks < KSLABS_D; ++ks) {
+                if (j == 0 && ks == KSLABS_D - 1) {      // prefetched into the extra slot
+                  sm100::mbar_wait(xfull, n_ph & 1);
+                  sm100::tc_fence_after();
+                  issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, sm100::smem_u32(x_mlp), idesc_n, false);
+                  continue;
+                }
                 const uint32_t bs = wait_stage();
                 issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, bs, idesc_n, ks == 0);
                 done_stage();
@@ -448,7 +491,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
             }
           }
           sm100::umma_commit(accB_full);
-          ++n_dr;   // the MLP -> next attention (or end of tile) boundary
+          ++n_dr; ++n_ph;   // the MLP -> next attention (or end of tile) boundary
         }
       }
     }
@@ -494,7 +537,14 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
     uint8_t* smQKV = smMid;
     uint8_t* smAO = smMid + 3 * A_SLAB_BYTES;
     const uint32_t qkv_base = sm100::smem_u32(smQKV);
-    const uint32_t job_slot = ew >> 1, job_h = ew & 1;      // attention job of this warp within a head pair
+    // attention job of this warp within a head pair: a slot of its own TMEM lane quadrant and one head, so that the q/k/v rows
+    // it stages (bf16, warp-private 3 KB block: [part][token][64 B], 16-byte chunks XOR-swizzled with (token / 2) % 4) are
+    // exactly the ones its own mma.sync job reads: no barrier between staging and the attention core
+    const uint32_t job_slot = 2 * q + (sub >> 1), job_h = sub & 1;
+    const bool job_lane = (lane >> 4) == (sub >> 1);        // lanes whose TMEM rows belong to the job's slot
+    const uint32_t job_tok = lane & 15;
+    uint8_t* const stg = smQKV + ew * 3072;
+    const uint32_t stg_base = sm100::smem_u32(stg);
     const uint32_t g = lane >> 2, t4 = lane & 3;
     const int hs = sub >> 1, hh = sub & 1;                  // SwiGLU: slab hs of the chunk, 32-column half hh
     uint32_t n_accA = 0, n_accB = 0, n_ao = 0, n_h0 = 0, n_h1 = 0, n_dr = 0;
@@ -513,46 +563,55 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
       ba.xin = x_io; ba.in_cs = io_cs;
       ba.mod = p.mod; ba.rows = smRows; ba.mod_stride = p.mod_stride; ba.eps = p.eps;
       ba.off_mul = 0; ba.off_add = D;
+      ba.sm_bias_q = smBiasQ; ba.next_bias_q = p.bias_q;
       sy.n_drained = n_dr;
-      boundary_step<B_FIRST, false>(ba, sy, smem, smMid, tmem_base, q, sub, lane, etid, [] {}, nullptr);
+      boundary_step<B_FIRST, false>(ba, sy, smem, park_pre_attn, tmem_base, q, sub, lane, etid, [] {}, nullptr);
       for (int l = 0; l < p.n_layer; ++l) {
         long long* dbg = (p.dbg != nullptr && l == p.dbg_layer && tile_no == 1) ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
         const int mo = l * 6 * D;
         // ================= attention half =================
-        if (etid < 64) reinterpret_cast<float4*>(smBiasQ)[etid] = *reinterpret_cast<const float4*>(p.bias_q + (size_t)l * 3 * D + etid * 4);
         if (dbg && etid == 0) dbg[4] = clock64();
         for (int hp = 0; hp < AB_HP; ++hp) {
           sm100::mbar_wait(accA_full, n_accA & 1); ++n_accA;
           sm100::tc_fence_after();
           if (dbg && etid == 0) dbg[8 + 3 * hp] = clock64();
-          uint32_t v0[32], v1[16];
-          sm100::tmem_ld_32x32b_x32(taddr_q + sub * 48, v0);
-          sm100::tmem_ld_32x32b_x16(taddr_q + sub * 48 + 32, v1);
-          sm100::tmem_ld_wait();
-          sm100::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) sm100::mbar_arrive(accA_free);
-          sm100::named_bar_sync(1, EPI_THREADS);   // previous head pair's attention jobs are done with the q/k/v staging (hp = 0: smBiasQ visible)
+          __syncwarp();                                     // the previous job's ldmatrix reads of the staging block are done
+          // q | k | v of this head: 32 accumulator columns each (q at 32 h, k at 64 + 32 h, v at 128 + 32 h); the next part's
+          // TMEM load is in flight while this one is converted
+          uint32_t pv[2][32];
+          sm100::tmem_ld_32x32b_x32(taddr_q + job_h * 32, pv[0]);
 #pragma unroll
-          for (int c8 = 0; c8 < 6; ++c8) {
-            const uint32_t gcol = sub * 48 + c8 * 8;             // accumulator column: [0,64) q, [64,128) k, [128,192) v
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (gcol < 64) {
-              b0 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + gcol);
-              b1 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + gcol + 4);
+          for (int part = 0; part < 3; ++part) {
+            sm100::tmem_ld_wait();
+            if (part < 2) sm100::tmem_ld_32x32b_x32(taddr_q + (part + 1) * 64 + job_h * 32, pv[(part + 1) & 1]);
+            const uint32_t (&vv)[32] = pv[part & 1];
+            if (job_lane) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (part == 0) {                             // q columns carry a bias (see AttnBlockParams)
+                  b0 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + job_h * 32 + c * 8);
+                  b1 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + job_h * 32 + c * 8 + 4);
+                }
+                uint4 o;
+                o.x = sm100::pack_bf16x2(__uint_as_float(vv[c * 8 + 0]) + b0.x, __uint_as_float(vv[c * 8 + 1]) + b0.y);
+                o.y = sm100::pack_bf16x2(__uint_as_float(vv[c * 8 + 2]) + b0.z, __uint_as_float(vv[c * 8 + 3]) + b0.w);
+                o.z = sm100::pack_bf16x2(__uint_as_float(vv[c * 8 + 4]) + b1.x, __uint_as_float(vv[c * 8 + 5]) + b1.y);
+                o.w = sm100::pack_bf16x2(__uint_as_float(vv[c * 8 + 6]) + b1.z, __uint_as_float(vv[c * 8 + 7]) + b1.w);
+                *reinterpret_cast<uint4*>(stg + part * 1024 + job_tok * 64 + ((c ^ ((job_tok >> 1) & 3)) << 4)) = o;
+              }
             }
-            const uint32_t* vv = c8 < 4 ? &v0[c8 * 8] : &v1[(c8 - 4) * 8];
-            uint4 o;
-            o.x = sm100::pack_bf16x2(__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y);
-            o.y = sm100::pack_bf16x2(__uint_as_float(vv[2]) + b0.z, __uint_as_float(vv[3]) + b0.w);
-            o.z = sm100::pack_bf16x2(__uint_as_float(vv[4]) + b1.x, __uint_as_float(vv[5]) + b1.y);
-            o.w = sm100::pack_bf16x2(__uint_as_float(vv[6]) + b1.z, __uint_as_float(vv[7]) + b1.w);
-            *reinterpret_cast<uint4*>(smQKV + (gcol >> 6) * A_SLAB_BYTES + sm100::swz_chunk_offset(row, (gcol & 63) >> 3)) = o;
+            if (part == 1) {                                 // every load of the accumulator has completed
+              sm100::tmem_ld_wait();
+              sm100::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) sm100::mbar_arrive(accA_free);
+            }
           }
-          sm100::named_bar_sync(1, EPI_THREADS);   // q/k/v of this head pair staged
+          __syncwarp();
           if (dbg && etid == 0) dbg[9 + 3 * hp] = clock64();
           auto chunk_addr = [&](uint32_t token, uint32_t part, uint32_t dim) -> uint32_t {
-            return qkv_base + part * A_SLAB_BYTES + sm100::swz_chunk_offset(job_slot * TOK + token, (job_h * HD + dim) >> 3);
+            return stg_base + part * 1024 + token * 64 + (((dim >> 3) ^ ((token >> 1) & 3)) << 4);
           };
           float o[4][4];
           attn16_core(chunk_addr, lane, o);
@@ -572,9 +631,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         }
         // ---- boundary: attention residual + LN2 / modulate ----
         ba.off_gate = mo + 2 * D; ba.bias = p.bias_proj + (size_t)l * D;
-        ba.off_mul = mo + 3 * D; ba.off_add = mo + 4 * D;
+        ba.off_mul = mo + 3 * D; ba.off_add = mo + 4 * D; ba.next_bias_q = nullptr;
         sy.accB_parity = n_accB & 1; sy.n_drained = n_dr;
-        boundary_step<B_MID, true>(ba, sy, smem, smMid, tmem_base, q, sub, lane, etid,
+        boundary_step<B_MID, true>(ba, sy, smem, park_pre_mlp, tmem_base, q, sub, lane, etid,
                                    [] { sm100::named_bar_sync(1, EPI_THREADS); /* every attention job has read its q/k/v */ },
                                    dbg ? dbg + 20 : nullptr);
         ++n_accB; ++n_dr;
@@ -616,14 +675,14 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         // ---- boundary: MLP residual (+ LN1 / modulate of the next layer).  The park goes into the H buffer that the last
         //      chunk does not use; it is free once the MMAs of chunk T - 2 have retired. ----
         const int pb = T & 1;
-        uint8_t* park = smMid + pb * 2 * A_SLAB_BYTES;
+        uint8_t* park = park_pre_attn;
         const uint32_t pcnt = pb ? n_h1 : n_h0;
         auto h_region_free = [&] {
           if (pcnt > 0) sm100::mbar_wait(&h_free[pb], (pcnt - 1) & 1);
           sm100::named_bar_sync(1, EPI_THREADS);   // every warp has read the last chunk's accumulator
         };
         ba.off_gate = mo + 5 * D; ba.bias = nullptr;
-        ba.off_mul = mo + 6 * D; ba.off_add = mo + 7 * D;
+        ba.off_mul = mo + 6 * D; ba.off_add = mo + 7 * D; ba.next_bias_q = p.bias_q + (size_t)(l + 1) * 3 * D;
         sy.accB_parity = n_accB & 1; sy.n_drained = n_dr;
         if (l + 1 < p.n_layer)
           boundary_step<B_MID, false>(ba, sy, smem, park, tmem_base, q, sub, lane, etid, h_region_free, dbg ? dbg + 40 : nullptr);
