@@ -117,7 +117,7 @@ def algorithmic_flops_per_row(G: int, evals: int = 49) -> dict:
 
 
 # per-launch algorithmic FLOPs of the GEMM kernel classes (rows = slots*16 actual, unpadded N/K)
-def kernel_flops(name: str, rows: int, mod_rows: int) -> float | None:
+def kernel_flops(name: str, rows: int, mod_rows: int, evals: int = 1) -> float | None:
     D, H = 256, 684
     return {
         "gemm_ares<LN,QKV>": 2.0 * rows * D * 3 * D,
@@ -130,6 +130,9 @@ def kernel_flops(name: str, rows: int, mod_rows: int) -> float | None:
         "attn_block": 2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D,
         "dit_blocks": 8 * (2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D + 2.0 * rows * D * 2 * H + 2.0 * rows * H * D),
         "dit_stack": 8 * (2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D + 2.0 * rows * D * 2 * H + 2.0 * rows * H * D),
+        # whole-solve launch: the block stack of every evaluation + input projection (256 x 16) and final Linear (16 x 256) per row
+        "dit_solve": evals * (8 * (2.0 * rows * D * 3 * D + 4.0 * rows * 16 * D + 2.0 * rows * D * D + 2.0 * rows * D * 2 * H + 2.0 * rows * H * D)
+                              + 2 * 2.0 * rows * 16 * D),
     }.get(name)
 
 
@@ -695,7 +698,8 @@ def main():
         top = max(gemm.items(), key=lambda kv: kv[1][1])
         name, (cnt, tms) = top
         # 3 forwards per cell (CFG) x 16 tokens; every chunk launches the kernel the same number of times
-        fl = sum(kernel_flops(name, 3 * c * 16, 1 + c) for c in chunks) / len(chunks)   # mean algorithmic FLOPs per launch
+        n_evals = {"euler": 1, "heun2": 2, "midpoint": 2}.get(args.method, 1) * (NUM_STEPS - 1)
+        fl = sum(kernel_flops(name, 3 * c * 16, 1 + c, n_evals) for c in chunks) / len(chunks)   # mean algorithmic FLOPs per launch
         ach = fl / (tms / cnt * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         traffic = None

@@ -47,23 +47,18 @@ typedef struct scldm_dit_weights {
   float eps;          /* LayerNorm eps (1e-8)                                                  */
   const void* w_mod;    /* bf16 [mod_stride/256][4][256x64]: all adaLN Linear weights, stacked   */
   const float* b_mod;   /* [mod_stride]                                                          */
-  const void* w_qkv;    /* bf16 [n_layer][3][4][256x64]   attn.c_attn                             */
-  const float* b_qkv;   /* [n_layer][768]                                                        */
-  const void* w_proj;   /* bf16 [n_layer][4][256x64]      attn.c_proj                             */
-  const float* b_proj;  /* [n_layer][256]                                                        */
-  const void* w_mlp1;   /* bf16 [n_layer][mlp1_tiles][4][256x64]  rows 0-127 = w1, 128-255 = w2   */
-  const void* w_mlp2;   /* bf16 [n_layer][hid_slabs][256x64]      mlp.c_proj                      */
-  const void* w_mlp_stream; /* bf16 [n_layer][mlp1_tiles*4 + hid_slabs][256x64]: the same [w1|w2] tiles and c_proj slabs
-                               in the consumption order of the fused MLP kernel (M1_0, M1_1, M2_0, M1_2, M2_1, ...);
-                               NULL selects the unfused pair of kernels                                              */
-  const void* w_attn_stream; /* bf16 [n_layer][262144]: attn.c_attn + attn.c_proj in the consumption order of the fused
-                                attention-block kernel.  Per head pair hp (heads 2hp, 2hp+1) a "Q item" is the 192 x 64 K-major
-                                swizzled slab [Wq rows 64hp.. | Wk rows 64hp.. | Wv rows 64hp..] for one 64-wide K slab, a
-                                "P item" the 128 x 64 slab c_proj.weight[128*half.., 64hp..64hp+64]; order Q_0 (4 items),
-                                Q_1, P_0 (2 items), Q_2, P_1, Q_3, P_2, P_3.  NULL selects the three unfused kernels          */
-  const float* b_proj_fused; /* [n_layer][256] = c_proj.bias + c_proj.weight @ c_attn.bias[512:768] (with w_attn_stream): the v bias
-                                passes through softmax-weighted averaging unchanged, the k bias cancels in the softmax, so the
-                                fused kernel adds only the q bias (b_qkv[:, 0:256]) before the attention                      */
+  const float* b_qkv;   /* [n_layer][768] attn.c_attn.bias (the kernels add the q part; k cancels in the softmax, v is folded below) */
+  const void* w_mlp_stream; /* bf16, per layer the SwiGLU MLP in the consumption order of dit_stack_kernel: N tile j of the fused
+                               [w1|w2] GEMM = four K slabs [w1 rows of hidden chunk j (halved) | w2 rows of chunk j] x 64, c_proj
+                               slab c = [256 x 64] for hidden columns 64c..64c+63; order M1_0, M1_1, M2_0, M1_2, M2_1, ...
+                               (M2_j = the one or two c_proj slabs of chunk j).  Chunks are 128 hidden units wide; the last one
+                               is padded to a multiple of 16 only.                                                         */
+  const void* w_attn_stream; /* bf16 [n_layer][262144]: attn.c_attn + attn.c_proj in consumption order.  Per head pair hp (heads
+                                2hp, 2hp+1) a "Q item" is the 192 x 64 K-major swizzled slab [Wq rows 64hp.. | Wk rows 64hp.. |
+                                Wv rows 64hp..] for one 64-wide K slab, a "P item" the 256 x 64 slab c_proj.weight[:, 64hp..64hp+64];
+                                order Q_0 (4 items), Q_1, P_0, Q_2, P_1, Q_3, P_2, P_3                                      */
+  const float* b_proj_fused; /* [n_layer][256] = c_proj.bias + c_proj.weight @ c_attn.bias[512:768]: the v bias passes through
+                                the softmax-weighted averaging unchanged                                                    */
   const float* temb_w0t; /* t_embedder.mlp.0.weight^T [256][256] */
   const float* temb_b0;
   const float* temb_w2t; /* t_embedder.mlp.2.weight^T [256][256] */
@@ -73,9 +68,15 @@ typedef struct scldm_dit_weights {
   const float* pos;    /* pos_embed [16][256]                 */
   const float* w_out;  /* final_layer.linear.weight [16][256] */
   const float* b_out;  /* [16]                                */
-  const void* wout_frag; /* bf16 final_layer.linear.weight in mma.sync B-fragment order [16][2][32][4]; NULL: fp32 CUDA-core path */
+  const void* wout_frag; /* bf16 final_layer.linear.weight in mma.sync B-fragment order [16][2][32][4]                         */
   const void* win_frag;  /* bf16 input_proj.weight in mma.sync B-fragment order [1][32][32][4]                                   */
   const float* class_tables[SCLDM_MAX_CLASSES]; /* class_embeddings.<name>.weight [(V+1)][256] */
+  const void* w_solve;  /* bf16, whole-solve kernel (scldm_dit_sample_ode): one 256 x 64 K-major swizzled slab, row n =
+                           [input_proj.weight[n, 0:16] | the same again | bf16 hi part of (pos_embed + input_proj.bias)[0:16, n] |
+                           its bf16 lo part] (the state enters as bf16 hi | lo parts followed by one-hot(token) twice), then
+                           final_layer.linear.weight as four 16 x 64 slabs.  NULL: one block-stack launch + one step kernel per
+                           evaluation                                                                                         */
+  const float* posb;    /* [16][256] pos_embed + input_proj.bias in fp32 (informational; the kernel uses the slab above)       */
 } scldm_dit_weights;
 
 /* Which model evaluations one call performs and how they are combined.

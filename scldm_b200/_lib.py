@@ -27,13 +27,13 @@ class DitWeights(C.Structure):
     _fields_ = [
         ("n_layer", C.c_int32), ("hidden", C.c_int32), ("hid_slabs", C.c_int32), ("mlp1_tiles", C.c_int32),
         ("mod_stride", C.c_int32), ("n_class", C.c_int32), ("eps", C.c_float),
-        ("w_mod", C.c_void_p), ("b_mod", C.c_void_p), ("w_qkv", C.c_void_p), ("b_qkv", C.c_void_p),
-        ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("w_mlp1", C.c_void_p), ("w_mlp2", C.c_void_p),
+        ("w_mod", C.c_void_p), ("b_mod", C.c_void_p), ("b_qkv", C.c_void_p),
         ("w_mlp_stream", C.c_void_p), ("w_attn_stream", C.c_void_p), ("b_proj_fused", C.c_void_p),
         ("temb_w0t", C.c_void_p), ("temb_b0", C.c_void_p), ("temb_w2t", C.c_void_p), ("temb_b2", C.c_void_p),
         ("w_in", C.c_void_p), ("b_in", C.c_void_p), ("pos", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
         ("wout_frag", C.c_void_p), ("win_frag", C.c_void_p),
         ("class_tables", C.c_void_p * MAX_CLASSES),
+        ("w_solve", C.c_void_p), ("posb", C.c_void_p),
     ]
 
 

@@ -46,24 +46,19 @@ std::vector<cudaEvent_t> g_prof_pool;
 bool g_prof_on = false;
 // Runtime options (scldm_set_option / scldm_get_option).  The SCLDM_* environment variables only provide the initial values.
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-int g_opt_mega = env_int("SCLDM_MEGA", 2);            // 2: dit_stack_kernel (fused residual / LayerNorm boundaries, blocked residual layout); 1: dit_blocks_kernel; 0: one kernel per block half
 int g_num_sms = 148;
-// dit_blocks_kernel micro-variants (bit mask): 1 = hand the MLP accumulator over before M2 is queued (measured slower: 971 vs 942 us),
-// 2 = no setup barrier in phases whose rows come from the stash (927 vs 942 us), 4 = butterfly LayerNorm reductions (937 vs 942 us)
-int g_opt_exp = env_int("SCLDM_EXP", 6);
 int g_opt_dec_cpb = env_int("SCLDM_DEC_CPB", 0);      // cells per MCAB decode CTA (0: heuristic)
 int g_opt_dec_occ = env_int("SCLDM_DEC_OCC", 2);      // resident CTAs per SM the MCAB decode kernel is compiled for (2: 128 registers, 3: 80 registers + spills)
 int g_opt_pdl = env_int("SCLDM_PDL", 1);              // programmatic dependent launch between the kernels of a call
 int g_opt_mod_batch = env_int("SCLDM_MOD_BATCH", 1);  // adaLN vectors of all evaluations of a fixed-grid solve from ONE GEMM
-#define g_use_mega (g_opt_mega != 0)
-#define g_exp g_opt_exp
+int g_opt_solve = env_int("SCLDM_SOLVE", 1);          // fixed-grid ODE solves as ONE launch of dit_stack_kernel (every evaluation in the kernel)
 #define g_dec_cpb g_opt_dec_cpb
 #define g_dec_occ g_opt_dec_occ
 #define g_use_pdl (g_opt_pdl != 0)
 #define g_mod_batch (g_opt_mod_batch != 0)
 struct OptionEntry { const char* name; int* value; };
-const OptionEntry g_options[] = {{"mega", &g_opt_mega}, {"exp", &g_opt_exp}, {"dec_cpb", &g_opt_dec_cpb}, {"dec_occ", &g_opt_dec_occ},
-                                 {"pdl", &g_opt_pdl}, {"mod_batch", &g_opt_mod_batch}};
+const OptionEntry g_options[] = {{"dec_cpb", &g_opt_dec_cpb}, {"dec_occ", &g_opt_dec_occ},
+                                 {"pdl", &g_opt_pdl}, {"mod_batch", &g_opt_mod_batch}, {"solve", &g_opt_solve}};
 cudaStream_t g_prof_stream = nullptr;
 
 cudaEvent_t prof_event() {
@@ -130,14 +125,12 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 struct DitWs {
   float* X;
-  dit::bf16* qkv;
-  dit::bf16* ao;
-  dit::bf16* hid;
   float* mod;
   float* cls;
   float* temb;
   float* acc;
   float* tvals;
+  float4* stage;
   size_t total;
 };
 
@@ -155,7 +148,7 @@ DitWs carve_dit(void* base, const scldm_dit_weights* w, const scldm_dit_plan* pl
   const size_t slots_pad = scldm_dit_slots_pad(plan);
   const size_t batch_rows = mod_batch_rows(w, plan, n_evals);
   const size_t mod_pad = scldm_dit_mod_pad(plan), mod_rows = batch_rows > mod_pad ? batch_rows : mod_pad;
-  const size_t rows = slots_pad * dit::TOK, row_tiles = rows / dit::BLOCK_M;
+  const size_t rows = slots_pad * dit::TOK;
   const size_t n_states = (size_t)plan->n_u + plan->n_g;
   const size_t temb_rows = (size_t)n_evals > mod_pad ? (size_t)n_evals : mod_pad;
   size_t off = 0;
@@ -166,15 +159,13 @@ DitWs carve_dit(void* base, const scldm_dit_weights* w, const scldm_dit_plan* pl
   };
   char* b = static_cast<char*>(base);
   DitWs ws;
-  ws.X = reinterpret_cast<float*>(b + take(rows * dit::D * 4));
-  ws.qkv = reinterpret_cast<dit::bf16*>(b + take(rows * 3 * dit::D * 2));
-  ws.ao = reinterpret_cast<dit::bf16*>(b + take(rows * dit::D * 2));
-  ws.hid = reinterpret_cast<dit::bf16*>(b + take(row_tiles * w->hid_slabs * dit::A_SLAB_BYTES));
+  ws.X = reinterpret_cast<float*>(b + take((rows + dit::BLOCK_M) * dit::D * 4));   // + one tile: the whole-solve kernel may shift the guided slots by one
   ws.mod = reinterpret_cast<float*>(b + take(mod_rows * (size_t)w->mod_stride * 4));
   ws.cls = reinterpret_cast<float*>(b + take(mod_pad * dit::D * 4));
   ws.temb = reinterpret_cast<float*>(b + take(temb_rows * dit::D * 4));
   ws.acc = reinterpret_cast<float*>(b + take(n_states * dit::TOK * dit::LAT * 4));
   ws.tvals = reinterpret_cast<float*>(b + take(align_up((size_t)(n_evals > 0 ? n_evals : 1) * 4, 1024)));
+  ws.stage = reinterpret_cast<float4*>(b + take(align_up((size_t)(n_evals > 0 ? n_evals : 1) * 16, 1024)));
   ws.total = off;
   return ws;
 }
@@ -191,6 +182,7 @@ int check_dit(const scldm_dit_weights* w, const scldm_dit_plan* plan) {
   if (plan->n_mod < 1) return fail(SCLDM_EINVAL, "n_mod must be >= 1");
   if (!plan->slot_mod || (w->n_class > 0 && !plan->cls_idx)) return fail(SCLDM_EINVAL, "null index arrays");
   if (plan->slot_mode < 0 || plan->slot_mode > 2) return fail(SCLDM_EINVAL, "bad slot_mode %d", plan->slot_mode);
+  if (!w->w_attn_stream || !w->w_mlp_stream || !w->b_proj_fused || !w->b_qkv || !w->wout_frag || !w->win_frag) return fail(SCLDM_EINVAL, "null packed weights");
   return SCLDM_OK;
 }
 
@@ -204,12 +196,16 @@ struct TimeArgs { float t[64]; };
 __global__ void set_times_kernel(float* dst, TimeArgs a, int n) {
   if ((int)threadIdx.x < n) dst[threadIdx.x] = a.t[threadIdx.x];
 }
+struct StageArgs { float4 s[64]; };   // {a_dt, b_dt, first_stage, last_stage} per evaluation (dit_stack_kernel, whole-solve mode)
+__global__ void set_stage_kernel(float4* dst, StageArgs a, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = a.s[threadIdx.x];
+}
 
 // adaLN modulation vectors of every block + final layer for all conditioning rows
 int launch_mod(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, const float* temb, long long temb_stride,
                cudaStream_t st, int batch_rows = 0, int n_evals = 0) {
   const int mod_pad = batch_rows > 0 ? batch_rows : scldm_dit_mod_pad(plan);
-  dit::AResParams p{};
+  dit::ModGemmParams p{};
   p.temb = temb;
   p.temb_row_stride = temb_stride;
   p.cls = ws.cls;
@@ -222,10 +218,10 @@ int launch_mod(const scldm_dit_weights* w, const scldm_dit_plan* plan, const Dit
   if (groups < 1) groups = 1;
   p.tiles_per_cta = ceil_div(p.n_tiles_total, groups);
   p.bias = w->b_mod;
-  p.out_f32 = ws.mod;
+  p.out = ws.mod;
   p.out_ld = w->mod_stride;
   dim3 grid(row_tiles, ceil_div(p.n_tiles_total, p.tiles_per_cta));
-  LAUNCH("gemm_ares<COND,MOD>", launch_pdl(dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD>, grid, dim3(dit::NUM_THREADS), dit::ares_smem_bytes(), st, p));
+  LAUNCH("mod_gemm", launch_pdl(dit::mod_gemm_kernel, grid, dim3(dit::NUM_THREADS), dit::mod_gemm_smem_bytes(), st, p));
   return SCLDM_OK;
 }
 
@@ -239,124 +235,40 @@ dit::ModIndex mod_index(const scldm_dit_plan* plan) {
   return mi;
 }
 
-// dit_stack_kernel needs the fused weight streams; with it the residual stream is tile-blocked (x_index)
-bool use_stack(const scldm_dit_weights* w) {
-  return g_opt_mega == 2 && w->w_attn_stream != nullptr && w->b_proj_fused != nullptr && w->w_mlp_stream != nullptr;
+dit::StackParams stack_params(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, int row_tiles) {
+  dit::StackParams sp{};
+  sp.X = ws.X; sp.mod = ws.mod; sp.slot_mod = mod_index(plan); sp.mod_stride = w->mod_stride; sp.eps = w->eps;
+  sp.w_attn = static_cast<const dit::bf16*>(w->w_attn_stream); sp.attn_w_stride = 4LL * dit::D * dit::D;
+  sp.w_mlp = static_cast<const dit::bf16*>(w->w_mlp_stream);
+  sp.hid_last = (w->hidden - 128 * (w->mlp1_tiles - 1) + 31) / 32 * 32;
+  sp.mlp_w_stride = ((long long)(w->mlp1_tiles - 1) * dit::KSLABS_D + w->hid_slabs) * dit::B_SLAB_ELEMS + (long long)dit::KSLABS_D * 2 * sp.hid_last * dit::BLOCK_K;
+  sp.bias_q = w->b_qkv; sp.bias_proj = w->b_proj_fused;
+  sp.n_layer = w->n_layer; sp.n_tiles = row_tiles; sp.n_chunks = w->mlp1_tiles; sp.hid_slabs = w->hid_slabs;
+  sp.dbg = g_dbg_clk; sp.dbg_layer = g_dbg_layer;
+  return sp;
+}
+
+// Fixed-grid solves whose modulation tables were all precomputed run as ONE launch of dit_stack_kernel when a state has at most
+// two slots (plain forwards, CFG of a 1-class or joint model): the kernel keeps the two slots of a guided state in one warp.
+bool use_solve(const scldm_dit_weights* w, const scldm_dit_plan* plan, size_t batch_rows) {
+  if (!g_opt_solve || !w->w_solve || !w->posb || batch_rows == 0) return false;
+  return plan->n_g == 0 || plan->n_f <= 2;
 }
 
 // the n_layer adaLN blocks on the residual stream ws.X (reference layers.py:208-221)
 // `rowmajor_scratch` (dit_stack_kernel only): ws.X is row-major and this buffer (scldm_stack_scratch_bytes) holds the blocked interior
 int launch_blocks(const scldm_dit_weights* w, const scldm_dit_plan* plan, const DitWs& ws, cudaStream_t st, float* rowmajor_scratch = nullptr) {
-  const int slots_pad = scldm_dit_slots_pad(plan);
-  const int row_tiles = slots_pad * dit::TOK / dit::BLOCK_M;
-  const size_t tile_elems = (size_t)dit::KSLABS_D * dit::B_SLAB_ELEMS;
-  if (use_stack(w)) {
-    dit::StackParams sp{};
-    sp.X = ws.X; sp.mod = ws.mod; sp.slot_mod = mod_index(plan); sp.mod_stride = w->mod_stride; sp.eps = w->eps;
-    sp.w_attn = static_cast<const dit::bf16*>(w->w_attn_stream); sp.attn_w_stride = 4LL * dit::D * dit::D;
-    sp.w_mlp = static_cast<const dit::bf16*>(w->w_mlp_stream);
-    sp.mlp_w_stride = ((long long)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs) * dit::B_SLAB_ELEMS;
-    sp.bias_q = w->b_qkv; sp.bias_proj = w->b_proj_fused;
-    sp.n_layer = w->n_layer; sp.n_tiles = row_tiles; sp.n_chunks = w->mlp1_tiles; sp.hid_slabs = w->hid_slabs;
-    sp.dbg = g_dbg_clk; sp.dbg_layer = g_dbg_layer;
-    sp.io_blocked = rowmajor_scratch == nullptr; sp.scratch = rowmajor_scratch;
-    const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
-    LAUNCH("dit_stack", launch_pdl(dit::dit_stack_kernel, dim3(grid), dim3(dit::S2_THREADS), dit::stack_smem_bytes(), st, sp));
-    return SCLDM_OK;
-  }
-  if (g_use_mega && w->w_attn_stream != nullptr && w->b_proj_fused != nullptr && w->w_mlp_stream != nullptr) {
-    // the whole block stack as one persistent kernel (one CTA per SM, tiles walk through all layers without grid syncs)
-    dit::BlocksParams bp{};
-    dit::AttnBlockParams& a = bp.attn;
-    a.X = ws.X; a.mod = ws.mod; a.slot_mod = mod_index(plan); a.mod_stride = w->mod_stride;
-    a.mod_off_mul = 0; a.mod_off_add = dit::D; a.mod_off_gate = 2 * dit::D; a.eps = w->eps;
-    a.Wstream = static_cast<const dit::bf16*>(w->w_attn_stream); a.bias_q = w->b_qkv; a.bias_proj = w->b_proj_fused;
-    dit::MlpFusedParams& m = bp.mlp;
-    m.X = ws.X; m.mod = ws.mod; m.slot_mod = mod_index(plan); m.mod_stride = w->mod_stride;
-    m.mod_off_mul = 3 * dit::D; m.mod_off_add = 4 * dit::D; m.mod_off_gate = 5 * dit::D; m.eps = w->eps;
-    m.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream); m.n_chunks = w->mlp1_tiles; m.hid_slabs = w->hid_slabs;
-    a.exp = g_exp; m.exp = g_exp;
-    bp.n_layer = w->n_layer; bp.n_tiles = row_tiles;
-    bp.dbg = g_dbg_clk; bp.dbg_layer = g_dbg_layer; bp.stagger_cycles = 0;
-    bp.attn_w_stride = 4LL * dit::D * dit::D;
-    bp.mlp_w_stride = ((long long)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs) * dit::B_SLAB_ELEMS;
-    const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
-    LAUNCH("dit_blocks", launch_pdl(dit::dit_blocks_kernel, dim3(grid), dim3(dit::NUM_THREADS), dit::phase_smem_bytes(), st, bp));
-    return SCLDM_OK;
-  }
-  for (int l = 0; l < w->n_layer; ++l) {
-    const int mo = l * 6 * dit::D;
-    if (w->w_attn_stream != nullptr && w->b_proj_fused != nullptr) {  // fused attention half: LN1 + QKV + attention + c_proj + gated residual
-      dit::AttnBlockParams p{};
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
-      p.mod_off_mul = mo + 0 * dit::D; p.mod_off_add = mo + 1 * dit::D; p.mod_off_gate = mo + 2 * dit::D; p.eps = w->eps;
-      p.Wstream = static_cast<const dit::bf16*>(w->w_attn_stream) + (size_t)l * 4 * dit::D * dit::D;
-      p.bias_q = w->b_qkv + (size_t)l * 3 * dit::D;
-      p.bias_proj = w->b_proj_fused + (size_t)l * dit::D;
-      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk : nullptr;
-      LAUNCH("attn_block", launch_pdl(dit::attn_block_kernel, dim3(row_tiles), dim3(dit::NUM_THREADS), dit::attn_block_smem_bytes(), st, p));
-    } else {
-    {  // LN1 + modulate + QKV
-      dit::AResParams p{};
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
-      p.mod_off_mul = mo + 0 * dit::D; p.mod_off_add = mo + 1 * dit::D; p.eps = w->eps;
-      p.Wp = static_cast<const dit::bf16*>(w->w_qkv) + (size_t)l * 3 * tile_elems;
-      p.n_tiles_total = 3; p.tiles_per_cta = 3;
-      p.bias = w->b_qkv + (size_t)l * 3 * dit::D;
-      p.out_bf16 = ws.qkv; p.out_ld = 3 * dit::D;  // 12 packed slabs per row tile
-      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk : nullptr;
-      LAUNCH("gemm_ares<LN,QKV>", dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
-    }
-    LAUNCH("attn16", dit::attn16_kernel<<<slots_pad, 256, 0, st>>>(ws.qkv, ws.ao, slots_pad));
-    {  // c_proj + gated residual
-      dit::AStreamParams p{};
-      p.Ap = ws.ao; p.Wp = static_cast<const dit::bf16*>(w->w_proj) + (size_t)l * tile_elems; p.k_slabs = dit::KSLABS_D;
-      p.bias = w->b_proj + (size_t)l * dit::D;
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 2 * dit::D;
-      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + (1 << 17) : nullptr;
-      LAUNCH("gemm_astream<proj>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
-    }
-    }
-    if (w->w_mlp_stream != nullptr) {  // fused MLP half: LN2 + modulate + [w1|w2] + SwiGLU + c_proj + gated residual
-      dit::MlpFusedParams p{};
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
-      p.mod_off_mul = mo + 3 * dit::D; p.mod_off_add = mo + 4 * dit::D; p.mod_off_gate = mo + 5 * dit::D; p.eps = w->eps;
-      const size_t n_stream = (size_t)w->mlp1_tiles * dit::KSLABS_D + w->hid_slabs;
-      p.Wstream = static_cast<const dit::bf16*>(w->w_mlp_stream) + (size_t)l * n_stream * dit::B_SLAB_ELEMS;
-      p.n_chunks = w->mlp1_tiles; p.hid_slabs = w->hid_slabs;
-      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 2 * (1 << 17) : nullptr;
-      LAUNCH("mlp_fused", launch_pdl(dit::mlp_fused_kernel, dim3(row_tiles), dim3(dit::NUM_THREADS), dit::mlp_fused_smem_bytes(), st, p));
-      continue;
-    }
-    {  // LN2 + modulate + [w1|w2] + SwiGLU
-      dit::AResParams p{};
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride;
-      p.mod_off_mul = mo + 3 * dit::D; p.mod_off_add = mo + 4 * dit::D; p.eps = w->eps;
-      p.Wp = static_cast<const dit::bf16*>(w->w_mlp1) + (size_t)l * w->mlp1_tiles * tile_elems;
-      p.n_tiles_total = w->mlp1_tiles; p.tiles_per_cta = w->mlp1_tiles;
-      p.out_packed = ws.hid; p.out_slabs = w->hid_slabs;
-      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 2 * (1 << 17) : nullptr;
-      LAUNCH("gemm_ares<LN,SWIGLU>", dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU><<<dim3(row_tiles, 1), dit::NUM_THREADS, dit::ares_smem_bytes(), st>>>(p));
-    }
-    {  // mlp.c_proj + gated residual
-      dit::AStreamParams p{};
-      p.Ap = ws.hid; p.Wp = static_cast<const dit::bf16*>(w->w_mlp2) + (size_t)l * w->hid_slabs * dit::B_SLAB_ELEMS;
-      p.k_slabs = w->hid_slabs; p.bias = nullptr;
-      p.X = ws.X; p.mod = ws.mod; p.slot_mod = mod_index(plan); p.mod_stride = w->mod_stride; p.mod_off_gate = mo + 5 * dit::D;
-      p.dbg = (g_dbg_clk && l == g_dbg_layer) ? g_dbg_clk + 3 * (1 << 17) : nullptr;
-      LAUNCH("gemm_astream<mlp2>", dit::gemm_astream_resid_kernel<<<row_tiles, dit::NUM_THREADS, dit::astream_smem_bytes(), st>>>(p));
-    }
-  }
+  const int row_tiles = scldm_dit_slots_pad(plan) * dit::TOK / dit::BLOCK_M;
+  dit::StackParams sp = stack_params(w, plan, ws, row_tiles);
+  sp.io_blocked = rowmajor_scratch == nullptr; sp.scratch = rowmajor_scratch;
+  const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
+  LAUNCH("dit_stack", launch_pdl(dit::dit_stack_kernel<false>, dim3(grid), dim3(dit::S2_THREADS), dit::stack_smem_bytes(), st, sp));
   return SCLDM_OK;
 }
 
 int launch_final(const scldm_dit_weights* w, const dit::StepParams& s, int n_states, cudaStream_t st) {
-  if (w->wout_frag != nullptr && w->win_frag != nullptr) {
-    dit::StepTcWeights tw{static_cast<const uint2*>(w->wout_frag), static_cast<const uint2*>(w->win_frag)};
-    LAUNCH("final_step_tc", launch_pdl(dit::final_step_tc_kernel, dim3(ceil_div(n_states, 4)), dim3(128), 0, st, s, tw, n_states));
-  } else {
-    LAUNCH("final_step", dit::final_step_kernel<<<n_states < 296 ? n_states : 296, 512, 0, st>>>(s, n_states));
-  }
+  dit::StepTcWeights tw{static_cast<const uint2*>(w->wout_frag), static_cast<const uint2*>(w->win_frag)};
+  LAUNCH("final_step_tc", launch_pdl(dit::final_step_tc_kernel, dim3(ceil_div(n_states, 4)), dim3(128), 0, st, s, tw, n_states));
   return SCLDM_OK;
 }
 
@@ -368,7 +280,7 @@ dit::StepParams make_step(const scldm_dit_weights* w, const scldm_dit_plan* plan
   s.n_u = plan->n_u; s.n_g = plan->n_g; s.n_f = plan->n_g > 0 ? plan->n_f : 1;
   for (int i = 0; i < SCLDM_MAX_COMBINE; ++i) s.coef[i] = plan->coef[i];
   s.acc = ws.acc;
-  s.x_blocked = use_stack(w) ? 1 : 0;
+  s.x_blocked = 1;   // dit_stack_kernel keeps the residual stream tile-blocked (x_index)
   return s;
 }
 
@@ -392,14 +304,9 @@ int prepare_kernels() {
   if (dev < 0 || dev >= MAX_DEVICES) return fail(SCLDM_EINVAL, "device index %d out of range", dev);
   if (done[dev].load()) { g_num_sms = g_sms_of[dev]; return SCLDM_OK; }
   int rc;
-  if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_QKV>, dit::ares_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_LN, dit::EPI_SWIGLU>, dit::ares_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::gemm_ares_kernel<dit::PRO_COND, dit::EPI_MOD>, dit::ares_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::gemm_astream_resid_kernel, dit::astream_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::mlp_fused_kernel, dit::mlp_fused_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::attn_block_kernel, dit::attn_block_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::dit_blocks_kernel, dit::phase_smem_bytes()))) return rc;
-  if ((rc = set_smem(dit::dit_stack_kernel, dit::stack_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::mod_gemm_kernel, dit::mod_gemm_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::dit_stack_kernel<false>, dit::stack_smem_bytes()))) return rc;
+  if ((rc = set_smem(dit::dit_stack_kernel<true>, dit::stack_smem_bytes()))) return rc;
   {
     int n = 0;
     CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
@@ -431,10 +338,9 @@ int32_t scldm_dit_workspace_layout(const scldm_dit_weights* w, const scldm_dit_p
                                    int32_t max_entries) {
   if (!w || !plan || !offsets) return 0;
   const DitWs ws = carve_dit(nullptr, w, plan, n_evals);
-  const size_t v[9] = {(size_t)ws.X,   (size_t)ws.qkv,  (size_t)ws.ao,  (size_t)ws.hid,  (size_t)ws.mod,
-                       (size_t)ws.cls, (size_t)ws.temb, (size_t)ws.acc, (size_t)ws.tvals};
+  const size_t v[6] = {(size_t)ws.X, (size_t)ws.mod, (size_t)ws.cls, (size_t)ws.temb, (size_t)ws.acc, (size_t)ws.tvals};
   int n = 0;
-  for (; n < 9 && n < max_entries; ++n) offsets[n] = v[n];
+  for (; n < 6 && n < max_entries; ++n) offsets[n] = v[n];
   return n;
 }
 
@@ -525,11 +431,44 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
   LAUNCH("temb", dit::temb_kernel<<<n_evals, dit::TEMB_THREADS, 0, st>>>(ws.tvals, n_evals, w->temb_w0t, w->temb_b0, w->temb_w2t, w->temb_b2, ws.temb));
   if ((rc = launch_cls(w, plan, ws, st))) return rc;
 
+  const int batch_rows = (int)mod_batch_rows(w, plan, n_evals);
+  if (use_solve(w, plan, batch_rows)) {
+    // ---- the whole solve in one launch: every evaluation, the CFG combine and the stage updates inside dit_stack_kernel ----
+    for (int e0 = 0; e0 < n_evals; e0 += 64) {
+      StageArgs sa{};
+      int n = 0;
+      for (; n < 64 && e0 + n < n_evals; ++n) {
+        const int idx = e0 + n, k = idx / stages, sg = idx % stages;
+        const float dt = t_grid_host[k + 1] - t_grid_host[k];
+        float a_dt, b_dt;
+        if (method == SCLDM_ODE_EULER) { a_dt = 0.f; b_dt = dt; }
+        else if (method == SCLDM_ODE_HEUN2) { a_dt = dt; b_dt = 0.5f * dt; }
+        else { a_dt = 0.5f * dt; b_dt = sg == 0 ? 0.f : dt; }
+        sa.s[n] = make_float4(a_dt, b_dt, sg == 0 ? 1.f : 0.f, sg == stages - 1 ? 1.f : 0.f);
+      }
+      LAUNCH("set_stage", set_stage_kernel<<<1, 64, 0, st>>>(ws.stage + e0, sa, n));
+    }
+    if ((rc = launch_mod(w, plan, ws, ws.temb, dit::D, st, batch_rows, n_evals))) return rc;
+    const int n_f = plan->n_g > 0 ? plan->n_f : 1;
+    const int slot_shift = (n_f == 2 && (plan->n_u & 1)) ? 1 : 0;   // see StackParams::slot_shift
+    const int row_tiles = ceil_div(plan->n_u + slot_shift + plan->n_g * n_f, 8);
+    dit::StackParams sp = stack_params(w, plan, ws, row_tiles);
+    sp.slot_shift = slot_shift;
+    sp.X = nullptr; sp.io_blocked = 0; sp.scratch = ws.X;   // residual rows: one CTA-private tile each, L2 resident
+    sp.n_evals = n_evals; sp.mod_eval_stride = (long long)plan->n_mod * w->mod_stride; sp.stage = ws.stage;
+    sp.w_solve = static_cast<const dit::bf16*>(w->w_solve); sp.posb = w->posb; sp.b_out = w->b_out;
+    sp.x_base = x; sp.acc = ws.acc;
+    sp.n_u = plan->n_u; sp.n_g = plan->n_g; sp.n_f = n_f;
+    sp.coef[0] = plan->coef[0]; sp.coef[1] = plan->coef[1];
+    sp.mod_off_final = w->n_layer * 6 * dit::D;
+    const int grid = row_tiles < g_num_sms ? row_tiles : g_num_sms;
+    LAUNCH("dit_solve", launch_pdl(dit::dit_stack_kernel<true>, dim3(grid), dim3(dit::S2_THREADS), dit::stack_smem_bytes(), st, sp));
+    return SCLDM_OK;
+  }
   dit::StepParams s = make_step(w, plan, ws);
   s.x_base = x;
   LAUNCH("inproj", dit::inproj_kernel<<<n_states, 256, 0, st>>>(s));
   s.do_update = 1;
-  const int batch_rows = (int)mod_batch_rows(w, plan, n_evals);
   if (batch_rows > 0 && (rc = launch_mod(w, plan, ws, ws.temb, dit::D, st, batch_rows, n_evals))) return rc;
   for (int k = 0; k < n_steps; ++k) {
     const float dt = t_grid_host[k + 1] - t_grid_host[k];
@@ -697,7 +636,7 @@ int scldm_set_option(const char* name, int32_t value) {
   if (!name) return fail(SCLDM_EINVAL, "null option name");
   for (const OptionEntry& o : g_options)
     if (strcmp(o.name, name) == 0) { *o.value = value; return SCLDM_OK; }
-  return fail(SCLDM_EINVAL, "unknown option '%s' (mega, exp, dec_cpb, dec_occ, pdl, mod_batch)", name);
+  return fail(SCLDM_EINVAL, "unknown option '%s' (dec_cpb, dec_occ, pdl, mod_batch, solve)", name);
 }
 int32_t scldm_get_option(const char* name) {
   if (name)

@@ -65,12 +65,32 @@ struct StackParams {
   const bf16* w_attn;       // attention weight stream, per layer attn_w_stride elements (pack.py)
   const bf16* w_mlp;        // MLP weight stream
   long long attn_w_stride, mlp_w_stride;
-  const float* bias_q;      // [L][768] c_attn.bias (only the q part is used, see AttnBlockParams)
+  const float* bias_q;      // [L][768] c_attn.bias (only the q part is used: the k bias cancels in the softmax, the v bias is folded into bias_proj)
   const float* bias_proj;   // [L][256] fused c_proj bias
   int n_layer, n_tiles;
-  int n_chunks, hid_slabs;  // MLP: ceil(hidden / 128), ceil(hidden / 64)
-  long long* dbg;           // optional timeline of (second tile, layer dbg_layer): 64 stamps per CTA
+  int n_chunks, hid_slabs;  // MLP: ceil(hidden / 128) hidden chunks, ceil(hidden / 64) K slabs of c_proj
+  int hid_last;             // hidden units of the last chunk, padded to a multiple of 32 (32 .. 128): its [w1|w2] tile is 2 hid_last wide
+  long long* dbg;           // optional timeline of (second tile, layer dbg_layer): 128 stamps per CTA
   int dbg_layer;
+  // ---- whole-solve mode (n_evals > 0): every evaluation of a fixed-grid ODE solve in this one launch.  A tile's rows never meet
+  // another tile's, in time as little as across layers, so each CTA carries its tiles through ALL evaluations: input projection
+  // (tcgen05, the state as bf16 hi | lo parts) -> block stack -> final LayerNorm / modulate / Linear (tcgen05) -> CFG combine ->
+  // explicit Runge-Kutta stage update of the state (transport/integrators.py:100-112, nnets.py:336-378).  X is not used: the
+  // residual rows live in `scratch` (one tile per CTA, L2 resident).
+  int n_evals;
+  long long mod_eval_stride;   // floats between the modulation tables of consecutive evaluations
+  const float4* stage;         // [n_evals] {a_dt, b_dt, first_stage, last_stage}: acc (+)= b_dt v; last: x += acc; else x_eval = x + a_dt v
+  const bf16* w_solve;         // input-projection slab (32 KB) + final-linear slabs (8 KB), pack.py
+  const float* posb;           // [16][256] pos_embed + input_proj.bias
+  const float* b_out;          // [16] final_layer.linear.bias
+  float* x_base;               // [n_states][16][16] ODE state, updated in place
+  float* acc;                  // [n_states][16][16] stage accumulator (multi-stage methods)
+  int n_u, n_g, n_f;           // state <-> slot mapping (StepParams); n_f <= 2
+  int slot_shift;              // 1: one unused slot sits between the unguided and the guided slots (odd n_u), so that the two slots
+                               // of a guided state are always lanes l and l ^ 16 of one warp.  Kernel-internal: slot s >= n_u of the
+                               // kernel is slot s - slot_shift of the plan.
+  float coef[2];
+  int mod_off_final;           // column of the final layer's (shift | scale) chunks in a modulation row
 };
 
 constexpr int S2_NST = 3;
@@ -81,7 +101,7 @@ constexpr int S2_OFF_BIASQ = S2_OFF_RING + S2_NST * S2_STAGE;   // 224 KB
 constexpr int S2_OFF_BIASP = S2_OFF_BIASQ + D * 4;             // c_proj bias of the attention half (boundary pass 1)
 constexpr int S2_OFF_BARS = S2_OFF_BIASP + D * 4;
 enum { SB_FULL = 0, SB_EMPTY = 3, SB_A_READY = 6, SB_ACCA_FULL = 7, SB_ACCA_FREE = 8, SB_AO_READY = 9, SB_AO_FREE = 10,
-       SB_H_READY = 11, SB_H_FREE = 13, SB_ACCB_FULL = 15, SB_PARK_READY = 16, SB_PARK_DRAINED = 17, SB_XFULL = 18, SB_COUNT = 19 };
+       SB_H_READY = 11, SB_H_FREE = 13, SB_ACCB_FULL = 15, SB_PARK_READY = 16, SB_PARK_DRAINED = 17, SB_XFULL = 18, SB_Z_READY = 19, SB_COUNT = 20 };
 constexpr int S2_WARPS = 24, S2_THREADS = S2_WARPS * 32, S2_WORKER_WARP0 = 8, S2_DRAIN_WARP0 = 4;
 constexpr int S2_REGS_LAUNCH = 80, S2_REGS_IDLE = 56, S2_REGS_DRAIN = 40, S2_REGS_WORKER = 96;
 static_assert(S2_THREADS * S2_REGS_LAUNCH >= 128 * S2_REGS_IDLE + 128 * S2_REGS_DRAIN + 512 * S2_REGS_WORKER, "setmaxnreg budget");
@@ -115,11 +135,12 @@ struct BoundarySync {
   uint64_t* a_ready;
   uint64_t* park_ready;
   uint64_t* park_drained; uint32_t n_drained;   // drained boundaries so far (all of them must be complete before x_old is read)
+  bool drain;            // hand the parked rows to the drain warps (false: nobody needs them in global memory)
 };
 
 // One boundary on the calling worker warp.  `region_free()` returns once every worker warp has finished the phase's last chunk
 // (the chunk accumulator's TMEM columns and the park region are dead); it is called after the global loads have been issued.
-template <int KIND, bool HAS_BIAS, typename RegionFree>
+template <int KIND, bool HAS_BIAS, bool HAS_X, typename RegionFree>
 __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const BoundarySync& sy, uint8_t* smem, uint8_t* park, uint32_t tmem_base,
                                               uint32_t q, uint32_t sub, uint32_t lane, uint32_t etid, RegionFree&& region_free, long long* dbg) {
   const uint32_t row = q * 32 + lane;
@@ -127,7 +148,7 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   const int pslot = etid >> 6, pc4 = etid & 63;
   const float* mrow = b.mod + (size_t)b.rows[pslot] * b.mod_stride + pc4 * 4;
   float4 gate_v = make_float4(0.f, 0.f, 0.f, 0.f), mul_v = gate_v, add_v = gate_v, bias_v = gate_v;
-  if constexpr (KIND != B_FIRST) gate_v = *reinterpret_cast<const float4*>(mrow + b.off_gate);
+  if constexpr (KIND != B_FIRST) gate_v = b.off_gate >= 0 ? *reinterpret_cast<const float4*>(mrow + b.off_gate) : make_float4(1.f, 1.f, 1.f, 1.f);
   if constexpr (KIND != B_LAST) {
     mul_v = *reinterpret_cast<const float4*>(mrow + b.off_mul);
     add_v = *reinterpret_cast<const float4*>(mrow + b.off_add);
@@ -144,8 +165,11 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
       dst[4 * i + 2] = __float_as_uint(t.z); dst[4 * i + 3] = __float_as_uint(t.w);
     }
   };
-  load_x(xr, 0);
-  if constexpr (KIND != B_FIRST) load_x(xr2, 1);   // nothing else is live here: both halves in flight at once
+  constexpr bool has_x = HAS_X;   // false: the accumulator IS the new row (input projection incl. pos_embed + bias)
+  if constexpr (has_x) {
+    load_x(xr, 0);
+    if constexpr (KIND != B_FIRST) load_x(xr2, 1);   // nothing else is live here: both halves in flight at once
+  }
   region_free();
   if (dbg && etid == 0) dbg[4] = clock64();
   if constexpr (KIND != B_FIRST) *reinterpret_cast<float4*>(park + PK_GATE + etid * 16) = gate_v;
@@ -161,9 +185,11 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   const uint32_t taddr = taddrA + 256;                                // c_proj accumulator, then the park of x_new
   if constexpr (KIND != B_FIRST) {
     // the old rows wait in TMEM while the phase's last MMAs retire (this warp writes and reads the same lanes / columns)
-    tmem_st_32x32b_x32(taddrA, xr);
-    tmem_st_32x32b_x32(taddrA + 32, xr2);
-    tmem_st_wait();
+    if constexpr (has_x) {
+      tmem_st_32x32b_x32(taddrA, xr);
+      tmem_st_32x32b_x32(taddrA + 32, xr2);
+      tmem_st_wait();
+    }
     if (dbg && etid == 0) dbg[5] = clock64();
     sm100::mbar_wait(sy.accB_full, sy.accB_parity);
     sm100::tc_fence_after();
@@ -195,18 +221,19 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   if constexpr (KIND != B_FIRST) {
     uint32_t av[2][16], xv[2][16];
     sm100::tmem_ld_32x32b_x16(taddr, av[0]);
-    sm100::tmem_ld_32x32b_x16(taddrA, xv[0]);
+    if constexpr (has_x) sm100::tmem_ld_32x32b_x16(taddrA, xv[0]);
     float m_prev = 0.f, q_prev = 0.f;
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
       sm100::tmem_ld_wait();
       if (st < 3) {
         sm100::tmem_ld_32x32b_x16(taddr + (st + 1) * 16, av[(st + 1) & 1]);
-        sm100::tmem_ld_32x32b_x16(taddrA + (st + 1) * 16, xv[(st + 1) & 1]);
+        if constexpr (has_x) sm100::tmem_ld_32x32b_x16(taddrA + (st + 1) * 16, xv[(st + 1) & 1]);
       }
       uint32_t (&v)[16] = av[st & 1];
       const uint32_t (&xo)[16] = xv[st & 1];
       const int col0 = sub * 64 + st * 16;
+      if constexpr (has_x) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 g = *reinterpret_cast<const float4*>(park + PK_GATE + (slot * D + col0 + i * 4) * 4);
@@ -222,6 +249,7 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
         sm100::unpack2u(a1, v[4 * i + 2], v[4 * i + 3]);
       }
       tmem_st_32x32b_x16(taddr + st * 16, v);
+      }
       if constexpr (KIND != B_LAST) {
         float m, qq;
         stats16(v, m, qq);
@@ -251,7 +279,7 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   if constexpr (KIND != B_FIRST) {   // hand the parked rows to the drain warps (B_FIRST: they are in global memory already)
     sm100::tc_fence_before();
     __syncwarp();
-    if (lane == 0) sm100::mbar_arrive(sy.park_ready);
+    if (lane == 0 && sy.drain) sm100::mbar_arrive(sy.park_ready);
   }
   if (dbg && etid == 0) dbg[1] = clock64();
   if constexpr (KIND == B_LAST) return;
@@ -311,6 +339,7 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   if (dbg && etid == 0) dbg[3] = clock64();
 }
 
+template <bool SOLVE>
 __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -335,13 +364,14 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
   uint64_t* park_ready = bars + SB_PARK_READY;
   uint64_t* park_drained = bars + SB_PARK_DRAINED;
   uint64_t* xfull = bars + SB_XFULL;
+  uint64_t* z_ready = bars + SB_Z_READY;
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
   if (threadIdx.x == 0) {
     for (int i = 0; i < SB_COUNT; ++i) {
       const bool workers = i == SB_A_READY || i == SB_ACCA_FREE || i == SB_AO_READY || i == SB_H_READY || i == SB_H_READY + 1 || i == SB_PARK_READY;
-      sm100::mbar_init(&bars[i], workers ? EPI_WARPS : (i == SB_PARK_DRAINED ? 4 : 1));
+      sm100::mbar_init(&bars[i], workers ? EPI_WARPS : ((i == SB_PARK_DRAINED || i == SB_Z_READY) ? 4 : 1));
     }
     sm100::fence_barrier_init();
   }
@@ -351,7 +381,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int T = p.n_chunks;
-  const int mlp_items = KSLABS_D * T + p.hid_slabs;
+  const int hl = p.hid_last;   // width of the last hidden chunk
   // Before an attention half the boundary park lives in H buffer (T & 1) (the one the last MLP chunk does not use), before an
   // MLP half in the (dead) q/k/v staging.  The OTHER 32 KB of the mid region is free from the finishing phase's last MMA until
   // the starting phase's first chunk epilogue: the 4th weight item of the starting phase is prefetched there (the ring holds
@@ -362,6 +392,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
   uint8_t* const x_mlp = smMid + 2 * A_SLAB_BYTES;
   // blocked interior storage of a tile: its own rows of X, or this CTA's scratch tile when X is row-major
   auto interior = [&](int tile) { return p.io_blocked ? p.X + (size_t)tile * BLOCK_M * D : p.scratch + (size_t)blockIdx.x * BLOCK_M * D; };
+  constexpr bool solve = SOLVE;
+  const int n_ev = solve ? p.n_evals : 1;
+  constexpr uint32_t SOLVE_I_BYTES = B_SLAB_BYTES, SOLVE_F_BYTES = 4 * 16 * BLOCK_K * 2;
 
   if (warp < S2_DRAIN_WARP0) {
     reg_dec<S2_REGS_IDLE>();
@@ -381,35 +414,48 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         sm100::bulk_g2s(dst, src, bytes, xfull);
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < p.n_layer; ++l) {
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_attn + (size_t)l * p.attn_w_stride);
-          for (int step = 0; step <= AB_HP; ++step) {
-            if (step < AB_HP)
-              for (int ks = 0; ks < KSLABS_D; ++ks) {
-                if (step == 0 && ks == KSLABS_D - 1) put_x(src, AB_Q_ITEM_BYTES, x_attn);
-                else put(src, AB_Q_ITEM_BYTES);
-                src += AB_Q_ITEM_BYTES;
+        for (int e = 0; e < n_ev; ++e) {
+          if (solve) { put(reinterpret_cast<const uint8_t*>(p.w_solve), SOLVE_I_BYTES); ++n_phase; }
+          for (int l = 0; l < p.n_layer; ++l) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_attn + (size_t)l * p.attn_w_stride);
+            for (int step = 0; step <= AB_HP; ++step) {
+              if (step < AB_HP)
+                for (int ks = 0; ks < KSLABS_D; ++ks) {
+                  if (step == 0 && ks == KSLABS_D - 1) put_x(src, AB_Q_ITEM_BYTES, x_attn);
+                  else put(src, AB_Q_ITEM_BYTES);
+                  src += AB_Q_ITEM_BYTES;
+                }
+              if (step >= 1) { put(src, 2 * AB_P_ITEM_BYTES); src += 2 * AB_P_ITEM_BYTES; }
+            }
+            ++n_phase;
+            src = reinterpret_cast<const uint8_t*>(p.w_mlp + (size_t)l * p.mlp_w_stride);
+            for (int j = 0; j <= T; ++j) {   // M1_0 M1_1 M2_0 M1_2 M2_1 ...
+              if (j < T) {
+                const uint32_t bytes = j + 1 < T ? (uint32_t)B_SLAB_BYTES : (uint32_t)(2 * hl * BLOCK_K * 2);   // [w1 | w2] rows of the chunk, one K slab
+                for (int ks = 0; ks < KSLABS_D; ++ks) {
+                  if (j == 0 && ks == KSLABS_D - 1) put_x(src, bytes, x_mlp);
+                  else put(src, bytes);
+                  src += bytes;
+                }
               }
-            if (step >= 1) { put(src, 2 * AB_P_ITEM_BYTES); src += 2 * AB_P_ITEM_BYTES; }
+              if (j >= 1)
+                for (int s2 = 0, ns = min(2, p.hid_slabs - 2 * (j - 1)); s2 < ns; ++s2) { put(src, B_SLAB_BYTES); src += B_SLAB_BYTES; }
+            }
+            ++n_phase;
           }
-          ++n_phase;
-          src = reinterpret_cast<const uint8_t*>(p.w_mlp + (size_t)l * p.mlp_w_stride);
-          for (int i = 0; i < mlp_items; ++i) {
-            if (i == KSLABS_D - 1) put_x(src, B_SLAB_BYTES, x_mlp);
-            else put(src, B_SLAB_BYTES);
-            src += B_SLAB_BYTES;
-          }
-          ++n_phase;
+          if (solve) put(reinterpret_cast<const uint8_t*>(p.w_solve) + SOLVE_I_BYTES, SOLVE_F_BYTES);
         }
       }
     } else if (warp == 1 && lane == 0) {
       // ===================== MMA issuer ========================================================================================
       const uint32_t idesc_q = sm100::make_idesc_bf16(BLOCK_M, AB_QN);
       const uint32_t idesc_n = sm100::make_idesc_bf16(BLOCK_M, BLOCK_N);
+      const uint32_t idesc_l = sm100::make_idesc_bf16(BLOCK_M, 2 * hl);   // last hidden chunk
       const uint32_t accA = tmem_base, accB = tmem_base + 256;
       const uint32_t a_base = sm100::smem_u32(smA), ao_base = sm100::smem_u32(smMid + 3 * A_SLAB_BYTES), h_base = sm100::smem_u32(smMid);
       RingState rs;
-      uint32_t n_ar = 0, u_accA = 0, n_aor = 0, n_hr0 = 0, n_hr1 = 0, n_dr = 0, n_ph = 0;
+      uint32_t n_ar = 0, u_accA = 0, n_aor = 0, n_hr0 = 0, n_hr1 = 0, n_dr = 0, n_xu = 0, n_z = 0;
+      const uint32_t idesc_f = sm100::make_idesc_bf16(BLOCK_M, 16);
       auto wait_stage = [&]() -> uint32_t {
         sm100::mbar_wait(&full[rs.stage], rs.phase);
         sm100::tc_fence_after();
@@ -424,6 +470,18 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         if (n_dr > 0) { sm100::mbar_wait(park_drained, (n_dr - 1) & 1); sm100::tc_fence_after(); }
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+       for (int e = 0; e < n_ev; ++e) {
+        if (solve) {
+          // ---- input projection + pos_embed + bias: accB[128 x 256] = [z_hi | z_lo | 1hot(tok) | 1hot(tok)] x [Win | Win | posb_hi | posb_lo]^T ----
+          sm100::mbar_wait(z_ready, n_z & 1); ++n_z;
+          sm100::tc_fence_after();
+          wait_drained();
+          const uint32_t bs = wait_stage();
+          issue_slab_mmas(accB, a_base, bs, idesc_n, true);
+          done_stage();
+          sm100::umma_commit(accB_full);
+          ++n_dr;   // the boundary that follows is drained
+        }
         for (int l = 0; l < p.n_layer; ++l) {
           // ---- attention half: Q0 Q1 P0 Q2 P1 Q3 P2 P3 ----
           sm100::mbar_wait(a_ready, n_ar & 1); ++n_ar;
@@ -433,7 +491,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
               if (step > 0) { sm100::mbar_wait(accA_free, (u_accA - 1) & 1); sm100::tc_fence_after(); }
               for (int ks = 0; ks < KSLABS_D; ++ks) {
                 if (step == 0 && ks == KSLABS_D - 1) {   // prefetched into the extra slot
-                  sm100::mbar_wait(xfull, n_ph & 1);
+                  sm100::mbar_wait(xfull, n_xu & 1); ++n_xu;
                   sm100::tc_fence_after();
                   issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, sm100::smem_u32(x_attn), idesc_q, false);
                   continue;
@@ -455,7 +513,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
             }
           }
           sm100::umma_commit(accB_full);
-          ++n_dr; ++n_ph;   // the attention -> MLP boundary
+          ++n_dr;   // the attention -> MLP boundary
           // ---- MLP half: M1_0 M1_1 M2_0 M1_2 M2_1 ... ----
           sm100::mbar_wait(a_ready, n_ar & 1); ++n_ar;
           sm100::tc_fence_after();
@@ -464,13 +522,13 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
               if (j > 0) { sm100::mbar_wait(accA_free, (u_accA - 1) & 1); sm100::tc_fence_after(); }
               for (int ks = 0; ks < KSLABS_D; ++ks) {
                 if (j == 0 && ks == KSLABS_D - 1) {      // prefetched into the extra slot
-                  sm100::mbar_wait(xfull, n_ph & 1);
+                  sm100::mbar_wait(xfull, n_xu & 1); ++n_xu;
                   sm100::tc_fence_after();
-                  issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, sm100::smem_u32(x_mlp), idesc_n, false);
+                  issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, sm100::smem_u32(x_mlp), T == 1 ? idesc_l : idesc_n, false);
                   continue;
                 }
                 const uint32_t bs = wait_stage();
-                issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, bs, idesc_n, ks == 0);
+                issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, bs, j + 1 < T ? idesc_n : idesc_l, ks == 0);
                 done_stage();
               }
               sm100::umma_commit(accA_full); ++u_accA;
@@ -491,8 +549,18 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
             }
           }
           sm100::umma_commit(accB_full);
-          ++n_dr; ++n_ph;   // the MLP -> next attention (or end of tile) boundary
+          if (!(solve && l + 1 == p.n_layer)) ++n_dr;   // the MLP -> next attention (or end of tile) boundary; not drained before the final layer
         }
+        if (solve) {
+          // ---- final linear: accA[128 x 16] = LN_mod(x) x Wout^T ----
+          sm100::mbar_wait(a_ready, n_ar & 1); ++n_ar;
+          sm100::tc_fence_after();
+          const uint32_t bs = wait_stage();
+          for (int ks = 0; ks < KSLABS_D; ++ks) issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, bs + ks * (16 * BLOCK_K * 2), idesc_f, ks == 0);
+          done_stage();
+          sm100::umma_commit(accA_full); ++u_accA;
+        }
+       }
       }
     }
   } else if (warp < S2_WORKER_WARP0) {
@@ -505,8 +573,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
       float* const x_in = interior(tile) + row * 4;
       float* const x_io = p.X + (size_t)tile * BLOCK_M * D + (p.io_blocked ? row * 4 : row * D);
       const int io_cs = p.io_blocked ? BLOCK_M * 4 : 4;
+      for (int e = 0; e < n_ev; ++e) {
       for (int bnd = 0; bnd < 2 * p.n_layer; ++bnd) {
-        const bool last = bnd == 2 * p.n_layer - 1;
+        // plain mode: boundary bnd follows phase bnd (the last one writes the io buffer); solve mode: boundary 0 follows the input
+        // projection, boundary bnd >= 1 phase bnd - 1 (the one before the final layer is not drained): everything stays interior
+        const bool last = !solve && bnd == 2 * p.n_layer - 1;
         float* dst = last ? x_io : x_in;
         const int cs = last ? io_cs : BLOCK_M * 4;
         sm100::mbar_wait(park_ready, n & 1); ++n;
@@ -524,8 +595,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         sm100::tc_fence_before();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(park_drained);
-        if (p.dbg != nullptr && warp == S2_DRAIN_WARP0 && lane == 0 && (bnd >> 1) == p.dbg_layer && tile == (int)(blockIdx.x + gridDim.x))
-          p.dbg[(size_t)blockIdx.x * 64 + ((bnd & 1) ? 47 : 27)] = clock64();
+        if (p.dbg != nullptr && warp == S2_DRAIN_WARP0 && lane == 0 && !solve && (bnd >> 1) == p.dbg_layer && tile == (int)(blockIdx.x + gridDim.x))
+          p.dbg[(size_t)blockIdx.x * 128 + ((bnd & 1) ? 47 : 27)] = clock64();
+      }
       }
     }
   } else {
@@ -551,23 +623,95 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
     BoundarySync sy{};
     sy.accB_full = accB_full; sy.a_ready = a_ready; sy.park_ready = park_ready; sy.park_drained = park_drained;
     sm100::grid_dep_wait();   // X and the modulation table come from the preceding kernels
+    if (p.dbg != nullptr && etid == 0) {
+      unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.dbg[(size_t)blockIdx.x * 128 + 60] = clock64(); p.dbg[(size_t)blockIdx.x * 128 + 62] = (long long)gt;
+    }
     int tile_no = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_no) {
-      if (etid < 8) smRows[etid] = p.slot_mod.row(tile * 8 + etid);
+      if (etid < 8) {
+        const int s = tile * 8 + (int)etid;
+        smRows[etid] = (solve && s >= p.n_u) ? (s < p.n_u + p.slot_shift ? 0 : p.slot_mod.row(s - p.slot_shift)) : p.slot_mod.row(s);
+      }
       sm100::named_bar_sync(1, EPI_THREADS);   // rows resolved; every warp has left the previous tile
+      if (p.dbg != nullptr && etid == 0 && tile_no < 4) p.dbg[(size_t)blockIdx.x * 128 + 52 + tile_no] = clock64();
       BoundaryArgs ba{};
       // lane-resolved addresses of (row, column 64 sub) in the io buffer and in the blocked interior storage
       const float* const x_io = p.X + (size_t)tile * BLOCK_M * D + (p.io_blocked ? ((size_t)(sub * 16) * BLOCK_M + row) * 4 : (size_t)row * D + sub * 64);
       const int io_cs = p.io_blocked ? BLOCK_M * 4 : 4;
       const float* const x_in = interior(tile) + ((size_t)(sub * 16) * BLOCK_M + row) * 4;
-      ba.xin = x_io; ba.in_cs = io_cs;
       ba.mod = p.mod; ba.rows = smRows; ba.mod_stride = p.mod_stride; ba.eps = p.eps;
-      ba.off_mul = 0; ba.off_add = D;
-      ba.sm_bias_q = smBiasQ; ba.next_bias_q = p.bias_q;
-      sy.n_drained = n_dr;
-      boundary_step<B_FIRST, false>(ba, sy, smem, park_pre_attn, tmem_base, q, sub, lane, etid, [] {}, nullptr);
+      ba.sm_bias_q = smBiasQ;
+      // ---- whole-solve mode: state <-> slot mapping of this lane's row (StepParams), recomputed where needed ----
+      struct RowState { int state, k; bool valid, pair; };
+      auto row_state = [&]() {
+        RowState r{0, 0, false, false};
+        const int s_g = tile * 8 + (int)(row >> 4);
+        const int g0 = p.n_u + p.slot_shift;   // first guided slot
+        r.valid = s_g < g0 + p.n_g * p.n_f && !(s_g >= p.n_u && s_g < g0);
+        if (s_g < g0) r.state = s_g < p.n_u ? s_g : 0;
+        else { const int j = (s_g - g0) / p.n_f; r.k = (s_g - g0) - j * p.n_f; r.state = p.n_u + j; r.pair = p.n_f == 2; }
+        return r;
+      };
+      // the state of this row as the A operand of the input projection: 128-byte row = [hi 16 bf16 | lo 16 bf16 | unused]
+      auto write_z = [&](const float (&z)[16]) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat16 h0 = __float2bfloat16(z[2 * i]), h1 = __float2bfloat16(z[2 * i + 1]);
+          hi[i] = sm100::pack_bf16x2(z[2 * i], z[2 * i + 1]);
+          lo[i] = sm100::pack_bf16x2(z[2 * i] - __bfloat162float(h0), z[2 * i + 1] - __bfloat162float(h1));
+        }
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 1)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 3)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        // one-hot(token) twice (bf16 1.0 = 0x3F80): picks pos_embed + bias (hi and lo parts) out of the weight slab
+        const int tok = (int)(row & 15);
+        const uint32_t one = 0x3F80u << (16 * (tok & 1));
+        const int w = (tok & 7) >> 1;
+        const uint4 oh = make_uint4(w == 0 ? one : 0u, w == 1 ? one : 0u, w == 2 ? one : 0u, w == 3 ? one : 0u), zero4 = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 4)) = tok < 8 ? oh : zero4;
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 5)) = tok < 8 ? zero4 : oh;
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 6)) = tok < 8 ? oh : zero4;
+        *reinterpret_cast<uint4*>(smA + sm100::swz_chunk_offset(row, 7)) = tok < 8 ? zero4 : oh;
+        sm100::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(z_ready);
+      };
+      if constexpr (solve) {
+        if (sub == 0) {
+          const RowState rs0 = row_state();
+          float z[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = rs0.valid ? *reinterpret_cast<const float4*>(p.x_base + ((size_t)rs0.state * TOK + (row & 15)) * LAT + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            z[4 * i] = t.x; z[4 * i + 1] = t.y; z[4 * i + 2] = t.z; z[4 * i + 3] = t.w;
+          }
+          write_z(z);
+        }
+      } else {
+        ba.xin = x_io; ba.in_cs = io_cs;
+        ba.off_mul = 0; ba.off_add = D; ba.next_bias_q = p.bias_q;
+        sy.n_drained = n_dr; sy.drain = true;
+        boundary_step<B_FIRST, false, true>(ba, sy, smem, park_pre_attn, tmem_base, q, sub, lane, etid, [] {}, nullptr);
+      }
+     for (int e = 0; e < n_ev; ++e) {
+      if constexpr (solve) {
+        // ---- boundary after the input projection: x = (pos_embed + bias) + acc, LN1 / modulate of layer 0 ----
+        ba.mod = p.mod + (size_t)e * p.mod_eval_stride;
+        ba.xin = nullptr; ba.in_cs = 0;
+        ba.off_gate = -1; ba.bias = nullptr; ba.off_mul = 0; ba.off_add = D; ba.next_bias_q = p.bias_q;
+        sy.accB_parity = n_accB & 1; sy.n_drained = n_dr; sy.drain = true;
+        boundary_step<B_MID, false, false>(ba, sy, smem, park_pre_attn, tmem_base, q, sub, lane, etid,
+                                    [] { sm100::named_bar_sync(1, EPI_THREADS); /* every warp is past the previous evaluation's final step */ },
+                                    (p.dbg != nullptr && tile_no == 1 && e > 0) ? p.dbg + (size_t)blockIdx.x * 128 + 64 : nullptr);
+        ++n_accB; ++n_dr;
+        ba.xin = x_in; ba.in_cs = BLOCK_M * 4;
+        if (p.dbg != nullptr && tile_no == 1 && etid == 0) p.dbg[(size_t)blockIdx.x * 128 + 51] = clock64();
+      }
       for (int l = 0; l < p.n_layer; ++l) {
-        long long* dbg = (p.dbg != nullptr && l == p.dbg_layer && tile_no == 1) ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+        long long* dbg = (p.dbg != nullptr && l == p.dbg_layer && tile_no == 1) ? p.dbg + (size_t)blockIdx.x * 128 : nullptr;
         const int mo = l * 6 * D;
         // ================= attention half =================
         if (dbg && etid == 0) dbg[4] = clock64();
@@ -589,7 +733,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                if (part == 0) {                             // q columns carry a bias (see AttnBlockParams)
+                if (part == 0) {                             // q columns carry a bias
                   b0 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + job_h * 32 + c * 8);
                   b1 = *reinterpret_cast<const float4*>(smBiasQ + hp * 64 + job_h * 32 + c * 8 + 4);
                 }
@@ -632,8 +776,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         // ---- boundary: attention residual + LN2 / modulate ----
         ba.off_gate = mo + 2 * D; ba.bias = p.bias_proj + (size_t)l * D;
         ba.off_mul = mo + 3 * D; ba.off_add = mo + 4 * D; ba.next_bias_q = nullptr;
-        sy.accB_parity = n_accB & 1; sy.n_drained = n_dr;
-        boundary_step<B_MID, true>(ba, sy, smem, park_pre_mlp, tmem_base, q, sub, lane, etid,
+        sy.accB_parity = n_accB & 1; sy.n_drained = n_dr; sy.drain = true;
+        boundary_step<B_MID, true, true>(ba, sy, smem, park_pre_mlp, tmem_base, q, sub, lane, etid,
                                    [] { sm100::named_bar_sync(1, EPI_THREADS); /* every attention job has read its q/k/v */ },
                                    dbg ? dbg + 20 : nullptr);
         ++n_accB; ++n_dr;
@@ -643,9 +787,13 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
           sm100::mbar_wait(accA_full, n_accA & 1); ++n_accA;
           sm100::tc_fence_after();
           if (dbg && etid == 0 && j < 6) dbg[28 + 2 * j] = clock64();
+          // the chunk's accumulator: columns [0, w) = w1 part, [w, 2 w) = w2 part (w = 128, the last chunk hid_last); this warp
+          // handles hidden units [32 sub, 32 sub + 32) of the chunk when the chunk has them
+          const int cw = j + 1 < T ? 128 : hl;
+          const bool active = (int)(sub * 32) < cw;
           uint32_t va[32], vb[32];
-          sm100::tmem_ld_32x32b_x32(taddr_q + hs * 64 + hh * 32, va);
-          sm100::tmem_ld_32x32b_x32(taddr_q + 128 + hs * 64 + hh * 32, vb);
+          sm100::tmem_ld_32x32b_x32(taddr_q + sub * 32, va);        // (an inactive warp reads columns it does not use)
+          sm100::tmem_ld_32x32b_x32(taddr_q + cw + sub * 32, vb);
           sm100::tmem_ld_wait();
           sm100::tc_fence_before();
           __syncwarp();
@@ -655,17 +803,22 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
           if (cnt > 0) sm100::mbar_wait(&h_free[hb], (cnt - 1) & 1);   // the MMAs that read this H buffer last have retired
           if (hb) ++n_h1; else ++n_h0;
           uint8_t* buf = smMid + (hb * 2 + hs) * A_SLAB_BYTES;
+          if (active) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float hv[8];
+            for (int c = 0; c < 4; ++c) {
+              float hv[8];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) hv[jj] = sm100::silu_from_half(__uint_as_float(va[c * 8 + jj])) * __uint_as_float(vb[c * 8 + jj]);
-            uint4 o;
-            o.x = sm100::pack_bf16x2(hv[0], hv[1]);
-            o.y = sm100::pack_bf16x2(hv[2], hv[3]);
-            o.z = sm100::pack_bf16x2(hv[4], hv[5]);
-            o.w = sm100::pack_bf16x2(hv[6], hv[7]);
-            *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, hh * 4 + c)) = o;
+              for (int jj = 0; jj < 8; ++jj) hv[jj] = sm100::silu_from_half(__uint_as_float(va[c * 8 + jj])) * __uint_as_float(vb[c * 8 + jj]);
+              uint4 o;
+              o.x = sm100::pack_bf16x2(hv[0], hv[1]);
+              o.y = sm100::pack_bf16x2(hv[2], hv[3]);
+              o.z = sm100::pack_bf16x2(hv[4], hv[5]);
+              o.w = sm100::pack_bf16x2(hv[6], hv[7]);
+              *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, hh * 4 + c)) = o;
+            }
+          } else if (hs < min(2, p.hid_slabs - 2 * j)) {   // beyond the chunk's width but inside a slab the c_proj MMAs read (zero weights there)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(buf + sm100::swz_chunk_offset(row, hh * 4 + c)) = make_uint4(0u, 0u, 0u, 0u);
           }
           sm100::fence_proxy_async_smem();
           __syncwarp();
@@ -683,14 +836,97 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         };
         ba.off_gate = mo + 5 * D; ba.bias = nullptr;
         ba.off_mul = mo + 6 * D; ba.off_add = mo + 7 * D; ba.next_bias_q = p.bias_q + (size_t)(l + 1) * 3 * D;
-        sy.accB_parity = n_accB & 1; sy.n_drained = n_dr;
-        if (l + 1 < p.n_layer)
-          boundary_step<B_MID, false>(ba, sy, smem, park, tmem_base, q, sub, lane, etid, h_region_free, dbg ? dbg + 40 : nullptr);
-        else
-          boundary_step<B_LAST, false>(ba, sy, smem, park, tmem_base, q, sub, lane, etid, h_region_free, dbg ? dbg + 40 : nullptr);
-        ++n_accB; ++n_dr;
+        sy.accB_parity = n_accB & 1; sy.n_drained = n_dr; sy.drain = true;
+        if (l + 1 < p.n_layer) {
+          boundary_step<B_MID, false, true>(ba, sy, smem, park, tmem_base, q, sub, lane, etid, h_region_free, dbg ? dbg + 40 : nullptr);
+          ++n_dr;
+        } else if constexpr (!solve) {
+          boundary_step<B_LAST, false, true>(ba, sy, smem, park, tmem_base, q, sub, lane, etid, h_region_free, dbg ? dbg + 40 : nullptr);
+          ++n_dr;
+        } else {
+          // final layer (layers.py:397-401): LN(x) * (1 + scale) + shift -> A tile of the final Linear; the rows themselves are dead
+          ba.off_mul = p.mod_off_final + D; ba.off_add = p.mod_off_final; ba.next_bias_q = nullptr;
+          sy.drain = false;
+          boundary_step<B_MID, false, true>(ba, sy, smem, park, tmem_base, q, sub, lane, etid, h_region_free, dbg ? dbg + 40 : nullptr);
+        }
+        ++n_accB;
         if (dbg && etid == 0) dbg[5] = clock64();
       }
+      if constexpr (solve) {
+        // ---- v = final Linear (+ bias), CFG combine, Runge-Kutta stage update, next evaluation point (column quarter 0 warps) ----
+        long long* dbs = (p.dbg != nullptr && tile_no == 1 && etid == 0) ? p.dbg + (size_t)blockIdx.x * 128 : nullptr;
+        if (dbs) dbs[48] = clock64();
+        // the state, the accumulator and the coefficients are fetched while the final Linear runs
+        const RowState rs1 = row_state();
+        const int st_state = rs1.state, st_k = rs1.k;
+        const bool st_valid = rs1.valid, st_pair = rs1.pair;
+        float* xb = p.x_base + ((size_t)st_state * TOK + (row & 15)) * LAT;
+        float* ac = p.acc + ((size_t)st_state * TOK + (row & 15)) * LAT;
+        float4 stg4 = make_float4(0.f, 0.f, 0.f, 0.f), xb4[4], ac4[4], bo4[4];
+        if (sub == 0) {
+          stg4 = p.stage[e];   // {a_dt, b_dt, first_stage, last_stage}
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            bo4[i] = *reinterpret_cast<const float4*>(p.b_out + 4 * i);
+            xb4[i] = st_valid ? *reinterpret_cast<const float4*>(xb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ac4[i] = st_valid ? *reinterpret_cast<const float4*>(ac + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        sm100::mbar_wait(accA_full, n_accA & 1); ++n_accA;
+        sm100::tc_fence_after();
+        if (dbs) dbs[49] = clock64();
+        if (sub == 0) {
+          uint32_t o16[16];
+          sm100::tmem_ld_32x32b_x16(taddr_q, o16);
+          sm100::tmem_ld_wait();
+          sm100::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) sm100::mbar_arrive(accA_free);
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[4 * i + 0] = __uint_as_float(o16[4 * i + 0]) + bo4[i].x; v[4 * i + 1] = __uint_as_float(o16[4 * i + 1]) + bo4[i].y;
+            v[4 * i + 2] = __uint_as_float(o16[4 * i + 2]) + bo4[i].z; v[4 * i + 3] = __uint_as_float(o16[4 * i + 3]) + bo4[i].w;
+            if (stg4.z != 0.f) ac4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // first stage: the accumulator starts from zero
+          }
+          // a guided state owns two consecutive slots = lanes l and l ^ 16 of this warp: v = c0 v_0 + c1 v_1
+          const float c_mine = st_pair ? p.coef[st_k] : 1.f, c_other = st_pair ? p.coef[st_k ^ 1] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float other = __shfl_xor_sync(0xffffffffu, v[i], 16);
+            v[i] = fmaf(c_other, other, c_mine * v[i]);
+          }
+          float z[16];
+          __syncwarp();   // both lanes of a pair have read the state before one of them updates it
+          const bool writer = st_valid && st_k == 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 a = ac4[i];
+            a.x = fmaf(stg4.y, v[4 * i + 0], a.x); a.y = fmaf(stg4.y, v[4 * i + 1], a.y);
+            a.z = fmaf(stg4.y, v[4 * i + 2], a.z); a.w = fmaf(stg4.y, v[4 * i + 3], a.w);
+            float4 xe;
+            if (stg4.w != 0.f) {
+              xe = make_float4(xb4[i].x + a.x, xb4[i].y + a.y, xb4[i].z + a.z, xb4[i].w + a.w);
+              if (writer) *reinterpret_cast<float4*>(xb + 4 * i) = xe;
+            } else {
+              if (writer) *reinterpret_cast<float4*>(ac + 4 * i) = a;
+              xe = make_float4(fmaf(stg4.x, v[4 * i + 0], xb4[i].x), fmaf(stg4.x, v[4 * i + 1], xb4[i].y),
+                               fmaf(stg4.x, v[4 * i + 2], xb4[i].z), fmaf(stg4.x, v[4 * i + 3], xb4[i].w));
+            }
+            z[4 * i] = xe.x; z[4 * i + 1] = xe.y; z[4 * i + 2] = xe.z; z[4 * i + 3] = xe.w;
+          }
+          if (e + 1 < n_ev) write_z(z);   // the final Linear's MMAs have retired: the A tile is dead
+          if (dbs) dbs[50] = clock64();
+        } else {
+          __syncwarp();
+          if (lane == 0) sm100::mbar_arrive(accA_free);
+        }
+      }
+     }
+    }
+    if (p.dbg != nullptr && etid == 0) {
+      unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.dbg[(size_t)blockIdx.x * 128 + 61] = clock64(); p.dbg[(size_t)blockIdx.x * 128 + 63] = (long long)gt;
     }
   }
   sm100::tc_fence_before();

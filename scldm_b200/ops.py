@@ -171,27 +171,22 @@ def dit_sample_ode(plan: DitPlan, x: torch.Tensor, t_grid: torch.Tensor, method:
 def dit_workspace_views(plan: DitPlan, ws: torch.Tensor, n_evals: int = 0) -> dict:
     """Test helper: typed views of the intermediates a call left in the workspace."""
     lib = _lib.load()
-    offs = (C.c_size_t * 9)()
-    n = lib.scldm_dit_workspace_layout(C.byref(plan.packed.struct), C.byref(plan.struct), n_evals, offs, 9)
-    assert n == 9
+    offs = (C.c_size_t * 6)()
+    n = lib.scldm_dit_workspace_layout(C.byref(plan.packed.struct), C.byref(plan.struct), n_evals, offs, 6)
+    assert n == 6
     base = (-ws.data_ptr()) % 1024
     rows = plan.slots_pad * 16
     w = plan.packed
-    names = ["X", "qkv", "ao", "hid", "mod", "cls", "temb", "acc", "tvals"]
+    names = ["X", "mod", "cls", "temb", "acc", "tvals"]
     o = {k: base + int(offs[i]) for i, k in enumerate(names)}
 
     def view(off, nbytes, dtype, shape):
         return ws[off: off + nbytes].view(dtype).view(*shape)
 
-    X = view(o["X"], rows * 256 * 4, torch.float32, (rows, 256))
-    if get_option("mega") == 2 and w.use_fused_attn and w.use_fused_mlp:
-        # dit_stack_kernel keeps the residual stream tile-blocked: [tile][col / 4][row % 128][4] (csrc/dit_kernels.cuh: x_index)
-        X = X.view(rows // 128, 64, 128, 4).permute(0, 2, 1, 3).reshape(rows, 256)
+    # dit_stack_kernel keeps the residual stream tile-blocked: [tile][col / 4][row % 128][4] (csrc/dit_kernels.cuh: x_index)
+    X = view(o["X"], rows * 256 * 4, torch.float32, (rows // 128, 64, 128, 4)).permute(0, 2, 1, 3).reshape(rows, 256)
     return {
         "X": X,
-        "qkv": view(o["qkv"], rows * 768 * 2, torch.bfloat16, (rows // 128, 12, 128 * 64)),
-        "ao": view(o["ao"], rows * 256 * 2, torch.bfloat16, (rows // 128, 4, 128 * 64)),
-        "hid": view(o["hid"], (rows // 128) * w.hid_slabs * 16384, torch.bfloat16, (rows // 128, w.hid_slabs, 128 * 64)),
         "mod": view(o["mod"], plan.mod_pad * w.mod_stride * 4, torch.float32, (plan.mod_pad, w.mod_stride)),
         "cls": view(o["cls"], plan.mod_pad * 256 * 4, torch.float32, (plan.mod_pad, 256)),
         "temb": view(o["temb"], plan.mod_pad * 256 * 4, torch.float32, (plan.mod_pad, 256)),
@@ -446,7 +441,7 @@ def prof_summary() -> dict[str, tuple[int, float]]:
 
 
 def set_option(name: str, value: int) -> None:
-    """Runtime switch of the library (`scldm_set_option`): "mega", "pdl", "mod_batch", "exp", "dec_cpb", "dec_occ"."""
+    """Runtime switch of the library (`scldm_set_option`): "solve", "pdl", "mod_batch", "dec_cpb", "dec_occ"."""
     _lib.check(_lib.load().scldm_set_option(name.encode(), int(value)), "scldm_set_option")
 
 

@@ -89,12 +89,9 @@ class PackedDiT:
         self.w_mod = dev(pack_kmajor_tiles(torch.cat(mod_w, 0), BLOCK_N))
         self.b_mod = f32(torch.cat(mod_b, 0))
         self.mod_stride = L * 6 * D + 2 * D
-        self.w_qkv = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.attn.c_attn.weight"), BLOCK_N) for i in range(L)]))
         self.b_qkv = f32(torch.stack([get(f"blocks.{i}.attn.c_attn.bias", (3 * D,)) for i in range(L)]))
-        self.w_proj = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.attn.c_proj.weight"), BLOCK_N) for i in range(L)]))
-        self.b_proj = f32(torch.stack([get(f"blocks.{i}.attn.c_proj.bias", (D,)) for i in range(L)]))
-        # fused attention-block weight stream (csrc/dit_kernels.cuh: attn_block_kernel): per head pair hp the items
-        # Q_hp = [Wq | Wk | Wv rows 64hp..64hp+63] as four 192 x 64 slabs, P_hp = c_proj[:, 64hp..] as two 128 x 64 slabs
+        # attention weight stream (csrc/dit_stack.cuh): per head pair hp the items Q_hp = [Wq | Wk | Wv rows 64hp..64hp+63] as four
+        # 192 x 64 slabs, P_hp = c_proj[:, 64hp..64hp+63] as one 256 x 64 slab (two 128-row halves, contiguous)
         streams, biases = [], []
         for i in range(L):
             wqkv, wp = get(f"blocks.{i}.attn.c_attn.weight"), get(f"blocks.{i}.attn.c_proj.weight")
@@ -114,37 +111,31 @@ class PackedDiT:
         self.w_attn_stream = dev(torch.stack(streams))
         assert self.w_attn_stream.shape[1] == 4 * D * D
         self.b_proj_fused = f32(torch.stack(biases).float())
-        self.use_fused_attn = os.environ.get("SCLDM_FUSED_ATTN", "1") != "0"
-        self.mlp1_tiles = -(-H // 128)
+        # MLP weight stream: M1_0, M1_1, M2_0, M1_2, M2_1, ..., M2_{T-1}.  M1_j = the [w1 | w2] rows of hidden chunk j (128 units; the
+        # last chunk padded to a multiple of 32 only) as four K slabs, w1 halved (exact in bf16): the SwiGLU epilogue computes
+        # SiLU(2h) = h + h tanh(h);  M2_j = the one or two 256 x 64 c_proj slabs of chunk j
+        self.mlp1_tiles = T = -(-H // 128)
         self.hid_slabs = -(-H // 64)
-        mlp1 = []
-        for i in range(L):
-            w1 = torch.zeros(self.mlp1_tiles * 128, D)
-            w2 = torch.zeros(self.mlp1_tiles * 128, D)
-            w1[:H] = 0.5 * get(f"blocks.{i}.mlp.w1.weight")   # halved (exact in bf16): the SwiGLU epilogue computes SiLU(2h) = h + h tanh(h)
-            w2[:H] = get(f"blocks.{i}.mlp.w2.weight")
-            # N tile j = [w1 rows 128j..128j+127 | w2 rows 128j..128j+127] so SwiGLU pairs share an accumulator tile
-            inter = torch.stack([w1.view(self.mlp1_tiles, 128, D), w2.view(self.mlp1_tiles, 128, D)], 1).reshape(-1, D)
-            mlp1.append(pack_kmajor_tiles(inter, BLOCK_N))
-        self.w_mlp1 = dev(torch.stack(mlp1))
-        self.w_mlp2 = dev(torch.stack([pack_kmajor_tiles(get(f"blocks.{i}.mlp.c_proj.weight"), BLOCK_N)[0] for i in range(L)]))
-        assert self.w_mlp2.shape[1] == self.hid_slabs
-        # fused-MLP weight stream: M1_0, M1_1, M2_0, M1_2, M2_1, ..., M2_{T-1} (csrc/dit_kernels.cuh: mlp_fused_kernel)
-        T = self.mlp1_tiles
+        self.hid_last = -(-(H - 128 * (T - 1)) // 32) * 32
         streams = []
         for i in range(L):
-            m1, m2 = self.w_mlp1[i], self.w_mlp2[i]   # [T][4][256*64], [hid_slabs][256*64]
+            w1, w2, w3 = 0.5 * get(f"blocks.{i}.mlp.w1.weight"), get(f"blocks.{i}.mlp.w2.weight"), get(f"blocks.{i}.mlp.c_proj.weight")
+            m2 = pack_kmajor_tiles(w3, BLOCK_N)[0]   # [hid_slabs][256*64]
             parts = []
             for j in range(T + 1):
                 if j < T:
-                    parts.append(m1[j])
+                    cw = 128 if j + 1 < T else self.hid_last
+                    tile = torch.zeros(2 * cw, D)
+                    n = min(128 * j + cw, H) - 128 * j
+                    tile[:n] = w1[128 * j: 128 * j + n]
+                    tile[cw: cw + n] = w2[128 * j: 128 * j + n]
+                    parts.append(pack_kmajor_tiles(tile, 2 * cw).reshape(-1))
                 if j >= 1:
                     c = j - 1
-                    parts.append(m2[2 * c: min(2 * c + 2, self.hid_slabs)])
-            streams.append(torch.cat(parts, 0))
-        self.w_mlp_stream = torch.stack(streams).contiguous()
-        assert self.w_mlp_stream.shape[1] == 4 * T + self.hid_slabs
-        self.use_fused_mlp = os.environ.get("SCLDM_FUSED_MLP", "1") != "0"
+                    parts.append(m2[2 * c: min(2 * c + 2, self.hid_slabs)].reshape(-1))
+            streams.append(torch.cat(parts))
+        self.w_mlp_stream = dev(torch.stack(streams))
+        assert self.w_mlp_stream.shape[1] == ((T - 1) * 4 + self.hid_slabs) * BLOCK_N * BLOCK_K + 4 * 2 * self.hid_last * BLOCK_K
         self.temb_w0t = f32(get("t_embedder.mlp.0.weight").T)
         self.temb_b0 = f32(get("t_embedder.mlp.0.bias"))
         self.temb_w2t = f32(get("t_embedder.mlp.2.weight").T)
@@ -158,18 +149,25 @@ class PackedDiT:
         # tensor-core final step (csrc/dit_kernels.cuh: final_step_tc_kernel)
         self.wout_frag = dev(mma_b_frags(get("final_layer.linear.weight")))   # [16][2][32][4]
         self.win_frag = dev(mma_b_frags(get("input_proj.weight")))            # [1][32][32][4]
-        self.use_tc_final = os.environ.get("SCLDM_TC_FINAL", "1") != "0"
+        # whole-solve kernel (csrc/dit_stack.cuh): input projection + pos_embed + bias as ONE K = 64 MMA group: the A row of a token is
+        # [state hi (16 bf16) | state lo | one-hot(token) | one-hot(token)], the B row of channel n below; then final_layer.linear as
+        # four 16 x 64 slabs
+        posb = get("pos_embed").reshape(cfg.seq_len, D) + get("input_proj.bias", (D,))[None, :]
+        posb_hi = posb.to(torch.bfloat16).float()
+        w_in2 = torch.zeros(D, BLOCK_K)   # row n: [Win[n, :] | Win[n, :] | posb_hi[:, n] | posb_lo[:, n]]: the last two multiply one-hot(token)
+        w_in2[:, :16] = get("input_proj.weight")
+        w_in2[:, 16:32] = get("input_proj.weight")
+        w_in2[:, 32:48] = posb_hi.T
+        w_in2[:, 48:64] = (posb - posb_hi).T
+        self.w_solve = dev(torch.cat([pack_kmajor_tiles(w_in2, BLOCK_N).reshape(-1), pack_kmajor_tiles(get("final_layer.linear.weight"), 16).reshape(-1)]))
+        assert self.w_solve.numel() == BLOCK_N * BLOCK_K + 4 * 16 * BLOCK_K
+        self.posb = f32(posb)
 
         s = _lib.DitWeights()
         s.n_layer, s.hidden, s.hid_slabs, s.mlp1_tiles = L, H, self.hid_slabs, self.mlp1_tiles
         s.mod_stride, s.n_class, s.eps = self.mod_stride, len(self.class_names), float(cfg.layernorm_eps)
-        s.w_mlp_stream = self.w_mlp_stream.data_ptr() if self.use_fused_mlp else None
-        s.w_attn_stream = self.w_attn_stream.data_ptr() if self.use_fused_attn else None
-        s.b_proj_fused = self.b_proj_fused.data_ptr() if self.use_fused_attn else None
-        s.wout_frag = self.wout_frag.data_ptr() if self.use_tc_final else None
-        s.win_frag = self.win_frag.data_ptr() if self.use_tc_final else None
-        for name in ("w_mod", "b_mod", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_mlp1", "w_mlp2", "temb_w0t", "temb_b0",
-                     "temb_w2t", "temb_b2", "w_in", "b_in", "pos", "w_out", "b_out"):
+        for name in ("w_mod", "b_mod", "b_qkv", "w_mlp_stream", "w_attn_stream", "b_proj_fused", "wout_frag", "win_frag", "temb_w0t", "temb_b0",
+                     "temb_w2t", "temb_b2", "w_in", "b_in", "pos", "w_out", "b_out", "w_solve", "posb"):
             setattr(s, name, getattr(self, name).data_ptr())
         for i, t in enumerate(self.class_tables):
             s.class_tables[i] = t.data_ptr()

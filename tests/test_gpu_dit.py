@@ -84,19 +84,11 @@ def test_intermediates_one_layer():
     errs["temb"] = rel_l2(views["temb"][:n], temb)
     errs["mod_block0"] = rel_l2(views["mod"][:n, :1536], mod0)
     errs["mod_final"] = rel_l2(views["mod"][:n, 1536:2048], modf)
-    if not packed.use_fused_attn:  # the fused attention-block kernel keeps q/k/v and the attention output on chip
-        qkv_gpu = unpack_kmajor_tiles(views["qkv"].cpu(), 128)[: n * 16]
-        errs["qkv"] = rel_l2(qkv_gpu.float(), qkv.reshape(n * 16, 768))
-        ao_gpu = unpack_kmajor_tiles(views["ao"].cpu(), 128).view(-1, 128, 256).reshape(-1, 256)[: n * 16]
-        errs["attn_out"] = rel_l2(ao_gpu.float(), ao.reshape(n * 16, 256))
-    if not packed.use_fused_mlp:  # the fused MLP kernel keeps the hidden activations on chip
-        hid_gpu = unpack_kmajor_tiles(views["hid"].cpu(), 128)[: n * 16, : cfg.hidden]
-        errs["hidden"] = rel_l2(hid_gpu.float(), hid.reshape(n * 16, -1))
     errs["x_final"] = rel_l2(views["X"][: n * 16], x2.reshape(n * 16, 256))
     errs["v"] = rel_l2(v, v_ref)
     print("stage errors:", {k: f"{e:.2e}" for k, e in errs.items()})
     assert errs["cls"] < 1e-6 and errs["temb"] < 1e-4
-    for k in ("mod_block0", "mod_final", "qkv", "attn_out", "hidden", "x_final", "v"):
+    for k in ("mod_block0", "mod_final", "x_final", "v"):
         assert errs.get(k, 0.0) < TOL_FWD, (k, errs)
 
 

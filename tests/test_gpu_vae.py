@@ -599,5 +599,5 @@ def test_torch_library_ops_run_the_same_kernels():
     x = torch.cat([z, z])
     grid = torch.linspace(0, 1, 6)
     assert torch.equal(torch.ops.scldm_b200.dit_sample_ode(x, grid, "euler", hp), ops.dit_sample_ode(plan, x.clone(), grid, "euler"))
-    assert ops.get_option("mega") == 2 and ops.get_option("nonexistent") == -1
+    assert ops.get_option("solve") == 1 and ops.get_option("nonexistent") == -1
     torch_ops.release(hd), torch_ops.release(he), torch_ops.release(hp)

@@ -1,6 +1,5 @@
-"""The per-phase and unfused kernel variants must reproduce the same golden vectors as the default persistent
-block-stack kernel.  The variants are selected by environment switches that are read when the library / the packed
-weights are created, so each one runs in a fresh interpreter."""
+"""The non-default launch structures must reproduce the same golden vectors as the default (one kernel per fixed-grid solve).
+The switches are read when the library is loaded, so each variant runs in a fresh interpreter."""
 import os
 import subprocess
 import sys
@@ -10,9 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 VARIANTS = {
-    "first_generation_block_stack_kernel": {"SCLDM_MEGA": "1"},
-    "one_kernel_per_block_half": {"SCLDM_MEGA": "0"},
-    "unfused_no_pdl": {"SCLDM_MEGA": "0", "SCLDM_FUSED_ATTN": "0", "SCLDM_FUSED_MLP": "0", "SCLDM_TC_FINAL": "0", "SCLDM_PDL": "0"},
+    "one_launch_per_evaluation": {"SCLDM_SOLVE": "0"},
+    "no_pdl_modulation_per_evaluation": {"SCLDM_SOLVE": "0", "SCLDM_PDL": "0", "SCLDM_MOD_BATCH": "0"},
 }
 
 

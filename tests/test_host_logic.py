@@ -46,13 +46,21 @@ def test_dit_pack_layout_cpu():
     mod = pack.unpack_kmajor_tiles(pk.w_mod, 256)
     assert torch.equal(mod[1536:3072], sd["blocks.1.adaln_modulation.1.weight"].to(torch.bfloat16))
     assert torch.equal(mod[3072:3584], sd["final_layer.adaln_modulation.1.weight"].to(torch.bfloat16))
-    m1 = pack.unpack_kmajor_tiles(pk.w_mlp1[1], 256)  # layer 1: [6*256, 256]
-    assert torch.equal(m1[256:256 + 128], (0.5 * sd["blocks.1.mlp.w1.weight"][128:256]).to(torch.bfloat16))   # stored halved (silu_from_half)
-    assert torch.equal(m1[256 + 128:512], sd["blocks.1.mlp.w2.weight"][128:256].to(torch.bfloat16))
-    assert torch.equal(m1[5 * 256:5 * 256 + 44], (0.5 * sd["blocks.1.mlp.w1.weight"][640:684]).to(torch.bfloat16))
-    assert float(m1[5 * 256 + 44:5 * 256 + 128].abs().max()) == 0
-    m2 = pack.unpack_kmajor_tiles(pk.w_mlp2[0].unsqueeze(0), 256)
-    assert torch.equal(m2[:, :684], sd["blocks.0.mlp.c_proj.weight"].to(torch.bfloat16))
+    # MLP stream of layer 1: M1_0 M1_1 M2_0 M1_2 M2_1 ... ; full [w1|w2] tiles are 4 x (256 x 64), the last one 4 x (2 hid_last x 64)
+    assert pk.hid_last == 64
+    st = pk.w_mlp_stream[1]
+    tile, slab = 4 * 256 * 64, 256 * 64
+    m1_1 = pack.unpack_kmajor_tiles(st[tile: 2 * tile].view(1, 4, slab), 256)                 # M1_1 follows M1_0
+    assert torch.equal(m1_1[:128], (0.5 * sd["blocks.1.mlp.w1.weight"][128:256]).to(torch.bfloat16))   # stored halved (silu_from_half)
+    assert torch.equal(m1_1[128:], sd["blocks.1.mlp.w2.weight"][128:256].to(torch.bfloat16))
+    m2_0 = pack.unpack_kmajor_tiles(st[2 * tile: 2 * tile + 2 * slab].view(1, 2, slab), 256)  # then the two c_proj slabs of chunk 0
+    assert torch.equal(m2_0, sd["blocks.1.mlp.c_proj.weight"][:, :128].to(torch.bfloat16))
+    off = 5 * tile + 8 * slab                                                                  # M1_0..M1_4 and M2_0..M2_3 precede M1_5
+    last = pack.unpack_kmajor_tiles(st[off: off + 4 * 128 * 64].view(1, 4, 128 * 64), 128)    # [w1 64 | w2 64] rows
+    assert torch.equal(last[:44], (0.5 * sd["blocks.1.mlp.w1.weight"][640:684]).to(torch.bfloat16))
+    assert float(last[44:64].abs().max()) == 0 and float(last[64 + 44:].abs().max()) == 0
+    assert torch.equal(last[64:64 + 44], sd["blocks.1.mlp.w2.weight"][640:684].to(torch.bfloat16))
+    assert st.numel() == off + 4 * 128 * 64 + 3 * slab                                          # + M2_4 (2 slabs) + M2_5 (1 slab)
 
 
 def test_attention_stream_pack_layout_cpu():
@@ -261,7 +269,7 @@ def test_abi_library_loads_and_exports_declared_symbols():
     assert b"sm_100a" in lib.scldm_version()
     assert lib.scldm_vae_decode_workspace_bytes(4, 1000) > 4 * 1000 * 4
     # ctypes struct sizes match the C structs (8-byte pointers, natural alignment)
-    assert ctypes.sizeof(_lib.DitWeights) == 7 * 4 + 4 + 22 * 8 + 8 * 8
+    assert ctypes.sizeof(_lib.DitWeights) == 7 * 4 + 4 + 19 * 8 + 8 * 8   # 7 ints + pad, 17 + 2 pointers, 8 class tables
     assert ctypes.sizeof(_lib.DitPlan) == 3 * 4 + 8 * 4 + 4 + 2 * 8 + 8
 
 
