@@ -180,6 +180,36 @@ def test_batch_invariance_and_padding():
     assert torch.equal(full[5:14], part)
 
 
+@pytest.mark.parametrize("multiple_of,hidden,odd", [(48, 720, False), (256, 768, False), (64, 704, True)])
+def test_other_hidden_widths_and_odd_unguided_count(multiple_of, hidden, odd):
+    """SwiGLU widths whose last hidden chunk is 96 / 128 / 64 units wide (the shipped 684 pads to 64), through a whole-solve launch
+    (3-step Euler with CFG) and through a plain forward; `odd`: an odd number of unguided states, which shifts the guided slots by
+    one inside the whole-solve kernel."""
+    from scldm_b200 import ops
+    from scldm_b200.transport.transport import FusedCFGModel, Sampler, create_transport
+
+    cfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=2, multiple_of=multiple_of)
+    assert cfg.hidden == hidden
+    dit, sd = make_dit(cfg)
+    B = 21 if odd else 20
+    x = synthetic.randn("hw.x", (2 * B, 16, 16))
+    lab = {"clusters": synthetic.randint("hw.lab", 14, (2 * B,))}
+    t = torch.full((2 * B,), 0.41)
+    out = dit.forward_with_cfg(x.cuda(), t.cuda(), {k: v.cuda() for k, v in lab.items()}, {"clusters": 2.0}).cpu()
+    with torch.no_grad():
+        ref = O.dit_forward_with_cfg(x, t, lab, {"clusters": 2.0}, sd, cfg)
+    assert rel_l2(out, ref) < 2 * TOL_FWD
+    assert ops.get_option("solve") == 1
+    fn = Sampler(create_transport("Linear", "velocity", "velocity")).sample_ode(sampling_method="euler", num_steps=4)
+    got = fn(x.cuda(), FusedCFGModel(dit, {"clusters": 2.0}), condition={k: v.cuda() for k, v in lab.items()})[-1].cpu()
+    with torch.no_grad():
+        xs, ts = x.clone(), torch.linspace(0, 1, 4)
+        for k in range(3):
+            v = O.dit_forward_with_cfg(xs, torch.full((2 * B,), float(ts[k])), lab, {"clusters": 2.0}, sd, cfg)
+            xs = xs + (ts[k + 1] - ts[k]) * v
+    assert rel_l2(got, xs) < TOL_TRAJ * 2
+
+
 def test_large_batch_matches_oracle_sample():
     """B=300 cells with CFG: every row finite, random rows match the oracle."""
     cfg = DiTConfig(class_vocab_sizes={"clusters": 14}, n_layer=2)
