@@ -76,7 +76,6 @@ typedef struct scldm_dit_weights {
                            its bf16 lo part] (the state enters as bf16 hi | lo parts followed by one-hot(token) twice), then
                            final_layer.linear.weight as four 16 x 64 slabs.  NULL: one block-stack launch + one step kernel per
                            evaluation                                                                                         */
-  const float* posb;    /* [16][256] pos_embed + input_proj.bias in fp32 (informational; the kernel uses the slab above)       */
 } scldm_dit_weights;
 
 /* Which model evaluations one call performs and how they are combined.

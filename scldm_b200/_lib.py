@@ -33,7 +33,7 @@ class DitWeights(C.Structure):
         ("w_in", C.c_void_p), ("b_in", C.c_void_p), ("pos", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
         ("wout_frag", C.c_void_p), ("win_frag", C.c_void_p),
         ("class_tables", C.c_void_p * MAX_CLASSES),
-        ("w_solve", C.c_void_p), ("posb", C.c_void_p),
+        ("w_solve", C.c_void_p),
     ]
 
 

@@ -251,7 +251,7 @@ dit::StackParams stack_params(const scldm_dit_weights* w, const scldm_dit_plan* 
 // Fixed-grid solves whose modulation tables were all precomputed run as ONE launch of dit_stack_kernel when a state has at most
 // two slots (plain forwards, CFG of a 1-class or joint model): the kernel keeps the two slots of a guided state in one warp.
 bool use_solve(const scldm_dit_weights* w, const scldm_dit_plan* plan, size_t batch_rows) {
-  if (!g_opt_solve || !w->w_solve || !w->posb || batch_rows == 0) return false;
+  if (!g_opt_solve || !w->w_solve || batch_rows == 0) return false;
   return plan->n_g == 0 || plan->n_f <= 2;
 }
 
@@ -456,7 +456,7 @@ int scldm_dit_sample_ode(const scldm_dit_weights* w, const scldm_dit_plan* plan,
     sp.slot_shift = slot_shift;
     sp.X = nullptr; sp.io_blocked = 0; sp.scratch = ws.X;   // residual rows: one CTA-private tile each, L2 resident
     sp.n_evals = n_evals; sp.mod_eval_stride = (long long)plan->n_mod * w->mod_stride; sp.stage = ws.stage;
-    sp.w_solve = static_cast<const dit::bf16*>(w->w_solve); sp.posb = w->posb; sp.b_out = w->b_out;
+    sp.w_solve = static_cast<const dit::bf16*>(w->w_solve); sp.b_out = w->b_out;
     sp.x_base = x; sp.acc = ws.acc;
     sp.n_u = plan->n_u; sp.n_g = plan->n_g; sp.n_f = n_f;
     sp.coef[0] = plan->coef[0]; sp.coef[1] = plan->coef[1];

@@ -1,7 +1,8 @@
-// dit_stack_kernel: the adaLN block stack of the DiT denoiser (reference layers.py:208-221, nnets.py:273-297) as one
-// persistent kernel, second generation.
+// dit_stack_kernel: the adaLN block stack of the DiT denoiser (reference layers.py:208-221, nnets.py:273-297) as one persistent
+// kernel - and, in whole-solve mode (template argument SOLVE, see StackParams), every evaluation of a fixed-grid ODE solve with its
+// input projection, final layer, CFG combine and Runge-Kutta stage updates in ONE launch.
 //
-// What changed against dit_blocks_kernel (dit_kernels.cuh), and why:
+// Design points (what changed against the first-generation block kernel of round 1, and why):
 //   * The residual stream is kept in a TILE-BLOCKED layout in global memory / L2:  X[tile][c4 = col / 4][row (128)][4 floats].
 //     A TMEM accumulator arrives row-per-lane (tcgen05.ld 32x32b); with this layout the lane that owns a row reads and writes
 //     that row's residual values as 16-byte accesses that are contiguous across the warp (512 B per instruction): the
@@ -80,8 +81,7 @@ struct StackParams {
   int n_evals;
   long long mod_eval_stride;   // floats between the modulation tables of consecutive evaluations
   const float4* stage;         // [n_evals] {a_dt, b_dt, first_stage, last_stage}: acc (+)= b_dt v; last: x += acc; else x_eval = x + a_dt v
-  const bf16* w_solve;         // input-projection slab (32 KB) + final-linear slabs (8 KB), pack.py
-  const float* posb;           // [16][256] pos_embed + input_proj.bias
+  const bf16* w_solve;         // input projection + pos_embed + bias slab (32 KB), final-linear slabs (8 KB), pack.py
   const float* b_out;          // [16] final_layer.linear.bias
   float* x_base;               // [n_states][16][16] ODE state, updated in place
   float* acc;                  // [n_states][16][16] stage accumulator (multi-stage methods)

@@ -161,13 +161,12 @@ class PackedDiT:
         w_in2[:, 48:64] = (posb - posb_hi).T
         self.w_solve = dev(torch.cat([pack_kmajor_tiles(w_in2, BLOCK_N).reshape(-1), pack_kmajor_tiles(get("final_layer.linear.weight"), 16).reshape(-1)]))
         assert self.w_solve.numel() == BLOCK_N * BLOCK_K + 4 * 16 * BLOCK_K
-        self.posb = f32(posb)
 
         s = _lib.DitWeights()
         s.n_layer, s.hidden, s.hid_slabs, s.mlp1_tiles = L, H, self.hid_slabs, self.mlp1_tiles
         s.mod_stride, s.n_class, s.eps = self.mod_stride, len(self.class_names), float(cfg.layernorm_eps)
         for name in ("w_mod", "b_mod", "b_qkv", "w_mlp_stream", "w_attn_stream", "b_proj_fused", "wout_frag", "win_frag", "temb_w0t", "temb_b0",
-                     "temb_w2t", "temb_b2", "w_in", "b_in", "pos", "w_out", "b_out", "w_solve", "posb"):
+                     "temb_w2t", "temb_b2", "w_in", "b_in", "pos", "w_out", "b_out", "w_solve"):
             setattr(s, name, getattr(self, name).data_ptr())
         for i, t in enumerate(self.class_tables):
             s.class_tables[i] = t.data_ptr()

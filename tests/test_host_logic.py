@@ -269,7 +269,7 @@ def test_abi_library_loads_and_exports_declared_symbols():
     assert b"sm_100a" in lib.scldm_version()
     assert lib.scldm_vae_decode_workspace_bytes(4, 1000) > 4 * 1000 * 4
     # ctypes struct sizes match the C structs (8-byte pointers, natural alignment)
-    assert ctypes.sizeof(_lib.DitWeights) == 7 * 4 + 4 + 19 * 8 + 8 * 8   # 7 ints + pad, 17 + 2 pointers, 8 class tables
+    assert ctypes.sizeof(_lib.DitWeights) == 7 * 4 + 4 + 18 * 8 + 8 * 8   # 7 ints + pad, 18 pointers, 8 class tables
     assert ctypes.sizeof(_lib.DitPlan) == 3 * 4 + 8 * 4 + 4 + 2 * 8 + 8
 
 
