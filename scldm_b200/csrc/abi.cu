@@ -313,6 +313,7 @@ int prepare_kernels() {
     g_sms_of[dev] = n > 0 ? n : 148;
     g_num_sms = g_sms_of[dev];
   }
+  if ((rc = set_smem(vae::dec_latent_multi_kernel, vae::dec_latent_multi_smem_bytes()))) return rc;
   if ((rc = set_smem(vae::mcab_decode_kernel, (vae::MW_TOTAL + vae::TOK * vae::KV) * sizeof(float)))) return rc;
   done[dev].store(1);
   return SCLDM_OK;
@@ -535,7 +536,7 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
   dp.z = z; dp.win_t = w->win_t; dp.blocks = w->blocks; dp.n_layer = w->n_layer;
   dp.ca_ln1_w = w->ca_ln1_w; dp.ca_ln1_b = w->ca_ln1_b; dp.ca_wkv_t = w->ca_wkv_t; dp.eps = w->eps;
   dp.kv = tc ? nullptr : kv; dp.kvb = tc ? kvb : nullptr;
-  LAUNCH("dec_latent", vae::dec_latent_kernel<<<n_cells, 128, 0, st>>>(dp, n_cells));
+  LAUNCH("dec_latent", vae::dec_latent_multi_kernel<<<ceil_div(n_cells, vae::DL_CELLS), 128 * vae::DL_CELLS, vae::dec_latent_multi_smem_bytes(), st>>>(dp, n_cells));
 
   // enough blocks for ~4 waves, but amortise the gene-side loads over several cells
   int cpb = (int)(((long long)tiles * n_cells) / (148LL * 2 * 4));

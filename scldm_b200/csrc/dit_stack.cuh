@@ -856,22 +856,6 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
         // ---- v = final Linear (+ bias), CFG combine, Runge-Kutta stage update, next evaluation point (column quarter 0 warps) ----
         long long* dbs = (p.dbg != nullptr && tile_no == 1 && etid == 0) ? p.dbg + (size_t)blockIdx.x * 128 : nullptr;
         if (dbs) dbs[48] = clock64();
-        // the state, the accumulator and the coefficients are fetched while the final Linear runs
-        const RowState rs1 = row_state();
-        const int st_state = rs1.state, st_k = rs1.k;
-        const bool st_valid = rs1.valid, st_pair = rs1.pair;
-        float* xb = p.x_base + ((size_t)st_state * TOK + (row & 15)) * LAT;
-        float* ac = p.acc + ((size_t)st_state * TOK + (row & 15)) * LAT;
-        float4 stg4 = make_float4(0.f, 0.f, 0.f, 0.f), xb4[4], ac4[4], bo4[4];
-        if (sub == 0) {
-          stg4 = p.stage[e];   // {a_dt, b_dt, first_stage, last_stage}
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            bo4[i] = *reinterpret_cast<const float4*>(p.b_out + 4 * i);
-            xb4[i] = st_valid ? *reinterpret_cast<const float4*>(xb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            ac4[i] = st_valid ? *reinterpret_cast<const float4*>(ac + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
         sm100::mbar_wait(accA_full, n_accA & 1); ++n_accA;
         sm100::tc_fence_after();
         if (dbs) dbs[49] = clock64();
@@ -882,12 +866,21 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
           sm100::tc_fence_before();
           __syncwarp();
           if (lane == 0) sm100::mbar_arrive(accA_free);
+          const RowState rs1 = row_state();
+          const int st_state = rs1.state, st_k = rs1.k;
+          const bool st_valid = rs1.valid, st_pair = rs1.pair;
+          float* xb = p.x_base + ((size_t)st_state * TOK + (row & 15)) * LAT;
+          float* ac = p.acc + ((size_t)st_state * TOK + (row & 15)) * LAT;
+          const float4 stg4 = p.stage[e];   // {a_dt, b_dt, first_stage, last_stage}
+          float4 xb4[4], ac4[4];
           float v[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            v[4 * i + 0] = __uint_as_float(o16[4 * i + 0]) + bo4[i].x; v[4 * i + 1] = __uint_as_float(o16[4 * i + 1]) + bo4[i].y;
-            v[4 * i + 2] = __uint_as_float(o16[4 * i + 2]) + bo4[i].z; v[4 * i + 3] = __uint_as_float(o16[4 * i + 3]) + bo4[i].w;
-            if (stg4.z != 0.f) ac4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // first stage: the accumulator starts from zero
+            const float4 bo = *reinterpret_cast<const float4*>(p.b_out + 4 * i);
+            xb4[i] = st_valid ? *reinterpret_cast<const float4*>(xb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ac4[i] = (st_valid && stg4.z == 0.f) ? *reinterpret_cast<const float4*>(ac + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * i + 0] = __uint_as_float(o16[4 * i + 0]) + bo.x; v[4 * i + 1] = __uint_as_float(o16[4 * i + 1]) + bo.y;
+            v[4 * i + 2] = __uint_as_float(o16[4 * i + 2]) + bo.z; v[4 * i + 3] = __uint_as_float(o16[4 * i + 3]) + bo.w;
           }
           // a guided state owns two consecutive slots = lanes l and l ^ 16 of this warp: v = c0 v_0 + c1 v_1
           const float c_mine = st_pair ? p.coef[st_k] : 1.f, c_other = st_pair ? p.coef[st_k ^ 1] : 0.f;

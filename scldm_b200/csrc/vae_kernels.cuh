@@ -1,6 +1,6 @@
 // Transformer-VAE decoder kernels (scLDM generation hot path), fp32 CUDA-core first version.
 //
-//   dec_latent_kernel   per cell: LN16 -> Linear(16->32) -> n_layer Blocks (E=32, 8 heads of 4) ->
+//   dec_latent_multi_kernel   per cell: LN16 -> Linear(16->32) -> n_layer Blocks (E=32, 8 heads of 4) ->
 //                       K,V = c_attn(LN1(x)) of the MCAB (16 keys x 64)      nnets.py:203-205, layers.py:252
 //   qside_kernel        per gene id: Qp = c_attn_q(LN1q(emb[g]))  -- cell-invariant when use_adaln=false,
 //                       computed once per vocabulary                            layers.py:253,326
@@ -75,11 +75,12 @@ __device__ __forceinline__ void ln32_tokens(const float (*x)[E], float (*y)[E], 
   }
 }
 
-// n_layer non-adaLN Blocks (layers.py:222-226) on a 16 x 32 tile in shared memory; nt = threads of the CTA (>= 128)
-__device__ __forceinline__ void vae_block_stack(float (*x)[E], float (*h)[E], float (*qkv)[3 * E], float (*hid)[HID],
-                                                const float* blocks, int n_layer, float eps, int tid, int nt) {
-  for (int l = 0; l < n_layer; ++l) {
-    const float* w = blocks + (size_t)l * BLOCK_STRIDE;
+// One non-adaLN Block (layers.py:222-226) on a 16 x 32 tile in shared memory; nt = threads working on this tile (>= 128), tid
+// their index; `w` = the block's packed weights (global or shared memory).  Every barrier is CTA-wide: all tiles of a CTA run
+// in lock-step.
+__device__ __forceinline__ void vae_block_layer(float (*x)[E], float (*h)[E], float (*qkv)[3 * E], float (*hid)[HID], const float* w, float eps,
+                                                int tid, int nt) {
+  {
     if (tid < 128) ln32_tokens(x, h, w + BLK_LN1W, w + BLK_LN1B, eps, tid);
     __syncthreads();
     for (int i = tid; i < TOK * 3 * E; i += nt) {
@@ -151,14 +152,30 @@ __device__ __forceinline__ void vae_block_stack(float (*x)[E], float (*h)[E], fl
   }
 }
 
-__global__ void __launch_bounds__(128) dec_latent_kernel(const DecLatentParams p, int n_cells) {
-  __shared__ float x[TOK][E];
-  __shared__ float h[TOK][E];
-  __shared__ float qkv[TOK][3 * E];
-  __shared__ float hid[TOK][HID];
-  const int cell = blockIdx.x, tid = threadIdx.x;
-  if (cell >= n_cells) return;
-  // LN over the 16 latent channels (no affine) then Linear(16 -> 32, no bias)
+// n_layer Blocks with the weights read from global memory (one tile per CTA)
+__device__ __forceinline__ void vae_block_stack(float (*x)[E], float (*h)[E], float (*qkv)[3 * E], float (*hid)[HID],
+                                                const float* blocks, int n_layer, float eps, int tid, int nt) {
+  for (int l = 0; l < n_layer; ++l) vae_block_layer(x, h, qkv, hid, blocks + (size_t)l * BLOCK_STRIDE, eps, tid, nt);
+}
+
+// Decoder front (nnets.py:200-205): LN16 -> Linear(16 -> 32) -> n_layer Blocks -> K/V of the MCAB, DL_CELLS cells per CTA (one
+// 128-thread group each) with every layer's weights staged in shared memory once per CTA.  (A one-cell-per-CTA version re-read 50 KB
+// of weights per layer and cell through L2 and was bound by that latency: 0.44 ms for 1184 cells.)
+constexpr int DL_CELLS = 4;
+constexpr int DL_ACT_FLOATS = TOK * (E + E + 3 * E + HID);   // x | h | qkv | hid of one cell
+constexpr size_t dec_latent_multi_smem_bytes() { return (size_t)(BLOCK_STRIDE + DL_CELLS * DL_ACT_FLOATS) * sizeof(float); }
+
+__global__ void __launch_bounds__(128 * DL_CELLS) dec_latent_multi_kernel(const DecLatentParams p, int n_cells) {
+  extern __shared__ __align__(16) float dl_smem[];
+  float* sw = dl_smem;                                   // one Block's weights
+  const int grp = threadIdx.x >> 7, tid = threadIdx.x & 127;
+  float* act = dl_smem + BLOCK_STRIDE + grp * DL_ACT_FLOATS;
+  float (*x)[E] = reinterpret_cast<float (*)[E]>(act);
+  float (*h)[E] = reinterpret_cast<float (*)[E]>(act + TOK * E);
+  float (*qkv)[3 * E] = reinterpret_cast<float (*)[3 * E]>(act + 2 * TOK * E);
+  float (*hid)[HID] = reinterpret_cast<float (*)[HID]>(act + 5 * TOK * E);
+  const int cell = min(blockIdx.x * DL_CELLS + grp, n_cells - 1);   // a surplus group recomputes the last cell (no divergent barriers)
+  const bool live = blockIdx.x * DL_CELLS + grp < n_cells;
   {
     float (*zs)[LAT] = reinterpret_cast<float (*)[LAT]>(&qkv[0][0]);
     for (int i = tid; i < TOK * LAT; i += 128) zs[i / LAT][i % LAT] = p.z[(size_t)cell * TOK * LAT + i];
@@ -180,12 +197,17 @@ __global__ void __launch_bounds__(128) dec_latent_kernel(const DecLatentParams p
       for (int k = 0; k < LAT; ++k) acc += zs[tok][k] * p.win_t[k * E + c];
       x[tok][c] = acc;
     }
-    __syncthreads();
   }
-  vae_block_stack(x, h, qkv, hid, p.blocks, p.n_layer, p.eps, tid, 128);
-  // MCAB key/value projection of the latents
+  for (int l = 0; l < p.n_layer; ++l) {
+    __syncthreads();   // the previous layer's readers of `sw` are done (and x is complete)
+    const float4* src = reinterpret_cast<const float4*>(p.blocks + (size_t)l * BLOCK_STRIDE);
+    for (int i = threadIdx.x; i < BLOCK_STRIDE / 4; i += 128 * DL_CELLS) reinterpret_cast<float4*>(sw)[i] = src[i];
+    __syncthreads();
+    vae_block_layer(x, h, qkv, hid, sw, p.eps, tid, 128);
+  }
   ln32_tokens(x, h, p.ca_ln1_w, p.ca_ln1_b, p.eps, tid);
   __syncthreads();
+  if (!live) return;
   for (int i = tid; i < TOK * KV; i += 128) {
     const int tok = i / KV, j = i % KV;
     float acc = 0.f;
@@ -198,6 +220,7 @@ __global__ void __launch_bounds__(128) dec_latent_kernel(const DecLatentParams p
     }
   }
 }
+static_assert(BLOCK_STRIDE % 4 == 0, "float4 staging of a Block's weights");
 
 // Qp[g] = Wq * LN1q(emb[g]) for every vocabulary id (incl. the mask id 0)
 __global__ void __launch_bounds__(128) qside_kernel(const float* __restrict__ emb, const float* __restrict__ ln_w,
