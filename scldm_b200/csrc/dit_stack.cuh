@@ -100,8 +100,9 @@ constexpr int S2_OFF_RING = S2_OFF_MID + 4 * A_SLAB_BYTES;      // 128 KB
 constexpr int S2_OFF_BIASQ = S2_OFF_RING + S2_NST * S2_STAGE;   // 224 KB
 constexpr int S2_OFF_BIASP = S2_OFF_BIASQ + D * 4;             // c_proj bias of the attention half (boundary pass 1)
 constexpr int S2_OFF_BARS = S2_OFF_BIASP + D * 4;
-enum { SB_FULL = 0, SB_EMPTY = 3, SB_A_READY = 6, SB_ACCA_FULL = 7, SB_ACCA_FREE = 8, SB_AO_READY = 9, SB_AO_FREE = 10,
-       SB_H_READY = 11, SB_H_FREE = 13, SB_ACCB_FULL = 15, SB_PARK_READY = 16, SB_PARK_DRAINED = 17, SB_XFULL = 18, SB_Z_READY = 19, SB_COUNT = 20 };
+enum { SB_FULL = 0, SB_EMPTY = 3, SB_ACCA_FULL = 7, SB_ACCA_FREE = 8, SB_AO_READY = 9, SB_AO_FREE = 10,
+       SB_H_READY = 11, SB_H_FREE = 13, SB_ACCB_FULL = 15, SB_PARK_READY = 16, SB_PARK_DRAINED = 17, SB_XFULL = 18, SB_Z_READY = 19,
+       SB_A_READY = 20 /* [4]: one per K slab of the A tile */, SB_COUNT = 24 };
 constexpr int S2_WARPS = 24, S2_THREADS = S2_WARPS * 32, S2_WORKER_WARP0 = 8, S2_DRAIN_WARP0 = 4;
 constexpr int S2_REGS_LAUNCH = 80, S2_REGS_IDLE = 56, S2_REGS_DRAIN = 40, S2_REGS_WORKER = 96;
 static_assert(S2_THREADS * S2_REGS_LAUNCH >= 128 * S2_REGS_IDLE + 128 * S2_REGS_DRAIN + 512 * S2_REGS_WORKER, "setmaxnreg budget");
@@ -117,7 +118,7 @@ constexpr int PK_GATE = 0, PK_MUL = 8192, PK_ADD = 16384, PK_EXCH = 24576;   // 
 enum { B_FIRST = 0, B_MID = 1, B_LAST = 2 };
 
 struct BoundaryArgs {
-  const float* xin;      // this lane's row of x_old at column 64 sub; consecutive 4-column groups are in_cs floats apart
+  const float* xin;      // column 0 of this lane's row of x_old; consecutive 4-column groups are in_cs floats apart
   int in_cs;
   const float* mod;
   const int* rows;       // shared memory: conditioning row of each of the tile's 8 slots
@@ -156,11 +157,15 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   if constexpr (HAS_BIAS) { if (etid < 64) bias_v = *reinterpret_cast<const float4*>(b.bias + etid * 4); }
   // the drain warps have written every earlier x_new (the rows read below) and are done with the TMEM park
   if (sy.n_drained > 0) sm100::mbar_wait(sy.park_drained, (sy.n_drained - 1) & 1);
-  uint32_t xr[32], xr2[32];
-  auto load_x = [&](uint32_t (&dst)[32], int half) {
+  // Column ownership of this warp: in every K slab j of the tile the 16 columns [64 j + 16 sub, + 16).  The passes walk the slabs in
+  // order ("step" st = slab st), so that the A tile of the next phase completes slab by slab and its first MMA group can start on
+  // slab 0 while the later slabs are still being normalised (per-slab a_ready barriers).
+  uint32_t xr[32], xr2[32];   // x_old of steps 0, 1 and 2, 3
+  auto load_x = [&](uint32_t (&dst)[32], int pair) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(b.xin + (half * 8 + i) * b.in_cs));
+      const int c4 = (2 * pair + (i >> 2)) * 16 + sub * 4 + (i & 3);   // 4-column group of the row
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(b.xin + c4 * b.in_cs));
       dst[4 * i + 0] = __float_as_uint(t.x); dst[4 * i + 1] = __float_as_uint(t.y);
       dst[4 * i + 2] = __float_as_uint(t.z); dst[4 * i + 3] = __float_as_uint(t.w);
     }
@@ -168,7 +173,7 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   constexpr bool has_x = HAS_X;   // false: the accumulator IS the new row (input projection incl. pos_embed + bias)
   if constexpr (has_x) {
     load_x(xr, 0);
-    if constexpr (KIND != B_FIRST) load_x(xr2, 1);   // nothing else is live here: both halves in flight at once
+    if constexpr (KIND != B_FIRST) load_x(xr2, 1);   // nothing else is live here: everything in flight at once
   }
   region_free();
   if (dbg && etid == 0) dbg[4] = clock64();
@@ -181,8 +186,8 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
   if constexpr (KIND != B_LAST) {
     if (b.next_bias_q != nullptr && etid < 64) reinterpret_cast<float4*>(b.sm_bias_q)[etid] = *reinterpret_cast<const float4*>(b.next_bias_q + etid * 4);
   }
-  const uint32_t taddrA = tmem_base + ((q * 32u) << 16) + sub * 64;   // dead chunk accumulator: staging of x_old
-  const uint32_t taddr = taddrA + 256;                                // c_proj accumulator, then the park of x_new
+  const uint32_t taddrA = tmem_base + ((q * 32u) << 16) + sub * 64;   // dead chunk accumulator: warp-private staging of x_old (step st at + 16 st)
+  const uint32_t taddr = tmem_base + ((q * 32u) << 16) + 256 + sub * 16;   // c_proj accumulator, then the park of x_new: step st at + 64 st
   if constexpr (KIND != B_FIRST) {
     // the old rows wait in TMEM while the phase's last MMAs retire (this warp writes and reads the same lanes / columns)
     if constexpr (has_x) {
@@ -227,12 +232,12 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
     for (int st = 0; st < 4; ++st) {
       sm100::tmem_ld_wait();
       if (st < 3) {
-        sm100::tmem_ld_32x32b_x16(taddr + (st + 1) * 16, av[(st + 1) & 1]);
+        sm100::tmem_ld_32x32b_x16(taddr + (st + 1) * 64, av[(st + 1) & 1]);
         if constexpr (has_x) sm100::tmem_ld_32x32b_x16(taddrA + (st + 1) * 16, xv[(st + 1) & 1]);
       }
       uint32_t (&v)[16] = av[st & 1];
       const uint32_t (&xo)[16] = xv[st & 1];
-      const int col0 = sub * 64 + st * 16;
+      const int col0 = st * 64 + sub * 16;
       if constexpr (has_x) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -248,7 +253,7 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
         sm100::unpack2u(a0, v[4 * i + 0], v[4 * i + 1]);
         sm100::unpack2u(a1, v[4 * i + 2], v[4 * i + 3]);
       }
-      tmem_st_32x32b_x16(taddr + st * 16, v);
+      tmem_st_32x32b_x16(taddr + st * 64, v);
       }
       if constexpr (KIND != B_LAST) {
         float m, qq;
@@ -262,17 +267,18 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
     }
   } else {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if (half == 1) load_x(xr, 1);
-      tmem_st_32x32b_x32(taddr + half * 32, xr);
-      float ma, qa, mb, qb;
+    for (int pair = 0; pair < 2; ++pair) {
+      if (pair == 1) load_x(xr, 1);
       uint32_t lo[16], hi[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { lo[i] = xr[i]; hi[i] = xr[16 + i]; }
+      tmem_st_32x32b_x16(taddr + (2 * pair) * 64, lo);
+      tmem_st_32x32b_x16(taddr + (2 * pair + 1) * 64, hi);
+      float ma, qa, mb, qb;
       stats16(lo, ma, qa);
       stats16(hi, mb, qb);
       const float dm = mb - ma;
-      exch[(sub * 2 + half) * BLOCK_M + row] = make_float2(0.5f * (ma + mb), fmaf(8.0f * dm, dm, qa + qb));
+      exch[(sub * 2 + pair) * BLOCK_M + row] = make_float2(0.5f * (ma + mb), fmaf(8.0f * dm, dm, qa + qb));
     }
   }
   tmem_st_wait();
@@ -301,19 +307,20 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
     rstd = rsqrtf(m2 * (1.0f / D) + b.eps);
   }
   if (dbg && etid == 0) dbg[2] = clock64();
-  // ---- pass 2: A tile of the next phase = bf16( (x_new - mean) * rstd * (1 + mul) + add ), K slab `sub` ----
-  uint8_t* a_slab = smem + sub * A_SLAB_BYTES;
+  // ---- pass 2: A tile of the next phase = bf16( (x_new - mean) * rstd * (1 + mul) + add ), slab by slab ----
   const sm100::f32x2 rstd2 = sm100::pack2(rstd, rstd), nmr2 = sm100::pack2(-mean * rstd, -mean * rstd);   // (x - mean) * rstd = fma(x, rstd, nmr)
-  uint32_t pv[2][32];
-  sm100::tmem_ld_32x32b_x32(taddr, pv[0]);
-  sm100::tmem_ld_32x32b_x32(taddr + 32, pv[1]);
+  uint32_t pv[4][16];
+#pragma unroll
+  for (int st = 0; st < 4; ++st) sm100::tmem_ld_32x32b_x16(taddr + st * 64, pv[st]);
   sm100::tmem_ld_wait();
+  sm100::tc_fence_before();
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const uint32_t (&v)[32] = pv[half];
-    const int col0 = sub * 64 + half * 32;
+  for (int st = 0; st < 4; ++st) {
+    const uint32_t (&v)[16] = pv[st];
+    const int col0 = st * 64 + sub * 16;
+    uint8_t* a_slab = smem + st * A_SLAB_BYTES;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       float h[8];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -329,13 +336,14 @@ __device__ __forceinline__ void boundary_step(const BoundaryArgs& b, const Bound
       o.y = sm100::pack_bf16x2(h[2], h[3]);
       o.z = sm100::pack_bf16x2(h[4], h[5]);
       o.w = sm100::pack_bf16x2(h[6], h[7]);
-      *reinterpret_cast<uint4*>(a_slab + sm100::swz_chunk_offset(row, half * 4 + c)) = o;
+      *reinterpret_cast<uint4*>(a_slab + sm100::swz_chunk_offset(row, sub * 2 + c)) = o;
+    }
+    if (st & 1) {   // one proxy fence per two slabs: this warp's share of K slabs st - 1 and st is in place
+      sm100::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { sm100::mbar_arrive(sy.a_ready + st - 1); sm100::mbar_arrive(sy.a_ready + st); }
     }
   }
-  sm100::tc_fence_before();
-  sm100::fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) sm100::mbar_arrive(sy.a_ready);
   if (dbg && etid == 0) dbg[3] = clock64();
 }
 
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
   if (warp == 1) sm100::tmem_alloc(tmem_ptr_smem, 512);
   if (threadIdx.x == 0) {
     for (int i = 0; i < SB_COUNT; ++i) {
-      const bool workers = i == SB_A_READY || i == SB_ACCA_FREE || i == SB_AO_READY || i == SB_H_READY || i == SB_H_READY + 1 || i == SB_PARK_READY;
+      const bool workers = (i >= SB_A_READY && i < SB_A_READY + 4) || i == SB_ACCA_FREE || i == SB_AO_READY || i == SB_H_READY || i == SB_H_READY + 1 || i == SB_PARK_READY;
       sm100::mbar_init(&bars[i], workers ? EPI_WARPS : ((i == SB_PARK_DRAINED || i == SB_Z_READY) ? 4 : 1));
     }
     sm100::fence_barrier_init();
@@ -483,13 +491,12 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
           ++n_dr;   // the boundary that follows is drained
         }
         for (int l = 0; l < p.n_layer; ++l) {
-          // ---- attention half: Q0 Q1 P0 Q2 P1 Q3 P2 P3 ----
-          sm100::mbar_wait(a_ready, n_ar & 1); ++n_ar;
-          sm100::tc_fence_after();
+          // ---- attention half: Q0 Q1 P0 Q2 P1 Q3 P2 P3 (Q0 follows the A tile slab by slab) ----
           for (int step = 0; step <= AB_HP; ++step) {
             if (step < AB_HP) {
               if (step > 0) { sm100::mbar_wait(accA_free, (u_accA - 1) & 1); sm100::tc_fence_after(); }
               for (int ks = 0; ks < KSLABS_D; ++ks) {
+                if (step == 0) { sm100::mbar_wait(a_ready + ks, n_ar & 1); sm100::tc_fence_after(); }
                 if (step == 0 && ks == KSLABS_D - 1) {   // prefetched into the extra slot
                   sm100::mbar_wait(xfull, n_xu & 1); ++n_xu;
                   sm100::tc_fence_after();
@@ -513,14 +520,13 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
             }
           }
           sm100::umma_commit(accB_full);
-          ++n_dr;   // the attention -> MLP boundary
+          ++n_dr; ++n_ar;   // the attention -> MLP boundary
           // ---- MLP half: M1_0 M1_1 M2_0 M1_2 M2_1 ... ----
-          sm100::mbar_wait(a_ready, n_ar & 1); ++n_ar;
-          sm100::tc_fence_after();
           for (int j = 0; j <= T; ++j) {
             if (j < T) {
               if (j > 0) { sm100::mbar_wait(accA_free, (u_accA - 1) & 1); sm100::tc_fence_after(); }
               for (int ks = 0; ks < KSLABS_D; ++ks) {
+                if (j == 0) { sm100::mbar_wait(a_ready + ks, n_ar & 1); sm100::tc_fence_after(); }
                 if (j == 0 && ks == KSLABS_D - 1) {      // prefetched into the extra slot
                   sm100::mbar_wait(xfull, n_xu & 1); ++n_xu;
                   sm100::tc_fence_after();
@@ -550,13 +556,17 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
           }
           sm100::umma_commit(accB_full);
           if (!(solve && l + 1 == p.n_layer)) ++n_dr;   // the MLP -> next attention (or end of tile) boundary; not drained before the final layer
+          ++n_ar;
         }
         if (solve) {
           // ---- final linear: accA[128 x 16] = LN_mod(x) x Wout^T ----
-          sm100::mbar_wait(a_ready, n_ar & 1); ++n_ar;
-          sm100::tc_fence_after();
           const uint32_t bs = wait_stage();
-          for (int ks = 0; ks < KSLABS_D; ++ks) issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, bs + ks * (16 * BLOCK_K * 2), idesc_f, ks == 0);
+          for (int ks = 0; ks < KSLABS_D; ++ks) {
+            sm100::mbar_wait(a_ready + ks, n_ar & 1);
+            sm100::tc_fence_after();
+            issue_slab_mmas(accA, a_base + ks * A_SLAB_BYTES, bs + ks * (16 * BLOCK_K * 2), idesc_f, ks == 0);
+          }
+          ++n_ar;
           done_stage();
           sm100::umma_commit(accA_full); ++u_accA;
         }
@@ -637,9 +647,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) dit_stack_kernel(const StackPar
       if (p.dbg != nullptr && etid == 0 && tile_no < 4) p.dbg[(size_t)blockIdx.x * 128 + 52 + tile_no] = clock64();
       BoundaryArgs ba{};
       // lane-resolved addresses of (row, column 64 sub) in the io buffer and in the blocked interior storage
-      const float* const x_io = p.X + (size_t)tile * BLOCK_M * D + (p.io_blocked ? ((size_t)(sub * 16) * BLOCK_M + row) * 4 : (size_t)row * D + sub * 64);
+      const float* const x_io = p.X + (size_t)tile * BLOCK_M * D + (p.io_blocked ? (size_t)row * 4 : (size_t)row * D);   // column 0 of this lane's row
       const int io_cs = p.io_blocked ? BLOCK_M * 4 : 4;
-      const float* const x_in = interior(tile) + ((size_t)(sub * 16) * BLOCK_M + row) * 4;
+      const float* const x_in = interior(tile) + (size_t)row * 4;
       ba.mod = p.mod; ba.rows = smRows; ba.mod_stride = p.mod_stride; ba.eps = p.eps;
       ba.sm_bias_q = smBiasQ;
       // ---- whole-solve mode: state <-> slot mapping of this lane's row (StepParams), recomputed where needed ----
