@@ -78,75 +78,99 @@ __device__ __forceinline__ void ln32_tokens(const float (*x)[E], float (*y)[E], 
 // One non-adaLN Block (layers.py:222-226) on a 16 x 32 tile in shared memory; nt = threads working on this tile (>= 128), tid
 // their index; `w` = the block's packed weights (global or shared memory).  Every barrier is CTA-wide: all tiles of a CTA run
 // in lock-step.
+// out[4 tokens][NC columns] += h[4 tokens][K] x w[K][ldw] for one thread: the four tokens' activations come as float4 along k
+// (broadcast reads: the token group is warp-uniform), the weights as one scalar per (k, column): 4 + 4 NC shared-memory reads per
+// 16 NC FMAs (the plain one-output-per-thread loop issued two reads per FMA and was bound by that).  K % 4 == 0; rows 16-byte aligned.
+template <int NC>
+__device__ __forceinline__ void tile_gemm4(const float* h0, int ldh, int K, const float* w, int ldw, const int (&col)[NC], float (&acc)[4][NC]) {
+  for (int k = 0; k < K; k += 4) {
+    float4 hv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) hv[t] = *reinterpret_cast<const float4*>(h0 + t * ldh + k);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float wv[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) wv[c] = w[(k + kk) * ldw + col[c]];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float hk = kk == 0 ? hv[t].x : (kk == 1 ? hv[t].y : (kk == 2 ? hv[t].z : hv[t].w));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[t][c] = fmaf(hk, wv[c], acc[t][c]);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void vae_block_layer(float (*x)[E], float (*h)[E], float (*qkv)[3 * E], float (*hid)[HID], const float* w, float eps,
                                                 int tid, int nt) {
+  (void)nt;   // the first 128 threads of the tile's group do the work: thread = (token group tg = 4 tokens, column lane cl)
+  const int tg = (tid >> 5) & 3, cl = tid & 31, t0 = tg * 4;
   {
     if (tid < 128) ln32_tokens(x, h, w + BLK_LN1W, w + BLK_LN1B, eps, tid);
     __syncthreads();
-    for (int i = tid; i < TOK * 3 * E; i += nt) {
-      const int tok = i / (3 * E), j = i % (3 * E);
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WQKV + k * 3 * E + j];
-      qkv[tok][j] = acc;
+    if (tid < 128) {   // q | k | v = h x Wqkv: columns cl, cl + 32, cl + 64
+      float acc[4][3] = {};
+      const int col[3] = {cl, cl + 32, cl + 64};
+      tile_gemm4<3>(&h[t0][0], E, E, w + BLK_WQKV, 3 * E, col, acc);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { qkv[t0 + t][cl] = acc[t][0]; qkv[t0 + t][cl + 32] = acc[t][1]; qkv[t0 + t][cl + 64] = acc[t][2]; }
     }
     __syncthreads();
     if (tid < 128) {
-      // one thread per (query token, head): head_dim 4, softmax over 16 keys, scale 1/sqrt(4)
+      // one thread per (query token, head): head_dim 4 = one float4, softmax over 16 keys, scale 1/sqrt(4)
       const int tok = tid >> 3, hd = tid & 7;
-      float q[4], s[TOK];
-#pragma unroll
-      for (int d = 0; d < 4; ++d) q[d] = qkv[tok][hd * 4 + d];
+      const float4 q = *reinterpret_cast<const float4*>(&qkv[tok][hd * 4]);
+      float s[TOK];
       float mx = -INFINITY;
 #pragma unroll
       for (int k = 0; k < TOK; ++k) {
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) a += q[d] * qkv[k][E + hd * 4 + d];
-        s[k] = a * 0.5f;
+        const float4 kk = *reinterpret_cast<const float4*>(&qkv[k][E + hd * 4]);
+        s[k] = (q.x * kk.x + q.y * kk.y + q.z * kk.z + q.w * kk.w) * 0.5f;
         mx = fmaxf(mx, s[k]);
       }
       float den = 0.f;
 #pragma unroll
       for (int k = 0; k < TOK; ++k) { s[k] = __expf(s[k] - mx); den += s[k]; }
       const float inv = 1.0f / den;
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < TOK; ++k) {
-#pragma unroll
-        for (int d = 0; d < 4; ++d) o[d] += s[k] * qkv[k][2 * E + hd * 4 + d];
+        const float4 vv = *reinterpret_cast<const float4*>(&qkv[k][2 * E + hd * 4]);
+        o.x += s[k] * vv.x; o.y += s[k] * vv.y; o.z += s[k] * vv.z; o.w += s[k] * vv.w;
       }
-#pragma unroll
-      for (int d = 0; d < 4; ++d) h[tok][hd * 4 + d] = o[d] * inv;
+      *reinterpret_cast<float4*>(&h[tok][hd * 4]) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
     }
     __syncthreads();
-    for (int i = tid; i < TOK * E; i += nt) {
-      const int tok = i / E, c = i % E;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < E; ++k) acc += h[tok][k] * w[BLK_WPROJ + k * E + c];
-      x[tok][c] += acc;
+    if (tid < 128) {   // x += attn x Wproj
+      float acc[4][1] = {};
+      const int col[1] = {cl};
+      tile_gemm4<1>(&h[t0][0], E, E, w + BLK_WPROJ, E, col, acc);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) x[t0 + t][cl] += acc[t][0];
     }
     __syncthreads();
     if (tid < 128) ln32_tokens(x, h, w + BLK_LN2W, w + BLK_LN2B, eps, tid);
     __syncthreads();
-    for (int i = tid; i < TOK * HID; i += nt) {
-      const int tok = i / HID, j = i % HID;
-      float a = 0.f, b = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < E; ++k) {
-        a += h[tok][k] * w[BLK_W1 + k * HID + j];
-        b += h[tok][k] * w[BLK_W2 + k * HID + j];
+    if (tid < 128) {   // SwiGLU hidden units cl, cl + 32, cl + 64 (HID = 88: the third only for cl < 24)
+      float a[4][3] = {}, b[4][3] = {};
+      const int col[3] = {cl, cl + 32, cl + 64 < HID ? cl + 64 : cl};   // (an out-of-range column re-reads column cl; its result is dropped)
+      tile_gemm4<3>(&h[t0][0], E, E, w + BLK_W1, HID, col, a);
+      tile_gemm4<3>(&h[t0][0], E, E, w + BLK_W2, HID, col, b);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        hid[t0 + t][cl] = sm100::silu(a[t][0]) * b[t][0];
+        hid[t0 + t][cl + 32] = sm100::silu(a[t][1]) * b[t][1];
+        if (cl + 64 < HID) hid[t0 + t][cl + 64] = sm100::silu(a[t][2]) * b[t][2];
       }
-      hid[tok][j] = sm100::silu(a) * b;
     }
     __syncthreads();
-    for (int i = tid; i < TOK * E; i += nt) {
-      const int tok = i / E, c = i % E;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < HID; ++k) acc += hid[tok][k] * w[BLK_W3 + k * E + c];
-      x[tok][c] += acc;
+    if (tid < 128) {   // x += hid x W3
+      float acc[4][1] = {};
+      const int col[1] = {cl};
+      tile_gemm4<1>(&hid[t0][0], HID, HID, w + BLK_W3, E, col, acc);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) x[t0 + t][cl] += acc[t][0];
     }
     __syncthreads();
   }
@@ -734,10 +758,10 @@ struct EncParams {
 __global__ void __launch_bounds__(256) mcab_encode_kernel(const EncParams p) {
   __shared__ uint2 s_wkv[16 * 32];              // 4 KB
   __shared__ float s_state[8][4][16][10];       // per warp, head, query: m, l, acc[8]   (20 KB)
-  __shared__ float x[TOK][E];
-  __shared__ float h[TOK][E];
-  __shared__ float qkv[TOK][3 * E];
-  __shared__ float hid[TOK][HID];
+  __shared__ __align__(16) float x[TOK][E];
+  __shared__ __align__(16) float h[TOK][E];
+  __shared__ __align__(16) float qkv[TOK][3 * E];
+  __shared__ __align__(16) float hid[TOK][HID];
   const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   for (int i = tid; i < 16 * 32; i += 256) s_wkv[i] = reinterpret_cast<const uint2*>(p.wkv_frag)[i];
