@@ -15,6 +15,20 @@ import torch.nn as nn
 from .config import swiglu_hidden
 
 
+def weights_key(module: nn.Module, cache_attr: str, select=None) -> tuple:
+    """(data_ptr, version) of the module's parameters and buffers: the validity key of a packed-weights cache.  The tensor list is
+    collected once (a `state_dict()` walk per call costs a millisecond of host time, which a synchronous generation step waits
+    for); in-place updates (`load_state_dict`, optimizer steps) bump `_version`, `.to()` / `.cuda()` change `data_ptr`, and a
+    re-registered parameter changes the module's tensor count."""
+    cached = module.__dict__.get(cache_attr)
+    n_now = sum(len(m._parameters) + len(m._buffers) for m in module.modules())
+    if cached is None or cached[0] != n_now:
+        named = list(module.named_parameters()) + list(module.named_buffers())
+        cached = (n_now, [t for k, t in named if select is None or select(k)])
+        module.__dict__[cache_attr] = cached
+    return tuple((t.data_ptr(), t._version) for t in cached[1])
+
+
 class _KernelOnly(nn.Module):
     def forward(self, *args, **kwargs):  # pragma: no cover - guard
         raise RuntimeError(

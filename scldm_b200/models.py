@@ -176,15 +176,21 @@ class LatentDiffusion(nn.Module):
                 self._copy_stream = torch.cuda.Stream(device=dev)
             copy_stream = self._copy_stream
             copy_stream.wait_stream(torch.cuda.current_stream(dev))   # earlier readers of the host buffers are ordered before us
-        # cells are independent: run the ODE + decode chunk by chunk so the working set stays L2-sized.  The evaluation plans
-        # of ALL chunks are built first: deduplicating label combinations synchronises with the device, and doing that between
-        # chunks would leave the GPU idle while the host prepares the next chunk's launches.
+        # cells are independent: run the ODE + decode chunk by chunk.  A chunk's evaluation plan is built right before its solve is
+        # queued, i.e. (from the second chunk on) while the GPU is still busy with the previous chunk - unless deduplicating the
+        # label combinations has to synchronise with the device (large label spaces, `torch.unique`): then all plans are built
+        # first, because a synchronisation between chunks would leave the GPU idle while the host prepares the next launches.
         chunks = [(c0, min(c0 + self.cell_chunk, batch_size)) for c0 in range(0, batch_size, self.cell_chunk)]
-        conds = [{k: torch.cat([v[c0:c1], v[c0:c1]]) for k, v in cond.items()} for c0, c1 in chunks]
-        plans = [None] * len(chunks)
-        if self.sampling_method.lower() in Sampler.FIXED:
-            plans = [dit.cfg_plan(cc if cond else None, guidance_weight, c1 - c0, dev, shared_time=True)[0] for (c0, c1), cc in zip(chunks, conds)]
-        for (c0, c1), cc, plan in zip(chunks, conds, plans):
+        fixed = self.sampling_method.lower() in Sampler.FIXED
+
+        def make(c0, c1):
+            cc = {k: torch.cat([v[c0:c1], v[c0:c1]]) for k, v in cond.items()}
+            plan = dit.cfg_plan(cc if cond else None, guidance_weight, c1 - c0, dev, shared_time=True)[0] if fixed else None
+            return cc, plan
+
+        ahead = None if dit.plans_are_sync_free() else [make(c0, c1) for c0, c1 in chunks]
+        for i, (c0, c1) in enumerate(chunks):
+            cc, plan = ahead[i] if ahead is not None else make(c0, c1)
             zc = z0[c0:c1]
             zf = sample_fn(torch.cat([zc, zc]), model_fn, condition=cc, **({"_plan": plan} if plan is not None else {}))[-1]
             n = c1 - c0

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from . import ops
 from .config import DiTConfig
-from .layers import Block, CrossAttentionBlock, FinalLayerDit, TimestepEmbedder, get_1d_sincos_pos_embed
+from .layers import Block, CrossAttentionBlock, FinalLayerDit, TimestepEmbedder, get_1d_sincos_pos_embed, weights_key
 from .pack import PackedDiT
 
 
@@ -118,8 +118,7 @@ class DiT(nn.Module):
 
     # ---- packed-weight cache ----
     def packed(self) -> PackedDiT:
-        params = list(self.state_dict(keep_vars=True).values())
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = weights_key(self, "_wkey_all")
         dev = self.pos_embed.device
         if dev.type != "cuda":
             raise RuntimeError("scldm_b200.DiT runs on CUDA only (no CPU fallback): call .cuda() first")
@@ -245,6 +244,14 @@ class DiT(nn.Module):
             t_index = torch.cat([ar, (half + ar).repeat_interleave(n_f)]).long()
         slot_mod = torch.cat([slot_u, slot_g.reshape(-1)])
         return dict(n_u=half, n_g=half, n_f=n_f, coef=coef, cls_idx=cls_idx, slot_mod=slot_mod, t_index=t_index, slot_mode=slot_mode)
+
+    def plans_are_sync_free(self) -> bool:
+        """True when building a shared-time CFG plan never synchronises with the device (`_label_combinations` enumerates small
+        label spaces; larger ones go through `torch.unique`)."""
+        total = 1
+        for v in self.class_vocab_sizes.values():
+            total *= v + 1
+        return total <= 256
 
     def _label_combinations(self, cols: torch.Tensor):
         """Distinct columns of `cols` [n_class, n] (embedding rows per class, null = vocab size) and the column -> combination map.

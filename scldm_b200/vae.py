@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from . import ops
 from .config import VAEConfig
-from .layers import InputTransformerVAE
+from .layers import InputTransformerVAE, weights_key
 from .nnets import Decoder, Encoder
 from .pack import PackedVAEDecoder, PackedVAEEncoder
 from .pack256 import PackedVAE256Decoder, PackedVAE256Encoder
@@ -56,15 +56,14 @@ class TransformerVAE(nn.Module):
                          shared_theta=self.decoder_head.shared_theta)
 
     def packed_decoder(self) -> PackedVAEDecoder:
-        sd = self.state_dict(keep_vars=True)
-        key = tuple((p.data_ptr(), p._version) for k, p in sd.items() if not k.startswith("encoder."))
+        key = weights_key(self, "_wkey_dec", lambda k: not k.startswith("encoder."))
         dev = self.input_layer.gene_embedding.weight.device
         if dev.type != "cuda":
             raise RuntimeError("scldm_b200.TransformerVAE runs on CUDA only (no CPU fallback): call .cuda() first")
         if self._packed_dec is None or self._packed_key != key:
             cfg = self.config()
             cls = PackedVAE256Decoder if cfg.n_embed == 256 else PackedVAEDecoder      # kernels exist for n_embed 32 (vae_base.yaml) and 256 (census scale)
-            self._packed_dec = cls({k: v.detach() for k, v in sd.items()}, cfg, dev)
+            self._packed_dec = cls({k: v.detach() for k, v in self.state_dict(keep_vars=True).items()}, cfg, dev)
             self._packed_key = key
         return self._packed_dec
 
@@ -109,15 +108,14 @@ class TransformerVAE(nn.Module):
         return counts, mu, theta
 
     def packed_encoder(self) -> PackedVAEEncoder:
-        sd = self.state_dict(keep_vars=True)
-        key = tuple((p.data_ptr(), p._version) for k, p in sd.items() if k.startswith("encoder.") or k.startswith("input_layer."))
+        key = weights_key(self, "_wkey_enc", lambda k: k.startswith("encoder.") or k.startswith("input_layer."))
         dev = self.input_layer.gene_embedding.weight.device
         if dev.type != "cuda":
             raise RuntimeError("scldm_b200.TransformerVAE runs on CUDA only (no CPU fallback): call .cuda() first")
         if getattr(self, "_packed_enc", None) is None or self._packed_enc_key != key:
             cfg = self.config()
             cls = PackedVAE256Encoder if cfg.n_embed == 256 else PackedVAEEncoder
-            self._packed_enc = cls({k: v.detach() for k, v in sd.items()}, cfg, dev)
+            self._packed_enc = cls({k: v.detach() for k, v in self.state_dict(keep_vars=True).items()}, cfg, dev)
             self._packed_enc_key = key
         return self._packed_enc
 
