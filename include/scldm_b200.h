@@ -164,6 +164,8 @@ int scldm_vae_decode(const scldm_vae_dec_weights* w, const float* qp, const void
 typedef struct scldm_vae_enc_weights {
   int32_t n_layer;
   int32_t has_pos;
+  int32_t agg_func;       /* count transform of InputTransformerVAE (layers.py:28-44): token = emb[gene] * f(count) with
+                             0: log1p(c)   1: c == 0 ? -1 : log1p(c) ("log1pzero")   2: asinh(sqrt(c + 1)) ("anscombe")   3: sqrt(c + 1) */
   float eps;
   const float* emb;       /* input_layer.gene_embedding.weight [n_ids][32]                                  */
   const void* wkv_frag;   /* encoder.ca_layer.attn.c_attn.weight (k|v) in mma.sync B-fragment order          */

@@ -349,8 +349,23 @@ def sde_golden() -> None:
     np.savez_compressed(os.path.join(GOLDEN_DIR, "sde_me1.npz"), **arrays)
 
 
+def vae_agg_golden() -> None:
+    """The other multiplicative count transforms of `InputTransformerVAE` (reference `layers.py:28-44`: log1pzero, anscombe, sqrt)
+    through the reference's own encoder (the shipped yaml uses log1p, which `vae_small` / `vae_dentate` cover)."""
+    arrays = {}
+    for agg in ("log1pzero", "anscombe", "sqrt"):
+        vcfg = VAEConfig(n_genes=1500, agg_func=agg)
+        vae = ref_loader.build_reference_vae(vcfg, synthetic.vae_state_dict(vcfg, WEIGHT_SEED))
+        _, _, _, cs, gs = vae_inputs("vae_small", vcfg, 3, 400)
+        with torch.no_grad():
+            arrays["z_enc_" + agg] = vae.encode(None, None, cs, gs).numpy()
+    arrays.update(counts_subset=cs.numpy(), genes_subset=gs.numpy())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "vae_agg.npz"), **arrays)
+    print("vae_agg", {k: v.shape for k, v in arrays.items()})
+
+
 if __name__ == "__main__":
-    later = {"nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden, "vae256": vae256_golden, "sde": sde_golden}   # fixtures added after the first set; minted
+    later = {"vae_agg": vae_agg_golden, "nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden, "vae256": vae256_golden, "sde": sde_golden}   # fixtures added after the first set; minted
     if len(sys.argv) > 1 and sys.argv[1] in later:                                 # alone so the others stay byte-identical
         later[sys.argv[1]]()
     else:

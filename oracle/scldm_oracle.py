@@ -329,12 +329,25 @@ def nb_sample(mu, theta, generator=None):
 # ----------------------------------------------------------------------------------------
 
 
+def count_transform(counts, agg_func: str = "log1p"):
+    """The multiplicative count transforms of `InputTransformerVAE` (reference `layers.py:28-44`, `PROJ_FUNC`)."""
+    if agg_func == "log1p":
+        return torch.log1p(counts)
+    if agg_func == "log1pzero":
+        return torch.where(counts == 0, torch.tensor(-1.0), torch.log1p(counts))
+    if agg_func == "anscombe":
+        return torch.asinh(torch.sqrt(counts + 1.0))
+    if agg_func == "sqrt":
+        return torch.sqrt(counts + 1.0)
+    raise NotImplementedError(agg_func)
+
+
 def vae_encode(counts_subset, genes_subset, sd, cfg):
     """`TransformerVAE.encode` reference `vae.py:58-69`: emb[gene]*log1p(count) (`layers.py:28-31`) ->
     MCAB pool with inducing points (no key masking, quirk 3) -> +pos_embed -> blocks ->
     Linear(E->L) -> LN(no affine)."""
     emb = sd["input_layer.gene_embedding.weight"][genes_subset.long()]
-    x = emb * torch.log1p(counts_subset).unsqueeze(-1)
+    x = emb * count_transform(counts_subset, getattr(cfg, "agg_func", "log1p")).unsqueeze(-1)
     B = x.shape[0]
     q = sd["encoder.ca_layer.inducing_points"].unsqueeze(0).expand(B, -1, -1)
     h = mcab(x, q, sd, "encoder.ca_layer.", cfg.n_head_cross, cfg.layernorm_eps)

@@ -55,7 +55,7 @@ class VaeDecWeights(C.Structure):
 
 
 class VaeEncWeights(C.Structure):
-    _fields_ = [("n_layer", C.c_int32), ("has_pos", C.c_int32), ("eps", C.c_float)] + [
+    _fields_ = [("n_layer", C.c_int32), ("has_pos", C.c_int32), ("agg_func", C.c_int32), ("eps", C.c_float)] + [
         (n, C.c_void_p) for n in ("emb", "wkv_frag", "q_tbl", "ln1_w", "ln1_b", "inducing", "wproj_t", "ln2_w", "ln2_b", "w1_t", "w2_t",
                                   "w3_t", "pos", "blocks", "wlat_t")]
 

@@ -576,6 +576,7 @@ int scldm_vae_encode(const scldm_vae_enc_weights* w, const int64_t* genes_subset
   if (n_cells < 1 || seq_len < 1) return fail(SCLDM_EINVAL, "empty encode: n_cells=%d seq_len=%d", n_cells, seq_len);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vae::EncParams p{};
+  p.agg = w->agg_func;
   p.emb = w->emb; p.genes = reinterpret_cast<const long long*>(genes_subset); p.counts = counts_subset; p.S = seq_len; p.n_cells = n_cells;
   p.wkv_frag = static_cast<const uint32_t*>(w->wkv_frag); p.q_tbl = static_cast<const __nv_bfloat16*>(w->q_tbl);
   p.ln1_w = w->ln1_w; p.ln1_b = w->ln1_b; p.inducing = w->inducing; p.wproj_t = w->wproj_t; p.ln2_w = w->ln2_w; p.ln2_b = w->ln2_b;

@@ -734,7 +734,18 @@ __global__ void __launch_bounds__(256) nb_nll_kernel(const float* __restrict__ x
 // tokens (NO key masking: padding tokens keep their softmax mass) -> P V (V^T via movmatrix).
 // Phase 2 merges the warps' (max, sum, acc) states; phase 3 is the fp32 tail on the 16 x 32 latent tile:
 // c_proj, + inducing points (raw-query residual), LN2 + SwiGLU, + pos_embed, n_layer Blocks, Linear(32->16), LN.
+// multiplicative count transforms of InputTransformerVAE (layers.py:28-44, PROJ_FUNC): token = emb[gene] * count_scale(count)
+__device__ __forceinline__ float count_scale(float c, int agg) {
+  switch (agg) {
+    case 1: return c == 0.f ? -1.f : log1pf(c);       // "log1pzero"
+    case 2: return asinhf(sqrtf(c + 1.f));            // "anscombe"
+    case 3: return sqrtf(c + 1.f);                    // "sqrt"
+    default: return log1pf(c);                        // "log1p"
+  }
+}
+
 struct EncParams {
+  int agg;                      // count transform, see count_scale
   const float* emb;             // gene embedding table [n_ids][32]
   const long long* genes;       // [cells][S]
   const float* counts;          // [cells][S]
@@ -822,7 +833,7 @@ __global__ void __launch_bounds__(256) mcab_encode_kernel(const EncParams p) {
     gather(ids_nxt, emb_nxt);                       // rows of block blk + 8 (row 0 of the table when that block does not exist)
     const TokIds ids_nn = load_ids(blk + 16);
     // ---- tokens g and g+8 of this block: scale by log1p(count), LayerNorm over 32 channels ----
-    const float c0 = log1pf(ids_cur.c0), c1 = log1pf(ids_cur.c1);   // absent tokens: id 0 / count 0 -> zero rows, masked below
+    const float c0 = count_scale(ids_cur.c0, p.agg), c1 = count_scale(ids_cur.c1, p.agg);   // (tokens beyond S are masked below)
     float xv[2][2][4];  // [row g / g+8][ks][4 cols]
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {

@@ -124,12 +124,16 @@ class FinalLayerDit(_KernelOnly):
 
 
 class InputTransformerVAE(_KernelOnly):
-    """weights of `InputTransformerVAE` (`layers.py:97-109`); only agg_func='log1p' (vae_base.yaml:40)."""
+    """weights of `InputTransformerVAE` (`layers.py:97-109`).  The multiplicative count transforms ('log1p', the shipped one
+    (vae_base.yaml:40), 'log1pzero', 'anscombe', 'sqrt': `layers.py:28-44`) run inside the encoder kernels; the three variants
+    with learned count embeddings ('proj', 'projconcat', 'softbin') are not built."""
+
+    AGG_CODES = {"log1p": 0, "log1pzero": 1, "anscombe": 2, "sqrt": 3}
 
     def __init__(self, n_genes: int, n_embed: int, agg_func: str = "log1p"):
         super().__init__()
-        if agg_func != "log1p":
-            raise NotImplementedError(f"agg_func='{agg_func}': the shipped VAE uses 'log1p'")
+        if agg_func not in self.AGG_CODES:
+            raise NotImplementedError(f"agg_func='{agg_func}': implemented: {sorted(self.AGG_CODES)}")
         self.gene_embedding = nn.Embedding(n_genes + 1, n_embed)
         self.agg_func = agg_func
 

@@ -276,8 +276,11 @@ class PackedVAEEncoder:
     def __init__(self, sd: dict, cfg: VAEConfig, device):
         if (cfg.n_embed, cfg.n_embed_latent, cfg.n_inducing_points, cfg.n_head, cfg.n_head_cross, cfg.hidden) != (32, 16, 16, 8, 4, VAE_HID):
             raise NotImplementedError(f"sm_100a VAE kernels are specialised to the shipped vae_base dims; got {cfg}")
-        if cfg.bias or cfg.agg_func != "log1p":
-            raise NotImplementedError("encoder kernels cover bias=False, agg_func='log1p'")
+        from .layers import InputTransformerVAE
+
+        if cfg.bias or cfg.agg_func not in InputTransformerVAE.AGG_CODES:
+            raise NotImplementedError("encoder kernels cover bias=False and the multiplicative count transforms (log1p, log1pzero, anscombe, sqrt)")
+        self.agg_func = InputTransformerVAE.AGG_CODES[cfg.agg_func]
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
         g = lambda n: sd[n].detach().float().cpu()  # noqa: E731
         c = "encoder.ca_layer."
@@ -299,7 +302,7 @@ class PackedVAEEncoder:
         self.blocks = f32(_pack_vae_blocks(g, "encoder.encoder_layers.", cfg.n_layer))
         self.wlat_t = f32(g("encoder.encoder_latent_input.0.weight").T)
         s = _lib.VaeEncWeights()
-        s.n_layer, s.has_pos, s.eps = cfg.n_layer, int(self.has_pos), eps
+        s.n_layer, s.has_pos, s.agg_func, s.eps = cfg.n_layer, int(self.has_pos), self.agg_func, eps
         for name in ("emb", "wkv_frag", "q_tbl", "ln1_w", "ln1_b", "inducing", "wproj_t", "ln2_w", "ln2_b", "w1_t", "w2_t", "w3_t", "pos",
                      "blocks", "wlat_t"):
             setattr(s, name, getattr(self, name).data_ptr())

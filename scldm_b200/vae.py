@@ -53,7 +53,7 @@ class TransformerVAE(nn.Module):
                          n_head_cross=d["n_head_cross"], bias=d["bias"], multiple_of=d["multiple_of"],
                          layernorm_eps=d["layernorm_eps"], positional_encoding=e["positional_encoding"],
                          shared_embedding=d["shared_embedding"], use_adaln=d["use_adaln"],
-                         shared_theta=self.decoder_head.shared_theta)
+                         shared_theta=self.decoder_head.shared_theta, agg_func=self.input_layer.agg_func)
 
     def packed_decoder(self) -> PackedVAEDecoder:
         key = weights_key(self, "_wkey_dec", lambda k: not k.startswith("encoder."))

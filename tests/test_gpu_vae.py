@@ -231,6 +231,19 @@ def test_encode_vs_golden(golden_dir, name, G, B, S):
     assert z.shape == (B, 16, 16) and e < 1e-2, e
 
 
+@pytest.mark.parametrize("agg", ["log1pzero", "anscombe", "sqrt"])
+def test_encode_count_transforms_vs_golden(golden_dir, agg):
+    """agg_func variants of InputTransformerVAE (reference layers.py:28-44) in the encoder kernel vs reference-minted vectors; with
+    'anscombe' / 'sqrt' the zero-count padding tokens carry f(0) != 0 and, unmasked as in the reference, do contribute."""
+    g = dict(np.load(os.path.join(golden_dir, "vae_agg.npz")))
+    cfg = VAEConfig(n_genes=1500, agg_func=agg)
+    vae, sd = make_vae(cfg)
+    z = vae.encode(None, None, torch.from_numpy(g["counts_subset"]).cuda(), torch.from_numpy(g["genes_subset"]).cuda())
+    e = rel_l2(z, g["z_enc_" + agg])
+    print(agg, f"encode z rel-L2 {e:.2e}")
+    assert e < 1e-2, e
+
+
 def test_encode_ragged_lengths_vs_oracle():
     """S not a multiple of 16 (ragged last token block), S < 128 (some warps idle), many cells."""
     cfg = VAEConfig(n_genes=700, n_layer=2)

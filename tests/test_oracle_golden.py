@@ -82,6 +82,18 @@ def test_vae_decode_encode(golden_dir, name, G, B, S):
         assert rel_l2(z_enc, g["z_enc"]) < 1e-4
 
 
+@pytest.mark.parametrize("agg", ["log1pzero", "anscombe", "sqrt"])
+def test_encode_count_transforms(golden_dir, agg):
+    """The other multiplicative count transforms of InputTransformerVAE (reference layers.py:28-44) through the oracle's encoder vs
+    the reference-minted vectors (`python -m oracle.make_golden vae_agg`)."""
+    g = load(golden_dir, "vae_agg")
+    cfg = VAEConfig(n_genes=1500, agg_func=agg)
+    sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
+    with torch.no_grad():
+        z_enc = O.vae_encode(torch.from_numpy(g["counts_subset"]), torch.from_numpy(g["genes_subset"]), sd, cfg)
+    assert rel_l2(z_enc, g["z_enc_" + agg]) < 1e-4
+
+
 def test_full_sample(golden_dir):
     g = load(golden_dir, "sample_me1")
     cfg = golden_cases()["dit_me1"]["cfg"]
