@@ -290,6 +290,55 @@ int scldm_repack(const float* params, const int32_t* pk_dst, void* pk, int64_t n
 /* ema += (1 - decay) * (params - ema)   (ema_pytorch update with the decay the caller scheduled) */
 int scldm_ema_update(float* ema, const float* params, int64_t n, float decay, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * VAE training step, n_embed = 32 (reference: VAE.training_step, src/scldm/models.py:249-287; TransformerVAE.forward,
+ * src/scldm/vae.py:29-56; VAE.loss, models.py:233-247; log_nb_positive, distributions.py:6-42; torch autograd through
+ * Encoder / Decoder / CrossAttentionBlock / Block, nnets.py:82-208, layers.py:177-330; optimizer: AdamWLegacy,
+ * optimizers.py:72-141 = scldm_adamw_step above with pk_dst = NULL).
+ *
+ * All trainable VAE parameters live in ONE flat fp32 buffer, gradients in a second one with the same layout.  Parameter
+ * groups (element offsets, every tensor padded to a multiple of 4 floats):
+ *   Block [12672]:               ln_1.weight 32 | ln_1.bias 32 | attn.c_attn.weight [96][32] | attn.c_proj.weight [32][32] |
+ *                                ln_2.weight | ln_2.bias | mlp.w1.weight [88][32] | mlp.w2.weight [88][32] | mlp.c_proj.weight [32][88]
+ *   CrossAttentionBlock [12736]: ln_1.w | ln_1.b | ln_1q.w | ln_1q.b | ln_2.w | ln_2.b | attn.c_attn.weight [64][32] (k | v) |
+ *                                attn.c_attn_q.weight [32][32] | attn.c_proj.weight [32][32] | mlp.w1 | mlp.w2 | mlp.c_proj
+ * Covered: bias = False, use_adaln = False, shared_theta = True, shared_embedding = True, the multiplicative agg_func
+ * variants (vae_base.yaml).                                                                                        */
+typedef struct scldm_vae_train {
+  int32_t n_layer, n_ids, agg_func, has_pos;
+  float eps;
+  float* params;        /* flat fp32 parameters                                                            */
+  float* grads;         /* flat fp32 gradients (same layout); may be NULL for forward-only calls             */
+  int64_t emb;          /* input_layer.gene_embedding.weight [n_ids][32]                                    */
+  int64_t theta;        /* decoder_head.theta.weight [n_ids]                                                */
+  int64_t head_w;       /* decoder_head.params.weight [32]                                                  */
+  int64_t head_b;       /* decoder_head.params.bias [1]                                                     */
+  int64_t enc_ca;       /* encoder.ca_layer (CrossAttentionBlock group)                                     */
+  int64_t dec_ca;       /* decoder.decoder_cross_attention (CrossAttentionBlock group)                      */
+  int64_t inducing;     /* encoder.ca_layer.inducing_points [16][32]                                        */
+  int64_t enc_blocks;   /* encoder.encoder_layers.0 .. n_layer-1, contiguous Block groups                   */
+  int64_t dec_blocks;   /* decoder.decoder_layers.0 .. n_layer-1                                            */
+  int64_t enc_lat;      /* encoder.encoder_latent_input.0.weight [16][32]                                   */
+  int64_t dec_lat;      /* decoder.decoder_latent_input.1.weight [32][16]                                   */
+  int64_t n_params;
+  const float* pos;     /* encoder.pos_embed [16][32] (requires_grad = False, nnets.py:103-106) or NULL     */
+} scldm_vae_train;
+
+size_t scldm_vae_train_workspace_bytes(const scldm_vae_train* tr, int32_t n_cells, int32_t S, int32_t G);
+
+/* One forward (+ backward) of the VAE on n_cells cells:
+ *   genes_subset / counts_subset [n_cells][S]  encoder tokens ("expressed" packing, datamodule.py:708-731)
+ *   genes [G] the shared gene-id row, counts [n_cells][G], library [n_cells]
+ *   nll [n_cells] = -sum_g log_nb_positive (the per-cell term of VAE.loss); z_out [n_cells][16][16], mu_out [n_cells][G] nullable.
+ * backward != 0: d(loss_scale * sum_cells nll) / d params is ACCUMULATED into tr->grads (cleared first if zero_grads != 0);
+ * loss_scale = 1 / global batch gives the gradient of `recon_loss.sum(dim=1).mean()`.
+ * exact != 0: the decoder MCAB GEMMs use 3 x TF32 (fp32-grade products) instead of TF32.
+ * workspace: 256-byte aligned, scldm_vae_train_workspace_bytes.  Stream-ordered, no host sync.                      */
+int scldm_vae_train_step(const scldm_vae_train* tr, const int64_t* genes_subset, const float* counts_subset, int32_t S, const int64_t* genes,
+                         const float* counts, const float* library, int32_t n_cells, int32_t G, float loss_scale, int32_t backward,
+                         int32_t zero_grads, int32_t exact, float* nll, float* z_out, float* mu_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* Stand-alone access to the slab GEMM for unit tests: mode 0 forward  out[M][N]  = A[M][K] W[N][K]^T (+bias[N]),
  * mode 1 dgrad out[M][K] = dY[M][N] W[N][K], mode 2 wgrad out[N][K] += dY[M][N]^T A[M][K].  a_f32 / dy_f32 are fp32
  * row-major inputs (converted to bf16 slab tensors in `workspace`), w_packed = bf16 [N/256][K/64][256 x 64] tiles.

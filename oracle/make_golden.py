@@ -291,6 +291,75 @@ def train_step_golden() -> None:
     print("train_step_me1 loss", float(loss), "total grad norm", float(total), "dropped", int(drop.sum()))
 
 
+
+VAE_TRAIN_FULL = ("decoder_head.params.weight", "decoder_head.params.bias", "encoder.ca_layer.inducing_points", "encoder.ca_layer.attn.c_attn_q.weight",
+                  "decoder.decoder_cross_attention.mlp.w1.weight", "decoder.decoder_cross_attention.attn.c_attn_q.weight",
+                  "encoder.encoder_latent_input.0.weight", "decoder.decoder_latent_input.1.weight", "decoder.decoder_layers.1.attn.c_attn.weight",
+                  "encoder.encoder_layers.0.ln_1.weight", "encoder.ca_layer.ln_1.bias")
+
+
+def vae_train_inputs(cfg: VAEConfig, B: int, S: int):
+    """Seeded batch of the VAE training step: "expressed"-mode encoder tokens + the dense counts they come from (+ a few large counts
+    for the lgamma / digamma terms), library size = row sum (datamodule.py:708-731)."""
+    _, genes, _, cs, gs = vae_inputs("vae_train", cfg, B, S)
+    counts = torch.zeros(B, cfg.n_genes)
+    for i in range(B):
+        m = gs[i] > 0
+        counts[i, gs[i][m] - 1] = cs[i][m]
+    counts[0, :5] = torch.tensor([0.0, 1.0, 17.0, 250.0, 40.0])
+    lib = counts.sum(1, keepdim=True)
+    return counts, genes, lib, cs, gs
+
+
+def vae_train_step_golden() -> None:
+    """One VAE training step of the REFERENCE (`VAE.training_step`, models.py:249-287, minus the Lightning shell): unmodified
+    `TransformerVAE.forward` -> `-log_nb_positive(...).sum(1).mean()` -> autograd -> `clip_grad_norm_(10)` (training/default.yaml:15)
+    -> `AdamWLegacy(lr=1e-3, weight_decay=0)` (vae_base.yaml:56-60; the class itself needs no third-party package).  Stores loss, every
+    gradient's norm, a few gradients in full, strided slices of the rest, and the same for the updated weights:
+    tests/golden/vae_train_step.npz.  flex_attention has no CPU backward -> minted on the GPU box like train_step_me1."""
+    ref = ref_loader.load_reference()
+    import scldm.distributions as ref_dist
+    dev = torch.device(os.environ.get("SCLDM_GOLDEN_DEVICE", "cuda" if torch.cuda.is_available() else "cpu"))
+    out_dir = os.environ.get("SCLDM_GOLDEN_DIR", GOLDEN_DIR)
+    os.makedirs(out_dir, exist_ok=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    cfg, B, S = VAEConfig(n_genes=1500, n_layer=2), 3, 400
+    sd = synthetic.vae_state_dict(cfg, WEIGHT_SEED)
+    vae = ref_loader.build_reference_vae(cfg, sd).to(dev).train()
+    counts, genes, lib, cs, gs = [a.to(dev) for a in vae_train_inputs(cfg, B, S)]
+    params, h_z = vae.forward(counts, genes, lib, cs, gs)
+    per_cell = (-ref_dist.log_nb_positive(counts, params["mu"], params["theta"])).sum(dim=1)
+    loss = per_cell.mean()
+    loss.backward()
+    c = lambda a: a.detach().cpu().numpy().copy()  # noqa: E731
+    arrays = dict(loss=np.float32(loss.item()), per_cell=c(per_cell), h_z=c(h_z), mu=c(params["mu"]), device=np.array(str(dev)))
+    named = dict(vae.named_parameters())
+    names = [n for n, p in named.items() if p.requires_grad]
+    arrays["names"] = np.array(names)
+    arrays["grad_norms"] = np.array([float(named[n].grad.norm()) for n in names], dtype=np.float64)
+    for n in names:
+        g = named[n].grad
+        arrays["grad." + n] = c(g) if n in VAE_TRAIN_FULL else c(g.reshape(-1)[::53])
+    total = torch.nn.utils.clip_grad_norm_([named[n] for n in names], 10.0)
+    arrays["total_norm"] = np.float64(float(total))
+    try:
+        import scldm.optimizers as ref_opt
+        opt = ref_opt.AdamWLegacy([named[n] for n in names], lr=1e-3, weight_decay=0.0)
+        arrays["optimizer"] = np.array("scldm.optimizers.AdamWLegacy")
+    except Exception as e:  # noqa: BLE001
+        print("AdamWLegacy not importable (", e, ") -> torch.optim.AdamW (same update for amsgrad=False, caution=False)")
+        opt = torch.optim.AdamW([named[n] for n in names], lr=1e-3, weight_decay=0.0)
+        arrays["optimizer"] = np.array("torch.optim.AdamW")
+    opt.step()
+    for n in names:
+        w = named[n].detach()
+        arrays["new." + n] = c(w) if n in VAE_TRAIN_FULL else c(w.reshape(-1)[::53])
+    np.savez_compressed(os.path.join(out_dir, "vae_train_step.npz"), **arrays)
+    print("vae_train_step loss", float(loss), "total grad norm", float(total))
+
+
 @torch.no_grad()
 def vae256_golden() -> None:
     """Census-scale VAE width (n_embed = 256: 8 heads, 4 cross heads, SwiGLU hidden 684) through the REFERENCE modules:
@@ -365,7 +434,7 @@ def vae_agg_golden() -> None:
 
 
 if __name__ == "__main__":
-    later = {"vae_agg": vae_agg_golden, "nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden, "vae256": vae256_golden, "sde": sde_golden}   # fixtures added after the first set; minted
+    later = {"vae_agg": vae_agg_golden, "nb_loss": nb_loss_golden, "unshared_theta": unshared_theta_golden, "label_dropout": label_dropout_golden, "train_step": train_step_golden, "vae_train_step": vae_train_step_golden, "vae256": vae256_golden, "sde": sde_golden}   # fixtures added after the first set; minted
     if len(sys.argv) > 1 and sys.argv[1] in later:                                 # alone so the others stay byte-identical
         later[sys.argv[1]]()
     else:

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libscldm_b200.so")
 SOURCES = ["abi.cu"]
-HEADERS = ["sm100.cuh", "dit_kernels.cuh", "dit_stack.cuh", "vae_kernels.cuh", "csr_kernels.cuh", "rng.cuh", "train_kernels.cuh", "train_abi.inc", "vae256_kernels.cuh", "vae256_abi.inc", "eval_kernels.cuh", os.path.join("..", "..", "include", "scldm_b200.h")]
+HEADERS = ["sm100.cuh", "dit_kernels.cuh", "dit_stack.cuh", "vae_kernels.cuh", "csr_kernels.cuh", "rng.cuh", "train_kernels.cuh", "train_abi.inc", "vae256_kernels.cuh", "vae256_abi.inc", "eval_kernels.cuh", "vae_train_kernels.cuh", "vae_train_abi.inc", os.path.join("..", "..", "include", "scldm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 

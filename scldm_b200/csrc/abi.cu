@@ -17,6 +17,7 @@
 #include "train_kernels.cuh"
 #include "vae256_kernels.cuh"
 #include "eval_kernels.cuh"
+#include "vae_train_kernels.cuh"
 
 namespace {
 
@@ -687,6 +688,7 @@ const char* scldm_version(void) { return "scldm_b200 0.1 (sm_100a)"; }
 
 #include "train_abi.inc"
 #include "vae256_abi.inc"
+#include "vae_train_abi.inc"
 
 extern "C" {
 

@@ -1,0 +1,1238 @@
+// VAE training step (n_embed = 32) on the device: forward with the activations the backward pass needs, NB loss and its
+// gradient, backward of decoder / encoder into a flat gradient buffer.
+// Reference: VAE.training_step src/scldm/models.py:249-287, TransformerVAE.forward vae.py:29-56, VAE.loss models.py:233-247,
+// log_nb_positive distributions.py:6-42, Encoder / Decoder nnets.py:82-208, CrossAttentionBlock layers.py:267-330,
+// Block layers.py:177-226, InputTransformerVAE layers.py:97-118, NegativeBinomialTransformerLayer stochastic_layers.py:102-116.
+//
+// Where the work is: the decoder's cross-attention block runs on every (cell, gene) token - B x G of them (4.6 M for 128 cells
+// of the census vocabulary), 28 k multiply-adds each for forward + dgrad + wgrad.  dec_mcab_train_kernel keeps a 64-token tile of
+// one cell in shared memory, recomputes its forward and differentiates it there; every GEMM of the tile (c_proj, [w1|w2], mlp.c_proj,
+// their dgrads and the weight gradients, which accumulate in registers over all tiles a CTA visits) is TF32 mma.sync fed from
+// shared memory - the precision the reference trains in (torch.set_float32_matmul_precision("high"), scripts/train.py:18).
+// Everything that is per cell (16 latent tokens x 32 channels through 2 x n_layer Blocks) or per encoder token is fp32 CUDA-core
+// code: < 3 % of the step's arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstddef>
+
+#include "vae_kernels.cuh"
+
+namespace vtr {
+
+constexpr int E = 32, M = 16, LAT = 16, H = 88;
+constexpr int NHB = 8, HDB = 4;   // Block self attention: 8 heads x 4
+constexpr int NHC = 4, HDC = 8;   // cross attention: 4 heads x 8
+// parameter group of a Block (element offsets inside the flat buffer, from the block's base)
+constexpr int B_LN1W = 0, B_LN1B = 32, B_CATTN = 64, B_CPROJ = B_CATTN + 96 * 32, B_LN2W = B_CPROJ + 1024, B_LN2B = B_LN2W + 32,
+              B_W1 = B_LN2B + 32, B_W2 = B_W1 + H * 32, B_W3 = B_W2 + H * 32, B_SIZE = B_W3 + 32 * H;
+// parameter group of a CrossAttentionBlock
+constexpr int C_LN1W = 0, C_LN1B = 32, C_LN1QW = 64, C_LN1QB = 96, C_LN2W = 128, C_LN2B = 160, C_CATTN = 192,
+              C_CATTNQ = C_CATTN + 64 * 32, C_CPROJ = C_CATTNQ + 1024, C_W1 = C_CPROJ + 1024, C_W2 = C_W1 + H * 32,
+              C_W3 = C_W2 + H * 32, C_SIZE = C_W3 + 32 * H;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-cooperative fp32 helpers on 16-row tiles in shared memory (the per-cell latent chain)
+// ---------------------------------------------------------------------------------------------------------------
+// y[r][o] (=, +=) sum_k x[r][k] W[o][k]   (W: global, row-major [O][K], K % 4 == 0)
+template <int ADD>
+__device__ __forceinline__ void lin16(const float* x, int ldx, int K, const float* __restrict__ W, int O, float* y, int ldy) {
+  for (int idx = threadIdx.x; idx < 16 * O; idx += blockDim.x) {
+    const int r = idx / O, o = idx - r * O;
+    const float* w = W + (size_t)o * K;
+    const float* xr = x + r * ldx;
+    float acc = 0.f;
+    for (int k = 0; k < K; k += 4) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + k);
+      acc += wv.x * xr[k] + wv.y * xr[k + 1] + wv.z * xr[k + 2] + wv.w * xr[k + 3];
+    }
+    if (ADD) y[r * ldy + o] += acc; else y[r * ldy + o] = acc;
+  }
+}
+// dx[r][k] (=, +=) sum_o dy[r][o] W[o][k]
+template <int ADD>
+__device__ __forceinline__ void lin16_t(const float* dy, int ldy, int O, const float* __restrict__ W, int K, float* dx, int ldx) {
+  for (int idx = threadIdx.x; idx < 16 * K; idx += blockDim.x) {
+    const int r = idx / K, k = idx - r * K;
+    const float* d = dy + r * ldy;
+    float acc = 0.f;
+    for (int o = 0; o < O; ++o) acc += d[o] * W[(size_t)o * K + k];
+    if (ADD) dx[r * ldx + k] += acc; else dx[r * ldx + k] = acc;
+  }
+}
+// gW[o][k] += sum_{r < R} dy[r][o] x[r][k]   (atomics into the flat gradient buffer)
+__device__ __forceinline__ void wgrad_rows(const float* dy, int ldy, int O, const float* x, int ldx, int K, int R, float* gW) {
+  for (int idx = threadIdx.x; idx < O * K; idx += blockDim.x) {
+    const int o = idx / K, k = idx - o * K;
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) acc += dy[r * ldy + o] * x[r * ldx + k];
+    atomicAdd(gW + idx, acc);
+  }
+}
+// LayerNorm over `dim` <= 32 channels of 16 rows, one warp per row (w / b nullable: no affine)
+__device__ __forceinline__ void ln16(const float* x, int ldx, int dim, const float* __restrict__ w, const float* __restrict__ b,
+                                     float eps, float* y, int ldy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float inv = 1.f / (float)dim;
+  for (int r = warp; r < 16; r += nw) {
+    const float v = lane < dim ? x[r * ldx + lane] : 0.f;
+    const float mean = warp_sum(v) * inv;
+    const float d = lane < dim ? v - mean : 0.f;
+    const float rstd = rsqrtf(warp_sum(d * d) * inv + eps);
+    if (lane < dim) y[r * ldy + lane] = d * rstd * (w ? w[lane] : 1.f) + (b ? b[lane] : 0.f);
+  }
+}
+// backward of the above: dy = gradient w.r.t. the LayerNorm output, x = its input; dx (=, +=); gw / gb nullable
+template <int ADD>
+__device__ __forceinline__ void ln16_bwd(const float* dy, int ldd, const float* x, int ldx, int dim, const float* __restrict__ w,
+                                         float eps, float* dx, int lddx, float* gw, float* gb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float inv = 1.f / (float)dim;
+  float accw = 0.f, accb = 0.f;
+  for (int r = warp; r < 16; r += nw) {
+    const float v = lane < dim ? x[r * ldx + lane] : 0.f;
+    const float mean = warp_sum(v) * inv;
+    const float d = lane < dim ? v - mean : 0.f;
+    const float rstd = rsqrtf(warp_sum(d * d) * inv + eps);
+    const float xhat = d * rstd;
+    const float g = lane < dim ? dy[r * ldd + lane] : 0.f;
+    accw += g * xhat;
+    accb += g;
+    const float gy = g * (w ? (lane < dim ? w[lane] : 0.f) : 1.f);
+    const float m1 = warp_sum(gy) * inv, m2 = warp_sum(gy * xhat) * inv;
+    const float dxv = rstd * (gy - m1 - xhat * m2);
+    if (lane < dim) { if (ADD) dx[r * lddx + lane] += dxv; else dx[r * lddx + lane] = dxv; }
+  }
+  if (gw && lane < dim) { atomicAdd(gw + lane, accw); atomicAdd(gb + lane, accb); }
+}
+
+// shared-memory working set of the latent chain (floats)
+struct LatS {
+  float x[16 * 32], xn[16 * 32], qkv[16 * 96], ao[16 * 32], u[16 * H], v[16 * H];
+  // backward only
+  float xm[16 * 32], hh[16 * H], P[NHB * 16 * 16], dS[NHB * 16 * 16], dx[16 * 32], dt[16 * 96], dao[16 * 32], dhh[16 * H];
+};
+constexpr size_t LAT_FWD_SMEM = offsetof(LatS, xm);
+
+// Block self attention on the 16 tokens: thread (head, query)
+__device__ __forceinline__ void attn16_fwd(const float* qkv, float* ao, float* P) {
+  if (threadIdx.x < 128) {
+    const int h = threadIdx.x >> 4, i = threadIdx.x & 15;
+    float q[HDB], s[16], mx = -1e30f;
+#pragma unroll
+    for (int d = 0; d < HDB; ++d) q[d] = qkv[i * 96 + h * HDB + d] * 0.5f;   // 1 / sqrt(head_dim = 4)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < HDB; ++d) a += q[d] * qkv[j * 96 + 32 + h * HDB + d];
+      s[j] = a;
+      mx = fmaxf(mx, a);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { s[j] = __expf(s[j] - mx); l += s[j]; }
+    const float il = 1.f / l;
+    float o[HDB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float p = s[j] * il;
+      if (P) P[(h * 16 + i) * 16 + j] = p;
+#pragma unroll
+      for (int d = 0; d < HDB; ++d) o[d] += p * qkv[j * 96 + 64 + h * HDB + d];
+    }
+#pragma unroll
+    for (int d = 0; d < HDB; ++d) ao[i * 32 + h * HDB + d] = o[d];
+  }
+}
+// backward: dao -> dqkv (q | k | v gradients, [16][96]); dS is scratch.  Contains its own CTA barriers.
+__device__ __forceinline__ void attn16_bwd(const float* qkv, const float* P, const float* dao, float* dS, float* dqkv) {
+  if (threadIdx.x < 128) {
+    const int h = threadIdx.x >> 4, i = threadIdx.x & 15;
+    float g[HDB], dp[16], D = 0.f;
+#pragma unroll
+    for (int d = 0; d < HDB; ++d) g[d] = dao[i * 32 + h * HDB + d];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < HDB; ++d) a += g[d] * qkv[j * 96 + 64 + h * HDB + d];
+      dp[j] = a;
+      D += P[(h * 16 + i) * 16 + j] * a;
+    }
+    float dq[HDB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float ds = P[(h * 16 + i) * 16 + j] * (dp[j] - D) * 0.5f;   // includes the 1 / sqrt(head_dim) of the scores
+      dS[(h * 16 + i) * 16 + j] = ds;
+#pragma unroll
+      for (int d = 0; d < HDB; ++d) dq[d] += ds * qkv[j * 96 + 32 + h * HDB + d];
+    }
+#pragma unroll
+    for (int d = 0; d < HDB; ++d) dqkv[i * 96 + h * HDB + d] = dq[d];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int h = threadIdx.x >> 4, j = threadIdx.x & 15;
+    float dk[HDB] = {0.f, 0.f, 0.f, 0.f}, dv[HDB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float ds = dS[(h * 16 + i) * 16 + j], p = P[(h * 16 + i) * 16 + j];
+#pragma unroll
+      for (int d = 0; d < HDB; ++d) {
+        dk[d] += ds * qkv[i * 96 + h * HDB + d];
+        dv[d] += p * dao[i * 32 + h * HDB + d];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < HDB; ++d) { dqkv[j * 96 + 32 + h * HDB + d] = dk[d]; dqkv[j * 96 + 64 + h * HDB + d] = dv[d]; }
+  }
+  __syncthreads();
+}
+
+// x <- x + c_proj(silu(w1 LN2(x)) * (w2 LN2(x)))   (SwiGLU MLP of Block / CrossAttentionBlock, layers.py:161-174)
+__device__ __forceinline__ void mlp16_fwd(LatS& s, const float* ln2w, const float* ln2b, const float* w1, const float* w2, const float* w3,
+                                          float eps) {
+  ln16(s.x, 32, 32, ln2w, ln2b, eps, s.xn, 32);
+  __syncthreads();
+  lin16<0>(s.xn, 32, 32, w1, H, s.u, H);
+  lin16<0>(s.xn, 32, 32, w2, H, s.v, H);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) { const float a = s.u[i]; s.u[i] = a * sigmoidf_(a) * s.v[i]; }
+  __syncthreads();
+  lin16<1>(s.u, H, H, w3, 32, s.x, 32);
+  __syncthreads();
+}
+// backward of the MLP half: xin = its input (LN2 input), s.dx = gradient of its output on entry, of its input on exit
+__device__ __forceinline__ void mlp16_bwd(LatS& s, const float* xin, const float* ln2w, const float* ln2b, const float* w1, const float* w2,
+                                          const float* w3, float* g_ln2w, float* g_ln2b, float* g_w1, float* g_w2, float* g_w3, float eps) {
+  ln16(xin, 32, 32, ln2w, ln2b, eps, s.xn, 32);
+  __syncthreads();
+  lin16<0>(s.xn, 32, 32, w1, H, s.u, H);
+  lin16<0>(s.xn, 32, 32, w2, H, s.v, H);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) { const float a = s.u[i]; s.hh[i] = a * sigmoidf_(a) * s.v[i]; }
+  __syncthreads();
+  wgrad_rows(s.dx, 32, 32, s.hh, H, H, 16, g_w3);
+  lin16_t<0>(s.dx, 32, 32, w3, H, s.dhh, H);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) {
+    const float a = s.u[i], sg = sigmoidf_(a), dh = s.dhh[i];
+    s.u[i] = dh * s.v[i] * sg * (1.f + a * (1.f - sg));   // du
+    s.v[i] = dh * a * sg;                                 // dv
+  }
+  __syncthreads();
+  wgrad_rows(s.u, H, H, s.xn, 32, 32, 16, g_w1);
+  wgrad_rows(s.v, H, H, s.xn, 32, 32, 16, g_w2);
+  lin16_t<0>(s.u, H, H, w1, 32, s.dao, 32);
+  __syncthreads();
+  lin16_t<1>(s.v, H, H, w2, 32, s.dao, 32);
+  __syncthreads();
+  ln16_bwd<1>(s.dao, 32, xin, 32, 32, ln2w, eps, s.dx, 32, g_ln2w, g_ln2b);
+  __syncthreads();
+}
+
+__device__ __forceinline__ void block16_fwd(LatS& s, const float* bp, float eps) {
+  ln16(s.x, 32, 32, bp + B_LN1W, bp + B_LN1B, eps, s.xn, 32);
+  __syncthreads();
+  lin16<0>(s.xn, 32, 32, bp + B_CATTN, 96, s.qkv, 96);
+  __syncthreads();
+  attn16_fwd(s.qkv, s.ao, nullptr);
+  __syncthreads();
+  lin16<1>(s.ao, 32, 32, bp + B_CPROJ, 32, s.x, 32);
+  __syncthreads();
+  mlp16_fwd(s, bp + B_LN2W, bp + B_LN2B, bp + B_W1, bp + B_W2, bp + B_W3, eps);
+}
+// s.x = the block's input, s.dx = gradient of its output -> s.dx = gradient of its input; weight gradients into gp
+__device__ __forceinline__ void block16_bwd(LatS& s, const float* bp, float* gp, float eps) {
+  ln16(s.x, 32, 32, bp + B_LN1W, bp + B_LN1B, eps, s.xn, 32);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s.xm[i] = s.x[i];
+  __syncthreads();
+  lin16<0>(s.xn, 32, 32, bp + B_CATTN, 96, s.qkv, 96);
+  __syncthreads();
+  attn16_fwd(s.qkv, s.ao, s.P);
+  __syncthreads();
+  lin16<1>(s.ao, 32, 32, bp + B_CPROJ, 32, s.xm, 32);   // xm = x + attention
+  __syncthreads();
+  mlp16_bwd(s, s.xm, bp + B_LN2W, bp + B_LN2B, bp + B_W1, bp + B_W2, bp + B_W3, gp + B_LN2W, gp + B_LN2B, gp + B_W1, gp + B_W2, gp + B_W3, eps);
+  // s.dx = d xm.  attention half (s.xn was overwritten by the MLP's LN2 output: recompute LN1)
+  ln16(s.x, 32, 32, bp + B_LN1W, bp + B_LN1B, eps, s.xn, 32);
+  wgrad_rows(s.dx, 32, 32, s.ao, 32, 32, 16, gp + B_CPROJ);
+  lin16_t<0>(s.dx, 32, 32, bp + B_CPROJ, 32, s.dao, 32);
+  __syncthreads();
+  attn16_bwd(s.qkv, s.P, s.dao, s.dS, s.dt);
+  wgrad_rows(s.dt, 96, 96, s.xn, 32, 32, 16, gp + B_CATTN);
+  lin16_t<0>(s.dt, 96, 96, bp + B_CATTN, 32, s.dao, 32);
+  __syncthreads();
+  ln16_bwd<1>(s.dao, 32, s.x, 32, 32, bp + B_LN1W, eps, s.dx, 32, gp + B_LN1W, gp + B_LN1B);
+  __syncthreads();
+}
+
+struct LatParams {
+  const float* params; float* grads;
+  long long enc_ca, dec_ca, inducing, enc_blocks, dec_blocks, enc_lat, dec_lat;   // element offsets
+  const float* pos;         // encoder.pos_embed [16][32] or nullptr (frozen in the reference, nnets.py:103-106)
+  int n_layer; float eps;
+  const float* ao_enc;      // [B][16][32] pooled attention output of the encoder MCAB
+  float* x1_enc;            // [B][16][32] inducing + c_proj(ao)
+  float* xe;                // [n_layer + 1][B][16][32] encoder block inputs / output
+  float* hlat;              // [B][16][16] encoder_latent_input Linear output (before the LayerNorm)
+  float* z;                 // [B][16][16] latents
+  float* xd;                // [n_layer + 1][B][16][32]
+  float* kdec; float* vdec; // [B][16][32] keys / values of the decoder MCAB
+  const float* dkdec; const float* dvdec;
+  float* dao_enc;           // [B][16][32]
+  int B;
+};
+
+__device__ __forceinline__ void tile_load(float* dst, const float* __restrict__ src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+__device__ __forceinline__ void tile_store(float* __restrict__ dst, const float* src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// One CTA per cell: encoder MCAB tail -> encoder Blocks -> latent projection + LN -> decoder front -> decoder Blocks -> K, V
+__global__ void __launch_bounds__(128) latent_fwd_kernel(const LatParams p) {
+  extern __shared__ float4 lat_smem4[];
+  LatS& s = *reinterpret_cast<LatS*>(lat_smem4);
+  const int b = blockIdx.x;
+  const size_t cell = (size_t)b * 512, lay = (size_t)p.B * 512;
+  const float* eca = p.params + p.enc_ca;
+  tile_load(s.ao, p.ao_enc + cell, 512);
+  tile_load(s.x, p.params + p.inducing, 512);
+  __syncthreads();
+  lin16<1>(s.ao, 32, 32, eca + C_CPROJ, 32, s.x, 32);   // x1 = q + attention (the residual is the raw query, layers.py:327)
+  __syncthreads();
+  tile_store(p.x1_enc + cell, s.x, 512);
+  mlp16_fwd(s, eca + C_LN2W, eca + C_LN2B, eca + C_W1, eca + C_W2, eca + C_W3, p.eps);
+  if (p.pos) { for (int i = threadIdx.x; i < 512; i += blockDim.x) s.x[i] += p.pos[i]; __syncthreads(); }
+  tile_store(p.xe + cell, s.x, 512);
+  for (int l = 0; l < p.n_layer; ++l) {
+    block16_fwd(s, p.params + p.enc_blocks + (size_t)l * B_SIZE, p.eps);
+    tile_store(p.xe + (size_t)(l + 1) * lay + cell, s.x, 512);
+  }
+  lin16<0>(s.x, 32, 32, p.params + p.enc_lat, LAT, s.ao, LAT);
+  __syncthreads();
+  tile_store(p.hlat + (size_t)b * 256, s.ao, 256);
+  ln16(s.ao, LAT, LAT, nullptr, nullptr, p.eps, s.xn, LAT);
+  __syncthreads();
+  tile_store(p.z + (size_t)b * 256, s.xn, 256);
+  ln16(s.xn, LAT, LAT, nullptr, nullptr, p.eps, s.ao, LAT);     // the decoder normalises the latents again (nnets.py:203)
+  __syncthreads();
+  lin16<0>(s.ao, LAT, LAT, p.params + p.dec_lat, 32, s.x, 32);
+  __syncthreads();
+  tile_store(p.xd + cell, s.x, 512);
+  for (int l = 0; l < p.n_layer; ++l) {
+    block16_fwd(s, p.params + p.dec_blocks + (size_t)l * B_SIZE, p.eps);
+    tile_store(p.xd + (size_t)(l + 1) * lay + cell, s.x, 512);
+  }
+  const float* dca = p.params + p.dec_ca;
+  ln16(s.x, 32, 32, dca + C_LN1W, dca + C_LN1B, p.eps, s.xn, 32);
+  __syncthreads();
+  lin16<0>(s.xn, 32, 32, dca + C_CATTN, 64, s.qkv, 64);   // k first, then v (layers.py:252)
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const int j = i >> 5, c = i & 31;
+    p.kdec[cell + i] = s.qkv[j * 64 + c];
+    p.vdec[cell + i] = s.qkv[j * 64 + 32 + c];
+  }
+}
+
+__global__ void __launch_bounds__(128) latent_bwd_kernel(const LatParams p) {
+  extern __shared__ float4 lat_smem4[];
+  LatS& s = *reinterpret_cast<LatS*>(lat_smem4);
+  const int b = blockIdx.x;
+  const size_t cell = (size_t)b * 512, lay = (size_t)p.B * 512;
+  const float* dca = p.params + p.dec_ca;
+  float* gdca = p.grads + p.dec_ca;
+  // K, V of the decoder MCAB = c_attn(LN1(latents))
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const int j = i >> 5, c = i & 31;
+    s.dt[j * 64 + c] = p.dkdec[cell + i];
+    s.dt[j * 64 + 32 + c] = p.dvdec[cell + i];
+  }
+  tile_load(s.x, p.xd + (size_t)p.n_layer * lay + cell, 512);
+  __syncthreads();
+  ln16(s.x, 32, 32, dca + C_LN1W, dca + C_LN1B, p.eps, s.xn, 32);
+  __syncthreads();
+  wgrad_rows(s.dt, 64, 64, s.xn, 32, 32, 16, gdca + C_CATTN);
+  lin16_t<0>(s.dt, 64, 64, dca + C_CATTN, 32, s.dao, 32);
+  __syncthreads();
+  ln16_bwd<0>(s.dao, 32, s.x, 32, 32, dca + C_LN1W, p.eps, s.dx, 32, gdca + C_LN1W, gdca + C_LN1B);
+  __syncthreads();
+  for (int l = p.n_layer - 1; l >= 0; --l) {
+    tile_load(s.x, p.xd + (size_t)l * lay + cell, 512);
+    __syncthreads();
+    block16_bwd(s, p.params + p.dec_blocks + (size_t)l * B_SIZE, p.grads + p.dec_blocks + (size_t)l * B_SIZE, p.eps);
+  }
+  // decoder front: x0 = W_d LN(z)
+  tile_load(s.qkv, p.z + (size_t)b * 256, 256);                 // z
+  __syncthreads();
+  ln16(s.qkv, LAT, LAT, nullptr, nullptr, p.eps, s.qkv + 256, LAT);   // LN(z)
+  __syncthreads();
+  wgrad_rows(s.dx, 32, 32, s.qkv + 256, LAT, LAT, 16, p.grads + p.dec_lat);
+  lin16_t<0>(s.dx, 32, 32, p.params + p.dec_lat, LAT, s.qkv + 512, LAT);   // d LN(z)
+  __syncthreads();
+  ln16_bwd<0>(s.qkv + 512, LAT, s.qkv, LAT, LAT, nullptr, p.eps, s.qkv + 768, LAT, nullptr, nullptr);   // dz
+  tile_load(s.ao, p.hlat + (size_t)b * 256, 256);
+  __syncthreads();
+  ln16_bwd<0>(s.qkv + 768, LAT, s.ao, LAT, LAT, nullptr, p.eps, s.qkv + 1024, LAT, nullptr, nullptr);   // d hlat
+  tile_load(s.x, p.xe + (size_t)p.n_layer * lay + cell, 512);
+  __syncthreads();
+  wgrad_rows(s.qkv + 1024, LAT, LAT, s.x, 32, 32, 16, p.grads + p.enc_lat);
+  lin16_t<0>(s.qkv + 1024, LAT, LAT, p.params + p.enc_lat, 32, s.dx, 32);
+  __syncthreads();
+  for (int l = p.n_layer - 1; l >= 0; --l) {
+    tile_load(s.x, p.xe + (size_t)l * lay + cell, 512);
+    __syncthreads();
+    block16_bwd(s, p.params + p.enc_blocks + (size_t)l * B_SIZE, p.grads + p.enc_blocks + (size_t)l * B_SIZE, p.eps);
+  }
+  // encoder MCAB tail: x2 = x1 + MLP(LN2(x1)), x1 = inducing + c_proj(ao)
+  const float* eca = p.params + p.enc_ca;
+  float* geca = p.grads + p.enc_ca;
+  tile_load(s.xm, p.x1_enc + cell, 512);
+  __syncthreads();
+  mlp16_bwd(s, s.xm, eca + C_LN2W, eca + C_LN2B, eca + C_W1, eca + C_W2, eca + C_W3, geca + C_LN2W, geca + C_LN2B, geca + C_W1, geca + C_W2,
+            geca + C_W3, p.eps);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) atomicAdd(p.grads + p.inducing + i, s.dx[i]);
+  tile_load(s.ao, p.ao_enc + cell, 512);
+  __syncthreads();
+  wgrad_rows(s.dx, 32, 32, s.ao, 32, 32, 16, geca + C_CPROJ);
+  lin16_t<0>(s.dx, 32, 32, eca + C_CPROJ, 32, s.dao, 32);
+  __syncthreads();
+  tile_store(p.dao_enc + cell, s.dao, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Query side of a CrossAttentionBlock: Q = c_attn_q(LN1q(row)); rows = inducing points (encoder) or emb[gene] (decoder).
+// Cell-invariant, so it is computed once per step and its backward once on the gradients summed over cells.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qside_fwd_kernel(const float* __restrict__ rows, const long long* __restrict__ ids, int n,
+                                                        const float* __restrict__ ca, float eps, float* __restrict__ Q) {
+  __shared__ float sW[1024], sw[32], sb[32];
+  for (int i = threadIdx.x; i < 1024; i += 128) sW[i] = ca[C_CATTNQ + i];
+  if (threadIdx.x < 32) { sw[threadIdx.x] = ca[C_LN1QW + threadIdx.x]; sb[threadIdx.x] = ca[C_LN1QB + threadIdx.x]; }
+  __syncthreads();
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  if (r >= n) return;
+  const float* src = rows + (size_t)(ids ? ids[r] : r) * 32;
+  float x[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) { const float4 v = *reinterpret_cast<const float4*>(src + k); x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w; }
+  float mean = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) mean += x[k];
+  mean *= (1.f / 32.f);
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { x[k] -= mean; var += x[k] * x[k]; }
+  const float rstd = rsqrtf(var * (1.f / 32.f) + eps);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) x[k] = x[k] * rstd * sw[k] + sb[k];
+#pragma unroll 4
+  for (int o = 0; o < 32; ++o) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a += sW[o * 32 + k] * x[k];
+    Q[(size_t)r * 32 + o] = a;
+  }
+}
+
+// dQ [n][32] (summed over cells) -> gradients of c_attn_q, ln_1q and of the rows themselves (+ dres, the residual path of the
+// block: x = q + attention); d_rows[id] += ...
+__global__ void __launch_bounds__(128) qside_bwd_kernel(const float* __restrict__ rows, const long long* __restrict__ ids, int n,
+                                                        const float* __restrict__ ca, float eps, const float* __restrict__ dQ,
+                                                        const float* __restrict__ dres, float* d_rows, float* gca) {
+  __shared__ float sW[1024], sw[32];
+  __shared__ float t1[128 * 33], t2[128 * 33];
+  for (int i = threadIdx.x; i < 1024; i += 128) sW[i] = ca[C_CATTNQ + i];
+  if (threadIdx.x < 32) sw[threadIdx.x] = ca[C_LN1QW + threadIdx.x];
+  __syncthreads();
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  const bool valid = r < n;
+  const long long id = valid ? (ids ? ids[r] : r) : 0;
+  const float* src = rows + (size_t)id * 32;
+  float x[32], dq[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + k);
+    x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) dq[k] = valid ? dQ[(size_t)r * 32 + k] : 0.f;
+  float mean = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) mean += x[k];
+  mean *= (1.f / 32.f);
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { x[k] -= mean; var += x[k] * x[k]; }
+  const float rstd = rsqrtf(var * (1.f / 32.f) + eps);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) x[k] *= rstd;                      // xhat
+  // d(LN output) = Wq^T dq
+  float m1 = 0.f, m2 = 0.f;
+  float g[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    float a = 0.f;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) a += sW[o * 32 + k] * dq[o];
+    t1[threadIdx.x * 33 + k] = a * x[k];     // -> d ln_1q.weight
+    t2[threadIdx.x * 33 + k] = a;            // -> d ln_1q.bias
+    g[k] = a * sw[k];
+    m1 += g[k];
+    m2 += g[k] * x[k];
+  }
+  m1 *= (1.f / 32.f); m2 *= (1.f / 32.f);
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float dxv = rstd * (g[k] - m1 - x[k] * m2);
+      if (dres) dxv += dres[(size_t)r * 32 + k];
+      atomicAdd(d_rows + (size_t)id * 32 + k, dxv);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x & 31;
+    const float* t = threadIdx.x < 32 ? t1 : t2;
+    float a = 0.f;
+    for (int i = 0; i < 128; ++i) a += t[i * 33 + k];
+    atomicAdd(gca + (threadIdx.x < 32 ? C_LN1QW : C_LN1QB) + k, a);
+  }
+  __syncthreads();
+  // c_attn_q weight gradient: sum over rows of dq (x) LN1q(row)
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    t1[threadIdx.x * 33 + k] = dq[k];
+    t2[threadIdx.x * 33 + k] = valid ? x[k] * sw[k] + ca[C_LN1QB + k] : 0.f;
+  }
+  __syncthreads();
+  wgrad_rows(t1, 33, 32, t2, 33, 32, 128, gca + C_CATTNQ);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Encoder tokens: x = emb[gene] * f(count) -> LN1 -> K, V = c_attn  (layers.py:97-118, 248-252), one thread per token
+// ---------------------------------------------------------------------------------------------------------------
+struct EncTokParams {
+  const float* emb; const long long* genes; const float* counts; int agg; long long n_tok;
+  const float* ca; float eps;
+  float* K; float* V;      // [n_tok][32]
+  float* stats;            // [n_tok][2] mean, rstd of LN1
+};
+__global__ void __launch_bounds__(128) enc_tokens_fwd_kernel(const EncTokParams p) {
+  __shared__ float sW[64 * 32], sw[32], sb[32];
+  for (int i = threadIdx.x; i < 2048; i += 128) sW[i] = p.ca[C_CATTN + i];
+  if (threadIdx.x < 32) { sw[threadIdx.x] = p.ca[C_LN1W + threadIdx.x]; sb[threadIdx.x] = p.ca[C_LN1B + threadIdx.x]; }
+  __syncthreads();
+  const long long tk = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (tk >= p.n_tok) return;
+  const float f = vae::count_scale(p.counts[tk], p.agg);
+  const float* src = p.emb + (size_t)p.genes[tk] * 32;
+  float x[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + k);
+    x[k] = v.x * f; x[k + 1] = v.y * f; x[k + 2] = v.z * f; x[k + 3] = v.w * f;
+  }
+  float mean = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) mean += x[k];
+  mean *= (1.f / 32.f);
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { x[k] -= mean; var += x[k] * x[k]; }
+  const float rstd = rsqrtf(var * (1.f / 32.f) + p.eps);
+  p.stats[tk * 2] = mean;
+  p.stats[tk * 2 + 1] = rstd;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) x[k] = x[k] * rstd * sw[k] + sb[k];
+#pragma unroll 2
+  for (int o = 0; o < 64; o += 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] += sW[(o + q) * 32 + k] * x[k];
+    }
+    float* dst = (o < 32 ? p.K : p.V) + tk * 32 + (o & 31);
+    *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+}
+
+// Encoder MCAB pooling: 16 inducing-point queries x 4 heads attend to all S tokens of a cell (no key masking).
+// One CTA per cell; thread = (query, head) pair x one of 8 interleaved token slices; online softmax, merged through shared memory.
+__global__ void __launch_bounds__(512) enc_pool_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                                                           int S, float* __restrict__ AO, float* __restrict__ lse) {
+  __shared__ float sm[8][64][10];
+  const int b = blockIdx.x, pair = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int m = pair >> 2, h = pair & 3;
+  float q[8], acc[8], mx = -1e30f, l = 0.f;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) { q[d] = Q[m * 32 + h * 8 + d] * 0.35355339059327373f; acc[d] = 0.f; }
+  const float* kb = K + (size_t)b * S * 32 + h * 8;
+  const float* vb = V + (size_t)b * S * 32 + h * 8;
+#pragma unroll 2
+  for (int s = slice; s < S; s += 8) {
+    const float4 k0 = *reinterpret_cast<const float4*>(kb + (size_t)s * 32), k1 = *reinterpret_cast<const float4*>(kb + (size_t)s * 32 + 4);
+    const float4 v0 = *reinterpret_cast<const float4*>(vb + (size_t)s * 32), v1 = *reinterpret_cast<const float4*>(vb + (size_t)s * 32 + 4);
+    const float sc = q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w + q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w;
+    if (sc > mx) {
+      const float corr = __expf(mx - sc);
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] *= corr;
+      mx = sc;
+    }
+    const float pr = __expf(sc - mx);
+    l += pr;
+    acc[0] += pr * v0.x; acc[1] += pr * v0.y; acc[2] += pr * v0.z; acc[3] += pr * v0.w;
+    acc[4] += pr * v1.x; acc[5] += pr * v1.y; acc[6] += pr * v1.z; acc[7] += pr * v1.w;
+  }
+  sm[slice][pair][0] = mx; sm[slice][pair][1] = l;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) sm[slice][pair][2 + d] = acc[d];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float gm = -1e30f;
+    for (int i = 0; i < 8; ++i) gm = fmaxf(gm, sm[i][pair][0]);
+    float gl = 0.f, ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < 8; ++i) {
+      const float c = __expf(sm[i][pair][0] - gm);
+      gl += sm[i][pair][1] * c;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) ga[d] += sm[i][pair][2 + d] * c;
+    }
+    const float il = 1.f / gl;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) AO[(size_t)b * 512 + m * 32 + h * 8 + d] = ga[d] * il;
+    lse[b * 64 + pair] = gm + __logf(gl);
+  }
+}
+
+// Backward of the pooling and of the token side, one thread per token of a 128-token tile of one cell:
+// dAO -> (dK, dV of the token) -> c_attn^T -> LN1 backward -> d emb[gene] (scatter) ; weight gradients of c_attn / ln_1 and
+// the query gradient dQ (summed over tokens and cells) through shared-memory tiles.
+struct EncBwdParams {
+  const float* emb; const long long* genes; const float* counts; int agg; int S;
+  const float* ca; float* gca; float eps;
+  const float* Q;            // [16][32]
+  const float* K; const float* V; const float* stats; const float* lse;   // saved by the forward
+  const float* AO; const float* dAO;     // [B][16][32]
+  float* dQ;                 // [16][32] accumulated (atomics)
+  float* g_emb;              // gradient of the embedding table
+};
+constexpr int ENC_BWD_SMEM_FLOATS = 128 * 65 + 128 * 33 + 128 * 65 + 128 * 33 + 512 * 2 + 64 + 2048 + 64;
+__global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams p) {
+  extern __shared__ float4 enc_smem4[];
+  float* sm = reinterpret_cast<float*>(enc_smem4);
+  float* tDKV = sm;                     // [128][65]  dK | dV of the tile's tokens
+  float* tXN = tDKV + 128 * 65;         // [128][33]  LN1 output
+  float* tDS = tXN + 128 * 33;          // [128][65]  dS[(query, head)] of the tile's tokens (scaled)
+  float* tK = tDS + 128 * 65;           // [128][33]
+  float* sQ = tK + 128 * 33;            // [16][32] scaled queries
+  float* sDAO = sQ + 512;               // [16][32]
+  float* sD = sDAO + 512;               // [64] rowsum(dAO * AO) per (query, head)
+  float* sW = sD + 64;                  // c_attn [64][32]
+  float* sLn = sW + 2048;               // ln_1 weight | bias
+  const int b = blockIdx.y, s = blockIdx.x * 128 + threadIdx.x;
+  const bool valid = s < p.S;
+  const long long tk = (long long)b * p.S + (valid ? s : 0);
+  for (int i = threadIdx.x; i < 512; i += 128) { sQ[i] = p.Q[i] * 0.35355339059327373f; sDAO[i] = p.dAO[(size_t)b * 512 + i]; }
+  for (int i = threadIdx.x; i < 2048; i += 128) sW[i] = p.ca[C_CATTN + i];
+  if (threadIdx.x < 64) sLn[threadIdx.x] = p.ca[C_LN1W + threadIdx.x];   // ln_1.weight, ln_1.bias are adjacent
+  if (threadIdx.x < 64) {
+    const int m = threadIdx.x >> 2, h = threadIdx.x & 3;
+    float a = 0.f;
+    for (int d = 0; d < 8; ++d) a += p.dAO[(size_t)b * 512 + m * 32 + h * 8 + d] * p.AO[(size_t)b * 512 + m * 32 + h * 8 + d];
+    sD[threadIdx.x] = a;
+  }
+  __syncthreads();
+  float kk[32], vv[32], dk[32], dv[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p.K + tk * 32 + k), c = *reinterpret_cast<const float4*>(p.V + tk * 32 + k);
+    kk[k] = a.x; kk[k + 1] = a.y; kk[k + 2] = a.z; kk[k + 3] = a.w;
+    vv[k] = c.x; vv[k + 1] = c.y; vv[k + 2] = c.z; vv[k + 3] = c.w;
+    dk[k] = dk[k + 1] = dk[k + 2] = dk[k + 3] = 0.f;
+    dv[k] = dv[k + 1] = dv[k + 2] = dv[k + 3] = 0.f;
+  }
+  const float* lse = p.lse + b * 64;
+#pragma unroll 1
+  for (int m = 0; m < 16; ++m) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float sc = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) { sc += sQ[m * 32 + h * 8 + d] * kk[h * 8 + d]; dp += sDAO[m * 32 + h * 8 + d] * vv[h * 8 + d]; }
+      const float pr = valid ? __expf(sc - lse[m * 4 + h]) : 0.f;
+      const float ds = pr * (dp - sD[m * 4 + h]);
+      tDS[threadIdx.x * 65 + m * 4 + h] = ds * 0.35355339059327373f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) { dk[h * 8 + d] += ds * sQ[m * 32 + h * 8 + d]; dv[h * 8 + d] += pr * sDAO[m * 32 + h * 8 + d]; }
+    }
+  }
+  // token side: recompute x, LN1
+  const float cnt = valid ? p.counts[tk] : 0.f;
+  const float f = vae::count_scale(cnt, p.agg);
+  const long long gid = valid ? p.genes[tk] : 0;
+  const float mean = p.stats[tk * 2], rstd = p.stats[tk * 2 + 1];
+  float xh[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p.emb + (size_t)gid * 32 + k);
+    xh[k] = (v.x * f - mean) * rstd; xh[k + 1] = (v.y * f - mean) * rstd; xh[k + 2] = (v.z * f - mean) * rstd; xh[k + 3] = (v.w * f - mean) * rstd;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    tDKV[threadIdx.x * 65 + k] = dk[k];
+    tDKV[threadIdx.x * 65 + 32 + k] = dv[k];
+    tXN[threadIdx.x * 33 + k] = valid ? xh[k] * sLn[k] + sLn[32 + k] : 0.f;
+    tK[threadIdx.x * 33 + k] = valid ? kk[k] : 0.f;
+  }
+  // d(LN1 output) = Wkv^T [dk | dv]
+  float g[32], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    float a = 0.f;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) a += sW[o * 32 + k] * dk[o] + sW[(32 + o) * 32 + k] * dv[o];
+    kk[k] = a;   // gradient w.r.t. the LN1 output (the key registers are dead: they live in tK)
+    g[k] = a * sLn[k];
+    m1 += g[k];
+    m2 += g[k] * xh[k];
+  }
+  m1 *= (1.f / 32.f); m2 *= (1.f / 32.f);
+  if (valid && f != 0.f) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) atomicAdd(p.g_emb + (size_t)gid * 32 + k, rstd * (g[k] - m1 - xh[k] * m2) * f);
+  }
+  __syncthreads();
+  // c_attn weight gradient and dQ from the tiles
+  wgrad_rows(tDKV, 65, 64, tXN, 33, 32, 128, p.gca + C_CATTN);
+  for (int idx = threadIdx.x; idx < 512; idx += 128) {
+    const int m = idx >> 5, c = idx & 31, h = c >> 3;
+    float a = 0.f;
+    for (int r = 0; r < 128; ++r) a += tDS[r * 65 + m * 4 + h] * tK[r * 33 + c];
+    atomicAdd(p.dQ + idx, a);
+  }
+  __syncthreads();
+  // ln_1 affine gradients: stage (d out * xhat, d out) in the two 33-wide tiles
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    tXN[threadIdx.x * 33 + k] = valid ? kk[k] * xh[k] : 0.f;
+    tK[threadIdx.x * 33 + k] = valid ? kk[k] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x & 31;
+    const float* t = threadIdx.x < 32 ? tXN : tK;
+    float a = 0.f;
+    for (int i = 0; i < 128; ++i) a += t[i * 33 + k];
+    atomicAdd(p.gca + (threadIdx.x < 32 ? C_LN1W : C_LN1B) + k, a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NB head: mu = softmax_genes(logit) * library, theta = exp(table[gene]); loss = sum_cells nll * loss_scale; d loss / d logit
+// (stochastic_layers.py:102-116, distributions.py:6-42, models.py:233-247).  One CTA per cell.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float digammaf_(float x) {
+  float r = 0.f;
+  while (x < 6.f) { r -= 1.f / x; x += 1.f; }
+  const float i = 1.f / x, i2 = i * i;
+  return r + __logf(x) - 0.5f * i - i2 * (1.f / 12.f - i2 * (1.f / 120.f - i2 * (1.f / 252.f)));
+}
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, t) : v + t; }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+struct NbLossParams {
+  const float* logits; const float* counts; const float* library; const float* theta_tbl; const long long* genes; int G;
+  float loss_scale; int backward;
+  float* nll;       // [B]
+  float* mu;        // nullable [B][G]
+  float* dlogit;    // [B][G]
+  float* g_theta;   // gradient of the theta table
+};
+__global__ void __launch_bounds__(512) nb_loss_kernel(const NbLossParams p) {
+  __shared__ float red[16];
+  const int b = blockIdx.x;
+  const float* lg = p.logits + (size_t)b * p.G;
+  const float* xc = p.counts + (size_t)b * p.G;
+  float mx = -1e30f;
+  for (int g = threadIdx.x; g < p.G; g += 512) mx = fmaxf(mx, lg[g]);
+  mx = block_reduce(mx, red, true);
+  float sum = 0.f;
+  for (int g = threadIdx.x; g < p.G; g += 512) sum += __expf(lg[g] - mx);
+  sum = block_reduce(sum, red, false);
+  const float lib = p.library[b], inv = 1.f / sum, eps = 1e-8f;
+  float nll = 0.f, sgm = 0.f;
+  for (int g = threadIdx.x; g < p.G; g += 512) {
+    const float pr = __expf(lg[g] - mx) * inv, mu = lib * pr, x = xc[g];
+    const long long gid = p.genes[g];
+    const float th = __expf(p.theta_tbl[gid]);
+    nll -= vae::nb_logp(x, mu, th);
+    if (p.mu) p.mu[(size_t)b * p.G + g] = mu;
+    if (p.backward) {
+      const float itm = 1.f / (th + mu + eps);
+      const float dmu = -(x / (mu + eps) - (th + x) * itm) * p.loss_scale;     // d(-ll)/dmu
+      const float gm = dmu * mu;
+      p.dlogit[(size_t)b * p.G + g] = gm;
+      sgm += gm;
+      float dps;   // digamma(x + theta) - digamma(theta)
+      const int k = (int)x;
+      if ((float)k == x && k <= 16) { dps = 0.f; for (int i = 0; i < k; ++i) dps += 1.f / (th + (float)i); }
+      else dps = digammaf_(x + th) - digammaf_(th);
+      const float dth = -(__logf(th + eps) - __logf(th + mu + eps) + th / (th + eps) - (th + x) * itm + dps) * p.loss_scale;
+      atomicAdd(p.g_theta + gid, dth * th);
+    }
+  }
+  nll = block_reduce(nll, red, false);
+  if (threadIdx.x == 0) p.nll[b] = nll;
+  if (p.backward) {
+    sgm = block_reduce(sgm, red, false);
+    for (int g = threadIdx.x; g < p.G; g += 512) {
+      const float pr = __expf(lg[g] - mx) * inv;
+      p.dlogit[(size_t)b * p.G + g] -= pr * sgm;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Decoder MCAB on (cell, gene) tokens: forward (logits) and, with BWD, the whole backward of the tile.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// acc[i] (16 x 8 tile i) += A[16 x 8 KS] * B[8 KS x 8] for `nt` column tiles; element strides: A(r, k) = A[r sar + k sac],
+// B(k, n) = Bm[k sbr + n sbc]; column tile i starts at n = i * nstep.  EXACT: 3 x TF32 (hi / lo split), fp32-grade products.
+template <bool EXACT, int NT, int KS>
+__device__ __forceinline__ void warp_gemm(float (*acc)[4], const float* A, int sar, int sac, const float* Bm, int sbr, int sbc, int nt,
+                                          int nstep) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = ks * 8;
+    float af[4];
+    af[0] = A[g * sar + (k0 + t) * sac];
+    af[1] = A[(g + 8) * sar + (k0 + t) * sac];
+    af[2] = A[g * sar + (k0 + t + 4) * sac];
+    af[3] = A[(g + 8) * sar + (k0 + t + 4) * sac];
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ah[i] = to_tf32(af[i]); if (EXACT) al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      if (i < nt) {
+        const float* bp = Bm + (i * nstep + g) * sbc;
+        const float b0 = bp[(k0 + t) * sbr], b1 = bp[(k0 + t + 4) * sbr];
+        uint32_t bh[2] = {to_tf32(b0), to_tf32(b1)};
+        if (EXACT) {
+          uint32_t bl[2] = {to_tf32(b0 - __uint_as_float(bh[0])), to_tf32(b1 - __uint_as_float(bh[1]))};
+          mma_tf32(acc[i], al, bh);
+          mma_tf32(acc[i], ah, bl);
+        }
+        mma_tf32(acc[i], ah, bh);
+      }
+    }
+  }
+}
+
+struct DecTrainParams {
+  const float* ca; float* gca;          // decoder_cross_attention parameter group / its gradients
+  const float* emb; const long long* genes; int G;
+  const float* Q;                       // [G][32] query-side table (qside_fwd_kernel)
+  const float* Kc; const float* Vc;     // [B][16][32]
+  const float* head_w; const float* head_b; float* g_head_w; float* g_head_b;
+  float* logits;                        // [B][G]   (forward)
+  const float* dlogit;                  // [B][G]   (backward)
+  float* dK; float* dV;                 // [B][16][32] accumulated (atomics)
+  float* dQ; float* dXsum;              // [G][32]   accumulated (atomics): gradient of Q, of the residual path
+  int B, cells_per_chunk; float eps;
+};
+constexpr int DT = 64, LD32 = 36, LD88 = 100;
+constexpr int DEC_SMEM_FLOATS = 8 * DT * LD32 + 3 * DT * LD88 + 2 * 512 + 2 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96;
+
+template <bool BWD, bool EXACT>
+__global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainParams p) {
+  extern __shared__ float4 dec_smem4[];
+  float* sm = reinterpret_cast<float*>(dec_smem4);
+  float* sQ = sm;                    float* sQin = sQ + DT * LD32;   float* sAO = sQin + DT * LD32;  float* sX1 = sAO + DT * LD32;
+  float* sN2 = sX1 + DT * LD32;      float* sX2 = sN2 + DT * LD32;   float* sD1 = sX2 + DT * LD32;   float* sD2 = sD1 + DT * LD32;
+  float* sU = sD2 + DT * LD32;       float* sV = sU + DT * LD88;     float* sH = sV + DT * LD88;
+  float* sK = sH + DT * LD88;        float* sVc = sK + 512;          float* sStat = sVc + 512;       float* sDl = sStat + 2 * DT;
+  float* sWp = sDl + DT;             float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;
+  float* sLn = sW3 + 32 * LD88;      float* sWh = sLn + 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int g0 = blockIdx.x * DT;
+  const int b_begin = blockIdx.y * p.cells_per_chunk, b_end = min(p.B, b_begin + p.cells_per_chunk);
+  const float scale = 0.35355339059327373f;   // 1 / sqrt(head_dim = 8)
+
+  // ---- weights of the block into shared memory (padded rows: conflict-free fragment reads) ----
+  for (int i = tid; i < 1024; i += 256) sWp[(i >> 5) * LD32 + (i & 31)] = p.ca[C_CPROJ + i];
+  for (int i = tid; i < H * 32; i += 256) { sW1[(i >> 5) * LD32 + (i & 31)] = p.ca[C_W1 + i]; sW2[(i >> 5) * LD32 + (i & 31)] = p.ca[C_W2 + i]; }
+  for (int i = tid; i < 32 * H; i += 256) sW3[(i / H) * LD88 + (i % H)] = p.ca[C_W3 + i];
+  if (tid < 64) sLn[tid] = p.ca[C_LN2W + tid];   // ln_2.weight | ln_2.bias
+  if (tid < 32) sWh[tid] = p.head_w[tid];
+  // ---- the tile's query-side rows (cell-invariant) ----
+  for (int i = tid; i < DT * 32; i += 256) {
+    const int tok = i >> 5, c = i & 31, gi = g0 + tok;
+    float qv = 0.f, ev = 0.f;
+    if (gi < p.G) { qv = p.Q[(size_t)gi * 32 + c]; ev = p.emb[(size_t)p.genes[gi] * 32 + c]; }
+    sQ[tok * LD32 + c] = qv;
+    sQin[tok * LD32 + c] = ev;
+  }
+  const float head_b = p.head_b[0];
+  // persistent gradient accumulators
+  float acc_w3[3][4] = {}, acc_w1[3][4] = {}, acc_w2[3][4] = {}, acc_wp[1][4] = {};
+  float acc_lnw[8] = {}, acc_lnb[8] = {}, acc_xs[8] = {}, acc_dq[8] = {}, acc_h = 0.f;
+  const int tok_a = tid >> 2, part = tid & 3;     // (token, head) of the attention phases / (token, 8-channel part) of the row phases
+  __syncthreads();
+
+  for (int b = b_begin; b < b_end; ++b) {
+    // (1) the cell's keys / values and, for the backward, d loss / d logit of the tile
+    for (int i = tid; i < 512; i += 256) { sK[i] = p.Kc[(size_t)b * 512 + i]; sVc[i] = p.Vc[(size_t)b * 512 + i]; }
+    if (BWD && tid < DT) sDl[tid] = (g0 + tid < p.G) ? p.dlogit[(size_t)b * p.G + g0 + tid] : 0.f;
+    __syncthreads();
+    // (2) cross attention of (token, head): 16 keys
+    {
+      const int h = part;
+      float q[8], s[16], mx = -1e30f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) q[d] = sQ[tok_a * LD32 + h * 8 + d] * scale;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) a += q[d] * sK[j * 32 + h * 8 + d];
+        s[j] = a;
+        mx = fmaxf(mx, a);
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { s[j] = __expf(s[j] - mx); l += s[j]; }
+      const float il = 1.f / l;
+      float o[8] = {};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float pj = s[j] * il;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) o[d] += pj * sVc[j * 32 + h * 8 + d];
+      }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) sAO[tok_a * LD32 + h * 8 + d] = o[d];
+    }
+    __syncthreads();
+    // (3) x1 = q_in + c_proj(ao)
+    {
+      float acc[2][4] = {};
+      warp_gemm<EXACT, 2, 4>(acc, sAO + mt * 16 * LD32, LD32, 1, sWp + (nh * 16) * LD32, 1, LD32, 2, 8);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int col = nh * 16 + i * 8 + 2 * t, r0 = mt * 16 + g;
+        sX1[r0 * LD32 + col] = sQin[r0 * LD32 + col] + acc[i][0];
+        sX1[r0 * LD32 + col + 1] = sQin[r0 * LD32 + col + 1] + acc[i][1];
+        sX1[(r0 + 8) * LD32 + col] = sQin[(r0 + 8) * LD32 + col] + acc[i][2];
+        sX1[(r0 + 8) * LD32 + col + 1] = sQin[(r0 + 8) * LD32 + col + 1] + acc[i][3];
+      }
+    }
+    __syncthreads();
+    // (4) LN2: four threads per token
+    {
+      float x[8], sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x[i] = sX1[tok_a * LD32 + part * 8 + i]; sum += x[i]; }
+      const float mean = quad_sum(sum) * (1.f / 32.f);
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x[i] -= mean; var += x[i] * x[i]; }
+      const float rstd = rsqrtf(quad_sum(var) * (1.f / 32.f) + p.eps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sN2[tok_a * LD32 + part * 8 + i] = x[i] * rstd * sLn[part * 8 + i] + sLn[32 + part * 8 + i];
+      if (part == 0) { sStat[tok_a * 2] = mean; sStat[tok_a * 2 + 1] = rstd; }
+    }
+    __syncthreads();
+    // (5) u = w1 n2, v = w2 n2, h = silu(u) v
+    {
+      const int nt0 = nh * 6, ntn = nh ? 5 : 6;
+      float au[6][4] = {}, av[6][4] = {};
+      warp_gemm<EXACT, 6, 4>(au, sN2 + mt * 16 * LD32, LD32, 1, sW1 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
+      warp_gemm<EXACT, 6, 4>(av, sN2 + mt * 16 * LD32, LD32, 1, sW2 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (i < ntn) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = mt * 16 + g + (e >> 1) * 8, col = (nt0 + i) * 8 + 2 * t + (e & 1);
+            const float u = au[i][e], v = av[i][e];
+            sH[r * LD88 + col] = u * sigmoidf_(u) * v;
+            if (BWD) { sU[r * LD88 + col] = u; sV[r * LD88 + col] = v; }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // (6) x2 = x1 + mlp.c_proj(h)
+    {
+      float acc[2][4] = {};
+      warp_gemm<EXACT, 2, 11>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nh * 16) * LD88, 1, LD88, 2, 8);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
+          sX2[r * LD32 + col] = sX1[r * LD32 + col] + acc[i][e];
+        }
+      }
+    }
+    __syncthreads();
+    if (!BWD) {
+      // (7) head logit
+      if (tid < DT && g0 + tid < p.G) {
+        float a = head_b;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a += sX2[tid * LD32 + c] * sWh[c];
+        p.logits[(size_t)b * p.G + g0 + tid] = a;
+      }
+      __syncthreads();
+      continue;
+    }
+    // (8) head gradients; dM = d x2 = dlogit * w_head
+    if (tid < 32) {
+      float a = 0.f;
+      for (int r = 0; r < DT; ++r) a += sDl[r] * sX2[r * LD32 + tid];
+      acc_h += a;
+    } else if (tid == 32) {
+      float a = 0.f;
+      for (int r = 0; r < DT; ++r) a += sDl[r];
+      acc_h += a;
+    }
+    {
+      const float dl = sDl[tok_a];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sD1[tok_a * LD32 + part * 8 + i] = dl * sWh[part * 8 + i];
+    }
+    __syncthreads();
+    // (9) d mlp.c_proj += dM^T h ;  dh = dM w3 -> du, dv (in place of u, v)
+    {
+      const int mw = warp & 1, nw0 = warp >> 1;
+      const int ntn = (nw0 + 8 < 11) ? 3 : 2;
+      warp_gemm<EXACT, 3, 8>(acc_w3, sD1 + mw * 16, 1, LD32, sH + nw0 * 8, LD88, 1, ntn, 32);
+      const int nt0 = nh * 6, n2 = nh ? 5 : 6;
+      float ah[6][4] = {};
+      warp_gemm<EXACT, 6, 4>(ah, sD1 + mt * 16 * LD32, LD32, 1, sW3 + nt0 * 8, LD88, 1, n2, 8);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (i < n2) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = mt * 16 + g + (e >> 1) * 8, col = (nt0 + i) * 8 + 2 * t + (e & 1);
+            const float u = sU[r * LD88 + col], v = sV[r * LD88 + col], sg = sigmoidf_(u), dh = ah[i][e];
+            sU[r * LD88 + col] = dh * v * sg * (1.f + u * (1.f - sg));
+            sV[r * LD88 + col] = dh * u * sg;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // (10) d w1 += du^T n2, d w2 += dv^T n2 ;  d n2 = du w1 + dv w2
+    {
+      const int nw = warp & 3, mw0 = warp >> 2;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        warp_gemm<EXACT, 1, 8>(&acc_w1[i], sU + (mw0 + 2 * i) * 16, 1, LD88, sN2 + nw * 8, LD32, 1, 1, 8);
+        warp_gemm<EXACT, 1, 8>(&acc_w2[i], sV + (mw0 + 2 * i) * 16, 1, LD88, sN2 + nw * 8, LD32, 1, 1, 8);
+      }
+      float acc[2][4] = {};
+      warp_gemm<EXACT, 2, 11>(acc, sU + mt * 16 * LD88, LD88, 1, sW1 + nh * 16, LD32, 1, 2, 8);
+      warp_gemm<EXACT, 2, 11>(acc, sV + mt * 16 * LD88, LD88, 1, sW2 + nh * 16, LD32, 1, 2, 8);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
+          sD2[r * LD32 + col] = acc[i][e];
+        }
+      }
+    }
+    __syncthreads();
+    // (11) LN2 backward + residual: d x1
+    {
+      const float mean = sStat[tok_a * 2], rstd = sStat[tok_a * 2 + 1], dl = sDl[tok_a];
+      float xh[8], gy[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = part * 8 + i;
+        xh[i] = (sX1[tok_a * LD32 + c] - mean) * rstd;
+        const float dn = sD2[tok_a * LD32 + c];
+        acc_lnw[i] += dn * xh[i];
+        acc_lnb[i] += dn;
+        gy[i] = dn * sLn[c];
+        s1 += gy[i];
+        s2 += gy[i] * xh[i];
+      }
+      const float m1 = quad_sum(s1) * (1.f / 32.f), m2 = quad_sum(s2) * (1.f / 32.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = part * 8 + i;
+        const float dx = rstd * (gy[i] - m1 - xh[i] * m2) + dl * sWh[c];
+        acc_xs[i] += dx;
+        sD1[tok_a * LD32 + c] = dx;
+      }
+    }
+    __syncthreads();
+    // (12) d c_proj += dx1^T ao ;  d ao = dx1 c_proj
+    {
+      warp_gemm<EXACT, 1, 8>(acc_wp, sD1 + (warp & 1) * 16, 1, LD32, sAO + (warp >> 1) * 8, LD32, 1, 1, 8);
+      float acc[2][4] = {};
+      warp_gemm<EXACT, 2, 4>(acc, sD1 + mt * 16 * LD32, LD32, 1, sWp + nh * 16, LD32, 1, 2, 8);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
+          sD2[r * LD32 + col] = acc[i][e];
+        }
+      }
+    }
+    __syncthreads();
+    // (13) attention backward of (token, head); dS and P tiles for the key / value gradients (aliasing the dead u, v tiles)
+    float* tDS = sU;   // [DT][68]
+    float* tP = sV;    // [DT][68]
+    {
+      const int h = part;
+      float q[8], s[16], mx = -1e30f, dao[8];
+#pragma unroll
+      for (int d = 0; d < 8; ++d) { q[d] = sQ[tok_a * LD32 + h * 8 + d] * scale; dao[d] = sD2[tok_a * LD32 + h * 8 + d]; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) a += q[d] * sK[j * 32 + h * 8 + d];
+        s[j] = a;
+        mx = fmaxf(mx, a);
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { s[j] = __expf(s[j] - mx); l += s[j]; }
+      const float il = 1.f / l;
+      float dp[16], D = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        s[j] *= il;
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) a += dao[d] * sVc[j * 32 + h * 8 + d];
+        dp[j] = a;
+        D += s[j] * a;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float ds = s[j] * (dp[j] - D) * scale;
+        tDS[tok_a * 68 + h * 16 + j] = ds;
+        tP[tok_a * 68 + h * 16 + j] = s[j];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc_dq[d] += ds * sK[j * 32 + h * 8 + d];
+      }
+    }
+    __syncthreads();
+    // (14) dK[j][c] = sum_tok dS[tok][h(c)][j] Q[tok][c] ;  dV[j][c] = sum_tok P[tok][h(c)][j] dAO[tok][c]
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int idx = tid + rep * 256, j = idx >> 5, c = idx & 31, h = c >> 3;
+      float ak = 0.f, av = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < DT; ++r) {
+        ak += tDS[r * 68 + h * 16 + j] * sQ[r * LD32 + c];
+        av += tP[r * 68 + h * 16 + j] * sD2[r * LD32 + c];
+      }
+      atomicAdd(p.dK + (size_t)b * 512 + idx, ak);
+      atomicAdd(p.dV + (size_t)b * 512 + idx, av);
+    }
+    __syncthreads();
+  }
+
+  if (!BWD) return;
+  // ---- flush the gradient accumulators ----
+  {
+    const int mw = warp & 1, nw0 = warp >> 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int ntile = nw0 + 4 * i;
+      if (ntile < 11) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int o = mw * 16 + g + (e >> 1) * 8, j = ntile * 8 + 2 * t + (e & 1);
+          atomicAdd(p.gca + C_W3 + o * H + j, acc_w3[i][e]);
+        }
+      }
+    }
+  }
+  {
+    const int nw = warp & 3, mw0 = warp >> 2;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = (mw0 + 2 * i) * 16 + g + (e >> 1) * 8, c = nw * 8 + 2 * t + (e & 1);
+        if (j < H) { atomicAdd(p.gca + C_W1 + j * 32 + c, acc_w1[i][e]); atomicAdd(p.gca + C_W2 + j * 32 + c, acc_w2[i][e]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int o = (warp & 1) * 16 + g + (e >> 1) * 8, c = (warp >> 1) * 8 + 2 * t + (e & 1);
+    atomicAdd(p.gca + C_CPROJ + o * 32 + c, acc_wp[0][e]);
+  }
+  if (tid < 32) atomicAdd(p.g_head_w + tid, acc_h);
+  else if (tid == 32) atomicAdd(p.g_head_b, acc_h);
+  {
+    const int gi = g0 + tok_a;
+    if (gi < p.G) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(p.dQ + (size_t)gi * 32 + part * 8 + i, acc_dq[i]);        // part = head in the attention phases
+        atomicAdd(p.dXsum + (size_t)gi * 32 + part * 8 + i, acc_xs[i]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sD1[tok_a * LD32 + part * 8 + i] = acc_lnw[i]; sD2[tok_a * LD32 + part * 8 + i] = acc_lnb[i]; }
+  __syncthreads();
+  if (tid < 64) {
+    const int c = tid & 31;
+    const float* tsrc = tid < 32 ? sD1 : sD2;
+    float a = 0.f;
+    for (int r = 0; r < DT; ++r) a += tsrc[r * LD32 + c];
+    atomicAdd(p.gca + (tid < 32 ? C_LN2W : C_LN2B) + c, a);
+  }
+}
+
+}  // namespace vtr
