@@ -875,8 +875,68 @@ struct DecTrainParams {
   float* dQ; float* dXsum;              // [G][32]   accumulated (atomics): gradient of Q, of the residual path
   int B, cells_per_chunk; float eps;
 };
-constexpr int DT = 64, LD32 = 36, LD88 = 100;
-constexpr int DEC_SMEM_FLOATS = 8 * DT * LD32 + 3 * DT * LD88 + 2 * 512 + 2 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96;
+constexpr int DT = 64, LD32 = 36, LD88 = 100, LDK = 36;
+constexpr int DEC_SMEM_FLOATS = 8 * DT * LD32 + 3 * DT * LD88 + 2 * 16 * LDK + 2 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96 + 96;
+
+// one m16n8k8 product on fp32 fragments (TF32, or 3 x TF32 when EXACT)
+template <bool EXACT>
+__device__ __forceinline__ void mma_f(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+  uint32_t ah[4], bh[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ah[i] = to_tf32(a[i]);
+  bh[0] = to_tf32(b[0]); bh[1] = to_tf32(b[1]);
+  if (EXACT) {
+    uint32_t al[4], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) al[i] = to_tf32(a[i] - __uint_as_float(ah[i]));
+    bl[0] = to_tf32(b[0] - __uint_as_float(bh[0])); bl[1] = to_tf32(b[1] - __uint_as_float(bh[1]));
+    mma_tf32(c, al, bh);
+    mma_tf32(c, ah, bl);
+  }
+  mma_tf32(c, ah, bh);
+}
+
+// Cross attention of one head for the 16 tokens of a warp's row tile, on mma.sync: S = Q K^T (two 8-key column tiles) -> softmax
+// over the 16 keys on the accumulator fragments (a row lives in one quad) -> p[n][e] = P[row g (+8 for e >= 2)][key 8 n + 2 t + (e & 1)].
+template <bool EXACT>
+__device__ __forceinline__ void attn_probs(const float* sQrow, const float* sK, int h, float scale, float (&p)[2][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float a[4] = {sQrow[g * LD32 + h * 8 + t], sQrow[(g + 8) * LD32 + h * 8 + t], sQrow[g * LD32 + h * 8 + t + 4], sQrow[(g + 8) * LD32 + h * 8 + t + 4]};
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    const float b[2] = {sK[(8 * n + g) * LDK + h * 8 + t], sK[(8 * n + g) * LDK + h * 8 + t + 4]};
+    p[n][0] = p[n][1] = p[n][2] = p[n][3] = 0.f;
+    mma_f<EXACT>(p[n], a, b);
+  }
+  float m0 = fmaxf(fmaxf(p[0][0], p[0][1]), fmaxf(p[1][0], p[1][1])), m1 = fmaxf(fmaxf(p[0][2], p[0][3]), fmaxf(p[1][2], p[1][3]));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    p[n][0] = __expf((p[n][0] - m0) * scale); p[n][1] = __expf((p[n][1] - m0) * scale);
+    p[n][2] = __expf((p[n][2] - m1) * scale); p[n][3] = __expf((p[n][3] - m1) * scale);
+    l0 += p[n][0] + p[n][1];
+    l1 += p[n][2] + p[n][3];
+  }
+  l0 = 1.f / quad_sum(l0); l1 = 1.f / quad_sum(l1);
+#pragma unroll
+  for (int n = 0; n < 2; ++n) { p[n][0] *= l0; p[n][1] *= l0; p[n][2] *= l1; p[n][3] *= l1; }
+}
+// out[16 x 8] = W[16 x 16 keys] * X[16 keys][h*8 .. h*8+7], W given as accumulator fragments of attn_probs' layout: the contraction
+// index is visited in the permuted order (k = t <-> key 8 ks + 2 t, k = t + 4 <-> key 8 ks + 2 t + 1), so the fragments feed the
+// A operand directly
+template <bool EXACT>
+__device__ __forceinline__ void attn_apply(const float (&w)[2][4], const float* sX, int h, float (&out)[4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  out[0] = out[1] = out[2] = out[3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const float a[4] = {w[ks][0], w[ks][2], w[ks][1], w[ks][3]};
+    const float b[2] = {sX[(8 * ks + 2 * t) * LDK + h * 8 + g], sX[(8 * ks + 2 * t + 1) * LDK + h * 8 + g]};
+    mma_f<EXACT>(out, a, b);
+  }
+}
 
 template <bool BWD, bool EXACT>
 __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainParams p) {
@@ -885,9 +945,9 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
   float* sQ = sm;                    float* sQin = sQ + DT * LD32;   float* sAO = sQin + DT * LD32;  float* sX1 = sAO + DT * LD32;
   float* sN2 = sX1 + DT * LD32;      float* sX2 = sN2 + DT * LD32;   float* sD1 = sX2 + DT * LD32;   float* sD2 = sD1 + DT * LD32;
   float* sU = sD2 + DT * LD32;       float* sV = sU + DT * LD88;     float* sH = sV + DT * LD88;
-  float* sK = sH + DT * LD88;        float* sVc = sK + 512;          float* sStat = sVc + 512;       float* sDl = sStat + 2 * DT;
+  float* sK = sH + DT * LD88;        float* sVc = sK + 16 * LDK;     float* sStat = sVc + 16 * LDK;  float* sDl = sStat + 2 * DT;
   float* sWp = sDl + DT;             float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;
-  float* sLn = sW3 + 32 * LD88;      float* sWh = sLn + 64;
+  float* sLn = sW3 + 32 * LD88;      float* sWh = sLn + 64;          float* sR = sLn + 96;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int mt = warp & 3, nh = warp >> 2;
   const int g0 = blockIdx.x * DT;
@@ -909,44 +969,37 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
     sQin[tok * LD32 + c] = ev;
   }
   const float head_b = p.head_b[0];
+  __syncthreads();
+  // The head is linear in x2 = x1 + w3 h, so its backward never needs the mlp.c_proj GEMMs: with r = w3^T w_head,
+  // dh[tok] = dlogit[tok] r, d w3 = w_head (x) sum_tok dlogit h, d w_head = sum_tok dlogit x1 + w3 sum_tok dlogit h.
+  if (BWD && tid < H) {
+    float a = 0.f;
+    for (int o = 0; o < 32; ++o) a += sWh[o] * sW3[o * LD88 + tid];
+    sR[tid] = a;
+  }
   // persistent gradient accumulators
-  float acc_w3[3][4] = {}, acc_w1[3][4] = {}, acc_w2[3][4] = {}, acc_wp[1][4] = {};
-  float acc_lnw[8] = {}, acc_lnb[8] = {}, acc_xs[8] = {}, acc_dq[8] = {}, acc_h = 0.f;
-  const int tok_a = tid >> 2, part = tid & 3;     // (token, head) of the attention phases / (token, 8-channel part) of the row phases
+  float acc_w1[3][4] = {}, acc_w2[3][4] = {}, acc_wp[1][4] = {};
+  float acc_lnw[8] = {}, acc_lnb[8] = {}, acc_xs[8] = {}, acc_dq[2][4] = {}, acc_s = 0.f;
+  const int tok_a = tid >> 2, part = tid & 3;     // (token, 8-channel part) of the row phases
   __syncthreads();
 
   for (int b = b_begin; b < b_end; ++b) {
     // (1) the cell's keys / values and, for the backward, d loss / d logit of the tile
-    for (int i = tid; i < 512; i += 256) { sK[i] = p.Kc[(size_t)b * 512 + i]; sVc[i] = p.Vc[(size_t)b * 512 + i]; }
+    for (int i = tid; i < 512; i += 256) {
+      sK[(i >> 5) * LDK + (i & 31)] = p.Kc[(size_t)b * 512 + i];
+      sVc[(i >> 5) * LDK + (i & 31)] = p.Vc[(size_t)b * 512 + i];
+    }
     if (BWD && tid < DT) sDl[tid] = (g0 + tid < p.G) ? p.dlogit[(size_t)b * p.G + g0 + tid] : 0.f;
     __syncthreads();
-    // (2) cross attention of (token, head): 16 keys
-    {
-      const int h = part;
-      float q[8], s[16], mx = -1e30f;
+    // (2) cross attention over the 16 latent keys: warp (row tile, head pair)
 #pragma unroll
-      for (int d = 0; d < 8; ++d) q[d] = sQ[tok_a * LD32 + h * 8 + d] * scale;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) a += q[d] * sK[j * 32 + h * 8 + d];
-        s[j] = a;
-        mx = fmaxf(mx, a);
-      }
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { s[j] = __expf(s[j] - mx); l += s[j]; }
-      const float il = 1.f / l;
-      float o[8] = {};
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float pj = s[j] * il;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) o[d] += pj * sVc[j * 32 + h * 8 + d];
-      }
-#pragma unroll
-      for (int d = 0; d < 8; ++d) sAO[tok_a * LD32 + h * 8 + d] = o[d];
+    for (int hh = 0; hh < 2; ++hh) {
+      const int h = nh * 2 + hh;
+      float pr[2][4], o[4];
+      attn_probs<EXACT>(sQ + mt * 16 * LD32, sK, h, scale, pr);
+      attn_apply<EXACT>(pr, sVc, h, o);
+      float* dst = sAO + (mt * 16 + g) * LD32 + h * 8 + 2 * t;
+      dst[0] = o[0]; dst[1] = o[1]; dst[8 * LD32] = o[2]; dst[8 * LD32 + 1] = o[3];
     }
     __syncthreads();
     // (3) x1 = q_in + c_proj(ao)
@@ -955,11 +1008,11 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
       warp_gemm<EXACT, 2, 4>(acc, sAO + mt * 16 * LD32, LD32, 1, sWp + (nh * 16) * LD32, 1, LD32, 2, 8);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int col = nh * 16 + i * 8 + 2 * t, r0 = mt * 16 + g;
-        sX1[r0 * LD32 + col] = sQin[r0 * LD32 + col] + acc[i][0];
-        sX1[r0 * LD32 + col + 1] = sQin[r0 * LD32 + col + 1] + acc[i][1];
-        sX1[(r0 + 8) * LD32 + col] = sQin[(r0 + 8) * LD32 + col] + acc[i][2];
-        sX1[(r0 + 8) * LD32 + col + 1] = sQin[(r0 + 8) * LD32 + col + 1] + acc[i][3];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
+          sX1[r * LD32 + col] = sQin[r * LD32 + col] + acc[i][e];
+        }
       }
     }
     __syncthreads();
@@ -978,41 +1031,46 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
       if (part == 0) { sStat[tok_a * 2] = mean; sStat[tok_a * 2 + 1] = rstd; }
     }
     __syncthreads();
-    // (5) u = w1 n2, v = w2 n2, h = silu(u) v
+    // (5) u = w1 n2, v = w2 n2, h = silu(u) v; backward: du, dv right away (dh = dlogit r)
     {
       const int nt0 = nh * 6, ntn = nh ? 5 : 6;
       float au[6][4] = {}, av[6][4] = {};
       warp_gemm<EXACT, 6, 4>(au, sN2 + mt * 16 * LD32, LD32, 1, sW1 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
       warp_gemm<EXACT, 6, 4>(av, sN2 + mt * 16 * LD32, LD32, 1, sW2 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
+      const float dl0 = BWD ? sDl[mt * 16 + g] : 0.f, dl1 = BWD ? sDl[mt * 16 + g + 8] : 0.f;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         if (i < ntn) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int r = mt * 16 + g + (e >> 1) * 8, col = (nt0 + i) * 8 + 2 * t + (e & 1);
-            const float u = au[i][e], v = av[i][e];
-            sH[r * LD88 + col] = u * sigmoidf_(u) * v;
-            if (BWD) { sU[r * LD88 + col] = u; sV[r * LD88 + col] = v; }
+            const float u = au[i][e], v = av[i][e], sg = sigmoidf_(u);
+            sH[r * LD88 + col] = u * sg * v;
+            if (BWD) {
+              const float dh = ((e >> 1) ? dl1 : dl0) * sR[col];
+              sU[r * LD88 + col] = dh * v * sg * (1.f + u * (1.f - sg));
+              sV[r * LD88 + col] = dh * u * sg;
+            }
           }
         }
       }
     }
     __syncthreads();
-    // (6) x2 = x1 + mlp.c_proj(h)
-    {
-      float acc[2][4] = {};
-      warp_gemm<EXACT, 2, 11>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nh * 16) * LD88, 1, LD88, 2, 8);
+    if (!BWD) {
+      // (6) x2 = x1 + mlp.c_proj(h)
+      {
+        float acc[2][4] = {};
+        warp_gemm<EXACT, 2, 11>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nh * 16) * LD88, 1, LD88, 2, 8);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 2; ++i) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
-          sX2[r * LD32 + col] = sX1[r * LD32 + col] + acc[i][e];
+          for (int e = 0; e < 4; ++e) {
+            const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
+            sX2[r * LD32 + col] = sX1[r * LD32 + col] + acc[i][e];
+          }
         }
       }
-    }
-    __syncthreads();
-    if (!BWD) {
+      __syncthreads();
       // (7) head logit
       if (tid < DT && g0 + tid < p.G) {
         float a = head_b;
@@ -1023,44 +1081,22 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
       __syncthreads();
       continue;
     }
-    // (8) head gradients; dM = d x2 = dlogit * w_head
-    if (tid < 32) {
+    // (8) sums for the head / mlp.c_proj gradients (threads 0..87: sum_tok dlogit h; 96..127: sum_tok dlogit x1; 128: sum_tok dlogit)
+    if (tid < H) {
       float a = 0.f;
-      for (int r = 0; r < DT; ++r) a += sDl[r] * sX2[r * LD32 + tid];
-      acc_h += a;
-    } else if (tid == 32) {
+#pragma unroll 8
+      for (int r = 0; r < DT; ++r) a += sDl[r] * sH[r * LD88 + tid];
+      acc_s += a;
+    } else if (tid >= 96 && tid < 128) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < DT; ++r) a += sDl[r] * sX1[r * LD32 + tid - 96];
+      acc_s += a;
+    } else if (tid == 128) {
       float a = 0.f;
       for (int r = 0; r < DT; ++r) a += sDl[r];
-      acc_h += a;
+      acc_s += a;
     }
-    {
-      const float dl = sDl[tok_a];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sD1[tok_a * LD32 + part * 8 + i] = dl * sWh[part * 8 + i];
-    }
-    __syncthreads();
-    // (9) d mlp.c_proj += dM^T h ;  dh = dM w3 -> du, dv (in place of u, v)
-    {
-      const int mw = warp & 1, nw0 = warp >> 1;
-      const int ntn = (nw0 + 8 < 11) ? 3 : 2;
-      warp_gemm<EXACT, 3, 8>(acc_w3, sD1 + mw * 16, 1, LD32, sH + nw0 * 8, LD88, 1, ntn, 32);
-      const int nt0 = nh * 6, n2 = nh ? 5 : 6;
-      float ah[6][4] = {};
-      warp_gemm<EXACT, 6, 4>(ah, sD1 + mt * 16 * LD32, LD32, 1, sW3 + nt0 * 8, LD88, 1, n2, 8);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        if (i < n2) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = mt * 16 + g + (e >> 1) * 8, col = (nt0 + i) * 8 + 2 * t + (e & 1);
-            const float u = sU[r * LD88 + col], v = sV[r * LD88 + col], sg = sigmoidf_(u), dh = ah[i][e];
-            sU[r * LD88 + col] = dh * v * sg * (1.f + u * (1.f - sg));
-            sV[r * LD88 + col] = dh * u * sg;
-          }
-        }
-      }
-    }
-    __syncthreads();
     // (10) d w1 += du^T n2, d w2 += dv^T n2 ;  d n2 = du w1 + dv w2
     {
       const int nw = warp & 3, mw0 = warp >> 2;
@@ -1122,78 +1158,54 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
       }
     }
     __syncthreads();
-    // (13) attention backward of (token, head); dS and P tiles for the key / value gradients (aliasing the dead u, v tiles)
+    // (13) attention backward, warp (row tile, head pair); dS and P tiles for the key / value gradients alias the dead du, dv tiles
     float* tDS = sU;   // [DT][68]
     float* tP = sV;    // [DT][68]
-    {
-      const int h = part;
-      float q[8], s[16], mx = -1e30f, dao[8];
 #pragma unroll
-      for (int d = 0; d < 8; ++d) { q[d] = sQ[tok_a * LD32 + h * 8 + d] * scale; dao[d] = sD2[tok_a * LD32 + h * 8 + d]; }
+    for (int hh = 0; hh < 2; ++hh) {
+      const int h = nh * 2 + hh;
+      float pr[2][4], dp[2][4];
+      attn_probs<EXACT>(sQ + mt * 16 * LD32, sK, h, scale, pr);
+      {
+        const float* dr = sD2 + mt * 16 * LD32;
+        const float a[4] = {dr[g * LD32 + h * 8 + t], dr[(g + 8) * LD32 + h * 8 + t], dr[g * LD32 + h * 8 + t + 4], dr[(g + 8) * LD32 + h * 8 + t + 4]};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) a += q[d] * sK[j * 32 + h * 8 + d];
-        s[j] = a;
-        mx = fmaxf(mx, a);
+        for (int n = 0; n < 2; ++n) {
+          const float bb[2] = {sVc[(8 * n + g) * LDK + h * 8 + t], sVc[(8 * n + g) * LDK + h * 8 + t + 4]};
+          dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+          mma_f<EXACT>(dp[n], a, bb);
+        }
       }
-      float l = 0.f;
+      const float D0 = quad_sum(pr[0][0] * dp[0][0] + pr[0][1] * dp[0][1] + pr[1][0] * dp[1][0] + pr[1][1] * dp[1][1]);
+      const float D1 = quad_sum(pr[0][2] * dp[0][2] + pr[0][3] * dp[0][3] + pr[1][2] * dp[1][2] + pr[1][3] * dp[1][3]);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { s[j] = __expf(s[j] - mx); l += s[j]; }
-      const float il = 1.f / l;
-      float dp[16], D = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        s[j] *= il;
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) a += dao[d] * sVc[j * 32 + h * 8 + d];
-        dp[j] = a;
-        D += s[j] * a;
+      for (int n = 0; n < 2; ++n) {
+        dp[n][0] = pr[n][0] * (dp[n][0] - D0) * scale; dp[n][1] = pr[n][1] * (dp[n][1] - D0) * scale;
+        dp[n][2] = pr[n][2] * (dp[n][2] - D1) * scale; dp[n][3] = pr[n][3] * (dp[n][3] - D1) * scale;
+        const int r0 = mt * 16 + g, col = h * 16 + 8 * n + 2 * t;
+        tDS[r0 * 68 + col] = dp[n][0]; tDS[r0 * 68 + col + 1] = dp[n][1]; tDS[(r0 + 8) * 68 + col] = dp[n][2]; tDS[(r0 + 8) * 68 + col + 1] = dp[n][3];
+        tP[r0 * 68 + col] = pr[n][0]; tP[r0 * 68 + col + 1] = pr[n][1]; tP[(r0 + 8) * 68 + col] = pr[n][2]; tP[(r0 + 8) * 68 + col + 1] = pr[n][3];
       }
+      float dq[4];
+      attn_apply<EXACT>(dp, sK, h, dq);      // dQ[tok][h*8 + d] = sum_keys dS K
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float ds = s[j] * (dp[j] - D) * scale;
-        tDS[tok_a * 68 + h * 16 + j] = ds;
-        tP[tok_a * 68 + h * 16 + j] = s[j];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) acc_dq[d] += ds * sK[j * 32 + h * 8 + d];
-      }
+      for (int e = 0; e < 4; ++e) acc_dq[hh][e] += dq[e];
     }
     __syncthreads();
-    // (14) dK[j][c] = sum_tok dS[tok][h(c)][j] Q[tok][c] ;  dV[j][c] = sum_tok P[tok][h(c)][j] dAO[tok][c]
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-      const int idx = tid + rep * 256, j = idx >> 5, c = idx & 31, h = c >> 3;
-      float ak = 0.f, av = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < DT; ++r) {
-        ak += tDS[r * 68 + h * 16 + j] * sQ[r * LD32 + c];
-        av += tP[r * 68 + h * 16 + j] * sD2[r * LD32 + c];
-      }
-      atomicAdd(p.dK + (size_t)b * 512 + idx, ak);
-      atomicAdd(p.dV + (size_t)b * 512 + idx, av);
+    // (14) dK[key][c] = sum_tok dS[tok][h(c)][key] Q[tok][c] ;  dV[key][c] = sum_tok P[tok][h(c)][key] dAO[tok][c]: warp (head, K | V)
+    {
+      const int h = warp & 3, which = warp >> 2;
+      float acc[1][4] = {};
+      warp_gemm<EXACT, 1, 8>(acc, (which ? tP : tDS) + h * 16, 1, 68, (which ? sD2 : sQ) + h * 8, LD32, 1, 1, 8);
+      float* dst = (which ? p.dV : p.dK) + (size_t)b * 512 + h * 8 + 2 * t;
+      atomicAdd(dst + g * 32, acc[0][0]); atomicAdd(dst + g * 32 + 1, acc[0][1]);
+      atomicAdd(dst + (g + 8) * 32, acc[0][2]); atomicAdd(dst + (g + 8) * 32 + 1, acc[0][3]);
     }
     __syncthreads();
   }
 
   if (!BWD) return;
   // ---- flush the gradient accumulators ----
-  {
-    const int mw = warp & 1, nw0 = warp >> 1;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int ntile = nw0 + 4 * i;
-      if (ntile < 11) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int o = mw * 16 + g + (e >> 1) * 8, j = ntile * 8 + 2 * t + (e & 1);
-          atomicAdd(p.gca + C_W3 + o * H + j, acc_w3[i][e]);
-        }
-      }
-    }
-  }
   {
     const int nw = warp & 3, mw0 = warp >> 2;
 #pragma unroll
@@ -1210,28 +1222,43 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
     const int o = (warp & 1) * 16 + g + (e >> 1) * 8, c = (warp >> 1) * 8 + 2 * t + (e & 1);
     atomicAdd(p.gca + C_CPROJ + o * 32 + c, acc_wp[0][e]);
   }
-  if (tid < 32) atomicAdd(p.g_head_w + tid, acc_h);
-  else if (tid == 32) atomicAdd(p.g_head_b, acc_h);
   {
+    const int gi0 = g0 + mt * 16 + g;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gi = gi0 + (e >> 1) * 8;
+        if (gi < p.G) atomicAdd(p.dQ + (size_t)gi * 32 + (nh * 2 + hh) * 8 + 2 * t + (e & 1), acc_dq[hh][e]);
+      }
+    }
     const int gi = g0 + tok_a;
     if (gi < p.G) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(p.dQ + (size_t)gi * 32 + part * 8 + i, acc_dq[i]);        // part = head in the attention phases
-        atomicAdd(p.dXsum + (size_t)gi * 32 + part * 8 + i, acc_xs[i]);
-      }
+      for (int i = 0; i < 8; ++i) atomicAdd(p.dXsum + (size_t)gi * 32 + part * 8 + i, acc_xs[i]);
     }
   }
   __syncthreads();
+  // sum_tok dlogit h -> d mlp.c_proj = w_head (x) s, and its share of d w_head
+  if (tid < H) sStat[tid] = acc_s;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sD1[tok_a * LD32 + part * 8 + i] = acc_lnw[i]; sD2[tok_a * LD32 + part * 8 + i] = acc_lnb[i]; }
   __syncthreads();
-  if (tid < 64) {
+  if (tid < H) {
+    for (int o = 0; o < 32; ++o) atomicAdd(p.gca + C_W3 + o * H + tid, sWh[o] * acc_s);
+  } else if (tid >= 96 && tid < 128) {
+    const int c = tid - 96;
+    float a = acc_s;
+    for (int j = 0; j < H; ++j) a += sW3[c * LD88 + j] * sStat[j];
+    atomicAdd(p.g_head_w + c, a);
+  } else if (tid == 128) {
+    atomicAdd(p.g_head_b, acc_s);
+  } else if (tid >= 160 && tid < 224) {
     const int c = tid & 31;
-    const float* tsrc = tid < 32 ? sD1 : sD2;
+    const float* tsrc = tid < 192 ? sD1 : sD2;
     float a = 0.f;
     for (int r = 0; r < DT; ++r) a += tsrc[r * LD32 + c];
-    atomicAdd(p.gca + (tid < 32 ? C_LN2W : C_LN2B) + c, a);
+    atomicAdd(p.gca + (tid < 192 ? C_LN2W : C_LN2B) + c, a);
   }
 }
 
