@@ -829,6 +829,11 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// Operand convention of the tile kernel: with EXACT every product is 3 x TF32 on raw fp32 operands (hi / lo split at load time); without,
+// every mma operand is rounded to TF32 ONCE, where it is stored to shared memory (rt<EXACT>), and the fragment loads feed the bits through.
+template <bool EXACT>
+__device__ __forceinline__ float rt(float x) { return EXACT ? x : __uint_as_float(to_tf32(x)); }
+
 // acc[i] (16 x 8 tile i) += A[16 x 8 KS] * B[8 KS x 8] for `nt` column tiles; element strides: A(r, k) = A[r sar + k sac],
 // B(k, n) = Bm[k sbr + n sbc]; column tile i starts at n = i * nstep.  EXACT: 3 x TF32 (hi / lo split), fp32-grade products.
 template <bool EXACT, int NT, int KS>
@@ -845,13 +850,13 @@ __device__ __forceinline__ void warp_gemm(float (*acc)[4], const float* A, int s
     af[3] = A[(g + 8) * sar + (k0 + t + 4) * sac];
     uint32_t ah[4], al[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { ah[i] = to_tf32(af[i]); if (EXACT) al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
+    for (int i = 0; i < 4; ++i) { ah[i] = EXACT ? to_tf32(af[i]) : __float_as_uint(af[i]); if (EXACT) al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       if (i < nt) {
         const float* bp = Bm + (i * nstep + g) * sbc;
         const float b0 = bp[(k0 + t) * sbr], b1 = bp[(k0 + t + 4) * sbr];
-        uint32_t bh[2] = {to_tf32(b0), to_tf32(b1)};
+        uint32_t bh[2] = {EXACT ? to_tf32(b0) : __float_as_uint(b0), EXACT ? to_tf32(b1) : __float_as_uint(b1)};
         if (EXACT) {
           uint32_t bl[2] = {to_tf32(b0 - __uint_as_float(bh[0])), to_tf32(b1 - __uint_as_float(bh[1]))};
           mma_tf32(acc[i], al, bh);
@@ -875,16 +880,17 @@ struct DecTrainParams {
   float* dQ; float* dXsum;              // [G][32]   accumulated (atomics): gradient of Q, of the residual path
   int B, cells_per_chunk; float eps;
 };
-constexpr int DT = 64, LD32 = 36, LD88 = 100, LDK = 36;
-constexpr int DEC_SMEM_FLOATS = 8 * DT * LD32 + 3 * DT * LD88 + 2 * 16 * LDK + 2 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96 + 96;
+constexpr int DT = 32, LD32 = 36, LD88 = 100, LDK = 36;
+// 6 32-wide tiles + du / dv (h in the forward-only kernel) + keys / values + small vectors + the block's weights: 103 KB, 2 CTAs per SM
+constexpr int DEC_SMEM_FLOATS = 6 * DT * LD32 + 2 * DT * LD88 + 2 * 16 * LDK + 2 * DT + DT + 4 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96 + 96;
 
 // one m16n8k8 product on fp32 fragments (TF32, or 3 x TF32 when EXACT)
 template <bool EXACT>
 __device__ __forceinline__ void mma_f(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
   uint32_t ah[4], bh[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) ah[i] = to_tf32(a[i]);
-  bh[0] = to_tf32(b[0]); bh[1] = to_tf32(b[1]);
+  for (int i = 0; i < 4; ++i) ah[i] = EXACT ? to_tf32(a[i]) : __float_as_uint(a[i]);
+  bh[0] = EXACT ? to_tf32(b[0]) : __float_as_uint(b[0]); bh[1] = EXACT ? to_tf32(b[1]) : __float_as_uint(b[1]);
   if (EXACT) {
     uint32_t al[4], bl[2];
 #pragma unroll
@@ -932,41 +938,50 @@ __device__ __forceinline__ void attn_apply(const float (&w)[2][4], const float* 
   out[0] = out[1] = out[2] = out[3] = 0.f;
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
-    const float a[4] = {w[ks][0], w[ks][2], w[ks][1], w[ks][3]};
+    const float a[4] = {rt<EXACT>(w[ks][0]), rt<EXACT>(w[ks][2]), rt<EXACT>(w[ks][1]), rt<EXACT>(w[ks][3])};
     const float b[2] = {sX[(8 * ks + 2 * t) * LDK + h * 8 + g], sX[(8 * ks + 2 * t + 1) * LDK + h * 8 + g]};
     mma_f<EXACT>(out, a, b);
   }
 }
 
+__device__ __forceinline__ float oct_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+// One CTA = a tile of 32 gene tokens; it walks the cells of its chunk.  8 warps = (row tile of 16 tokens) x (quarter of the N dimension /
+// attention head); two CTAs are resident per SM (103 KB of shared memory, <= 128 registers), so that the barrier-separated phases of one
+// tile overlap with those of the other.
 template <bool BWD, bool EXACT>
-__global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainParams p) {
+__global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainParams p) {
   extern __shared__ float4 dec_smem4[];
   float* sm = reinterpret_cast<float*>(dec_smem4);
-  float* sQ = sm;                    float* sQin = sQ + DT * LD32;   float* sAO = sQin + DT * LD32;  float* sX1 = sAO + DT * LD32;
-  float* sN2 = sX1 + DT * LD32;      float* sX2 = sN2 + DT * LD32;   float* sD1 = sX2 + DT * LD32;   float* sD2 = sD1 + DT * LD32;
-  float* sU = sD2 + DT * LD32;       float* sV = sU + DT * LD88;     float* sH = sV + DT * LD88;
-  float* sK = sH + DT * LD88;        float* sVc = sK + 16 * LDK;     float* sStat = sVc + 16 * LDK;  float* sDl = sStat + 2 * DT;
-  float* sWp = sDl + DT;             float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;
+  float* sQ = sm;                    float* sAO = sQ + DT * LD32;    float* sX1 = sAO + DT * LD32;   float* sN2 = sX1 + DT * LD32;
+  float* sD1 = sN2 + DT * LD32;      float* sD2 = sD1 + DT * LD32;   float* sU = sD2 + DT * LD32;    float* sV = sU + DT * LD88;
+  float* sH = sU;                    // forward-only kernel: h lives where the backward keeps du
+  float* sK = sV + DT * LD88;        float* sVc = sK + 16 * LDK;     float* sStat = sVc + 16 * LDK;  float* sDl = sStat + 2 * DT;
+  float* sLog = sDl + DT;            int* sGid = reinterpret_cast<int*>(sLog + 4 * DT);
+  float* sWp = sLog + 5 * DT;        float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;
   float* sLn = sW3 + 32 * LD88;      float* sWh = sLn + 64;          float* sR = sLn + 96;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int mt = warp & 3, nh = warp >> 2;
+  const int mt = warp & 1, nq = warp >> 1;
   const int g0 = blockIdx.x * DT;
   const int b_begin = blockIdx.y * p.cells_per_chunk, b_end = min(p.B, b_begin + p.cells_per_chunk);
   const float scale = 0.35355339059327373f;   // 1 / sqrt(head_dim = 8)
 
   // ---- weights of the block into shared memory (padded rows: conflict-free fragment reads) ----
-  for (int i = tid; i < 1024; i += 256) sWp[(i >> 5) * LD32 + (i & 31)] = p.ca[C_CPROJ + i];
-  for (int i = tid; i < H * 32; i += 256) { sW1[(i >> 5) * LD32 + (i & 31)] = p.ca[C_W1 + i]; sW2[(i >> 5) * LD32 + (i & 31)] = p.ca[C_W2 + i]; }
-  for (int i = tid; i < 32 * H; i += 256) sW3[(i / H) * LD88 + (i % H)] = p.ca[C_W3 + i];
+  for (int i = tid; i < 1024; i += 256) sWp[(i >> 5) * LD32 + (i & 31)] = rt<EXACT>(p.ca[C_CPROJ + i]);
+  for (int i = tid; i < H * 32; i += 256) { sW1[(i >> 5) * LD32 + (i & 31)] = rt<EXACT>(p.ca[C_W1 + i]); sW2[(i >> 5) * LD32 + (i & 31)] = rt<EXACT>(p.ca[C_W2 + i]); }
+  for (int i = tid; i < 32 * H; i += 256) sW3[(i / H) * LD88 + (i % H)] = rt<EXACT>(p.ca[C_W3 + i]);
   if (tid < 64) sLn[tid] = p.ca[C_LN2W + tid];   // ln_2.weight | ln_2.bias
   if (tid < 32) sWh[tid] = p.head_w[tid];
-  // ---- the tile's query-side rows (cell-invariant) ----
+  if (tid < DT) sGid[tid] = (g0 + tid < p.G) ? (int)p.genes[g0 + tid] : -1;
+  // ---- the tile's query rows (cell-invariant) ----
   for (int i = tid; i < DT * 32; i += 256) {
     const int tok = i >> 5, c = i & 31, gi = g0 + tok;
-    float qv = 0.f, ev = 0.f;
-    if (gi < p.G) { qv = p.Q[(size_t)gi * 32 + c]; ev = p.emb[(size_t)p.genes[gi] * 32 + c]; }
-    sQ[tok * LD32 + c] = qv;
-    sQin[tok * LD32 + c] = ev;
+    sQ[tok * LD32 + c] = gi < p.G ? rt<EXACT>(p.Q[(size_t)gi * 32 + c]) : 0.f;
   }
   const float head_b = p.head_b[0];
   __syncthreads();
@@ -977,79 +992,80 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
     for (int o = 0; o < 32; ++o) a += sWh[o] * sW3[o * LD88 + tid];
     sR[tid] = a;
   }
+  // the residual rows q_in = emb[gene] of this thread's accumulator positions (rows g, g + 8 of its row tile; columns nq * 8 + 2 t, + 1)
+  float qin[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const int ga = sGid[mt * 16 + g], gb = sGid[mt * 16 + g + 8], col = nq * 8 + 2 * t;
+    if (ga >= 0) { const float2 v = *reinterpret_cast<const float2*>(p.emb + (size_t)ga * 32 + col); qin[0] = v.x; qin[1] = v.y; }
+    if (gb >= 0) { const float2 v = *reinterpret_cast<const float2*>(p.emb + (size_t)gb * 32 + col); qin[2] = v.x; qin[3] = v.y; }
+  }
   // persistent gradient accumulators
   float acc_w1[3][4] = {}, acc_w2[3][4] = {}, acc_wp[1][4] = {};
-  float acc_lnw[8] = {}, acc_lnb[8] = {}, acc_xs[8] = {}, acc_dq[2][4] = {}, acc_s = 0.f;
-  const int tok_a = tid >> 2, part = tid & 3;     // (token, 8-channel part) of the row phases
+  float acc_lnw[4] = {}, acc_lnb[4] = {}, acc_xs[4] = {}, acc_dq[4] = {}, acc_sh[3][2] = {}, acc_s = 0.f;
+  const int tok_a = tid >> 3, part = tid & 7;     // (token, 4-channel part) of the row phases
+  const int nt0 = nq * 3, ntn = nq < 3 ? 3 : 2;   // this warp's column tiles of the 88 hidden units
   __syncthreads();
 
   for (int b = b_begin; b < b_end; ++b) {
     // (1) the cell's keys / values and, for the backward, d loss / d logit of the tile
     for (int i = tid; i < 512; i += 256) {
-      sK[(i >> 5) * LDK + (i & 31)] = p.Kc[(size_t)b * 512 + i];
-      sVc[(i >> 5) * LDK + (i & 31)] = p.Vc[(size_t)b * 512 + i];
+      sK[(i >> 5) * LDK + (i & 31)] = rt<EXACT>(p.Kc[(size_t)b * 512 + i]);
+      sVc[(i >> 5) * LDK + (i & 31)] = rt<EXACT>(p.Vc[(size_t)b * 512 + i]);
     }
     if (BWD && tid < DT) sDl[tid] = (g0 + tid < p.G) ? p.dlogit[(size_t)b * p.G + g0 + tid] : 0.f;
     __syncthreads();
-    // (2) cross attention over the 16 latent keys: warp (row tile, head pair)
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int h = nh * 2 + hh;
+    // (2) cross attention over the 16 latent keys: warp (row tile, head)
+    {
       float pr[2][4], o[4];
-      attn_probs<EXACT>(sQ + mt * 16 * LD32, sK, h, scale, pr);
-      attn_apply<EXACT>(pr, sVc, h, o);
-      float* dst = sAO + (mt * 16 + g) * LD32 + h * 8 + 2 * t;
-      dst[0] = o[0]; dst[1] = o[1]; dst[8 * LD32] = o[2]; dst[8 * LD32 + 1] = o[3];
+      attn_probs<EXACT>(sQ + mt * 16 * LD32, sK, nq, scale, pr);
+      attn_apply<EXACT>(pr, sVc, nq, o);
+      float* dst = sAO + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
+      dst[0] = rt<EXACT>(o[0]); dst[1] = rt<EXACT>(o[1]); dst[8 * LD32] = rt<EXACT>(o[2]); dst[8 * LD32 + 1] = rt<EXACT>(o[3]);
     }
     __syncthreads();
     // (3) x1 = q_in + c_proj(ao)
     {
-      float acc[2][4] = {};
-      warp_gemm<EXACT, 2, 4>(acc, sAO + mt * 16 * LD32, LD32, 1, sWp + (nh * 16) * LD32, 1, LD32, 2, 8);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
-          sX1[r * LD32 + col] = sQin[r * LD32 + col] + acc[i][e];
-        }
-      }
+      float acc[1][4] = {};
+      warp_gemm<EXACT, 1, 4>(acc, sAO + mt * 16 * LD32, LD32, 1, sWp + (nq * 8) * LD32, 1, LD32, 1, 8);
+      float* dst = sX1 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
+      dst[0] = qin[0] + acc[0][0]; dst[1] = qin[1] + acc[0][1]; dst[8 * LD32] = qin[2] + acc[0][2]; dst[8 * LD32 + 1] = qin[3] + acc[0][3];
     }
     __syncthreads();
-    // (4) LN2: four threads per token
+    // (4) LN2: eight threads per token
     {
-      float x[8], sum = 0.f;
+      float x[4], sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { x[i] = sX1[tok_a * LD32 + part * 8 + i]; sum += x[i]; }
-      const float mean = quad_sum(sum) * (1.f / 32.f);
+      for (int i = 0; i < 4; ++i) { x[i] = sX1[tok_a * LD32 + part * 4 + i]; sum += x[i]; }
+      const float mean = oct_sum(sum) * (1.f / 32.f);
       float var = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { x[i] -= mean; var += x[i] * x[i]; }
-      const float rstd = rsqrtf(quad_sum(var) * (1.f / 32.f) + p.eps);
+      for (int i = 0; i < 4; ++i) { x[i] -= mean; var += x[i] * x[i]; }
+      const float rstd = rsqrtf(oct_sum(var) * (1.f / 32.f) + p.eps);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sN2[tok_a * LD32 + part * 8 + i] = x[i] * rstd * sLn[part * 8 + i] + sLn[32 + part * 8 + i];
+      for (int i = 0; i < 4; ++i) sN2[tok_a * LD32 + part * 4 + i] = rt<EXACT>(x[i] * rstd * sLn[part * 4 + i] + sLn[32 + part * 4 + i]);
       if (part == 0) { sStat[tok_a * 2] = mean; sStat[tok_a * 2 + 1] = rstd; }
     }
     __syncthreads();
     // (5) u = w1 n2, v = w2 n2, h = silu(u) v; backward: du, dv right away (dh = dlogit r)
     {
-      const int nt0 = nh * 6, ntn = nh ? 5 : 6;
-      float au[6][4] = {}, av[6][4] = {};
-      warp_gemm<EXACT, 6, 4>(au, sN2 + mt * 16 * LD32, LD32, 1, sW1 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
-      warp_gemm<EXACT, 6, 4>(av, sN2 + mt * 16 * LD32, LD32, 1, sW2 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
+      float au[3][4] = {}, av[3][4] = {};
+      warp_gemm<EXACT, 3, 4>(au, sN2 + mt * 16 * LD32, LD32, 1, sW1 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
+      warp_gemm<EXACT, 3, 4>(av, sN2 + mt * 16 * LD32, LD32, 1, sW2 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
       const float dl0 = BWD ? sDl[mt * 16 + g] : 0.f, dl1 = BWD ? sDl[mt * 16 + g + 8] : 0.f;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
+      for (int i = 0; i < 3; ++i) {
         if (i < ntn) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int r = mt * 16 + g + (e >> 1) * 8, col = (nt0 + i) * 8 + 2 * t + (e & 1);
-            const float u = au[i][e], v = av[i][e], sg = sigmoidf_(u);
-            sH[r * LD88 + col] = u * sg * v;
+            const float u = au[i][e], v = av[i][e], sg = sigmoidf_(u), hv = u * sg * v;
             if (BWD) {
-              const float dh = ((e >> 1) ? dl1 : dl0) * sR[col];
-              sU[r * LD88 + col] = dh * v * sg * (1.f + u * (1.f - sg));
-              sV[r * LD88 + col] = dh * u * sg;
+              const float dl = (e >> 1) ? dl1 : dl0, dh = dl * sR[col];
+              acc_sh[i][e & 1] += dl * hv;
+              sU[r * LD88 + col] = rt<EXACT>(dh * v * sg * (1.f + u * (1.f - sg)));
+              sV[r * LD88 + col] = rt<EXACT>(dh * u * sg);
+            } else {
+              sH[r * LD88 + col] = rt<EXACT>(hv);
             }
           }
         }
@@ -1057,37 +1073,24 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
     }
     __syncthreads();
     if (!BWD) {
-      // (6) x2 = x1 + mlp.c_proj(h)
+      // (6) x2 = x1 + mlp.c_proj(h) and this warp's part of the head dot product
       {
-        float acc[2][4] = {};
-        warp_gemm<EXACT, 2, 11>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nh * 16) * LD88, 1, LD88, 2, 8);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
-            sX2[r * LD32 + col] = sX1[r * LD32 + col] + acc[i][e];
-          }
-        }
+        float acc[1][4] = {};
+        warp_gemm<EXACT, 1, 11>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nq * 8) * LD88, 1, LD88, 1, 8);
+        const float* x1 = sX1 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
+        const float w0 = sWh[nq * 8 + 2 * t], w1 = sWh[nq * 8 + 2 * t + 1];
+        const float lo = quad_sum((x1[0] + acc[0][0]) * w0 + (x1[1] + acc[0][1]) * w1);
+        const float hi = quad_sum((x1[8 * LD32] + acc[0][2]) * w0 + (x1[8 * LD32 + 1] + acc[0][3]) * w1);
+        if (t == 0) { sLog[nq * DT + mt * 16 + g] = lo; sLog[nq * DT + mt * 16 + g + 8] = hi; }
       }
       __syncthreads();
       // (7) head logit
-      if (tid < DT && g0 + tid < p.G) {
-        float a = head_b;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) a += sX2[tid * LD32 + c] * sWh[c];
-        p.logits[(size_t)b * p.G + g0 + tid] = a;
-      }
-      __syncthreads();
-      continue;
+      if (tid < DT && g0 + tid < p.G)
+        p.logits[(size_t)b * p.G + g0 + tid] = head_b + sLog[tid] + sLog[DT + tid] + sLog[2 * DT + tid] + sLog[3 * DT + tid];
+      continue;     // (the next writes of sLog / sX1 sit behind the barriers of the next iteration)
     }
-    // (8) sums for the head / mlp.c_proj gradients (threads 0..87: sum_tok dlogit h; 96..127: sum_tok dlogit x1; 128: sum_tok dlogit)
-    if (tid < H) {
-      float a = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < DT; ++r) a += sDl[r] * sH[r * LD88 + tid];
-      acc_s += a;
-    } else if (tid >= 96 && tid < 128) {
+    // (8) sums for the head gradient (threads 96..127: sum_tok dlogit x1; 128: sum_tok dlogit)
+    if (tid >= 96 && tid < 128) {
       float a = 0.f;
 #pragma unroll 8
       for (int r = 0; r < DT; ++r) a += sDl[r] * sX1[r * LD32 + tid - 96];
@@ -1101,30 +1104,32 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
     {
       const int nw = warp & 3, mw0 = warp >> 2;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        warp_gemm<EXACT, 1, 8>(&acc_w1[i], sU + (mw0 + 2 * i) * 16, 1, LD88, sN2 + nw * 8, LD32, 1, 1, 8);
-        warp_gemm<EXACT, 1, 8>(&acc_w2[i], sV + (mw0 + 2 * i) * 16, 1, LD88, sN2 + nw * 8, LD32, 1, 1, 8);
-      }
-      float acc[2][4] = {};
-      warp_gemm<EXACT, 2, 11>(acc, sU + mt * 16 * LD88, LD88, 1, sW1 + nh * 16, LD32, 1, 2, 8);
-      warp_gemm<EXACT, 2, 11>(acc, sV + mt * 16 * LD88, LD88, 1, sW2 + nh * 16, LD32, 1, 2, 8);
+      for (int ks = 0; ks < DT / 8; ++ks) {          // the n2 fragment of a token step is shared by the 3 + 3 row tiles of du / dv
+        const int k0 = ks * 8;
+        const float bf[2] = {sN2[(k0 + t) * LD32 + nw * 8 + g], sN2[(k0 + t + 4) * LD32 + nw * 8 + g]};
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
-          sD2[r * LD32 + col] = acc[i][e];
+        for (int i = 0; i < 3; ++i) {
+          const int j0 = (mw0 + 2 * i) * 16 + g;
+          const float a1[4] = {sU[(k0 + t) * LD88 + j0], sU[(k0 + t) * LD88 + j0 + 8], sU[(k0 + t + 4) * LD88 + j0], sU[(k0 + t + 4) * LD88 + j0 + 8]};
+          const float a2[4] = {sV[(k0 + t) * LD88 + j0], sV[(k0 + t) * LD88 + j0 + 8], sV[(k0 + t + 4) * LD88 + j0], sV[(k0 + t + 4) * LD88 + j0 + 8]};
+          mma_f<EXACT>(acc_w1[i], a1, bf);
+          mma_f<EXACT>(acc_w2[i], a2, bf);
         }
       }
+      float acc[1][4] = {};
+      warp_gemm<EXACT, 1, 11>(acc, sU + mt * 16 * LD88, LD88, 1, sW1 + nq * 8, LD32, 1, 1, 8);
+      warp_gemm<EXACT, 1, 11>(acc, sV + mt * 16 * LD88, LD88, 1, sW2 + nq * 8, LD32, 1, 1, 8);
+      float* dst = sD2 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
+      dst[0] = acc[0][0]; dst[1] = acc[0][1]; dst[8 * LD32] = acc[0][2]; dst[8 * LD32 + 1] = acc[0][3];
     }
     __syncthreads();
     // (11) LN2 backward + residual: d x1
     {
       const float mean = sStat[tok_a * 2], rstd = sStat[tok_a * 2 + 1], dl = sDl[tok_a];
-      float xh[8], gy[8], s1 = 0.f, s2 = 0.f;
+      float xh[4], gy[4], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = part * 8 + i;
+      for (int i = 0; i < 4; ++i) {
+        const int c = part * 4 + i;
         xh[i] = (sX1[tok_a * LD32 + c] - mean) * rstd;
         const float dn = sD2[tok_a * LD32 + c];
         acc_lnw[i] += dn * xh[i];
@@ -1133,37 +1138,30 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
         s1 += gy[i];
         s2 += gy[i] * xh[i];
       }
-      const float m1 = quad_sum(s1) * (1.f / 32.f), m2 = quad_sum(s2) * (1.f / 32.f);
+      const float m1 = oct_sum(s1) * (1.f / 32.f), m2 = oct_sum(s2) * (1.f / 32.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = part * 8 + i;
+      for (int i = 0; i < 4; ++i) {
+        const int c = part * 4 + i;
         const float dx = rstd * (gy[i] - m1 - xh[i] * m2) + dl * sWh[c];
         acc_xs[i] += dx;
-        sD1[tok_a * LD32 + c] = dx;
+        sD1[tok_a * LD32 + c] = rt<EXACT>(dx);
       }
     }
     __syncthreads();
     // (12) d c_proj += dx1^T ao ;  d ao = dx1 c_proj
     {
-      warp_gemm<EXACT, 1, 8>(acc_wp, sD1 + (warp & 1) * 16, 1, LD32, sAO + (warp >> 1) * 8, LD32, 1, 1, 8);
-      float acc[2][4] = {};
-      warp_gemm<EXACT, 2, 4>(acc, sD1 + mt * 16 * LD32, LD32, 1, sWp + nh * 16, LD32, 1, 2, 8);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = mt * 16 + g + (e >> 1) * 8, col = nh * 16 + i * 8 + 2 * t + (e & 1);
-          sD2[r * LD32 + col] = acc[i][e];
-        }
-      }
+      warp_gemm<EXACT, 1, DT / 8>(acc_wp, sD1 + (warp & 1) * 16, 1, LD32, sAO + (warp >> 1) * 8, LD32, 1, 1, 8);
+      float acc[1][4] = {};
+      warp_gemm<EXACT, 1, 4>(acc, sD1 + mt * 16 * LD32, LD32, 1, sWp + nq * 8, LD32, 1, 1, 8);
+      float* dst = sD2 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
+      dst[0] = rt<EXACT>(acc[0][0]); dst[1] = rt<EXACT>(acc[0][1]); dst[8 * LD32] = rt<EXACT>(acc[0][2]); dst[8 * LD32 + 1] = rt<EXACT>(acc[0][3]);
     }
     __syncthreads();
-    // (13) attention backward, warp (row tile, head pair); dS and P tiles for the key / value gradients alias the dead du, dv tiles
+    // (13) attention backward, warp (row tile, head); dS and P tiles for the key / value gradients alias the dead du, dv tiles
     float* tDS = sU;   // [DT][68]
     float* tP = sV;    // [DT][68]
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int h = nh * 2 + hh;
+    {
+      const int h = nq;
       float pr[2][4], dp[2][4];
       attn_probs<EXACT>(sQ + mt * 16 * LD32, sK, h, scale, pr);
       {
@@ -1183,20 +1181,22 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
         dp[n][0] = pr[n][0] * (dp[n][0] - D0) * scale; dp[n][1] = pr[n][1] * (dp[n][1] - D0) * scale;
         dp[n][2] = pr[n][2] * (dp[n][2] - D1) * scale; dp[n][3] = pr[n][3] * (dp[n][3] - D1) * scale;
         const int r0 = mt * 16 + g, col = h * 16 + 8 * n + 2 * t;
-        tDS[r0 * 68 + col] = dp[n][0]; tDS[r0 * 68 + col + 1] = dp[n][1]; tDS[(r0 + 8) * 68 + col] = dp[n][2]; tDS[(r0 + 8) * 68 + col + 1] = dp[n][3];
-        tP[r0 * 68 + col] = pr[n][0]; tP[r0 * 68 + col + 1] = pr[n][1]; tP[(r0 + 8) * 68 + col] = pr[n][2]; tP[(r0 + 8) * 68 + col + 1] = pr[n][3];
+        tDS[r0 * 68 + col] = rt<EXACT>(dp[n][0]); tDS[r0 * 68 + col + 1] = rt<EXACT>(dp[n][1]);
+        tDS[(r0 + 8) * 68 + col] = rt<EXACT>(dp[n][2]); tDS[(r0 + 8) * 68 + col + 1] = rt<EXACT>(dp[n][3]);
+        tP[r0 * 68 + col] = rt<EXACT>(pr[n][0]); tP[r0 * 68 + col + 1] = rt<EXACT>(pr[n][1]);
+        tP[(r0 + 8) * 68 + col] = rt<EXACT>(pr[n][2]); tP[(r0 + 8) * 68 + col + 1] = rt<EXACT>(pr[n][3]);
       }
       float dq[4];
       attn_apply<EXACT>(dp, sK, h, dq);      // dQ[tok][h*8 + d] = sum_keys dS K
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc_dq[hh][e] += dq[e];
+      for (int e = 0; e < 4; ++e) acc_dq[e] += dq[e];
     }
     __syncthreads();
     // (14) dK[key][c] = sum_tok dS[tok][h(c)][key] Q[tok][c] ;  dV[key][c] = sum_tok P[tok][h(c)][key] dAO[tok][c]: warp (head, K | V)
     {
       const int h = warp & 3, which = warp >> 2;
       float acc[1][4] = {};
-      warp_gemm<EXACT, 1, 8>(acc, (which ? tP : tDS) + h * 16, 1, 68, (which ? sD2 : sQ) + h * 8, LD32, 1, 1, 8);
+      warp_gemm<EXACT, 1, DT / 8>(acc, (which ? tP : tDS) + h * 16, 1, 68, (which ? sD2 : sQ) + h * 8, LD32, 1, 1, 8);
       float* dst = (which ? p.dV : p.dK) + (size_t)b * 512 + h * 8 + 2 * t;
       atomicAdd(dst + g * 32, acc[0][0]); atomicAdd(dst + g * 32 + 1, acc[0][1]);
       atomicAdd(dst + (g + 8) * 32, acc[0][2]); atomicAdd(dst + (g + 8) * 32 + 1, acc[0][3]);
@@ -1223,39 +1223,47 @@ __global__ void __launch_bounds__(256, 1) dec_mcab_train_kernel(const DecTrainPa
     atomicAdd(p.gca + C_CPROJ + o * 32 + c, acc_wp[0][e]);
   }
   {
-    const int gi0 = g0 + mt * 16 + g;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int gi = gi0 + (e >> 1) * 8;
-        if (gi < p.G) atomicAdd(p.dQ + (size_t)gi * 32 + (nh * 2 + hh) * 8 + 2 * t + (e & 1), acc_dq[hh][e]);
-      }
+    for (int e = 0; e < 4; ++e) {
+      const int gi = g0 + mt * 16 + g + (e >> 1) * 8;
+      if (gi < p.G) atomicAdd(p.dQ + (size_t)gi * 32 + nq * 8 + 2 * t + (e & 1), acc_dq[e]);
     }
     const int gi = g0 + tok_a;
     if (gi < p.G) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(p.dXsum + (size_t)gi * 32 + part * 8 + i, acc_xs[i]);
+      for (int i = 0; i < 4; ++i) atomicAdd(p.dXsum + (size_t)gi * 32 + part * 4 + i, acc_xs[i]);
     }
   }
   __syncthreads();
-  // sum_tok dlogit h -> d mlp.c_proj = w_head (x) s, and its share of d w_head
-  if (tid < H) sStat[tid] = acc_s;
+  // s[j] = sum_tok dlogit h[j] (per-thread partials over rows g, g + 8 -> lanes of equal t -> the two row-tile warps) in sD2[0..87];
+  // ln_2 partials in sD1 / sU
+  if (tid < H) sD2[tid] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sD1[tok_a * LD32 + part * 8 + i] = acc_lnw[i]; sD2[tok_a * LD32 + part * 8 + i] = acc_lnb[i]; }
+  for (int i = 0; i < 4; ++i) { sD1[tok_a * LD32 + part * 4 + i] = acc_lnw[i]; sU[tok_a * LD32 + part * 4 + i] = acc_lnb[i]; }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float v = acc_sh[i][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (g == 0 && i < ntn) atomicAdd(sD2 + (nt0 + i) * 8 + 2 * t + e, v);
+    }
+  }
   __syncthreads();
   if (tid < H) {
-    for (int o = 0; o < 32; ++o) atomicAdd(p.gca + C_W3 + o * H + tid, sWh[o] * acc_s);
+    const float sj = sD2[tid];
+    for (int o = 0; o < 32; ++o) atomicAdd(p.gca + C_W3 + o * H + tid, sWh[o] * sj);
   } else if (tid >= 96 && tid < 128) {
     const int c = tid - 96;
     float a = acc_s;
-    for (int j = 0; j < H; ++j) a += sW3[c * LD88 + j] * sStat[j];
+    for (int j = 0; j < H; ++j) a += sW3[c * LD88 + j] * sD2[j];
     atomicAdd(p.g_head_w + c, a);
   } else if (tid == 128) {
     atomicAdd(p.g_head_b, acc_s);
   } else if (tid >= 160 && tid < 224) {
     const int c = tid & 31;
-    const float* tsrc = tid < 192 ? sD1 : sD2;
+    const float* tsrc = tid < 192 ? sD1 : sU;
     float a = 0.f;
     for (int r = 0; r < DT; ++r) a += tsrc[r * LD32 + c];
     atomicAdd(p.gca + (tid < 192 ? C_LN2W : C_LN2B) + c, a);
