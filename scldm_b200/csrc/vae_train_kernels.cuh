@@ -41,6 +41,10 @@ __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 2);
   return v;
 }
+// 16-byte vector reduction into global memory (sm_90+): one L2 transaction instead of four
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -305,7 +309,7 @@ __device__ __forceinline__ void tile_store(float* __restrict__ dst, const float*
 }
 
 // One CTA per cell: encoder MCAB tail -> encoder Blocks -> latent projection + LN -> decoder front -> decoder Blocks -> K, V
-__global__ void __launch_bounds__(128) latent_fwd_kernel(const LatParams p) {
+__global__ void __launch_bounds__(256) latent_fwd_kernel(const LatParams p) {
   extern __shared__ float4 lat_smem4[];
   LatS& s = *reinterpret_cast<LatS*>(lat_smem4);
   const int b = blockIdx.x;
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(128) latent_fwd_kernel(const LatParams p) {
   }
 }
 
-__global__ void __launch_bounds__(128) latent_bwd_kernel(const LatParams p) {
+__global__ void __launch_bounds__(256) latent_bwd_kernel(const LatParams p) {
   extern __shared__ float4 lat_smem4[];
   LatS& s = *reinterpret_cast<LatS*>(lat_smem4);
   const int b = blockIdx.x;
@@ -414,6 +418,54 @@ __global__ void __launch_bounds__(128) latent_bwd_kernel(const LatParams p) {
   lin16_t<0>(s.dx, 32, 32, eca + C_CPROJ, 32, s.dao, 32);
   __syncthreads();
   tile_store(p.dao_enc + cell, s.dao, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TF32 mma.sync helpers (shared by the encoder-token backward and the decoder tile kernel)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// Operand convention of the tile kernel: with EXACT every product is 3 x TF32 on raw fp32 operands (hi / lo split at load time); without,
+// every mma operand is rounded to TF32 ONCE, where it is stored to shared memory (rt<EXACT>), and the fragment loads feed the bits through.
+template <bool EXACT>
+__device__ __forceinline__ float rt(float x) { return EXACT ? x : __uint_as_float(to_tf32(x)); }
+
+// acc[i] (16 x 8 tile i) += A[16 x 8 KS] * B[8 KS x 8] for `nt` column tiles; element strides: A(r, k) = A[r sar + k sac],
+// B(k, n) = Bm[k sbr + n sbc]; column tile i starts at n = i * nstep.  EXACT: 3 x TF32 (hi / lo split), fp32-grade products.
+template <bool EXACT, int NT, int KS>
+__device__ __forceinline__ void warp_gemm(float (*acc)[4], const float* A, int sar, int sac, const float* Bm, int sbr, int sbc, int nt,
+                                          int nstep) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = ks * 8;
+    float af[4];
+    af[0] = A[g * sar + (k0 + t) * sac];
+    af[1] = A[(g + 8) * sar + (k0 + t) * sac];
+    af[2] = A[g * sar + (k0 + t + 4) * sac];
+    af[3] = A[(g + 8) * sar + (k0 + t + 4) * sac];
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ah[i] = EXACT ? to_tf32(af[i]) : __float_as_uint(af[i]); if (EXACT) al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      if (i < nt) {
+        const float* bp = Bm + (i * nstep + g) * sbc;
+        const float b0 = bp[(k0 + t) * sbr], b1 = bp[(k0 + t + 4) * sbr];
+        uint32_t bh[2] = {EXACT ? to_tf32(b0) : __float_as_uint(b0), EXACT ? to_tf32(b1) : __float_as_uint(b1)};
+        if (EXACT) {
+          uint32_t bl[2] = {to_tf32(b0 - __uint_as_float(bh[0])), to_tf32(b1 - __uint_as_float(bh[1]))};
+          mma_tf32(acc[i], al, bh);
+          mma_tf32(acc[i], ah, bl);
+        }
+        mma_tf32(acc[i], ah, bh);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -500,10 +552,11 @@ __global__ void __launch_bounds__(128) qside_bwd_kernel(const float* __restrict_
   m1 *= (1.f / 32.f); m2 *= (1.f / 32.f);
   if (valid) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      float dxv = rstd * (g[k] - m1 - x[k] * m2);
-      if (dres) dxv += dres[(size_t)r * 32 + k];
-      atomicAdd(d_rows + (size_t)id * 32 + k, dxv);
+    for (int k = 0; k < 32; k += 4) {
+      float dxv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dxv[q] = rstd * (g[k + q] - m1 - x[k + q] * m2) + (dres ? dres[(size_t)r * 32 + k + q] : 0.f);
+      red_add_v4(d_rows + (size_t)id * 32 + k, dxv[0], dxv[1], dxv[2], dxv[3]);
     }
   }
   __syncthreads();
@@ -576,18 +629,53 @@ __global__ void __launch_bounds__(128) enc_tokens_fwd_kernel(const EncTokParams 
 
 // Encoder MCAB pooling: 16 inducing-point queries x 4 heads attend to all S tokens of a cell (no key masking).
 // One CTA per cell; thread = (query, head) pair x one of 8 interleaved token slices; online softmax, merged through shared memory.
+// grid (cells, POOL_SPLIT): a CTA pools one contiguous quarter of the cell's tokens and leaves an unnormalised (max, sum, acc) state per
+// (query, head); enc_pool_merge_kernel merges the quarters.
+constexpr int POOL_SPLIT = 4;
 __global__ void __launch_bounds__(512) enc_pool_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                                                           int S, float* __restrict__ AO, float* __restrict__ lse) {
+                                                           int S, float* __restrict__ part) {
   __shared__ float sm[8][64][10];
   const int b = blockIdx.x, pair = threadIdx.x & 63, slice = threadIdx.x >> 6;
   const int m = pair >> 2, h = pair & 3;
+  const int per = (S + POOL_SPLIT - 1) / POOL_SPLIT, s_begin = blockIdx.y * per;
+  const size_t cell_base = (size_t)b * S * 32;
+  S = min(S, s_begin + per);      // this CTA's token range [s_begin, S)
   float q[8], acc[8], mx = -1e30f, l = 0.f;
 #pragma unroll
   for (int d = 0; d < 8; ++d) { q[d] = Q[m * 32 + h * 8 + d] * 0.35355339059327373f; acc[d] = 0.f; }
-  const float* kb = K + (size_t)b * S * 32 + h * 8;
-  const float* vb = V + (size_t)b * S * 32 + h * 8;
-#pragma unroll 2
-  for (int s = slice; s < S; s += 8) {
+  const float* kb = K + cell_base + h * 8;
+  const float* vb = V + cell_base + h * 8;
+  // four keys per trip: one running-max update (one dependent exp chain) per four keys, 16 independent 16-byte loads in flight
+  int s = s_begin + slice;
+  for (; s + 24 < S; s += 32) {
+    float4 k0[4], k1[4], v0[4], v1[4];
+    float sc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const size_t o = (size_t)(s + 8 * i) * 32;
+      k0[i] = *reinterpret_cast<const float4*>(kb + o); k1[i] = *reinterpret_cast<const float4*>(kb + o + 4);
+      v0[i] = *reinterpret_cast<const float4*>(vb + o); v1[i] = *reinterpret_cast<const float4*>(vb + o + 4);
+    }
+    float mn = mx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sc[i] = q[0] * k0[i].x + q[1] * k0[i].y + q[2] * k0[i].z + q[3] * k0[i].w + q[4] * k1[i].x + q[5] * k1[i].y + q[6] * k1[i].z + q[7] * k1[i].w;
+      mn = fmaxf(mn, sc[i]);
+    }
+    const float corr = __expf(mx - mn);
+    mx = mn;
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] *= corr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float pr = __expf(sc[i] - mn);
+      l += pr;
+      acc[0] += pr * v0[i].x; acc[1] += pr * v0[i].y; acc[2] += pr * v0[i].z; acc[3] += pr * v0[i].w;
+      acc[4] += pr * v1[i].x; acc[5] += pr * v1[i].y; acc[6] += pr * v1[i].z; acc[7] += pr * v1[i].w;
+    }
+  }
+  for (; s < S; s += 8) {
     const float4 k0 = *reinterpret_cast<const float4*>(kb + (size_t)s * 32), k1 = *reinterpret_cast<const float4*>(kb + (size_t)s * 32 + 4);
     const float4 v0 = *reinterpret_cast<const float4*>(vb + (size_t)s * 32), v1 = *reinterpret_cast<const float4*>(vb + (size_t)s * 32 + 4);
     const float sc = q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w + q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w;
@@ -617,12 +705,30 @@ __global__ void __launch_bounds__(512) enc_pool_fwd_kernel(const float* __restri
 #pragma unroll
       for (int d = 0; d < 8; ++d) ga[d] += sm[i][pair][2 + d] * c;
     }
-    const float il = 1.f / gl;
+    float* dst = part + (((size_t)b * POOL_SPLIT + blockIdx.y) * 64 + pair) * 10;
+    dst[0] = gm; dst[1] = gl;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) AO[(size_t)b * 512 + m * 32 + h * 8 + d] = ga[d] * il;
-    lse[b * 64 + pair] = gm + __logf(gl);
+    for (int d = 0; d < 8; ++d) dst[2 + d] = ga[d];
   }
 }
+__global__ void __launch_bounds__(64) enc_pool_merge_kernel(const float* __restrict__ part, float* __restrict__ AO, float* __restrict__ lse) {
+  const int b = blockIdx.x, pair = threadIdx.x, m = pair >> 2, h = pair & 3;
+  const float* src = part + ((size_t)b * POOL_SPLIT * 64 + pair) * 10;
+  float gm = -1e30f;
+  for (int i = 0; i < POOL_SPLIT; ++i) gm = fmaxf(gm, src[i * 640]);
+  float gl = 0.f, ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < POOL_SPLIT; ++i) {
+    const float c = __expf(src[i * 640] - gm);
+    gl += src[i * 640 + 1] * c;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) ga[d] += src[i * 640 + 2 + d] * c;
+  }
+  const float il = 1.f / gl;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) AO[(size_t)b * 512 + m * 32 + h * 8 + d] = ga[d] * il;
+  lse[b * 64 + pair] = gm + __logf(gl);
+}
+
 
 // Backward of the pooling and of the token side, one thread per token of a 128-token tile of one cell:
 // dAO -> (dK, dV of the token) -> c_attn^T -> LN1 backward -> d emb[gene] (scatter) ; weight gradients of c_attn / ln_1 and
@@ -636,24 +742,26 @@ struct EncBwdParams {
   float* dQ;                 // [16][32] accumulated (atomics)
   float* g_emb;              // gradient of the embedding table
 };
-constexpr int ENC_BWD_SMEM_FLOATS = 128 * 65 + 128 * 33 + 128 * 65 + 128 * 33 + 512 * 2 + 64 + 2048 + 64;
+constexpr int ELD64 = 68, ELD32 = 40;   // row strides of the 64- / 32-wide token tiles
+constexpr int ENC_BWD_SMEM_FLOATS = 128 * ELD64 + 128 * ELD32 + 128 * ELD64 + 128 * ELD32 + 512 * 2 + 64 + 64 * ELD32 + 64;
+template <bool EXACT>
 __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams p) {
   extern __shared__ float4 enc_smem4[];
   float* sm = reinterpret_cast<float*>(enc_smem4);
-  float* tDKV = sm;                     // [128][65]  dK | dV of the tile's tokens
-  float* tXN = tDKV + 128 * 65;         // [128][33]  LN1 output
-  float* tDS = tXN + 128 * 33;          // [128][65]  dS[(query, head)] of the tile's tokens (scaled)
-  float* tK = tDS + 128 * 65;           // [128][33]
-  float* sQ = tK + 128 * 33;            // [16][32] scaled queries
+  float* tDKV = sm;                     // [128][68]  dK | dV of the tile's tokens
+  float* tXN = tDKV + 128 * ELD64;      // [128][40]  LN1 output
+  float* tDS = tXN + 128 * ELD32;       // [128][68]  dS[(query, head)] of the tile's tokens (scaled)
+  float* tK = tDS + 128 * ELD64;        // [128][40]
+  float* sQ = tK + 128 * ELD32;         // [16][32] scaled queries
   float* sDAO = sQ + 512;               // [16][32]
   float* sD = sDAO + 512;               // [64] rowsum(dAO * AO) per (query, head)
   float* sW = sD + 64;                  // c_attn [64][32]
-  float* sLn = sW + 2048;               // ln_1 weight | bias
+  float* sLn = sW + 64 * ELD32;         // ln_1 weight | bias
   const int b = blockIdx.y, s = blockIdx.x * 128 + threadIdx.x;
   const bool valid = s < p.S;
   const long long tk = (long long)b * p.S + (valid ? s : 0);
   for (int i = threadIdx.x; i < 512; i += 128) { sQ[i] = p.Q[i] * 0.35355339059327373f; sDAO[i] = p.dAO[(size_t)b * 512 + i]; }
-  for (int i = threadIdx.x; i < 2048; i += 128) sW[i] = p.ca[C_CATTN + i];
+  for (int i = threadIdx.x; i < 2048; i += 128) sW[(i >> 5) * ELD32 + (i & 31)] = rt<EXACT>(p.ca[C_CATTN + i]);
   if (threadIdx.x < 64) sLn[threadIdx.x] = p.ca[C_LN1W + threadIdx.x];   // ln_1.weight, ln_1.bias are adjacent
   if (threadIdx.x < 64) {
     const int m = threadIdx.x >> 2, h = threadIdx.x & 3;
@@ -676,14 +784,18 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
   for (int m = 0; m < 16; ++m) {
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
+      // the query / dAO rows are the same for every thread: four broadcast 16-byte reads per (query, head)
+      const float4 qa = *reinterpret_cast<const float4*>(sQ + m * 32 + h * 8), qb = *reinterpret_cast<const float4*>(sQ + m * 32 + h * 8 + 4);
+      const float4 ga = *reinterpret_cast<const float4*>(sDAO + m * 32 + h * 8), gb = *reinterpret_cast<const float4*>(sDAO + m * 32 + h * 8 + 4);
+      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w}, gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
       float sc = 0.f, dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < 8; ++d) { sc += sQ[m * 32 + h * 8 + d] * kk[h * 8 + d]; dp += sDAO[m * 32 + h * 8 + d] * vv[h * 8 + d]; }
+      for (int d = 0; d < 8; ++d) { sc += qv[d] * kk[h * 8 + d]; dp += gv[d] * vv[h * 8 + d]; }
       const float pr = valid ? __expf(sc - lse[m * 4 + h]) : 0.f;
       const float ds = pr * (dp - sD[m * 4 + h]);
-      tDS[threadIdx.x * 65 + m * 4 + h] = ds * 0.35355339059327373f;
+      tDS[threadIdx.x * ELD64 + m * 4 + h] = rt<EXACT>(ds * 0.35355339059327373f);
 #pragma unroll
-      for (int d = 0; d < 8; ++d) { dk[h * 8 + d] += ds * sQ[m * 32 + h * 8 + d]; dv[h * 8 + d] += pr * sDAO[m * 32 + h * 8 + d]; }
+      for (int d = 0; d < 8; ++d) { dk[h * 8 + d] += ds * qv[d]; dv[h * 8 + d] += pr * gv[d]; }
     }
   }
   // token side: recompute x, LN1
@@ -699,18 +811,50 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
   }
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    tDKV[threadIdx.x * 65 + k] = dk[k];
-    tDKV[threadIdx.x * 65 + 32 + k] = dv[k];
-    tXN[threadIdx.x * 33 + k] = valid ? xh[k] * sLn[k] + sLn[32 + k] : 0.f;
-    tK[threadIdx.x * 33 + k] = valid ? kk[k] : 0.f;
+    tDKV[threadIdx.x * ELD64 + k] = rt<EXACT>(dk[k]);
+    tDKV[threadIdx.x * ELD64 + 32 + k] = rt<EXACT>(dv[k]);
+    tXN[threadIdx.x * ELD32 + k] = valid ? rt<EXACT>(xh[k] * sLn[k] + sLn[32 + k]) : 0.f;
+    tK[threadIdx.x * ELD32 + k] = valid ? rt<EXACT>(kk[k]) : 0.f;
   }
-  // d(LN1 output) = Wkv^T [dk | dv]
+  __syncthreads();
+  // c_attn weight gradient (64 x 32 = dKV^T xn over the 128 tokens) and dQ (per head 16 queries x 8 = dS_h^T K_h) on mma.sync:
+  // warp w owns weight rows 16 w .. 16 w + 15 and head w
+  const int warp = threadIdx.x >> 5;
+  {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float acc[4][4] = {};
+    warp_gemm<EXACT, 4, 16>(acc, tDKV + warp * 16, 1, ELD64, tXN, ELD32, 1, 4, 8);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(p.gca + C_CATTN + (warp * 16 + g + (e >> 1) * 8) * 32 + i * 8 + 2 * t + (e & 1), acc[i][e]);
+    }
+    float aq[1][4] = {};
+    warp_gemm<EXACT, 1, 16>(aq, tDS + warp, 4, ELD64, tK + warp * 8, ELD32, 1, 1, 8);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) atomicAdd(p.dQ + (g + (e >> 1) * 8) * 32 + warp * 8 + 2 * t + (e & 1), aq[0][e]);
+  }
+  __syncthreads();
+  // d(LN1 output)[token][32] = [dk | dv] Wkv on mma.sync: warp w computes the rows of its own 32 tokens into the (now dead) dS tile
+  {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mtile = 0; mtile < 2; ++mtile) {
+      const int r0 = warp * 32 + mtile * 16;
+      float acc[4][4] = {};
+      warp_gemm<EXACT, 4, 8>(acc, tDKV + r0 * ELD64, ELD64, 1, sW, ELD32, 1, 4, 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tDS[(r0 + g + (e >> 1) * 8) * ELD64 + i * 8 + 2 * t + (e & 1)] = acc[i][e];
+      }
+    }
+  }
+  __syncwarp();
   float g[32], m1 = 0.f, m2 = 0.f;
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    float a = 0.f;
-#pragma unroll
-    for (int o = 0; o < 32; ++o) a += sW[o * 32 + k] * dk[o] + sW[(32 + o) * 32 + k] * dv[o];
+    const float a = tDS[threadIdx.x * ELD64 + k];
     kk[k] = a;   // gradient w.r.t. the LN1 output (the key registers are dead: they live in tK)
     g[k] = a * sLn[k];
     m1 += g[k];
@@ -718,31 +862,25 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
   }
   m1 *= (1.f / 32.f); m2 *= (1.f / 32.f);
   if (valid && f != 0.f) {
+    const float sf = rstd * f;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) atomicAdd(p.g_emb + (size_t)gid * 32 + k, rstd * (g[k] - m1 - xh[k] * m2) * f);
-  }
-  __syncthreads();
-  // c_attn weight gradient and dQ from the tiles
-  wgrad_rows(tDKV, 65, 64, tXN, 33, 32, 128, p.gca + C_CATTN);
-  for (int idx = threadIdx.x; idx < 512; idx += 128) {
-    const int m = idx >> 5, c = idx & 31, h = c >> 3;
-    float a = 0.f;
-    for (int r = 0; r < 128; ++r) a += tDS[r * 65 + m * 4 + h] * tK[r * 33 + c];
-    atomicAdd(p.dQ + idx, a);
+    for (int k = 0; k < 32; k += 4)
+      red_add_v4(p.g_emb + (size_t)gid * 32 + k, sf * (g[k] - m1 - xh[k] * m2), sf * (g[k + 1] - m1 - xh[k + 1] * m2),
+                 sf * (g[k + 2] - m1 - xh[k + 2] * m2), sf * (g[k + 3] - m1 - xh[k + 3] * m2));
   }
   __syncthreads();
   // ln_1 affine gradients: stage (d out * xhat, d out) in the two 33-wide tiles
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    tXN[threadIdx.x * 33 + k] = valid ? kk[k] * xh[k] : 0.f;
-    tK[threadIdx.x * 33 + k] = valid ? kk[k] : 0.f;
+    tXN[threadIdx.x * ELD32 + k] = valid ? kk[k] * xh[k] : 0.f;
+    tK[threadIdx.x * ELD32 + k] = valid ? kk[k] : 0.f;
   }
   __syncthreads();
   if (threadIdx.x < 64) {
     const int k = threadIdx.x & 31;
     const float* t = threadIdx.x < 32 ? tXN : tK;
     float a = 0.f;
-    for (int i = 0; i < 128; ++i) a += t[i * 33 + k];
+    for (int i = 0; i < 128; ++i) a += t[i * ELD32 + k];
     atomicAdd(p.gca + (threadIdx.x < 32 ? C_LN1W : C_LN1B) + k, a);
   }
 }
@@ -823,51 +961,6 @@ __global__ void __launch_bounds__(512) nb_loss_kernel(const NbLossParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // Decoder MCAB on (cell, gene) tokens: forward (logits) and, with BWD, the whole backward of the tile.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-// Operand convention of the tile kernel: with EXACT every product is 3 x TF32 on raw fp32 operands (hi / lo split at load time); without,
-// every mma operand is rounded to TF32 ONCE, where it is stored to shared memory (rt<EXACT>), and the fragment loads feed the bits through.
-template <bool EXACT>
-__device__ __forceinline__ float rt(float x) { return EXACT ? x : __uint_as_float(to_tf32(x)); }
-
-// acc[i] (16 x 8 tile i) += A[16 x 8 KS] * B[8 KS x 8] for `nt` column tiles; element strides: A(r, k) = A[r sar + k sac],
-// B(k, n) = Bm[k sbr + n sbc]; column tile i starts at n = i * nstep.  EXACT: 3 x TF32 (hi / lo split), fp32-grade products.
-template <bool EXACT, int NT, int KS>
-__device__ __forceinline__ void warp_gemm(float (*acc)[4], const float* A, int sar, int sac, const float* Bm, int sbr, int sbc, int nt,
-                                          int nstep) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int k0 = ks * 8;
-    float af[4];
-    af[0] = A[g * sar + (k0 + t) * sac];
-    af[1] = A[(g + 8) * sar + (k0 + t) * sac];
-    af[2] = A[g * sar + (k0 + t + 4) * sac];
-    af[3] = A[(g + 8) * sar + (k0 + t + 4) * sac];
-    uint32_t ah[4], al[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { ah[i] = EXACT ? to_tf32(af[i]) : __float_as_uint(af[i]); if (EXACT) al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      if (i < nt) {
-        const float* bp = Bm + (i * nstep + g) * sbc;
-        const float b0 = bp[(k0 + t) * sbr], b1 = bp[(k0 + t + 4) * sbr];
-        uint32_t bh[2] = {EXACT ? to_tf32(b0) : __float_as_uint(b0), EXACT ? to_tf32(b1) : __float_as_uint(b1)};
-        if (EXACT) {
-          uint32_t bl[2] = {to_tf32(b0 - __uint_as_float(bh[0])), to_tf32(b1 - __uint_as_float(bh[1]))};
-          mma_tf32(acc[i], al, bh);
-          mma_tf32(acc[i], ah, bl);
-        }
-        mma_tf32(acc[i], ah, bh);
-      }
-    }
-  }
-}
-
 struct DecTrainParams {
   const float* ca; float* gca;          // decoder_cross_attention parameter group / its gradients
   const float* emb; const long long* genes; int G;
@@ -1230,8 +1323,7 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
     }
     const int gi = g0 + tok_a;
     if (gi < p.G) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(p.dXsum + (size_t)gi * 32 + part * 4 + i, acc_xs[i]);
+      red_add_v4(p.dXsum + (size_t)gi * 32 + part * 4, acc_xs[0], acc_xs[1], acc_xs[2], acc_xs[3]);
     }
   }
   __syncthreads();
