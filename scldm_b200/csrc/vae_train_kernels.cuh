@@ -1093,7 +1093,7 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
     if (gb >= 0) { const float2 v = *reinterpret_cast<const float2*>(p.emb + (size_t)gb * 32 + col); qin[2] = v.x; qin[3] = v.y; }
   }
   // persistent gradient accumulators
-  float acc_w1[3][4] = {}, acc_w2[3][4] = {}, acc_wp[1][4] = {};
+  float acc_w[6][4] = {}, acc_wp[1][4] = {};
   float acc_lnw[4] = {}, acc_lnb[4] = {}, acc_xs[4] = {}, acc_dq[4] = {}, acc_sh[3][2] = {}, acc_s = 0.f;
   const int tok_a = tid >> 3, part = tid & 7;     // (token, 4-channel part) of the row phases
   const int nt0 = nq * 3, ntn = nq < 3 ? 3 : 2;   // this warp's column tiles of the 88 hidden units
@@ -1195,18 +1195,21 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
     }
     // (10) d w1 += du^T n2, d w2 += dv^T n2 ;  d n2 = du w1 + dv w2
     {
-      const int nw = warp & 3, mw0 = warp >> 2;
+      // weight-gradient tiles of a warp: one matrix (du | dv), 3 row tiles x 2 column tiles: per token step 12 + 4 fragment loads feed 6 mma
+      const float* sG = (warp & 1) ? sV : sU;
+      const int nw0 = ((warp >> 1) & 1) * 2, mw0 = (warp >> 2) * 3;
 #pragma unroll
-      for (int ks = 0; ks < DT / 8; ++ks) {          // the n2 fragment of a token step is shared by the 3 + 3 row tiles of du / dv
+      for (int ks = 0; ks < DT / 8; ++ks) {
         const int k0 = ks * 8;
-        const float bf[2] = {sN2[(k0 + t) * LD32 + nw * 8 + g], sN2[(k0 + t + 4) * LD32 + nw * 8 + g]};
+        float bf[2][2];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) { bf[n][0] = sN2[(k0 + t) * LD32 + (nw0 + n) * 8 + g]; bf[n][1] = sN2[(k0 + t + 4) * LD32 + (nw0 + n) * 8 + g]; }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const int j0 = (mw0 + 2 * i) * 16 + g;
-          const float a1[4] = {sU[(k0 + t) * LD88 + j0], sU[(k0 + t) * LD88 + j0 + 8], sU[(k0 + t + 4) * LD88 + j0], sU[(k0 + t + 4) * LD88 + j0 + 8]};
-          const float a2[4] = {sV[(k0 + t) * LD88 + j0], sV[(k0 + t) * LD88 + j0 + 8], sV[(k0 + t + 4) * LD88 + j0], sV[(k0 + t + 4) * LD88 + j0 + 8]};
-          mma_f<EXACT>(acc_w1[i], a1, bf);
-          mma_f<EXACT>(acc_w2[i], a2, bf);
+          const int j0 = (mw0 + i) * 16 + g;
+          const float a[4] = {sG[(k0 + t) * LD88 + j0], sG[(k0 + t) * LD88 + j0 + 8], sG[(k0 + t + 4) * LD88 + j0], sG[(k0 + t + 4) * LD88 + j0 + 8]};
+          mma_f<EXACT>(acc_w[i * 2], a, bf[0]);
+          mma_f<EXACT>(acc_w[i * 2 + 1], a, bf[1]);
         }
       }
       float acc[1][4] = {};
@@ -1300,13 +1303,14 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
   if (!BWD) return;
   // ---- flush the gradient accumulators ----
   {
-    const int nw = warp & 3, mw0 = warp >> 2;
+    float* gw = p.gca + ((warp & 1) ? C_W2 : C_W1);
+    const int nw0 = ((warp >> 1) & 1) * 2, mw0 = (warp >> 2) * 3;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 6; ++i) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int j = (mw0 + 2 * i) * 16 + g + (e >> 1) * 8, c = nw * 8 + 2 * t + (e & 1);
-        if (j < H) { atomicAdd(p.gca + C_W1 + j * 32 + c, acc_w1[i][e]); atomicAdd(p.gca + C_W2 + j * 32 + c, acc_w2[i][e]); }
+        const int j = (mw0 + (i >> 1)) * 16 + g + (e >> 1) * 8, c = (nw0 + (i & 1)) * 8 + 2 * t + (e & 1);
+        if (j < H) atomicAdd(gw + j * 32 + c, acc_w[i][e]);
       }
     }
   }

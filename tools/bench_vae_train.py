@@ -29,6 +29,7 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--exact", action="store_true")
 ap.add_argument("--no-eager", action="store_true")
+ap.add_argument("--no-e2e", action="store_true")
 ap.add_argument("--eager-cells", type=int, default=16)
 args = ap.parse_args()
 
@@ -83,6 +84,39 @@ if world > 1:
     torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
 ms = float(ms)
 loss_first, loss_last = float(losses[0]), float(losses[-1])
+
+# end to end through the public API from HOST buffers: pinned dense counts -> H2D -> device tokenizer -> training step -> D2H of the loss
+e2e_ms = None
+if not args.no_e2e:
+    counts_host = batch["counts"].cpu().pin_memory()
+    gene_row = torch.arange(1, G + 1, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        c = counts_host.to(dev, non_blocking=True)
+        tok = ops.tokenize_expressed(c, gene_row, S)
+        loss = trainer.training_step(dict(counts=c, genes=batch["genes"], library_size=tok["library_size"], counts_subset=tok["counts_subset"],
+                                          genes_subset=tok["genes_subset"]))
+        loss_host.copy_(loss, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    tot = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        e2e_step()
+        b.record()
+        b.synchronize()
+        tot += a.elapsed_time(b)
+    e = torch.tensor([tot / args.steps], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = float(e)
 
 breakdown = None
 if rank == 0:
@@ -154,6 +188,10 @@ if rank == 0:
                      "frac": round(B * 3 * dec_fwd / max(dec_ms, 1e-9) / 1e9 / (1393.8 / 2), 4),
                      "peak_source": "half the measured sustained cuBLAS bf16 rate of MEASURED_PEAKS.json (TF32 tensor-core rate = bf16 / 2); no TF32 measurement on this pool",
                      "traffic": None},
+        "e2e": None if e2e_ms is None else {"value": round(B * world / e2e_ms * 1e3, 1), "unit": "cells/s", "ms_per_step": round(e2e_ms, 3),
+                                            "h2d_bytes_per_step": B * G * 4, "d2h_bytes_per_step": 4,
+                                            "note": "pinned dense counts -> H2D -> scldm_tokenize_expressed -> VAETrainer.training_step -> D2H of the loss"},
+        "gpu_launches": 17 * (args.steps + args.warmup),
         "kernel_breakdown": breakdown, "gpu_eager_baseline": eager,
     }
     print(json.dumps(line))
