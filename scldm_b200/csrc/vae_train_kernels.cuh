@@ -1093,7 +1093,7 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
     if (gb >= 0) { const float2 v = *reinterpret_cast<const float2*>(p.emb + (size_t)gb * 32 + col); qin[2] = v.x; qin[3] = v.y; }
   }
   // persistent gradient accumulators
-  float acc_w[6][4] = {}, acc_wp[1][4] = {};
+  float acc_w[6][4] = {}, acc_wp[2][4] = {};
   float acc_lnw[4] = {}, acc_lnb[4] = {}, acc_xs[4] = {}, acc_dq[4] = {}, acc_sh[3][2] = {}, acc_s = 0.f;
   const int tok_a = tid >> 3, part = tid & 7;     // (token, 4-channel part) of the row phases
   const int nt0 = nq * 3, ntn = nq < 3 ? 3 : 2;   // this warp's column tiles of the 88 hidden units
@@ -1212,11 +1212,17 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
           mma_f<EXACT>(acc_w[i * 2 + 1], a, bf[1]);
         }
       }
-      float acc[1][4] = {};
-      warp_gemm<EXACT, 1, 11>(acc, sU + mt * 16 * LD88, LD88, 1, sW1 + nq * 8, LD32, 1, 1, 8);
-      warp_gemm<EXACT, 1, 11>(acc, sV + mt * 16 * LD88, LD88, 1, sW2 + nq * 8, LD32, 1, 1, 8);
-      float* dst = sD2 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
-      dst[0] = acc[0][0]; dst[1] = acc[0][1]; dst[8 * LD32] = acc[0][2]; dst[8 * LD32 + 1] = acc[0][3];
+      // d n2: warp (row tile, column half, du w1 | dv w2): the two K halves land in sD2 / sD1 and are summed by the row phase below
+      {
+        const int nh2 = (warp >> 1) & 1, kh = warp >> 2;
+        float acc[2][4] = {};
+        warp_gemm<EXACT, 2, 11>(acc, (kh ? sV : sU) + mt * 16 * LD88, LD88, 1, (kh ? sW2 : sW1) + nh2 * 16, LD32, 1, 2, 8);
+        float* dst = (kh ? sD1 : sD2) + (mt * 16 + g) * LD32 + nh2 * 16 + 2 * t;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          dst[i * 8] = acc[i][0]; dst[i * 8 + 1] = acc[i][1]; dst[8 * LD32 + i * 8] = acc[i][2]; dst[8 * LD32 + i * 8 + 1] = acc[i][3];
+        }
+      }
     }
     __syncthreads();
     // (11) LN2 backward + residual: d x1
@@ -1227,7 +1233,7 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
       for (int i = 0; i < 4; ++i) {
         const int c = part * 4 + i;
         xh[i] = (sX1[tok_a * LD32 + c] - mean) * rstd;
-        const float dn = sD2[tok_a * LD32 + c];
+        const float dn = sD2[tok_a * LD32 + c] + sD1[tok_a * LD32 + c];
         acc_lnw[i] += dn * xh[i];
         acc_lnb[i] += dn;
         gy[i] = dn * sLn[c];
@@ -1244,13 +1250,19 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
       }
     }
     __syncthreads();
-    // (12) d c_proj += dx1^T ao ;  d ao = dx1 c_proj
-    {
-      warp_gemm<EXACT, 1, DT / 8>(acc_wp, sD1 + (warp & 1) * 16, 1, LD32, sAO + (warp >> 1) * 8, LD32, 1, 1, 8);
-      float acc[1][4] = {};
-      warp_gemm<EXACT, 1, 4>(acc, sD1 + mt * 16 * LD32, LD32, 1, sWp + nq * 8, LD32, 1, 1, 8);
-      float* dst = sD2 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
-      dst[0] = rt<EXACT>(acc[0][0]); dst[1] = rt<EXACT>(acc[0][1]); dst[8 * LD32] = rt<EXACT>(acc[0][2]); dst[8 * LD32 + 1] = rt<EXACT>(acc[0][3]);
+    // (12) warps 0-3: d ao = dx1 c_proj (row tile, column half); warps 4-7: d c_proj += dx1^T ao (row tile of the weight, column half)
+    if (warp < 4) {
+      const int nh2 = warp >> 1;
+      float acc[2][4] = {};
+      warp_gemm<EXACT, 2, 4>(acc, sD1 + mt * 16 * LD32, LD32, 1, sWp + nh2 * 16, LD32, 1, 2, 8);
+      float* dst = sD2 + (mt * 16 + g) * LD32 + nh2 * 16 + 2 * t;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        dst[i * 8] = rt<EXACT>(acc[i][0]); dst[i * 8 + 1] = rt<EXACT>(acc[i][1]);
+        dst[8 * LD32 + i * 8] = rt<EXACT>(acc[i][2]); dst[8 * LD32 + i * 8 + 1] = rt<EXACT>(acc[i][3]);
+      }
+    } else {
+      warp_gemm<EXACT, 2, DT / 8>(acc_wp, sD1 + (warp & 1) * 16, 1, LD32, sAO + ((warp >> 1) & 1) * 16, LD32, 1, 2, 8);
     }
     __syncthreads();
     // (13) attention backward, warp (row tile, head); dS and P tiles for the key / value gradients alias the dead du, dv tiles
@@ -1314,10 +1326,15 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
       }
     }
   }
+  if (warp >= 4) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int o = (warp & 1) * 16 + g + (e >> 1) * 8, c = (warp >> 1) * 8 + 2 * t + (e & 1);
-    atomicAdd(p.gca + C_CPROJ + o * 32 + c, acc_wp[0][e]);
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int o = (warp & 1) * 16 + g + (e >> 1) * 8, c = ((warp >> 1) & 1) * 16 + i * 8 + 2 * t + (e & 1);
+        atomicAdd(p.gca + C_CPROJ + o * 32 + c, acc_wp[i][e]);
+      }
+    }
   }
   {
 #pragma unroll
