@@ -527,6 +527,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2368, help="cells per step per GPU (2x rows are generated)")
     ap.add_argument("--chunk", type=int, default=0, help="cells per ODE chunk (0 = library default)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --batch is the GLOBAL batch, split over the GPUs (default: weak, --batch cells per GPU)")
     ap.add_argument("--ref-batch", type=int, default=64, help="cells per step of the CPU reference arm (BASELINE configs[0]: batch 64)")
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -577,7 +578,7 @@ def main():
     ldm, dcfg, vcfg = build_models(device, args.dataset, method=args.method)
     if args.chunk > 0:
         ldm.cell_chunk = args.chunk
-    B, G = args.batch, vcfg.n_genes
+    B, G = (max(8, args.batch // world) if args.strong else args.batch), vcfg.n_genes
     gw = {k: GUIDANCE for k in dcfg.class_vocab_sizes}
     # the GLOBAL batch (B cells per GPU, weak scaling) is described once, identically on every rank; `dist.sample_sharded` - the
     # product's multi-GPU call - makes every rank generate its contiguous slice (Philox streams keyed by the global cell index)
@@ -750,7 +751,7 @@ def main():
         fl = algorithmic_flops_per_row(G, evals)
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": workload_name(args.dataset, dcfg, vcfg, args.method),
                        "cells_per_step_per_gpu": B, "rows_per_step": rows_per_step, "ode_chunk_cells": min(ldm.cell_chunk, B),

@@ -339,6 +339,14 @@ int scldm_vae_train_step(const scldm_vae_train* tr, const int64_t* genes_subset,
                          int32_t zero_grads, int32_t exact, float* nll, float* z_out, float* mu_out, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* Backward of the LAST scldm_vae_train_step(backward = 0) on the same workspace / inputs, from caller-provided gradients of the NB
+ * parameters (the torch.autograd bridge, scldm_b200/vae_training.py::differentiable_forward): dmu [n_cells][G] = dLoss/dmu,
+ * dtheta [n_cells][G] = dLoss/dtheta of the theta row expanded over the cells (nullable).  Parameter gradients are accumulated into
+ * tr->grads (cleared first if zero_grads != 0).                                                                     */
+int scldm_vae_train_backward(const scldm_vae_train* tr, const int64_t* genes_subset, const float* counts_subset, int32_t S, const int64_t* genes,
+                             const float* library, const float* dmu, const float* dtheta, int32_t n_cells, int32_t G, int32_t zero_grads,
+                             int32_t exact, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Stand-alone access to the slab GEMM for unit tests: mode 0 forward  out[M][N]  = A[M][K] W[N][K]^T (+bias[N]),
  * mode 1 dgrad out[M][K] = dY[M][N] W[N][K], mode 2 wgrad out[N][K] += dY[M][N]^T A[M][K].  a_f32 / dy_f32 are fp32
  * row-major inputs (converted to bf16 slab tensors in `workspace`), w_packed = bf16 [N/256][K/64][256 x 64] tiles.

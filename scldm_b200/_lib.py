@@ -18,7 +18,7 @@ EXPORTS = [
     "scldm_dit_slots_pad", "scldm_dit_mod_pad", "scldm_dit_workspace_bytes", "scldm_dit_workspace_layout",
     "scldm_dit_forward", "scldm_dit_forward_shared_t", "scldm_dit_sample_ode", "scldm_vae_qside", "scldm_vae_decode_workspace_bytes",
     "scldm_vae_decode", "scldm_vae_encode", "scldm_randn_cells", "scldm_csr_count", "scldm_csr_fill", "scldm_tokenize_expressed", "scldm_nb_nll", "scldm_dit_train_workspace_bytes", "scldm_dit_train_forward", "scldm_dit_train_backward", "scldm_adamw_step", "scldm_repack",
-    "scldm_ema_update", "scldm_vae_train_workspace_bytes", "scldm_vae_train_step", "scldm_vae256_qside_workspace_bytes", "scldm_vae256_qside", "scldm_vae256_decode_workspace_bytes", "scldm_vae256_decode",
+    "scldm_ema_update", "scldm_vae_train_workspace_bytes", "scldm_vae_train_step", "scldm_vae_train_backward", "scldm_vae256_qside_workspace_bytes", "scldm_vae256_qside", "scldm_vae256_decode_workspace_bytes", "scldm_vae256_decode",
     "scldm_vae256_encode_workspace_bytes", "scldm_vae256_encode", "scldm_pair_stats", "scldm_sinkhorn", "scldm_sde_drift", "scldm_sde_kick", "scldm_axpy2", "scldm_test_gemm", "scldm_test_nb_invert", "scldm_prof_enable", "scldm_prof_summary", "scldm_debug_timeline", "scldm_set_option", "scldm_get_option", "scldm_launch_count", "scldm_last_error", "scldm_version",
 ]
 
@@ -161,6 +161,9 @@ def load() -> C.CDLL:
                                          C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                          C.c_void_p]
     lib.scldm_vae_train_step.restype = C.c_int
+    lib.scldm_vae_train_backward.argtypes = [P(VaeTrain), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.scldm_vae_train_backward.restype = C.c_int
     lib.scldm_vae256_qside_workspace_bytes.argtypes = [C.c_int32]
     lib.scldm_vae256_qside_workspace_bytes.restype = C.c_size_t
     lib.scldm_vae256_qside.argtypes = [P(Vae256Weights), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]

@@ -958,6 +958,39 @@ __global__ void __launch_bounds__(512) nb_loss_kernel(const NbLossParams p) {
   }
 }
 
+// Autograd bridge: caller-provided dLoss/dmu (and dLoss/dtheta of the expanded theta) -> dLoss/dlogit, d theta table.
+// mu = library * softmax(logit): dlogit = mu dmu - p sum_genes(mu dmu)
+struct MuGradParams {
+  const float* logits; const float* library; const float* theta_tbl; const long long* genes; int G;
+  const float* dmu; const float* dtheta;   // [B][G]; dtheta nullable
+  float* dlogit; float* g_theta;
+};
+__global__ void __launch_bounds__(512) mu_grad_kernel(const MuGradParams p) {
+  __shared__ float red[16];
+  const int b = blockIdx.x;
+  const float* lg = p.logits + (size_t)b * p.G;
+  const float* dm = p.dmu + (size_t)b * p.G;
+  float mx = -1e30f;
+  for (int g = threadIdx.x; g < p.G; g += 512) mx = fmaxf(mx, lg[g]);
+  mx = block_reduce(mx, red, true);
+  float sum = 0.f;
+  for (int g = threadIdx.x; g < p.G; g += 512) sum += __expf(lg[g] - mx);
+  sum = block_reduce(sum, red, false);
+  const float lib = p.library[b], inv = 1.f / sum;
+  float sgm = 0.f;
+  for (int g = threadIdx.x; g < p.G; g += 512) {
+    const float gm = lib * __expf(lg[g] - mx) * inv * dm[g];
+    p.dlogit[(size_t)b * p.G + g] = gm;
+    sgm += gm;
+    if (p.dtheta) {
+      const long long gid = p.genes[g];
+      atomicAdd(p.g_theta + gid, p.dtheta[(size_t)b * p.G + g] * __expf(p.theta_tbl[gid]));
+    }
+  }
+  sgm = block_reduce(sgm, red, false);
+  for (int g = threadIdx.x; g < p.G; g += 512) p.dlogit[(size_t)b * p.G + g] -= __expf(lg[g] - mx) * inv * sgm;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Decoder MCAB on (cell, gene) tokens: forward (logits) and, with BWD, the whole backward of the tile.
 // ---------------------------------------------------------------------------------------------------------------

@@ -157,6 +157,25 @@ class VAETrainer:
         out = {"llh": nll.mean(), "per_cell": nll}
         return (out, z, mu) if want_mu else (out, z)
 
+    def backward_from(self, dmu: torch.Tensor, dtheta: torch.Tensor | None, inputs, *, zero_grads: bool = False) -> None:
+        """Backward of the last forward-only `forward_backward(backward=False)` on `inputs` = (genes, library_size, counts_subset,
+        genes_subset) from dLoss/dmu [B,G] (and dLoss/dtheta [B,G] of the expanded theta): the autograd bridge's backward."""
+        genes, library_size, counts_subset, genes_subset = inputs
+        B, G = dmu.shape
+        S = counts_subset.shape[1]
+        gvec = shared_gene_vector(genes).to(torch.int64).contiguous()
+        cs = counts_subset.contiguous().float()
+        gs = genes_subset.contiguous().to(torch.int64)
+        lib = library_size.reshape(-1).contiguous().float()
+        dmu = dmu.contiguous().float()
+        dth = dtheta.contiguous().float() if dtheta is not None else None
+        ws = self.workspace(B, S, G)
+        with torch.cuda.device(self.device):
+            rc = self.lib.scldm_vae_train_backward(C.byref(self.struct), gs.data_ptr(), cs.data_ptr(), S, gvec.data_ptr(), lib.data_ptr(), dmu.data_ptr(),
+                                                   dth.data_ptr() if dth is not None else None, B, G, int(zero_grads), int(self.exact), ws.data_ptr(),
+                                                   ws.numel(), self._stream())
+        _lib.check(rc, "scldm_vae_train_backward")
+
     def allreduce_grads(self) -> None:
         if self._dist() and self.world > 1:
             torch.distributed.all_reduce(self.grad, group=self.pg)
@@ -183,3 +202,32 @@ class VAETrainer:
         self.allreduce_grads()
         self.optimizer_step()
         return out["llh"]
+
+
+class _VAETrainFunction(torch.autograd.Function):
+    """autograd bridge: `TransformerVAE.forward` in training mode -> `VAETrainer` forward kernels; `loss.backward()` ->
+    `scldm_vae_train_backward`.  Parameter gradients land in the flat buffer (the `p.grad` views), as autograd would leave them."""
+
+    @staticmethod
+    def forward(ctx, anchor, trainer, counts, genes, library_size, counts_subset, genes_subset):
+        ctx.trainer = trainer
+        ctx.inputs = (genes, library_size, counts_subset, genes_subset)
+        _, z, mu = trainer.forward_backward(counts, genes, library_size, counts_subset, genes_subset, backward=False, want_mu=True)
+        gvec = shared_gene_vector(genes).to(torch.int64)
+        theta = torch.exp(trainer.vae.decoder_head.theta.weight.detach()[gvec].squeeze(-1)).unsqueeze(0).expand(mu.shape[0], -1).contiguous()
+        ctx.mark_non_differentiable(z)
+        return mu, theta, z
+
+    @staticmethod
+    def backward(ctx, dmu, dtheta, _dz):
+        ctx.trainer.backward_from(dmu, dtheta, ctx.inputs, zero_grads=False)
+        return (None,) * 7
+
+
+def differentiable_forward(trainer: VAETrainer, counts, genes, library_size, counts_subset, genes_subset):
+    """`TransformerVAE.forward` (`vae.py:29-56`) whose outputs carry a grad_fn: `({"mu", "theta"}, h_z)`; any loss built from mu / theta
+    (`VAE.loss`, `models.py:233-247`) can call `.backward()` - call `trainer.zero_grad()` first, gradients ACCUMULATE like autograd's.
+    h_z is returned detached (the reference's training loss does not use it)."""
+    anchor = torch.zeros((), device=trainer.device, requires_grad=True)   # makes autograd call backward although no input requires grad
+    mu, theta, z = _VAETrainFunction.apply(anchor, trainer, counts, genes, library_size, counts_subset, genes_subset)
+    return {"mu": mu, "theta": theta}, z

@@ -153,3 +153,26 @@ def test_vae_train_agg_variants_vs_oracle():
         out, z = tr.forward_backward(counts, genes, lib, cs, gs)
         assert rel_l2(z, z_o) < 1e-4 and abs(float(out["llh"]) - float(llh_o)) / abs(float(llh_o)) < 1e-5
         assert compare_grads(vae, g_o, 2e-3, agg) < 2e-3
+
+
+def test_vae_autograd_bridge_matches_fused_step():
+    """`loss.backward()` through `differentiable_forward` with the loss written in plain torch (`VAE.loss`) == the fused training step."""
+    from scldm_b200.vae_training import differentiable_forward
+
+    cfg = VAEConfig(n_genes=700, n_layer=1)
+    vae, tr, sd = make_trainer(cfg, True)
+    counts, genes, lib, cs, gs = [a.cuda() for a in vae_train_inputs(cfg, 3, 160)]
+    tr.forward_backward(counts, genes, lib, cs, gs)
+    g_fused = tr.grad.clone()
+    tr.zero_grad()
+    params, h_z = differentiable_forward(tr, counts, genes, lib, cs, gs)
+    assert params["mu"].requires_grad and params["theta"].requires_grad and not h_z.requires_grad
+    loss = (-O.log_nb_positive(counts, params["mu"], params["theta"])).sum(dim=1).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    e = rel_l2(tr.grad, g_fused)
+    print("autograd bridge vs fused step: gradient rel-L2", e, "loss", float(loss))
+    assert e < 1e-4
+    for name, p in vae.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and p.grad.data_ptr() >= tr.grad.data_ptr()      # views of the flat buffer
