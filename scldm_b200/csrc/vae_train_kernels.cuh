@@ -52,10 +52,10 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 // ---------------------------------------------------------------------------------------------------------------
 // y[r][o] (=, +=) sum_k x[r][k] W[o][k]   (W: global, row-major [O][K], K % 4 == 0)
 template <int ADD>
-__device__ __forceinline__ void lin16(const float* x, int ldx, int K, const float* __restrict__ W, int O, float* y, int ldy) {
+__device__ __forceinline__ void lin16(const float* x, int ldx, int K, const float* __restrict__ W, int ldw, int O, float* y, int ldy) {
   for (int idx = threadIdx.x; idx < 16 * O; idx += blockDim.x) {
     const int r = idx / O, o = idx - r * O;
-    const float* w = W + (size_t)o * K;
+    const float* w = W + (size_t)o * ldw;
     const float* xr = x + r * ldx;
     float acc = 0.f;
     for (int k = 0; k < K; k += 4) {
@@ -67,12 +67,12 @@ __device__ __forceinline__ void lin16(const float* x, int ldx, int K, const floa
 }
 // dx[r][k] (=, +=) sum_o dy[r][o] W[o][k]
 template <int ADD>
-__device__ __forceinline__ void lin16_t(const float* dy, int ldy, int O, const float* __restrict__ W, int K, float* dx, int ldx) {
+__device__ __forceinline__ void lin16_t(const float* dy, int ldy, int O, const float* __restrict__ W, int ldw, int K, float* dx, int ldx) {
   for (int idx = threadIdx.x; idx < 16 * K; idx += blockDim.x) {
     const int r = idx / K, k = idx - r * K;
     const float* d = dy + r * ldy;
     float acc = 0.f;
-    for (int o = 0; o < O; ++o) acc += d[o] * W[(size_t)o * K + k];
+    for (int o = 0; o < O; ++o) acc += d[o] * W[(size_t)o * ldw + k];
     if (ADD) dx[r * ldx + k] += acc; else dx[r * ldx + k] = acc;
   }
 }
@@ -208,29 +208,30 @@ __device__ __forceinline__ void attn16_bwd(const float* qkv, const float* P, con
 
 // x <- x + c_proj(silu(w1 LN2(x)) * (w2 LN2(x)))   (SwiGLU MLP of Block / CrossAttentionBlock, layers.py:161-174)
 __device__ __forceinline__ void mlp16_fwd(LatS& s, const float* ln2w, const float* ln2b, const float* w1, const float* w2, const float* w3,
-                                          float eps) {
+                                          int l32, int l88, float eps) {
   ln16(s.x, 32, 32, ln2w, ln2b, eps, s.xn, 32);
   __syncthreads();
-  lin16<0>(s.xn, 32, 32, w1, H, s.u, H);
-  lin16<0>(s.xn, 32, 32, w2, H, s.v, H);
+  lin16<0>(s.xn, 32, 32, w1, l32, H, s.u, H);
+  lin16<0>(s.xn, 32, 32, w2, l32, H, s.v, H);
   __syncthreads();
   for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) { const float a = s.u[i]; s.u[i] = a * sigmoidf_(a) * s.v[i]; }
   __syncthreads();
-  lin16<1>(s.u, H, H, w3, 32, s.x, 32);
+  lin16<1>(s.u, H, H, w3, l88, 32, s.x, 32);
   __syncthreads();
 }
 // backward of the MLP half: xin = its input (LN2 input), s.dx = gradient of its output on entry, of its input on exit
 __device__ __forceinline__ void mlp16_bwd(LatS& s, const float* xin, const float* ln2w, const float* ln2b, const float* w1, const float* w2,
-                                          const float* w3, float* g_ln2w, float* g_ln2b, float* g_w1, float* g_w2, float* g_w3, float eps) {
+                                          const float* w3, int l32, int l88, float* g_ln2w, float* g_ln2b, float* g_w1, float* g_w2, float* g_w3,
+                                          float eps) {
   ln16(xin, 32, 32, ln2w, ln2b, eps, s.xn, 32);
   __syncthreads();
-  lin16<0>(s.xn, 32, 32, w1, H, s.u, H);
-  lin16<0>(s.xn, 32, 32, w2, H, s.v, H);
+  lin16<0>(s.xn, 32, 32, w1, l32, H, s.u, H);
+  lin16<0>(s.xn, 32, 32, w2, l32, H, s.v, H);
   __syncthreads();
   for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) { const float a = s.u[i]; s.hh[i] = a * sigmoidf_(a) * s.v[i]; }
   __syncthreads();
   wgrad_rows(s.dx, 32, 32, s.hh, H, H, 16, g_w3);
-  lin16_t<0>(s.dx, 32, 32, w3, H, s.dhh, H);
+  lin16_t<0>(s.dx, 32, 32, w3, l88, H, s.dhh, H);
   __syncthreads();
   for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) {
     const float a = s.u[i], sg = sigmoidf_(a), dh = s.dhh[i];
@@ -240,47 +241,71 @@ __device__ __forceinline__ void mlp16_bwd(LatS& s, const float* xin, const float
   __syncthreads();
   wgrad_rows(s.u, H, H, s.xn, 32, 32, 16, g_w1);
   wgrad_rows(s.v, H, H, s.xn, 32, 32, 16, g_w2);
-  lin16_t<0>(s.u, H, H, w1, 32, s.dao, 32);
+  lin16_t<0>(s.u, H, H, w1, l32, 32, s.dao, 32);
   __syncthreads();
-  lin16_t<1>(s.v, H, H, w2, 32, s.dao, 32);
+  lin16_t<1>(s.v, H, H, w2, l32, 32, s.dao, 32);
   __syncthreads();
   ln16_bwd<1>(s.dao, 32, xin, 32, 32, ln2w, eps, s.dx, 32, g_ln2w, g_ln2b);
   __syncthreads();
 }
 
-__device__ __forceinline__ void block16_fwd(LatS& s, const float* bp, float eps) {
-  ln16(s.x, 32, 32, bp + B_LN1W, bp + B_LN1B, eps, s.xn, 32);
+// A Block's weights staged in shared memory with padded rows (16-byte row reads of 32 different rows are then conflict-free per
+// quarter warp): one bulk of coalesced L2 reads per block instead of latency-bound weight reads inside every small GEMM
+constexpr int SLD32 = 36, SLD88 = 92;
+constexpr int S_LN1W = 0, S_LN1B = 32, S_CATTN = 64, S_CPROJ = S_CATTN + 96 * SLD32, S_LN2W = S_CPROJ + 32 * SLD32, S_LN2B = S_LN2W + 32,
+              S_W1 = S_LN2B + 32, S_W2 = S_W1 + H * SLD32, S_W3 = S_W2 + H * SLD32, S_SIZE = S_W3 + 32 * SLD88;
+__device__ __forceinline__ void stage_block(const float* __restrict__ bp, float* sw) {
+  for (int i = threadIdx.x; i < B_SIZE / 4; i += blockDim.x) {
+    const int e = i * 4;
+    const float4 v = *reinterpret_cast<const float4*>(bp + e);
+    int dst;
+    if (e < B_CATTN) dst = e;                                                                   // ln_1 weight | bias
+    else if (e < B_CPROJ) dst = S_CATTN + ((e - B_CATTN) >> 5) * SLD32 + ((e - B_CATTN) & 31);
+    else if (e < B_LN2W) dst = S_CPROJ + ((e - B_CPROJ) >> 5) * SLD32 + ((e - B_CPROJ) & 31);
+    else if (e < B_W1) dst = S_LN2W + (e - B_LN2W);
+    else if (e < B_W2) dst = S_W1 + ((e - B_W1) >> 5) * SLD32 + ((e - B_W1) & 31);
+    else if (e < B_W3) dst = S_W2 + ((e - B_W2) >> 5) * SLD32 + ((e - B_W2) & 31);
+    else dst = S_W3 + ((e - B_W3) / H) * SLD88 + ((e - B_W3) % H);
+    *reinterpret_cast<float4*>(sw + dst) = v;
+  }
   __syncthreads();
-  lin16<0>(s.xn, 32, 32, bp + B_CATTN, 96, s.qkv, 96);
+}
+__device__ __forceinline__ void block16_fwd(LatS& s, const float* bp, float* sw, float eps) {
+  stage_block(bp, sw);
+  ln16(s.x, 32, 32, sw + S_LN1W, sw + S_LN1B, eps, s.xn, 32);
+  __syncthreads();
+  lin16<0>(s.xn, 32, 32, sw + S_CATTN, SLD32, 96, s.qkv, 96);
   __syncthreads();
   attn16_fwd(s.qkv, s.ao, nullptr);
   __syncthreads();
-  lin16<1>(s.ao, 32, 32, bp + B_CPROJ, 32, s.x, 32);
+  lin16<1>(s.ao, 32, 32, sw + S_CPROJ, SLD32, 32, s.x, 32);
   __syncthreads();
-  mlp16_fwd(s, bp + B_LN2W, bp + B_LN2B, bp + B_W1, bp + B_W2, bp + B_W3, eps);
+  mlp16_fwd(s, sw + S_LN2W, sw + S_LN2B, sw + S_W1, sw + S_W2, sw + S_W3, SLD32, SLD88, eps);
 }
 // s.x = the block's input, s.dx = gradient of its output -> s.dx = gradient of its input; weight gradients into gp
-__device__ __forceinline__ void block16_bwd(LatS& s, const float* bp, float* gp, float eps) {
-  ln16(s.x, 32, 32, bp + B_LN1W, bp + B_LN1B, eps, s.xn, 32);
+__device__ __forceinline__ void block16_bwd(LatS& s, const float* bp, float* sw, float* gp, float eps) {
+  stage_block(bp, sw);
+  ln16(s.x, 32, 32, sw + S_LN1W, sw + S_LN1B, eps, s.xn, 32);
   for (int i = threadIdx.x; i < 512; i += blockDim.x) s.xm[i] = s.x[i];
   __syncthreads();
-  lin16<0>(s.xn, 32, 32, bp + B_CATTN, 96, s.qkv, 96);
+  lin16<0>(s.xn, 32, 32, sw + S_CATTN, SLD32, 96, s.qkv, 96);
   __syncthreads();
   attn16_fwd(s.qkv, s.ao, s.P);
   __syncthreads();
-  lin16<1>(s.ao, 32, 32, bp + B_CPROJ, 32, s.xm, 32);   // xm = x + attention
+  lin16<1>(s.ao, 32, 32, sw + S_CPROJ, SLD32, 32, s.xm, 32);   // xm = x + attention
   __syncthreads();
-  mlp16_bwd(s, s.xm, bp + B_LN2W, bp + B_LN2B, bp + B_W1, bp + B_W2, bp + B_W3, gp + B_LN2W, gp + B_LN2B, gp + B_W1, gp + B_W2, gp + B_W3, eps);
+  mlp16_bwd(s, s.xm, sw + S_LN2W, sw + S_LN2B, sw + S_W1, sw + S_W2, sw + S_W3, SLD32, SLD88, gp + B_LN2W, gp + B_LN2B, gp + B_W1, gp + B_W2,
+            gp + B_W3, eps);
   // s.dx = d xm.  attention half (s.xn was overwritten by the MLP's LN2 output: recompute LN1)
-  ln16(s.x, 32, 32, bp + B_LN1W, bp + B_LN1B, eps, s.xn, 32);
+  ln16(s.x, 32, 32, sw + S_LN1W, sw + S_LN1B, eps, s.xn, 32);
   wgrad_rows(s.dx, 32, 32, s.ao, 32, 32, 16, gp + B_CPROJ);
-  lin16_t<0>(s.dx, 32, 32, bp + B_CPROJ, 32, s.dao, 32);
+  lin16_t<0>(s.dx, 32, 32, sw + S_CPROJ, SLD32, 32, s.dao, 32);
   __syncthreads();
   attn16_bwd(s.qkv, s.P, s.dao, s.dS, s.dt);
   wgrad_rows(s.dt, 96, 96, s.xn, 32, 32, 16, gp + B_CATTN);
-  lin16_t<0>(s.dt, 96, 96, bp + B_CATTN, 32, s.dao, 32);
+  lin16_t<0>(s.dt, 96, 96, sw + S_CATTN, SLD32, 32, s.dao, 32);
   __syncthreads();
-  ln16_bwd<1>(s.dao, 32, s.x, 32, 32, bp + B_LN1W, eps, s.dx, 32, gp + B_LN1W, gp + B_LN1B);
+  ln16_bwd<1>(s.dao, 32, s.x, 32, 32, sw + S_LN1W, eps, s.dx, 32, gp + B_LN1W, gp + B_LN1B);
   __syncthreads();
 }
 
@@ -312,23 +337,24 @@ __device__ __forceinline__ void tile_store(float* __restrict__ dst, const float*
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatParams p) {
   extern __shared__ float4 lat_smem4[];
   LatS& s = *reinterpret_cast<LatS*>(lat_smem4);
+  float* sw = reinterpret_cast<float*>(lat_smem4) + sizeof(LatS) / 4;
   const int b = blockIdx.x;
   const size_t cell = (size_t)b * 512, lay = (size_t)p.B * 512;
   const float* eca = p.params + p.enc_ca;
   tile_load(s.ao, p.ao_enc + cell, 512);
   tile_load(s.x, p.params + p.inducing, 512);
   __syncthreads();
-  lin16<1>(s.ao, 32, 32, eca + C_CPROJ, 32, s.x, 32);   // x1 = q + attention (the residual is the raw query, layers.py:327)
+  lin16<1>(s.ao, 32, 32, eca + C_CPROJ, 32, 32, s.x, 32);   // x1 = q + attention (the residual is the raw query, layers.py:327)
   __syncthreads();
   tile_store(p.x1_enc + cell, s.x, 512);
-  mlp16_fwd(s, eca + C_LN2W, eca + C_LN2B, eca + C_W1, eca + C_W2, eca + C_W3, p.eps);
+  mlp16_fwd(s, eca + C_LN2W, eca + C_LN2B, eca + C_W1, eca + C_W2, eca + C_W3, 32, H, p.eps);
   if (p.pos) { for (int i = threadIdx.x; i < 512; i += blockDim.x) s.x[i] += p.pos[i]; __syncthreads(); }
   tile_store(p.xe + cell, s.x, 512);
   for (int l = 0; l < p.n_layer; ++l) {
-    block16_fwd(s, p.params + p.enc_blocks + (size_t)l * B_SIZE, p.eps);
+    block16_fwd(s, p.params + p.enc_blocks + (size_t)l * B_SIZE, sw, p.eps);
     tile_store(p.xe + (size_t)(l + 1) * lay + cell, s.x, 512);
   }
-  lin16<0>(s.x, 32, 32, p.params + p.enc_lat, LAT, s.ao, LAT);
+  lin16<0>(s.x, 32, 32, p.params + p.enc_lat, 32, LAT, s.ao, LAT);
   __syncthreads();
   tile_store(p.hlat + (size_t)b * 256, s.ao, 256);
   ln16(s.ao, LAT, LAT, nullptr, nullptr, p.eps, s.xn, LAT);
@@ -336,17 +362,17 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatParams p) {
   tile_store(p.z + (size_t)b * 256, s.xn, 256);
   ln16(s.xn, LAT, LAT, nullptr, nullptr, p.eps, s.ao, LAT);     // the decoder normalises the latents again (nnets.py:203)
   __syncthreads();
-  lin16<0>(s.ao, LAT, LAT, p.params + p.dec_lat, 32, s.x, 32);
+  lin16<0>(s.ao, LAT, LAT, p.params + p.dec_lat, LAT, 32, s.x, 32);
   __syncthreads();
   tile_store(p.xd + cell, s.x, 512);
   for (int l = 0; l < p.n_layer; ++l) {
-    block16_fwd(s, p.params + p.dec_blocks + (size_t)l * B_SIZE, p.eps);
+    block16_fwd(s, p.params + p.dec_blocks + (size_t)l * B_SIZE, sw, p.eps);
     tile_store(p.xd + (size_t)(l + 1) * lay + cell, s.x, 512);
   }
   const float* dca = p.params + p.dec_ca;
   ln16(s.x, 32, 32, dca + C_LN1W, dca + C_LN1B, p.eps, s.xn, 32);
   __syncthreads();
-  lin16<0>(s.xn, 32, 32, dca + C_CATTN, 64, s.qkv, 64);   // k first, then v (layers.py:252)
+  lin16<0>(s.xn, 32, 32, dca + C_CATTN, 32, 64, s.qkv, 64);   // k first, then v (layers.py:252)
   __syncthreads();
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     const int j = i >> 5, c = i & 31;
@@ -358,6 +384,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatParams p) {
 __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatParams p) {
   extern __shared__ float4 lat_smem4[];
   LatS& s = *reinterpret_cast<LatS*>(lat_smem4);
+  float* sw = reinterpret_cast<float*>(lat_smem4) + sizeof(LatS) / 4;
   const int b = blockIdx.x;
   const size_t cell = (size_t)b * 512, lay = (size_t)p.B * 512;
   const float* dca = p.params + p.dec_ca;
@@ -373,14 +400,14 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatParams p) {
   ln16(s.x, 32, 32, dca + C_LN1W, dca + C_LN1B, p.eps, s.xn, 32);
   __syncthreads();
   wgrad_rows(s.dt, 64, 64, s.xn, 32, 32, 16, gdca + C_CATTN);
-  lin16_t<0>(s.dt, 64, 64, dca + C_CATTN, 32, s.dao, 32);
+  lin16_t<0>(s.dt, 64, 64, dca + C_CATTN, 32, 32, s.dao, 32);
   __syncthreads();
   ln16_bwd<0>(s.dao, 32, s.x, 32, 32, dca + C_LN1W, p.eps, s.dx, 32, gdca + C_LN1W, gdca + C_LN1B);
   __syncthreads();
   for (int l = p.n_layer - 1; l >= 0; --l) {
     tile_load(s.x, p.xd + (size_t)l * lay + cell, 512);
     __syncthreads();
-    block16_bwd(s, p.params + p.dec_blocks + (size_t)l * B_SIZE, p.grads + p.dec_blocks + (size_t)l * B_SIZE, p.eps);
+    block16_bwd(s, p.params + p.dec_blocks + (size_t)l * B_SIZE, sw, p.grads + p.dec_blocks + (size_t)l * B_SIZE, p.eps);
   }
   // decoder front: x0 = W_d LN(z)
   tile_load(s.qkv, p.z + (size_t)b * 256, 256);                 // z
@@ -388,7 +415,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatParams p) {
   ln16(s.qkv, LAT, LAT, nullptr, nullptr, p.eps, s.qkv + 256, LAT);   // LN(z)
   __syncthreads();
   wgrad_rows(s.dx, 32, 32, s.qkv + 256, LAT, LAT, 16, p.grads + p.dec_lat);
-  lin16_t<0>(s.dx, 32, 32, p.params + p.dec_lat, LAT, s.qkv + 512, LAT);   // d LN(z)
+  lin16_t<0>(s.dx, 32, 32, p.params + p.dec_lat, LAT, LAT, s.qkv + 512, LAT);   // d LN(z)
   __syncthreads();
   ln16_bwd<0>(s.qkv + 512, LAT, s.qkv, LAT, LAT, nullptr, p.eps, s.qkv + 768, LAT, nullptr, nullptr);   // dz
   tile_load(s.ao, p.hlat + (size_t)b * 256, 256);
@@ -397,25 +424,25 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatParams p) {
   tile_load(s.x, p.xe + (size_t)p.n_layer * lay + cell, 512);
   __syncthreads();
   wgrad_rows(s.qkv + 1024, LAT, LAT, s.x, 32, 32, 16, p.grads + p.enc_lat);
-  lin16_t<0>(s.qkv + 1024, LAT, LAT, p.params + p.enc_lat, 32, s.dx, 32);
+  lin16_t<0>(s.qkv + 1024, LAT, LAT, p.params + p.enc_lat, 32, 32, s.dx, 32);
   __syncthreads();
   for (int l = p.n_layer - 1; l >= 0; --l) {
     tile_load(s.x, p.xe + (size_t)l * lay + cell, 512);
     __syncthreads();
-    block16_bwd(s, p.params + p.enc_blocks + (size_t)l * B_SIZE, p.grads + p.enc_blocks + (size_t)l * B_SIZE, p.eps);
+    block16_bwd(s, p.params + p.enc_blocks + (size_t)l * B_SIZE, sw, p.grads + p.enc_blocks + (size_t)l * B_SIZE, p.eps);
   }
   // encoder MCAB tail: x2 = x1 + MLP(LN2(x1)), x1 = inducing + c_proj(ao)
   const float* eca = p.params + p.enc_ca;
   float* geca = p.grads + p.enc_ca;
   tile_load(s.xm, p.x1_enc + cell, 512);
   __syncthreads();
-  mlp16_bwd(s, s.xm, eca + C_LN2W, eca + C_LN2B, eca + C_W1, eca + C_W2, eca + C_W3, geca + C_LN2W, geca + C_LN2B, geca + C_W1, geca + C_W2,
+  mlp16_bwd(s, s.xm, eca + C_LN2W, eca + C_LN2B, eca + C_W1, eca + C_W2, eca + C_W3, 32, H, geca + C_LN2W, geca + C_LN2B, geca + C_W1, geca + C_W2,
             geca + C_W3, p.eps);
   for (int i = threadIdx.x; i < 512; i += blockDim.x) atomicAdd(p.grads + p.inducing + i, s.dx[i]);
   tile_load(s.ao, p.ao_enc + cell, 512);
   __syncthreads();
   wgrad_rows(s.dx, 32, 32, s.ao, 32, 32, 16, geca + C_CPROJ);
-  lin16_t<0>(s.dx, 32, 32, eca + C_CPROJ, 32, s.dao, 32);
+  lin16_t<0>(s.dx, 32, 32, eca + C_CPROJ, 32, 32, s.dao, 32);
   __syncthreads();
   tile_store(p.dao_enc + cell, s.dao, 512);
 }
@@ -1199,15 +1226,28 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
     }
     __syncthreads();
     if (!BWD) {
-      // (6) x2 = x1 + mlp.c_proj(h) and this warp's part of the head dot product
+      // (6) x2 = x1 + mlp.c_proj(h), folded straight into the head dot product: warp (row tile, column half, K half of the 88 hidden
+      //     units) leaves its share of sum_c w_head[c] x2[c] in one of four slots per token
       {
-        float acc[1][4] = {};
-        warp_gemm<EXACT, 1, 11>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nq * 8) * LD88, 1, LD88, 1, 8);
-        const float* x1 = sX1 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
-        const float w0 = sWh[nq * 8 + 2 * t], w1 = sWh[nq * 8 + 2 * t + 1];
-        const float lo = quad_sum((x1[0] + acc[0][0]) * w0 + (x1[1] + acc[0][1]) * w1);
-        const float hi = quad_sum((x1[8 * LD32] + acc[0][2]) * w0 + (x1[8 * LD32 + 1] + acc[0][3]) * w1);
-        if (t == 0) { sLog[nq * DT + mt * 16 + g] = lo; sLog[nq * DT + mt * 16 + g + 8] = hi; }
+        const int nh2 = (warp >> 1) & 1, kh = warp >> 2;
+        float acc[2][4] = {};
+        if (kh == 0) warp_gemm<EXACT, 2, 6>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nh2 * 16) * LD88, 1, LD88, 2, 8);
+        else warp_gemm<EXACT, 2, 5>(acc, sH + mt * 16 * LD88 + 48, LD88, 1, sW3 + (nh2 * 16) * LD88 + 48, 1, LD88, 2, 8);
+        float lo = 0.f, hi = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int col = nh2 * 16 + i * 8 + 2 * t;
+          const float w0 = sWh[col], w1 = sWh[col + 1];
+          float x00 = acc[i][0], x01 = acc[i][1], x10 = acc[i][2], x11 = acc[i][3];
+          if (kh == 0) {
+            const float* x1 = sX1 + (mt * 16 + g) * LD32 + col;
+            x00 += x1[0]; x01 += x1[1]; x10 += x1[8 * LD32]; x11 += x1[8 * LD32 + 1];
+          }
+          lo += x00 * w0 + x01 * w1;
+          hi += x10 * w0 + x11 * w1;
+        }
+        lo = quad_sum(lo); hi = quad_sum(hi);
+        if (t == 0) { sLog[(nh2 * 2 + kh) * DT + mt * 16 + g] = lo; sLog[(nh2 * 2 + kh) * DT + mt * 16 + g + 8] = hi; }
       }
       __syncthreads();
       // (7) head logit
