@@ -461,6 +461,24 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 template <bool EXACT>
 __device__ __forceinline__ float rt(float x) { return EXACT ? x : __uint_as_float(to_tf32(x)); }
 
+// one m16n8k8 product on fp32 fragments (TF32, or 3 x TF32 when EXACT)
+template <bool EXACT>
+__device__ __forceinline__ void mma_f(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+  uint32_t ah[4], bh[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ah[i] = EXACT ? to_tf32(a[i]) : __float_as_uint(a[i]);
+  bh[0] = EXACT ? to_tf32(b[0]) : __float_as_uint(b[0]); bh[1] = EXACT ? to_tf32(b[1]) : __float_as_uint(b[1]);
+  if (EXACT) {
+    uint32_t al[4], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) al[i] = to_tf32(a[i] - __uint_as_float(ah[i]));
+    bl[0] = to_tf32(b[0] - __uint_as_float(bh[0])); bl[1] = to_tf32(b[1] - __uint_as_float(bh[1]));
+    mma_tf32(c, al, bh);
+    mma_tf32(c, ah, bl);
+  }
+  mma_tf32(c, ah, bh);
+}
+
 // acc[i] (16 x 8 tile i) += A[16 x 8 KS] * B[8 KS x 8] for `nt` column tiles; element strides: A(r, k) = A[r sar + k sac],
 // B(k, n) = Bm[k sbr + n sbc]; column tile i starts at n = i * nstep.  EXACT: 3 x TF32 (hi / lo split), fp32-grade products.
 template <bool EXACT, int NT, int KS>
@@ -770,7 +788,9 @@ struct EncBwdParams {
   float* g_emb;              // gradient of the embedding table
 };
 constexpr int ELD64 = 68, ELD32 = 40;   // row strides of the 64- / 32-wide token tiles
-constexpr int ENC_BWD_SMEM_FLOATS = 128 * ELD64 + 128 * ELD32 + 128 * ELD64 + 128 * ELD32 + 512 * 2 + 64 + 64 * ELD32 + 64;
+constexpr int ENC_TILES_PER_CTA = 8;
+constexpr int EQ = 36;                  // row stride of the 16 x 32 query / dAO tiles (conflict-free B-fragment reads)
+constexpr int ENC_BWD_SMEM_FLOATS = 128 * ELD64 + 128 * ELD32 + 128 * ELD64 + 128 * ELD32 + 16 * EQ * 2 + 64 + 64 + 64 * ELD32 + 64;
 template <bool EXACT>
 __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams p) {
   extern __shared__ float4 enc_smem4[];
@@ -779,15 +799,18 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
   float* tXN = tDKV + 128 * ELD64;      // [128][40]  LN1 output
   float* tDS = tXN + 128 * ELD32;       // [128][68]  dS[(query, head)] of the tile's tokens (scaled)
   float* tK = tDS + 128 * ELD64;        // [128][40]
-  float* sQ = tK + 128 * ELD32;         // [16][32] scaled queries
-  float* sDAO = sQ + 512;               // [16][32]
-  float* sD = sDAO + 512;               // [64] rowsum(dAO * AO) per (query, head)
-  float* sW = sD + 64;                  // c_attn [64][32]
+  float* sQ = tK + 128 * ELD32;         // [16][36] scaled queries
+  float* sDAO = sQ + 16 * EQ;           // [16][36]
+  float* sD = sDAO + 16 * EQ;           // [64] rowsum(dAO * AO) per (query, head)
+  float* sLse = sD + 64;                // [64] log-sum-exp of the pooling softmax per (query, head)
+  float* sW = sLse + 64;                // c_attn [64][40]
+  float* tV = tXN;                      // values of the tile: dead before the LN1 output is written
   float* sLn = sW + 64 * ELD32;         // ln_1 weight | bias
-  const int b = blockIdx.y, s = blockIdx.x * 128 + threadIdx.x;
-  const bool valid = s < p.S;
-  const long long tk = (long long)b * p.S + (valid ? s : 0);
-  for (int i = threadIdx.x; i < 512; i += 128) { sQ[i] = p.Q[i] * 0.35355339059327373f; sDAO[i] = p.dAO[(size_t)b * 512 + i]; }
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 512; i += 128) {
+    sQ[(i >> 5) * EQ + (i & 31)] = rt<EXACT>(p.Q[i] * 0.35355339059327373f);
+    sDAO[(i >> 5) * EQ + (i & 31)] = rt<EXACT>(p.dAO[(size_t)b * 512 + i]);
+  }
   for (int i = threadIdx.x; i < 2048; i += 128) sW[(i >> 5) * ELD32 + (i & 31)] = rt<EXACT>(p.ca[C_CATTN + i]);
   if (threadIdx.x < 64) sLn[threadIdx.x] = p.ca[C_LN1W + threadIdx.x];   // ln_1.weight, ln_1.bias are adjacent
   if (threadIdx.x < 64) {
@@ -795,36 +818,79 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
     float a = 0.f;
     for (int d = 0; d < 8; ++d) a += p.dAO[(size_t)b * 512 + m * 32 + h * 8 + d] * p.AO[(size_t)b * 512 + m * 32 + h * 8 + d];
     sD[threadIdx.x] = a;
+    sLse[threadIdx.x] = p.lse[b * 64 + threadIdx.x];
   }
-  __syncthreads();
-  float kk[32], vv[32], dk[32], dv[32];
+  // A CTA walks ENC_TILES_PER_CTA consecutive 128-token tiles of its cell; the gradients that are sums over tokens (c_attn, dQ, ln_1)
+  // accumulate in registers across the tiles and reach global memory once per CTA (8 x fewer same-address atomics)
+  const int warp = threadIdx.x >> 5;
+  float acc_w[4][4] = {}, acc_q[1][4] = {}, acc_ln = 0.f;
+  const int n_tiles = (p.S + 127) / 128;
+  for (int tile = blockIdx.x * ENC_TILES_PER_CTA; tile < min(n_tiles, (blockIdx.x + 1) * ENC_TILES_PER_CTA); ++tile) {
+  const int s = tile * 128 + threadIdx.x;
+  const bool valid = s < p.S;
+  const long long tk = (long long)b * p.S + (valid ? s : 0);
+  float kk[32];
+  // the tile's keys / values into shared memory (one token row per thread; rows beyond S are zero and masked below)
 #pragma unroll
   for (int k = 0; k < 32; k += 4) {
     const float4 a = *reinterpret_cast<const float4*>(p.K + tk * 32 + k), c = *reinterpret_cast<const float4*>(p.V + tk * 32 + k);
-    kk[k] = a.x; kk[k + 1] = a.y; kk[k + 2] = a.z; kk[k + 3] = a.w;
-    vv[k] = c.x; vv[k + 1] = c.y; vv[k + 2] = c.z; vv[k + 3] = c.w;
-    dk[k] = dk[k + 1] = dk[k + 2] = dk[k + 3] = 0.f;
-    dv[k] = dv[k + 1] = dv[k + 2] = dv[k + 3] = 0.f;
+    float* dk_ = tK + threadIdx.x * ELD32 + k;
+    float* dv_ = tV + threadIdx.x * ELD32 + k;
+    dk_[0] = valid ? rt<EXACT>(a.x) : 0.f; dk_[1] = valid ? rt<EXACT>(a.y) : 0.f; dk_[2] = valid ? rt<EXACT>(a.z) : 0.f; dk_[3] = valid ? rt<EXACT>(a.w) : 0.f;
+    dv_[0] = valid ? rt<EXACT>(c.x) : 0.f; dv_[1] = valid ? rt<EXACT>(c.y) : 0.f; dv_[2] = valid ? rt<EXACT>(c.z) : 0.f; dv_[3] = valid ? rt<EXACT>(c.w) : 0.f;
   }
-  const float* lse = p.lse + b * 64;
+  __syncthreads();
+  // Attention backward of the tile on mma.sync, warp w = tokens 32 w .. 32 w + 31 (two row tiles), per head:
+  //   S^T = K_h Q_h^T (16 tokens x 16 queries), P = exp(S - lse), dP^T = V_h dAO_h^T, dS = P (dP - D);
+  //   dK_h = dS Q_h, dV_h = P dAO_h (the accumulator fragments feed the A operand through the permuted contraction order)
+  {
+    const int warp_ = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll 1
-  for (int m = 0; m < 16; ++m) {
+    for (int mtile = 0; mtile < 2; ++mtile) {
+      const int r0 = warp_ * 32 + mtile * 16;
+      const bool v_lo = tile * 128 + r0 + g < p.S, v_hi = tile * 128 + r0 + g + 8 < p.S;
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      // the query / dAO rows are the same for every thread: four broadcast 16-byte reads per (query, head)
-      const float4 qa = *reinterpret_cast<const float4*>(sQ + m * 32 + h * 8), qb = *reinterpret_cast<const float4*>(sQ + m * 32 + h * 8 + 4);
-      const float4 ga = *reinterpret_cast<const float4*>(sDAO + m * 32 + h * 8), gb = *reinterpret_cast<const float4*>(sDAO + m * 32 + h * 8 + 4);
-      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w}, gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-      float sc = 0.f, dp = 0.f;
+      for (int h = 0; h < 4; ++h) {
+        const float* kr = tK + r0 * ELD32 + h * 8;
+        const float* vr = tV + r0 * ELD32 + h * 8;
+        const float ak[4] = {kr[g * ELD32 + t], kr[(g + 8) * ELD32 + t], kr[g * ELD32 + t + 4], kr[(g + 8) * ELD32 + t + 4]};
+        const float av[4] = {vr[g * ELD32 + t], vr[(g + 8) * ELD32 + t], vr[g * ELD32 + t + 4], vr[(g + 8) * ELD32 + t + 4]};
+        float pr[2][4], ds[2][4];
 #pragma unroll
-      for (int d = 0; d < 8; ++d) { sc += qv[d] * kk[h * 8 + d]; dp += gv[d] * vv[h * 8 + d]; }
-      const float pr = valid ? __expf(sc - lse[m * 4 + h]) : 0.f;
-      const float ds = pr * (dp - sD[m * 4 + h]);
-      tDS[threadIdx.x * ELD64 + m * 4 + h] = rt<EXACT>(ds * 0.35355339059327373f);
+        for (int n = 0; n < 2; ++n) {
+          const float bq[2] = {sQ[(8 * n + g) * EQ + h * 8 + t], sQ[(8 * n + g) * EQ + h * 8 + t + 4]};
+          const float bd[2] = {sDAO[(8 * n + g) * EQ + h * 8 + t], sDAO[(8 * n + g) * EQ + h * 8 + t + 4]};
+          pr[n][0] = pr[n][1] = pr[n][2] = pr[n][3] = 0.f;
+          ds[n][0] = ds[n][1] = ds[n][2] = ds[n][3] = 0.f;
+          mma_f<EXACT>(pr[n], ak, bq);      // scores (the queries carry the 1 / sqrt(head_dim))
+          mma_f<EXACT>(ds[n], av, bd);      // dP
 #pragma unroll
-      for (int d = 0; d < 8; ++d) { dk[h * 8 + d] += ds * qv[d]; dv[h * 8 + d] += pr * gv[d]; }
+          for (int e = 0; e < 4; ++e) {
+            const int m = 8 * n + 2 * t + (e & 1);
+            const float pe = ((e >> 1) ? v_hi : v_lo) ? __expf(pr[n][e] - sLse[m * 4 + h]) : 0.f;
+            const float de = pe * (ds[n][e] - sD[m * 4 + h]);
+            pr[n][e] = pe;
+            ds[n][e] = de;
+            tDS[(r0 + g + (e >> 1) * 8) * ELD64 + m * 4 + h] = rt<EXACT>(de * 0.35355339059327373f);
+          }
+        }
+        float dk4[4] = {0.f, 0.f, 0.f, 0.f}, dv4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const float a1[4] = {rt<EXACT>(ds[ks][0]), rt<EXACT>(ds[ks][2]), rt<EXACT>(ds[ks][1]), rt<EXACT>(ds[ks][3])};
+          const float a2[4] = {rt<EXACT>(pr[ks][0]), rt<EXACT>(pr[ks][2]), rt<EXACT>(pr[ks][1]), rt<EXACT>(pr[ks][3])};
+          const float b1[2] = {sQ[(8 * ks + 2 * t) * EQ + h * 8 + g], sQ[(8 * ks + 2 * t + 1) * EQ + h * 8 + g]};
+          const float b2[2] = {sDAO[(8 * ks + 2 * t) * EQ + h * 8 + g], sDAO[(8 * ks + 2 * t + 1) * EQ + h * 8 + g]};
+          mma_f<EXACT>(dk4, a1, b1);
+          mma_f<EXACT>(dv4, a2, b2);
+        }
+        float* o = tDKV + (r0 + g) * ELD64 + h * 8 + 2 * t;
+        o[0] = rt<EXACT>(dk4[0]); o[1] = rt<EXACT>(dk4[1]); o[8 * ELD64] = rt<EXACT>(dk4[2]); o[8 * ELD64 + 1] = rt<EXACT>(dk4[3]);
+        o[32] = rt<EXACT>(dv4[0]); o[33] = rt<EXACT>(dv4[1]); o[8 * ELD64 + 32] = rt<EXACT>(dv4[2]); o[8 * ELD64 + 33] = rt<EXACT>(dv4[3]);
+      }
     }
   }
+  __syncthreads();    // every warp is done with the value tile before the LN1 output overwrites it
   // token side: recompute x, LN1
   const float cnt = valid ? p.counts[tk] : 0.f;
   const float f = vae::count_scale(cnt, p.agg);
@@ -837,30 +903,12 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
     xh[k] = (v.x * f - mean) * rstd; xh[k + 1] = (v.y * f - mean) * rstd; xh[k + 2] = (v.z * f - mean) * rstd; xh[k + 3] = (v.w * f - mean) * rstd;
   }
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    tDKV[threadIdx.x * ELD64 + k] = rt<EXACT>(dk[k]);
-    tDKV[threadIdx.x * ELD64 + 32 + k] = rt<EXACT>(dv[k]);
-    tXN[threadIdx.x * ELD32 + k] = valid ? rt<EXACT>(xh[k] * sLn[k] + sLn[32 + k]) : 0.f;
-    tK[threadIdx.x * ELD32 + k] = valid ? rt<EXACT>(kk[k]) : 0.f;
-  }
+  for (int k = 0; k < 32; ++k) tXN[threadIdx.x * ELD32 + k] = valid ? rt<EXACT>(xh[k] * sLn[k] + sLn[32 + k]) : 0.f;
   __syncthreads();
   // c_attn weight gradient (64 x 32 = dKV^T xn over the 128 tokens) and dQ (per head 16 queries x 8 = dS_h^T K_h) on mma.sync:
   // warp w owns weight rows 16 w .. 16 w + 15 and head w
-  const int warp = threadIdx.x >> 5;
-  {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    float acc[4][4] = {};
-    warp_gemm<EXACT, 4, 16>(acc, tDKV + warp * 16, 1, ELD64, tXN, ELD32, 1, 4, 8);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) atomicAdd(p.gca + C_CATTN + (warp * 16 + g + (e >> 1) * 8) * 32 + i * 8 + 2 * t + (e & 1), acc[i][e]);
-    }
-    float aq[1][4] = {};
-    warp_gemm<EXACT, 1, 16>(aq, tDS + warp, 4, ELD64, tK + warp * 8, ELD32, 1, 1, 8);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) atomicAdd(p.dQ + (g + (e >> 1) * 8) * 32 + warp * 8 + 2 * t + (e & 1), aq[0][e]);
-  }
+  warp_gemm<EXACT, 4, 16>(acc_w, tDKV + warp * 16, 1, ELD64, tXN, ELD32, 1, 4, 8);
+  warp_gemm<EXACT, 1, 16>(acc_q, tDS + warp, 4, ELD64, tK + warp * 8, ELD32, 1, 1, 8);
   __syncthreads();
   // d(LN1 output)[token][32] = [dk | dv] Wkv on mma.sync: warp w computes the rows of its own 32 tokens into the (now dead) dS tile
   {
@@ -882,7 +930,7 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     const float a = tDS[threadIdx.x * ELD64 + k];
-    kk[k] = a;   // gradient w.r.t. the LN1 output (the key registers are dead: they live in tK)
+    kk[k] = a;   // gradient w.r.t. the LN1 output
     g[k] = a * sLn[k];
     m1 += g[k];
     m2 += g[k] * xh[k];
@@ -908,7 +956,20 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
     const float* t = threadIdx.x < 32 ? tXN : tK;
     float a = 0.f;
     for (int i = 0; i < 128; ++i) a += t[i * ELD32 + k];
-    atomicAdd(p.gca + (threadIdx.x < 32 ? C_LN1W : C_LN1B) + k, a);
+    acc_ln += a;
+  }
+  __syncthreads();     // the tiles are rewritten by the next trip
+  }
+  {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(p.gca + C_CATTN + (warp * 16 + g + (e >> 1) * 8) * 32 + i * 8 + 2 * t + (e & 1), acc_w[i][e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) atomicAdd(p.dQ + (g + (e >> 1) * 8) * 32 + warp * 8 + 2 * t + (e & 1), acc_q[0][e]);
+    if (threadIdx.x < 64) atomicAdd(p.gca + (threadIdx.x < 32 ? C_LN1W : C_LN1B) + (threadIdx.x & 31), acc_ln);
   }
 }
 
@@ -1036,24 +1097,6 @@ struct DecTrainParams {
 constexpr int DT = 32, LD32 = 36, LD88 = 100, LDK = 36;
 // 6 32-wide tiles + du / dv (h in the forward-only kernel) + keys / values + small vectors + the block's weights: 103 KB, 2 CTAs per SM
 constexpr int DEC_SMEM_FLOATS = 6 * DT * LD32 + 2 * DT * LD88 + 2 * 16 * LDK + 2 * DT + DT + 4 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96 + 96;
-
-// one m16n8k8 product on fp32 fragments (TF32, or 3 x TF32 when EXACT)
-template <bool EXACT>
-__device__ __forceinline__ void mma_f(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
-  uint32_t ah[4], bh[2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) ah[i] = EXACT ? to_tf32(a[i]) : __float_as_uint(a[i]);
-  bh[0] = EXACT ? to_tf32(b[0]) : __float_as_uint(b[0]); bh[1] = EXACT ? to_tf32(b[1]) : __float_as_uint(b[1]);
-  if (EXACT) {
-    uint32_t al[4], bl[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) al[i] = to_tf32(a[i] - __uint_as_float(ah[i]));
-    bl[0] = to_tf32(b[0] - __uint_as_float(bh[0])); bl[1] = to_tf32(b[1] - __uint_as_float(bh[1]));
-    mma_tf32(c, al, bh);
-    mma_tf32(c, ah, bl);
-  }
-  mma_tf32(c, ah, bh);
-}
 
 // Cross attention of one head for the 16 tokens of a warp's row tile, on mma.sync: S = Q K^T (two 8-key column tiles) -> softmax
 // over the 16 keys on the accumulator fragments (a row lives in one quad) -> p[n][e] = P[row g (+8 for e >= 2)][key 8 n + 2 t + (e & 1)].
