@@ -712,6 +712,22 @@ def main():
         roofline = {"bound": "tensor", "kernel": name, "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
                     "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                     "avg_launch_us": round(1e3 * tms / cnt, 2), "flops_per_launch": fl}
+        # the decode-stage kernels against their own bounds (algorithmic work of SURVEY 8(d): 23 104 FLOP per (row, gene) token for the MCAB + head,
+        # 8 B per (row, gene) for the NB finalisation: logits in, counts out)
+        secondary = []
+        rows_step = 2 * B
+        if "mcab_decode_tc" in prof:
+            c2, t2 = prof["mcab_decode_tc"]
+            a2 = rows_step * G * 23104 / (t2 * 1e-3) / 1e12
+            secondary.append({"bound": "tensor", "kernel": "mcab_decode_tc (mma.sync bf16)", "achieved": round(a2, 1), "peak": peak, "unit": "TFLOP/s",
+                              "frac": round(a2 / peak, 4), "avg_launch_us": round(1e3 * t2 / c2, 2)})
+        if "nb_finalize" in prof:
+            c3, t3 = prof["nb_finalize"]
+            a3 = rows_step * G * 8 / (t3 * 1e-3) / 1e9
+            secondary.append({"bound": "hbm", "kernel": "nb_finalize", "achieved": round(a3, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": round(a3 / peaks["hbm_gbs"], 4), "avg_launch_us": round(1e3 * t3 / c3, 2),
+                              "note": "bound by the Philox / NB-inversion arithmetic, not by HBM (ncu: issue slots 78 %)"})
+        roofline["secondary"] = secondary
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -176,3 +176,22 @@ def test_vae_autograd_bridge_matches_fused_step():
     for name, p in vae.named_parameters():
         if p.requires_grad:
             assert p.grad is not None and p.grad.data_ptr() >= tr.grad.data_ptr()      # views of the flat buffer
+
+
+def test_vae_trainer_keeps_state_dict_contract():
+    """The module's parameters alias the flat buffer: `state_dict()` keys / shapes are the reference's, `load_state_dict` writes through
+    to the buffer the kernels read, and a step changes what `state_dict()` returns."""
+    cfg = VAEConfig(n_genes=500, n_layer=1)
+    vae, tr, sd = make_trainer(cfg, False)
+    assert set(vae.state_dict().keys()) == set(sd.keys())
+    sd2 = synthetic.vae_state_dict(cfg, WEIGHT_SEED + 1)
+    vae.load_state_dict(sd2, strict=True)
+    off = tr.offsets["decoder.decoder_cross_attention.mlp.w1.weight"]
+    w = sd2["decoder.decoder_cross_attention.mlp.w1.weight"]
+    assert torch.equal(tr.flat[off: off + w.numel()].cpu().view_as(w), w)
+    counts, genes, lib, cs, gs = [a.cuda() for a in vae_train_inputs(cfg, 4, 100)]
+    before = vae.state_dict()["encoder.ca_layer.inducing_points"].clone()
+    tr.training_step(dict(counts=counts, genes=genes, library_size=lib, counts_subset=cs, genes_subset=gs))
+    after = vae.state_dict()["encoder.ca_layer.inducing_points"]
+    assert not torch.equal(before, after) and torch.isfinite(after).all()
+    assert torch.equal(vae.state_dict()["encoder.pos_embed"].cpu(), sd2["encoder.pos_embed"])      # frozen (nnets.py:103-106)
