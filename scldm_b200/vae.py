@@ -128,13 +128,21 @@ class TransformerVAE(nn.Module):
             return ops.vae256_encode(packed, g.contiguous(), c.contiguous())
         return ops.vae_encode(packed, g.contiguous(), c.contiguous())
 
-    @torch.no_grad()
     def forward(self, counts, genes, library_size, counts_subset=None, genes_subset=None):
-        """`TransformerVAE.forward` (`vae.py:29-56`), inference only: encode the (subset) tokens, decode every gene ->
-        `({"mu", "theta"}, h_z)`.  No autograd graph is built (the backward pass / VAE training step is SURVEY.md 8f rank 3)."""
-        h_z = self.encode(counts, genes, counts_subset, genes_subset)
-        dist = self.decode(h_z, genes, library_size)
-        return {"mu": dist.mu, "theta": dist.theta}, h_z
+        """`TransformerVAE.forward` (`vae.py:29-56`): encode the (subset) tokens, decode every gene -> `({"mu", "theta"}, h_z)`.
+        In training mode with gradients enabled and a `vae_training.VAETrainer` attached (its constructor attaches itself) the outputs
+        carry a grad_fn: `VAE.loss(...)` -> `.backward()` fills `p.grad` through the library's backward kernels, so the reference's
+        Lightning `training_step` / optimizer loop runs unchanged.  Otherwise inference kernels, no autograd graph."""
+        trainer = getattr(self, "_trainer", None)
+        if self.training and torch.is_grad_enabled() and trainer is not None:
+            from .vae_training import differentiable_forward
+
+            return differentiable_forward(trainer, counts, genes, library_size, counts_subset if counts_subset is not None else counts,
+                                          genes_subset if genes_subset is not None else genes)
+        with torch.no_grad():
+            h_z = self.encode(counts, genes, counts_subset, genes_subset)
+            dist = self.decode(h_z, genes, library_size)
+            return {"mu": dist.mu, "theta": dist.theta}, h_z
 
     @staticmethod
     def reconstruction_loss(counts: torch.Tensor, params: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:

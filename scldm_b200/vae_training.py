@@ -114,6 +114,18 @@ class VAETrainer:
         self.struct = s
         self._ws, self._ws_key = None, None
         self.last_nll = None
+        self._named = [(name, sd[name]) for name in order]
+        object.__setattr__(vae, "_trainer", self)     # TransformerVAE.forward in training mode routes through the autograd bridge
+
+    def _attach_grads(self) -> bool:
+        """`optimizer.zero_grad(set_to_none=True)` (Lightning's default) drops the `p.grad` views: re-create them.  Returns True when
+        any was missing, i.e. the caller zeroed the gradients and the flat buffer has to be cleared before accumulating."""
+        dropped = False
+        for name, p in self._named:
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * self.offsets[name]:
+                dropped = dropped or p.grad is None
+                p.grad = self.grad[self.offsets[name]: self.offsets[name] + p.numel()].view(p.shape)
+        return dropped
 
     # ------------------------------------------------------------------------------------------------------------
     def _dist(self) -> bool:
@@ -161,6 +173,7 @@ class VAETrainer:
         """Backward of the last forward-only `forward_backward(backward=False)` on `inputs` = (genes, library_size, counts_subset,
         genes_subset) from dLoss/dmu [B,G] (and dLoss/dtheta [B,G] of the expanded theta): the autograd bridge's backward."""
         genes, library_size, counts_subset, genes_subset = inputs
+        zero_grads = self._attach_grads() or zero_grads
         B, G = dmu.shape
         S = counts_subset.shape[1]
         gvec = shared_gene_vector(genes).to(torch.int64).contiguous()
@@ -175,6 +188,8 @@ class VAETrainer:
                                                    dth.data_ptr() if dth is not None else None, B, G, int(zero_grads), int(self.exact), ws.data_ptr(),
                                                    ws.numel(), self._stream())
         _lib.check(rc, "scldm_vae_train_backward")
+        self.vae._packed_dec = None          # an optimizer of the caller's will move the weights: rebuild the inference packs lazily
+        self.vae._packed_enc = None
 
     def allreduce_grads(self) -> None:
         if self._dist() and self.world > 1:

@@ -195,3 +195,38 @@ def test_vae_trainer_keeps_state_dict_contract():
     after = vae.state_dict()["encoder.ca_layer.inducing_points"]
     assert not torch.equal(before, after) and torch.isfinite(after).all()
     assert torch.equal(vae.state_dict()["encoder.pos_embed"].cpu(), sd2["encoder.pos_embed"])      # frozen (nnets.py:103-106)
+
+
+def test_reference_style_training_loop_through_module_forward():
+    """What the reference's Lightning module does (`VAE.training_step` + automatic optimization), verbatim, on the drop-in module:
+    `vae(...)` -> `VAE.loss` in torch -> `zero_grad(set_to_none=True)` / `backward` / `clip_grad_norm_` / the reference's own AdamWLegacy.
+    Must land on the same weights as `VAETrainer.training_step`."""
+    from oracle import ref_loader
+    from scldm_b200.vae_training import VAETrainer
+
+    ref_loader.load_reference()
+    import scldm.optimizers as ref_opt
+
+    cfg = VAEConfig(n_genes=640, n_layer=1)
+    counts, genes, lib, cs, gs = [a.cuda() for a in vae_train_inputs(cfg, 4, 150)]
+    vae_a, tr_a, _ = make_trainer(cfg, True, lr=1e-3)
+    vae_b, tr_b, _ = make_trainer(cfg, True, lr=1e-3)
+    opt = ref_opt.AdamWLegacy([p for p in vae_b.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.0)
+    for _ in range(3):
+        tr_a.training_step(dict(counts=counts, genes=genes, library_size=lib, counts_subset=cs, genes_subset=gs))
+        opt.zero_grad(set_to_none=True)
+        params, _ = vae_b(counts, genes, lib, cs, gs)                      # module forward, training mode -> autograd bridge
+        loss = (-O.log_nb_positive(counts, params["mu"], params["theta"])).sum(dim=1).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in vae_b.parameters() if p.requires_grad], 10.0)
+        opt.step()
+    torch.cuda.synchronize()
+    e = rel_l2(tr_b.flat, tr_a.flat)
+    d = float((tr_b.flat - tr_a.flat).abs().max())
+    print("reference-style loop vs VAETrainer.training_step after 3 steps: rel", e, "max abs", d)
+    # Adam turns a noise-level gradient into a full +-lr step, so a few entries with g ~ 0 may differ by O(lr) per step: bound the norm
+    assert e < 1e-4 and d < 3 * 3 * 1e-3
+    # eval mode still runs the inference kernels on the trained weights
+    vae_b.eval()
+    p_eval, _ = vae_b(counts, genes, lib, cs, gs)
+    assert not p_eval["mu"].requires_grad and torch.isfinite(p_eval["mu"]).all()
