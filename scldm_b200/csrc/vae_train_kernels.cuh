@@ -1082,6 +1082,29 @@ __global__ void __launch_bounds__(512) mu_grad_kernel(const MuGradParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // Decoder MCAB on (cell, gene) tokens: forward (logits) and, with BWD, the whole backward of the tile.
 // ---------------------------------------------------------------------------------------------------------------
+// two products that share the A operand (u = n2 w1^T, v = n2 w2^T): the A fragments of a K step are loaded once
+template <bool EXACT, int NT, int KS>
+__device__ __forceinline__ void warp_gemm2(float (*acc1)[4], float (*acc2)[4], const float* A, int sar, int sac, const float* B1, const float* B2,
+                                           int sbr, int sbc, int nt, int nstep) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = ks * 8;
+    const float af[4] = {A[g * sar + (k0 + t) * sac], A[(g + 8) * sar + (k0 + t) * sac], A[g * sar + (k0 + t + 4) * sac],
+                         A[(g + 8) * sar + (k0 + t + 4) * sac]};
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      if (i < nt) {
+        const int o = (i * nstep + g) * sbc;
+        const float b1[2] = {B1[o + (k0 + t) * sbr], B1[o + (k0 + t + 4) * sbr]};
+        const float b2[2] = {B2[o + (k0 + t) * sbr], B2[o + (k0 + t + 4) * sbr]};
+        mma_f<EXACT>(acc1[i], af, b1);
+        mma_f<EXACT>(acc2[i], af, b2);
+      }
+    }
+  }
+}
+
 struct DecTrainParams {
   const float* ca; float* gca;          // decoder_cross_attention parameter group / its gradients
   const float* emb; const long long* genes; int G;
@@ -1245,8 +1268,7 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
     // (5) u = w1 n2, v = w2 n2, h = silu(u) v; backward: du, dv right away (dh = dlogit r)
     {
       float au[3][4] = {}, av[3][4] = {};
-      warp_gemm<EXACT, 3, 4>(au, sN2 + mt * 16 * LD32, LD32, 1, sW1 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
-      warp_gemm<EXACT, 3, 4>(av, sN2 + mt * 16 * LD32, LD32, 1, sW2 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
+      warp_gemm2<EXACT, 3, 4>(au, av, sN2 + mt * 16 * LD32, LD32, 1, sW1 + (nt0 * 8) * LD32, sW2 + (nt0 * 8) * LD32, 1, LD32, ntn, 8);
       const float dl0 = BWD ? sDl[mt * 16 + g] : 0.f, dl1 = BWD ? sDl[mt * 16 + g + 8] : 0.f;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
