@@ -230,3 +230,18 @@ def test_reference_style_training_loop_through_module_forward():
     vae_b.eval()
     p_eval, _ = vae_b(counts, genes, lib, cs, gs)
     assert not p_eval["mu"].requires_grad and torch.isfinite(p_eval["mu"]).all()
+
+
+def test_vae_train_census_shape_vs_oracle():
+    """Full census vocabulary and depth (G = 36 130, S = 8 000, 8 + 8 layers; BASELINE configs[4]) at 4 cells: multi-wave grids of the tile
+    kernel, three cell chunks, 63 encoder tiles per cell.  TF32 mode (what the bench runs) against the oracle's fp32 autograd."""
+    cfg = VAEConfig(n_genes=36130)
+    vae, tr, sd = make_trainer(cfg, False)
+    counts, genes, lib, cs, gs = [a.cuda() for a in vae_train_inputs(cfg, 4, 8000)]
+    mu_o, z_o, pc_o, llh_o, g_o = oracle_grads(cfg, sd, counts, genes, lib, cs, gs)
+    out, z, mu = tr.forward_backward(counts, genes, lib, cs, gs, want_mu=True)
+    torch.cuda.synchronize()
+    e_loss, e_z, e_mu = abs(float(out["llh"]) - float(llh_o)) / abs(float(llh_o)), rel_l2(z, z_o), rel_l2(mu, mu_o)
+    print(f"census shape: loss {float(out['llh']):.4f} vs {float(llh_o):.4f} rel {e_loss:.2e}; z {e_z:.2e}; mu {e_mu:.2e}")
+    worst = compare_grads(vae, g_o, 3e-3, "census")          # measured on B200: loss 1.0e-5, mu 3.6e-4, worst gradient 8.0e-4
+    assert e_loss < 5e-5 and e_z < 1e-4 and e_mu < 1e-3 and worst < 3e-3, (e_loss, e_z, e_mu, worst)
