@@ -1225,14 +1225,30 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
   const int nt0 = nq * 3, ntn = nq < 3 ? 3 : 2;   // this warp's column tiles of the 88 hidden units
   __syncthreads();
 
+  // software pipeline over the cells: the next cell's keys / values / dlogit are fetched into registers while this one is processed
+  // (otherwise every trip starts with an exposed L2 round trip in front of its first barrier)
+  float nk[2], nv[2], ndl = 0.f;
+  {
+    const int b = b_begin < b_end ? b_begin : 0;
+    nk[0] = p.Kc[(size_t)b * 512 + tid]; nk[1] = p.Kc[(size_t)b * 512 + tid + 256];
+    nv[0] = p.Vc[(size_t)b * 512 + tid]; nv[1] = p.Vc[(size_t)b * 512 + tid + 256];
+    if (BWD && tid < DT && g0 + tid < p.G) ndl = p.dlogit[(size_t)b * p.G + g0 + tid];
+  }
   for (int b = b_begin; b < b_end; ++b) {
     // (1) the cell's keys / values and, for the backward, d loss / d logit of the tile
-    for (int i = tid; i < 512; i += 256) {
-      sK[(i >> 5) * LDK + (i & 31)] = rt<EXACT>(p.Kc[(size_t)b * 512 + i]);
-      sVc[(i >> 5) * LDK + (i & 31)] = rt<EXACT>(p.Vc[(size_t)b * 512 + i]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = tid + r * 256;
+      sK[(i >> 5) * LDK + (i & 31)] = rt<EXACT>(nk[r]);
+      sVc[(i >> 5) * LDK + (i & 31)] = rt<EXACT>(nv[r]);
     }
-    if (BWD && tid < DT) sDl[tid] = (g0 + tid < p.G) ? p.dlogit[(size_t)b * p.G + g0 + tid] : 0.f;
+    if (BWD && tid < DT) sDl[tid] = ndl;
     __syncthreads();
+    if (b + 1 < b_end) {
+      nk[0] = p.Kc[(size_t)(b + 1) * 512 + tid]; nk[1] = p.Kc[(size_t)(b + 1) * 512 + tid + 256];
+      nv[0] = p.Vc[(size_t)(b + 1) * 512 + tid]; nv[1] = p.Vc[(size_t)(b + 1) * 512 + tid + 256];
+      if (BWD && tid < DT && g0 + tid < p.G) ndl = p.dlogit[(size_t)(b + 1) * p.G + g0 + tid];
+    }
     // (2) cross attention over the 16 latent keys: warp (row tile, head)
     {
       float pr[2][4], o[4];
