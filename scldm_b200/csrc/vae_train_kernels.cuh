@@ -1179,7 +1179,6 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
   float* sm = reinterpret_cast<float*>(dec_smem4);
   float* sQ = sm;                    float* sAO = sQ + DT * LD32;    float* sX1 = sAO + DT * LD32;   float* sN2 = sX1 + DT * LD32;
   float* sD1 = sN2 + DT * LD32;      float* sD2 = sD1 + DT * LD32;   float* sU = sD2 + DT * LD32;    float* sV = sU + DT * LD88;
-  float* sH = sU;                    // forward-only kernel: h lives where the backward keeps du
   float* sK = sV + DT * LD88;        float* sVc = sK + 16 * LDK;     float* sStat = sVc + 16 * LDK;  float* sDl = sStat + 2 * DT;
   float* sLog = sDl + DT;            int* sGid = reinterpret_cast<int*>(sLog + 4 * DT);
   float* sWp = sLog + 5 * DT;        float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;
@@ -1206,9 +1205,10 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
   __syncthreads();
   // The head is linear in x2 = x1 + w3 h, so its backward never needs the mlp.c_proj GEMMs: with r = w3^T w_head,
   // dh[tok] = dlogit[tok] r, d w3 = w_head (x) sum_tok dlogit h, d w_head = sum_tok dlogit x1 + w3 sum_tok dlogit h.
-  if (BWD && tid < H) {
+  // (forward: logit = w_head . x1 + r . h + b - no mlp.c_proj GEMM either.  r from the fp32 weights, not the TF32-rounded tile.)
+  if (tid < H) {
     float a = 0.f;
-    for (int o = 0; o < 32; ++o) a += sWh[o] * sW3[o * LD88 + tid];
+    for (int o = 0; o < 32; ++o) a += sWh[o] * p.ca[C_W3 + o * H + tid];
     sR[tid] = a;
   }
   // the residual rows q_in = emb[gene] of this thread's accumulator positions (rows g, g + 8 of its row tile; columns nq * 8 + 2 t, + 1)
@@ -1221,6 +1221,7 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
   // persistent gradient accumulators
   float acc_w[6][4] = {}, acc_wp[2][4] = {};
   float acc_lnw[4] = {}, acc_lnb[4] = {}, acc_xs[4] = {}, acc_dq[4] = {}, acc_sh[3][2] = {}, acc_s = 0.f;
+  float hx_lo = 0.f, hx_hi = 0.f;                 // forward: partial head dot products of this thread's rows
   const int tok_a = tid >> 3, part = tid & 7;     // (token, 4-channel part) of the row phases
   const int nt0 = nq * 3, ntn = nq < 3 ? 3 : 2;   // this warp's column tiles of the 88 hidden units
   __syncthreads();
@@ -1264,6 +1265,11 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
       warp_gemm<EXACT, 1, 4>(acc, sAO + mt * 16 * LD32, LD32, 1, sWp + (nq * 8) * LD32, 1, LD32, 1, 8);
       float* dst = sX1 + (mt * 16 + g) * LD32 + nq * 8 + 2 * t;
       dst[0] = qin[0] + acc[0][0]; dst[1] = qin[1] + acc[0][1]; dst[8 * LD32] = qin[2] + acc[0][2]; dst[8 * LD32 + 1] = qin[3] + acc[0][3];
+      if (!BWD) {   // this thread's share of w_head . x1 for its two rows
+        const float w0 = sWh[nq * 8 + 2 * t], w1 = sWh[nq * 8 + 2 * t + 1];
+        hx_lo = dst[0] * w0 + dst[1] * w1;
+        hx_hi = dst[8 * LD32] * w0 + dst[8 * LD32 + 1] * w1;
+      }
     }
     __syncthreads();
     // (4) LN2: eight threads per token
@@ -1299,36 +1305,18 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
               sU[r * LD88 + col] = rt<EXACT>(dh * v * sg * (1.f + u * (1.f - sg)));
               sV[r * LD88 + col] = rt<EXACT>(dh * u * sg);
             } else {
-              sH[r * LD88 + col] = rt<EXACT>(hv);
+              if (e >> 1) hx_hi += sR[col] * hv; else hx_lo += sR[col] * hv;
             }
           }
         }
       }
     }
-    __syncthreads();
+    if (BWD) __syncthreads();
     if (!BWD) {
-      // (6) x2 = x1 + mlp.c_proj(h), folded straight into the head dot product: warp (row tile, column half, K half of the 88 hidden
-      //     units) leaves its share of sum_c w_head[c] x2[c] in one of four slots per token
+      // (6) the four column-quarter warps of a row tile leave their shares of w_head . x1 + r . h in four slots per token
       {
-        const int nh2 = (warp >> 1) & 1, kh = warp >> 2;
-        float acc[2][4] = {};
-        if (kh == 0) warp_gemm<EXACT, 2, 6>(acc, sH + mt * 16 * LD88, LD88, 1, sW3 + (nh2 * 16) * LD88, 1, LD88, 2, 8);
-        else warp_gemm<EXACT, 2, 5>(acc, sH + mt * 16 * LD88 + 48, LD88, 1, sW3 + (nh2 * 16) * LD88 + 48, 1, LD88, 2, 8);
-        float lo = 0.f, hi = 0.f;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int col = nh2 * 16 + i * 8 + 2 * t;
-          const float w0 = sWh[col], w1 = sWh[col + 1];
-          float x00 = acc[i][0], x01 = acc[i][1], x10 = acc[i][2], x11 = acc[i][3];
-          if (kh == 0) {
-            const float* x1 = sX1 + (mt * 16 + g) * LD32 + col;
-            x00 += x1[0]; x01 += x1[1]; x10 += x1[8 * LD32]; x11 += x1[8 * LD32 + 1];
-          }
-          lo += x00 * w0 + x01 * w1;
-          hi += x10 * w0 + x11 * w1;
-        }
-        lo = quad_sum(lo); hi = quad_sum(hi);
-        if (t == 0) { sLog[(nh2 * 2 + kh) * DT + mt * 16 + g] = lo; sLog[(nh2 * 2 + kh) * DT + mt * 16 + g + 8] = hi; }
+        const float lo = quad_sum(hx_lo), hi = quad_sum(hx_hi);
+        if (t == 0) { sLog[nq * DT + mt * 16 + g] = lo; sLog[nq * DT + mt * 16 + g + 8] = hi; }
       }
       __syncthreads();
       // (7) head logit
