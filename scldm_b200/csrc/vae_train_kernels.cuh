@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(128) qside_bwd_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Encoder tokens: x = emb[gene] * f(count) -> LN1 -> K, V = c_attn  (layers.py:97-118, 248-252), one thread per token
+// Encoder tokens: x = emb[gene] * f(count) -> LN1 -> K, V = c_attn -> pooling by the inducing-point queries (layers.py:97-118, 248-264)
 // ---------------------------------------------------------------------------------------------------------------
 struct EncTokParams {
   const float* emb; const long long* genes; const float* counts; int agg; long long n_tok;
@@ -632,137 +632,16 @@ struct EncTokParams {
   float* K; float* V;      // [n_tok][32]
   float* stats;            // [n_tok][2] mean, rstd of LN1
 };
-__global__ void __launch_bounds__(128) enc_tokens_fwd_kernel(const EncTokParams p) {
-  __shared__ float sW[64 * 32], sw[32], sb[32];
-  for (int i = threadIdx.x; i < 2048; i += 128) sW[i] = p.ca[C_CATTN + i];
-  if (threadIdx.x < 32) { sw[threadIdx.x] = p.ca[C_LN1W + threadIdx.x]; sb[threadIdx.x] = p.ca[C_LN1B + threadIdx.x]; }
-  __syncthreads();
-  const long long tk = (long long)blockIdx.x * 128 + threadIdx.x;
-  if (tk >= p.n_tok) return;
-  const float f = vae::count_scale(p.counts[tk], p.agg);
-  const float* src = p.emb + (size_t)p.genes[tk] * 32;
-  float x[32];
-#pragma unroll
-  for (int k = 0; k < 32; k += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(src + k);
-    x[k] = v.x * f; x[k + 1] = v.y * f; x[k + 2] = v.z * f; x[k + 3] = v.w * f;
-  }
-  float mean = 0.f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) mean += x[k];
-  mean *= (1.f / 32.f);
-  float var = 0.f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) { x[k] -= mean; var += x[k] * x[k]; }
-  const float rstd = rsqrtf(var * (1.f / 32.f) + p.eps);
-  p.stats[tk * 2] = mean;
-  p.stats[tk * 2 + 1] = rstd;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) x[k] = x[k] * rstd * sw[k] + sb[k];
-#pragma unroll 2
-  for (int o = 0; o < 64; o += 4) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] += sW[(o + q) * 32 + k] * x[k];
-    }
-    float* dst = (o < 32 ? p.K : p.V) + tk * 32 + (o & 31);
-    *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
-  }
-}
-
-// Encoder MCAB pooling: 16 inducing-point queries x 4 heads attend to all S tokens of a cell (no key masking).
-// One CTA per cell; thread = (query, head) pair x one of 8 interleaved token slices; online softmax, merged through shared memory.
-// grid (cells, POOL_SPLIT): a CTA pools one contiguous quarter of the cell's tokens and leaves an unnormalised (max, sum, acc) state per
-// (query, head); enc_pool_merge_kernel merges the quarters.
-constexpr int POOL_SPLIT = 4;
-__global__ void __launch_bounds__(512) enc_pool_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                                                           int S, float* __restrict__ part) {
-  __shared__ float sm[8][64][10];
-  const int b = blockIdx.x, pair = threadIdx.x & 63, slice = threadIdx.x >> 6;
-  const int m = pair >> 2, h = pair & 3;
-  const int per = (S + POOL_SPLIT - 1) / POOL_SPLIT, s_begin = blockIdx.y * per;
-  const size_t cell_base = (size_t)b * S * 32;
-  S = min(S, s_begin + per);      // this CTA's token range [s_begin, S)
-  float q[8], acc[8], mx = -1e30f, l = 0.f;
-#pragma unroll
-  for (int d = 0; d < 8; ++d) { q[d] = Q[m * 32 + h * 8 + d] * 0.35355339059327373f; acc[d] = 0.f; }
-  const float* kb = K + cell_base + h * 8;
-  const float* vb = V + cell_base + h * 8;
-  // four keys per trip: one running-max update (one dependent exp chain) per four keys, 16 independent 16-byte loads in flight
-  int s = s_begin + slice;
-  for (; s + 24 < S; s += 32) {
-    float4 k0[4], k1[4], v0[4], v1[4];
-    float sc[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const size_t o = (size_t)(s + 8 * i) * 32;
-      k0[i] = *reinterpret_cast<const float4*>(kb + o); k1[i] = *reinterpret_cast<const float4*>(kb + o + 4);
-      v0[i] = *reinterpret_cast<const float4*>(vb + o); v1[i] = *reinterpret_cast<const float4*>(vb + o + 4);
-    }
-    float mn = mx;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      sc[i] = q[0] * k0[i].x + q[1] * k0[i].y + q[2] * k0[i].z + q[3] * k0[i].w + q[4] * k1[i].x + q[5] * k1[i].y + q[6] * k1[i].z + q[7] * k1[i].w;
-      mn = fmaxf(mn, sc[i]);
-    }
-    const float corr = __expf(mx - mn);
-    mx = mn;
-    l *= corr;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) acc[d] *= corr;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float pr = __expf(sc[i] - mn);
-      l += pr;
-      acc[0] += pr * v0[i].x; acc[1] += pr * v0[i].y; acc[2] += pr * v0[i].z; acc[3] += pr * v0[i].w;
-      acc[4] += pr * v1[i].x; acc[5] += pr * v1[i].y; acc[6] += pr * v1[i].z; acc[7] += pr * v1[i].w;
-    }
-  }
-  for (; s < S; s += 8) {
-    const float4 k0 = *reinterpret_cast<const float4*>(kb + (size_t)s * 32), k1 = *reinterpret_cast<const float4*>(kb + (size_t)s * 32 + 4);
-    const float4 v0 = *reinterpret_cast<const float4*>(vb + (size_t)s * 32), v1 = *reinterpret_cast<const float4*>(vb + (size_t)s * 32 + 4);
-    const float sc = q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w + q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w;
-    if (sc > mx) {
-      const float corr = __expf(mx - sc);
-      l *= corr;
-#pragma unroll
-      for (int d = 0; d < 8; ++d) acc[d] *= corr;
-      mx = sc;
-    }
-    const float pr = __expf(sc - mx);
-    l += pr;
-    acc[0] += pr * v0.x; acc[1] += pr * v0.y; acc[2] += pr * v0.z; acc[3] += pr * v0.w;
-    acc[4] += pr * v1.x; acc[5] += pr * v1.y; acc[6] += pr * v1.z; acc[7] += pr * v1.w;
-  }
-  sm[slice][pair][0] = mx; sm[slice][pair][1] = l;
-#pragma unroll
-  for (int d = 0; d < 8; ++d) sm[slice][pair][2 + d] = acc[d];
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float gm = -1e30f;
-    for (int i = 0; i < 8; ++i) gm = fmaxf(gm, sm[i][pair][0]);
-    float gl = 0.f, ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < 8; ++i) {
-      const float c = __expf(sm[i][pair][0] - gm);
-      gl += sm[i][pair][1] * c;
-#pragma unroll
-      for (int d = 0; d < 8; ++d) ga[d] += sm[i][pair][2 + d] * c;
-    }
-    float* dst = part + (((size_t)b * POOL_SPLIT + blockIdx.y) * 64 + pair) * 10;
-    dst[0] = gm; dst[1] = gl;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) dst[2 + d] = ga[d];
-  }
-}
-__global__ void __launch_bounds__(64) enc_pool_merge_kernel(const float* __restrict__ part, float* __restrict__ AO, float* __restrict__ lse) {
+// Merge of the per-CTA pooling states (max, sum, acc[8] per (query, head)) of a cell left by enc_fused_fwd_kernel: the 16 inducing-point
+// queries x 4 heads attend to ALL S tokens of a cell (no key masking); also leaves the log-sum-exp for the backward.
+__global__ void __launch_bounds__(64) enc_pool_merge_kernel(const float* __restrict__ part, int n_parts, float* __restrict__ AO,
+                                                            float* __restrict__ lse) {
   const int b = blockIdx.x, pair = threadIdx.x, m = pair >> 2, h = pair & 3;
-  const float* src = part + ((size_t)b * POOL_SPLIT * 64 + pair) * 10;
+  const float* src = part + ((size_t)b * n_parts * 64 + pair) * 10;
   float gm = -1e30f;
-  for (int i = 0; i < POOL_SPLIT; ++i) gm = fmaxf(gm, src[i * 640]);
+  for (int i = 0; i < n_parts; ++i) gm = fmaxf(gm, src[i * 640]);
   float gl = 0.f, ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = 0; i < POOL_SPLIT; ++i) {
+  for (int i = 0; i < n_parts; ++i) {
     const float c = __expf(src[i * 640] - gm);
     gl += src[i * 640 + 1] * c;
 #pragma unroll
@@ -774,6 +653,164 @@ __global__ void __launch_bounds__(64) enc_pool_merge_kernel(const float* __restr
   lse[b * 64 + pair] = gm + __logf(gl);
 }
 
+
+// Fused forward of the encoder's token side on mma.sync: a CTA walks ENC_FWD_TILES consecutive 128-token tiles of its cell; per tile
+//   emb x f(count) -> LN1 (thread per token) -> [K | V] = xn Wkv^T (TF32 mma; written to HBM for the backward AND kept in shared memory)
+//   -> S^T = K_h Q_h^T, running max / sum per (query, head) across the tiles, P tile -> AO_h += P_h^T V_h (mma over the tokens).
+// It leaves one unnormalised (max, sum, acc) state per (query, head) and CTA; enc_pool_merge_kernel merges the CTAs of a cell.
+constexpr int ENC_FWD_TILES = 8;
+constexpr int EF_LD = 40, EF_LDP = 68;
+constexpr int ENC_FWD_SMEM_FLOATS = 3 * 128 * EF_LD + 128 * EF_LDP + 64 * EF_LD + 16 * 36 + 64 + 4 * 64 + 4 * 64 + 3 * 64;
+template <bool EXACT>
+__global__ void __launch_bounds__(128) enc_fused_fwd_kernel(const EncTokParams p, const float* __restrict__ Q, int S, float* __restrict__ part) {
+  extern __shared__ float4 encf_smem4[];
+  float* sm = reinterpret_cast<float*>(encf_smem4);
+  float* tXN = sm;                      // [128][40] LN1 output
+  float* tK = tXN + 128 * EF_LD;        // [128][40]
+  float* tV = tK + 128 * EF_LD;         // [128][40]
+  float* tP = tV + 128 * EF_LD;         // [128][68] softmax numerators, column = query * 4 + head
+  float* sW = tP + 128 * EF_LDP;        // c_attn [64][40]
+  float* sQ = sW + 64 * EF_LD;          // [16][36] scaled queries
+  float* sLn = sQ + 16 * 36;            // ln_1 weight | bias
+  float* sTMax = sLn + 64;              // [4 warps][64] column maxima of the warps' tokens
+  float* sTSum = sTMax + 256;           // [4 warps][64] column sums
+  float* sMax = sTSum + 256;            // [64] running maximum per (query, head)
+  float* sSum = sMax + 64;              // [64] running sum
+  float* sScale = sSum + 64;            // [64] exp(old max - new max) of this tile
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 2048; i += 128) sW[(i >> 5) * EF_LD + (i & 31)] = rt<EXACT>(p.ca[C_CATTN + i]);
+  for (int i = tid; i < 512; i += 128) sQ[(i >> 5) * 36 + (i & 31)] = rt<EXACT>(Q[i] * 0.35355339059327373f);
+  if (tid < 64) { sLn[tid] = p.ca[C_LN1W + tid]; sMax[tid] = -1e30f; sSum[tid] = 0.f; }
+  float acc_o[1][4] = {};               // warp h: AO_h[query g (+8)][d = 2 t (+1)], unnormalised
+  const int n_tiles = (S + 127) / 128;
+  __syncthreads();
+  for (int tile = blockIdx.x * ENC_FWD_TILES; tile < min(n_tiles, (blockIdx.x + 1) * ENC_FWD_TILES); ++tile) {
+    // ---- token phase: LN1 of emb x f(count) ----
+    {
+      const int s_ = tile * 128 + tid;
+      const bool valid = s_ < S;
+      const long long tk = (long long)b * S + (valid ? s_ : 0);
+      const float f = vae::count_scale(valid ? p.counts[tk] : 0.f, p.agg);
+      const float* src = p.emb + (size_t)(valid ? p.genes[tk] : 0) * 32;
+      float x[32];
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + k);
+        x[k] = v.x * f; x[k + 1] = v.y * f; x[k + 2] = v.z * f; x[k + 3] = v.w * f;
+      }
+      float mean = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) mean += x[k];
+      mean *= (1.f / 32.f);
+      float var = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) { x[k] -= mean; var += x[k] * x[k]; }
+      const float rstd = rsqrtf(var * (1.f / 32.f) + p.eps);
+      if (valid) { p.stats[tk * 2] = mean; p.stats[tk * 2 + 1] = rstd; }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) tXN[tid * EF_LD + k] = valid ? rt<EXACT>(x[k] * rstd * sLn[k] + sLn[32 + k]) : 0.f;
+    }
+    __syncthreads();
+    // ---- [K | V] of the warp's 32 tokens ----
+#pragma unroll 1
+    for (int mtile = 0; mtile < 2; ++mtile) {
+      const int r0 = warp * 32 + mtile * 16;
+      float acc[8][4] = {};
+      warp_gemm<EXACT, 8, 4>(acc, tXN + r0 * EF_LD, EF_LD, 1, sW, 1, EF_LD, 8, 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = r0 + g + hh * 8, s_ = tile * 128 + row, col = (i & 3) * 8 + 2 * t;
+          const bool valid = s_ < S;
+          float* dt = (i < 4 ? tK : tV) + row * EF_LD + col;
+          const float a0 = acc[i][hh * 2], a1 = acc[i][hh * 2 + 1];
+          dt[0] = valid ? rt<EXACT>(a0) : 0.f; dt[1] = valid ? rt<EXACT>(a1) : 0.f;
+          if (valid) *reinterpret_cast<float2*>((i < 4 ? p.K : p.V) + ((long long)b * S + s_) * 32 + col) = make_float2(a0, a1);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- scores of the warp's tokens against the 16 queries, per head; column maxima ----
+    float sc[2][4][2][4];     // [row tile][head][query half][fragment]
+#pragma unroll
+    for (int mtile = 0; mtile < 2; ++mtile) {
+      const int r0 = warp * 32 + mtile * 16;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float* kr = tK + r0 * EF_LD + h * 8;
+        const float ak[4] = {kr[g * EF_LD + t], kr[(g + 8) * EF_LD + t], kr[g * EF_LD + t + 4], kr[(g + 8) * EF_LD + t + 4]};
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const float bq[2] = {sQ[(8 * n + g) * 36 + h * 8 + t], sQ[(8 * n + g) * 36 + h * 8 + t + 4]};
+          sc[mtile][h][n][0] = sc[mtile][h][n][1] = sc[mtile][h][n][2] = sc[mtile][h][n][3] = 0.f;
+          mma_f<EXACT>(sc[mtile][h][n], ak, bq);
+        }
+      }
+    }
+    const bool v00 = tile * 128 + warp * 32 + g < S, v01 = tile * 128 + warp * 32 + g + 8 < S;
+    const bool v10 = tile * 128 + warp * 32 + 16 + g < S, v11 = tile * 128 + warp * 32 + 24 + g < S;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {     // column m = 8 n + 2 t + e: maximum over this thread's four rows, then over the eight row groups g
+          float mx = fmaxf(fmaxf(v00 ? sc[0][h][n][e] : -1e30f, v01 ? sc[0][h][n][2 + e] : -1e30f),
+                           fmaxf(v10 ? sc[1][h][n][e] : -1e30f, v11 ? sc[1][h][n][2 + e] : -1e30f));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+          if (g == 0) sTMax[warp * 64 + (8 * n + 2 * t + e) * 4 + h] = mx;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 64) {
+      const float old = sMax[tid];
+      const float nm = fmaxf(fmaxf(old, fmaxf(sTMax[tid], sTMax[64 + tid])), fmaxf(sTMax[128 + tid], sTMax[192 + tid]));
+      sScale[tid] = __expf(old - nm);
+      sMax[tid] = nm;
+    }
+    __syncthreads();
+    // ---- numerators -> P tile, column sums ----
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = (8 * n + 2 * t + e) * 4 + h;
+          const float nm = sMax[col];
+          const float p00 = v00 ? __expf(sc[0][h][n][e] - nm) : 0.f, p01 = v01 ? __expf(sc[0][h][n][2 + e] - nm) : 0.f;
+          const float p10 = v10 ? __expf(sc[1][h][n][e] - nm) : 0.f, p11 = v11 ? __expf(sc[1][h][n][2 + e] - nm) : 0.f;
+          const int r0 = warp * 32 + g;
+          tP[r0 * EF_LDP + col] = rt<EXACT>(p00); tP[(r0 + 8) * EF_LDP + col] = rt<EXACT>(p01);
+          tP[(r0 + 16) * EF_LDP + col] = rt<EXACT>(p10); tP[(r0 + 24) * EF_LDP + col] = rt<EXACT>(p11);
+          float sum = p00 + p01 + p10 + p11;
+          sum += __shfl_xor_sync(0xffffffffu, sum, 4); sum += __shfl_xor_sync(0xffffffffu, sum, 8); sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+          if (g == 0) sTSum[warp * 64 + col] = sum;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 64) sSum[tid] = sSum[tid] * sScale[tid] + sTSum[tid] + sTSum[64 + tid] + sTSum[128 + tid] + sTSum[192 + tid];
+    // ---- AO_h = AO_h * scale + P_h^T V_h over the tile's 128 tokens: warp h ----
+    {
+      const float s0 = sScale[g * 4 + warp], s1 = sScale[(g + 8) * 4 + warp];
+      acc_o[0][0] *= s0; acc_o[0][1] *= s0; acc_o[0][2] *= s1; acc_o[0][3] *= s1;
+      warp_gemm<EXACT, 1, 16>(acc_o, tP + warp, 4, EF_LDP, tV + warp * 8, EF_LD, 1, 1, 8);
+    }
+    __syncthreads();   // the tiles are rewritten by the next trip
+  }
+  // ---- this CTA's state per (query, head): max | sum | acc[8] ----
+  {
+    float* dst = part + (((size_t)b * gridDim.x + blockIdx.x) * 64) * 10;
+    const int h = warp;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[((g + (e >> 1) * 8) * 4 + h) * 10 + 2 + 2 * t + (e & 1)] = acc_o[0][e];
+    if (tid < 64) { dst[tid * 10] = sMax[tid]; dst[tid * 10 + 1] = sSum[tid]; }
+  }
+}
 
 // Backward of the pooling and of the token side, one thread per token of a 128-token tile of one cell:
 // dAO -> (dK, dV of the token) -> c_attn^T -> LN1 backward -> d emb[gene] (scatter) ; weight gradients of c_attn / ln_1 and
