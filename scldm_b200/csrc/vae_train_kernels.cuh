@@ -824,10 +824,10 @@ struct EncBwdParams {
   float* dQ;                 // [16][32] accumulated (atomics)
   float* g_emb;              // gradient of the embedding table
 };
-constexpr int ELD64 = 68, ELD32 = 40;   // row strides of the 64- / 32-wide token tiles
+constexpr int ELD64 = 68, ELD32 = 36;   // row strides of the 64- / 32-wide token tiles (with the weights staged in a dead tile: 112 KB, 2 CTAs / SM)
 constexpr int ENC_TILES_PER_CTA = 8;
 constexpr int EQ = 36;                  // row stride of the 16 x 32 query / dAO tiles (conflict-free B-fragment reads)
-constexpr int ENC_BWD_SMEM_FLOATS = 128 * ELD64 + 128 * ELD32 + 128 * ELD64 + 128 * ELD32 + 16 * EQ * 2 + 64 + 64 + 64 * ELD32 + 64;
+constexpr int ENC_BWD_SMEM_FLOATS = 128 * ELD64 + 128 * ELD32 + 128 * ELD64 + 128 * ELD32 + 16 * EQ * 2 + 64 + 64 + 64;
 template <bool EXACT>
 __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams p) {
   extern __shared__ float4 enc_smem4[];
@@ -840,15 +840,14 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
   float* sDAO = sQ + 16 * EQ;           // [16][36]
   float* sD = sDAO + 16 * EQ;           // [64] rowsum(dAO * AO) per (query, head)
   float* sLse = sD + 64;                // [64] log-sum-exp of the pooling softmax per (query, head)
-  float* sW = sLse + 64;                // c_attn [64][40]
+  float* sW = tK;                       // c_attn [64][40]: staged into the key tile once the dQ product has consumed it (every trip)
   float* tV = tXN;                      // values of the tile: dead before the LN1 output is written
-  float* sLn = sW + 64 * ELD32;         // ln_1 weight | bias
+  float* sLn = sLse + 64;               // ln_1 weight | bias
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 512; i += 128) {
     sQ[(i >> 5) * EQ + (i & 31)] = rt<EXACT>(p.Q[i] * 0.35355339059327373f);
     sDAO[(i >> 5) * EQ + (i & 31)] = rt<EXACT>(p.dAO[(size_t)b * 512 + i]);
   }
-  for (int i = threadIdx.x; i < 2048; i += 128) sW[(i >> 5) * ELD32 + (i & 31)] = rt<EXACT>(p.ca[C_CATTN + i]);
   if (threadIdx.x < 64) sLn[threadIdx.x] = p.ca[C_LN1W + threadIdx.x];   // ln_1.weight, ln_1.bias are adjacent
   if (threadIdx.x < 64) {
     const int m = threadIdx.x >> 2, h = threadIdx.x & 3;
@@ -947,6 +946,8 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
   warp_gemm<EXACT, 4, 16>(acc_w, tDKV + warp * 16, 1, ELD64, tXN, ELD32, 1, 4, 8);
   warp_gemm<EXACT, 1, 16>(acc_q, tDS + warp, 4, ELD64, tK + warp * 8, ELD32, 1, 1, 8);
   __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 128) sW[(i >> 5) * 40 + (i & 31)] = rt<EXACT>(p.ca[C_CATTN + i]);
+  __syncthreads();
   // d(LN1 output)[token][32] = [dk | dv] Wkv on mma.sync: warp w computes the rows of its own 32 tokens into the (now dead) dS tile
   {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -954,7 +955,7 @@ __global__ void __launch_bounds__(128) enc_tokens_bwd_kernel(const EncBwdParams 
     for (int mtile = 0; mtile < 2; ++mtile) {
       const int r0 = warp * 32 + mtile * 16;
       float acc[4][4] = {};
-      warp_gemm<EXACT, 4, 8>(acc, tDKV + r0 * ELD64, ELD64, 1, sW, ELD32, 1, 4, 8);
+      warp_gemm<EXACT, 4, 8>(acc, tDKV + r0 * ELD64, ELD64, 1, sW, 40, 1, 4, 8);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
 #pragma unroll
