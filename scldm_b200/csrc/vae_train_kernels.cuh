@@ -1158,6 +1158,8 @@ struct DecTrainParams {
 constexpr int DT = 32, LD32 = 36, LD88 = 100, LDK = 36;
 // 6 32-wide tiles + du / dv (h in the forward-only kernel) + keys / values + small vectors + the block's weights: 103 KB, 2 CTAs per SM
 constexpr int DEC_SMEM_FLOATS = 6 * DT * LD32 + 2 * DT * LD88 + 2 * 16 * LDK + 2 * DT + DT + 4 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96 + 96;
+// the forward-only launch needs neither the gradient tiles nor mlp.c_proj: 54 KB, three CTAs per SM
+constexpr int DEC_FWD_SMEM_FLOATS = 4 * DT * LD32 + 2 * 16 * LDK + 2 * DT + DT + 4 * DT + DT + 32 * LD32 + 2 * H * LD32 + 96 + 96;
 
 // Cross attention of one head for the 16 tokens of a warp's row tile, on mma.sync: S = Q K^T (two 8-key column tiles) -> softmax
 // over the 16 keys on the accumulator fragments (a row lives in one quad) -> p[n][e] = P[row g (+8 for e >= 2)][key 8 n + 2 t + (e & 1)].
@@ -1212,15 +1214,17 @@ __device__ __forceinline__ float oct_sum(float v) {
 // attention head); two CTAs are resident per SM (103 KB of shared memory, <= 128 registers), so that the barrier-separated phases of one
 // tile overlap with those of the other.
 template <bool BWD, bool EXACT>
-__global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainParams p) {
+__global__ void __launch_bounds__(256, BWD ? 2 : 3) dec_mcab_train_kernel(const DecTrainParams p) {
   extern __shared__ float4 dec_smem4[];
   float* sm = reinterpret_cast<float*>(dec_smem4);
   float* sQ = sm;                    float* sAO = sQ + DT * LD32;    float* sX1 = sAO + DT * LD32;   float* sN2 = sX1 + DT * LD32;
-  float* sD1 = sN2 + DT * LD32;      float* sD2 = sD1 + DT * LD32;   float* sU = sD2 + DT * LD32;    float* sV = sU + DT * LD88;
-  float* sK = sV + DT * LD88;        float* sVc = sK + 16 * LDK;     float* sStat = sVc + 16 * LDK;  float* sDl = sStat + 2 * DT;
+  float* sD1 = sN2 + DT * LD32;      float* sD2 = sD1 + DT * LD32;   float* sU = sD2 + DT * LD32;    float* sV = sU + DT * LD88;   // backward only
+  float* sK = BWD ? sV + DT * LD88 : sN2 + DT * LD32;
+  float* sVc = sK + 16 * LDK;        float* sStat = sVc + 16 * LDK;  float* sDl = sStat + 2 * DT;
   float* sLog = sDl + DT;            int* sGid = reinterpret_cast<int*>(sLog + 4 * DT);
-  float* sWp = sLog + 5 * DT;        float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;
-  float* sLn = sW3 + 32 * LD88;      float* sWh = sLn + 64;          float* sR = sLn + 96;
+  float* sWp = sLog + 5 * DT;        float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;    // sW3: backward only
+  float* sLn = BWD ? sW3 + 32 * LD88 : sW3;
+  float* sWh = sLn + 64;             float* sR = sLn + 96;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int mt = warp & 1, nq = warp >> 1;
   const int g0 = blockIdx.x * DT;
@@ -1230,7 +1234,7 @@ __global__ void __launch_bounds__(256, 2) dec_mcab_train_kernel(const DecTrainPa
   // ---- weights of the block into shared memory (padded rows: conflict-free fragment reads) ----
   for (int i = tid; i < 1024; i += 256) sWp[(i >> 5) * LD32 + (i & 31)] = rt<EXACT>(p.ca[C_CPROJ + i]);
   for (int i = tid; i < H * 32; i += 256) { sW1[(i >> 5) * LD32 + (i & 31)] = rt<EXACT>(p.ca[C_W1 + i]); sW2[(i >> 5) * LD32 + (i & 31)] = rt<EXACT>(p.ca[C_W2 + i]); }
-  for (int i = tid; i < 32 * H; i += 256) sW3[(i / H) * LD88 + (i % H)] = rt<EXACT>(p.ca[C_W3 + i]);
+  if (BWD) { for (int i = tid; i < 32 * H; i += 256) sW3[(i / H) * LD88 + (i % H)] = rt<EXACT>(p.ca[C_W3 + i]); }
   if (tid < 64) sLn[tid] = p.ca[C_LN2W + tid];   // ln_2.weight | ln_2.bias
   if (tid < 32) sWh[tid] = p.head_w[tid];
   if (tid < DT) sGid[tid] = (g0 + tid < p.G) ? (int)p.genes[g0 + tid] : -1;
