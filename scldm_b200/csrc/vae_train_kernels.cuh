@@ -1156,6 +1156,12 @@ struct DecTrainParams {
   int B, cells_per_chunk; float eps;
 };
 constexpr int DT = 32, LD32 = 36, LD88 = 100, LDK = 36;
+// du / dv tiles: 96-float rows with an XOR swizzle of the column inside its 32-column group, so that BOTH fragment orientations are free of
+// bank conflicts: token-major rows as the A operand of the d n2 dgrad (rows g, columns k0 + t) and hidden-major columns as the A operand
+// of the weight-gradient products (rows k0 + t, columns j0 + g).  Padding alone serves only one of the two (4 (mod 32) vs 8 (mod 32)).
+constexpr int LDU = 96;
+__device__ __forceinline__ int usw(int r) { return ((r & 3) << 3) | (((r >> 2) & 1) << 2); }
+__device__ __forceinline__ int uidx(int r, int c) { return r * LDU + (c ^ usw(r)); }
 // 6 32-wide tiles + du / dv (h in the forward-only kernel) + keys / values + small vectors + the block's weights: 103 KB, 2 CTAs per SM
 constexpr int DEC_SMEM_FLOATS = 6 * DT * LD32 + 2 * DT * LD88 + 2 * 16 * LDK + 2 * DT + DT + 4 * DT + DT + 32 * LD32 + 2 * H * LD32 + 32 * LD88 + 96 + 96;
 // the forward-only launch needs neither the gradient tiles nor mlp.c_proj: 54 KB, three CTAs per SM
@@ -1218,8 +1224,8 @@ __global__ void __launch_bounds__(256, BWD ? 2 : 3) dec_mcab_train_kernel(const 
   extern __shared__ float4 dec_smem4[];
   float* sm = reinterpret_cast<float*>(dec_smem4);
   float* sQ = sm;                    float* sAO = sQ + DT * LD32;    float* sX1 = sAO + DT * LD32;   float* sN2 = sX1 + DT * LD32;
-  float* sD1 = sN2 + DT * LD32;      float* sD2 = sD1 + DT * LD32;   float* sU = sD2 + DT * LD32;    float* sV = sU + DT * LD88;   // backward only
-  float* sK = BWD ? sV + DT * LD88 : sN2 + DT * LD32;
+  float* sD1 = sN2 + DT * LD32;      float* sD2 = sD1 + DT * LD32;   float* sU = sD2 + DT * LD32;    float* sV = sU + DT * LDU;    // backward only
+  float* sK = BWD ? sV + DT * LDU : sN2 + DT * LD32;
   float* sVc = sK + 16 * LDK;        float* sStat = sVc + 16 * LDK;  float* sDl = sStat + 2 * DT;
   float* sLog = sDl + DT;            int* sGid = reinterpret_cast<int*>(sLog + 4 * DT);
   float* sWp = sLog + 5 * DT;        float* sW1 = sWp + 32 * LD32;   float* sW2 = sW1 + H * LD32;    float* sW3 = sW2 + H * LD32;    // sW3: backward only
@@ -1344,8 +1350,8 @@ __global__ void __launch_bounds__(256, BWD ? 2 : 3) dec_mcab_train_kernel(const 
             if (BWD) {
               const float dl = (e >> 1) ? dl1 : dl0, dh = dl * sR[col];
               acc_sh[i][e & 1] += dl * hv;
-              sU[r * LD88 + col] = rt<EXACT>(dh * v * sg * (1.f + u * (1.f - sg)));
-              sV[r * LD88 + col] = rt<EXACT>(dh * u * sg);
+              sU[uidx(r, col)] = rt<EXACT>(dh * v * sg * (1.f + u * (1.f - sg)));
+              sV[uidx(r, col)] = rt<EXACT>(dh * u * sg);
             } else {
               if (e >> 1) hx_hi += sR[col] * hv; else hx_lo += sR[col] * hv;
             }
@@ -1391,7 +1397,7 @@ __global__ void __launch_bounds__(256, BWD ? 2 : 3) dec_mcab_train_kernel(const 
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int j0 = (mw0 + i) * 16 + g;
-          const float a[4] = {sG[(k0 + t) * LD88 + j0], sG[(k0 + t) * LD88 + j0 + 8], sG[(k0 + t + 4) * LD88 + j0], sG[(k0 + t + 4) * LD88 + j0 + 8]};
+          const float a[4] = {sG[uidx(k0 + t, j0)], sG[uidx(k0 + t, j0 + 8)], sG[uidx(k0 + t + 4, j0)], sG[uidx(k0 + t + 4, j0 + 8)]};
           mma_f<EXACT>(acc_w[i * 2], a, bf[0]);
           mma_f<EXACT>(acc_w[i * 2 + 1], a, bf[1]);
         }
@@ -1400,7 +1406,21 @@ __global__ void __launch_bounds__(256, BWD ? 2 : 3) dec_mcab_train_kernel(const 
       {
         const int nh2 = (warp >> 1) & 1, kh = warp >> 2;
         float acc[2][4] = {};
-        warp_gemm<EXACT, 2, 11>(acc, (kh ? sV : sU) + mt * 16 * LD88, LD88, 1, (kh ? sW2 : sW1) + nh2 * 16, LD32, 1, 2, 8);
+        {
+          const float* A = kh ? sV : sU;
+          const float* Bw = (kh ? sW2 : sW1) + nh2 * 16;
+          const int ra = (mt * 16 + g) * LDU, rb = ra + 8 * LDU, sw = usw(mt * 16 + g);      // rows g and g + 8 share the swizzle
+#pragma unroll
+          for (int ks = 0; ks < 11; ++ks) {
+            const int k0 = ks * 8;
+            const float a[4] = {A[ra + ((k0 + t) ^ sw)], A[rb + ((k0 + t) ^ sw)], A[ra + ((k0 + t + 4) ^ sw)], A[rb + ((k0 + t + 4) ^ sw)]};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float bb[2] = {Bw[(k0 + t) * LD32 + i * 8 + g], Bw[(k0 + t + 4) * LD32 + i * 8 + g]};
+              mma_f<EXACT>(acc[i], a, bb);
+            }
+          }
+        }
         float* dst = (kh ? sD1 : sD2) + (mt * 16 + g) * LD32 + nh2 * 16 + 2 * t;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
