@@ -5,12 +5,14 @@
 // Block layers.py:177-226, InputTransformerVAE layers.py:97-118, NegativeBinomialTransformerLayer stochastic_layers.py:102-116.
 //
 // Where the work is: the decoder's cross-attention block runs on every (cell, gene) token - B x G of them (4.6 M for 128 cells
-// of the census vocabulary), 28 k multiply-adds each for forward + dgrad + wgrad.  dec_mcab_train_kernel keeps a 64-token tile of
-// one cell in shared memory, recomputes its forward and differentiates it there; every GEMM of the tile (c_proj, [w1|w2], mlp.c_proj,
-// their dgrads and the weight gradients, which accumulate in registers over all tiles a CTA visits) is TF32 mma.sync fed from
-// shared memory - the precision the reference trains in (torch.set_float32_matmul_precision("high"), scripts/train.py:18).
-// Everything that is per cell (16 latent tokens x 32 channels through 2 x n_layer Blocks) or per encoder token is fp32 CUDA-core
-// code: < 3 % of the step's arithmetic.
+// of the census vocabulary), 28 k multiply-adds each for forward + dgrad + wgrad.  dec_mcab_train_kernel keeps a 32-token tile of
+// one cell in shared memory, recomputes its forward and differentiates it there; every GEMM of the tile (attention products, c_proj,
+// [w1|w2], their dgrads and the weight gradients, which accumulate in registers over all cells a CTA visits) is TF32 mma.sync fed
+// from shared memory - the precision the reference trains in (torch.set_float32_matmul_precision("high"), scripts/train.py:18);
+// mlp.c_proj never runs: the head is linear in the block's output, which folds it into two dot products (forward) and rank-1
+// updates (backward).  The encoder's token side (K / V projection, pooling, their backward) runs on the same mma helpers over
+// 128-token tiles; what is per cell (16 latent tokens x 32 channels through 2 x n_layer Blocks) is fp32 CUDA-core code with the
+// Block weights staged in shared memory: < 1 % of the step's arithmetic.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
